@@ -1,0 +1,73 @@
+"""The oracle (oracle/graphnet_oracle.py) against the reference's own outputs (tests/golden/*.npz).
+
+The goldens were produced by the unmodified reference GraphNet / GraphChoice in the build container
+(tests/golden/make_golden.py).  Tolerance: the oracle restates the same fp32 PyTorch-CPU arithmetic in
+batched form, so only fp32 re-association noise is allowed: 2e-6 * max|s| (observed <= 5e-7).
+"""
+import pytest
+import torch
+
+from golden_io import ARCHS, load_case, load_gnn
+from oracle import graphnet_oracle as O
+
+TOL = 2e-6
+
+
+@pytest.mark.parametrize('arch', ARCHS)
+@pytest.mark.parametrize('case', ['fr', 'root'])
+@pytest.mark.parametrize('weights', ['shipped', 'random'])
+def test_oracle_matches_reference_scores_and_decisions(arch, case, weights):
+    fr, ref = load_case(arch, case)
+    scores, _ = O.gnn_forward(load_gnn(weights), fr)
+    s_ref = ref[f'scores_{weights}']
+    m = fr.mask != 0
+    scale = float(s_ref[m].abs().max())
+    err = float((scores - s_ref)[m].abs().max())
+    assert err <= TOL * scale, (err, scale)
+    _, flat, dec = O.decide(scores, fr.mask, fr.net.hidden_sizes)
+    assert dec == ref[f'decisions_{weights}'].tolist()
+    rep = O.parity_report(scores, s_ref, fr.mask, flat)
+    assert rep['ok'], rep
+
+
+@pytest.mark.parametrize('T', [1, 3])
+def test_oracle_other_round_counts(T):
+    fr, ref = load_case('base', 'fr')
+    scores, _ = O.gnn_forward(load_gnn('random'), fr, T=T)
+    s_ref = ref[f'scores_random_T{T}']
+    m = fr.mask != 0
+    assert float((scores - s_ref)[m].abs().max()) <= TOL * float(s_ref[m].abs().max())
+
+
+def test_dead_input_update_is_dead():
+    """the last round's input-layer update never reaches the scores."""
+    fr, _ = load_case('base', 'fr')
+    sd = load_gnn('random')
+    a, _ = O.gnn_forward(sd, fr)
+    b, _ = O.gnn_forward(sd, fr, dead_input_update=True)
+    assert torch.equal(a, b)
+
+
+def test_shipped_checkpoint_is_degenerate_in_forward_half():
+    """with the shipped checkpoint T=1 and T=2 agree (forward-half weights are denormals),
+    which is why every parity test also runs the non-degenerate random GraphNet."""
+    fr, _ = load_case('base', 'fr')
+    sd = load_gnn('shipped')
+    a, _ = O.gnn_forward(sd, fr, T=1)
+    b, _ = O.gnn_forward(sd, fr, T=2)
+    assert torch.equal(a, b)
+    r1, _ = O.gnn_forward(load_gnn('random'), fr, T=1)
+    r2, _ = O.gnn_forward(load_gnn('random'), fr, T=2)
+    assert not torch.allclose(r1, r2)
+
+
+def test_compute_ratio_cases():
+    l = torch.tensor([-1.0, 0.5, -2.0, 0.0, -3.0])
+    u = torch.tensor([1.0, 2.0, -1.0, 4.0, 0.0])
+    r0, r1, beta, amb = O.compute_ratio(l, u)
+    assert r0.tolist() == [0.5, 1.0, 0.0, 1.0, 0.0]
+    assert amb.tolist() == [1.0, 0.0, 0.0, 0.0, 0.0]
+    assert r1.tolist() == [0.5, 1.0, 0.0, 1.0, 0.0]
+    assert beta.tolist() == [0.5, 0.0, 0.0, 0.0, 0.0]
+    r0, _, _, _ = O.compute_ratio(torch.zeros(1), torch.zeros(1))
+    assert torch.isnan(r0).all()          # l = u = 0 is 0/0 in the reference too
