@@ -1,0 +1,502 @@
+// C ABI of libgnnb.so (include/gnnb.h): context, parameter packing, workspace, and the per-chunk stage schedule.
+//
+// HBM layout per chunk of Bc subdomains (all fp32, node-major, one 256-byte row of 64 channels per node):
+//   mu[k]      [Bc, n_k, 64]  k = 0 (input pixels) .. L (hidden) .. L+1 (output node)   init_mu, graph_conv.py:487-496
+//   nb         [Bc, max_k n_k, 64]   neighbour embeddings of the layer being updated (reused by every stage)
+//   relax_f[k], relax_b[k]  [Bc, n_k, 64]  round-independent relaxation features (see gnnb_simt.cu header)
+//   scores     [Bc, sum n_k]
+// Only adjacent layers are live at any time, so a chunk's stage working set is ~3 * Bc * n_k * 256 B.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "gnnb_common.cuh"
+
+using namespace gnnb;
+
+struct gnnb_ctx {
+    int device = 0;
+    int last_status = 0;
+    std::string err;
+    int64_t launches = 0;
+    // options
+    int math = GNNB_MATH_SIMT_FP32;
+    int chunk = 0;
+    int snapshot = 0;
+    // GNN parameters
+    bool have_gnn = false;
+    float* d_gnn = nullptr;
+    uint16_t* d_tc = nullptr;
+    GnnParams gp{};
+    // verified network
+    bool have_net = false;
+    float* d_net = nullptr;
+    std::vector<LayerDev> layers;
+    std::vector<int> n;             // n[0] = input nodes, n[1..L] hidden, n[L+1] = 1
+    std::vector<int> hidden_off;    // offset of layer k (1-based) in the flat ReLU index
+    int n_hidden = 0;
+    // workspace
+    int ws_cap = 0;                 // subdomains the workspace can hold
+    bool ws_host_staging = false;
+    float* d_ws = nullptr;
+    std::vector<float*> mu, relax_f, relax_b;
+    float* nb = nullptr;
+    float* ws_scores = nullptr;
+    float* ws_best = nullptr;
+    int32_t* ws_idx = nullptr;
+    // staged copies of host inputs
+    std::vector<float*> s_lb, s_ub, s_dual, s_pre, s_post;
+    float *s_pout = nullptr, *s_pin = nullptr, *s_wp = nullptr, *s_bp = nullptr, *s_mask = nullptr;
+    unsigned long long* d_nan = nullptr;
+    // debugging snapshots
+    std::map<std::string, std::pair<float*, int64_t>> snaps;
+};
+
+namespace {
+
+int fail(gnnb_ctx* c, int status, const std::string& msg) {
+    if (c) { c->last_status = status; c->err = msg; }
+    return status;
+}
+
+#define CU(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess)                                                                           \
+            return fail(ctx, GNNB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));         \
+    } while (0)
+
+size_t align4(size_t x) { return (x + 3) & ~size_t(3); }
+
+void free_workspace(gnnb_ctx* c) {
+    if (c->d_ws) cudaFree(c->d_ws);
+    c->d_ws = nullptr;
+    c->ws_cap = 0;
+    for (auto& kv : c->snaps) cudaFree(kv.second.first);
+    c->snaps.clear();
+}
+
+int ensure_workspace(gnnb_ctx* ctx, int Bc, bool host_staging) {
+    if (ctx->d_ws && ctx->ws_cap >= Bc && (ctx->ws_host_staging || !host_staging)) return GNNB_OK;
+    free_workspace(ctx);
+    const int L = (int)ctx->layers.size();
+    int nmax = 0;
+    for (int k = 0; k <= L; ++k) nmax = ctx->n[k] > nmax ? ctx->n[k] : nmax;
+    size_t total = 0;
+    auto take = [&](size_t elems) { size_t off = total; total += align4(elems) + 64; return off; };
+    std::vector<size_t> o_mu(L + 2), o_rf(L + 1), o_rb(L + 1), o_lb(L + 2), o_ub(L + 2), o_du(L), o_pr(L), o_po(L);
+    for (int k = 0; k <= L + 1; ++k) o_mu[k] = take((size_t)Bc * ctx->n[k] * P);
+    for (int k = 1; k <= L; ++k) { o_rf[k] = take((size_t)Bc * ctx->n[k] * P); o_rb[k] = take((size_t)Bc * ctx->n[k] * P); }
+    const size_t o_nb = take((size_t)Bc * nmax * P);
+    const size_t o_sc = take((size_t)Bc * ctx->n_hidden);
+    const size_t o_best = take(Bc), o_idx = take(Bc);
+    size_t o_pout = 0, o_pin = 0, o_wp = 0, o_bp = 0, o_mask = 0;
+    if (host_staging) {
+        for (int k = 0; k <= L + 1; ++k) { o_lb[k] = take((size_t)Bc * ctx->n[k]); o_ub[k] = take((size_t)Bc * ctx->n[k]); }
+        for (int k = 0; k < L; ++k) {
+            o_du[k] = take((size_t)Bc * ctx->n[k + 1] * 3);
+            o_pr[k] = take((size_t)Bc * ctx->n[k + 1]);
+            o_po[k] = take((size_t)Bc * ctx->n[k + 1]);
+        }
+        o_pout = take(Bc); o_pin = take((size_t)Bc * ctx->n[0]); o_wp = take((size_t)Bc * ctx->n[L]);
+        o_bp = take(Bc); o_mask = take((size_t)Bc * ctx->n_hidden);
+    }
+    CU(cudaMalloc(&ctx->d_ws, total * sizeof(float)));
+    float* base = ctx->d_ws;
+    ctx->mu.assign(L + 2, nullptr); ctx->relax_f.assign(L + 1, nullptr); ctx->relax_b.assign(L + 1, nullptr);
+    for (int k = 0; k <= L + 1; ++k) ctx->mu[k] = base + o_mu[k];
+    for (int k = 1; k <= L; ++k) { ctx->relax_f[k] = base + o_rf[k]; ctx->relax_b[k] = base + o_rb[k]; }
+    ctx->nb = base + o_nb; ctx->ws_scores = base + o_sc; ctx->ws_best = base + o_best;
+    ctx->ws_idx = reinterpret_cast<int32_t*>(base + o_idx);
+    ctx->s_lb.assign(L + 2, nullptr); ctx->s_ub.assign(L + 2, nullptr);
+    ctx->s_dual.assign(L, nullptr); ctx->s_pre.assign(L, nullptr); ctx->s_post.assign(L, nullptr);
+    if (host_staging) {
+        for (int k = 0; k <= L + 1; ++k) { ctx->s_lb[k] = base + o_lb[k]; ctx->s_ub[k] = base + o_ub[k]; }
+        for (int k = 0; k < L; ++k) { ctx->s_dual[k] = base + o_du[k]; ctx->s_pre[k] = base + o_pr[k]; ctx->s_post[k] = base + o_po[k]; }
+        ctx->s_pout = base + o_pout; ctx->s_pin = base + o_pin; ctx->s_wp = base + o_wp; ctx->s_bp = base + o_bp;
+        ctx->s_mask = base + o_mask;
+    }
+    ctx->ws_cap = Bc;
+    ctx->ws_host_staging = host_staging;
+    return GNNB_OK;
+}
+
+int snap(gnnb_ctx* ctx, const std::string& name, const float* src, int64_t numel, cudaStream_t st) {
+    if (!ctx->snapshot) return GNNB_OK;
+    auto it = ctx->snaps.find(name);
+    if (it == ctx->snaps.end() || it->second.second < numel) {
+        if (it != ctx->snaps.end()) cudaFree(it->second.first);
+        float* p = nullptr;
+        CU(cudaMalloc(&p, (size_t)numel * sizeof(float)));
+        ctx->snaps[name] = std::make_pair(p, numel);
+        it = ctx->snaps.find(name);
+    }
+    it->second.second = numel;
+    CU(cudaMemcpyAsync(it->second.first, src, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return GNNB_OK;
+}
+
+struct ChunkPtrs {
+    std::vector<const float*> lb, ub, dual, pre, post;
+    const float *pout, *pin, *wp, *bp, *mask;
+};
+
+#define TRY(expr) do { int s__ = (expr); if (s__ != GNNB_OK) return s__; } while (0)
+
+// the stage schedule for one chunk; every pointer is a device pointer
+int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* best_score, int32_t* best_idx,
+              cudaStream_t st) {
+    const int L = (int)ctx->layers.size();
+    const GnnParams& g = ctx->gp;
+    const bool tc = ctx->math == GNNB_MATH_TC_BF16X3;
+    int64_t* lc = &ctx->launches;
+    auto name = [](const char* fmt, int a, int b) { char buf[64]; snprintf(buf, sizeof buf, fmt, a, b); return std::string(buf); };
+
+    // round-independent relaxation features of every hidden layer
+    for (int k = 1; k <= L; ++k) {
+        NodeInputs ni{in.lb[k], in.ub[k], in.dual[k - 1], in.pre[k - 1], in.post[k - 1], ctx->layers[k - 1].bias_node,
+                      ctx->n[k], (int64_t)Bc * ctx->n[k]};
+        if (tc) tc_relax(g, ni, ctx->relax_f[k], ctx->relax_b[k], st, lc);
+        else simt_relax(g, ni, ctx->relax_f[k], ctx->relax_b[k], st, lc);
+        TRY(snap(ctx, name("relax_f%d", k, 0), ctx->relax_f[k], ni.rows * P, st));
+        TRY(snap(ctx, name("relax_b%d", k, 0), ctx->relax_b[k], ni.rows * P, st));
+    }
+    const int64_t rows0 = (int64_t)Bc * ctx->n[0];
+    if (tc) tc_input_embed(g, in.lb[0], in.pin, in.ub[0], ctx->mu[0], rows0, st, lc);
+    else simt_input_embed(g, in.lb[0], in.pin, in.ub[0], ctx->mu[0], rows0, st, lc);
+    TRY(snap(ctx, "mu0_embed", ctx->mu[0], rows0 * P, st));
+
+    for (int t = 0; t < g.T; ++t) {
+        const bool last = (t == g.T - 1);
+        // forward sweep
+        for (int k = 1; k <= L; ++k) {
+            const int64_t rows = (int64_t)Bc * ctx->n[k];
+            prop_forward(ctx->layers[k - 1], ctx->mu[k - 1], ctx->nb, Bc, st, lc);
+            TRY(snap(ctx, name("t%d_fwd_nb%d", t, k), ctx->nb, rows * P, st));
+            if (tc) tc_update(g, false, in.lb[k], in.ub[k], ctx->nb, ctx->relax_f[k], ctx->mu[k], nullptr, ctx->n[k], 0, 0, rows, ctx->d_nan, st, lc);
+            else simt_update(g, false, in.lb[k], in.ub[k], ctx->nb, ctx->relax_f[k], ctx->mu[k], nullptr, ctx->n[k], 0, 0, rows, ctx->d_nan, st, lc);
+            TRY(snap(ctx, name("t%d_fwd_mu%d", t, k), ctx->mu[k], rows * P, st));
+        }
+        output_node(g, in.wp, in.bp, ctx->mu[L], in.lb[L + 1], in.ub[L + 1], in.pout, ctx->mu[L + 1], ctx->n[L], Bc, st, lc);
+        TRY(snap(ctx, name("t%d_mu_out", t, 0), ctx->mu[L + 1], (int64_t)Bc * P, st));
+        // backward sweep
+        for (int k = L; k >= 1; --k) {
+            const int64_t rows = (int64_t)Bc * ctx->n[k];
+            if (k == L) prop_property_backward(in.wp, ctx->mu[L + 1], ctx->nb, ctx->n[L], Bc, st, lc);
+            else prop_backward(ctx->layers[k], ctx->mu[k + 1], ctx->nb, Bc, true, st, lc);
+            TRY(snap(ctx, name("t%d_bwd_nb%d", t, k), ctx->nb, rows * P, st));
+            float* sc = last ? scores : nullptr;
+            if (tc) tc_update(g, true, in.lb[k], in.ub[k], ctx->nb, ctx->relax_b[k], ctx->mu[k], sc, ctx->n[k], ctx->n_hidden, ctx->hidden_off[k], rows, ctx->d_nan, st, lc);
+            else simt_update(g, true, in.lb[k], in.ub[k], ctx->nb, ctx->relax_b[k], ctx->mu[k], sc, ctx->n[k], ctx->n_hidden, ctx->hidden_off[k], rows, ctx->d_nan, st, lc);
+            TRY(snap(ctx, name("t%d_bwd_mu%d", t, k), ctx->mu[k], rows * P, st));
+        }
+        // input layer: feeds the next round only (dead on the last round)
+        if (!last) {
+            prop_backward(ctx->layers[0], ctx->mu[1], ctx->nb, Bc, false, st, lc);
+            if (tc) tc_input_update(g, in.lb[0], in.ub[0], ctx->nb, ctx->mu[0], rows0, st, lc);
+            else simt_input_update(g, in.lb[0], in.ub[0], ctx->nb, ctx->mu[0], rows0, st, lc);
+            TRY(snap(ctx, name("t%d_mu0", t, 0), ctx->mu[0], rows0 * P, st));
+        }
+    }
+    masked_argmax(scores, in.mask, ctx->n_hidden, Bc, best_score, best_idx, st, lc);
+    CU(cudaGetLastError());
+    return GNNB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gnnb_abi_version(void) { return 1; }
+
+int gnnb_create(gnnb_ctx** out, int device) {
+    if (!out) return GNNB_ERR_INVALID;
+    *out = nullptr;
+    gnnb_ctx* ctx = new gnnb_ctx();
+    ctx->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { delete ctx; return GNNB_ERR_CUDA; }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { delete ctx; return GNNB_ERR_CUDA; }
+    if (prop.major != 10) {   // sm_100a cubins only; there is no other code path
+        fprintf(stderr, "libgnnb: device %d is sm_%d%d; this library is built for sm_100a (B200) only\n", device, prop.major, prop.minor);
+        delete ctx;
+        return GNNB_ERR_UNSUPPORTED;
+    }
+    if (cudaMalloc(&ctx->d_nan, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(ctx->d_nan, 0, sizeof(unsigned long long)) != cudaSuccess ||
+        simt_init() != 0 || prop_init(64 * 1024) != 0 || tc_init() != 0) {
+        fprintf(stderr, "libgnnb: initialisation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+        delete ctx;
+        return GNNB_ERR_CUDA;
+    }
+    *out = ctx;
+    return GNNB_OK;
+}
+
+void gnnb_destroy(gnnb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    free_workspace(ctx);
+    if (ctx->d_gnn) cudaFree(ctx->d_gnn);
+    if (ctx->d_tc) cudaFree(ctx->d_tc);
+    if (ctx->d_net) cudaFree(ctx->d_net);
+    if (ctx->d_nan) cudaFree(ctx->d_nan);
+    delete ctx;
+}
+
+int gnnb_set_gnn_weights(gnnb_ctx* ctx, const float* const* tensors, const int64_t* numels, int n_tensors, int T, int p) {
+    if (!ctx || !tensors || !numels) return fail(ctx, GNNB_ERR_INVALID, "null argument");
+    if (p != P) return fail(ctx, GNNB_ERR_UNSUPPORTED, "embedding size p must be 64");
+    if (T < 1) return fail(ctx, GNNB_ERR_INVALID, "T must be >= 1");
+    if (n_tensors != 2 * N_LIN) return fail(ctx, GNNB_ERR_INVALID, "expected 52 tensors (weight, bias of 26 linears)");
+    for (int l = 0; l < N_LIN; ++l) {
+        if (numels[2 * l] != (int64_t)lin_in(l) * lin_out(l) || numels[2 * l + 1] != lin_out(l))
+            return fail(ctx, GNNB_ERR_INVALID, "tensor " + std::to_string(2 * l) + " has the wrong number of elements");
+    }
+    CU(cudaSetDevice(ctx->device));
+    // fp32 blob: transposed weights + biases
+    std::vector<size_t> o_w(N_LIN), o_b(N_LIN);
+    size_t total = 0;
+    for (int l = 0; l < N_LIN; ++l) {
+        o_w[l] = total; total += align4((size_t)lin_in(l) * lin_out(l));
+        o_b[l] = total; total += align4(lin_out(l));
+    }
+    std::vector<float> blob(total, 0.f);
+    for (int l = 0; l < N_LIN; ++l) {
+        const int K = lin_in(l), N = lin_out(l);
+        const float* W = tensors[2 * l];
+        for (int nn = 0; nn < N; ++nn)
+            for (int k = 0; k < K; ++k) blob[o_w[l] + (size_t)k * N + nn] = W[(size_t)nn * K + k];
+        memcpy(&blob[o_b[l]], tensors[2 * l + 1], sizeof(float) * N);
+    }
+    // tensor-core planes for the K >= 64 linears
+    std::vector<size_t> o_tc(N_LIN, 0);
+    size_t tc_total = 0;
+    for (int l = 0; l < N_LIN; ++l)
+        if (lin_in(l) >= P && lin_out(l) == P) { o_tc[l] = tc_total; tc_total += (size_t)tc_packed_elems(lin_in(l)); }
+    std::vector<uint16_t> tcblob(tc_total ? tc_total : 1, 0);
+    for (int l = 0; l < N_LIN; ++l)
+        if (lin_in(l) >= P && lin_out(l) == P) tc_pack_weight(tensors[2 * l], lin_in(l), &tcblob[o_tc[l]]);
+    if (ctx->d_gnn) cudaFree(ctx->d_gnn);
+    if (ctx->d_tc) cudaFree(ctx->d_tc);
+    ctx->d_gnn = nullptr; ctx->d_tc = nullptr;
+    CU(cudaMalloc(&ctx->d_gnn, total * sizeof(float)));
+    CU(cudaMemcpy(ctx->d_gnn, blob.data(), total * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&ctx->d_tc, tcblob.size() * sizeof(uint16_t)));
+    CU(cudaMemcpy(ctx->d_tc, tcblob.data(), tcblob.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    for (int l = 0; l < N_LIN; ++l) {
+        ctx->gp.wt[l] = ctx->d_gnn + o_w[l];
+        ctx->gp.bias[l] = ctx->d_gnn + o_b[l];
+        ctx->gp.tc[l] = (lin_in(l) >= P && lin_out(l) == P) ? ctx->d_tc + o_tc[l] : nullptr;
+    }
+    ctx->gp.T = T;
+    ctx->have_gnn = true;
+    return GNNB_OK;
+}
+
+int gnnb_set_network(gnnb_ctx* ctx, const gnnb_layer_desc* layers, int n_layers, int c0, int h0, int w0) {
+    if (!ctx || !layers || n_layers < 1) return fail(ctx, GNNB_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<LayerDev> devs(n_layers);
+    std::vector<int> n(n_layers + 2);
+    n[0] = c0 * h0 * w0;
+    int pc = c0, ph = h0, pw = w0;
+    bool flat = false;
+    size_t total = 0;
+    std::vector<size_t> o_w(n_layers), o_b(n_layers);
+    for (int k = 0; k < n_layers; ++k) {
+        const gnnb_layer_desc& d = layers[k];
+        LayerDev& L = devs[k];
+        L.kind = d.kind;
+        L.c_in = d.c_in; L.h_in = d.h_in; L.w_in = d.w_in; L.c_out = d.c_out; L.h_out = d.h_out; L.w_out = d.w_out;
+        L.ksize = d.ksize; L.stride = d.stride; L.pad = d.pad;
+        L.n_in = d.c_in * d.h_in * d.w_in;
+        L.n_out = d.c_out * d.h_out * d.w_out;
+        if (!d.weight || !d.bias) return fail(ctx, GNNB_ERR_INVALID, "layer weight/bias is null");
+        if (L.n_in != n[k]) return fail(ctx, GNNB_ERR_INVALID, "layer " + std::to_string(k) + ": input size does not match the previous layer");
+        size_t wn;
+        if (d.kind == GNNB_LAYER_CONV) {
+            if (flat || d.c_in != pc || d.h_in != ph || d.w_in != pw) return fail(ctx, GNNB_ERR_INVALID, "conv layer input shape mismatch");
+            if (d.ksize < 1 || d.stride < 1 || d.pad < 0) return fail(ctx, GNNB_ERR_INVALID, "bad conv geometry");
+            if (d.h_out != (d.h_in + 2 * d.pad - d.ksize) / d.stride + 1 || d.w_out != (d.w_in + 2 * d.pad - d.ksize) / d.stride + 1)
+                return fail(ctx, GNNB_ERR_INVALID, "conv output shape mismatch");
+            // conv_transpose2d must land exactly on the input grid (no output_padding in the reference call)
+            if ((d.h_out - 1) * d.stride - 2 * d.pad + d.ksize != d.h_in || (d.w_out - 1) * d.stride - 2 * d.pad + d.ksize != d.w_in)
+                return fail(ctx, GNNB_ERR_UNSUPPORTED, "conv geometry needs output_padding in the backward pass");
+            if ((size_t)d.c_in * d.ksize * d.ksize * d.c_out * sizeof(float) > 64 * 1024)
+                return fail(ctx, GNNB_ERR_UNSUPPORTED, "conv weights exceed the 64 KB shared-memory staging buffer");
+            wn = (size_t)d.c_out * d.c_in * d.ksize * d.ksize;
+            pc = d.c_out; ph = d.h_out; pw = d.w_out;
+        } else if (d.kind == GNNB_LAYER_LINEAR) {
+            if (d.h_in != 1 || d.w_in != 1 || d.h_out != 1 || d.w_out != 1) return fail(ctx, GNNB_ERR_INVALID, "linear layers use c_in/c_out only");
+            wn = (size_t)L.n_out * L.n_in;
+            flat = true;
+        } else {
+            return fail(ctx, GNNB_ERR_INVALID, "unknown layer kind");
+        }
+        n[k + 1] = L.n_out;
+        o_w[k] = total; total += align4(wn);
+        o_b[k] = total; total += align4(L.n_out);
+    }
+    n[n_layers + 1] = 1;
+    std::vector<float> blob(total, 0.f);
+    for (int k = 0; k < n_layers; ++k) {
+        const gnnb_layer_desc& d = layers[k];
+        const LayerDev& L = devs[k];
+        const size_t wn = d.kind == GNNB_LAYER_CONV ? (size_t)d.c_out * d.c_in * d.ksize * d.ksize : (size_t)L.n_out * L.n_in;
+        memcpy(&blob[o_w[k]], d.weight, wn * sizeof(float));
+        const int per = d.kind == GNNB_LAYER_CONV ? d.h_out * d.w_out : 1;     // graph_conv.py:122-124
+        for (int j = 0; j < L.n_out; ++j) blob[o_b[k] + j] = d.bias[j / per];
+    }
+    free_workspace(ctx);
+    if (ctx->d_net) cudaFree(ctx->d_net);
+    ctx->d_net = nullptr;
+    CU(cudaMalloc(&ctx->d_net, total * sizeof(float)));
+    CU(cudaMemcpy(ctx->d_net, blob.data(), total * sizeof(float), cudaMemcpyHostToDevice));
+    for (int k = 0; k < n_layers; ++k) { devs[k].weight = ctx->d_net + o_w[k]; devs[k].bias_node = ctx->d_net + o_b[k]; }
+    ctx->layers = devs;
+    ctx->n = n;
+    ctx->hidden_off.assign(n_layers + 2, 0);
+    int off = 0;
+    for (int k = 1; k <= n_layers; ++k) { ctx->hidden_off[k] = off; off += n[k]; }
+    ctx->n_hidden = off;
+    ctx->have_net = true;
+    return GNNB_OK;
+}
+
+int gnnb_set_option(gnnb_ctx* ctx, const char* key, int64_t value) {
+    if (!ctx || !key) return fail(ctx, GNNB_ERR_INVALID, "null argument");
+    const std::string k(key);
+    if (k == "math") {
+        if (value != GNNB_MATH_TC_BF16X3 && value != GNNB_MATH_SIMT_FP32) return fail(ctx, GNNB_ERR_INVALID, "unknown math mode");
+        if (value == GNNB_MATH_TC_BF16X3 && !tc_available()) return fail(ctx, GNNB_ERR_UNSUPPORTED, "tensor-core path not built");
+        ctx->math = (int)value;
+    } else if (k == "chunk") {
+        if (value < 0) return fail(ctx, GNNB_ERR_INVALID, "chunk must be >= 0");
+        ctx->chunk = (int)value;
+    } else if (k == "snapshot") {
+        ctx->snapshot = value ? 1 : 0;
+    } else {
+        return fail(ctx, GNNB_ERR_INVALID, "unknown option " + k);
+    }
+    return GNNB_OK;
+}
+
+int64_t gnnb_get_option(gnnb_ctx* ctx, const char* key) {
+    if (!ctx || !key) return -1;
+    const std::string k(key);
+    if (k == "math") return ctx->math;
+    if (k == "chunk") return ctx->chunk;
+    if (k == "snapshot") return ctx->snapshot;
+    if (k == "n_hidden") return ctx->n_hidden;
+    if (k == "workspace_domains") return ctx->ws_cap;
+    return -1;
+}
+
+int gnnb_score(gnnb_ctx* ctx, const gnnb_frontier* in, float* best_score, int32_t* best_idx, float* scores, void* stream) {
+    if (!ctx || !in || !best_score || !best_idx) return fail(ctx, GNNB_ERR_INVALID, "null argument");
+    if (!ctx->have_gnn || !ctx->have_net) return fail(ctx, GNNB_ERR_STATE, "gnnb_set_gnn_weights and gnnb_set_network must be called first");
+    if (in->B < 0) return fail(ctx, GNNB_ERR_INVALID, "negative batch");
+    if (in->B == 0) return GNNB_OK;
+    if (!in->lb || !in->ub || !in->dual || !in->prim_pre || !in->prim_post || !in->prim_out || !in->primal_input || !in->wp ||
+        !in->bp || !in->mask)
+        return fail(ctx, GNNB_ERR_INVALID, "null frontier field");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int L = (int)ctx->layers.size();
+    const bool host = in->mem == GNNB_MEM_HOST;
+    int chunk = ctx->chunk > 0 ? ctx->chunk : 128;
+    if (chunk > in->B) chunk = in->B;
+    TRY(ensure_workspace(ctx, chunk, host));
+    const std::vector<int>& n = ctx->n;
+
+    for (int c0 = 0; c0 < in->B; c0 += chunk) {
+        const int Bc = (in->B - c0) < chunk ? (in->B - c0) : chunk;
+        ChunkPtrs cp;
+        cp.lb.resize(L + 2); cp.ub.resize(L + 2); cp.dual.resize(L); cp.pre.resize(L); cp.post.resize(L);
+        auto stage = [&](const float* src, float* dst, size_t per_domain) -> const float* {
+            const float* p = src + (size_t)c0 * per_domain;
+            if (!host) return p;
+            cudaMemcpyAsync(dst, p, (size_t)Bc * per_domain * sizeof(float), cudaMemcpyHostToDevice, st);
+            return dst;
+        };
+        for (int k = 0; k <= L + 1; ++k) {
+            if (!in->lb[k] || !in->ub[k]) return fail(ctx, GNNB_ERR_INVALID, "null bound array");
+            cp.lb[k] = stage(in->lb[k], ctx->s_lb[k], n[k]);
+            cp.ub[k] = stage(in->ub[k], ctx->s_ub[k], n[k]);
+        }
+        for (int k = 0; k < L; ++k) {
+            if (!in->dual[k] || !in->prim_pre[k] || !in->prim_post[k]) return fail(ctx, GNNB_ERR_INVALID, "null dual/primal array");
+            cp.dual[k] = stage(in->dual[k], ctx->s_dual[k], (size_t)n[k + 1] * 3);
+            cp.pre[k] = stage(in->prim_pre[k], ctx->s_pre[k], n[k + 1]);
+            cp.post[k] = stage(in->prim_post[k], ctx->s_post[k], n[k + 1]);
+        }
+        cp.pout = stage(in->prim_out, ctx->s_pout, 1);
+        cp.pin = stage(in->primal_input, ctx->s_pin, n[0]);
+        cp.wp = stage(in->wp, ctx->s_wp, n[L]);
+        cp.bp = stage(in->bp, ctx->s_bp, 1);
+        cp.mask = stage(in->mask, ctx->s_mask, ctx->n_hidden);
+        CU(cudaGetLastError());
+
+        float* d_scores = (!host && scores) ? scores + (size_t)c0 * ctx->n_hidden : ctx->ws_scores;
+        float* d_best = host ? ctx->ws_best : best_score + c0;
+        int32_t* d_idx = host ? ctx->ws_idx : best_idx + c0;
+        TRY(run_chunk(ctx, cp, Bc, d_scores, d_best, d_idx, st));
+        if (host) {
+            CU(cudaMemcpyAsync(best_score + c0, d_best, (size_t)Bc * sizeof(float), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(best_idx + c0, d_idx, (size_t)Bc * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            if (scores)
+                CU(cudaMemcpyAsync(scores + (size_t)c0 * ctx->n_hidden, d_scores, (size_t)Bc * ctx->n_hidden * sizeof(float),
+                                   cudaMemcpyDeviceToHost, st));
+        }
+    }
+    if (host) return gnnb_check(ctx, stream, nullptr);
+    return GNNB_OK;
+}
+
+int gnnb_check(gnnb_ctx* ctx, void* stream, int64_t* nan_count) {
+    if (!ctx) return GNNB_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long h = 0;
+    CU(cudaMemcpyAsync(&h, ctx->d_nan, sizeof h, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (nan_count) *nan_count = (int64_t)h;
+    if (h != 0) {
+        CU(cudaMemsetAsync(ctx->d_nan, 0, sizeof h, st));
+        return fail(ctx, GNNB_ERR_NAN, "mu contains nan (" + std::to_string(h) + " tiles)");
+    }
+    return GNNB_OK;
+}
+
+int64_t gnnb_launch_count(gnnb_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+int gnnb_last_error(gnnb_ctx* ctx, char* buf, int n) {
+    if (!ctx) return GNNB_ERR_INVALID;
+    if (buf && n > 0) {
+        strncpy(buf, ctx->err.c_str(), (size_t)n - 1);
+        buf[n - 1] = 0;
+    }
+    return ctx->last_status;
+}
+
+int gnnb_debug_snapshot(gnnb_ctx* ctx, const char* name, float* dst, int64_t max_numel, int64_t* numel) {
+    if (!ctx || !name) return fail(ctx, GNNB_ERR_INVALID, "null argument");
+    auto it = ctx->snaps.find(name);
+    if (it == ctx->snaps.end()) return fail(ctx, GNNB_ERR_INVALID, std::string("no snapshot named ") + name);
+    if (numel) *numel = it->second.second;
+    if (!dst) return GNNB_OK;
+    if (max_numel < it->second.second) return fail(ctx, GNNB_ERR_INVALID, "snapshot buffer too small");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(dst, it->second.first, (size_t)it->second.second * sizeof(float), cudaMemcpyDeviceToHost));
+    return GNNB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,114 @@
+// Internal declarations shared by the libgnnb.so translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gnnb.h"
+
+namespace gnnb {
+
+constexpr int P = 64;                 // embedding size (GraphNet p; the shipped checkpoint and graph_score.py:9 use 64)
+
+// The 26 nn.Linear modules of the GNN in state_dict order (graph_conv.py:36-74, 431-432).
+enum Lin : int {
+    INP_F = 0, INP_F_1, INP_B, INP_B_1, INP_B2, INP_B2_2, FC1, FC1_1, FC3, FC3_2, FC4, FC4_2,
+    OUT1, OUT2, OUT3, BC1, BC1_1, BC1_2, BC2, BC2_1, BC3, BC3_1, BC4, BC4_1, FNODE, FSCORE, N_LIN
+};
+
+// in-features of each linear (out-features are P, except FSCORE = 1)
+__host__ __device__ constexpr int lin_in(int l) {
+    return l == INP_F ? 3 : l == INP_B ? 2 : (l == FC1 || l == BC1) ? 7 : l == OUT1 ? 4
+         : (l == INP_B2 || l == FC3 || l == FC4 || l == OUT2 || l == BC3 || l == BC4) ? 2 * P
+         : l == BC2 ? 3 * P : P;
+}
+__host__ __device__ constexpr int lin_out(int l) { return l == FSCORE ? 1 : P; }
+
+// GNN parameters on the device.
+//   wt[l]   fp32 [K][64]   transposed weight (wt[k][n] = W[n][k]), SIMT kernels and first layers
+//   bias[l] fp32 [64]
+//   tc[l]   bf16 hi/lo planes in the UMMA shared-memory layout, one 16 KB block per 64 input features
+//           (see gnnb_tc.cu for the layout); only for K >= 64 linears
+struct GnnParams {
+    const float* wt[N_LIN];
+    const float* bias[N_LIN];
+    const uint16_t* tc[N_LIN];
+    int T;
+};
+
+// One edge set of the verified network on the device.
+struct LayerDev {
+    int kind;
+    int c_in, h_in, w_in, c_out, h_out, w_out, ksize, stride, pad;
+    int n_in, n_out;
+    const float* weight;      // as given (conv [co,ci,k,k], linear [out,in])
+    const float* bias_node;   // [n_out] bias of the layer expanded per node (graph_conv.py:122-124, 133)
+};
+
+// Per-row (node) inputs of one hidden layer for one chunk of subdomains; rows = Bc * n.
+struct NodeInputs {
+    const float* lb;          // [rows]
+    const float* ub;          // [rows]
+    const float* dual;        // [rows, 3]
+    const float* prim_pre;    // [rows]
+    const float* prim_post;   // [rows]
+    const float* bias_node;   // [n]
+    int n;                    // nodes per subdomain in this layer
+    int64_t rows;
+};
+
+// ---- launchers (each enqueues on `st` and bumps *launches) -------------------------------------
+// SIMT fp32 node kernels (gnnb_simt.cu)
+void simt_relax(const GnnParams& g, const NodeInputs& in, float* relax_f, float* relax_b, cudaStream_t st, int64_t* launches);
+void simt_update(const GnnParams& g, bool backward, const float* lb, const float* ub, const float* nb, const float* relax,
+                 float* mu_out, float* scores /*or null*/, int n, int64_t score_stride, int64_t score_off, int64_t rows,
+                 unsigned long long* nan_count, cudaStream_t st, int64_t* launches);
+void simt_input_embed(const GnnParams& g, const float* lb0, const float* x, const float* ub0, float* mu0, int64_t rows,
+                      cudaStream_t st, int64_t* launches);
+void simt_input_update(const GnnParams& g, const float* lb0, const float* ub0, const float* nb, float* mu0, int64_t rows,
+                       cudaStream_t st, int64_t* launches);
+
+int simt_init();  // opt-in shared memory sizes; returns cudaError_t
+
+// tcgen05 node kernels (gnnb_tc.cu) — same contracts as the SIMT ones
+void tc_relax(const GnnParams& g, const NodeInputs& in, float* relax_f, float* relax_b, cudaStream_t st, int64_t* launches);
+void tc_update(const GnnParams& g, bool backward, const float* lb, const float* ub, const float* nb, const float* relax,
+               float* mu_out, float* scores, int n, int64_t score_stride, int64_t score_off, int64_t rows,
+               unsigned long long* nan_count, cudaStream_t st, int64_t* launches);
+void tc_input_embed(const GnnParams& g, const float* lb0, const float* x, const float* ub0, float* mu0, int64_t rows,
+                    cudaStream_t st, int64_t* launches);
+void tc_input_update(const GnnParams& g, const float* lb0, const float* ub0, const float* nb, float* mu0, int64_t rows,
+                     cudaStream_t st, int64_t* launches);
+// repack one nn.Linear weight [64][K] (host) into the tensor-core plane layout; returns elements written
+int64_t tc_pack_weight(const float* w_host, int K, uint16_t* dst_host);
+int64_t tc_packed_elems(int K);
+int tc_init();   // opt-in shared memory sizes; returns cudaError_t
+bool tc_available();
+
+// propagation through the verified network and the small kernels (gnnb_prop.cu)
+int prop_init(int max_smem_bytes);
+void prop_forward(const LayerDev& L, const float* mu_prev, float* nb, int Bc, cudaStream_t st, int64_t* launches);
+void prop_backward(const LayerDev& L, const float* mu_next, float* nb, int Bc, bool normalise, cudaStream_t st, int64_t* launches);
+void prop_property_backward(const float* wp, const float* mu_out, float* nb, int nL, int Bc, cudaStream_t st, int64_t* launches);
+void output_node(const GnnParams& g, const float* wp, const float* bp, const float* mu_L, const float* lb_out,
+                 const float* ub_out, const float* prim_out, float* mu_out, int nL, int Bc, cudaStream_t st, int64_t* launches);
+void masked_argmax(const float* scores, const float* mask, int n_hidden, int Bc, float* best_score, int32_t* best_idx,
+                   cudaStream_t st, int64_t* launches);
+
+// ---- device helpers ---------------------------------------------------------------------------
+// compute_ratio of graph_conv.py:499-514 in the reference's operation order (IEEE division, no fast-math)
+struct Ratio { float r0, r1, beta, amb; };
+__device__ __forceinline__ Ratio compute_ratio(float l, float u) {
+    Ratio r;
+    float lt = l - fmaxf(l, 0.0f);          // lower - relu(lower)
+    float ut = fmaxf(u, 0.0f);
+    if (u != u) ut = u;                     // F.relu propagates NaN, fmaxf does not
+    if (l != l) lt = l;
+    r.r0 = __fdiv_rn(ut, __fsub_rn(ut, lt));
+    r.beta = __fmul_rn(__fmul_rn(-1.0f, lt), r.r0);
+    r.amb = (r.beta > 0.0f) ? 1.0f : 0.0f;
+    r.r1 = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, __fmul_rn(2.0f, __fmul_rn(r.r0, r.amb))), r.amb), r.r0);
+    return r;
+}
+
+}  // namespace gnnb

@@ -1,0 +1,196 @@
+"""Host-side owner of a libgnnb context: uploads GNN parameters and the verified network once, then scores
+frontiers of subdomains through the C ABI (include/gnnb.h).  PyTorch is used for device memory and streams only."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from .frontier import Frontier
+from .networks import NetSpec
+
+# state_dict order of the 26 linears (graph_conv.py:36-74, 431-432) — the order gnnb_set_gnn_weights expects
+UPDATE_LINEARS = ['inp_f', 'inp_f_1', 'inp_b', 'inp_b_1', 'inp_b2', 'inp_b2_2', 'fc1', 'fc1_1', 'fc3', 'fc3_2',
+                  'fc4', 'fc4_2', 'out1', 'out2', 'out3', 'bc1', 'bc1_1', 'bc1_2', 'bc2', 'bc2_1', 'bc3', 'bc3_1',
+                  'bc4', 'bc4_1']
+SCORE_LINEARS = ['fnode', 'fscore']
+STATE_DICT_KEYS = ([f'EmbedUpdates.update.{n}.{s}' for n in UPDATE_LINEARS for s in ('weight', 'bias')]
+                   + [f'ComputeFinalScore.{n}.{s}' for n in SCORE_LINEARS for s in ('weight', 'bias')])
+
+_MATH = {'tc': _lib.MATH_TC_BF16X3, 'simt': _lib.MATH_SIMT_FP32}
+
+
+class Scorer:
+    """One libgnnb context bound to one CUDA device."""
+
+    def __init__(self, device: int = 0, math: Optional[str] = None, chunk: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError('gnn_branching_b200 needs a CUDA device (sm_100a); there is no CPU path')
+        self.lib = _lib.load()
+        self.device = int(device)
+        h = C.c_void_p()
+        st = self.lib.gnnb_create(C.byref(h), self.device)
+        if st != _lib.GNNB_OK:
+            raise _lib.GnnbError(st, 'gnnb_create failed (see stderr)')
+        self.h = h
+        self._net_key = None
+        self._gnn_key = None
+        self.net: Optional[NetSpec] = None
+        if math is not None:
+            self.set_option('math', _MATH[math])
+        if chunk:
+            self.set_option('chunk', chunk)
+
+    def __del__(self):
+        h, self.h = getattr(self, 'h', None), None
+        if h:
+            try:
+                self.lib.gnnb_destroy(h)
+            except Exception:
+                pass
+
+    # ---- helpers ----
+    def _raise(self, st: int):
+        buf = C.create_string_buffer(512)
+        self.lib.gnnb_last_error(self.h, buf, 512)
+        raise _lib.GnnbError(st, buf.value.decode(errors='replace'))
+
+    def _ok(self, st: int):
+        if st != _lib.GNNB_OK:
+            self._raise(st)
+
+    def set_option(self, key: str, value: int):
+        self._ok(self.lib.gnnb_set_option(self.h, key.encode(), int(value)))
+
+    def get_option(self, key: str) -> int:
+        return int(self.lib.gnnb_get_option(self.h, key.encode()))
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.gnnb_launch_count(self.h))
+
+    # ---- parameters ----
+    def set_gnn(self, state_dict: Dict[str, torch.Tensor], T: int = 2, p: int = 64, key=None):
+        """Upload the 52 GNN tensors (models/cifar_trained_gnn/*.pt loads unchanged)."""
+        if key is not None and key == self._gnn_key:
+            return
+        missing = [k for k in STATE_DICT_KEYS if k not in state_dict]
+        if missing:
+            raise KeyError(f'state_dict is missing {missing[:3]}...')
+        host = [state_dict[k].detach().to('cpu', torch.float32).contiguous() for k in STATE_DICT_KEYS]
+        ptrs, keep = _lib.fptr_array(host)
+        numels = (C.c_int64 * len(host))(*[t.numel() for t in host])
+        self._ok(self.lib.gnnb_set_gnn_weights(self.h, ptrs, numels, len(host), int(T), int(p)))
+        self._gnn_key = key
+        del keep
+
+    def set_network(self, net: NetSpec, key=None):
+        if key is not None and key == self._net_key:
+            return
+        descs = (_lib.LayerDesc * net.L)()
+        keep = []
+        for k, a in enumerate(net.affine):
+            w = a.weight.detach().to('cpu', torch.float32).contiguous()
+            b = a.bias.detach().to('cpu', torch.float32).contiguous()
+            keep += [w, b]
+            d = descs[k]
+            if a.kind == 'conv':
+                d.kind = _lib.LAYER_CONV
+                d.c_in, d.h_in, d.w_in = a.in_shape
+                d.c_out, d.h_out, d.w_out = a.out_shape
+                d.ksize, d.stride, d.pad = int(a.weight.shape[2]), int(a.stride), int(a.padding)
+            else:
+                d.kind = _lib.LAYER_LINEAR
+                d.c_in, d.h_in, d.w_in = a.n_in, 1, 1
+                d.c_out, d.h_out, d.w_out = a.n_out, 1, 1
+                d.ksize, d.stride, d.pad = 1, 1, 0
+            d.weight, d.bias = _lib.fptr(w), _lib.fptr(b)
+        c0, h0, w0 = net.input_shape
+        self._ok(self.lib.gnnb_set_network(self.h, descs, net.L, c0, h0, w0))
+        self.net = net
+        self._net_key = key
+        del keep
+
+    # ---- scoring ----
+    def score(self, fr: Frontier, return_scores: bool = True, check: bool = True
+              ) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+        """Score every subdomain of ``fr``.
+
+        ``fr`` on the CUDA device: zero-copy, results are CUDA tensors.  ``fr`` on the CPU: inputs are copied
+        host->device and results device->host inside the call (pin the frontier for full copy speed).
+        Returns (best_score [B] f32, best_idx [B] i32, scores [B, sum n_k] f32 or None).
+        """
+        if self.net is None:
+            raise RuntimeError('set_network first')
+        net, B = self.net, fr.B
+        L = net.L
+        host = fr.device.type == 'cpu'
+        if not host and fr.device.index not in (None, self.device):
+            raise ValueError(f'frontier is on {fr.device}, scorer on cuda:{self.device}')
+        sizes = [net.n0] + net.hidden_sizes + [1]
+        f = lambda t, shape: self._as_f32(t, shape)
+        lb = [f(fr.lb[k], (B, sizes[k])) for k in range(L + 2)]
+        ub = [f(fr.ub[k], (B, sizes[k])) for k in range(L + 2)]
+        dual = [f(fr.dual[k], (B, sizes[k + 1], 3)) for k in range(L)]
+        pre = [f(fr.prim_pre[k], (B, sizes[k + 1])) for k in range(L)]
+        post = [f(fr.prim_post[k], (B, sizes[k + 1])) for k in range(L)]
+        pout, pin = f(fr.prim_out, (B,)), f(fr.primal_input, (B, net.n0))
+        wp, bp, mask = f(fr.Wp, (B, sizes[L])), f(fr.bp, (B,)), f(fr.mask, (B, net.n_hidden))
+        dev = fr.device
+        best = torch.empty(B, dtype=torch.float32, device=dev)
+        idx = torch.empty(B, dtype=torch.int32, device=dev)
+        scores = torch.empty(B, net.n_hidden, dtype=torch.float32, device=dev) if return_scores else None
+        if B == 0:
+            return best, idx, scores
+        d = _lib.FrontierDesc()
+        d.B, d.mem = B, (_lib.MEM_HOST if host else _lib.MEM_DEVICE)
+        keep = []
+        for name, arrs in (('lb', lb), ('ub', ub), ('dual', dual), ('prim_pre', pre), ('prim_post', post)):
+            p, k = _lib.fptr_array(arrs)
+            setattr(d, name, p)
+            keep.append(k)
+        d.prim_out, d.primal_input, d.wp, d.bp, d.mask = map(_lib.fptr, (pout, pin, wp, bp, mask))
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            st = self.lib.gnnb_score(self.h, C.byref(d), _lib.fptr(best), C.cast(idx.data_ptr(), C.POINTER(C.c_int32)),
+                                     _lib.fptr(scores) if scores is not None else None, C.c_void_p(stream))
+            if st != _lib.GNNB_OK:
+                self._raise(st)
+            if check and not host:
+                self.check()
+        return best, idx, scores
+
+    def check(self) -> None:
+        """Synchronise and raise if a NaN appeared in an embedding (the reference drops into pdb there)."""
+        n = C.c_int64(0)
+        with torch.cuda.device(self.device):
+            st = self.lib.gnnb_check(self.h, C.c_void_p(torch.cuda.current_stream().cuda_stream), C.byref(n))
+        if st != _lib.GNNB_OK:
+            self._raise(st)
+
+    def snapshot(self, name: str) -> torch.Tensor:
+        n = C.c_int64(0)
+        self._ok(self.lib.gnnb_debug_snapshot(self.h, name.encode(), None, 0, C.byref(n)))
+        out = torch.empty(n.value, dtype=torch.float32)
+        self._ok(self.lib.gnnb_debug_snapshot(self.h, name.encode(), _lib.fptr(out), n.value, C.byref(n)))
+        return out
+
+    @staticmethod
+    def _as_f32(t: torch.Tensor, shape) -> torch.Tensor:
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f'expected shape {tuple(shape)}, got {tuple(t.shape)}')
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            t = t.float().contiguous()
+        return t
+
+
+def flat_to_layer_index(flat_idx: int, hidden_sizes) -> list:
+    """graph_score.py:43-47: flat ReLU index -> [dec_lay, dec_idx] via the cumulative layer sizes."""
+    off = 0
+    for lay, n in enumerate(hidden_sizes):
+        if flat_idx < off + n:
+            return [lay, flat_idx - off]
+        off += n
+    raise IndexError(flat_idx)

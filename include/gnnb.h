@@ -1,0 +1,127 @@
+/*
+ * gnnb.h — C ABI of libgnnb.so: B200-native batched GNN branching scores.
+ *
+ * Drop-in boundary for the GNN ReLU-scoring hot path of oval-group/GNN_branching.  The reference has no
+ * FFI layer; its boundary is the Python class API (graphnet/graph_conv.py:473-483 GraphNet,
+ * graphnet/graph_score.py:8-56 GraphChoice).  Each entry point below names the reference interface it
+ * replaces; gnn_branching_b200/graph_conv.py and graph_score.py bind them with ctypes and keep the
+ * reference's Python signatures.  See INTEGRATION.md for the binding a reference maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only; every function returns a status (0 = ok) and never throws;
+ * the context is bound to one CUDA device and is not re-entrant; all fp32, indices int32.
+ */
+#ifndef GNNB_H
+#define GNNB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gnnb_ctx gnnb_ctx;
+
+enum gnnb_status {
+    GNNB_OK = 0,
+    GNNB_ERR_INVALID = 1,      /* bad argument / shape mismatch */
+    GNNB_ERR_CUDA = 2,         /* a CUDA runtime call failed (message in gnnb_last_error) */
+    GNNB_ERR_STATE = 3,        /* weights or network not set */
+    GNNB_ERR_NAN = 4,          /* NaN appeared in an embedding: the reference stops in pdb here
+                                  (graphnet/graph_conv.py:184-186, 339-341); outputs are still written */
+    GNNB_ERR_UNSUPPORTED = 5
+};
+
+enum gnnb_layer_kind { GNNB_LAYER_CONV = 0, GNNB_LAYER_LINEAR = 1 };
+enum gnnb_mem_kind { GNNB_MEM_DEVICE = 0, GNNB_MEM_HOST = 1 };
+
+/* Arithmetic of the per-node MLP GEMMs.  Both are sm_100a CUDA; TC is the product path, SIMT the
+ * exact-fp32 validation path used by the tests to localise tensor-path errors. */
+enum gnnb_math_mode {
+    GNNB_MATH_TC_BF16X3 = 0,   /* tcgen05.mma kind::f16, bf16 hi/lo split, 3 MMAs, fp32 accumulate in TMEM */
+    GNNB_MATH_SIMT_FP32 = 1    /* fp32 FMA on CUDA cores */
+};
+
+/* One edge set A_k of the graph = one conv / linear layer of the verified network followed by a ReLU
+ * (reference: layers['fixed_layers'], graphnet/graph_conv.py:107-137).  Weight and bias are HOST pointers,
+ * copied (and repacked) by gnnb_set_network. */
+typedef struct {
+    int32_t kind;                        /* gnnb_layer_kind */
+    int32_t c_in, h_in, w_in;            /* conv input shape (linear: c_in = n_in, h_in = w_in = 1) */
+    int32_t c_out, h_out, w_out;         /* conv output shape (linear: c_out = n_out, 1, 1) */
+    int32_t ksize, stride, pad;          /* conv only (square kernels) */
+    const float* weight;                 /* conv [c_out, c_in, k, k]; linear [n_out, n_in] (nn.Linear layout) */
+    const float* bias;                   /* [c_out] */
+} gnnb_layer_desc;
+
+/* A frontier of B subdomains, struct-of-arrays, node index within a layer = PyTorch NCHW flatten
+ * (reference: the argument lists of GraphNet.forward, graphnet/graph_conv.py:479).
+ * All pointers live in the memory space named by `mem` (device, or host — pinned for full copy speed). */
+typedef struct {
+    int32_t B;
+    int32_t mem;                         /* gnnb_mem_kind of every pointer below AND of gnnb_score's outputs */
+    const float* const* lb;              /* L+2 arrays [B, n_k]: k = 0 input, 1..L hidden pre-ReLU, L+1 output */
+    const float* const* ub;              /* L+2 arrays [B, n_k] */
+    const float* const* dual;            /* L arrays [B, n_k, 3]   (dual_vars) */
+    const float* const* prim_pre;        /* L arrays [B, n_k]      (primals[i_k]) */
+    const float* const* prim_post;       /* L arrays [B, n_k]      (primals[i_k + 1]) */
+    const float* prim_out;               /* [B]                    (primals[-1]) */
+    const float* primal_input;           /* [B, n_0]               (primal_inputs) */
+    const float* wp;                     /* [B, n_L] property layer weights (layers['prop_layers'][b].weight) */
+    const float* bp;                     /* [B]      property layer biases */
+    const float* mask;                   /* [B, sum n_k] 0/1, 1 = branching candidate (masks) */
+} gnnb_frontier;
+
+/* Create a context on CUDA device `device`.  Replaces GraphChoice.__init__'s `.cuda()` (graph_score.py:13). */
+int gnnb_create(gnnb_ctx** out, int device);
+void gnnb_destroy(gnnb_ctx* ctx);
+
+/* Load the GNN parameters: 52 HOST fp32 tensors in state_dict order — for each of
+ * inp_f, inp_f_1, inp_b, inp_b_1, inp_b2, inp_b2_2, fc1, fc1_1, fc3, fc3_2, fc4, fc4_2, out1, out2, out3,
+ * bc1, bc1_1, bc1_2, bc2, bc2_1, bc3, bc3_1, bc4, bc4_1 (EmbedUpdates.update.*), fnode, fscore
+ * (ComputeFinalScore.*): weight [out, in] then bias [out].  Replaces model.load_state_dict
+ * (graph_score.py:11); T, p are GraphNet's constructor arguments (graph_conv.py:474); p must be 64. */
+int gnnb_set_gnn_weights(gnnb_ctx* ctx, const float* const* tensors, const int64_t* numels, int n_tensors,
+                         int T, int p);
+
+/* Describe the verified network (the graph).  Replaces the per-call walk over layers['fixed_layers']
+ * (graph_conv.py:107-137, 222-249). */
+int gnnb_set_network(gnnb_ctx* ctx, const gnnb_layer_desc* layers, int n_layers, int c0, int h0, int w0);
+
+/* Options: "math" (gnnb_math_mode), "chunk" (subdomains per wave; 0 = auto), "snapshot" (0/1: keep
+ * per-stage copies for gnnb_debug_snapshot; debugging only). */
+int gnnb_set_option(gnnb_ctx* ctx, const char* key, int64_t value);
+int64_t gnnb_get_option(gnnb_ctx* ctx, const char* key);
+
+/* Score a frontier.  Replaces GraphNet.forward (graph_conv.py:479-483) + the argmax / index mapping of
+ * GraphChoice.decision (graph_score.py:41-47) for B subdomains at once.
+ *   best_score [B]   score of the winning ReLU (-inf when the domain has no candidate)
+ *   best_idx   [B]   its flat index into the concatenated hidden layers, lowest index on ties, -1 when none
+ *   scores     [B, sum n_k] or NULL: dense scores of every hidden ReLU (only rows with mask != 0 are
+ *                    what the reference returns)
+ * Work is enqueued on `stream` (a cudaStream_t, NULL = default stream).  With mem = HOST the call copies
+ * inputs in and results out on that stream and returns after they have landed; with mem = DEVICE it
+ * returns without synchronising and GNNB_ERR_NAN is reported by gnnb_check. */
+int gnnb_score(gnnb_ctx* ctx, const gnnb_frontier* in, float* best_score, int32_t* best_idx, float* scores,
+               void* stream);
+
+/* Synchronise `stream` and report sticky device-side errors of earlier gnnb_score calls
+ * (GNNB_ERR_NAN with the NaN count in *nan_count, may be NULL).  Clears the flag. */
+int gnnb_check(gnnb_ctx* ctx, void* stream, int64_t* nan_count);
+
+/* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
+int64_t gnnb_launch_count(gnnb_ctx* ctx);
+
+/* Copy the last error message into buf (NUL-terminated, truncated to n). Returns the last status. */
+int gnnb_last_error(gnnb_ctx* ctx, char* buf, int n);
+
+/* Debugging: copy a per-stage snapshot (names follow the oracle's `stages` keys, e.g. "t0_fwd_mu1") of
+ * the LAST chunk processed to a HOST buffer; returns the element count through *numel. */
+int gnnb_debug_snapshot(gnnb_ctx* ctx, const char* name, float* dst, int64_t max_numel, int64_t* numel);
+
+/* ABI version of this header. */
+int gnnb_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNNB_H */
