@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Benchmark of the GNN branching-score hot path: subdomains scored per second on a B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload base|wide|deep] [--domains B_per_gpu]
+    python bench.py --impl reference ...      # the reference algorithm on the host CPU (oracle port)
+
+One step = one pass of the hot path over one frontier of synthetic subdomains (SURVEY §8d generator):
+at N = 1 the workload is BASELINE.json configs[1], cifar_base_kw x 1 024 subdomains; at N > 1 every rank scores
+the same number of subdomains (weak scaling, no data-path collective) and the per-subdomain winners are
+all-gathered with NCCL inside the timed region.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+METRIC = 'gnn_subdomains_scored_per_sec'
+UNIT = 'subdomains/s'
+DEFAULT_DOMAINS = {'base': 1024, 'wide': 4096, 'deep': 4096}
+CPU_SAMPLE = 32          # subdomains per CPU-baseline pass (the reference's CPU rate is flat from B = 4)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='base', choices=['base', 'wide', 'deep'])
+    ap.add_argument('--domains', type=int, default=0, help='subdomains per GPU per step (default: BASELINE config size)')
+    ap.add_argument('--math', default=None, choices=['tc', 'simt'])
+    ap.add_argument('--chunk', type=int, default=0)
+    ap.add_argument('--weights', default='random', choices=['random', 'shipped'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+def load_problem(workload):
+    """Verified net + KW root bounds of one property (tests/golden/nets.npz) and the GNN weights."""
+    from golden_io import load_root
+    return load_root(workload)
+
+
+def load_weights(which):
+    from golden_io import load_gnn
+    return load_gnn(which)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '200', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons, power = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': max(mx), 'reasons': sorted(reasons),
+                'power_w_max': max(power), 'samples': len(sm)}
+
+
+def cpu_baseline(workload, weights, threads=None, reps=3):
+    """The reference algorithm (oracle port, fp32 PyTorch-CPU like the reference itself) on the host cores."""
+    import torch
+    from gnn_branching_b200 import synthetic_frontier
+    from oracle import graphnet_oracle as O
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    net, lbs, ubs, wp, bp = load_problem(workload)
+    fr = synthetic_frontier(net, lbs, ubs, wp, bp, CPU_SAMPLE, seed=99)
+    sd = load_weights(weights)
+    with torch.no_grad():
+        O.gnn_forward(sd, fr.slice(0, 4))                  # warm-up
+        times = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            s, _ = O.gnn_forward(sd, fr)
+            O.decide(s, fr.mask, net.hidden_sizes)
+            times.append(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        O.gnn_forward(sd, fr.slice(0, 1))
+        lat1 = time.perf_counter() - t0
+    best = min(times)
+    return {'value': CPU_SAMPLE / best, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+            'sample': f'{CPU_SAMPLE} cifar_{workload}_kw subdomains x {reps} passes, best pass; oracle/graphnet_oracle.py '
+                      f'(fp32 torch-CPU restatement of graphnet/graph_conv.py); B=1 latency {lat1 * 1e3:.1f} ms',
+            'median_value': CPU_SAMPLE / statistics.median(times)}, times
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm on this box's host cores (oracle port)."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cb, times = cpu_baseline(args.workload, args.weights, reps=max(1, args.steps + args.warmup))
+    times = times[args.warmup:] or times
+    per = sum(times) / len(times)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': CPU_SAMPLE / per, 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': len(times), 'warmup': args.warmup, 'ms_per_step': per * 1e3, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': f'cifar_{args.workload}_kw, {CPU_SAMPLE}-subdomain sample per step on the host CPU',
+                       'gnn': 'GraphNet(T=2,p=64)', 'weights': args.weights},
+            'cpu_baseline': {**cb, 'value': CPU_SAMPLE / per},
+            'e2e': {'value': CPU_SAMPLE / per, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from gnn_branching_b200 import GraphNet, synthetic_frontier
+    from gnn_branching_b200.dist import gather_winners
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the scoring path has no CPU fallback')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    B = args.domains or DEFAULT_DOMAINS[args.workload]
+    K, W = args.steps, max(args.warmup, 0)
+
+    net, lbs, ubs, wp, bp = load_problem(args.workload)
+    sd = load_weights(args.weights)
+    model = GraphNet(2, 64, math=args.math, chunk=args.chunk)
+    model.load_state_dict(sd)
+    model = model.eval().to(dev)
+    # two different frontiers used alternately: with the workspace they exceed the 126 MB L2 several times over
+    fronts = [synthetic_frontier(net, lbs, ubs, wp, bp, B, seed=1000 * (7 + rank) + i, device=dev) for i in range(2)]
+    scorer = model.scorer(local)
+    math_mode = {0: 'tc', 1: 'simt'}[scorer.get_option('math')]
+
+    def step(i):
+        best, idx, _ = scorer_score(fronts[i % 2])
+        if world > 1:
+            best, idx = gather_winners(best, idx, B * world)
+        return best, idx
+
+    def scorer_score(fr):
+        scorer.set_network(fr.net, key='bench')
+        return scorer.score(fr, return_scores=False, check=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        step(i)
+    scorer.check()
+    barrier()
+    launches0 = scorer.launches
+    scorer.set_option('profile', 1)
+    scorer.profile_reset()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        ev0.record()
+        for i in range(K):
+            step(i)
+        ev1.record()
+        barrier()
+    scorer.check()
+    ms = ev0.elapsed_time(ev1)
+    launches = scorer.launches - launches0
+    prof = scorer.profile_read()
+    scorer.set_option('profile', 0)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = B * world * K / (ms * 1e-3)
+
+    # ---- end to end through the public API with pinned HOST buffers (copies inside the timed region) ----
+    e2e = None
+    if not args.no_e2e:
+        host_fronts = [f.cpu().pin() for f in fronts]
+        for i in range(min(W, 2)):
+            model.score_frontier(host_fronts[i % 2], return_scores=False)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            hb, hi, _ = model.score_frontier(host_fronts[i % 2], return_scores=False)
+            if world > 1:
+                gather_winners(hb.to(dev), hi.to(dev), B * world)
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {'value': B * world * K / dt, 'unit': UNIT, 'h2d_bytes_per_step': host_fronts[0].input_bytes(),
+               'd2h_bytes_per_step': B * 8, 'api': 'GraphNet.score_frontier(pinned host Frontier)'}
+        del host_fronts
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (node-update MLP), from live CUDA-event timings ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except (OSError, ValueError):
+        pass
+    peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
+    peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if peaks else 'B200_PROFILING.md fallback 1.4 PF sustained (of fallback)'
+    p = 64
+    per_row = {'update_fwd': 2 * 6 * p * p, 'update_bwd': 2 * 6 * p * p, 'update_bwd_score': 2 * (7 * p * p + p)}
+    upd_ms = sum(prof[k]['ms'] for k in per_row)
+    upd_flop = sum(prof[k]['rows'] * f for k, f in per_row.items())
+    upd_launches = sum(prof[k]['launches'] for k in per_row)
+    total_prof_ms = sum(v['ms'] for v in prof.values())
+    achieved = upd_flop / (upd_ms * 1e-3) / 1e12 if upd_ms > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'update_kernel_traffic.json')))['dram_bytes_per_launch']
+    except (OSError, ValueError, KeyError):
+        pass
+    flops_dom = net.flops_per_domain()
+    roofline = {'bound': 'tensor', 'kernel': 'node-update MLP (update_fwd / update_bwd / update_bwd_score)',
+                'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
+                'peak_source': peak_src, 'traffic': traffic,
+                'algorithmic_flop_per_node': per_row, 'launches': upd_launches,
+                'avg_launch_ms': upd_ms / max(upd_launches, 1),
+                'share_of_step': upd_ms / total_prof_ms if total_prof_ms else None,
+                'whole_path': {'flop_per_subdomain': flops_dom, 'achieved_tflops': value / world * flops_dom / 1e12,
+                               'frac_of_peak': value / world * flops_dom / 1e12 / peak_tf},
+                'kernel_ms': {k: round(v['ms'], 3) for k, v in prof.items()}}
+
+    cb = None
+    if not args.no_cpu_baseline and world == 1:
+        cb, _ = cpu_baseline(args.workload, args.weights)
+
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
+            'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16x3 (fp32 accumulate)' if math_mode == 'tc' else 'f32', 'data': 'synthetic',
+            'config': {'workload': f'cifar_{args.workload}_kw x {B} synthetic subdomains per GPU per step',
+                       'gnn': 'GraphNet(T=2,p=64)', 'weights': args.weights, 'math': math_mode,
+                       'chunk': scorer.get_option('workspace_domains'),
+                       'l2': 'two alternating frontiers; inputs + per-chunk workspace exceed the 126 MB L2',
+                       'sharding': f'{world} ranks x {B} subdomains, winners all-gathered (8 B/subdomain)'},
+            'clocks': clk.summary(), 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cb}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

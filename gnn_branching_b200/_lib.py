@@ -11,10 +11,12 @@ GNNB_OK, GNNB_ERR_INVALID, GNNB_ERR_CUDA, GNNB_ERR_STATE, GNNB_ERR_NAN, GNNB_ERR
 LAYER_CONV, LAYER_LINEAR = 0, 1
 MEM_DEVICE, MEM_HOST = 0, 1
 MATH_TC_BF16X3, MATH_SIMT_FP32 = 0, 1
+KERNEL_CLASSES = ['relax', 'update_fwd', 'update_bwd', 'update_bwd_score', 'input_embed', 'input_update', 'prop_fwd',
+                  'prop_bwd', 'output', 'argmax']
 
 EXPORTS = ['gnnb_create', 'gnnb_destroy', 'gnnb_set_gnn_weights', 'gnnb_set_network', 'gnnb_set_option',
            'gnnb_get_option', 'gnnb_score', 'gnnb_check', 'gnnb_launch_count', 'gnnb_last_error',
-           'gnnb_debug_snapshot', 'gnnb_abi_version']
+           'gnnb_debug_snapshot', 'gnnb_abi_version', 'gnnb_profile_read', 'gnnb_profile_reset']
 
 _fp = C.POINTER(C.c_float)
 _fpp = C.POINTER(_fp)
@@ -67,6 +69,8 @@ def load() -> C.CDLL:
     lib.gnnb_launch_count.restype = C.c_int64
     lib.gnnb_last_error.argtypes = [vp, C.c_char_p, C.c_int]
     lib.gnnb_debug_snapshot.argtypes = [vp, C.c_char_p, _fp, C.c_int64, C.POINTER(C.c_int64)]
+    lib.gnnb_profile_read.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.gnnb_profile_reset.argtypes = [vp]
     for name in EXPORTS:
         getattr(lib, name)
     _lib = lib

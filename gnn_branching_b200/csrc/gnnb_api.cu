@@ -54,6 +54,14 @@ struct gnnb_ctx {
     unsigned long long* d_nan = nullptr;
     // debugging snapshots
     std::map<std::string, std::pair<float*, int64_t>> snaps;
+    // per-kernel-class device timing (option "profile")
+    int profile = 0;
+    struct Pending { int klass; int64_t rows; cudaEvent_t a, b; };
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> ev_pool;
+    double prof_ms[GNNB_K_COUNT] = {0};
+    int64_t prof_launches[GNNB_K_COUNT] = {0};
+    int64_t prof_rows[GNNB_K_COUNT] = {0};
 };
 
 namespace {
@@ -140,6 +148,41 @@ int snap(gnnb_ctx* ctx, const std::string& name, const float* src, int64_t numel
     return GNNB_OK;
 }
 
+cudaEvent_t prof_event(gnnb_ctx* ctx) {
+    if (!ctx->ev_pool.empty()) { cudaEvent_t e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+// brackets one stage launch with events on its stream
+struct ProfScope {
+    gnnb_ctx* ctx; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr; int klass; int64_t rows;
+    ProfScope(gnnb_ctx* c, int k, int64_t r, cudaStream_t s) : ctx(c), st(s), klass(k), rows(r) {
+        if (ctx->profile) { a = prof_event(ctx); b = prof_event(ctx); cudaEventRecord(a, st); }
+    }
+    ~ProfScope() {
+        if (ctx->profile) { cudaEventRecord(b, st); ctx->pending.push_back({klass, rows, a, b}); }
+    }
+};
+
+int prof_collect(gnnb_ctx* ctx) {
+    if (ctx->pending.empty()) return GNNB_OK;
+    CU(cudaDeviceSynchronize());
+    for (auto& p : ctx->pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            ctx->prof_ms[p.klass] += ms;
+            ctx->prof_launches[p.klass] += 1;
+            ctx->prof_rows[p.klass] += p.rows;
+        }
+        ctx->ev_pool.push_back(p.a);
+        ctx->ev_pool.push_back(p.b);
+    }
+    ctx->pending.clear();
+    return GNNB_OK;
+}
+
 struct ChunkPtrs {
     std::vector<const float*> lb, ub, dual, pre, post;
     const float *pout, *pin, *wp, *bp, *mask;
@@ -160,14 +203,20 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
     for (int k = 1; k <= L; ++k) {
         NodeInputs ni{in.lb[k], in.ub[k], in.dual[k - 1], in.pre[k - 1], in.post[k - 1], ctx->layers[k - 1].bias_node,
                       ctx->n[k], (int64_t)Bc * ctx->n[k]};
-        if (tc) tc_relax(g, ni, ctx->relax_f[k], ctx->relax_b[k], st, lc);
-        else simt_relax(g, ni, ctx->relax_f[k], ctx->relax_b[k], st, lc);
+        {
+            ProfScope ps(ctx, GNNB_K_RELAX, ni.rows, st);
+            if (tc) tc_relax(g, ni, ctx->relax_f[k], ctx->relax_b[k], st, lc);
+            else simt_relax(g, ni, ctx->relax_f[k], ctx->relax_b[k], st, lc);
+        }
         TRY(snap(ctx, name("relax_f%d", k, 0), ctx->relax_f[k], ni.rows * P, st));
         TRY(snap(ctx, name("relax_b%d", k, 0), ctx->relax_b[k], ni.rows * P, st));
     }
     const int64_t rows0 = (int64_t)Bc * ctx->n[0];
-    if (tc) tc_input_embed(g, in.lb[0], in.pin, in.ub[0], ctx->mu[0], rows0, st, lc);
-    else simt_input_embed(g, in.lb[0], in.pin, in.ub[0], ctx->mu[0], rows0, st, lc);
+    {
+        ProfScope ps(ctx, GNNB_K_INPUT_EMBED, rows0, st);
+        if (tc) tc_input_embed(g, in.lb[0], in.pin, in.ub[0], ctx->mu[0], rows0, st, lc);
+        else simt_input_embed(g, in.lb[0], in.pin, in.ub[0], ctx->mu[0], rows0, st, lc);
+    }
     TRY(snap(ctx, "mu0_embed", ctx->mu[0], rows0 * P, st));
 
     for (int t = 0; t < g.T; ++t) {
@@ -175,34 +224,58 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
         // forward sweep
         for (int k = 1; k <= L; ++k) {
             const int64_t rows = (int64_t)Bc * ctx->n[k];
-            prop_forward(ctx->layers[k - 1], ctx->mu[k - 1], ctx->nb, Bc, st, lc);
+            {
+                ProfScope ps(ctx, GNNB_K_PROP_FWD, rows, st);
+                prop_forward(ctx->layers[k - 1], ctx->mu[k - 1], ctx->nb, Bc, st, lc);
+            }
             TRY(snap(ctx, name("t%d_fwd_nb%d", t, k), ctx->nb, rows * P, st));
-            if (tc) tc_update(g, false, in.lb[k], in.ub[k], ctx->nb, ctx->relax_f[k], ctx->mu[k], nullptr, ctx->n[k], 0, 0, rows, ctx->d_nan, st, lc);
-            else simt_update(g, false, in.lb[k], in.ub[k], ctx->nb, ctx->relax_f[k], ctx->mu[k], nullptr, ctx->n[k], 0, 0, rows, ctx->d_nan, st, lc);
+            {
+                ProfScope ps(ctx, GNNB_K_UPDATE_FWD, rows, st);
+                if (tc) tc_update(g, false, in.lb[k], in.ub[k], ctx->nb, ctx->relax_f[k], ctx->mu[k], nullptr, ctx->n[k], 0, 0, rows, ctx->d_nan, st, lc);
+                else simt_update(g, false, in.lb[k], in.ub[k], ctx->nb, ctx->relax_f[k], ctx->mu[k], nullptr, ctx->n[k], 0, 0, rows, ctx->d_nan, st, lc);
+            }
             TRY(snap(ctx, name("t%d_fwd_mu%d", t, k), ctx->mu[k], rows * P, st));
         }
-        output_node(g, in.wp, in.bp, ctx->mu[L], in.lb[L + 1], in.ub[L + 1], in.pout, ctx->mu[L + 1], ctx->n[L], Bc, st, lc);
+        {
+            ProfScope ps(ctx, GNNB_K_OUTPUT, Bc, st);
+            output_node(g, in.wp, in.bp, ctx->mu[L], in.lb[L + 1], in.ub[L + 1], in.pout, ctx->mu[L + 1], ctx->n[L], Bc, st, lc);
+        }
         TRY(snap(ctx, name("t%d_mu_out", t, 0), ctx->mu[L + 1], (int64_t)Bc * P, st));
         // backward sweep
         for (int k = L; k >= 1; --k) {
             const int64_t rows = (int64_t)Bc * ctx->n[k];
-            if (k == L) prop_property_backward(in.wp, ctx->mu[L + 1], ctx->nb, ctx->n[L], Bc, st, lc);
-            else prop_backward(ctx->layers[k], ctx->mu[k + 1], ctx->nb, Bc, true, st, lc);
+            {
+                ProfScope ps(ctx, GNNB_K_PROP_BWD, rows, st);
+                if (k == L) prop_property_backward(in.wp, ctx->mu[L + 1], ctx->nb, ctx->n[L], Bc, st, lc);
+                else prop_backward(ctx->layers[k], ctx->mu[k + 1], ctx->nb, Bc, true, st, lc);
+            }
             TRY(snap(ctx, name("t%d_bwd_nb%d", t, k), ctx->nb, rows * P, st));
             float* sc = last ? scores : nullptr;
-            if (tc) tc_update(g, true, in.lb[k], in.ub[k], ctx->nb, ctx->relax_b[k], ctx->mu[k], sc, ctx->n[k], ctx->n_hidden, ctx->hidden_off[k], rows, ctx->d_nan, st, lc);
-            else simt_update(g, true, in.lb[k], in.ub[k], ctx->nb, ctx->relax_b[k], ctx->mu[k], sc, ctx->n[k], ctx->n_hidden, ctx->hidden_off[k], rows, ctx->d_nan, st, lc);
+            {
+                ProfScope ps(ctx, last ? GNNB_K_UPDATE_BWD_SCORE : GNNB_K_UPDATE_BWD, rows, st);
+                if (tc) tc_update(g, true, in.lb[k], in.ub[k], ctx->nb, ctx->relax_b[k], ctx->mu[k], sc, ctx->n[k], ctx->n_hidden, ctx->hidden_off[k], rows, ctx->d_nan, st, lc);
+                else simt_update(g, true, in.lb[k], in.ub[k], ctx->nb, ctx->relax_b[k], ctx->mu[k], sc, ctx->n[k], ctx->n_hidden, ctx->hidden_off[k], rows, ctx->d_nan, st, lc);
+            }
             TRY(snap(ctx, name("t%d_bwd_mu%d", t, k), ctx->mu[k], rows * P, st));
         }
         // input layer: feeds the next round only (dead on the last round)
         if (!last) {
-            prop_backward(ctx->layers[0], ctx->mu[1], ctx->nb, Bc, false, st, lc);
-            if (tc) tc_input_update(g, in.lb[0], in.ub[0], ctx->nb, ctx->mu[0], rows0, st, lc);
-            else simt_input_update(g, in.lb[0], in.ub[0], ctx->nb, ctx->mu[0], rows0, st, lc);
+            {
+                ProfScope ps(ctx, GNNB_K_PROP_BWD, rows0, st);
+                prop_backward(ctx->layers[0], ctx->mu[1], ctx->nb, Bc, false, st, lc);
+            }
+            {
+                ProfScope ps(ctx, GNNB_K_INPUT_UPDATE, rows0, st);
+                if (tc) tc_input_update(g, in.lb[0], in.ub[0], ctx->nb, ctx->mu[0], rows0, st, lc);
+                else simt_input_update(g, in.lb[0], in.ub[0], ctx->nb, ctx->mu[0], rows0, st, lc);
+            }
             TRY(snap(ctx, name("t%d_mu0", t, 0), ctx->mu[0], rows0 * P, st));
         }
     }
-    masked_argmax(scores, in.mask, ctx->n_hidden, Bc, best_score, best_idx, st, lc);
+    {
+        ProfScope ps(ctx, GNNB_K_ARGMAX, Bc, st);
+        masked_argmax(scores, in.mask, ctx->n_hidden, Bc, best_score, best_idx, st, lc);
+    }
     CU(cudaGetLastError());
     return GNNB_OK;
 }
@@ -247,6 +320,8 @@ void gnnb_destroy(gnnb_ctx* ctx) {
     if (ctx->d_tc) cudaFree(ctx->d_tc);
     if (ctx->d_net) cudaFree(ctx->d_net);
     if (ctx->d_nan) cudaFree(ctx->d_nan);
+    for (auto& p : ctx->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     delete ctx;
 }
 
@@ -382,6 +457,8 @@ int gnnb_set_option(gnnb_ctx* ctx, const char* key, int64_t value) {
         ctx->chunk = (int)value;
     } else if (k == "snapshot") {
         ctx->snapshot = value ? 1 : 0;
+    } else if (k == "profile") {
+        ctx->profile = value ? 1 : 0;
     } else {
         return fail(ctx, GNNB_ERR_INVALID, "unknown option " + k);
     }
@@ -394,6 +471,7 @@ int64_t gnnb_get_option(gnnb_ctx* ctx, const char* key) {
     if (k == "math") return ctx->math;
     if (k == "chunk") return ctx->chunk;
     if (k == "snapshot") return ctx->snapshot;
+    if (k == "profile") return ctx->profile;
     if (k == "n_hidden") return ctx->n_hidden;
     if (k == "workspace_domains") return ctx->ws_cap;
     return -1;
@@ -484,6 +562,24 @@ int gnnb_last_error(gnnb_ctx* ctx, char* buf, int n) {
         buf[n - 1] = 0;
     }
     return ctx->last_status;
+}
+
+int gnnb_profile_read(gnnb_ctx* ctx, int klass, double* ms, int64_t* launches, int64_t* rows) {
+    if (!ctx || klass < 0 || klass >= GNNB_K_COUNT) return fail(ctx, GNNB_ERR_INVALID, "bad kernel class");
+    CU(cudaSetDevice(ctx->device));
+    TRY(prof_collect(ctx));
+    if (ms) *ms = ctx->prof_ms[klass];
+    if (launches) *launches = ctx->prof_launches[klass];
+    if (rows) *rows = ctx->prof_rows[klass];
+    return GNNB_OK;
+}
+
+int gnnb_profile_reset(gnnb_ctx* ctx) {
+    if (!ctx) return GNNB_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    TRY(prof_collect(ctx));
+    for (int k = 0; k < GNNB_K_COUNT; ++k) { ctx->prof_ms[k] = 0; ctx->prof_launches[k] = 0; ctx->prof_rows[k] = 0; }
+    return GNNB_OK;
 }
 
 int gnnb_debug_snapshot(gnnb_ctx* ctx, const char* name, float* dst, int64_t max_numel, int64_t* numel) {

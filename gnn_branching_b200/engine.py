@@ -130,7 +130,12 @@ class Scorer:
         if not host and fr.device.index not in (None, self.device):
             raise ValueError(f'frontier is on {fr.device}, scorer on cuda:{self.device}')
         sizes = [net.n0] + net.hidden_sizes + [1]
-        f = lambda t, shape: self._as_f32(t, shape)
+
+        def f(t, shape):
+            if t.device != fr.device:
+                raise ValueError(f'frontier tensors live on different devices ({t.device} vs {fr.device})')
+            return self._as_f32(t, shape)
+
         lb = [f(fr.lb[k], (B, sizes[k])) for k in range(L + 2)]
         ub = [f(fr.ub[k], (B, sizes[k])) for k in range(L + 2)]
         dual = [f(fr.dual[k], (B, sizes[k + 1], 3)) for k in range(L)]
@@ -169,6 +174,18 @@ class Scorer:
             st = self.lib.gnnb_check(self.h, C.c_void_p(torch.cuda.current_stream().cuda_stream), C.byref(n))
         if st != _lib.GNNB_OK:
             self._raise(st)
+
+    def profile_reset(self):
+        self._ok(self.lib.gnnb_profile_reset(self.h))
+
+    def profile_read(self) -> Dict[str, dict]:
+        """{kernel class: {'ms', 'launches', 'rows'}} accumulated while option 'profile' = 1."""
+        out = {}
+        for i, name in enumerate(_lib.KERNEL_CLASSES):
+            ms, n, rows = C.c_double(0), C.c_int64(0), C.c_int64(0)
+            self._ok(self.lib.gnnb_profile_read(self.h, i, C.byref(ms), C.byref(n), C.byref(rows)))
+            out[name] = dict(ms=ms.value, launches=n.value, rows=rows.value)
+        return out
 
     def snapshot(self, name: str) -> torch.Tensor:
         n = C.c_int64(0)

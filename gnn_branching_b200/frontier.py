@@ -89,7 +89,8 @@ class Frontier:
             raise ValueError(f'expected {L + 2} bound tensors, got {len(lower_bounds_all)}')
         if len(dual_vars) < L:
             raise ValueError(f'expected {L} dual tensors, got {len(dual_vars)}')
-        f32 = lambda t: torch.as_tensor(t).float()
+        dev = torch.as_tensor(lower_bounds_all[0]).device     # everything follows the bounds' device
+        f32 = lambda t: torch.as_tensor(t).to(dev).float()
         lb = [f32(t).reshape(B, -1) for t in lower_bounds_all]
         ub = [f32(t).reshape(B, -1) for t in upper_bounds_all]
         dual = [f32(dual_vars[k]).reshape(B, net.affine[k].n_out, 3) for k in range(L)]

@@ -41,6 +41,21 @@ enum gnnb_math_mode {
     GNNB_MATH_SIMT_FP32 = 1    /* fp32 FMA on CUDA cores */
 };
 
+/* Kernel classes of the stage schedule, for gnnb_profile_read. */
+enum gnnb_kernel_class {
+    GNNB_K_RELAX = 0,          /* round-independent relaxation-feature MLPs of a hidden layer */
+    GNNB_K_UPDATE_FWD,         /* forward-sweep node update (fc3, fc3_2, fc4, fc4_2) */
+    GNNB_K_UPDATE_BWD,         /* backward-sweep node update (bc3, bc3_1, bc4, bc4_1) */
+    GNNB_K_UPDATE_BWD_SCORE,   /* last backward sweep: node update + score head (fnode, fscore) */
+    GNNB_K_INPUT_EMBED,        /* input-node embedding, round 0 */
+    GNNB_K_INPUT_UPDATE,       /* input-node backward update, rounds < T-1 */
+    GNNB_K_PROP_FWD,           /* embeddings through A_k (conv / linear) */
+    GNNB_K_PROP_BWD,           /* embeddings through A_k^T (transposed conv / linear / property rank-1) */
+    GNNB_K_OUTPUT,             /* output node */
+    GNNB_K_ARGMAX,             /* masked argmax per subdomain */
+    GNNB_K_COUNT
+};
+
 /* One edge set A_k of the graph = one conv / linear layer of the verified network followed by a ReLU
  * (reference: layers['fixed_layers'], graphnet/graph_conv.py:107-137).  Weight and bias are HOST pointers,
  * copied (and repacked) by gnnb_set_network. */
@@ -88,7 +103,8 @@ int gnnb_set_gnn_weights(gnnb_ctx* ctx, const float* const* tensors, const int64
 int gnnb_set_network(gnnb_ctx* ctx, const gnnb_layer_desc* layers, int n_layers, int c0, int h0, int w0);
 
 /* Options: "math" (gnnb_math_mode), "chunk" (subdomains per wave; 0 = auto), "snapshot" (0/1: keep
- * per-stage copies for gnnb_debug_snapshot; debugging only). */
+ * per-stage copies for gnnb_debug_snapshot; debugging only), "profile" (0/1: time every stage launch with
+ * CUDA events for gnnb_profile_read). */
 int gnnb_set_option(gnnb_ctx* ctx, const char* key, int64_t value);
 int64_t gnnb_get_option(gnnb_ctx* ctx, const char* key);
 
@@ -110,6 +126,12 @@ int gnnb_check(gnnb_ctx* ctx, void* stream, int64_t* nan_count);
 
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
 int64_t gnnb_launch_count(gnnb_ctx* ctx);
+
+/* Device time per kernel class, measured with CUDA events on the launching stream while option "profile" = 1.
+ * Synchronises the device.  ms = summed duration, launches = launch count, rows = summed rows (nodes, or
+ * subdomains for OUTPUT / ARGMAX) since the last gnnb_profile_reset. */
+int gnnb_profile_read(gnnb_ctx* ctx, int klass, double* ms, int64_t* launches, int64_t* rows);
+int gnnb_profile_reset(gnnb_ctx* ctx);
 
 /* Copy the last error message into buf (NUL-terminated, truncated to n). Returns the last status. */
 int gnnb_last_error(gnnb_ctx* ctx, char* buf, int n);
