@@ -24,7 +24,7 @@ struct gnnb_ctx {
     std::string err;
     int64_t launches = 0;
     // options
-    int math = GNNB_MATH_SIMT_FP32;
+    int math = GNNB_MATH_TC_BF16X3;
     int chunk = 0;
     int snapshot = 0;
     // GNN parameters
