@@ -286,7 +286,7 @@ def main():
 
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'bf16x3 (fp32 accumulate)' if math_mode == 'tc' else 'f32', 'data': 'synthetic',
+            'dtype': 'fp16x3 (fp32 accumulate)' if math_mode == 'tc' else 'f32', 'data': 'synthetic',
             'config': {'workload': f'cifar_{args.workload}_kw x {B} synthetic subdomains per GPU per step',
                        'gnn': 'GraphNet(T=2,p=64)', 'weights': args.weights, 'math': math_mode,
                        'chunk': scorer.get_option('workspace_domains'),

@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, 'libgnnb.so')
 GNNB_OK, GNNB_ERR_INVALID, GNNB_ERR_CUDA, GNNB_ERR_STATE, GNNB_ERR_NAN, GNNB_ERR_UNSUPPORTED = range(6)
 LAYER_CONV, LAYER_LINEAR = 0, 1
 MEM_DEVICE, MEM_HOST = 0, 1
-MATH_TC_BF16X3, MATH_SIMT_FP32 = 0, 1
+MATH_TC_FP16X3, MATH_SIMT_FP32 = 0, 1
 KERNEL_CLASSES = ['relax', 'update_fwd', 'update_bwd', 'update_bwd_score', 'input_embed', 'input_update', 'prop_fwd',
                   'prop_bwd', 'output', 'argmax']
 

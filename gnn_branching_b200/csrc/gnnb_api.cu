@@ -8,6 +8,7 @@
 // Only adjacent layers are live at any time, so a chunk's stage working set is ~3 * Bc * n_k * 256 B.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -24,7 +25,7 @@ struct gnnb_ctx {
     std::string err;
     int64_t launches = 0;
     // options
-    int math = GNNB_MATH_TC_BF16X3;
+    int math = GNNB_MATH_TC_FP16X3;
     int chunk = 0;
     int snapshot = 0;
     // GNN parameters
@@ -36,6 +37,7 @@ struct gnnb_ctx {
     bool have_net = false;
     float* d_net = nullptr;
     std::vector<LayerDev> layers;
+    std::vector<PropPlan*> plan_fwd, plan_bwd;   // tensor-core propagation plans per layer
     std::vector<int> n;             // n[0] = input nodes, n[1..L] hidden, n[L+1] = 1
     std::vector<int> hidden_off;    // offset of layer k (1-based) in the flat ReLU index
     int n_hidden = 0;
@@ -195,7 +197,7 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
               cudaStream_t st) {
     const int L = (int)ctx->layers.size();
     const GnnParams& g = ctx->gp;
-    const bool tc = ctx->math == GNNB_MATH_TC_BF16X3;
+    const bool tc = ctx->math == GNNB_MATH_TC_FP16X3;
     int64_t* lc = &ctx->launches;
     auto name = [](const char* fmt, int a, int b) { char buf[64]; snprintf(buf, sizeof buf, fmt, a, b); return std::string(buf); };
 
@@ -226,7 +228,8 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
             const int64_t rows = (int64_t)Bc * ctx->n[k];
             {
                 ProfScope ps(ctx, GNNB_K_PROP_FWD, rows, st);
-                prop_forward(ctx->layers[k - 1], ctx->mu[k - 1], ctx->nb, Bc, st, lc);
+                if (tc) prop_tc_run(ctx->plan_fwd[k - 1], ctx->mu[k - 1], ctx->nb, Bc, st, lc);
+                else prop_forward(ctx->layers[k - 1], ctx->mu[k - 1], ctx->nb, Bc, st, lc);
             }
             TRY(snap(ctx, name("t%d_fwd_nb%d", t, k), ctx->nb, rows * P, st));
             {
@@ -247,6 +250,7 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
             {
                 ProfScope ps(ctx, GNNB_K_PROP_BWD, rows, st);
                 if (k == L) prop_property_backward(in.wp, ctx->mu[L + 1], ctx->nb, ctx->n[L], Bc, st, lc);
+                else if (tc) prop_tc_run(ctx->plan_bwd[k], ctx->mu[k + 1], ctx->nb, Bc, st, lc);
                 else prop_backward(ctx->layers[k], ctx->mu[k + 1], ctx->nb, Bc, true, st, lc);
             }
             TRY(snap(ctx, name("t%d_bwd_nb%d", t, k), ctx->nb, rows * P, st));
@@ -262,7 +266,8 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
         if (!last) {
             {
                 ProfScope ps(ctx, GNNB_K_PROP_BWD, rows0, st);
-                prop_backward(ctx->layers[0], ctx->mu[1], ctx->nb, Bc, false, st, lc);
+                if (tc) prop_tc_run(ctx->plan_bwd[0], ctx->mu[1], ctx->nb, Bc, st, lc);
+                else prop_backward(ctx->layers[0], ctx->mu[1], ctx->nb, Bc, false, st, lc);
             }
             {
                 ProfScope ps(ctx, GNNB_K_INPUT_UPDATE, rows0, st);
@@ -303,7 +308,7 @@ int gnnb_create(gnnb_ctx** out, int device) {
     }
     if (cudaMalloc(&ctx->d_nan, sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(ctx->d_nan, 0, sizeof(unsigned long long)) != cudaSuccess ||
-        simt_init() != 0 || prop_init(64 * 1024) != 0 || tc_init() != 0) {
+        simt_init() != 0 || prop_init(64 * 1024) != 0 || tc_init() != 0 || prop_tc_init() != 0) {
         fprintf(stderr, "libgnnb: initialisation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
         delete ctx;
         return GNNB_ERR_CUDA;
@@ -320,6 +325,8 @@ void gnnb_destroy(gnnb_ctx* ctx) {
     if (ctx->d_tc) cudaFree(ctx->d_tc);
     if (ctx->d_net) cudaFree(ctx->d_net);
     if (ctx->d_nan) cudaFree(ctx->d_nan);
+    for (PropPlan* p : ctx->plan_fwd) prop_plan_free(p);
+    for (PropPlan* p : ctx->plan_bwd) prop_plan_free(p);
     for (auto& p : ctx->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     delete ctx;
@@ -435,6 +442,16 @@ int gnnb_set_network(gnnb_ctx* ctx, const gnnb_layer_desc* layers, int n_layers,
     CU(cudaMalloc(&ctx->d_net, total * sizeof(float)));
     CU(cudaMemcpy(ctx->d_net, blob.data(), total * sizeof(float), cudaMemcpyHostToDevice));
     for (int k = 0; k < n_layers; ++k) { devs[k].weight = ctx->d_net + o_w[k]; devs[k].bias_node = ctx->d_net + o_b[k]; }
+    for (PropPlan* p : ctx->plan_fwd) prop_plan_free(p);
+    for (PropPlan* p : ctx->plan_bwd) prop_plan_free(p);
+    ctx->plan_fwd.assign(n_layers, nullptr);
+    ctx->plan_bwd.assign(n_layers, nullptr);
+    for (int k = 0; k < n_layers; ++k) {
+        // layer 0's transpose feeds the input nodes and is not normalised (graph_conv.py:361-372); the others are (:299-318)
+        ctx->plan_fwd[k] = prop_plan_build(devs[k], layers[k].weight, false, false);
+        ctx->plan_bwd[k] = prop_plan_build(devs[k], layers[k].weight, true, k > 0);
+        if (!ctx->plan_fwd[k] || !ctx->plan_bwd[k]) return fail(ctx, GNNB_ERR_CUDA, "building the propagation plans failed");
+    }
     ctx->layers = devs;
     ctx->n = n;
     ctx->hidden_off.assign(n_layers + 2, 0);
@@ -449,8 +466,8 @@ int gnnb_set_option(gnnb_ctx* ctx, const char* key, int64_t value) {
     if (!ctx || !key) return fail(ctx, GNNB_ERR_INVALID, "null argument");
     const std::string k(key);
     if (k == "math") {
-        if (value != GNNB_MATH_TC_BF16X3 && value != GNNB_MATH_SIMT_FP32) return fail(ctx, GNNB_ERR_INVALID, "unknown math mode");
-        if (value == GNNB_MATH_TC_BF16X3 && !tc_available()) return fail(ctx, GNNB_ERR_UNSUPPORTED, "tensor-core path not built");
+        if (value != GNNB_MATH_TC_FP16X3 && value != GNNB_MATH_SIMT_FP32) return fail(ctx, GNNB_ERR_INVALID, "unknown math mode");
+        if (value == GNNB_MATH_TC_FP16X3 && !tc_available()) return fail(ctx, GNNB_ERR_UNSUPPORTED, "tensor-core path not built");
         ctx->math = (int)value;
     } else if (k == "chunk") {
         if (value < 0) return fail(ctx, GNNB_ERR_INVALID, "chunk must be >= 0");
@@ -474,6 +491,12 @@ int64_t gnnb_get_option(gnnb_ctx* ctx, const char* key) {
     if (k == "profile") return ctx->profile;
     if (k == "n_hidden") return ctx->n_hidden;
     if (k == "workspace_domains") return ctx->ws_cap;
+    if (k.rfind("plan_density_pct_", 0) == 0) {      // e.g. plan_density_pct_f0 / plan_density_pct_b1
+        const bool bwd = k[17] == 'b';
+        const size_t i = (size_t)atoi(k.c_str() + 18);
+        const auto& v = bwd ? ctx->plan_bwd : ctx->plan_fwd;
+        return i < v.size() ? (int64_t)(100.0 * prop_plan_density(v[i])) : -1;
+    }
     return -1;
 }
 

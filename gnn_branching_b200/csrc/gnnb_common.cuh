@@ -27,7 +27,7 @@ __host__ __device__ constexpr int lin_out(int l) { return l == FSCORE ? 1 : P; }
 // GNN parameters on the device.
 //   wt[l]   fp32 [K][64]   transposed weight (wt[k][n] = W[n][k]), SIMT kernels and first layers
 //   bias[l] fp32 [64]
-//   tc[l]   bf16 hi/lo planes in the UMMA shared-memory layout, one 16 KB block per 64 input features
+//   tc[l]   fp16 hi/lo planes in the UMMA shared-memory layout, one 16 KB block per 64 input features
 //           (see gnnb_tc.cu for the layout); only for K >= 64 linears
 struct GnnParams {
     const float* wt[N_LIN];
@@ -94,6 +94,14 @@ void output_node(const GnnParams& g, const float* wp, const float* bp, const flo
                  const float* ub_out, const float* prim_out, float* mu_out, int nL, int Bc, cudaStream_t st, int64_t* launches);
 void masked_argmax(const float* scores, const float* mask, int n_hidden, int Bc, float* best_score, int32_t* best_idx,
                    cudaStream_t st, int64_t* launches);
+
+// tensor-core propagation (gnnb_prop_tc.cu): block plans built once per network, gather-GEMM kernel
+struct PropPlan;
+int prop_tc_init();
+PropPlan* prop_plan_build(const LayerDev& L, const float* host_weight, bool backward, bool normalise);
+void prop_plan_free(PropPlan* p);
+double prop_plan_density(const PropPlan* p);
+void prop_tc_run(const PropPlan* plan, const float* mu_in, float* nb_out, int Bc, cudaStream_t st, int64_t* launches);
 
 // ---- device helpers ---------------------------------------------------------------------------
 // compute_ratio of graph_conv.py:499-514 in the reference's operation order (IEEE division, no fast-math)

@@ -1,12 +1,13 @@
-// Per-node MLP kernels on the 5th-generation tensor cores (GNNB_MATH_TC_BF16X3) — the product path.
+// Per-node MLP kernels on the 5th-generation tensor cores (GNNB_MATH_TC_FP16X3) — the product path.
 //
 // Every dense layer of the GNN with K >= 64 is a [128 nodes x K] x [K x N] GEMM per tile, issued as
 // tcgen05.mma (cta_group::1, kind::f16, M = 128, N = 64 / 128 / 192, K = 16 per instruction) with fp32
-// accumulators in tensor memory.  fp32 accuracy (scores within 1e-4, BASELINE.json) comes from a bf16 hi/lo
-// split of BOTH operands and three MMAs per K step:  x*w ~= xh*wh + xl*wh + xh*wl  (error ~2^-17 per product).
+// accumulators in tensor memory.  fp32 accuracy (scores within 1e-4, BASELINE.json) comes from an fp16 hi/lo
+// split of BOTH operands and three MMAs per K step:  x*w ~= xh*wh + xl*wh + xh*wl  (error ~2^-22 per product;
+// see gnnb_umma.cuh for the scaled operand domain that keeps fp16 in range).
 //
 // Structure of a CTA (256 threads = 2 warpgroups, 1 CTA per SM, persistent over tiles):
-//   * the stage's weights sit in shared memory for the CTA's lifetime as bf16 hi/lo planes in the UMMA K-major
+//   * the stage's weights sit in shared memory for the CTA's lifetime as fp16 hi/lo planes in the UMMA K-major
 //     SWIZZLE_128B layout; they are repacked once on the host (tc_pack_weight) so one cp.async.bulk per linear
 //     (TMA, 1-D) lands them;
 //   * each warpgroup owns one 128-node tile at a time, its own 32 KB A-operand buffer (hi + lo plane), 256 TMEM
@@ -21,139 +22,12 @@
 //     [s1, -d2 s1, d1 s1] input one N = 192 MMA.
 //
 // Stage contracts are those of the SIMT twins in gnnb_simt.cu (same inputs, outputs, reference citations).
-#include <cuda_bf16.h>
-#include <string.h>
-
-#include "gnnb_common.cuh"
+#include "gnnb_umma.cuh"
 
 namespace gnnb {
 namespace {
 
-constexpr int TILE = 128;                        // nodes per tile = UMMA M
-constexpr int WGS = 2;                           // warpgroups (tiles in flight) per CTA
-constexpr int NTHREADS = 128 * WGS;
-constexpr uint32_t WPLANE = 64 * 64 * 2;         // one 64(n) x 64(k) bf16 weight plane: 8 KB
-constexpr uint32_t APLANE = TILE * 64 * 2;       // one A plane: 16 KB
-constexpr uint32_t ABUF = 2 * APLANE;            // hi + lo
-
-// byte offset of 16-byte chunk `chunk` (8 bf16 along K) of row `row` inside a K-major SWIZZLE_128B tile whose rows
-// are 128 bytes (64 bf16): 8-row groups are 1024 bytes apart (SBO), chunks are XOR-swizzled with the row
-__host__ __device__ inline uint32_t swz(uint32_t row, uint32_t chunk) {
-    return (row >> 3) * 1024u + (row & 7u) * 128u + ((chunk ^ (row & 7u)) << 4);
-}
-
-// ---- host-side weight packing ------------------------------------------------------------------
-uint16_t f2bf(float f) {       // round to nearest even
-    uint32_t u;
-    memcpy(&u, &f, 4);
-    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40u);
-    u += 0x7fffu + ((u >> 16) & 1u);
-    return (uint16_t)(u >> 16);
-}
-float bf2f(uint16_t h) {
-    uint32_t u = (uint32_t)h << 16;
-    float f;
-    memcpy(&f, &u, 4);
-    return f;
-}
-
-// ---- PTX wrappers ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t a, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(a), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(mbar) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void named_bar(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t slot, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 x bf16 -> fp32
-__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t mbar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
-}
-// 16 consecutive fp32 columns of this thread's TMEM lane (lane = accumulator row).  The load is asynchronous:
-// tmem_wait16 must run on the same array before its values are read (the "+r" operands pin that order for the compiler)
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_wait16(uint32_t (&r)[16], float (&v)[16]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-                 :: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_ld16_sync(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    tmem_ld16(taddr, r);
-    tmem_wait16(r, v);
-}
-
-// UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);          // start address, bits [0,14)
-    d |= (uint64_t)1 << 16;                                 // leading byte offset (unused for swizzled K-major), [16,30)
-    d |= (uint64_t)(1024u >> 4) << 32;                      // stride byte offset, bits [32,46)
-    d |= (uint64_t)1 << 46;                                 // descriptor version (Blackwell), bits [46,48)
-    d |= (uint64_t)2 << 61;                                 // layout type SWIZZLE_128B, bits [61,64)
-    return d;
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B bf16, both K-major, M = 128
-__device__ __forceinline__ uint32_t make_idesc(uint32_t N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
-}
-
-__device__ __forceinline__ float relu_nan(float x) { return (x != x) ? x : fmaxf(x, 0.f); }   // F.relu keeps NaN
-
-// (a, b) -> packed bf16x2 hi and lo words; element a sits at the lower address
-__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    const __nv_bfloat162 l = __floats2bfloat162_rn(a - __low2float(h), b - __high2float(h));
-    hi = *reinterpret_cast<const uint32_t*>(&h);
-    lo = *reinterpret_cast<const uint32_t*>(&l);
-}
+using namespace tcx;
 
 // ---- warpgroup context ------------------------------------------------------------------------------
 struct WG {
@@ -181,7 +55,7 @@ __device__ __forceinline__ void gemm_start(const WG& c, uint32_t b_hi, uint32_t 
             const uint64_t ad = make_desc(pass == 1 ? c.a_lo : c.a_hi);
             const uint64_t bd = make_desc(pass == 2 ? b_lo : b_hi);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)      // 16 bf16 = 32 bytes along K per instruction
+            for (int k = 0; k < 4; ++k)      // 16 fp16 = 32 bytes along K per instruction
                 umma(d, ad + 2 * k, bd + 2 * k, idesc, (accumulate || pass > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(c.mbar);
@@ -225,8 +99,8 @@ __device__ __forceinline__ void tile_to_a(const WG& c, const TileRegs& r) {
     for (int i = 0; i < 16; ++i) {
         const int rr = warp * 32 + 2 * i + (lane >> 4);
         uint32_t h0, h1, l0, l1;
-        split2(r.v[i].x, r.v[i].y, h0, l0);
-        split2(r.v[i].z, r.v[i].w, h1, l1);
+        split2(r.v[i].x * ASCALE, r.v[i].y * ASCALE, h0, l0);
+        split2(r.v[i].z * ASCALE, r.v[i].w * ASCALE, h1, l1);
         const uint32_t off = swz((uint32_t)rr, (uint32_t)(c4 >> 1)) + (uint32_t)(c4 & 1) * 8u;
         asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(c.a_hi + off), "r"(h0), "r"(h1) : "memory");
         asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(c.a_lo + off), "r"(l0), "r"(l1) : "memory");
@@ -279,6 +153,7 @@ __device__ __forceinline__ void first_layer_to_a(const WG& c, const float (&feat
 __device__ __forceinline__ bool epilogue_to_global(const WG& c, uint32_t dcol, const float* __restrict__ bias_s, float rowscale,
                                                    float* __restrict__ dst, int64_t row0, int64_t rows) {
     bool bad = false;
+    rowscale *= AINV;                                  // leave the scaled operand domain
     const uint32_t rbase = c.a_hi + (uint32_t)c.t * 256u;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -373,8 +248,8 @@ __device__ __forceinline__ void cta_teardown(const CtaSetup& s) {
     __syncthreads();
     if (threadIdx.x < 32) tmem_dealloc(s.tmem_base, 512);
 }
-__device__ __forceinline__ void copy_vec(float* dst, const float* __restrict__ src, int n) {
-    for (int i = threadIdx.x; i < n; i += NTHREADS) dst[i] = src[i];
+__device__ __forceinline__ void copy_vec(float* dst, const float* __restrict__ src, int n, float scale = ASCALE) {
+    for (int i = threadIdx.x; i < n; i += NTHREADS) dst[i] = src[i] * scale;     // biases live in the scaled domain
 }
 
 // TMEM column map inside a warpgroup's 256 columns
@@ -397,7 +272,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_update(GnnParams g, int back
     CtaSetup s = cta_setup<5>(UPD_WBYTES, wsrc, woff, wlen);
     Tail& tl = *s.tail;
     copy_vec(tl.bias[0], g.bias[l3], P); copy_vec(tl.bias[1], g.bias[l3b], P); copy_vec(tl.bias[2], g.bias[l4], P);
-    copy_vec(tl.bias[3], g.bias[l4b], P); copy_vec(tl.bias[4], g.bias[FNODE], P); copy_vec(tl.vec, g.wt[FSCORE], P);
+    copy_vec(tl.bias[3], g.bias[l4b], P); copy_vec(tl.bias[4], g.bias[FNODE], P); copy_vec(tl.vec, g.wt[FSCORE], P, 1.0f);
     const float bscore = g.bias[FSCORE][0];
     __syncthreads();
     mbar_wait(smem_u32(&tl.mbar[0]), 0);                      // weight planes have landed
@@ -472,7 +347,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_update(GnnParams g, int back
 #pragma unroll
                 for (int j = 0; j < 16; ++j) sc = fmaf(relu_nan(v[j] + tl.bias[4][qd * 16 + j]), tl.vec[qd * 16 + j], sc);
             }
-            if (grow < rows) scores[(grow / n) * score_stride + score_off + (grow % n)] = sc + bscore;
+            if (grow < rows) scores[(grow / n) * score_stride + score_off + (grow % n)] = fmaf(sc, AINV, bscore);
             tc_fence_before();
             wg_barrier(c);            // all reads of D2 are done before the next tile's first MMA overwrites it
         }
@@ -643,7 +518,7 @@ int tc_init() {
 }
 
 // packed layout of one nn.Linear weight W[64][K], K = 64 * nblk:  [hi plane of K-block 0 .. nblk-1][lo plane 0 .. nblk-1],
-// each plane 64 (n) x 64 (k) bf16 in the K-major SWIZZLE_128B shared-memory image (8 KB), so that the planes of
+// each plane 64 (n) x 64 (k) fp16 in the K-major SWIZZLE_128B shared-memory image (8 KB), so that the planes of
 // consecutive K-blocks also read as one (64 * nblk)-row B tile
 int64_t tc_packed_elems(int K) { return (int64_t)2 * (K / 64) * 64 * 64; }
 
@@ -651,10 +526,8 @@ int64_t tc_pack_weight(const float* w, int K, uint16_t* dst) {
     const int nblk = K / 64;
     for (int n = 0; n < 64; ++n)
         for (int k = 0; k < K; ++k) {
-            const float x = w[(size_t)n * K + k];
-            const uint16_t hi = f2bf(x);
-            const float rem = x - bf2f(hi);
-            const uint16_t lo = (rem == rem && rem - rem == 0.f) ? f2bf(rem) : 0;
+            uint16_t hi, lo;
+            split_host(w[(size_t)n * K + k], hi, lo);
             const int kb = k / 64, kk = k % 64;
             const size_t e = (size_t)(swz((uint32_t)n, (uint32_t)(kk / 8)) + (kk % 8) * 2) / 2;
             dst[(size_t)kb * 4096 + e] = hi;

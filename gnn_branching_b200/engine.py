@@ -19,7 +19,7 @@ SCORE_LINEARS = ['fnode', 'fscore']
 STATE_DICT_KEYS = ([f'EmbedUpdates.update.{n}.{s}' for n in UPDATE_LINEARS for s in ('weight', 'bias')]
                    + [f'ComputeFinalScore.{n}.{s}' for n in SCORE_LINEARS for s in ('weight', 'bias')])
 
-_MATH = {'tc': _lib.MATH_TC_BF16X3, 'simt': _lib.MATH_SIMT_FP32}
+_MATH = {'tc': _lib.MATH_TC_FP16X3, 'simt': _lib.MATH_SIMT_FP32}
 
 
 class Scorer:

@@ -37,7 +37,7 @@ enum gnnb_mem_kind { GNNB_MEM_DEVICE = 0, GNNB_MEM_HOST = 1 };
 /* Arithmetic of the per-node MLP GEMMs.  Both are sm_100a CUDA; TC is the product path, SIMT the
  * exact-fp32 validation path used by the tests to localise tensor-path errors. */
 enum gnnb_math_mode {
-    GNNB_MATH_TC_BF16X3 = 0,   /* tcgen05.mma kind::f16, bf16 hi/lo split, 3 MMAs, fp32 accumulate in TMEM */
+    GNNB_MATH_TC_FP16X3 = 0,   /* tcgen05.mma kind::f16, fp16 hi/lo split, 3 MMAs, fp32 accumulate in TMEM */
     GNNB_MATH_SIMT_FP32 = 1    /* fp32 FMA on CUDA cores */
 };
 
