@@ -188,7 +188,7 @@ def main():
         return best, idx
 
     def scorer_score(fr):
-        scorer.set_network(fr.net, key='bench')
+        scorer.set_network(fr.net, key=fr.net.key)
         return scorer.score(fr, return_scores=False, check=False)
 
     def barrier():

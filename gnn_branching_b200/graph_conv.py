@@ -90,9 +90,7 @@ class GraphNet(nn.Module):
     def score_frontier(self, fr: Frontier, return_scores: bool = True):
         """Batched entry (addition to the reference API): (best_score [B], best_idx [B], scores [B, sum n_k])."""
         sc = self.scorer(fr.device.index if fr.device.type == 'cuda' else None)
-        key = tuple((a.kind, a.weight.data_ptr(), a.weight._version, a.bias.data_ptr(), a.stride, a.padding,
-                     tuple(a.in_shape)) for a in fr.net.affine)
-        sc.set_network(fr.net, key=key)
+        sc.set_network(fr.net, key=fr.net.key)
         return sc.score(fr, return_scores=return_scores)
 
     def forward(self, lower_bounds_all, upper_bounds_all, dual_vars, primals, primal_inputs, layers, masks) -> List[torch.Tensor]:

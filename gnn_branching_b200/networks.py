@@ -10,6 +10,7 @@ deep ``cifar_model_deep``).
 """
 from __future__ import annotations
 
+import itertools
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
 
@@ -22,6 +23,9 @@ class Flatten(nn.Module):
 
     def forward(self, x):
         return x.view(x.size(0), -1)
+
+
+_NET_IDS = itertools.count()
 
 
 @dataclass
@@ -68,6 +72,11 @@ class NetSpec:
     input_shape: Tuple[int, int, int]
     affine: List[AffineSpec] = field(default_factory=list)
     n_layers_total: int = 0        # number of modules in fixed_layers
+    key: object = None             # identity of the network's weights; survives .to(); lets the engine skip re-uploads
+
+    def __post_init__(self):
+        if self.key is None:
+            self.key = ('netspec', next(_NET_IDS))
 
     @property
     def L(self) -> int:
@@ -110,7 +119,7 @@ class NetSpec:
         return sizes
 
     def to(self, device) -> 'NetSpec':
-        out = NetSpec(self.name, self.input_shape, [], self.n_layers_total)
+        out = NetSpec(self.name, self.input_shape, [], self.n_layers_total, key=self.key)
         for a in self.affine:
             out.affine.append(AffineSpec(a.kind, a.weight.to(device), a.bias.to(device), a.in_shape,
                                          a.out_shape, a.stride, a.padding, a.layer_index))
@@ -206,6 +215,9 @@ def netspec_from_modules(fixed_layers: Sequence[nn.Module], input_shape: Tuple[i
             raise NotImplementedError(f'unsupported layer type {type(m).__name__}')
     if pending is not None:
         raise NotImplementedError('fixed_layers must end with a ReLU (the property layer is separate)')
+    # the same module list scored again (every BaB step) maps to the same key, edited weights to a new one
+    spec.key = ('modules',) + tuple((a.kind, a.weight.data_ptr(), a.weight._version, a.bias.data_ptr(), a.bias._version,
+                                     a.stride, a.padding, tuple(a.in_shape)) for a in spec.affine)
     return spec
 
 
