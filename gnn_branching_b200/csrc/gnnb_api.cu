@@ -99,9 +99,11 @@ int ensure_workspace(gnnb_ctx* ctx, int Bc, bool host_staging) {
     size_t total = 0;
     auto take = [&](size_t elems) { size_t off = total; total += align4(elems) + 64; return off; };
     std::vector<size_t> o_mu(L + 2), o_rf(L + 1), o_rb(L + 1), o_lb(L + 2), o_ub(L + 2), o_du(L), o_pr(L), o_po(L);
+    // nb and relax' are stored per tile of 128 rows by the tensor-core kernels: round the row counts up
+    auto tiled = [](size_t rows) { return ((rows + 127) / 128) * 128; };
     for (int k = 0; k <= L + 1; ++k) o_mu[k] = take((size_t)Bc * ctx->n[k] * P);
-    for (int k = 1; k <= L; ++k) { o_rf[k] = take((size_t)Bc * ctx->n[k] * P); o_rb[k] = take((size_t)Bc * ctx->n[k] * P); }
-    const size_t o_nb = take((size_t)Bc * nmax * P);
+    for (int k = 1; k <= L; ++k) { o_rf[k] = take(tiled((size_t)Bc * ctx->n[k]) * P); o_rb[k] = take(tiled((size_t)Bc * ctx->n[k]) * P); }
+    const size_t o_nb = take(tiled((size_t)Bc * nmax) * P);
     const size_t o_sc = take((size_t)Bc * ctx->n_hidden);
     const size_t o_best = take(Bc), o_idx = take(Bc);
     size_t o_pout = 0, o_pin = 0, o_wp = 0, o_bp = 0, o_mask = 0;
@@ -134,6 +136,8 @@ int ensure_workspace(gnnb_ctx* ctx, int Bc, bool host_staging) {
     ctx->ws_host_staging = host_staging;
     return GNNB_OK;
 }
+
+#define TRY_(expr) do { int s__ = (expr); if (s__ != GNNB_OK) return s__; } while (0)
 
 int snap(gnnb_ctx* ctx, const std::string& name, const float* src, int64_t numel, cudaStream_t st) {
     if (!ctx->snapshot) return GNNB_OK;
@@ -185,6 +189,15 @@ int prof_collect(gnnb_ctx* ctx) {
     return GNNB_OK;
 }
 
+// nb is an fp16 tile image in tensor-core mode: unpack it into the snapshot
+int snap_nb(gnnb_ctx* ctx, const std::string& name, const float* nb, int64_t rows, cudaStream_t st) {
+    if (!ctx->snapshot) return GNNB_OK;
+    if (ctx->math != GNNB_MATH_TC_FP16X3) return snap(ctx, name, nb, rows * P, st);
+    TRY_(snap(ctx, name, nb, rows * P, st));          // allocates / sizes the snapshot buffer
+    tc_unpack_tile_image(nb, ctx->snaps[name].first, rows, st);
+    return GNNB_OK;
+}
+
 struct ChunkPtrs {
     std::vector<const float*> lb, ub, dual, pre, post;
     const float *pout, *pin, *wp, *bp, *mask;
@@ -210,8 +223,9 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
             if (tc) tc_relax(g, ni, ctx->relax_f[k], ctx->relax_b[k], st, lc);
             else simt_relax(g, ni, ctx->relax_f[k], ctx->relax_b[k], st, lc);
         }
-        TRY(snap(ctx, name("relax_f%d", k, 0), ctx->relax_f[k], ni.rows * P, st));
-        TRY(snap(ctx, name("relax_b%d", k, 0), ctx->relax_b[k], ni.rows * P, st));
+        // tensor-core mode stores relax' (pre-multiplied by fc4 / bc4's relax half, tile-transposed): not comparable 1:1
+        TRY(snap(ctx, name(tc ? "relaxp_f%d" : "relax_f%d", k, 0), ctx->relax_f[k], ni.rows * P, st));
+        TRY(snap(ctx, name(tc ? "relaxp_b%d" : "relax_b%d", k, 0), ctx->relax_b[k], ni.rows * P, st));
     }
     const int64_t rows0 = (int64_t)Bc * ctx->n[0];
     {
@@ -231,7 +245,7 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
                 if (tc) prop_tc_run(ctx->plan_fwd[k - 1], ctx->mu[k - 1], ctx->nb, Bc, st, lc);
                 else prop_forward(ctx->layers[k - 1], ctx->mu[k - 1], ctx->nb, Bc, st, lc);
             }
-            TRY(snap(ctx, name("t%d_fwd_nb%d", t, k), ctx->nb, rows * P, st));
+            TRY(snap_nb(ctx, name("t%d_fwd_nb%d", t, k), ctx->nb, rows, st));
             {
                 ProfScope ps(ctx, GNNB_K_UPDATE_FWD, rows, st);
                 if (tc) tc_update(g, false, in.lb[k], in.ub[k], ctx->nb, ctx->relax_f[k], ctx->mu[k], nullptr, ctx->n[k], 0, 0, rows, ctx->d_nan, st, lc);
@@ -249,11 +263,12 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
             const int64_t rows = (int64_t)Bc * ctx->n[k];
             {
                 ProfScope ps(ctx, GNNB_K_PROP_BWD, rows, st);
-                if (k == L) prop_property_backward(in.wp, ctx->mu[L + 1], ctx->nb, ctx->n[L], Bc, st, lc);
+                if (k == L && tc) prop_tc_property_backward(in.wp, ctx->mu[L + 1], ctx->nb, ctx->n[L], Bc, st, lc);
+                else if (k == L) prop_property_backward(in.wp, ctx->mu[L + 1], ctx->nb, ctx->n[L], Bc, st, lc);
                 else if (tc) prop_tc_run(ctx->plan_bwd[k], ctx->mu[k + 1], ctx->nb, Bc, st, lc);
                 else prop_backward(ctx->layers[k], ctx->mu[k + 1], ctx->nb, Bc, true, st, lc);
             }
-            TRY(snap(ctx, name("t%d_bwd_nb%d", t, k), ctx->nb, rows * P, st));
+            TRY(snap_nb(ctx, name("t%d_bwd_nb%d", t, k), ctx->nb, rows, st));
             float* sc = last ? scores : nullptr;
             {
                 ProfScope ps(ctx, last ? GNNB_K_UPDATE_BWD_SCORE : GNNB_K_UPDATE_BWD, rows, st);
@@ -357,14 +372,48 @@ int gnnb_set_gnn_weights(gnnb_ctx* ctx, const float* const* tensors, const int64
             for (int k = 0; k < K; ++k) blob[o_w[l] + (size_t)k * N + nn] = W[(size_t)nn * K + k];
         memcpy(&blob[o_b[l]], tensors[2 * l + 1], sizeof(float) * N);
     }
+    // composed linears of the tensor-core path (gnnb_tc.cu header), formed in double
+    std::vector<float> cw((size_t)N_TCLIN * P * P, 0.f), cb((size_t)N_TCLIN * P, 0.f);
+    auto compose = [&](int id, int outer, int half, int inner, bool add_outer_bias) {
+        // W = outer[:, half*64 : half*64+64] * inner (or the slice itself when inner < 0);  b = [b_outer +] slice * b_inner
+        const float* Wo = tensors[2 * outer];
+        const float* bo = tensors[2 * outer + 1];
+        const int Ko = lin_in(outer);
+        for (int nn = 0; nn < P; ++nn) {
+            double bacc = add_outer_bias ? (double)bo[nn] : 0.0;
+            for (int k = 0; k < P; ++k) {
+                double acc = 0.0;
+                if (inner < 0) acc = Wo[(size_t)nn * Ko + half * P + k];
+                else
+                    for (int j = 0; j < P; ++j) acc += (double)Wo[(size_t)nn * Ko + half * P + j] * (double)tensors[2 * inner][(size_t)j * P + k];
+                cw[((size_t)id * P + nn) * P + k] = (float)acc;
+            }
+            if (inner >= 0)
+                for (int j = 0; j < P; ++j) bacc += (double)Wo[(size_t)nn * Ko + half * P + j] * (double)tensors[2 * inner + 1][j];
+            cb[(size_t)id * P + nn] = (float)bacc;
+        }
+    };
+    compose(T_FWD_R, FC4, 0, FC1_1, false);
+    compose(T_FWD_C, FC4, 1, FC3_2, true);
+    compose(T_BWD_R, BC4, 0, BC2_1, false);
+    compose(T_BWD_C, BC4, 1, BC3_1, true);
+    compose(T_INP_C, INP_B2, 0, INP_B_1, true);
+    compose(T_INP_NB, INP_B2, 1, -1, false);
     // tensor-core planes for the K >= 64 linears
     std::vector<size_t> o_tc(N_LIN, 0);
     size_t tc_total = 0;
     for (int l = 0; l < N_LIN; ++l)
         if (lin_in(l) >= P && lin_out(l) == P) { o_tc[l] = tc_total; tc_total += (size_t)tc_packed_elems(lin_in(l)); }
+    std::vector<size_t> o_tcx(N_TCLIN, 0);
+    for (int i = 0; i < N_TCLIN; ++i) { o_tcx[i] = tc_total; tc_total += (size_t)tc_packed_elems(P); }
     std::vector<uint16_t> tcblob(tc_total ? tc_total : 1, 0);
     for (int l = 0; l < N_LIN; ++l)
         if (lin_in(l) >= P && lin_out(l) == P) tc_pack_weight(tensors[2 * l], lin_in(l), &tcblob[o_tc[l]]);
+    for (int i = 0; i < N_TCLIN; ++i) tc_pack_weight(&cw[(size_t)i * P * P], P, &tcblob[o_tcx[i]]);
+    const size_t o_cb = total;            // composed biases ride at the end of the fp32 blob
+    total += cb.size();
+    blob.resize(total, 0.f);
+    memcpy(&blob[o_cb], cb.data(), cb.size() * sizeof(float));
     if (ctx->d_gnn) cudaFree(ctx->d_gnn);
     if (ctx->d_tc) cudaFree(ctx->d_tc);
     ctx->d_gnn = nullptr; ctx->d_tc = nullptr;
@@ -376,6 +425,10 @@ int gnnb_set_gnn_weights(gnnb_ctx* ctx, const float* const* tensors, const int64
         ctx->gp.wt[l] = ctx->d_gnn + o_w[l];
         ctx->gp.bias[l] = ctx->d_gnn + o_b[l];
         ctx->gp.tc[l] = (lin_in(l) >= P && lin_out(l) == P) ? ctx->d_tc + o_tc[l] : nullptr;
+    }
+    for (int i = 0; i < N_TCLIN; ++i) {
+        ctx->gp.tcx_w[i] = ctx->d_tc + o_tcx[i];
+        ctx->gp.tcx_b[i] = ctx->d_gnn + o_cb + (size_t)i * P;
     }
     ctx->gp.T = T;
     ctx->have_gnn = true;

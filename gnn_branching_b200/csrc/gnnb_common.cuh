@@ -24,6 +24,18 @@ __host__ __device__ constexpr int lin_in(int l) {
 }
 __host__ __device__ constexpr int lin_out(int l) { return l == FSCORE ? 1 : P; }
 
+// Composed linears used only by the tensor-core kernels (see gnnb_tc.cu header): products of two reference linears
+// with nothing but a bias between them, formed once on the host in double precision.
+enum TcLin : int {
+    T_FWD_R = 0,   // fc4[:, :64] o fc1_1      bias = fc4[:, :64] b_fc1_1
+    T_FWD_C,       // fc4[:, 64:] o fc3_2      bias = b_fc4 + fc4[:, 64:] b_fc3_2
+    T_BWD_R,       // bc4[:, :64] o bc2_1
+    T_BWD_C,       // bc4[:, 64:] o bc3_1      bias = b_bc4 + bc4[:, 64:] b_bc3_1
+    T_INP_C,       // inp_b2[:, :64] o inp_b_1 bias = b_inp_b2 + inp_b2[:, :64] b_inp_b_1
+    T_INP_NB,      // inp_b2[:, 64:]           (no bias)
+    N_TCLIN
+};
+
 // GNN parameters on the device.
 //   wt[l]   fp32 [K][64]   transposed weight (wt[k][n] = W[n][k]), SIMT kernels and first layers
 //   bias[l] fp32 [64]
@@ -33,6 +45,8 @@ struct GnnParams {
     const float* wt[N_LIN];
     const float* bias[N_LIN];
     const uint16_t* tc[N_LIN];
+    const uint16_t* tcx_w[N_TCLIN];   // composed 64x64 linears, same plane layout as tc[]
+    const float* tcx_b[N_TCLIN];      // their biases, fp32 [64]
     int T;
 };
 
@@ -84,6 +98,7 @@ int64_t tc_pack_weight(const float* w_host, int K, uint16_t* dst_host);
 int64_t tc_packed_elems(int K);
 int tc_init();   // opt-in shared memory sizes; returns cudaError_t
 bool tc_available();
+void tc_unpack_tile_image(const float* img, float* out, int64_t rows, cudaStream_t st);   // debugging snapshots
 
 // propagation through the verified network and the small kernels (gnnb_prop.cu)
 int prop_init(int max_smem_bytes);
@@ -101,7 +116,8 @@ int prop_tc_init();
 PropPlan* prop_plan_build(const LayerDev& L, const float* host_weight, bool backward, bool normalise);
 void prop_plan_free(PropPlan* p);
 double prop_plan_density(const PropPlan* p);
-void prop_tc_run(const PropPlan* plan, const float* mu_in, float* nb_out, int Bc, cudaStream_t st, int64_t* launches);
+void prop_tc_run(const PropPlan* plan, const float* mu_in, float* nb_img, int Bc, cudaStream_t st, int64_t* launches);
+void prop_tc_property_backward(const float* wp, const float* mu_out, float* nb_img, int nL, int Bc, cudaStream_t st, int64_t* launches);
 
 // ---- device helpers ---------------------------------------------------------------------------
 // compute_ratio of graph_conv.py:499-514 in the reference's operation order (IEEE division, no fast-math)

@@ -12,7 +12,8 @@
 //   * gathers the 64 input-node rows of both subdomains (256 B each, coalesced), splits them into fp16 hi/lo and
 //     writes them as the MN-major B operand  [k][(subdomain, channel)]  (N = 128),
 //   * issues 3 x ksteps tcgen05.mma (M = 128, N = 128, K = 16) into 128 TMEM columns,
-// then scatters the accumulator rows (one output node per TMEM lane) as full 256-byte rows to nb.
+// then scatters the accumulator rows (one output node per TMEM lane) into nb, already split into the fp16 hi/lo
+// A-operand tile image the node-update kernels load with one cp.async.bulk.
 #include <algorithm>
 #include <functional>
 #include <map>
@@ -64,7 +65,7 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lb
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1) k_tc_prop(PropPlanDev plan, const float* __restrict__ mu_in,
-                                                         float* __restrict__ nb_out, int Bc) {
+                                                         uint16_t* __restrict__ nb_img, int Bc) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     PropTail* tail = reinterpret_cast<PropTail*>(base + WGS * PROP_WG_BYTES);
@@ -143,36 +144,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_prop(PropPlanDev plan, const
             ph_d ^= 1u;
             tc_fence_after();
         }
-        // epilogue: TMEM lane = output node of the tile, columns [64 * dom, 64 * dom + 64) = its channels for subdomain dom
+        // epilogue: TMEM lane = output node of the tile, columns [64 * dom, 64 * dom + 64) = its channels for subdomain dom.
+        // nb leaves as the A-operand image the node kernels TMA in: per 128 consecutive global rows a hi and a lo
+        // fp16 plane in the K-major SWIZZLE_128B layout, still in the scaled domain (no split work left for the consumer).
+        const int orow = __ldg(plan.out_rows + (size_t)tile * TILE + t);
 #pragma unroll 1
         for (int dom = 0; dom < 2; ++dom) {
             if (d0 + dom >= Bc) break;
-            const uint32_t rbase = b_hi + (uint32_t)t * 256u;
+            const int64_t grow = (int64_t)(d0 + dom) * plan.n_out + orow;
+            unsigned char* img = reinterpret_cast<unsigned char*>(nb_img) + (grow / TILE) * (int64_t)ABUF;
+            const uint32_t ur = (uint32_t)(grow % TILE);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 float x[16];
                 tmem_ld16_sync(tmem + (uint32_t)(dom * 64 + q * 16), x);
+                if (orow >= 0) {
 #pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    const uint32_t chunk = (uint32_t)(q * 4 + h);
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + ((chunk ^ ((uint32_t)t & 7u)) << 4)),
-                                 "f"(x[h * 4 + 0] * AINV), "f"(x[h * 4 + 1] * AINV), "f"(x[h * 4 + 2] * AINV), "f"(x[h * 4 + 3] * AINV)
-                                 : "memory");
+                    for (int h = 0; h < 2; ++h) {
+                        uint4 hi, lo;
+                        split2(x[h * 8 + 0], x[h * 8 + 1], hi.x, lo.x);
+                        split2(x[h * 8 + 2], x[h * 8 + 3], hi.y, lo.y);
+                        split2(x[h * 8 + 4], x[h * 8 + 5], hi.z, lo.z);
+                        split2(x[h * 8 + 6], x[h * 8 + 7], hi.w, lo.w);
+                        const uint32_t off = swz(ur, (uint32_t)(q * 2 + h));
+                        *reinterpret_cast<uint4*>(img + off) = hi;
+                        *reinterpret_cast<uint4*>(img + APLANE + off) = lo;
+                    }
                 }
             }
-            named_bar(1 + wg, 128);
-            float* dst = nb_out + (int64_t)(d0 + dom) * plan.n_out * P;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int rr = warp * 32 + 2 * i + (lane >> 4);
-                const uint32_t chunk = (uint32_t)(lane & 15);
-                const int orow = __ldg(plan.out_rows + (size_t)tile * TILE + rr);
-                float4 o;
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
-                             : "r"(b_hi + (uint32_t)rr * 256u + ((chunk ^ ((uint32_t)rr & 7u)) << 4)));
-                if (orow >= 0) *(reinterpret_cast<float4*>(dst + (int64_t)orow * P) + chunk) = o;
-            }
-            named_bar(1 + wg, 128);
         }
     }
     tc_fence_before();
@@ -364,11 +363,43 @@ void prop_plan_free(PropPlan* p) {
 
 double prop_plan_density(const PropPlan* p) { return p ? p->density : 0.0; }
 
-void prop_tc_run(const PropPlan* plan, const float* mu_in, float* nb_out, int Bc, cudaStream_t st, int64_t* launches) {
+void prop_tc_run(const PropPlan* plan, const float* mu_in, float* nb_img, int Bc, cudaStream_t st, int64_t* launches) {
     const int64_t nitems = (int64_t)plan->dev.ntiles * ((Bc + 1) / 2);
     const int64_t ctas = (nitems + WGS - 1) / WGS;
     const int grid = (int)(ctas < 1 ? 1 : (ctas < 148 ? ctas : 148));
-    k_tc_prop<<<grid, NTHREADS, PROP_SMEM, st>>>(plan->dev, mu_in, nb_out, Bc);
+    k_tc_prop<<<grid, NTHREADS, PROP_SMEM, st>>>(plan->dev, mu_in, reinterpret_cast<uint16_t*>(nb_img), Bc);
+    ++*launches;
+}
+
+// nb[b, n, :] = Wp[b, n] * mu[L+1][b, :] (graph_conv.py:324-326) written as the fp16 tile image
+namespace {
+__global__ void k_property_backward_img(const float* __restrict__ wp, const float* __restrict__ mu_out,
+                                        uint16_t* __restrict__ nb_img, int nL, int64_t total8) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
+        const int chunk = (int)(i & 7);
+        const int64_t row = i >> 3;              // b * nL + n
+        const int64_t b = row / nL;
+        const float w = wp[row] * ASCALE;
+        const float4 m0 = *reinterpret_cast<const float4*>(mu_out + b * P + chunk * 8);
+        const float4 m1 = *reinterpret_cast<const float4*>(mu_out + b * P + chunk * 8 + 4);
+        uint4 hi, lo;
+        split2(w * m0.x, w * m0.y, hi.x, lo.x);
+        split2(w * m0.z, w * m0.w, hi.y, lo.y);
+        split2(w * m1.x, w * m1.y, hi.z, lo.z);
+        split2(w * m1.z, w * m1.w, hi.w, lo.w);
+        unsigned char* img = reinterpret_cast<unsigned char*>(nb_img) + (row / TILE) * (int64_t)ABUF;
+        const uint32_t off = swz((uint32_t)(row % TILE), (uint32_t)chunk);
+        *reinterpret_cast<uint4*>(img + off) = hi;
+        *reinterpret_cast<uint4*>(img + APLANE + off) = lo;
+    }
+}
+}  // namespace
+
+void prop_tc_property_backward(const float* wp, const float* mu_out, float* nb_img, int nL, int Bc, cudaStream_t st, int64_t* launches) {
+    const int64_t total8 = (int64_t)Bc * nL * 8;
+    const int64_t blocks = (total8 + 255) / 256;
+    k_property_backward_img<<<(unsigned)(blocks < 1 ? 1 : (blocks < 148 * 16 ? blocks : 148 * 16)), 256, 0, st>>>(
+        wp, mu_out, reinterpret_cast<uint16_t*>(nb_img), nL, total8);
     ++*launches;
 }
 
