@@ -67,7 +67,7 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lb
 __global__ void __launch_bounds__(NTHREADS, 1) k_tc_prop(PropPlanDev plan, const float* __restrict__ mu_in,
                                                          uint16_t* __restrict__ nb_img, int Bc) {
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
     PropTail* tail = reinterpret_cast<PropTail*>(base + WGS * PROP_WG_BYTES);
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2 * WGS; ++i) mbar_init(smem_u32(&tail->mbar[i]), 1);

@@ -105,6 +105,18 @@ __device__ __forceinline__ void a_store8(const WG& c, int chunk, const float (&v
 
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
+// read-only global loads the compiler must not sink past the MMA waits (they are issued early to hide DRAM latency)
+__device__ __forceinline__ float4 ldg4_now(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ldg1_now(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
 // accumulator columns [dcol, dcol+64) + bias (optionally ReLU) -> A planes
 template <bool RELU>
 __device__ __forceinline__ void epilogue_to_a(const WG& c, uint32_t dcol, const float* __restrict__ bias_s) {
@@ -188,6 +200,30 @@ __device__ __forceinline__ bool epilogue_to_global(const WG& c, uint32_t dcol, c
     return bad && (row0 + c.t < rows);
 }
 
+// (accumulator columns [dcol, dcol+64) + bias) * rowscale * AINV -> this thread's row of global fp32 [rows][64], straight
+// from registers (16-byte pieces; the A buffer stays free for the next tile's TMA).  Returns true on NaN in a valid row.
+__device__ __forceinline__ bool epilogue_to_global_direct(const WG& c, uint32_t dcol, const float* __restrict__ bias_s, float rowscale,
+                                                          float* __restrict__ dst, int64_t row0, int64_t rows) {
+    bool bad = false;
+    rowscale *= AINV;
+    const bool ok = row0 + c.t < rows;
+    float4* out = reinterpret_cast<float4*>(dst + (row0 + c.t) * P);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float v[16];
+        tmem_ld16_sync(c.tmem + dcol + q * 16, v);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const float4 b4 = lds4(bias_s + q * 16 + h * 4);
+            const float4 o = make_float4((v[h * 4 + 0] + b4.x) * rowscale, (v[h * 4 + 1] + b4.y) * rowscale,
+                                         (v[h * 4 + 2] + b4.z) * rowscale, (v[h * 4 + 3] + b4.w) * rowscale);
+            bad |= (o.x != o.x) | (o.y != o.y) | (o.z != o.z) | (o.w != o.w);
+            if (ok) out[q * 4 + h] = o;
+        }
+    }
+    return bad && ok;
+}
+
 // (accumulator columns [dcol, dcol+64) + bias) * rowscale -> relax' layout [tile][16][128][4] (scaled domain, coalesced)
 __device__ __forceinline__ void epilogue_to_rlx(const WG& c, uint32_t dcol, const float* __restrict__ bias_s, float rowscale,
                                                 float* __restrict__ dst_tile) {
@@ -228,7 +264,7 @@ __device__ __forceinline__ CtaSetup cta_setup(uint32_t wbytes, const uint16_t* c
                                               const uint32_t (&wlen)[NW]) {
     extern __shared__ unsigned char smem_raw[];
     CtaSetup s;
-    s.base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    s.base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // pointer arithmetic keeps the shared address space
     s.w = smem_u32(s.base);
     s.tail = reinterpret_cast<Tail*>(s.base + wbytes + NWG * ABUF);
     if (threadIdx.x == 0) {
@@ -297,15 +333,18 @@ __global__ void __launch_bounds__(128 * UPD_WG, 1) k_tc_update(GnnParams g, int 
     const uint32_t W = s.w;
     const int64_t ntiles = (rows + TILE - 1) / TILE;
     bool bad = false;
-    for (int64_t tile = (int64_t)blockIdx.x * UPD_WG + c.wg; tile < ntiles; tile += (int64_t)gridDim.x * UPD_WG) {
+    const int64_t tile_step = (int64_t)gridDim.x * UPD_WG;
+    int64_t tile = (int64_t)blockIdx.x * UPD_WG + c.wg;
+    if (tile < ntiles) tma_tile(c, nb_img + (size_t)tile * (ABUF / 2));          // first tile's nb image
+    for (; tile < ntiles; tile += tile_step) {
         const int64_t row0 = tile * TILE, grow = row0 + c.t;
-        tma_tile(c, nb_img + (size_t)tile * (ABUF / 2));
+        const bool has_next = tile + tile_step < ntiles;
         float l = 0.f, u = 1.f;
-        if (grow < rows) { l = lb[grow]; u = ub[grow]; }
-        const Ratio q = compute_ratio(l, u);
-        const float gate = (q.r0 != 0.0f) ? 1.0f : 0.0f;
+        if (grow < rows) { l = ldg1_now(lb + grow); u = ldg1_now(ub + grow); }
         // D[0:128) = nb [W3a; W3b]^T
         gemm<true>(c, W + UPD_W3, W + UPD_W3 + 2 * WPLANE, 128, 0, false);
+        const Ratio q = compute_ratio(l, u);
+        const float gate = (q.r0 != 0.0f) ? 1.0f : 0.0f;
         // h3 = relu(r0 * D[0:64) + r1 * D[64:128) + b3) -> A   (graph_conv.py:169-170 / 331-336)
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
@@ -333,7 +372,7 @@ __global__ void __launch_bounds__(128 * UPD_WG, 1) k_tc_update(GnnParams g, int 
         {
             const float* rt = rlx + (size_t)tile * (TILE * P);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) rx[i] = __ldg(reinterpret_cast<const float4*>(rt + ((size_t)i * TILE + c.t) * 4));
+            for (int i = 0; i < 16; ++i) rx[i] = ldg4_now(rt + ((size_t)i * TILE + c.t) * 4);
         }
         gemm_finish(c);
         // g = relu(D + relax' + bc) -> A
@@ -354,7 +393,9 @@ __global__ void __launch_bounds__(128 * UPD_WG, 1) k_tc_update(GnnParams g, int 
         }
         // D[64:128) = g W4_2^T;  mu = (D + b) * (r0 != 0) -> global
         gemm(c, W + UPD_W42, W + UPD_W42 + WPLANE, 64, 64, false);
-        bad |= epilogue_to_global(c, 64, tl.bias[2], gate, mu_out, row0, rows);
+        // the A buffer is free again: fetch the next tile's nb image while this tile's results leave
+        if (scores == nullptr && has_next) tma_tile(c, nb_img + (size_t)(tile + tile_step) * (ABUF / 2));
+        bad |= epilogue_to_global_direct(c, 64, tl.bias[2], gate, mu_out, row0, rows);
         if (scores != nullptr) {      // score head on the new embeddings (graph_conv.py:448-449)
 #pragma unroll
             for (int qd = 0; qd < 4; ++qd) {
@@ -371,6 +412,7 @@ __global__ void __launch_bounds__(128 * UPD_WG, 1) k_tc_update(GnnParams g, int 
                 }
             }
             gemm(c, W + UPD_FN, W + UPD_FN + WPLANE, 64, 0, false);
+            if (has_next) tma_tile(c, nb_img + (size_t)(tile + tile_step) * (ABUF / 2));
             float sc = 0.f;
 #pragma unroll
             for (int qd = 0; qd < 4; ++qd) {
@@ -380,9 +422,6 @@ __global__ void __launch_bounds__(128 * UPD_WG, 1) k_tc_update(GnnParams g, int 
                 for (int j = 0; j < 16; ++j) sc = fmaf(relu_nan(v[j] + tl.bias[3][qd * 16 + j]), tl.vec[qd * 16 + j], sc);
             }
             if (grow < rows) scores[(grow / n) * score_stride + score_off + (grow % n)] = fmaf(sc, AINV, bscore);
-            fence_proxy_async();
-            tc_fence_before();
-            wg_barrier(c);            // A buffer and accumulators are free for the next tile
         }
     }
     if (bad) atomicAdd(nan_count, 1ULL);
