@@ -565,7 +565,7 @@ int gnnb_score(gnnb_ctx* ctx, const gnnb_frontier* in, float* best_score, int32_
     cudaStream_t st = (cudaStream_t)stream;
     const int L = (int)ctx->layers.size();
     const bool host = in->mem == GNNB_MEM_HOST;
-    int chunk = ctx->chunk > 0 ? ctx->chunk : 128;
+    int chunk = ctx->chunk > 0 ? ctx->chunk : 512;
     if (chunk > in->B) chunk = in->B;
     TRY(ensure_workspace(ctx, chunk, host));
     const std::vector<int>& n = ctx->n;

@@ -7,7 +7,7 @@
 // any of them touches, padded to chunks of 64, and its values are stored as fp16 hi/lo planes in the UMMA K-major
 // SWIZZLE_128B image.  conv_transpose's 1/freq tap-count normalisation is folded into the rows.
 //
-// The kernel is a gather-GEMM: a warpgroup owns (tile, pair of subdomains); per K chunk it
+// The kernel is a gather-GEMM: a warpgroup (3 per CTA) owns (tile, pair of subdomains); per K chunk it
 //   * TMA-loads the 32 KB weight block (A operand, K-major) with one cp.async.bulk,
 //   * gathers the 64 input-node rows of both subdomains (256 B each, coalesced), splits them into fp16 hi/lo and
 //     writes them as the MN-major B operand  [k][(subdomain, channel)]  (N = 128),
@@ -48,7 +48,7 @@ constexpr uint32_t PROP_B_BYTES = 2 * 2 * 64 * 128;  // 32 KB: [plane][subdomain
 constexpr uint32_t PROP_WG_BYTES = PROP_A_BYTES + PROP_B_BYTES;
 
 struct PropTail {
-    uint64_t mbar[2 * WGS];
+    uint64_t mbar[2 * 4];
     uint32_t tmem_slot;
 };
 
@@ -64,13 +64,21 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lb
     return d;
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) k_tc_prop(PropPlanDev plan, const float* __restrict__ mu_in,
-                                                         uint16_t* __restrict__ nb_img, int Bc) {
+constexpr int PWG = 3;                               // warpgroups per CTA: 3 x (32 KB weights + 32 KB gathered rows)
+
+__device__ __forceinline__ float4 ldg4_now(const float* p) {      // asm volatile: issued where written, never sunk
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+__global__ void __launch_bounds__(128 * PWG, 1) k_tc_prop(PropPlanDev plan, const float* __restrict__ mu_in,
+                                                          uint16_t* __restrict__ nb_img, int Bc) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
-    PropTail* tail = reinterpret_cast<PropTail*>(base + WGS * PROP_WG_BYTES);
+    PropTail* tail = reinterpret_cast<PropTail*>(base + PWG * PROP_WG_BYTES);
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2 * WGS; ++i) mbar_init(smem_u32(&tail->mbar[i]), 1);
+        for (int i = 0; i < 2 * PWG; ++i) mbar_init(smem_u32(&tail->mbar[i]), 1);
         fence_mbar_init();
     }
     __syncwarp();
@@ -84,74 +92,94 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_prop(PropPlanDev plan, const
     const uint32_t a_hi = smem_u32(base) + (uint32_t)wg * PROP_WG_BYTES, a_lo = a_hi + APLANE;
     const uint32_t b_hi = a_hi + PROP_A_BYTES, b_lo = b_hi + PROP_B_BYTES / 2;
     const uint32_t mbar_a = smem_u32(&tail->mbar[2 * wg]), mbar_d = smem_u32(&tail->mbar[2 * wg + 1]);
-    const uint32_t tmem = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)wg * 256u;
-    const uint32_t tmem_d = (tmem_base & 0x0000FFFFu) + (uint32_t)wg * 256u;
+    const uint32_t tmem = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)wg * 128u;
+    const uint32_t tmem_d = (tmem_base & 0x0000FFFFu) + (uint32_t)wg * 128u;
     // D fp32, A fp16 K-major, B fp16 MN-major (bit 16), M = 128, N = 128
     const uint32_t idesc = (1u << 4) | (1u << 16) | ((128u >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
     uint32_t ph_a = 0, ph_d = 0;
 
     const int npairs = (Bc + 1) >> 1;
-    const int64_t nitems = (int64_t)plan.ntiles * npairs;
-    for (int64_t item = (int64_t)blockIdx.x * WGS + wg; item < nitems; item += (int64_t)gridDim.x * WGS) {
-        const int tile = (int)(item / npairs), d0 = 2 * (int)(item % npairs);
-        const int ch0 = plan.tile_chunk0[tile], ch1 = plan.tile_chunk0[tile + 1];
-        for (int ch = ch0; ch < ch1; ++ch) {
-            if (t == 0) {   // weight block of this chunk (the previous chunk's MMAs have completed: A buffer is free)
-                mbar_expect_tx(mbar_a, PROP_A_BYTES);
-                bulk_g2s(a_hi, plan.a_planes + (size_t)ch * (PROP_A_BYTES / 2), PROP_A_BYTES, mbar_a);
-            }
-            // gather 64 input-node rows x 2 subdomains -> B planes
-            float4 v[16];
+    const int64_t nitems = (int64_t)plan.ntiles * npairs, item_step = (int64_t)gridDim.x * PWG;
+
+    // the walk over (item = (tile, subdomain pair), K chunk) is flattened so that the rows of the NEXT chunk are
+    // requested before waiting for the current chunk's MMAs, across item boundaries too
+    int64_t item = (int64_t)blockIdx.x * PWG + wg;
+    int tile = 0, d0 = 0, ch = 0, ch0 = 0, ch1 = 0;
+    auto open_item = [&]() {
+        tile = (int)(item / npairs);
+        d0 = 2 * (int)(item % npairs);
+        ch0 = plan.tile_chunk0[tile];
+        ch1 = plan.tile_chunk0[tile + 1];
+        ch = ch0;
+    };
+    float4 v[16];
+    auto gather_issue = [&](int g_ch, int g_d0) {        // 64 input-node rows x 2 subdomains, two 256-byte rows per warp load
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int rr = warp * 32 + 2 * i + (lane >> 4);
-                const int dom = rr >> 6, k = rr & 63;
-                const int idx = __ldg(plan.in_rows + (size_t)ch * 64 + k);
-                const int d = d0 + dom;
-                v[i] = (idx >= 0 && d < Bc)
-                           ? __ldg(reinterpret_cast<const float4*>(mu_in + ((int64_t)d * plan.n_in + idx) * P) + (lane & 15))
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int rr = warp * 32 + 2 * i + (lane >> 4);
-                const int dom = rr >> 6, k = rr & 63, c4 = lane & 15;
-                uint32_t h0, h1, l0, l1;
-                split2(v[i].x * ASCALE, v[i].y * ASCALE, h0, l0);
-                split2(v[i].z * ASCALE, v[i].w * ASCALE, h1, l1);
-                const uint32_t off = (uint32_t)dom * 8192u + swz((uint32_t)k, (uint32_t)(c4 >> 1)) + (uint32_t)(c4 & 1) * 8u;
-                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(b_hi + off), "r"(h0), "r"(h1) : "memory");
-                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(b_lo + off), "r"(l0), "r"(l1) : "memory");
-            }
-            fence_proxy_async();
-            tc_fence_before();
-            named_bar(1 + wg, 128);
-            if (t == 0) {
-                tc_fence_after();
-                mbar_wait(mbar_a, ph_a);
-                const int ks_n = plan.ksteps[ch];
-#pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
-                    const uint64_t ad = make_desc(pass == 1 ? a_lo : a_hi);
-                    const uint64_t bd = make_desc_mn(pass == 2 ? b_lo : b_hi, 8192u);
-                    for (int ks = 0; ks < ks_n; ++ks)
-                        umma(tmem_d, ad + 2 * ks, bd + 128 * ks, idesc, (ch > ch0 || pass > 0 || ks > 0) ? 1u : 0u);
-                }
-                umma_commit(mbar_d);
-            }
-            ph_a ^= 1u;
-            mbar_wait(mbar_d, ph_d);
-            ph_d ^= 1u;
-            tc_fence_after();
+        for (int i = 0; i < 16; ++i) {
+            const int rr = warp * 32 + 2 * i + (lane >> 4);
+            const int dom = rr >> 6, k = rr & 63;
+            const int idx = __ldg(plan.in_rows + (size_t)g_ch * 64 + k);
+            const int d = g_d0 + dom;
+            if (idx >= 0 && d < Bc) v[i] = ldg4_now(mu_in + ((int64_t)d * plan.n_in + idx) * P + (lane & 15) * 4);
+            else v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+    };
+    if (item < nitems) { open_item(); gather_issue(ch, d0); }
+    while (item < nitems) {
+        if (t == 0) {   // weight block of this chunk (the previous chunk's MMAs have completed: A buffer is free)
+            mbar_expect_tx(mbar_a, PROP_A_BYTES);
+            bulk_g2s(a_hi, plan.a_planes + (size_t)ch * (PROP_A_BYTES / 2), PROP_A_BYTES, mbar_a);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {                   // gathered rows -> B planes (MN-major image)
+            const int rr = warp * 32 + 2 * i + (lane >> 4);
+            const int dom = rr >> 6, k = rr & 63, c4 = lane & 15;
+            uint32_t h0, h1, l0, l1;
+            split2(v[i].x * ASCALE, v[i].y * ASCALE, h0, l0);
+            split2(v[i].z * ASCALE, v[i].w * ASCALE, h1, l1);
+            const uint32_t off = (uint32_t)dom * 8192u + swz((uint32_t)k, (uint32_t)(c4 >> 1)) + (uint32_t)(c4 & 1) * 8u;
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(b_hi + off), "r"(h0), "r"(h1) : "memory");
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(b_lo + off), "r"(l0), "r"(l1) : "memory");
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        named_bar(1 + wg, 128);
+        if (t == 0) {
+            tc_fence_after();
+            mbar_wait(mbar_a, ph_a);
+            const int ks_n = plan.ksteps[ch];
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+                const uint64_t ad = make_desc(pass == 1 ? a_lo : a_hi);
+                const uint64_t bd = make_desc_mn(pass == 2 ? b_lo : b_hi, 8192u);
+                for (int ks = 0; ks < ks_n; ++ks)
+                    umma(tmem_d, ad + 2 * ks, bd + 128 * ks, idesc, (ch > ch0 || pass > 0 || ks > 0) ? 1u : 0u);
+            }
+            umma_commit(mbar_d);
+        }
+        ph_a ^= 1u;
+        // what comes next, and its rows (in flight while the MMAs run)
+        const bool last_chunk = (ch + 1 == ch1);
+        const int e_tile = tile, e_d0 = d0;
+        if (!last_chunk) {
+            ++ch;
+        } else {
+            item += item_step;
+            if (item < nitems) open_item();
+        }
+        if (item < nitems) gather_issue(ch, d0);
+        mbar_wait(mbar_d, ph_d);
+        ph_d ^= 1u;
+        tc_fence_after();
+        if (!last_chunk) continue;
         // epilogue: TMEM lane = output node of the tile, columns [64 * dom, 64 * dom + 64) = its channels for subdomain dom.
         // nb leaves as the A-operand image the node kernels TMA in: per 128 consecutive global rows a hi and a lo
         // fp16 plane in the K-major SWIZZLE_128B layout, still in the scaled domain (no split work left for the consumer).
-        const int orow = __ldg(plan.out_rows + (size_t)tile * TILE + t);
+        const int orow = __ldg(plan.out_rows + (size_t)e_tile * TILE + t);
 #pragma unroll 1
         for (int dom = 0; dom < 2; ++dom) {
-            if (d0 + dom >= Bc) break;
-            const int64_t grow = (int64_t)(d0 + dom) * plan.n_out + orow;
+            if (e_d0 + dom >= Bc) break;
+            const int64_t grow = (int64_t)(e_d0 + dom) * plan.n_out + orow;
             unsigned char* img = reinterpret_cast<unsigned char*>(nb_img) + (grow / TILE) * (int64_t)ABUF;
             const uint32_t ur = (uint32_t)(grow % TILE);
 #pragma unroll
@@ -179,7 +207,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tc_prop(PropPlanDev plan, const
     if (threadIdx.x < 32) tmem_dealloc(tmem_base, 512);
 }
 
-constexpr size_t PROP_SMEM = 1024 + WGS * PROP_WG_BYTES + sizeof(PropTail);
+constexpr size_t PROP_SMEM = 1024 + PWG * PROP_WG_BYTES + sizeof(PropTail);
 
 // ---- host-side plan construction ------------------------------------------------------------------------
 struct Edge { int in; float w; };
@@ -365,9 +393,9 @@ double prop_plan_density(const PropPlan* p) { return p ? p->density : 0.0; }
 
 void prop_tc_run(const PropPlan* plan, const float* mu_in, float* nb_img, int Bc, cudaStream_t st, int64_t* launches) {
     const int64_t nitems = (int64_t)plan->dev.ntiles * ((Bc + 1) / 2);
-    const int64_t ctas = (nitems + WGS - 1) / WGS;
+    const int64_t ctas = (nitems + PWG - 1) / PWG;
     const int grid = (int)(ctas < 1 ? 1 : (ctas < 148 ? ctas : 148));
-    k_tc_prop<<<grid, NTHREADS, PROP_SMEM, st>>>(plan->dev, mu_in, reinterpret_cast<uint16_t*>(nb_img), Bc);
+    k_tc_prop<<<grid, 128 * PWG, PROP_SMEM, st>>>(plan->dev, mu_in, reinterpret_cast<uint16_t*>(nb_img), Bc);
     ++*launches;
 }
 
