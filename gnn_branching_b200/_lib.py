@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libgnnb.so')
+LIB_PATH = os.environ.get('GNNB_LIB') or os.path.join(_HERE, 'libgnnb.so')   # GNNB_LIB: debug builds (phase tracing)
 
 GNNB_OK, GNNB_ERR_INVALID, GNNB_ERR_CUDA, GNNB_ERR_STATE, GNNB_ERR_NAN, GNNB_ERR_UNSUPPORTED = range(6)
 LAYER_CONV, LAYER_LINEAR = 0, 1

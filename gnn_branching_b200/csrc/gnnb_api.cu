@@ -1,10 +1,12 @@
 // C ABI of libgnnb.so (include/gnnb.h): context, parameter packing, workspace, and the per-chunk stage schedule.
 //
-// HBM layout per chunk of Bc subdomains (all fp32, node-major, one 256-byte row of 64 channels per node):
+// HBM layout per chunk of Bc subdomains (node-major, 256 bytes of 64 channels per node = global row b * n_k + node):
 //   mu[k]      [Bc, n_k, 64]  k = 0 (input pixels) .. L (hidden) .. L+1 (output node)   init_mu, graph_conv.py:487-496
 //   nb         [Bc, max_k n_k, 64]   neighbour embeddings of the layer being updated (reused by every stage)
 //   relax_f[k], relax_b[k]  [Bc, n_k, 64]  round-independent relaxation features (see gnnb_simt.cu header)
 //   scores     [Bc, sum n_k]
+// SIMT mode keeps them as plain fp32 rows; the tensor-core mode keeps mu[0..L] and nb as fp16 hi/lo tile images of 128
+// rows (32 KB per tile, same 256 bytes per node; formats in gnnb_umma.cuh) and relax' tile-transposed (gnnb_tc.cu).
 // Only adjacent layers are live at any time, so a chunk's stage working set is ~3 * Bc * n_k * 256 B.
 #include <math.h>
 #include <stdio.h>
@@ -99,9 +101,9 @@ int ensure_workspace(gnnb_ctx* ctx, int Bc, bool host_staging) {
     size_t total = 0;
     auto take = [&](size_t elems) { size_t off = total; total += align4(elems) + 64; return off; };
     std::vector<size_t> o_mu(L + 2), o_rf(L + 1), o_rb(L + 1), o_lb(L + 2), o_ub(L + 2), o_du(L), o_pr(L), o_po(L);
-    // nb and relax' are stored per tile of 128 rows by the tensor-core kernels: round the row counts up
+    // mu, nb and relax' are stored per tile of 128 rows by the tensor-core kernels: round the row counts up
     auto tiled = [](size_t rows) { return ((rows + 127) / 128) * 128; };
-    for (int k = 0; k <= L + 1; ++k) o_mu[k] = take((size_t)Bc * ctx->n[k] * P);
+    for (int k = 0; k <= L + 1; ++k) o_mu[k] = take(tiled((size_t)Bc * ctx->n[k]) * P);
     for (int k = 1; k <= L; ++k) { o_rf[k] = take(tiled((size_t)Bc * ctx->n[k]) * P); o_rb[k] = take(tiled((size_t)Bc * ctx->n[k]) * P); }
     const size_t o_nb = take(tiled((size_t)Bc * nmax) * P);
     const size_t o_sc = take((size_t)Bc * ctx->n_hidden);
@@ -189,12 +191,12 @@ int prof_collect(gnnb_ctx* ctx) {
     return GNNB_OK;
 }
 
-// nb is an fp16 tile image in tensor-core mode: unpack it into the snapshot
-int snap_nb(gnnb_ctx* ctx, const std::string& name, const float* nb, int64_t rows, cudaStream_t st) {
+// mu and nb are fp16 tile images in tensor-core mode (mu swizzled, nb piece-major): unpack them into the snapshot
+int snap_img(gnnb_ctx* ctx, const std::string& name, const float* img, int64_t rows, bool piece_major, cudaStream_t st) {
     if (!ctx->snapshot) return GNNB_OK;
-    if (ctx->math != GNNB_MATH_TC_FP16X3) return snap(ctx, name, nb, rows * P, st);
-    TRY_(snap(ctx, name, nb, rows * P, st));          // allocates / sizes the snapshot buffer
-    tc_unpack_tile_image(nb, ctx->snaps[name].first, rows, st);
+    if (ctx->math != GNNB_MATH_TC_FP16X3) return snap(ctx, name, img, rows * P, st);
+    TRY_(snap(ctx, name, img, rows * P, st));          // allocates / sizes the snapshot buffer
+    tc_unpack_tile_image(img, ctx->snaps[name].first, rows, piece_major, st);
     return GNNB_OK;
 }
 
@@ -233,7 +235,7 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
         if (tc) tc_input_embed(g, in.lb[0], in.pin, in.ub[0], ctx->mu[0], rows0, st, lc);
         else simt_input_embed(g, in.lb[0], in.pin, in.ub[0], ctx->mu[0], rows0, st, lc);
     }
-    TRY(snap(ctx, "mu0_embed", ctx->mu[0], rows0 * P, st));
+    TRY(snap_img(ctx, "mu0_embed", ctx->mu[0], rows0, false, st));
 
     for (int t = 0; t < g.T; ++t) {
         const bool last = (t == g.T - 1);
@@ -245,17 +247,17 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
                 if (tc) prop_tc_run(ctx->plan_fwd[k - 1], ctx->mu[k - 1], ctx->nb, Bc, st, lc);
                 else prop_forward(ctx->layers[k - 1], ctx->mu[k - 1], ctx->nb, Bc, st, lc);
             }
-            TRY(snap_nb(ctx, name("t%d_fwd_nb%d", t, k), ctx->nb, rows, st));
+            TRY(snap_img(ctx, name("t%d_fwd_nb%d", t, k), ctx->nb, rows, true, st));
             {
                 ProfScope ps(ctx, GNNB_K_UPDATE_FWD, rows, st);
                 if (tc) tc_update(g, false, in.lb[k], in.ub[k], ctx->nb, ctx->relax_f[k], ctx->mu[k], nullptr, ctx->n[k], 0, 0, rows, ctx->d_nan, st, lc);
                 else simt_update(g, false, in.lb[k], in.ub[k], ctx->nb, ctx->relax_f[k], ctx->mu[k], nullptr, ctx->n[k], 0, 0, rows, ctx->d_nan, st, lc);
             }
-            TRY(snap(ctx, name("t%d_fwd_mu%d", t, k), ctx->mu[k], rows * P, st));
+            TRY(snap_img(ctx, name("t%d_fwd_mu%d", t, k), ctx->mu[k], rows, false, st));
         }
         {
             ProfScope ps(ctx, GNNB_K_OUTPUT, Bc, st);
-            output_node(g, in.wp, in.bp, ctx->mu[L], in.lb[L + 1], in.ub[L + 1], in.pout, ctx->mu[L + 1], ctx->n[L], Bc, st, lc);
+            output_node(g, in.wp, in.bp, ctx->mu[L], tc, in.lb[L + 1], in.ub[L + 1], in.pout, ctx->mu[L + 1], ctx->n[L], Bc, st, lc);
         }
         TRY(snap(ctx, name("t%d_mu_out", t, 0), ctx->mu[L + 1], (int64_t)Bc * P, st));
         // backward sweep
@@ -268,14 +270,14 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
                 else if (tc) prop_tc_run(ctx->plan_bwd[k], ctx->mu[k + 1], ctx->nb, Bc, st, lc);
                 else prop_backward(ctx->layers[k], ctx->mu[k + 1], ctx->nb, Bc, true, st, lc);
             }
-            TRY(snap_nb(ctx, name("t%d_bwd_nb%d", t, k), ctx->nb, rows, st));
+            TRY(snap_img(ctx, name("t%d_bwd_nb%d", t, k), ctx->nb, rows, true, st));
             float* sc = last ? scores : nullptr;
             {
                 ProfScope ps(ctx, last ? GNNB_K_UPDATE_BWD_SCORE : GNNB_K_UPDATE_BWD, rows, st);
                 if (tc) tc_update(g, true, in.lb[k], in.ub[k], ctx->nb, ctx->relax_b[k], ctx->mu[k], sc, ctx->n[k], ctx->n_hidden, ctx->hidden_off[k], rows, ctx->d_nan, st, lc);
                 else simt_update(g, true, in.lb[k], in.ub[k], ctx->nb, ctx->relax_b[k], ctx->mu[k], sc, ctx->n[k], ctx->n_hidden, ctx->hidden_off[k], rows, ctx->d_nan, st, lc);
             }
-            TRY(snap(ctx, name("t%d_bwd_mu%d", t, k), ctx->mu[k], rows * P, st));
+            TRY(snap_img(ctx, name("t%d_bwd_mu%d", t, k), ctx->mu[k], rows, false, st));
         }
         // input layer: feeds the next round only (dead on the last round)
         if (!last) {
@@ -289,7 +291,7 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
                 if (tc) tc_input_update(g, in.lb[0], in.ub[0], ctx->nb, ctx->mu[0], rows0, st, lc);
                 else simt_input_update(g, in.lb[0], in.ub[0], ctx->nb, ctx->mu[0], rows0, st, lc);
             }
-            TRY(snap(ctx, name("t%d_mu0", t, 0), ctx->mu[0], rows0 * P, st));
+            TRY(snap_img(ctx, name("t%d_mu0", t, 0), ctx->mu[0], rows0, false, st));
         }
     }
     {

@@ -98,14 +98,15 @@ int64_t tc_pack_weight(const float* w_host, int K, uint16_t* dst_host);
 int64_t tc_packed_elems(int K);
 int tc_init();   // opt-in shared memory sizes; returns cudaError_t
 bool tc_available();
-void tc_unpack_tile_image(const float* img, float* out, int64_t rows, cudaStream_t st);   // debugging snapshots
+// tile image (gnnb_umma.cuh: mu = swizzled, nb = piece-major) -> fp32 [rows][64]; debugging snapshots
+void tc_unpack_tile_image(const float* img, float* out, int64_t rows, bool piece_major, cudaStream_t st);
 
 // propagation through the verified network and the small kernels (gnnb_prop.cu)
 int prop_init(int max_smem_bytes);
 void prop_forward(const LayerDev& L, const float* mu_prev, float* nb, int Bc, cudaStream_t st, int64_t* launches);
 void prop_backward(const LayerDev& L, const float* mu_next, float* nb, int Bc, bool normalise, cudaStream_t st, int64_t* launches);
 void prop_property_backward(const float* wp, const float* mu_out, float* nb, int nL, int Bc, cudaStream_t st, int64_t* launches);
-void output_node(const GnnParams& g, const float* wp, const float* bp, const float* mu_L, const float* lb_out,
+void output_node(const GnnParams& g, const float* wp, const float* bp, const float* mu_L, bool mu_image, const float* lb_out,
                  const float* ub_out, const float* prim_out, float* mu_out, int nL, int Bc, cudaStream_t st, int64_t* launches);
 void masked_argmax(const float* scores, const float* mask, int n_hidden, int Bc, float* best_score, int32_t* best_idx,
                    cudaStream_t st, int64_t* launches);

@@ -10,6 +10,7 @@
 //   prop_property_backward   nb[b,n,:] = Wp[b,n] * mu[L+1][b,:]   (graph_conv.py:324-326, rank-1)
 //   output_node    graph_conv.py:196-210
 //   masked_argmax  torch.max over the candidate rows + index mapping (graph_score.py:41-47)
+#include <cuda_fp16.h>
 #include <math.h>
 
 #include "gnnb_common.cuh"
@@ -185,16 +186,27 @@ __global__ void k_property_backward(const float* __restrict__ wp, const float* _
     }
 }
 
+// embedding channel c of global row `row`: fp32 [rows][64], or (mu_image) the tensor-core path's mu tile image —
+// fp16 hi + lo planes, K-major SWIZZLE_128B, scaled by 1/8 (gnnb_umma.cuh)
+__device__ __forceinline__ float mu_at(const float* __restrict__ mu, int mu_image, int64_t row, int c) {
+    if (!mu_image) return mu[row * P + c];
+    const uint32_t r = (uint32_t)(row & 127);
+    const uint32_t off = (r >> 3) * 1024u + (r & 7u) * 128u + ((((uint32_t)c >> 3) ^ (r & 7u)) << 4) + ((uint32_t)c & 7u) * 2u;
+    const unsigned char* tile = reinterpret_cast<const unsigned char*>(mu) + (row >> 7) * 32768;
+    const __half hi = *reinterpret_cast<const __half*>(tile + off), lo = *reinterpret_cast<const __half*>(tile + 16384 + off);
+    return (__half2float(hi) + __half2float(lo)) * 8.0f;
+}
+
 // one 64-thread block per subdomain
 __global__ void __launch_bounds__(64) k_output_node(GnnParams g, const float* __restrict__ wp, const float* __restrict__ bp,
-                                                    const float* __restrict__ mu_L, const float* __restrict__ lb_out,
+                                                    const float* __restrict__ mu_L, int mu_image, const float* __restrict__ lb_out,
                                                     const float* __restrict__ ub_out, const float* __restrict__ prim_out,
                                                     float* __restrict__ mu_out, int nL) {
     __shared__ float cat[2 * P];
     __shared__ float h2[P];
     const int b = blockIdx.x, c = threadIdx.x;
     float nbv = 0.f;                                       // prop.weight @ mu[L]  (graph_conv.py:196)
-    for (int n = 0; n < nL; ++n) nbv = fmaf(wp[(int64_t)b * nL + n], mu_L[((int64_t)b * nL + n) * P + c], nbv);
+    for (int n = 0; n < nL; ++n) nbv = fmaf(wp[(int64_t)b * nL + n], mu_at(mu_L, mu_image, (int64_t)b * nL + n, c), nbv);
     const float feat[4] = {lb_out[b], ub_out[b], prim_out[b], bp[b]};   // graph_conv.py:202-205
     float h = g.bias[OUT1][c];
 #pragma unroll
@@ -298,9 +310,9 @@ void prop_property_backward(const float* wp, const float* mu_out, float* nb, int
     ++*launches;
 }
 
-void output_node(const GnnParams& g, const float* wp, const float* bp, const float* mu_L, const float* lb_out,
+void output_node(const GnnParams& g, const float* wp, const float* bp, const float* mu_L, bool mu_image, const float* lb_out,
                  const float* ub_out, const float* prim_out, float* mu_out, int nL, int Bc, cudaStream_t st, int64_t* launches) {
-    k_output_node<<<Bc, 64, 0, st>>>(g, wp, bp, mu_L, lb_out, ub_out, prim_out, mu_out, nL);
+    k_output_node<<<Bc, 64, 0, st>>>(g, wp, bp, mu_L, mu_image ? 1 : 0, lb_out, ub_out, prim_out, mu_out, nL);
     ++*launches;
 }
 

@@ -7,13 +7,9 @@
 // any of them touches, padded to chunks of 64, and its values are stored as fp16 hi/lo planes in the UMMA K-major
 // SWIZZLE_128B image.  conv_transpose's 1/freq tap-count normalisation is folded into the rows.
 //
-// The kernel is a gather-GEMM: a warpgroup (3 per CTA) owns (tile, pair of subdomains); per K chunk it
-//   * TMA-loads the 32 KB weight block (A operand, K-major) with one cp.async.bulk,
-//   * gathers the 64 input-node rows of both subdomains (256 B each, coalesced), splits them into fp16 hi/lo and
-//     writes them as the MN-major B operand  [k][(subdomain, channel)]  (N = 128),
-//   * issues 3 x ksteps tcgen05.mma (M = 128, N = 128, K = 16) into 128 TMEM columns,
-// then scatters the accumulator rows (one output node per TMEM lane) into nb, already split into the fp16 hi/lo
-// A-operand tile image the node-update kernels load with one cp.async.bulk.
+// The kernel (k_tc_prop below) is a warp-specialised gather-GEMM over (tile, 4 subdomains) items; its input is the mu
+// tile image of the producing layer and its output the piece-major nb tile image the node-update kernels TMA in
+// (formats: gnnb_umma.cuh).
 #include <algorithm>
 #include <functional>
 #include <map>
@@ -43,171 +39,196 @@ struct PropPlan {
 
 namespace {
 
-constexpr uint32_t PROP_A_BYTES = 2 * APLANE;        // 32 KB: hi + lo weight block of one chunk
-constexpr uint32_t PROP_B_BYTES = 2 * 2 * 64 * 128;  // 32 KB: [plane][subdomain][64 rows x 128 B]
-constexpr uint32_t PROP_WG_BYTES = PROP_A_BYTES + PROP_B_BYTES;
+// ---- the gather-GEMM kernel ---------------------------------------------------------------------------------
+// A persistent CTA (1 per SM) walks items = (tile of 128 output nodes, group of PD = 4 subdomains); per K chunk
+//   D[128 nodes x (4 subdomains x 64 channels)] += Wblock[128 x 64] * Mu[64 input nodes x (4 x 64)]
+// as tcgen05.mma M = 128, N = 256, K = 16, three passes for the fp16 hi/lo split (Wh Mh + Wl Mh + Wh Ml).
+// Warp roles (14 warps), decoupled by mbarrier rings:
+//   warp 0      TMA: the chunk's 32 KB weight block (hi, lo plane; K-major SWIZZLE_128B)      -> W ring, 3 stages
+//   warp 1      MMA issue + tcgen05.commit (frees ring stages, publishes accumulators)
+//   warps 2-5   gather, one subdomain each: the chunk's input-node rows are copied with 16-byte cp.async straight
+//               from the mu tile images (already fp16 hi/lo, scaled) into the MN-major SWIZZLE_128B B operand — no
+//               registers, no conversion; half a chunk (32 rows x 4 subdomains x 2 planes = 32 KB) per stage, 4 stages
+//   warps 6-13  two epilogue warpgroups, alternating items on a double-buffered accumulator (2 x 256 TMEM columns):
+//               tcgen05.ld -> fp16 hi/lo split -> piece-major nb tile image (consecutive rows = consecutive 16 bytes)
+constexpr int PD = 4;
+constexpr int W_STAGES = 3, B_STAGES = 4;
+constexpr uint32_t W_STAGE_BYTES = 2 * APLANE;            // 32 KB
+constexpr uint32_t B_ROWS = 32;                           // input nodes per B stage (half a chunk = 2 K steps)
+constexpr uint32_t B_DOM_BYTES = B_ROWS * 128;            // 4 KB: one plane of one subdomain
+constexpr uint32_t B_PLANE_BYTES = PD * B_DOM_BYTES;      // 16 KB
+constexpr uint32_t B_STAGE_BYTES = 2 * B_PLANE_BYTES;     // 32 KB
+constexpr int PROP_WARPS = 14, PROP_THREADS = PROP_WARPS * 32;
+constexpr int GATHER_WARP0 = 2, EPI_WARP0 = 6;
 
 struct PropTail {
-    uint64_t mbar[2 * 4];
+    uint64_t w_full[W_STAGES], w_empty[W_STAGES], b_full[B_STAGES], b_empty[B_STAGES], acc_full[2], acc_empty[2];
     uint32_t tmem_slot;
 };
+constexpr size_t PROP_SMEM = 1024 + W_STAGES * W_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + sizeof(PropTail);
 
-// MN-major SWIZZLE_128B descriptor: 64-element (128 B) rows along N, 8 K-rows per 1024 B group (SBO), the second
-// 64-wide N block (second subdomain) `lbo_bytes` further (cute::UMMA::make_umma_desc<Major::MN>)
-__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)(lbo_bytes >> 4) << 16;
-    d |= (uint64_t)(1024u >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-
-constexpr int PWG = 3;                               // warpgroups per CTA: 3 x (32 KB weights + 32 KB gathered rows)
-
-__device__ __forceinline__ float4 ldg4_now(const float* p) {      // asm volatile: issued where written, never sunk
-    float4 v;
-    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
-
-__global__ void __launch_bounds__(128 * PWG, 1) k_tc_prop(PropPlanDev plan, const float* __restrict__ mu_in,
-                                                          uint16_t* __restrict__ nb_img, int Bc) {
+__global__ void __launch_bounds__(PROP_THREADS, 1) k_tc_prop(PropPlanDev plan, const uint16_t* __restrict__ mu_img,
+                                                             uint16_t* __restrict__ nb_img, int Bc) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
-    PropTail* tail = reinterpret_cast<PropTail*>(base + PWG * PROP_WG_BYTES);
+    const uint32_t w_ring = smem_u32(base), b_ring = w_ring + W_STAGES * W_STAGE_BYTES;
+    PropTail* tail = reinterpret_cast<PropTail*>(base + W_STAGES * W_STAGE_BYTES + B_STAGES * B_STAGE_BYTES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2 * PWG; ++i) mbar_init(smem_u32(&tail->mbar[i]), 1);
+        for (int i = 0; i < W_STAGES; ++i) { mbar_init(smem_u32(&tail->w_full[i]), 1); mbar_init(smem_u32(&tail->w_empty[i]), 1); }
+        for (int i = 0; i < B_STAGES; ++i) { mbar_init(smem_u32(&tail->b_full[i]), PD * 32); mbar_init(smem_u32(&tail->b_empty[i]), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tail->acc_full[i]), 1); mbar_init(smem_u32(&tail->acc_empty[i]), 128); }
         fence_mbar_init();
     }
     __syncwarp();
-    if (threadIdx.x < 32) tmem_alloc(smem_u32(&tail->tmem_slot), 512);
+    if (warp == 0) tmem_alloc(smem_u32(&tail->tmem_slot), 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tail->tmem_slot;
 
-    const int wg = threadIdx.x >> 7, t = threadIdx.x & 127, lane = t & 31, warp = t >> 5;
-    const uint32_t a_hi = smem_u32(base) + (uint32_t)wg * PROP_WG_BYTES, a_lo = a_hi + APLANE;
-    const uint32_t b_hi = a_hi + PROP_A_BYTES, b_lo = b_hi + PROP_B_BYTES / 2;
-    const uint32_t mbar_a = smem_u32(&tail->mbar[2 * wg]), mbar_d = smem_u32(&tail->mbar[2 * wg + 1]);
-    const uint32_t tmem = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)wg * 128u;
-    const uint32_t tmem_d = (tmem_base & 0x0000FFFFu) + (uint32_t)wg * 128u;
-    // D fp32, A fp16 K-major, B fp16 MN-major (bit 16), M = 128, N = 128
-    const uint32_t idesc = (1u << 4) | (1u << 16) | ((128u >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
-    uint32_t ph_a = 0, ph_d = 0;
+    const int ngroups = (Bc + PD - 1) / PD;
+    const int64_t nitems = (int64_t)plan.ntiles * ngroups;       // item = group * ntiles + tile
 
-    const int npairs = (Bc + 1) >> 1;
-    const int64_t nitems = (int64_t)plan.ntiles * npairs, item_step = (int64_t)gridDim.x * PWG;
-
-    // the walk over (item = (tile, subdomain pair), K chunk) is flattened so that the rows of the NEXT chunk are
-    // requested before waiting for the current chunk's MMAs, across item boundaries too
-    int64_t item = (int64_t)blockIdx.x * PWG + wg;
-    int tile = 0, d0 = 0, ch = 0, ch0 = 0, ch1 = 0;
-    auto open_item = [&]() {
-        tile = (int)(item / npairs);
-        d0 = 2 * (int)(item % npairs);
-        ch0 = plan.tile_chunk0[tile];
-        ch1 = plan.tile_chunk0[tile + 1];
-        ch = ch0;
-    };
-    float4 v[16];
-    auto gather_issue = [&](int g_ch, int g_d0) {        // 64 input-node rows x 2 subdomains, two 256-byte rows per warp load
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int rr = warp * 32 + 2 * i + (lane >> 4);
-            const int dom = rr >> 6, k = rr & 63;
-            const int idx = __ldg(plan.in_rows + (size_t)g_ch * 64 + k);
-            const int d = g_d0 + dom;
-            if (idx >= 0 && d < Bc) v[i] = ldg4_now(mu_in + ((int64_t)d * plan.n_in + idx) * P + (lane & 15) * 4);
-            else v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    };
-    if (item < nitems) { open_item(); gather_issue(ch, d0); }
-    while (item < nitems) {
-        if (t == 0) {   // weight block of this chunk (the previous chunk's MMAs have completed: A buffer is free)
-            mbar_expect_tx(mbar_a, PROP_A_BYTES);
-            bulk_g2s(a_hi, plan.a_planes + (size_t)ch * (PROP_A_BYTES / 2), PROP_A_BYTES, mbar_a);
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {                   // gathered rows -> B planes (MN-major image)
-            const int rr = warp * 32 + 2 * i + (lane >> 4);
-            const int dom = rr >> 6, k = rr & 63, c4 = lane & 15;
-            uint32_t h0, h1, l0, l1;
-            split2(v[i].x * ASCALE, v[i].y * ASCALE, h0, l0);
-            split2(v[i].z * ASCALE, v[i].w * ASCALE, h1, l1);
-            const uint32_t off = (uint32_t)dom * 8192u + swz((uint32_t)k, (uint32_t)(c4 >> 1)) + (uint32_t)(c4 & 1) * 8u;
-            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(b_hi + off), "r"(h0), "r"(h1) : "memory");
-            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(b_lo + off), "r"(l0), "r"(l1) : "memory");
-        }
-        fence_proxy_async();
-        tc_fence_before();
-        named_bar(1 + wg, 128);
-        if (t == 0) {
-            tc_fence_after();
-            mbar_wait(mbar_a, ph_a);
-            const int ks_n = plan.ksteps[ch];
-#pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {
-                const uint64_t ad = make_desc(pass == 1 ? a_lo : a_hi);
-                const uint64_t bd = make_desc_mn(pass == 2 ? b_lo : b_hi, 8192u);
-                for (int ks = 0; ks < ks_n; ++ks)
-                    umma(tmem_d, ad + 2 * ks, bd + 128 * ks, idesc, (ch > ch0 || pass > 0 || ks > 0) ? 1u : 0u);
+    if (warp == 0) {
+        // ---- weight blocks ----
+        if (lane == 0) {
+            uint32_t ws = 0, wph = 0;
+            for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const int tile = (int)(item % plan.ntiles);
+                const int ch0 = plan.tile_chunk0[tile], ch1 = plan.tile_chunk0[tile + 1];
+                for (int ch = ch0; ch < ch1; ++ch) {
+                    mbar_wait(smem_u32(&tail->w_empty[ws]), wph ^ 1u);
+                    const uint32_t full = smem_u32(&tail->w_full[ws]);
+                    mbar_expect_tx(full, W_STAGE_BYTES);
+                    bulk_g2s(w_ring + ws * W_STAGE_BYTES, plan.a_planes + (size_t)ch * (W_STAGE_BYTES / 2), W_STAGE_BYTES, full);
+                    if (++ws == W_STAGES) { ws = 0; wph ^= 1u; }
+                }
             }
-            umma_commit(mbar_d);
         }
-        ph_a ^= 1u;
-        // what comes next, and its rows (in flight while the MMAs run)
-        const bool last_chunk = (ch + 1 == ch1);
-        const int e_tile = tile, e_d0 = d0;
-        if (!last_chunk) {
-            ++ch;
-        } else {
-            item += item_step;
-            if (item < nitems) open_item();
+    } else if (warp == 1) {
+        // ---- MMA issue ----
+        if (lane == 0) {
+            // D fp32, A fp16 K-major, B fp16 MN-major (bit 16), M = 128, N = 256
+            const uint32_t idesc = (1u << 4) | (1u << 16) | ((uint32_t)(PD * 64 >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+            uint32_t ws = 0, wph = 0, bs = 0, bph = 0, it = 0;
+            for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+                const int tile = (int)(item % plan.ntiles);
+                const int ch0 = plan.tile_chunk0[tile], ch1 = plan.tile_chunk0[tile + 1];
+                const uint32_t a = it & 1u, aph = (it >> 1) & 1u;
+                mbar_wait(smem_u32(&tail->acc_empty[a]), aph ^ 1u);      // the epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d = (tmem_base & 0x0000FFFFu) + a * 256u;
+                uint32_t first = 1;
+                for (int ch = ch0; ch < ch1; ++ch) {
+                    mbar_wait(smem_u32(&tail->w_full[ws]), wph);
+                    const int nks = plan.ksteps[ch];
+                    const uint32_t wa = w_ring + ws * W_STAGE_BYTES;
+                    for (int h = 0; 2 * h < nks; ++h) {
+                        mbar_wait(smem_u32(&tail->b_full[bs]), bph);
+                        tc_fence_after();
+                        const uint32_t ba = b_ring + bs * B_STAGE_BYTES;
+                        const int kc = (nks - 2 * h) < 2 ? (nks - 2 * h) : 2;
+#pragma unroll
+                        for (int pass = 0; pass < 3; ++pass) {
+                            const uint64_t ad = make_desc(pass == 1 ? wa + APLANE : wa);
+                            const uint64_t bd = make_desc_mn(pass == 2 ? ba + B_PLANE_BYTES : ba, B_DOM_BYTES);
+                            for (int kk = 0; kk < kc; ++kk) {
+                                umma(d, ad + 2 * (2 * h + kk), bd + 128 * kk, idesc, first ? 0u : 1u);
+                                first = 0;
+                            }
+                        }
+                        umma_commit(smem_u32(&tail->b_empty[bs]));
+                        if (++bs == B_STAGES) { bs = 0; bph ^= 1u; }
+                    }
+                    umma_commit(smem_u32(&tail->w_empty[ws]));
+                    if (++ws == W_STAGES) { ws = 0; wph ^= 1u; }
+                }
+                umma_commit(smem_u32(&tail->acc_full[a]));
+            }
         }
-        if (item < nitems) gather_issue(ch, d0);
-        mbar_wait(mbar_d, ph_d);
-        ph_d ^= 1u;
-        tc_fence_after();
-        if (!last_chunk) continue;
-        // epilogue: TMEM lane = output node of the tile, columns [64 * dom, 64 * dom + 64) = its channels for subdomain dom.
-        // nb leaves as the A-operand image the node kernels TMA in: per 128 consecutive global rows a hi and a lo
-        // fp16 plane in the K-major SWIZZLE_128B layout, still in the scaled domain (no split work left for the consumer).
-        const int orow = __ldg(plan.out_rows + (size_t)e_tile * TILE + t);
+    } else if (warp < EPI_WARP0) {
+        // ---- gather: warp g copies the rows of subdomain d0 + g ----
+        const int g = warp - GATHER_WARP0;
+        const unsigned char* mu_bytes = reinterpret_cast<const unsigned char*>(mu_img);
+        uint32_t bs = 0, bph = 0;
+        for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const int tile = (int)(item % plan.ntiles);
+            const int d = (int)(item / plan.ntiles) * PD + g;
+            const bool dom_ok = d < Bc;
+            const int64_t drow = (int64_t)d * plan.n_in;
+            const int ch0 = plan.tile_chunk0[tile], ch1 = plan.tile_chunk0[tile + 1];
+            for (int ch = ch0; ch < ch1; ++ch) {
+                const int nks = plan.ksteps[ch];
+                for (int h = 0; 2 * h < nks; ++h) {
+                    const int idx = __ldg(plan.in_rows + (size_t)ch * 64 + h * B_ROWS + lane);
+                    mbar_wait(smem_u32(&tail->b_empty[bs]), bph ^ 1u);
+                    const uint32_t dst0 = b_ring + bs * B_STAGE_BYTES + (uint32_t)g * B_DOM_BYTES;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int k = i * 4 + (lane >> 3);               // row of the stage: 4 rows x 8 chunks per instruction
+                        const int node = __shfl_sync(0xffffffffu, idx, k);
+                        const bool ok = dom_ok && node >= 0;
+                        const int64_t grow = ok ? drow + node : 0;
+                        const uint32_t r = (uint32_t)(grow & (TILE - 1));
+                        const uint32_t jp = (uint32_t)(lane & 7);       // physical 16-byte chunk of the row in the mu image
+                        const unsigned char* src = mu_bytes + (grow >> 7) * (int64_t)ABUF + (r >> 3) * 1024u + (r & 7u) * 128u + jp * 16u;
+                        const uint32_t dst = dst0 + swz((uint32_t)k, jp ^ (r & 7u));   // logical chunk = physical ^ (row & 7)
+                        cp_async16(dst, src, ok);
+                        cp_async16(dst + B_PLANE_BYTES, src + APLANE, ok);
+                    }
+                    cp_async_arrive(smem_u32(&tail->b_full[bs]));
+                    if (++bs == B_STAGES) { bs = 0; bph ^= 1u; }
+                }
+            }
+        }
+    } else {
+        // ---- epilogue: warpgroup ew takes the items it & 1 == ew ----
+        const int ew = (warp - EPI_WARP0) >> 2;
+        const int m = (warp & 3) * 32 + lane;                      // TMEM lane = tile row (a warp reaches lanes 32 * (warp % 4) ..)
+        const uint32_t tmem = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)ew * 256u;
+        const uint32_t full = smem_u32(&tail->acc_full[ew]), empty = smem_u32(&tail->acc_empty[ew]);
+        uint32_t aph = 0, it = 0;
+        for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+            if ((int)(it & 1u) != ew) continue;
+            const int tile = (int)(item % plan.ntiles);
+            const int d0 = (int)(item / plan.ntiles) * PD;
+            const int orow = __ldg(plan.out_rows + (size_t)tile * TILE + m);
+            mbar_wait(full, aph);
+            aph ^= 1u;
+            tc_fence_after();
 #pragma unroll 1
-        for (int dom = 0; dom < 2; ++dom) {
-            if (e_d0 + dom >= Bc) break;
-            const int64_t grow = (int64_t)(e_d0 + dom) * plan.n_out + orow;
-            unsigned char* img = reinterpret_cast<unsigned char*>(nb_img) + (grow / TILE) * (int64_t)ABUF;
-            const uint32_t ur = (uint32_t)(grow % TILE);
+            for (int dom = 0; dom < PD; ++dom) {
+                if (d0 + dom >= Bc) break;
+                const int64_t grow = (int64_t)(d0 + dom) * plan.n_out + (orow >= 0 ? orow : 0);
+                unsigned char* img = reinterpret_cast<unsigned char*>(nb_img) + (grow >> 7) * (int64_t)ABUF + (uint32_t)(grow & (TILE - 1)) * 16u;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float x[16];
-                tmem_ld16_sync(tmem + (uint32_t)(dom * 64 + q * 16), x);
-                if (orow >= 0) {
+                for (int q = 0; q < 4; ++q) {
+                    float x[16];
+                    tmem_ld16_sync(tmem + (uint32_t)(dom * 64 + q * 16), x);
+                    if (orow >= 0) {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        uint4 hi, lo;
-                        split2(x[h * 8 + 0], x[h * 8 + 1], hi.x, lo.x);
-                        split2(x[h * 8 + 2], x[h * 8 + 3], hi.y, lo.y);
-                        split2(x[h * 8 + 4], x[h * 8 + 5], hi.z, lo.z);
-                        split2(x[h * 8 + 6], x[h * 8 + 7], hi.w, lo.w);
-                        const uint32_t off = swz(ur, (uint32_t)(q * 2 + h));
-                        *reinterpret_cast<uint4*>(img + off) = hi;
-                        *reinterpret_cast<uint4*>(img + APLANE + off) = lo;
+                        for (int h = 0; h < 2; ++h) {
+                            uint4 hi, lo;
+                            split2(x[h * 8 + 0], x[h * 8 + 1], hi.x, lo.x);
+                            split2(x[h * 8 + 2], x[h * 8 + 3], hi.y, lo.y);
+                            split2(x[h * 8 + 4], x[h * 8 + 5], hi.z, lo.z);
+                            split2(x[h * 8 + 6], x[h * 8 + 7], hi.w, lo.w);
+                            const uint32_t off = (uint32_t)(q * 2 + h) * NB_PIECE;
+                            *reinterpret_cast<uint4*>(img + off) = hi;
+                            *reinterpret_cast<uint4*>(img + APLANE + off) = lo;
+                        }
                     }
                 }
             }
+            tc_fence_before();
+            mbar_arrive(empty);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (threadIdx.x < 32) tmem_dealloc(tmem_base, 512);
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
-
-constexpr size_t PROP_SMEM = 1024 + PWG * PROP_WG_BYTES + sizeof(PropTail);
 
 // ---- host-side plan construction ------------------------------------------------------------------------
 struct Edge { int in; float w; };
@@ -391,11 +412,11 @@ void prop_plan_free(PropPlan* p) {
 
 double prop_plan_density(const PropPlan* p) { return p ? p->density : 0.0; }
 
-void prop_tc_run(const PropPlan* plan, const float* mu_in, float* nb_img, int Bc, cudaStream_t st, int64_t* launches) {
-    const int64_t nitems = (int64_t)plan->dev.ntiles * ((Bc + 1) / 2);
-    const int64_t ctas = (nitems + PWG - 1) / PWG;
-    const int grid = (int)(ctas < 1 ? 1 : (ctas < 148 ? ctas : 148));
-    k_tc_prop<<<grid, 128 * PWG, PROP_SMEM, st>>>(plan->dev, mu_in, reinterpret_cast<uint16_t*>(nb_img), Bc);
+void prop_tc_run(const PropPlan* plan, const float* mu_img, float* nb_img, int Bc, cudaStream_t st, int64_t* launches) {
+    const int64_t nitems = (int64_t)plan->dev.ntiles * ((Bc + PD - 1) / PD);
+    const int grid = (int)(nitems < 1 ? 1 : (nitems < 148 ? nitems : 148));
+    k_tc_prop<<<grid, PROP_THREADS, PROP_SMEM, st>>>(plan->dev, reinterpret_cast<const uint16_t*>(mu_img),
+                                                     reinterpret_cast<uint16_t*>(nb_img), Bc);
     ++*launches;
 }
 
@@ -416,7 +437,7 @@ __global__ void k_property_backward_img(const float* __restrict__ wp, const floa
         split2(w * m1.x, w * m1.y, hi.z, lo.z);
         split2(w * m1.z, w * m1.w, hi.w, lo.w);
         unsigned char* img = reinterpret_cast<unsigned char*>(nb_img) + (row / TILE) * (int64_t)ABUF;
-        const uint32_t off = swz((uint32_t)(row % TILE), (uint32_t)chunk);
+        const uint32_t off = (uint32_t)chunk * NB_PIECE + (uint32_t)(row % TILE) * 16u;     // piece-major nb image
         *reinterpret_cast<uint4*>(img + off) = hi;
         *reinterpret_cast<uint4*>(img + APLANE + off) = lo;
     }

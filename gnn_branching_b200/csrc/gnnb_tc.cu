@@ -18,14 +18,20 @@
 //   * row scalings of GEMM *inputs* move to the epilogue by linearity: [nb r0, nb r1] W3^T is one
 //     N = 128 MMA, bc2's [s1, -d2 s1, d1 s1] input one N = 192 MMA.
 //
-// Structure of a CTA (1 per SM, persistent over tiles): NWG warpgroups of 128 threads; the stage's weights sit in
-// shared memory for the CTA's lifetime as fp16 hi/lo planes in the UMMA K-major SWIZZLE_128B image (repacked once on
-// the host, landed with one cp.async.bulk per linear); each warpgroup owns one 128-node tile at a time with its own
-// 32 KB A-operand buffer, 512 / NWG TMEM columns and two mbarriers, and walks the chain of its tile sequentially:
-//   A operand (TMA of a pre-split tile image, or thread = node row writing hi/lo planes) -> fence.proxy.async ->
-//   warpgroup barrier -> one thread issues the MMAs + tcgen05.commit -> everyone waits on the mbarrier ->
-//   tcgen05.ld -> bias / ReLU / row scaling in registers -> hi/lo split -> next A ...
-// The warpgroups are independent, so one tile's epilogue overlaps the others' MMAs and loads.
+// Structure of a CTA (1 per SM, persistent over tiles): 4 warpgroups of 128 threads; the stage's weights sit in shared
+// memory for the CTA's lifetime as fp16 hi/lo planes in the UMMA K-major SWIZZLE_128B image (repacked once on the host,
+// landed with one cp.async.bulk per linear); each warpgroup owns one 128-node tile at a time with 128 tensor-memory
+// columns, a 32 KB shared-memory landing buffer for the tile's nb image and two mbarriers, and walks the chain of its
+// tile sequentially:
+//   GEMM (one thread issues 3 x 4 tcgen05.mma + tcgen05.commit) -> everyone waits on the mbarrier -> tcgen05.ld ->
+//   bias / ReLU / row scaling in registers (thread = node row = TMEM lane) -> fp16 hi/lo split -> tcgen05.st of the next
+//   A operand straight back into tensor memory -> tcgen05.wait::st + fence + warpgroup barrier -> next GEMM ...
+// Only the first GEMM of the update chain reads its A operand from shared memory (the TMA'd nb image); every chained
+// GEMM takes A from tensor memory (the ".ts" form of tcgen05.mma), so intermediate activations never touch shared
+// memory: no generic-proxy stores, no proxy fences, and the tensor core's shared-memory reads are the weights only.
+// The landing buffer is free as soon as the first GEMM has completed, so the next tile's image (and an L2 prefetch of
+// its relax' tile) is in flight during the whole rest of the chain.  The warpgroups are independent, so one tile's
+// epilogue overlaps the others' MMAs and loads.
 //
 // Private workspace layouts (produced and consumed only by the tensor-core kernels):
 //   nb       per tile of 128 consecutive rows: the A-operand image itself, [hi plane 16 KB][lo plane 16 KB], scaled by
@@ -39,71 +45,112 @@ namespace {
 using namespace tcx;
 
 // ---- warpgroup context ------------------------------------------------------------------------------
+// Tensor-memory map of a warpgroup (128 columns): [0, 64) the A operand of the chained GEMMs — fp16 hi/lo pairs written by
+// the epilogues with tcgen05.st, K step ks at columns [16 ks, 16 ks + 8) (hi) and [16 ks + 8, 16 ks + 16) (lo) — and
+// [64, 128) the fp32 accumulator of a 64-wide GEMM.  The first GEMM of the update chain (N = 128, A = nb from shared
+// memory) accumulates into [0, 128); its epilogue overwrites the columns it has consumed with the next A operand in place.
+constexpr uint32_t ACOL = 0, DCOL = 64, WG_COLS = 128;
+
 struct WG {
-    uint32_t a_hi, a_lo;        // shared addresses of this warpgroup's A planes (a_lo = a_hi + APLANE)
+    uint32_t land;              // shared address of this warpgroup's 32 KB landing buffer (TMA'd nb tile image: hi, lo plane)
     uint32_t mbar_mma, mbar_tma;
     uint32_t ph_mma, ph_tma;
     uint32_t tmem;              // TMEM address: lane base of this warp, first column of this warpgroup
+    uint32_t tmem0;             // lane 0, first column of this warpgroup (MMA operand / accumulator addresses)
     int t;                      // thread index within the warpgroup = row of the tile this thread owns
     int wg;
 };
 
 __device__ __forceinline__ void wg_barrier(const WG& c) { named_bar(1 + c.wg, 128); }
 
-// one 32 KB pre-split tile image (global) -> this warpgroup's A planes.  The A buffer must be free: its last MMA has
-// completed and generic-proxy accesses to it were fenced (fence.proxy.async) before the preceding barrier.
+// one 32 KB pre-split tile image (global) -> this warpgroup's landing buffer.  The buffer must be free: the MMAs that
+// read it have completed (it is only ever touched by the async proxy: TMA writes, tensor-core reads)
 __device__ __forceinline__ void tma_tile(const WG& c, const void* src) {
     if (c.t == 0) {
         mbar_expect_tx(c.mbar_tma, ABUF);
-        bulk_g2s(c.a_hi, src, ABUF, c.mbar_tma);
+        bulk_g2s(c.land, src, ABUF, c.mbar_tma);
     }
 }
 
-// make this thread's A-plane writes visible to the tensor core, then one thread issues 3 x 4 MMAs + commit
-template <bool WAIT_TMA>
-__device__ __forceinline__ void gemm_start(WG& c, uint32_t b_hi, uint32_t b_lo, uint32_t N, uint32_t dcol, bool accumulate) {
-    fence_proxy_async();
+// 3 passes x 4 K steps with the A operand in tensor memory (issued by one thread)
+__device__ __forceinline__ void issue_ts(const WG& c, uint32_t b_hi, uint32_t b_lo, uint32_t N, uint32_t dcol, bool accumulate) {
+    const uint32_t idesc = make_idesc(N);
+    const uint32_t d = c.tmem0 + dcol, a = c.tmem0 + ACOL;
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+        const uint64_t bd = make_desc(pass == 2 ? b_lo : b_hi);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)          // 16 fp16 along K per instruction: 32 bytes of B, 8 columns of A
+            umma_ts(d, a + 16 * k + (pass == 1 ? 8 : 0), bd + 2 * k, idesc, (accumulate || pass > 0 || k > 0) ? 1u : 0u);
+    }
+}
+// the same with the A operand in the landing buffer: the nb tile image, piece-major without swizzle (gnnb_umma.cuh)
+__device__ __forceinline__ void issue_ss(const WG& c, uint32_t b_hi, uint32_t b_lo, uint32_t N, uint32_t dcol, bool accumulate) {
+    const uint32_t idesc = make_idesc(N);
+    const uint32_t d = c.tmem0 + dcol;
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+        const uint64_t ad = make_desc_nosw(pass == 1 ? c.land + APLANE : c.land, NB_PIECE, 128u);
+        const uint64_t bd = make_desc(pass == 2 ? b_lo : b_hi);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)          // one K step = two pieces = 2 * NB_PIECE bytes of A
+            umma(d, ad + (uint64_t)(k * ((2 * NB_PIECE) >> 4)), bd + 2 * k, idesc, (accumulate || pass > 0 || k > 0) ? 1u : 0u);
+    }
+}
+
+// every thread: its tensor-memory accesses (A stores, accumulator loads) are complete and ordered before the MMAs
+__device__ __forceinline__ void gemm_sync(const WG& c) {
+    tmem_st_wait();
     tc_fence_before();
     wg_barrier(c);
-    if (c.t == 0) {
-        tc_fence_after();
-        if (WAIT_TMA) mbar_wait(c.mbar_tma, c.ph_tma);
-        const uint32_t idesc = make_idesc(N);
-        const uint32_t d = (c.tmem & 0x0000FFFFu) + dcol;      // lane 0, column base
-#pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-            const uint64_t ad = make_desc(pass == 1 ? c.a_lo : c.a_hi);
-            const uint64_t bd = make_desc(pass == 2 ? b_lo : b_hi);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)      // 16 fp16 = 32 bytes along K per instruction
-                umma(d, ad + 2 * k, bd + 2 * k, idesc, (accumulate || pass > 0 || k > 0) ? 1u : 0u);
-        }
-        umma_commit(c.mbar_mma);
-    }
-    if (WAIT_TMA) c.ph_tma ^= 1u;
 }
 __device__ __forceinline__ void gemm_finish(WG& c) {
     mbar_wait(c.mbar_mma, c.ph_mma);
     c.ph_mma ^= 1u;
     tc_fence_after();
 }
-template <bool WAIT_TMA = false>
-__device__ __forceinline__ void gemm(WG& c, uint32_t b_hi, uint32_t b_lo, uint32_t N, uint32_t dcol, bool accumulate) {
-    gemm_start<WAIT_TMA>(c, b_hi, b_lo, N, dcol, accumulate);
+// D[dcol, dcol + N) = A(tmem) W^T
+__device__ __forceinline__ void gemm_ts_start(WG& c, uint32_t b_hi, uint32_t b_lo, uint32_t N, uint32_t dcol, bool accumulate = false) {
+    gemm_sync(c);
+    if (c.t == 0) {
+        tc_fence_after();
+        issue_ts(c, b_hi, b_lo, N, dcol, accumulate);
+        umma_commit(c.mbar_mma);
+    }
+}
+__device__ __forceinline__ void gemm_ts(WG& c, uint32_t b_hi, uint32_t b_lo, uint32_t N, uint32_t dcol, bool accumulate = false) {
+    gemm_ts_start(c, b_hi, b_lo, N, dcol, accumulate);
+    gemm_finish(c);
+}
+// D[dcol, dcol + N) = A(landing buffer, after its TMA has completed) W^T
+__device__ __forceinline__ void gemm_ss(WG& c, uint32_t b_hi, uint32_t b_lo, uint32_t N, uint32_t dcol, bool accumulate = false) {
+    gemm_sync(c);
+    if (c.t == 0) {
+        tc_fence_after();
+        mbar_wait(c.mbar_tma, c.ph_tma);
+        issue_ss(c, b_hi, b_lo, N, dcol, accumulate);
+        umma_commit(c.mbar_mma);
+    }
+    c.ph_tma ^= 1u;
     gemm_finish(c);
 }
 
-// 8 consecutive features [8*chunk, 8*chunk+8) of this thread's row -> A planes
-__device__ __forceinline__ void a_store8(const WG& c, int chunk, const float (&v)[8]) {
-    uint32_t h[4], l[4];
+// 16 consecutive features [16 ks, 16 ks + 16) of this thread's row -> A operand columns of K step ks
+__device__ __forceinline__ void a_store16(const WG& c, int ks, const float (&v)[16]) {
+    uint32_t w[16];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) split2(v[2 * i], v[2 * i + 1], h[i], l[i]);
-    const uint32_t off = swz((uint32_t)c.t, (uint32_t)chunk);
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(c.a_hi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(c.a_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+    for (int i = 0; i < 8; ++i) split2(v[2 * i], v[2 * i + 1], w[i], w[8 + i]);
+    tmem_st16(c.tmem + ACOL + 16 * ks, w);
 }
 
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void lds16(const float* p, float (&b)[16]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 x = lds4(p + 4 * i);
+        b[4 * i] = x.x; b[4 * i + 1] = x.y; b[4 * i + 2] = x.z; b[4 * i + 3] = x.w;
+    }
+}
 
 // read-only global loads the compiler must not sink past the MMA waits (they are issued early to hide DRAM latency)
 __device__ __forceinline__ float4 ldg4_now(const float* p) {
@@ -117,111 +164,89 @@ __device__ __forceinline__ float ldg1_now(const float* p) {
     return v;
 }
 
-// accumulator columns [dcol, dcol+64) + bias (optionally ReLU) -> A planes
+// accumulator columns [dcol, dcol+64) + bias (optionally ReLU) -> A operand
 template <bool RELU>
 __device__ __forceinline__ void epilogue_to_a(const WG& c, uint32_t dcol, const float* __restrict__ bias_s) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        float v[16];
+        float v[16], bb[16];
         tmem_ld16_sync(c.tmem + dcol + q * 16, v);
+        lds16(bias_s + q * 16, bb);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const float4 b0 = lds4(bias_s + q * 16 + h * 8), b1 = lds4(bias_s + q * 16 + h * 8 + 4);
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            float o[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float x = v[h * 8 + j] + bb[j];
-                o[j] = RELU ? relu_nan(x) : x;
-            }
-            a_store8(c, q * 2 + h, o);
+        for (int j = 0; j < 16; ++j) {
+            const float x = v[j] + bb[j];
+            v[j] = RELU ? relu_nan(x) : x;
         }
+        a_store16(c, q, v);
     }
 }
 
-// K < 64 first layer on CUDA cores: relu(bias + sum_k feat[k] * wt[k][:]) -> A planes.  wt_s: fp32 [K][64] in smem
+// K < 64 first layer on CUDA cores: relu(bias + sum_k feat[k] * wt[k][:]) -> A operand.  wt_s: fp32 [K][64] in smem
 template <int K>
 __device__ __forceinline__ void first_layer_to_a(const WG& c, const float (&feat)[K], const float* __restrict__ wt_s,
                                                  const float* __restrict__ bias_s) {
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
-        float o[8];
-        const float4 b0 = lds4(bias_s + ch * 8), b1 = lds4(bias_s + ch * 8 + 4);
-        o[0] = b0.x; o[1] = b0.y; o[2] = b0.z; o[3] = b0.w; o[4] = b1.x; o[5] = b1.y; o[6] = b1.z; o[7] = b1.w;
+    for (int q = 0; q < 4; ++q) {
+        float o[16];
+        lds16(bias_s + q * 16, o);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const float4 w0 = lds4(wt_s + k * P + ch * 8), w1 = lds4(wt_s + k * P + ch * 8 + 4);
-            o[0] = fmaf(feat[k], w0.x, o[0]); o[1] = fmaf(feat[k], w0.y, o[1]); o[2] = fmaf(feat[k], w0.z, o[2]); o[3] = fmaf(feat[k], w0.w, o[3]);
-            o[4] = fmaf(feat[k], w1.x, o[4]); o[5] = fmaf(feat[k], w1.y, o[5]); o[6] = fmaf(feat[k], w1.z, o[6]); o[7] = fmaf(feat[k], w1.w, o[7]);
+            float w[16];
+            lds16(wt_s + k * P + q * 16, w);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = fmaf(feat[k], w[j], o[j]);
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = relu_nan(o[j]);
-        a_store8(c, ch, o);
+        for (int j = 0; j < 16; ++j) o[j] = relu_nan(o[j]);
+        a_store16(c, q, o);
     }
 }
 
-// (accumulator columns [dcol, dcol+64) + bias) * rowscale * AINV -> global fp32 [rows][64], staged through this
-// warpgroup's A buffer (free at this point) so that the global stores are full 256-byte rows.
-// Returns true if this thread's (valid) row holds a NaN.
-__device__ __forceinline__ bool epilogue_to_global(const WG& c, uint32_t dcol, const float* __restrict__ bias_s, float rowscale,
-                                                   float* __restrict__ dst, int64_t row0, int64_t rows) {
+// (accumulator columns [dcol, dcol+64) + bias) * rowscale -> this thread's row of the mu tile image, staged in the
+// warpgroup's landing buffer (free at this point: the tile's first GEMM has completed and the next tile's nb image has
+// not been requested yet): fp16 hi / lo planes, K-major SWIZZLE_128B, scaled domain — conflict-free 16-byte stores.
+// TO_A: the same values also become the next A operand (score head).  Returns true on NaN in a valid row.
+template <bool TO_A>
+__device__ __forceinline__ bool epilogue_to_mu(const WG& c, uint32_t dcol, const float* __restrict__ bias_s, float rowscale,
+                                               int64_t row0, int64_t rows) {
     bool bad = false;
-    rowscale *= AINV;                                  // leave the scaled operand domain
-    const uint32_t rbase = c.a_hi + (uint32_t)c.t * 256u;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        float v[16];
+        float v[16], bb[16];
         tmem_ld16_sync(c.tmem + dcol + q * 16, v);
+        lds16(bias_s + q * 16, bb);
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            const float4 b4 = lds4(bias_s + q * 16 + h * 4);
-            float o[4] = {(v[h * 4 + 0] + b4.x) * rowscale, (v[h * 4 + 1] + b4.y) * rowscale, (v[h * 4 + 2] + b4.z) * rowscale,
-                          (v[h * 4 + 3] + b4.w) * rowscale};
-            bad |= (o[0] != o[0]) | (o[1] != o[1]) | (o[2] != o[2]) | (o[3] != o[3]);
-            const uint32_t chunk = (uint32_t)(q * 4 + h);
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + ((chunk ^ ((uint32_t)c.t & 7u)) << 4)), "f"(o[0]),
-                         "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
+        for (int j = 0; j < 16; ++j) {
+            v[j] = (v[j] + bb[j]) * rowscale;
+            bad |= (v[j] != v[j]);
         }
-    }
-    wg_barrier(c);
-    const int lane = c.t & 31, warp = c.t >> 5;
+        uint32_t w[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const int rr = warp * 32 + 2 * i + (lane >> 4);
-        const uint32_t chunk = (uint32_t)(lane & 15);
-        float4 o;
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
-                     : "r"(c.a_hi + (uint32_t)rr * 256u + ((chunk ^ ((uint32_t)rr & 7u)) << 4)));
-        const int64_t grow = row0 + rr;
-        if (grow < rows) *(reinterpret_cast<float4*>(dst + grow * P) + chunk) = o;
+        for (int i = 0; i < 8; ++i) split2(v[2 * i], v[2 * i + 1], w[i], w[8 + i]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t off = swz((uint32_t)c.t, (uint32_t)(q * 2 + h));
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(c.land + off), "r"(w[4 * h]), "r"(w[4 * h + 1]),
+                         "r"(w[4 * h + 2]), "r"(w[4 * h + 3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(c.land + APLANE + off), "r"(w[8 + 4 * h]),
+                         "r"(w[8 + 4 * h + 1]), "r"(w[8 + 4 * h + 2]), "r"(w[8 + 4 * h + 3]) : "memory");
+        }
+        if (TO_A) tmem_st16(c.tmem + ACOL + 16 * q, w);
     }
-    fence_proxy_async();       // the next user of the A buffer may be the async proxy (TMA tile load)
-    wg_barrier(c);             // staging fully read before the A buffer is written again
     return bad && (row0 + c.t < rows);
 }
-
-// (accumulator columns [dcol, dcol+64) + bias) * rowscale * AINV -> this thread's row of global fp32 [rows][64], straight
-// from registers (16-byte pieces; the A buffer stays free for the next tile's TMA).  Returns true on NaN in a valid row.
-__device__ __forceinline__ bool epilogue_to_global_direct(const WG& c, uint32_t dcol, const float* __restrict__ bias_s, float rowscale,
-                                                          float* __restrict__ dst, int64_t row0, int64_t rows) {
-    bool bad = false;
-    rowscale *= AINV;
-    const bool ok = row0 + c.t < rows;
-    float4* out = reinterpret_cast<float4*>(dst + (row0 + c.t) * P);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        float v[16];
-        tmem_ld16_sync(c.tmem + dcol + q * 16, v);
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            const float4 b4 = lds4(bias_s + q * 16 + h * 4);
-            const float4 o = make_float4((v[h * 4 + 0] + b4.x) * rowscale, (v[h * 4 + 1] + b4.y) * rowscale,
-                                         (v[h * 4 + 2] + b4.z) * rowscale, (v[h * 4 + 3] + b4.w) * rowscale);
-            bad |= (o.x != o.x) | (o.y != o.y) | (o.z != o.z) | (o.w != o.w);
-            if (ok) out[q * 4 + h] = o;
+// the staged tile image -> global with one bulk store; then (optionally) the next tile's nb image into the same buffer
+__device__ __forceinline__ void commit_tile(const WG& c, void* dst_tile, const void* next_nb) {
+    fence_proxy_async();                 // the staging stores are generic-proxy writes, the bulk store reads through the async proxy
+    wg_barrier(c);
+    if (c.t == 0) {
+        bulk_s2g(dst_tile, c.land, ABUF);
+        if (next_nb != nullptr) {
+            bulk_wait_read();            // the store has read the buffer: it may be overwritten
+            mbar_expect_tx(c.mbar_tma, ABUF);
+            bulk_g2s(c.land, next_nb, ABUF, c.mbar_tma);
         }
     }
-    return bad && ok;
 }
 
 // (accumulator columns [dcol, dcol+64) + bias) * rowscale -> relax' layout [tile][16][128][4] (scaled domain, coalesced)
@@ -229,25 +254,25 @@ __device__ __forceinline__ void epilogue_to_rlx(const WG& c, uint32_t dcol, cons
                                                 float* __restrict__ dst_tile) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        float v[16];
+        float v[16], bb[16];
         tmem_ld16_sync(c.tmem + dcol + q * 16, v);
+        lds16(bias_s + q * 16, bb);
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
-            const float4 b4 = lds4(bias_s + q * 16 + h * 4);
-            const float4 o = make_float4((v[h * 4 + 0] + b4.x) * rowscale, (v[h * 4 + 1] + b4.y) * rowscale,
-                                         (v[h * 4 + 2] + b4.z) * rowscale, (v[h * 4 + 3] + b4.w) * rowscale);
+            const float4 o = make_float4((v[h * 4 + 0] + bb[h * 4 + 0]) * rowscale, (v[h * 4 + 1] + bb[h * 4 + 1]) * rowscale,
+                                         (v[h * 4 + 2] + bb[h * 4 + 2]) * rowscale, (v[h * 4 + 3] + bb[h * 4 + 3]) * rowscale);
             *reinterpret_cast<float4*>(dst_tile + ((size_t)(q * 4 + h) * TILE + c.t) * 4) = o;
         }
     }
 }
 
 // ---- shared-memory layout -----------------------------------------------------------------------------
-constexpr int MAXWG = 4;
-struct Tail {                   // small fp32 data after the weight planes and A buffers
+constexpr int NWG = 4;          // warpgroups (tiles in flight) per CTA: 4 x 128 tensor-memory columns
+struct Tail {                   // small fp32 data after the weight planes and landing buffers
     float bias[6][P];           // pre-scaled by ASCALE
     float w_small[2][8 * P];    // first-layer weights (K <= 7), transposed [K][64], pre-scaled
     float vec[P];
-    uint64_t mbar[1 + 2 * MAXWG];
+    uint64_t mbar[1 + 2 * NWG];
     uint32_t tmem_slot;
 };
 
@@ -258,15 +283,16 @@ struct CtaSetup {
     uint32_t tmem_base;
 };
 
-// common prologue: carve shared memory, allocate TMEM, init mbarriers, TMA the weight planes in
-template <int NWG, int NW>
+// common prologue: carve shared memory, allocate TMEM, init mbarriers, TMA the weight planes in.
+// LAND: the kernel has a 32 KB landing buffer per warpgroup after the weights.
+template <bool LAND, int NW>
 __device__ __forceinline__ CtaSetup cta_setup(uint32_t wbytes, const uint16_t* const (&wsrc)[NW], const uint32_t (&woff)[NW],
                                               const uint32_t (&wlen)[NW]) {
     extern __shared__ unsigned char smem_raw[];
     CtaSetup s;
     s.base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // pointer arithmetic keeps the shared address space
     s.w = smem_u32(s.base);
-    s.tail = reinterpret_cast<Tail*>(s.base + wbytes + NWG * ABUF);
+    s.tail = reinterpret_cast<Tail*>(s.base + wbytes + (LAND ? NWG * ABUF : 0));
     if (threadIdx.x == 0) {
         for (int i = 0; i < 1 + 2 * NWG; ++i) mbar_init(smem_u32(&s.tail->mbar[i]), 1);
         fence_mbar_init();
@@ -286,18 +312,17 @@ __device__ __forceinline__ CtaSetup cta_setup(uint32_t wbytes, const uint16_t* c
     }
     return s;
 }
-template <int NWG>
 __device__ __forceinline__ WG make_wg(const CtaSetup& s, uint32_t wbytes) {
     WG c;
     c.wg = threadIdx.x >> 7;
     c.t = threadIdx.x & 127;
-    c.a_hi = s.w + wbytes + (uint32_t)c.wg * ABUF;
-    c.a_lo = c.a_hi + APLANE;
+    c.land = s.w + wbytes + (uint32_t)c.wg * ABUF;
     c.mbar_mma = smem_u32(&s.tail->mbar[1 + 2 * c.wg]);
     c.mbar_tma = smem_u32(&s.tail->mbar[2 + 2 * c.wg]);
     c.ph_mma = 0;
     c.ph_tma = 0;
-    c.tmem = s.tmem_base + ((uint32_t)((c.t >> 5) * 32) << 16) + (uint32_t)c.wg * (512u / NWG);
+    c.tmem0 = (s.tmem_base & 0x0000FFFFu) + (uint32_t)c.wg * WG_COLS;
+    c.tmem = s.tmem_base + ((uint32_t)((c.t >> 5) * 32) << 16) + (uint32_t)c.wg * WG_COLS;
     return c;
 }
 __device__ __forceinline__ void cta_teardown(const CtaSetup& s) {
@@ -310,45 +335,56 @@ __device__ __forceinline__ void copy_vec(float* dst, const float* __restrict__ s
 }
 
 // ---- update: 3 GEMMs per tile (see the header) [+ score head] ---------------------------------------------
-constexpr int UPD_WG = 4;
 constexpr uint32_t UPD_W3 = 0, UPD_WC = 4 * WPLANE, UPD_W42 = 6 * WPLANE, UPD_FN = 8 * WPLANE, UPD_WBYTES = 10 * WPLANE;   // 80 KB
 
-__global__ void __launch_bounds__(128 * UPD_WG, 1) k_tc_update(GnnParams g, int backward, const float* __restrict__ lb,
-                                                               const float* __restrict__ ub, const uint16_t* __restrict__ nb_img,
-                                                               const float* __restrict__ rlx, float* __restrict__ mu_out,
-                                                               float* __restrict__ scores, int n, int64_t score_stride,
-                                                               int64_t score_off, int64_t rows, unsigned long long* nan_count) {
+__global__ void __launch_bounds__(128 * NWG, 1) k_tc_update(GnnParams g, int backward, const float* __restrict__ lb,
+                                                            const float* __restrict__ ub, const uint16_t* __restrict__ nb_img,
+                                                            const float* __restrict__ rlx, uint16_t* __restrict__ mu_out,
+                                                            float* __restrict__ scores, int n, int64_t score_stride,
+                                                            int64_t score_off, int64_t rows, unsigned long long* nan_count) {
     const int l3 = backward ? BC3 : FC3, l4b = backward ? BC4_1 : FC4_2, lc = backward ? T_BWD_C : T_FWD_C;
     const uint16_t* const wsrc[4] = {g.tc[l3], g.tcx_w[lc], g.tc[l4b], g.tc[FNODE]};
     const uint32_t woff[4] = {UPD_W3, UPD_WC, UPD_W42, UPD_FN};
     const uint32_t wlen[4] = {4 * WPLANE, 2 * WPLANE, 2 * WPLANE, 2 * WPLANE};
-    CtaSetup s = cta_setup<UPD_WG, 4>(UPD_WBYTES, wsrc, woff, wlen);
+    CtaSetup s = cta_setup<true, 4>(UPD_WBYTES, wsrc, woff, wlen);
     Tail& tl = *s.tail;
     copy_vec(tl.bias[0], g.bias[l3], P); copy_vec(tl.bias[1], g.tcx_b[lc], P); copy_vec(tl.bias[2], g.bias[l4b], P);
     copy_vec(tl.bias[3], g.bias[FNODE], P); copy_vec(tl.vec, g.wt[FSCORE], P, 1.0f);
     const float bscore = g.bias[FSCORE][0];
     __syncthreads();
     mbar_wait(smem_u32(&tl.mbar[0]), 0);                      // weight planes have landed
-    WG c = make_wg<UPD_WG>(s, UPD_WBYTES);
+    WG c = make_wg(s, UPD_WBYTES);
     const uint32_t W = s.w;
     const int64_t ntiles = (rows + TILE - 1) / TILE;
     bool bad = false;
-    const int64_t tile_step = (int64_t)gridDim.x * UPD_WG;
-    int64_t tile = (int64_t)blockIdx.x * UPD_WG + c.wg;
-    if (tile < ntiles) tma_tile(c, nb_img + (size_t)tile * (ABUF / 2));          // first tile's nb image
+    GNNB_TR_DECL;
+    const int64_t tile_step = (int64_t)gridDim.x * NWG;
+    int64_t tile = (int64_t)blockIdx.x * NWG + c.wg;
+    if (tile < ntiles) {                                      // first tile's nb image; its relax' tile towards L2
+        tma_tile(c, nb_img + (size_t)tile * (ABUF / 2));
+        if (c.t == 0) prefetch_l2(rlx + (size_t)tile * (TILE * P), TILE * P * 4);
+    }
     for (; tile < ntiles; tile += tile_step) {
         const int64_t row0 = tile * TILE, grow = row0 + c.t;
         const bool has_next = tile + tile_step < ntiles;
         float l = 0.f, u = 1.f;
         if (grow < rows) { l = ldg1_now(lb + grow); u = ldg1_now(ub + grow); }
+        GNNB_TR(0);
         // D[0:128) = nb [W3a; W3b]^T
-        gemm<true>(c, W + UPD_W3, W + UPD_W3 + 2 * WPLANE, 128, 0, false);
+        gemm_ss(c, W + UPD_W3, W + UPD_W3 + 2 * WPLANE, 128, 0);
+        GNNB_TR(1);
+        // the next tile's inputs move towards L2 while this tile runs its chain (its nb image lands after this tile's
+        // results have left the landing buffer, see commit_tile)
+        if (has_next && c.t == 0) {
+            prefetch_l2(nb_img + (size_t)(tile + tile_step) * (ABUF / 2), ABUF);
+            prefetch_l2(rlx + (size_t)(tile + tile_step) * (TILE * P), TILE * P * 4);
+        }
         const Ratio q = compute_ratio(l, u);
         const float gate = (q.r0 != 0.0f) ? 1.0f : 0.0f;
-        // h3 = relu(r0 * D[0:64) + r1 * D[64:128) + b3) -> A   (graph_conv.py:169-170 / 331-336)
+        // h3 = relu(r0 * D[0:64) + r1 * D[64:128) + b3) -> A, in place over the consumed columns (graph_conv.py:169-170 / 331-336)
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
-            float a[16], b[16];
+            float a[16], b[16], bb[16];
             {
                 uint32_t ra[16], rb[16];
                 tmem_ld16(c.tmem + qd * 16, ra);
@@ -356,18 +392,14 @@ __global__ void __launch_bounds__(128 * UPD_WG, 1) k_tc_update(GnnParams g, int 
                 tmem_wait16(ra, a);
                 tmem_wait16(rb, b);
             }
+            lds16(tl.bias[0] + qd * 16, bb);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const float4 b0 = lds4(tl.bias[0] + qd * 16 + h * 8), b1 = lds4(tl.bias[0] + qd * 16 + h * 8 + 4);
-                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                float o[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = relu_nan(fmaf(q.r0, a[h * 8 + j], fmaf(q.r1, b[h * 8 + j], bb[j])));
-                a_store8(c, qd * 2 + h, o);
-            }
+            for (int j = 0; j < 16; ++j) a[j] = relu_nan(fmaf(q.r0, a[j], fmaf(q.r1, b[j], bb[j])));
+            a_store16(c, qd, a);
         }
-        // D[0:64) = h3 Wc^T; meanwhile fetch this row's relax' (coalesced by layout)
-        gemm_start<false>(c, W + UPD_WC, W + UPD_WC + WPLANE, 64, 0, false);
+        GNNB_TR(2);
+        // D[64:128) = h3 Wc^T; meanwhile fetch this row's relax' (coalesced by layout, L2-resident by prefetch)
+        gemm_ts_start(c, W + UPD_WC, W + UPD_WC + WPLANE, 64, DCOL);
         float4 rx[16];
         {
             const float* rt = rlx + (size_t)tile * (TILE * P);
@@ -375,71 +407,66 @@ __global__ void __launch_bounds__(128 * UPD_WG, 1) k_tc_update(GnnParams g, int 
             for (int i = 0; i < 16; ++i) rx[i] = ldg4_now(rt + ((size_t)i * TILE + c.t) * 4);
         }
         gemm_finish(c);
+        GNNB_TR(3);
         // g = relu(D + relax' + bc) -> A
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
-            float v[16];
-            tmem_ld16_sync(c.tmem + qd * 16, v);
+            float v[16], bb[16];
+            tmem_ld16_sync(c.tmem + DCOL + qd * 16, v);
+            lds16(tl.bias[1] + qd * 16, bb);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const float4 b0 = lds4(tl.bias[1] + qd * 16 + h * 8), b1 = lds4(tl.bias[1] + qd * 16 + h * 8 + 4);
-                const float4 x0 = rx[qd * 4 + h * 2], x1 = rx[qd * 4 + h * 2 + 1];
-                float o[8] = {v[h * 8 + 0] + x0.x + b0.x, v[h * 8 + 1] + x0.y + b0.y, v[h * 8 + 2] + x0.z + b0.z, v[h * 8 + 3] + x0.w + b0.w,
-                              v[h * 8 + 4] + x1.x + b1.x, v[h * 8 + 5] + x1.y + b1.y, v[h * 8 + 6] + x1.z + b1.z, v[h * 8 + 7] + x1.w + b1.w};
-#pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = relu_nan(o[j]);
-                a_store8(c, qd * 2 + h, o);
+            for (int h = 0; h < 4; ++h) {
+                const float4 x = rx[qd * 4 + h];
+                v[h * 4 + 0] = relu_nan(v[h * 4 + 0] + x.x + bb[h * 4 + 0]);
+                v[h * 4 + 1] = relu_nan(v[h * 4 + 1] + x.y + bb[h * 4 + 1]);
+                v[h * 4 + 2] = relu_nan(v[h * 4 + 2] + x.z + bb[h * 4 + 2]);
+                v[h * 4 + 3] = relu_nan(v[h * 4 + 3] + x.w + bb[h * 4 + 3]);
             }
+            a_store16(c, qd, v);
         }
+        GNNB_TR(4);
         // D[64:128) = g W4_2^T;  mu = (D + b) * (r0 != 0) -> global
-        gemm(c, W + UPD_W42, W + UPD_W42 + WPLANE, 64, 64, false);
-        // the A buffer is free again: fetch the next tile's nb image while this tile's results leave
-        if (scores == nullptr && has_next) tma_tile(c, nb_img + (size_t)(tile + tile_step) * (ABUF / 2));
-        bad |= epilogue_to_global_direct(c, 64, tl.bias[2], gate, mu_out, row0, rows);
-        if (scores != nullptr) {      // score head on the new embeddings (graph_conv.py:448-449)
-#pragma unroll
-            for (int qd = 0; qd < 4; ++qd) {
-                float v[16];
-                tmem_ld16_sync(c.tmem + 64 + qd * 16, v);
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const float4 b0 = lds4(tl.bias[2] + qd * 16 + h * 8), b1 = lds4(tl.bias[2] + qd * 16 + h * 8 + 4);
-                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                    float o[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) o[j] = (v[h * 8 + j] + bb[j]) * gate;
-                    a_store8(c, qd * 2 + h, o);
-                }
-            }
-            gemm(c, W + UPD_FN, W + UPD_FN + WPLANE, 64, 0, false);
-            if (has_next) tma_tile(c, nb_img + (size_t)(tile + tile_step) * (ABUF / 2));
+        gemm_ts(c, W + UPD_W42, W + UPD_W42 + WPLANE, 64, DCOL);
+        GNNB_TR(5);
+        const void* next_nb = has_next ? nb_img + (size_t)(tile + tile_step) * (ABUF / 2) : nullptr;
+        if (scores == nullptr) {
+            bad |= epilogue_to_mu<false>(c, DCOL, tl.bias[2], gate, row0, rows);
+            commit_tile(c, mu_out + (size_t)tile * (ABUF / 2), next_nb);
+        } else {      // score head on the new embeddings (graph_conv.py:448-449)
+            bad |= epilogue_to_mu<true>(c, DCOL, tl.bias[2], gate, row0, rows);
+            commit_tile(c, mu_out + (size_t)tile * (ABUF / 2), next_nb);
+            gemm_ts(c, W + UPD_FN, W + UPD_FN + WPLANE, 64, DCOL);
             float sc = 0.f;
 #pragma unroll
             for (int qd = 0; qd < 4; ++qd) {
-                float v[16];
-                tmem_ld16_sync(c.tmem + qd * 16, v);
+                float v[16], bb[16], ww[16];
+                tmem_ld16_sync(c.tmem + DCOL + qd * 16, v);
+                lds16(tl.bias[3] + qd * 16, bb);
+                lds16(tl.vec + qd * 16, ww);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) sc = fmaf(relu_nan(v[j] + tl.bias[3][qd * 16 + j]), tl.vec[qd * 16 + j], sc);
+                for (int j = 0; j < 16; ++j) sc = fmaf(relu_nan(v[j] + bb[j]), ww[j], sc);
             }
             if (grow < rows) scores[(grow / n) * score_stride + score_off + (grow % n)] = fmaf(sc, AINV, bscore);
         }
+        GNNB_TR(6);
+        GNNB_TR_NEXT();
     }
+    GNNB_TR_PRINT("update[top gemm1 epi1 gemm2 epi2 gemm3 epi3]", 7);
     if (bad) atomicAdd(nan_count, 1ULL);
+    if (c.t == 0) bulk_wait_all();       // the last tile's bulk store still reads this CTA's shared memory
     cta_teardown(s);
 }
 
 // ---- relax: round-independent part of the fc4 / bc4 pre-activation of a hidden layer --------------------------
-constexpr int RLX_WG = 2;
 constexpr uint32_t RLX_FR = 0, RLX_BC11 = 2 * WPLANE, RLX_BC12 = 4 * WPLANE, RLX_BC2 = 6 * WPLANE, RLX_BR = 12 * WPLANE;
 constexpr uint32_t RLX_WBYTES = 14 * WPLANE;
-constexpr uint32_t RD1 = 0, RD2 = 192;         // TMEM columns inside a warpgroup's 256
 
-__global__ void __launch_bounds__(128 * RLX_WG, 1) k_tc_relax(GnnParams g, NodeInputs in, float* __restrict__ rlx_f,
-                                                              float* __restrict__ rlx_b) {
+__global__ void __launch_bounds__(128 * NWG, 1) k_tc_relax(GnnParams g, NodeInputs in, float* __restrict__ rlx_f,
+                                                           float* __restrict__ rlx_b) {
     const uint16_t* const wsrc[5] = {g.tcx_w[T_FWD_R], g.tc[BC1_1], g.tc[BC1_2], g.tc[BC2], g.tcx_w[T_BWD_R]};
     const uint32_t woff[5] = {RLX_FR, RLX_BC11, RLX_BC12, RLX_BC2, RLX_BR};
     const uint32_t wlen[5] = {2 * WPLANE, 2 * WPLANE, 2 * WPLANE, 6 * WPLANE, 2 * WPLANE};
-    CtaSetup s = cta_setup<RLX_WG, 5>(RLX_WBYTES, wsrc, woff, wlen);
+    CtaSetup s = cta_setup<false, 5>(RLX_WBYTES, wsrc, woff, wlen);
     Tail& tl = *s.tail;
     copy_vec(tl.bias[0], g.tcx_b[T_FWD_R], P); copy_vec(tl.bias[1], g.bias[BC1_1], P); copy_vec(tl.bias[2], g.bias[BC1_2], P);
     copy_vec(tl.bias[3], g.bias[BC2], P); copy_vec(tl.bias[4], g.tcx_b[T_BWD_R], P);
@@ -447,10 +474,10 @@ __global__ void __launch_bounds__(128 * RLX_WG, 1) k_tc_relax(GnnParams g, NodeI
     copy_vec(tl.bias[5], g.bias[FC1], P); copy_vec(tl.vec, g.bias[BC1], P);
     __syncthreads();
     mbar_wait(smem_u32(&tl.mbar[0]), 0);
-    WG c = make_wg<RLX_WG>(s, RLX_WBYTES);
+    WG c = make_wg(s, RLX_WBYTES);
     const uint32_t W = s.w;
     const int64_t ntiles = (in.rows + TILE - 1) / TILE;
-    for (int64_t tile = (int64_t)blockIdx.x * RLX_WG + c.wg; tile < ntiles; tile += (int64_t)gridDim.x * RLX_WG) {
+    for (int64_t tile = (int64_t)blockIdx.x * NWG + c.wg; tile < ntiles; tile += (int64_t)gridDim.x * NWG) {
         const int64_t row0 = tile * TILE, grow = row0 + c.t;
         float l = 0.f, u = 1.f, d1 = 0.f, d2 = 0.f, pp = 0.f, po = 0.f, bs = 0.f;
         if (grow < in.rows) {
@@ -465,129 +492,151 @@ __global__ void __launch_bounds__(128 * RLX_WG, 1) k_tc_relax(GnnParams g, NodeI
             const float feat[7] = {q.beta, l, u, d1 - d2, pp, po, bs};
             first_layer_to_a<7>(c, feat, tl.w_small[0], tl.bias[5]);
         }
-        gemm(c, W + RLX_FR, W + RLX_FR + WPLANE, 64, RD2, false);
-        epilogue_to_rlx(c, RD2, tl.bias[0], q.amb, rlx_f + (size_t)tile * (TILE * P));
+        gemm_ts(c, W + RLX_FR, W + RLX_FR + WPLANE, 64, DCOL);
+        epilogue_to_rlx(c, DCOL, tl.bias[0], q.amb, rlx_f + (size_t)tile * (TILE * P));
         // backward (graph_conv.py:273-293, :344)
         {
             const float feat[7] = {l, u, q.beta, -d2 + d1, po, pp, bs};
             first_layer_to_a<7>(c, feat, tl.w_small[1], tl.vec);
         }
-        gemm(c, W + RLX_BC11, W + RLX_BC11 + WPLANE, 64, RD2, false);
-        epilogue_to_a<true>(c, RD2, tl.bias[1]);
-        gemm(c, W + RLX_BC12, W + RLX_BC12 + WPLANE, 64, RD2, false);
-        epilogue_to_a<false>(c, RD2, tl.bias[2]);                                  // s1
-        gemm(c, W + RLX_BC2, W + RLX_BC2 + 3 * WPLANE, 192, RD1, false);          // s1 [W2a; W2b; W2c]^T
-        {   // relu(Da + (-d2) Db + d1 Dc + b2) -> A
+        gemm_ts(c, W + RLX_BC11, W + RLX_BC11 + WPLANE, 64, DCOL);
+        epilogue_to_a<true>(c, DCOL, tl.bias[1]);
+        gemm_ts(c, W + RLX_BC12, W + RLX_BC12 + WPLANE, 64, DCOL);
+        epilogue_to_a<false>(c, DCOL, tl.bias[2]);                                  // s1
+        // relu(s1 W2a^T - d2 s1 W2b^T + d1 s1 W2c^T + b2): the three 64-wide products share the A operand and the one
+        // accumulator, so they run one after the other with the running sum in registers
+        float acc[64];
+        gemm_ts(c, W + RLX_BC2, W + RLX_BC2 + 3 * WPLANE, 64, DCOL);
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+            float v[16], bb[16];
+            tmem_ld16_sync(c.tmem + DCOL + qd * 16, v);
+            lds16(tl.bias[3] + qd * 16, bb);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[qd * 16 + j] = v[j] + bb[j];
+        }
+        gemm_ts(c, W + RLX_BC2 + WPLANE, W + RLX_BC2 + 4 * WPLANE, 64, DCOL);
+        {
             const float nd2 = -d2;
 #pragma unroll
             for (int qd = 0; qd < 4; ++qd) {
-                float a[16], b[16], cc[16];
-                {
-                    uint32_t ra[16], rb[16], rc[16];
-                    tmem_ld16(c.tmem + RD1 + qd * 16, ra);
-                    tmem_ld16(c.tmem + RD1 + 64 + qd * 16, rb);
-                    tmem_ld16(c.tmem + RD1 + 128 + qd * 16, rc);
-                    tmem_wait16(ra, a);
-                    tmem_wait16(rb, b);
-                    tmem_wait16(rc, cc);
-                }
+                float v[16];
+                tmem_ld16_sync(c.tmem + DCOL + qd * 16, v);
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float o[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        o[j] = relu_nan(a[h * 8 + j] + fmaf(nd2, b[h * 8 + j], fmaf(d1, cc[h * 8 + j], tl.bias[3][qd * 16 + h * 8 + j])));
-                    a_store8(c, qd * 2 + h, o);
-                }
+                for (int j = 0; j < 16; ++j) acc[qd * 16 + j] = fmaf(nd2, v[j], acc[qd * 16 + j]);
             }
         }
-        gemm(c, W + RLX_BR, W + RLX_BR + WPLANE, 64, RD2, false);
-        epilogue_to_rlx(c, RD2, tl.bias[4], q.amb, rlx_b + (size_t)tile * (TILE * P));
+        gemm_ts(c, W + RLX_BC2 + 2 * WPLANE, W + RLX_BC2 + 5 * WPLANE, 64, DCOL);
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+            float v[16];
+            tmem_ld16_sync(c.tmem + DCOL + qd * 16, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = relu_nan(fmaf(d1, v[j], acc[qd * 16 + j]));
+            a_store16(c, qd, v);
+        }
+        gemm_ts(c, W + RLX_BR, W + RLX_BR + WPLANE, 64, DCOL);
+        epilogue_to_rlx(c, DCOL, tl.bias[4], q.amb, rlx_b + (size_t)tile * (TILE * P));
     }
     cta_teardown(s);
 }
 
 // ---- input embedding: mu0 = inp_f_1(relu(inp_f([l0, x, u0])))   (graph_conv.py:90-95) ---------------------------
-constexpr int EMB_WG = 4;
 constexpr uint32_t EMB_WBYTES = 2 * WPLANE;
 
-__global__ void __launch_bounds__(128 * EMB_WG, 1) k_tc_input_embed(GnnParams g, const float* __restrict__ lb0,
-                                                                    const float* __restrict__ x, const float* __restrict__ ub0,
-                                                                    float* __restrict__ mu0, int64_t rows) {
+__global__ void __launch_bounds__(128 * NWG, 1) k_tc_input_embed(GnnParams g, const float* __restrict__ lb0,
+                                                                 const float* __restrict__ x, const float* __restrict__ ub0,
+                                                                 uint16_t* __restrict__ mu0, int64_t rows) {
     const uint16_t* const wsrc[1] = {g.tc[INP_F_1]};
     const uint32_t woff[1] = {0};
     const uint32_t wlen[1] = {2 * WPLANE};
-    CtaSetup s = cta_setup<EMB_WG, 1>(EMB_WBYTES, wsrc, woff, wlen);
+    CtaSetup s = cta_setup<true, 1>(EMB_WBYTES, wsrc, woff, wlen);
     Tail& tl = *s.tail;
     copy_vec(tl.bias[0], g.bias[INP_F_1], P); copy_vec(tl.bias[5], g.bias[INP_F], P); copy_vec(tl.w_small[0], g.wt[INP_F], 3 * P);
     __syncthreads();
     mbar_wait(smem_u32(&tl.mbar[0]), 0);
-    WG c = make_wg<EMB_WG>(s, EMB_WBYTES);
+    WG c = make_wg(s, EMB_WBYTES);
     const int64_t ntiles = (rows + TILE - 1) / TILE;
-    for (int64_t tile = (int64_t)blockIdx.x * EMB_WG + c.wg; tile < ntiles; tile += (int64_t)gridDim.x * EMB_WG) {
+    for (int64_t tile = (int64_t)blockIdx.x * NWG + c.wg; tile < ntiles; tile += (int64_t)gridDim.x * NWG) {
         const int64_t row0 = tile * TILE, grow = row0 + c.t;
         float feat[3] = {0.f, 0.f, 0.f};
         if (grow < rows) { feat[0] = lb0[grow]; feat[1] = x[grow]; feat[2] = ub0[grow]; }
         first_layer_to_a<3>(c, feat, tl.w_small[0], tl.bias[5]);
-        gemm(c, s.w, s.w + WPLANE, 64, 0, false);
-        epilogue_to_global(c, 0, tl.bias[0], 1.0f, mu0, row0, rows);
+        if (c.t == 0) bulk_wait_read();          // the previous tile's bulk store has read the staging buffer
+        gemm_ts(c, s.w, s.w + WPLANE, 64, DCOL);
+        epilogue_to_mu<false>(c, DCOL, tl.bias[0], 1.0f, row0, rows);
+        commit_tile(c, mu0 + (size_t)tile * (ABUF / 2), nullptr);
     }
+    if (c.t == 0) bulk_wait_all();
     cta_teardown(s);
 }
 
 // ---- input update: mu0 = inp_b2_2(relu(inp_b2([inp_b_1(relu(inp_b([l0,u0]))), nb])))   (graph_conv.py:380-385) ----
 //      = inp_b2_2(relu(Wi relu(inp_b([l0,u0])) + Wn nb + bi)),  Wi = W_b2[:, :64] W_b1,  Wn = W_b2[:, 64:]
-constexpr int INU_WG = 4;
 constexpr uint32_t INU_WI = 0, INU_WN = 2 * WPLANE, INU_B22 = 4 * WPLANE, INU_WBYTES = 6 * WPLANE;
 
-__global__ void __launch_bounds__(128 * INU_WG, 1) k_tc_input_update(GnnParams g, const float* __restrict__ lb0,
-                                                                     const float* __restrict__ ub0, const uint16_t* __restrict__ nb_img,
-                                                                     float* __restrict__ mu0, int64_t rows) {
+__global__ void __launch_bounds__(128 * NWG, 1) k_tc_input_update(GnnParams g, const float* __restrict__ lb0,
+                                                                  const float* __restrict__ ub0, const uint16_t* __restrict__ nb_img,
+                                                                  uint16_t* __restrict__ mu0, int64_t rows) {
     const uint16_t* const wsrc[3] = {g.tcx_w[T_INP_C], g.tcx_w[T_INP_NB], g.tc[INP_B2_2]};
     const uint32_t woff[3] = {INU_WI, INU_WN, INU_B22};
     const uint32_t wlen[3] = {2 * WPLANE, 2 * WPLANE, 2 * WPLANE};
-    CtaSetup s = cta_setup<INU_WG, 3>(INU_WBYTES, wsrc, woff, wlen);
+    CtaSetup s = cta_setup<true, 3>(INU_WBYTES, wsrc, woff, wlen);
     Tail& tl = *s.tail;
     copy_vec(tl.bias[0], g.tcx_b[T_INP_C], P); copy_vec(tl.bias[1], g.bias[INP_B2_2], P);
     copy_vec(tl.bias[5], g.bias[INP_B], P); copy_vec(tl.w_small[0], g.wt[INP_B], 2 * P);
     __syncthreads();
     mbar_wait(smem_u32(&tl.mbar[0]), 0);
-    WG c = make_wg<INU_WG>(s, INU_WBYTES);
+    WG c = make_wg(s, INU_WBYTES);
     const uint32_t W = s.w;
     const int64_t ntiles = (rows + TILE - 1) / TILE;
-    for (int64_t tile = (int64_t)blockIdx.x * INU_WG + c.wg; tile < ntiles; tile += (int64_t)gridDim.x * INU_WG) {
+    const int64_t tile_step = (int64_t)gridDim.x * NWG;
+    int64_t tile = (int64_t)blockIdx.x * NWG + c.wg;
+    if (tile < ntiles) tma_tile(c, nb_img + (size_t)tile * (ABUF / 2));
+    for (; tile < ntiles; tile += tile_step) {
         const int64_t row0 = tile * TILE, grow = row0 + c.t;
         float feat[2] = {0.f, 0.f};
         if (grow < rows) { feat[0] = lb0[grow]; feat[1] = ub0[grow]; }
         first_layer_to_a<2>(c, feat, tl.w_small[0], tl.bias[5]);
-        gemm(c, W + INU_WI, W + INU_WI + WPLANE, 64, 0, false);                         // Wi relu(inp_b(.))
-        fence_proxy_async();
-        wg_barrier(c);
-        tma_tile(c, nb_img + (size_t)tile * (ABUF / 2));
-        gemm<true>(c, W + INU_WN, W + INU_WN + WPLANE, 64, 0, true);                     // + Wn nb
-        epilogue_to_a<true>(c, 0, tl.bias[0]);
-        gemm(c, W + INU_B22, W + INU_B22 + WPLANE, 64, 64, false);
-        epilogue_to_global(c, 64, tl.bias[1], 1.0f, mu0, row0, rows);
+        // D = Wi relu(inp_b(.)) + Wn nb: both products into the one accumulator, one commit
+        gemm_sync(c);
+        if (c.t == 0) {
+            tc_fence_after();
+            issue_ts(c, W + INU_WI, W + INU_WI + WPLANE, 64, DCOL, false);
+            mbar_wait(c.mbar_tma, c.ph_tma);
+            issue_ss(c, W + INU_WN, W + INU_WN + WPLANE, 64, DCOL, true);
+            umma_commit(c.mbar_mma);
+        }
+        c.ph_tma ^= 1u;
+        gemm_finish(c);
+        const bool has_next = tile + tile_step < ntiles;
+        if (has_next && c.t == 0) prefetch_l2(nb_img + (size_t)(tile + tile_step) * (ABUF / 2), ABUF);
+        epilogue_to_a<true>(c, DCOL, tl.bias[0]);
+        gemm_ts(c, W + INU_B22, W + INU_B22 + WPLANE, 64, DCOL);
+        epilogue_to_mu<false>(c, DCOL, tl.bias[1], 1.0f, row0, rows);
+        commit_tile(c, mu0 + (size_t)tile * (ABUF / 2), has_next ? nb_img + (size_t)(tile + tile_step) * (ABUF / 2) : nullptr);
     }
+    if (c.t == 0) bulk_wait_all();
     cta_teardown(s);
 }
 
-constexpr size_t smem_bytes(uint32_t wbytes, int nwg) { return 1024 + wbytes + nwg * ABUF + sizeof(Tail); }
+constexpr size_t smem_bytes(uint32_t wbytes, bool land) { return 1024 + wbytes + (land ? NWG * ABUF : 0) + sizeof(Tail); }
 
-int grid_for(int64_t rows, int nwg) {
-    const int64_t tiles = (rows + TILE - 1) / TILE, ctas = (tiles + nwg - 1) / nwg;
+int grid_for(int64_t rows) {
+    const int64_t tiles = (rows + TILE - 1) / TILE, ctas = (tiles + NWG - 1) / NWG;
     return (int)(ctas < 1 ? 1 : (ctas < 148 ? ctas : 148));
 }
 
-// fp16 tile image of nb (hi + lo planes, scaled domain) -> fp32 [rows][64]; debugging snapshots only
-__global__ void k_unpack_tile_image(const uint16_t* __restrict__ img, float* __restrict__ out, int64_t rows) {
+// tile images (hi + lo planes, scaled domain) -> fp32 [rows][64]; debugging snapshots and the output-node kernel's view
+__global__ void k_unpack_tile_image(const uint16_t* __restrict__ img, float* __restrict__ out, int64_t rows, int piece_major) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // one thread per (row, 8-channel chunk)
     if (i >= rows * 8) return;
     const int64_t row = i >> 3;
     const int chunk = (int)(i & 7);
     const int64_t tile = row / TILE;
     const uint32_t r = (uint32_t)(row % TILE);
-    const __half* hi = reinterpret_cast<const __half*>(img) + tile * (ABUF / 2) + swz(r, (uint32_t)chunk) / 2;
+    const uint32_t off = piece_major ? (uint32_t)chunk * NB_PIECE + r * 16u : swz(r, (uint32_t)chunk);
+    const __half* hi = reinterpret_cast<const __half*>(img) + tile * (ABUF / 2) + off / 2;
     const __half* lo = hi + APLANE / 2;
     for (int j = 0; j < 8; ++j) out[row * P + chunk * 8 + j] = (__half2float(hi[j]) + __half2float(lo[j])) * AINV;
 }
@@ -598,10 +647,10 @@ bool tc_available() { return true; }
 
 int tc_init() {
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(k_tc_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(UPD_WBYTES, UPD_WG))) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_tc_relax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(RLX_WBYTES, RLX_WG))) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_tc_input_embed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(EMB_WBYTES, EMB_WG))) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_tc_input_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(INU_WBYTES, INU_WG))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_tc_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(UPD_WBYTES, true))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_tc_relax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(RLX_WBYTES, false))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_tc_input_embed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(EMB_WBYTES, true))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_tc_input_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(INU_WBYTES, true))) != cudaSuccess) return e;
     return 0;
 }
 
@@ -625,35 +674,35 @@ int64_t tc_pack_weight(const float* w, int K, uint16_t* dst) {
 }
 
 void tc_relax(const GnnParams& g, const NodeInputs& in, float* relax_f, float* relax_b, cudaStream_t st, int64_t* launches) {
-    k_tc_relax<<<grid_for(in.rows, RLX_WG), 128 * RLX_WG, smem_bytes(RLX_WBYTES, RLX_WG), st>>>(g, in, relax_f, relax_b);
+    k_tc_relax<<<grid_for(in.rows), 128 * NWG, smem_bytes(RLX_WBYTES, false), st>>>(g, in, relax_f, relax_b);
     ++*launches;
 }
 
 void tc_update(const GnnParams& g, bool backward, const float* lb, const float* ub, const float* nb, const float* relax,
                float* mu_out, float* scores, int n, int64_t score_stride, int64_t score_off, int64_t rows,
                unsigned long long* nan_count, cudaStream_t st, int64_t* launches) {
-    k_tc_update<<<grid_for(rows, UPD_WG), 128 * UPD_WG, smem_bytes(UPD_WBYTES, UPD_WG), st>>>(
-        g, backward ? 1 : 0, lb, ub, reinterpret_cast<const uint16_t*>(nb), relax, mu_out, scores, n, score_stride, score_off, rows,
-        nan_count);
+    k_tc_update<<<grid_for(rows), 128 * NWG, smem_bytes(UPD_WBYTES, true), st>>>(
+        g, backward ? 1 : 0, lb, ub, reinterpret_cast<const uint16_t*>(nb), relax, reinterpret_cast<uint16_t*>(mu_out), scores, n,
+        score_stride, score_off, rows, nan_count);
     ++*launches;
 }
 
 void tc_input_embed(const GnnParams& g, const float* lb0, const float* x, const float* ub0, float* mu0, int64_t rows,
                     cudaStream_t st, int64_t* launches) {
-    k_tc_input_embed<<<grid_for(rows, EMB_WG), 128 * EMB_WG, smem_bytes(EMB_WBYTES, EMB_WG), st>>>(g, lb0, x, ub0, mu0, rows);
+    k_tc_input_embed<<<grid_for(rows), 128 * NWG, smem_bytes(EMB_WBYTES, true), st>>>(g, lb0, x, ub0, reinterpret_cast<uint16_t*>(mu0), rows);
     ++*launches;
 }
 
 void tc_input_update(const GnnParams& g, const float* lb0, const float* ub0, const float* nb, float* mu0, int64_t rows,
                      cudaStream_t st, int64_t* launches) {
-    k_tc_input_update<<<grid_for(rows, INU_WG), 128 * INU_WG, smem_bytes(INU_WBYTES, INU_WG), st>>>(
-        g, lb0, ub0, reinterpret_cast<const uint16_t*>(nb), mu0, rows);
+    k_tc_input_update<<<grid_for(rows), 128 * NWG, smem_bytes(INU_WBYTES, true), st>>>(
+        g, lb0, ub0, reinterpret_cast<const uint16_t*>(nb), reinterpret_cast<uint16_t*>(mu0), rows);
     ++*launches;
 }
 
-void tc_unpack_tile_image(const float* img, float* out, int64_t rows, cudaStream_t st) {
+void tc_unpack_tile_image(const float* img, float* out, int64_t rows, bool piece_major, cudaStream_t st) {
     const int64_t n = rows * 8;
-    k_unpack_tile_image<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(img), out, rows);
+    k_unpack_tile_image<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(img), out, rows, piece_major ? 1 : 0);
 }
 
 }  // namespace gnnb

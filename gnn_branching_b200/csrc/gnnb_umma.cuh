@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_fp16.h>
+#include <stdio.h>
 #include <string.h>
 
 #include "gnnb_common.cuh"
@@ -10,8 +11,6 @@ namespace gnnb {
 namespace tcx {
 
 constexpr int TILE = 128;                        // nodes per tile = UMMA M
-constexpr int WGS = 2;                           // warpgroups (tiles in flight) per CTA
-constexpr int NTHREADS = 128 * WGS;
 constexpr uint32_t WPLANE = 64 * 64 * 2;         // one 64(n) x 64(k) fp16 weight plane: 8 KB
 constexpr uint32_t APLANE = TILE * 64 * 2;       // one A plane: 16 KB
 constexpr uint32_t ABUF = 2 * APLANE;            // hi + lo
@@ -87,6 +86,16 @@ __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t b
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem desc]^T: the A operand is read from tensor memory (lane = row, 32-bit column j holds
+// k = 2j in its low half and k = 2j + 1 in its high half; one K = 16 instruction reads 8 columns)
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t mbar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
 }
@@ -113,6 +122,20 @@ __device__ __forceinline__ void tmem_ld16_sync(uint32_t taddr, float (&v)[16]) {
     tmem_wait16(r, v);
 }
 
+// 16 consecutive 32-bit columns of this thread's TMEM lane <- registers (asynchronous: tmem_st_wait before the data is used)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// L2 prefetch of a contiguous global range (one thread issues it; bytes is a multiple of 16)
+__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -123,12 +146,67 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                                 // layout type SWIZZLE_128B, bits [61,64)
     return d;
 }
+// K-major operand without swizzle ("piece-major" tile image): 16-byte pieces (8 fp16 along K) of consecutive rows are
+// contiguous, so a core matrix (8 rows x 16 B) is 128 contiguous bytes; 8-row groups are `sbo` bytes apart and the
+// pieces (K direction) `lbo` bytes apart (cute::UMMA::make_umma_desc<Major::K>, LayoutType::INTERLEAVE)
+__device__ __forceinline__ uint64_t make_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// MN-major SWIZZLE_128B operand: 64-element (128 B) rows along N, 8 K-rows per 1024 B group (SBO), further 64-wide N
+// blocks `lbo_bytes` apart (cute::UMMA::make_umma_desc<Major::MN>)
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// ---- tile images in global memory (private workspace formats of the tensor-core kernels) ------------------------------
+// Every per-node tensor of the tensor-core path lives in tiles of 128 consecutive global rows (row = subdomain * n + node),
+// 32 KB per tile = [fp16 hi plane 16 KB][fp16 lo plane 16 KB], values in the scaled domain (x ASCALE):
+//   mu image  each plane is the K-major SWIZZLE_128B image (byte offset swz(row, chunk)): a row's 64 channels are 128
+//             contiguous bytes (16-byte chunks XOR-permuted), written with one bulk store per tile, gathered row-wise;
+//   nb image  each plane is piece-major (byte offset piece * 2048 + row * 16): rows of one piece are contiguous, so the
+//             propagation epilogue (thread = row) stores coalesced and the update kernels read it as a no-swizzle A operand.
+constexpr uint32_t NB_PIECE = TILE * 16;          // 2 KB: one 16-byte piece of all 128 rows
+
+// shared -> global bulk copy (async proxy reads shared memory: generic-proxy writes need fence.proxy.async first)
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// 16-byte asynchronous copy global -> shared (L2 only), zero-filled when !valid; completion is tracked by an mbarrier
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16u : 0u) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint32_t mbar) {      // arrives when this thread's earlier cp.async have landed
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+
 // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (bits [4,6) = 1), A/B fp16 (format 0), both K-major, M = 128
 __device__ __forceinline__ uint32_t make_idesc(uint32_t N) {
     return (1u << 4) | ((N >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
 }
 
-__device__ __forceinline__ float relu_nan(float x) { return (x != x) ? x : fmaxf(x, 0.f); }   // F.relu keeps NaN
+__device__ __forceinline__ float relu_nan(float x) {      // F.relu keeps NaN: max.NaN propagates it (fmaxf would not)
+    float y;
+    asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 // (a, b) -> packed fp16x2 hi and lo words; element a sits at the lower address
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
@@ -137,6 +215,22 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+
+// ---- phase tracing (debug builds with -DGNNB_TRACE only; scripts/trace_build.sh) ---------------------------------
+// One thread of one warpgroup records clock64() at fixed points of its first tiles and prints the deltas at kernel end.
+#ifdef GNNB_TRACE
+#define GNNB_TR_DECL long long tr_[16 * 12]; int tr_n_ = 0; const bool tr_on_ = (blockIdx.x == 1 && (threadIdx.x & 127) == 0 && (threadIdx.x >> 7) == 1)
+#define GNNB_TR(i) do { if (tr_on_ && tr_n_ < 16) tr_[tr_n_ * 12 + (i)] = clock64(); } while (0)
+#define GNNB_TR_NEXT() do { if (tr_on_ && tr_n_ < 16) ++tr_n_; } while (0)
+#define GNNB_TR_PRINT(name, npts) do { if (tr_on_) { for (int a_ = 0; a_ < tr_n_; ++a_) { printf("TRACE %s it %d:", name, a_); \
+    for (int b_ = 1; b_ < (npts); ++b_) printf(" %lld", tr_[a_ * 12 + b_] - tr_[a_ * 12 + b_ - 1]); \
+    if (a_ + 1 < tr_n_) printf(" | next %lld", tr_[(a_ + 1) * 12] - tr_[a_ * 12 + (npts) - 1]); printf("\n"); } } } while (0)
+#else
+#define GNNB_TR_DECL
+#define GNNB_TR(i) do {} while (0)
+#define GNNB_TR_NEXT() do {} while (0)
+#define GNNB_TR_PRINT(name, npts) do {} while (0)
+#endif
 
 }  // namespace tcx
 }  // namespace gnnb
