@@ -48,6 +48,7 @@ struct gnnb_ctx {
     bool ws_host_staging = false;
     float* d_ws = nullptr;
     std::vector<float*> mu, relax_f, relax_b;
+    std::vector<int32_t*> amb_cnt, amb_base, amb_rows;   // compaction of the ambiguous rows of each hidden layer (tensor-core path)
     float* nb = nullptr;
     float* ws_scores = nullptr;
     float* ws_best = nullptr;
@@ -105,6 +106,11 @@ int ensure_workspace(gnnb_ctx* ctx, int Bc, bool host_staging) {
     auto tiled = [](size_t rows) { return ((rows + 127) / 128) * 128; };
     for (int k = 0; k <= L + 1; ++k) o_mu[k] = take(tiled((size_t)Bc * ctx->n[k]) * P);
     for (int k = 1; k <= L; ++k) { o_rf[k] = take(tiled((size_t)Bc * ctx->n[k]) * P); o_rb[k] = take(tiled((size_t)Bc * ctx->n[k]) * P); }
+    std::vector<size_t> o_ac(L + 1), o_ab(L + 1), o_ar(L + 1);
+    for (int k = 1; k <= L; ++k) {
+        const size_t rows = (size_t)Bc * ctx->n[k], nt = (rows + 127) / 128;
+        o_ac[k] = take(nt + 1); o_ab[k] = take(nt + 1); o_ar[k] = take(rows);
+    }
     const size_t o_nb = take(tiled((size_t)Bc * nmax) * P);
     const size_t o_sc = take((size_t)Bc * ctx->n_hidden);
     const size_t o_best = take(Bc), o_idx = take(Bc);
@@ -124,6 +130,12 @@ int ensure_workspace(gnnb_ctx* ctx, int Bc, bool host_staging) {
     ctx->mu.assign(L + 2, nullptr); ctx->relax_f.assign(L + 1, nullptr); ctx->relax_b.assign(L + 1, nullptr);
     for (int k = 0; k <= L + 1; ++k) ctx->mu[k] = base + o_mu[k];
     for (int k = 1; k <= L; ++k) { ctx->relax_f[k] = base + o_rf[k]; ctx->relax_b[k] = base + o_rb[k]; }
+    ctx->amb_cnt.assign(L + 1, nullptr); ctx->amb_base.assign(L + 1, nullptr); ctx->amb_rows.assign(L + 1, nullptr);
+    for (int k = 1; k <= L; ++k) {
+        ctx->amb_cnt[k] = reinterpret_cast<int32_t*>(base + o_ac[k]);
+        ctx->amb_base[k] = reinterpret_cast<int32_t*>(base + o_ab[k]);
+        ctx->amb_rows[k] = reinterpret_cast<int32_t*>(base + o_ar[k]);
+    }
     ctx->nb = base + o_nb; ctx->ws_scores = base + o_sc; ctx->ws_best = base + o_best;
     ctx->ws_idx = reinterpret_cast<int32_t*>(base + o_idx);
     ctx->s_lb.assign(L + 2, nullptr); ctx->s_ub.assign(L + 2, nullptr);
@@ -219,9 +231,10 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
     // round-independent relaxation features of every hidden layer
     for (int k = 1; k <= L; ++k) {
         NodeInputs ni{in.lb[k], in.ub[k], in.dual[k - 1], in.pre[k - 1], in.post[k - 1], ctx->layers[k - 1].bias_node,
-                      ctx->n[k], (int64_t)Bc * ctx->n[k]};
+                      ctx->n[k], (int64_t)Bc * ctx->n[k], ctx->amb_rows[k], ctx->amb_base[k]};
         {
             ProfScope ps(ctx, GNNB_K_RELAX, ni.rows, st);
+            if (tc) amb_compact(in.lb[k], in.ub[k], ni.rows, ctx->amb_cnt[k], ctx->amb_base[k], ctx->amb_rows[k], st, lc);
             if (tc) tc_relax(g, ni, ctx->relax_f[k], ctx->relax_b[k], st, lc);
             else simt_relax(g, ni, ctx->relax_f[k], ctx->relax_b[k], st, lc);
         }
@@ -250,7 +263,7 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
             TRY(snap_img(ctx, name("t%d_fwd_nb%d", t, k), ctx->nb, rows, true, st));
             {
                 ProfScope ps(ctx, GNNB_K_UPDATE_FWD, rows, st);
-                if (tc) tc_update(g, false, in.lb[k], in.ub[k], ctx->nb, ctx->relax_f[k], ctx->mu[k], nullptr, ctx->n[k], 0, 0, rows, ctx->d_nan, st, lc);
+                if (tc) tc_update(g, false, in.lb[k], in.ub[k], ctx->nb, ctx->relax_f[k], ctx->amb_base[k], ctx->mu[k], nullptr, ctx->n[k], 0, 0, rows, ctx->d_nan, st, lc);
                 else simt_update(g, false, in.lb[k], in.ub[k], ctx->nb, ctx->relax_f[k], ctx->mu[k], nullptr, ctx->n[k], 0, 0, rows, ctx->d_nan, st, lc);
             }
             TRY(snap_img(ctx, name("t%d_fwd_mu%d", t, k), ctx->mu[k], rows, false, st));
@@ -274,7 +287,7 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
             float* sc = last ? scores : nullptr;
             {
                 ProfScope ps(ctx, last ? GNNB_K_UPDATE_BWD_SCORE : GNNB_K_UPDATE_BWD, rows, st);
-                if (tc) tc_update(g, true, in.lb[k], in.ub[k], ctx->nb, ctx->relax_b[k], ctx->mu[k], sc, ctx->n[k], ctx->n_hidden, ctx->hidden_off[k], rows, ctx->d_nan, st, lc);
+                if (tc) tc_update(g, true, in.lb[k], in.ub[k], ctx->nb, ctx->relax_b[k], ctx->amb_base[k], ctx->mu[k], sc, ctx->n[k], ctx->n_hidden, ctx->hidden_off[k], rows, ctx->d_nan, st, lc);
                 else simt_update(g, true, in.lb[k], in.ub[k], ctx->nb, ctx->relax_b[k], ctx->mu[k], sc, ctx->n[k], ctx->n_hidden, ctx->hidden_off[k], rows, ctx->d_nan, st, lc);
             }
             TRY(snap_img(ctx, name("t%d_bwd_mu%d", t, k), ctx->mu[k], rows, false, st));

@@ -69,6 +69,10 @@ struct NodeInputs {
     const float* bias_node;   // [n]
     int n;                    // nodes per subdomain in this layer
     int64_t rows;
+    // tensor-core path only: the ambiguous rows (beta > 0, the only ones whose relaxation features are non-zero,
+    // graph_conv.py:161, 293), compacted in row order by amb_compact()
+    const int32_t* amb_rows;  // [amb_base[ntiles]] global row of each compacted slot
+    const int32_t* amb_base;  // [ntiles + 1] first slot of each tile of 128 rows; amb_base[ntiles] = number of ambiguous rows
 };
 
 // ---- launchers (each enqueues on `st` and bumps *launches) -------------------------------------
@@ -87,8 +91,12 @@ int simt_init();  // opt-in shared memory sizes; returns cudaError_t
 // tcgen05 node kernels (gnnb_tc.cu) — same contracts as the SIMT ones
 void tc_relax(const GnnParams& g, const NodeInputs& in, float* relax_f, float* relax_b, cudaStream_t st, int64_t* launches);
 void tc_update(const GnnParams& g, bool backward, const float* lb, const float* ub, const float* nb, const float* relax,
-               float* mu_out, float* scores, int n, int64_t score_stride, int64_t score_off, int64_t rows,
+               const int32_t* amb_base, float* mu_out, float* scores, int n, int64_t score_stride, int64_t score_off, int64_t rows,
                unsigned long long* nan_count, cudaStream_t st, int64_t* launches);
+// slot of every ambiguous row of a layer, in row order: amb_base[tile] (+ the rank inside the tile), amb_rows[slot] = row;
+// cnt is scratch of ntiles + 1 ints (three small launches: count per tile, scan, fill)
+void amb_compact(const float* lb, const float* ub, int64_t rows, int32_t* cnt, int32_t* amb_base, int32_t* amb_rows,
+                 cudaStream_t st, int64_t* launches);
 void tc_input_embed(const GnnParams& g, const float* lb0, const float* x, const float* ub0, float* mu0, int64_t rows,
                     cudaStream_t st, int64_t* launches);
 void tc_input_update(const GnnParams& g, const float* lb0, const float* ub0, const float* nb, float* mu0, int64_t rows,

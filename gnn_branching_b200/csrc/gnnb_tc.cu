@@ -274,6 +274,7 @@ struct Tail {                   // small fp32 data after the weight planes and l
     float vec[P];
     uint64_t mbar[1 + 2 * NWG];
     uint32_t tmem_slot;
+    int32_t wcnt[NWG][4];       // ambiguous rows per warp of the warpgroup's current tile
 };
 
 struct CtaSetup {
@@ -339,7 +340,8 @@ constexpr uint32_t UPD_W3 = 0, UPD_WC = 4 * WPLANE, UPD_W42 = 6 * WPLANE, UPD_FN
 
 __global__ void __launch_bounds__(128 * NWG, 1) k_tc_update(GnnParams g, int backward, const float* __restrict__ lb,
                                                             const float* __restrict__ ub, const uint16_t* __restrict__ nb_img,
-                                                            const float* __restrict__ rlx, uint16_t* __restrict__ mu_out,
+                                                            const float* __restrict__ rlx, const int32_t* __restrict__ amb_base,
+                                                            uint16_t* __restrict__ mu_out,
                                                             float* __restrict__ scores, int n, int64_t score_stride,
                                                             int64_t score_off, int64_t rows, unsigned long long* nan_count) {
     const int l3 = backward ? BC3 : FC3, l4b = backward ? BC4_1 : FC4_2, lc = backward ? T_BWD_C : T_FWD_C;
@@ -360,27 +362,29 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_update(GnnParams g, int bac
     GNNB_TR_DECL;
     const int64_t tile_step = (int64_t)gridDim.x * NWG;
     int64_t tile = (int64_t)blockIdx.x * NWG + c.wg;
-    if (tile < ntiles) {                                      // first tile's nb image; its relax' tile towards L2
-        tma_tile(c, nb_img + (size_t)tile * (ABUF / 2));
-        if (c.t == 0) prefetch_l2(rlx + (size_t)tile * (TILE * P), TILE * P * 4);
-    }
+    if (tile < ntiles) tma_tile(c, nb_img + (size_t)tile * (ABUF / 2));      // first tile's nb image
     for (; tile < ntiles; tile += tile_step) {
         const int64_t row0 = tile * TILE, grow = row0 + c.t;
         const bool has_next = tile + tile_step < ntiles;
         float l = 0.f, u = 1.f;
         if (grow < rows) { l = ldg1_now(lb + grow); u = ldg1_now(ub + grow); }
+        const int slot0 = __ldg(amb_base + tile);
+        const Ratio q = compute_ratio(l, u);
+        const float gate = (q.r0 != 0.0f) ? 1.0f : 0.0f;
+        // slot of this row's relax' = first slot of the tile + number of ambiguous rows before it (amb_compact keeps row order)
+        const bool amb = (q.amb != 0.0f) && grow < rows;
+        const unsigned bal = __ballot_sync(0xffffffffu, amb);
+        if ((c.t & 31) == 0) tl.wcnt[c.wg][c.t >> 5] = __popc(bal);
         GNNB_TR(0);
         // D[0:128) = nb [W3a; W3b]^T
         gemm_ss(c, W + UPD_W3, W + UPD_W3 + 2 * WPLANE, 128, 0);
         GNNB_TR(1);
-        // the next tile's inputs move towards L2 while this tile runs its chain (its nb image lands after this tile's
-        // results have left the landing buffer, see commit_tile)
-        if (has_next && c.t == 0) {
-            prefetch_l2(nb_img + (size_t)(tile + tile_step) * (ABUF / 2), ABUF);
-            prefetch_l2(rlx + (size_t)(tile + tile_step) * (TILE * P), TILE * P * 4);
-        }
-        const Ratio q = compute_ratio(l, u);
-        const float gate = (q.r0 != 0.0f) ? 1.0f : 0.0f;
+        // the next tile's nb image moves towards L2 while this tile runs its chain (it lands in shared memory after this
+        // tile's results have left the landing buffer, see commit_tile)
+        if (has_next && c.t == 0) prefetch_l2(nb_img + (size_t)(tile + tile_step) * (ABUF / 2), ABUF);
+        int slot = slot0 + __popc(bal & ((1u << (c.t & 31)) - 1u));
+#pragma unroll
+        for (int w = 0; w < 3; ++w) slot += (w < (c.t >> 5)) ? tl.wcnt[c.wg][w] : 0;
         // h3 = relu(r0 * D[0:64) + r1 * D[64:128) + b3) -> A, in place over the consumed columns (graph_conv.py:169-170 / 331-336)
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
@@ -402,9 +406,9 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_update(GnnParams g, int bac
         gemm_ts_start(c, W + UPD_WC, W + UPD_WC + WPLANE, 64, DCOL);
         float4 rx[16];
         {
-            const float* rt = rlx + (size_t)tile * (TILE * P);
+            const float* rt = rlx + (size_t)(slot >> 7) * (TILE * P) + (size_t)(slot & (TILE - 1)) * 4;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) rx[i] = ldg4_now(rt + ((size_t)i * TILE + c.t) * 4);
+            for (int i = 0; i < 16; ++i) rx[i] = amb ? ldg4_now(rt + (size_t)i * (TILE * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         gemm_finish(c);
         GNNB_TR(3);
@@ -476,11 +480,14 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_relax(GnnParams g, NodeInpu
     mbar_wait(smem_u32(&tl.mbar[0]), 0);
     WG c = make_wg(s, RLX_WBYTES);
     const uint32_t W = s.w;
-    const int64_t ntiles = (in.rows + TILE - 1) / TILE;
+    // only the ambiguous rows have non-zero relaxation features: walk them in compacted order (slot = tile * 128 + t)
+    const int64_t namb = __ldg(in.amb_base + (in.rows + TILE - 1) / TILE);
+    const int64_t ntiles = (namb + TILE - 1) / TILE;
     for (int64_t tile = (int64_t)blockIdx.x * NWG + c.wg; tile < ntiles; tile += (int64_t)gridDim.x * NWG) {
-        const int64_t row0 = tile * TILE, grow = row0 + c.t;
+        const int64_t slot = tile * TILE + c.t;
         float l = 0.f, u = 1.f, d1 = 0.f, d2 = 0.f, pp = 0.f, po = 0.f, bs = 0.f;
-        if (grow < in.rows) {
+        if (slot < namb) {
+            const int64_t grow = __ldg(in.amb_rows + slot);
             l = in.lb[grow]; u = in.ub[grow];
             d1 = in.dual[grow * 3 + 1]; d2 = in.dual[grow * 3 + 2];
             pp = in.prim_pre[grow]; po = in.prim_post[grow];
@@ -641,7 +648,56 @@ __global__ void k_unpack_tile_image(const uint16_t* __restrict__ img, float* __r
     for (int j = 0; j < 8; ++j) out[row * P + chunk * 8 + j] = (__half2float(hi[j]) + __half2float(lo[j])) * AINV;
 }
 
+// ---- compaction of the ambiguous rows (three small launches per layer and chunk) ---------------------------------
+__global__ void __launch_bounds__(TILE) k_amb_count(const float* __restrict__ lb, const float* __restrict__ ub, int64_t rows,
+                                                    int32_t* __restrict__ cnt) {
+    const int64_t row = (int64_t)blockIdx.x * TILE + threadIdx.x;
+    const bool amb = row < rows && compute_ratio(lb[row], ub[row]).amb != 0.0f;
+    const int total = __syncthreads_count(amb);
+    if (threadIdx.x == 0) cnt[blockIdx.x] = total;
+}
+// exclusive scan of cnt[0 .. n) into base[0 .. n], base[n] = total; one block
+__global__ void __launch_bounds__(1024) k_amb_scan(const int32_t* __restrict__ cnt, int32_t* __restrict__ base, int n) {
+    __shared__ int32_t part[1024];
+    const int per = (n + 1023) / 1024, lo = threadIdx.x * per, hi = min(n, lo + per);
+    int32_t sum = 0;
+    for (int i = lo; i < hi; ++i) sum += cnt[i];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        const int32_t v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int32_t run = part[threadIdx.x] - sum;
+    for (int i = lo; i < hi; ++i) { base[i] = run; run += cnt[i]; }
+    if (threadIdx.x == 1023) base[n] = part[1023];
+}
+__global__ void __launch_bounds__(TILE) k_amb_fill(const float* __restrict__ lb, const float* __restrict__ ub, int64_t rows,
+                                                   const int32_t* __restrict__ base, int32_t* __restrict__ amb_rows) {
+    __shared__ int32_t wc[4];
+    const int64_t row = (int64_t)blockIdx.x * TILE + threadIdx.x;
+    const bool amb = row < rows && compute_ratio(lb[row], ub[row]).amb != 0.0f;
+    const unsigned bal = __ballot_sync(0xffffffffu, amb);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) wc[warp] = __popc(bal);
+    __syncthreads();
+    int slot = base[blockIdx.x] + __popc(bal & ((1u << lane) - 1u));
+    for (int w = 0; w < warp; ++w) slot += wc[w];
+    if (amb) amb_rows[slot] = (int32_t)row;
+}
+
 }  // namespace
+
+void amb_compact(const float* lb, const float* ub, int64_t rows, int32_t* cnt, int32_t* amb_base, int32_t* amb_rows,
+                 cudaStream_t st, int64_t* launches) {
+    const int ntiles = (int)((rows + TILE - 1) / TILE);
+    k_amb_count<<<ntiles, TILE, 0, st>>>(lb, ub, rows, cnt);
+    k_amb_scan<<<1, 1024, 0, st>>>(cnt, amb_base, ntiles);
+    k_amb_fill<<<ntiles, TILE, 0, st>>>(lb, ub, rows, amb_base, amb_rows);
+    *launches += 3;
+}
 
 bool tc_available() { return true; }
 
@@ -679,10 +735,10 @@ void tc_relax(const GnnParams& g, const NodeInputs& in, float* relax_f, float* r
 }
 
 void tc_update(const GnnParams& g, bool backward, const float* lb, const float* ub, const float* nb, const float* relax,
-               float* mu_out, float* scores, int n, int64_t score_stride, int64_t score_off, int64_t rows,
+               const int32_t* amb_base, float* mu_out, float* scores, int n, int64_t score_stride, int64_t score_off, int64_t rows,
                unsigned long long* nan_count, cudaStream_t st, int64_t* launches) {
     k_tc_update<<<grid_for(rows), 128 * NWG, smem_bytes(UPD_WBYTES, true), st>>>(
-        g, backward ? 1 : 0, lb, ub, reinterpret_cast<const uint16_t*>(nb), relax, reinterpret_cast<uint16_t*>(mu_out), scores, n,
+        g, backward ? 1 : 0, lb, ub, reinterpret_cast<const uint16_t*>(nb), relax, amb_base, reinterpret_cast<uint16_t*>(mu_out), scores, n,
         score_stride, score_off, rows, nan_count);
     ++*launches;
 }
