@@ -53,9 +53,20 @@ struct gnnb_ctx {
     float* ws_scores = nullptr;
     float* ws_best = nullptr;
     int32_t* ws_idx = nullptr;
-    // staged copies of host inputs
-    std::vector<float*> s_lb, s_ub, s_dual, s_pre, s_post;
-    float *s_pout = nullptr, *s_pin = nullptr, *s_wp = nullptr, *s_bp = nullptr, *s_mask = nullptr;
+    // staged copies of host inputs: two sets, so that the copies of the next chunk (copy stream) overlap the kernels of
+    // the current one (caller's stream)
+    struct Staging {
+        std::vector<float*> lb, ub, dual, pre, post;
+        float *pout = nullptr, *pin = nullptr, *wp = nullptr, *bp = nullptr, *mask = nullptr;
+        float* best = nullptr;
+        int32_t* idx = nullptr;
+        float* scores = nullptr;
+    } stg[2];
+    float* res_best = nullptr;      // winners of a whole host-buffer call (one device->host copy at the end, so that a
+    int32_t* res_idx = nullptr;     // pageable result buffer cannot stall the wave pipeline)
+    int res_cap = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     unsigned long long* d_nan = nullptr;
     // debugging snapshots
     std::map<std::string, std::pair<float*, int64_t>> snaps;
@@ -114,16 +125,21 @@ int ensure_workspace(gnnb_ctx* ctx, int Bc, bool host_staging) {
     const size_t o_nb = take(tiled((size_t)Bc * nmax) * P);
     const size_t o_sc = take((size_t)Bc * ctx->n_hidden);
     const size_t o_best = take(Bc), o_idx = take(Bc);
-    size_t o_pout = 0, o_pin = 0, o_wp = 0, o_bp = 0, o_mask = 0;
+    struct StgOff { std::vector<size_t> lb, ub, du, pr, po; size_t pout, pin, wp, bp, mask, best, idx, sc; } so[2];
     if (host_staging) {
-        for (int k = 0; k <= L + 1; ++k) { o_lb[k] = take((size_t)Bc * ctx->n[k]); o_ub[k] = take((size_t)Bc * ctx->n[k]); }
-        for (int k = 0; k < L; ++k) {
-            o_du[k] = take((size_t)Bc * ctx->n[k + 1] * 3);
-            o_pr[k] = take((size_t)Bc * ctx->n[k + 1]);
-            o_po[k] = take((size_t)Bc * ctx->n[k + 1]);
+        for (int i = 0; i < 2; ++i) {
+            StgOff& o = so[i];
+            o.lb.resize(L + 2); o.ub.resize(L + 2); o.du.resize(L); o.pr.resize(L); o.po.resize(L);
+            for (int k = 0; k <= L + 1; ++k) { o.lb[k] = take((size_t)Bc * ctx->n[k]); o.ub[k] = take((size_t)Bc * ctx->n[k]); }
+            for (int k = 0; k < L; ++k) {
+                o.du[k] = take((size_t)Bc * ctx->n[k + 1] * 3);
+                o.pr[k] = take((size_t)Bc * ctx->n[k + 1]);
+                o.po[k] = take((size_t)Bc * ctx->n[k + 1]);
+            }
+            o.pout = take(Bc); o.pin = take((size_t)Bc * ctx->n[0]); o.wp = take((size_t)Bc * ctx->n[L]);
+            o.bp = take(Bc); o.mask = take((size_t)Bc * ctx->n_hidden);
+            o.best = take(Bc); o.idx = take(Bc); o.sc = take((size_t)Bc * ctx->n_hidden);
         }
-        o_pout = take(Bc); o_pin = take((size_t)Bc * ctx->n[0]); o_wp = take((size_t)Bc * ctx->n[L]);
-        o_bp = take(Bc); o_mask = take((size_t)Bc * ctx->n_hidden);
     }
     CU(cudaMalloc(&ctx->d_ws, total * sizeof(float)));
     float* base = ctx->d_ws;
@@ -138,13 +154,23 @@ int ensure_workspace(gnnb_ctx* ctx, int Bc, bool host_staging) {
     }
     ctx->nb = base + o_nb; ctx->ws_scores = base + o_sc; ctx->ws_best = base + o_best;
     ctx->ws_idx = reinterpret_cast<int32_t*>(base + o_idx);
-    ctx->s_lb.assign(L + 2, nullptr); ctx->s_ub.assign(L + 2, nullptr);
-    ctx->s_dual.assign(L, nullptr); ctx->s_pre.assign(L, nullptr); ctx->s_post.assign(L, nullptr);
     if (host_staging) {
-        for (int k = 0; k <= L + 1; ++k) { ctx->s_lb[k] = base + o_lb[k]; ctx->s_ub[k] = base + o_ub[k]; }
-        for (int k = 0; k < L; ++k) { ctx->s_dual[k] = base + o_du[k]; ctx->s_pre[k] = base + o_pr[k]; ctx->s_post[k] = base + o_po[k]; }
-        ctx->s_pout = base + o_pout; ctx->s_pin = base + o_pin; ctx->s_wp = base + o_wp; ctx->s_bp = base + o_bp;
-        ctx->s_mask = base + o_mask;
+        for (int i = 0; i < 2; ++i) {
+            gnnb_ctx::Staging& g = ctx->stg[i];
+            const StgOff& o = so[i];
+            g.lb.assign(L + 2, nullptr); g.ub.assign(L + 2, nullptr); g.dual.assign(L, nullptr); g.pre.assign(L, nullptr); g.post.assign(L, nullptr);
+            for (int k = 0; k <= L + 1; ++k) { g.lb[k] = base + o.lb[k]; g.ub[k] = base + o.ub[k]; }
+            for (int k = 0; k < L; ++k) { g.dual[k] = base + o.du[k]; g.pre[k] = base + o.pr[k]; g.post[k] = base + o.po[k]; }
+            g.pout = base + o.pout; g.pin = base + o.pin; g.wp = base + o.wp; g.bp = base + o.bp; g.mask = base + o.mask;
+            g.best = base + o.best; g.idx = reinterpret_cast<int32_t*>(base + o.idx); g.scores = base + o.sc;
+        }
+        if (!ctx->copy_stream) {
+            CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; ++i) {
+                CU(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+                CU(cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming));
+            }
+        }
     }
     ctx->ws_cap = Bc;
     ctx->ws_host_staging = host_staging;
@@ -357,6 +383,10 @@ void gnnb_destroy(gnnb_ctx* ctx) {
     if (ctx->d_nan) cudaFree(ctx->d_nan);
     for (PropPlan* p : ctx->plan_fwd) prop_plan_free(p);
     for (PropPlan* p : ctx->plan_bwd) prop_plan_free(p);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->res_best) cudaFree(ctx->res_best);
+    if (ctx->res_idx) cudaFree(ctx->res_idx);
+    for (int i = 0; i < 2; ++i) { if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]); if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]); }
     for (auto& p : ctx->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     delete ctx;
@@ -580,52 +610,76 @@ int gnnb_score(gnnb_ctx* ctx, const gnnb_frontier* in, float* best_score, int32_
     cudaStream_t st = (cudaStream_t)stream;
     const int L = (int)ctx->layers.size();
     const bool host = in->mem == GNNB_MEM_HOST;
-    int chunk = ctx->chunk > 0 ? ctx->chunk : 512;
+    // subdomains per wave: large waves amortise launches and tails; with host buffers smaller waves let the copies of
+    // wave i + 1 (copy stream, second staging set) run under the kernels of wave i
+    int chunk = ctx->chunk > 0 ? ctx->chunk : (host ? 512 : 1024);
     if (chunk > in->B) chunk = in->B;
     TRY(ensure_workspace(ctx, chunk, host));
     const std::vector<int>& n = ctx->n;
+    if (host && ctx->res_cap < in->B) {
+        if (ctx->res_best) cudaFree(ctx->res_best);
+        if (ctx->res_idx) cudaFree(ctx->res_idx);
+        ctx->res_best = nullptr; ctx->res_idx = nullptr; ctx->res_cap = 0;
+        CU(cudaMalloc(&ctx->res_best, (size_t)in->B * sizeof(float)));
+        CU(cudaMalloc(&ctx->res_idx, (size_t)in->B * sizeof(int32_t)));
+        ctx->res_cap = in->B;
+    }
 
-    for (int c0 = 0; c0 < in->B; c0 += chunk) {
-        const int Bc = (in->B - c0) < chunk ? (in->B - c0) : chunk;
+    // host buffers: the first waves are small so that the kernels start after a short copy, then the wave size doubles
+    // up to `chunk` (the copy engine outruns the kernels, so later waves always find their inputs staged)
+    int wave = 0, ramp = host ? (chunk / 4 > 64 ? chunk / 4 : (chunk < 64 ? chunk : 64)) : chunk;
+    for (int c0 = 0, Bc = 0; c0 < in->B; c0 += Bc, ++wave) {
+        Bc = (in->B - c0) < ramp ? (in->B - c0) : ramp;
+        ramp = ramp * 2 > chunk ? chunk : ramp * 2;
+        gnnb_ctx::Staging& sg = ctx->stg[wave & 1];
+        cudaStream_t cs = host ? ctx->copy_stream : st;
+        if (host && wave >= 2) CU(cudaStreamWaitEvent(cs, ctx->ev_free[wave & 1], 0));   // this staging set's previous wave is done
         ChunkPtrs cp;
         cp.lb.resize(L + 2); cp.ub.resize(L + 2); cp.dual.resize(L); cp.pre.resize(L); cp.post.resize(L);
         auto stage = [&](const float* src, float* dst, size_t per_domain) -> const float* {
             const float* p = src + (size_t)c0 * per_domain;
             if (!host) return p;
-            cudaMemcpyAsync(dst, p, (size_t)Bc * per_domain * sizeof(float), cudaMemcpyHostToDevice, st);
+            cudaMemcpyAsync(dst, p, (size_t)Bc * per_domain * sizeof(float), cudaMemcpyHostToDevice, cs);
             return dst;
         };
         for (int k = 0; k <= L + 1; ++k) {
             if (!in->lb[k] || !in->ub[k]) return fail(ctx, GNNB_ERR_INVALID, "null bound array");
-            cp.lb[k] = stage(in->lb[k], ctx->s_lb[k], n[k]);
-            cp.ub[k] = stage(in->ub[k], ctx->s_ub[k], n[k]);
+            cp.lb[k] = stage(in->lb[k], host ? sg.lb[k] : nullptr, n[k]);
+            cp.ub[k] = stage(in->ub[k], host ? sg.ub[k] : nullptr, n[k]);
         }
         for (int k = 0; k < L; ++k) {
             if (!in->dual[k] || !in->prim_pre[k] || !in->prim_post[k]) return fail(ctx, GNNB_ERR_INVALID, "null dual/primal array");
-            cp.dual[k] = stage(in->dual[k], ctx->s_dual[k], (size_t)n[k + 1] * 3);
-            cp.pre[k] = stage(in->prim_pre[k], ctx->s_pre[k], n[k + 1]);
-            cp.post[k] = stage(in->prim_post[k], ctx->s_post[k], n[k + 1]);
+            cp.dual[k] = stage(in->dual[k], host ? sg.dual[k] : nullptr, (size_t)n[k + 1] * 3);
+            cp.pre[k] = stage(in->prim_pre[k], host ? sg.pre[k] : nullptr, n[k + 1]);
+            cp.post[k] = stage(in->prim_post[k], host ? sg.post[k] : nullptr, n[k + 1]);
         }
-        cp.pout = stage(in->prim_out, ctx->s_pout, 1);
-        cp.pin = stage(in->primal_input, ctx->s_pin, n[0]);
-        cp.wp = stage(in->wp, ctx->s_wp, n[L]);
-        cp.bp = stage(in->bp, ctx->s_bp, 1);
-        cp.mask = stage(in->mask, ctx->s_mask, ctx->n_hidden);
+        cp.pout = stage(in->prim_out, sg.pout, 1);
+        cp.pin = stage(in->primal_input, sg.pin, n[0]);
+        cp.wp = stage(in->wp, sg.wp, n[L]);
+        cp.bp = stage(in->bp, sg.bp, 1);
+        cp.mask = stage(in->mask, sg.mask, ctx->n_hidden);
         CU(cudaGetLastError());
+        if (host) {
+            CU(cudaEventRecord(ctx->ev_copied[wave & 1], cs));
+            CU(cudaStreamWaitEvent(st, ctx->ev_copied[wave & 1], 0));
+        }
 
-        float* d_scores = (!host && scores) ? scores + (size_t)c0 * ctx->n_hidden : ctx->ws_scores;
-        float* d_best = host ? ctx->ws_best : best_score + c0;
-        int32_t* d_idx = host ? ctx->ws_idx : best_idx + c0;
+        float* d_scores = host ? sg.scores : (scores ? scores + (size_t)c0 * ctx->n_hidden : ctx->ws_scores);
+        float* d_best = host ? ctx->res_best + c0 : best_score + c0;
+        int32_t* d_idx = host ? ctx->res_idx + c0 : best_idx + c0;
         TRY(run_chunk(ctx, cp, Bc, d_scores, d_best, d_idx, st));
         if (host) {
-            CU(cudaMemcpyAsync(best_score + c0, d_best, (size_t)Bc * sizeof(float), cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(best_idx + c0, d_idx, (size_t)Bc * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
             if (scores)
                 CU(cudaMemcpyAsync(scores + (size_t)c0 * ctx->n_hidden, d_scores, (size_t)Bc * ctx->n_hidden * sizeof(float),
                                    cudaMemcpyDeviceToHost, st));
+            CU(cudaEventRecord(ctx->ev_free[wave & 1], st));
         }
     }
-    if (host) return gnnb_check(ctx, stream, nullptr);
+    if (host) {
+        CU(cudaMemcpyAsync(best_score, ctx->res_best, (size_t)in->B * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(best_idx, ctx->res_idx, (size_t)in->B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        return gnnb_check(ctx, stream, nullptr);
+    }
     return GNNB_OK;
 }
 

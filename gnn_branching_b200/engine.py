@@ -144,9 +144,10 @@ class Scorer:
         pout, pin = f(fr.prim_out, (B,)), f(fr.primal_input, (B, net.n0))
         wp, bp, mask = f(fr.Wp, (B, sizes[L])), f(fr.bp, (B,)), f(fr.mask, (B, net.n_hidden))
         dev = fr.device
-        best = torch.empty(B, dtype=torch.float32, device=dev)
-        idx = torch.empty(B, dtype=torch.int32, device=dev)
-        scores = torch.empty(B, net.n_hidden, dtype=torch.float32, device=dev) if return_scores else None
+        pinned = host and torch.cuda.is_available()      # pinned results: device->host copies stay asynchronous
+        best = torch.empty(B, dtype=torch.float32, device=dev, pin_memory=pinned)
+        idx = torch.empty(B, dtype=torch.int32, device=dev, pin_memory=pinned)
+        scores = torch.empty(B, net.n_hidden, dtype=torch.float32, device=dev, pin_memory=pinned) if return_scores else None
         if B == 0:
             return best, idx, scores
         d = _lib.FrontierDesc()
