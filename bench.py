@@ -149,6 +149,59 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def kernel_rooflines(net, fr, prof, n_domains, T, peak_tf, peak_gbs, p=64):
+    """Per-kernel-class algorithmic FLOPs / HBM bytes against the live CUDA-event times.
+
+    Bytes are the compulsory ones of the private layout: 256 B per node for every mu / nb row read or written once,
+    relax' only for ambiguous rows (fraction taken from the frontier's bounds), the caller's inputs once."""
+    import torch
+    n = net.hidden_sizes
+    L = len(n)
+    mac = [a.macs_per_channel for a in net.affine]
+    amb = [float(((fr.lb[k + 1] < 0) & (fr.ub[k + 1] > 0)).float().mean()) for k in range(L)]
+    row = 4 * p                                                        # bytes of one embedding row (fp32 or fp16 hi + lo)
+    flop, byts = {}, {}
+    upd_f = 2 * 6 * p * p
+    flop['update'] = sum(n) * (T * upd_f + (T - 1) * upd_f + (upd_f + 2 * (p * p + p)))
+    byts['update'] = 2 * T * sum(nk * (2 * row + 8 + row * a) for nk, a in zip(n, amb)) + 4 * sum(n)
+    flop['prop'] = 2 * p * (T * (sum(mac) + 0) + T * (sum(mac[1:]) + n[-1]) + (T - 1) * mac[0])
+    n_all = [net.n0] + n
+    fwd_rows = sum(n_all[k] + n_all[k + 1] for k in range(L))
+    bwd_rows = sum(n_all[k + 1] + n_all[k] for k in range(1, L)) + n[-1]
+    byts['prop'] = row * (T * fwd_rows + T * bwd_rows + (T - 1) * (n_all[1] + n_all[0]))
+    flop['relax'] = sum(nk * a for nk, a in zip(n, amb)) * 2 * (14 * p + 7 * p * p)
+    byts['relax'] = sum(nk * (8 + a * (28 + 2 * row)) for nk, a in zip(n, amb))
+    flop['input'] = net.n0 * 2 * ((3 * p + p * p) + (T - 1) * (2 * p + 4 * p * p))
+    byts['input'] = net.n0 * ((12 + row) + (T - 1) * (8 + 2 * row))
+    groups = {'update': ['update_fwd', 'update_bwd', 'update_bwd_score'], 'prop': ['prop_fwd', 'prop_bwd'],
+              'relax': ['relax'], 'input': ['input_embed', 'input_update']}
+    names = {'update': 'k_tc_update (node update MLP chain, forward / backward / + score head)',
+             'prop': 'k_tc_prop (embedding propagation through the verified network, gather-GEMM)',
+             'relax': 'k_tc_relax (+ ambiguous-row compaction)', 'input': 'k_tc_input_embed / k_tc_input_update'}
+    total_ms = sum(v['ms'] for v in prof.values()) or 1.0
+    classes = {}
+    for gname, members in groups.items():
+        ms = sum(prof[m]['ms'] for m in members)
+        launches = sum(prof[m]['launches'] for m in members)
+        if ms <= 0:
+            continue
+        gbs = byts[gname] * n_domains / (ms * 1e-3) / 1e9
+        tfs = flop[gname] * n_domains / (ms * 1e-3) / 1e12
+        classes[gname] = {'ms': round(ms, 3), 'share_of_step': round(ms / total_ms, 4), 'launches': launches,
+                          'avg_launch_ms': ms / max(launches, 1), 'hbm_gbs': gbs, 'hbm_frac': gbs / peak_gbs,
+                          'tflops': tfs, 'tensor_frac': tfs / peak_tf,
+                          'algorithmic_bytes_per_subdomain': byts[gname], 'algorithmic_flop_per_subdomain': flop[gname]}
+    top = max(classes, key=lambda k: classes[k]['ms'])
+    c = classes[top]
+    return {'bound': 'hbm', 'kernel': names[top], 'kernel_class': top, 'achieved': c['hbm_gbs'], 'peak': peak_gbs, 'unit': 'GB/s',
+            'frac': c['hbm_frac'], 'launches': c['launches'], 'avg_launch_ms': c['avg_launch_ms'],
+            'share_of_step': c['share_of_step'],
+            'tensor': {'achieved': c['tflops'], 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': c['tensor_frac']},
+            'classes': classes, 'ambiguous_fraction': [round(a, 3) for a in amb],
+            'kernel_ms': {k: round(v['ms'], 3) for k, v in prof.items()},
+            '_bytes_per_subdomain': sum(byts.values())}
+
+
 def main():
     args = parse()
     if args.impl == 'reference':
@@ -249,36 +302,27 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (node-update MLP), from live CUDA-event timings ----
+    # ---- roofline of the dominant kernel class, from live CUDA-event timings on the launching stream ----
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
     except (OSError, ValueError):
         pass
     peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
-    peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if peaks else 'B200_PROFILING.md fallback 1.4 PF sustained (of fallback)'
-    p = 64
-    per_row = {'update_fwd': 2 * 6 * p * p, 'update_bwd': 2 * 6 * p * p, 'update_bwd_score': 2 * (7 * p * p + p)}
-    upd_ms = sum(prof[k]['ms'] for k in per_row)
-    upd_flop = sum(prof[k]['rows'] * f for k, f in per_row.items())
-    upd_launches = sum(prof[k]['launches'] for k in per_row)
-    total_prof_ms = sum(v['ms'] for v in prof.values())
-    achieved = upd_flop / (upd_ms * 1e-3) / 1e12 if upd_ms > 0 else 0.0
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'update_kernel_traffic.json')))['dram_bytes_per_launch']
-    except (OSError, ValueError, KeyError):
-        pass
+    peak_gbs = peaks.get('hbm_gbs', 6650.0)
+    peak_src = 'MEASURED_PEAKS.json hbm_gbs / bf16_tflops_sustained (of measured)' if peaks else \
+        'B200_PROFILING.md fallback 6.65 TB/s / 1.4 PF sustained (of fallback)'
+    roofline = kernel_rooflines(net, fronts[0], prof, K * B, T=2, peak_tf=peak_tf, peak_gbs=peak_gbs)
+    roofline['peak_source'] = peak_src
     flops_dom = net.flops_per_domain()
-    roofline = {'bound': 'tensor', 'kernel': 'node-update MLP (update_fwd / update_bwd / update_bwd_score)',
-                'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
-                'peak_source': peak_src, 'traffic': traffic,
-                'algorithmic_flop_per_node': per_row, 'launches': upd_launches,
-                'avg_launch_ms': upd_ms / max(upd_launches, 1),
-                'share_of_step': upd_ms / total_prof_ms if total_prof_ms else None,
-                'whole_path': {'flop_per_subdomain': flops_dom, 'achieved_tflops': value / world * flops_dom / 1e12,
-                               'frac_of_peak': value / world * flops_dom / 1e12 / peak_tf},
-                'kernel_ms': {k: round(v['ms'], 3) for k, v in prof.items()}}
+    roofline['whole_path'] = {'flop_per_subdomain': flops_dom, 'achieved_tflops': value / world * flops_dom / 1e12,
+                              'frac_of_bf16_peak': value / world * flops_dom / 1e12 / peak_tf,
+                              'hbm_bytes_per_subdomain': roofline.pop('_bytes_per_subdomain'),
+                              'note': 'fp32 accuracy needs 3 fp16 MMA passes per product: the tensor ceiling is 1/3 of the bf16 peak'}
+    try:
+        roofline['traffic'] = json.load(open(os.path.join(ROOT, 'profiles', 'kernel_traffic.json')))[roofline['kernel_class']]
+    except (OSError, ValueError, KeyError):
+        roofline['traffic'] = None
 
     cb = None
     if not args.no_cpu_baseline and world == 1:
