@@ -188,3 +188,28 @@ def test_full_size_frontier_properties(arch, B, math):
     masked = torch.where(m, scores, torch.full_like(scores, float('-inf')))
     assert torch.equal(masked.max(1).values, best)
     assert bool(m[torch.arange(B, device='cuda'), idx.long()].all())
+
+
+def test_frontier_of_65536_subdomains():
+    """BASELINE config 5 size on one GPU (>= 64 k CIFAR-base subdomains per call, scored in waves): every winner is a
+    candidate and the masked maximum of its row; a slice scored on its own gives bit-identical results."""
+    B = 65536
+    net, lbs, ubs, wp, bp = load_root('base')
+    model = _model('random', 'tc')
+    fr = synthetic_frontier(net, lbs, ubs, wp, bp, B, seed=424242, device='cuda')
+    best, idx, _ = model.score_frontier(fr, return_scores=False)
+    assert best.shape == (B,) and idx.shape == (B,)
+    assert bool((idx >= 0).all()) and bool(torch.isfinite(best).all())
+    m = fr.mask != 0
+    assert bool(m[torch.arange(B, device='cuda'), idx.long()].all())
+    for start in (0, 40000, B - 5):
+        sl = fr.slice(start, start + 5).contiguous()
+        b2, i2, s2 = model.score_frontier(sl, return_scores=True)
+        assert torch.equal(b2, best[start:start + 5]) and torch.equal(i2, idx[start:start + 5])
+        masked = torch.where(sl.mask != 0, s2, torch.full_like(s2, float('-inf')))
+        assert torch.equal(masked.max(1).values, b2)
+    sl = fr.slice(B - 2, B).cpu().contiguous()
+    s_or, _ = O.gnn_forward(load_gnn('random'), sl)
+    _, i3, s3 = model.score_frontier(fr.slice(B - 2, B).contiguous())
+    rep = O.parity_report(s3.cpu(), s_or, sl.mask, i3.cpu(), rtol=RTOL['tc'])
+    assert rep['ok'], rep
