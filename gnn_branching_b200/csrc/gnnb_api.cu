@@ -41,6 +41,10 @@ struct gnnb_ctx {
     std::vector<LayerDev> layers;
     std::vector<PropPlan*> plan_fwd, plan_bwd;   // tensor-core propagation plans per layer
     std::vector<int> n;             // n[0] = input nodes, n[1..L] hidden, n[L+1] = 1
+    // slot order of the tensor-core path (gnnb_common.cuh): tiling and device map of layers 0..L
+    std::vector<LayerTiling> tiling;
+    std::vector<RowMap> rowmap;
+    int32_t* d_maps = nullptr;
     std::vector<int> hidden_off;    // offset of layer k (1-based) in the flat ReLU index
     int n_hidden = 0;
     // workspace
@@ -114,15 +118,18 @@ int ensure_workspace(gnnb_ctx* ctx, int Bc, bool host_staging) {
     auto take = [&](size_t elems) { size_t off = total; total += align4(elems) + 64; return off; };
     std::vector<size_t> o_mu(L + 2), o_rf(L + 1), o_rb(L + 1), o_lb(L + 2), o_ub(L + 2), o_du(L), o_pr(L), o_po(L);
     // mu, nb and relax' are stored per tile of 128 rows by the tensor-core kernels: round the row counts up
-    auto tiled = [](size_t rows) { return ((rows + 127) / 128) * 128; };
-    for (int k = 0; k <= L + 1; ++k) o_mu[k] = take(tiled((size_t)Bc * ctx->n[k]) * P);
-    for (int k = 1; k <= L; ++k) { o_rf[k] = take(tiled((size_t)Bc * ctx->n[k]) * P); o_rb[k] = take(tiled((size_t)Bc * ctx->n[k]) * P); }
+    // rows of a layer in the workspace: slots (multiple of 128 per subdomain) >= nodes, so the SIMT path's node-order rows fit too
+    auto wrows = [&](int k) { return (size_t)Bc * (k <= L ? (size_t)ctx->rowmap[k].nslots : 128); };
+    for (int k = 0; k <= L + 1; ++k) o_mu[k] = take(wrows(k) * P);
+    for (int k = 1; k <= L; ++k) { o_rf[k] = take(wrows(k) * P); o_rb[k] = take(wrows(k) * P); }
     std::vector<size_t> o_ac(L + 1), o_ab(L + 1), o_ar(L + 1);
     for (int k = 1; k <= L; ++k) {
-        const size_t rows = (size_t)Bc * ctx->n[k], nt = (rows + 127) / 128;
+        const size_t rows = wrows(k), nt = rows / 128;
         o_ac[k] = take(nt + 1); o_ab[k] = take(nt + 1); o_ar[k] = take(rows);
     }
-    const size_t o_nb = take(tiled((size_t)Bc * nmax) * P);
+    size_t nb_rows = 0;
+    for (int k = 0; k <= L; ++k) nb_rows = wrows(k) > nb_rows ? wrows(k) : nb_rows;
+    const size_t o_nb = take(nb_rows * P);
     const size_t o_sc = take((size_t)Bc * ctx->n_hidden);
     const size_t o_best = take(Bc), o_idx = take(Bc);
     struct StgOff { std::vector<size_t> lb, ub, du, pr, po; size_t pout, pin, wp, bp, mask, best, idx, sc; } so[2];
@@ -230,11 +237,12 @@ int prof_collect(gnnb_ctx* ctx) {
 }
 
 // mu and nb are fp16 tile images in tensor-core mode (mu swizzled, nb piece-major): unpack them into the snapshot
-int snap_img(gnnb_ctx* ctx, const std::string& name, const float* img, int64_t rows, bool piece_major, cudaStream_t st) {
+int snap_img(gnnb_ctx* ctx, const std::string& name, const float* img, int k, int Bc, bool piece_major, cudaStream_t st) {
     if (!ctx->snapshot) return GNNB_OK;
-    if (ctx->math != GNNB_MATH_TC_FP16X3) return snap(ctx, name, img, rows * P, st);
-    TRY_(snap(ctx, name, img, rows * P, st));          // allocates / sizes the snapshot buffer
-    tc_unpack_tile_image(img, ctx->snaps[name].first, rows, piece_major, st);
+    const int64_t numel = (int64_t)Bc * ctx->n[k] * P;                     // snapshots are in node order in both modes
+    if (ctx->math != GNNB_MATH_TC_FP16X3) return snap(ctx, name, img, numel, st);
+    TRY_(snap(ctx, name, img, numel, st));          // allocates / sizes the snapshot buffer
+    tc_unpack_tile_image(img, ctx->snaps[name].first, ctx->rowmap[k], (int64_t)Bc * ctx->rowmap[k].nslots, piece_major, st);
     return GNNB_OK;
 }
 
@@ -254,83 +262,88 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
     int64_t* lc = &ctx->launches;
     auto name = [](const char* fmt, int a, int b) { char buf[64]; snprintf(buf, sizeof buf, fmt, a, b); return std::string(buf); };
 
+    // rows of layer k in the mode's row order: slots (tensor-core path) or nodes (SIMT path)
+    auto R = [&](int k) { return (int64_t)Bc * (tc ? ctx->rowmap[k].nslots : ctx->n[k]); };
+    const RowMap nomap{nullptr, 0, 0};
+    auto M = [&](int k) { return tc ? ctx->rowmap[k] : nomap; };
+
     // round-independent relaxation features of every hidden layer
     for (int k = 1; k <= L; ++k) {
         NodeInputs ni{in.lb[k], in.ub[k], in.dual[k - 1], in.pre[k - 1], in.post[k - 1], ctx->layers[k - 1].bias_node,
-                      ctx->n[k], (int64_t)Bc * ctx->n[k], ctx->amb_rows[k], ctx->amb_base[k]};
+                      ctx->n[k], R(k), ctx->amb_rows[k], ctx->amb_base[k], M(k)};
         {
-            ProfScope ps(ctx, GNNB_K_RELAX, ni.rows, st);
-            if (tc) amb_compact(in.lb[k], in.ub[k], ni.rows, ctx->amb_cnt[k], ctx->amb_base[k], ctx->amb_rows[k], st, lc);
+            ProfScope ps(ctx, GNNB_K_RELAX, (int64_t)Bc * ctx->n[k], st);
+            if (tc) amb_compact(in.lb[k], in.ub[k], M(k), ni.rows, ctx->amb_cnt[k], ctx->amb_base[k], ctx->amb_rows[k], st, lc);
             if (tc) tc_relax(g, ni, ctx->relax_f[k], ctx->relax_b[k], st, lc);
             else simt_relax(g, ni, ctx->relax_f[k], ctx->relax_b[k], st, lc);
         }
-        // tensor-core mode stores relax' (pre-multiplied by fc4 / bc4's relax half, tile-transposed): not comparable 1:1
-        TRY(snap(ctx, name(tc ? "relaxp_f%d" : "relax_f%d", k, 0), ctx->relax_f[k], ni.rows * P, st));
-        TRY(snap(ctx, name(tc ? "relaxp_b%d" : "relax_b%d", k, 0), ctx->relax_b[k], ni.rows * P, st));
+        // tensor-core mode stores relax' (pre-multiplied by fc4 / bc4's relax half, compacted, tile-transposed): not comparable 1:1
+        TRY(snap(ctx, name(tc ? "relaxp_f%d" : "relax_f%d", k, 0), ctx->relax_f[k], (int64_t)Bc * ctx->n[k] * P, st));
+        TRY(snap(ctx, name(tc ? "relaxp_b%d" : "relax_b%d", k, 0), ctx->relax_b[k], (int64_t)Bc * ctx->n[k] * P, st));
     }
-    const int64_t rows0 = (int64_t)Bc * ctx->n[0];
     {
-        ProfScope ps(ctx, GNNB_K_INPUT_EMBED, rows0, st);
-        if (tc) tc_input_embed(g, in.lb[0], in.pin, in.ub[0], ctx->mu[0], rows0, st, lc);
-        else simt_input_embed(g, in.lb[0], in.pin, in.ub[0], ctx->mu[0], rows0, st, lc);
+        ProfScope ps(ctx, GNNB_K_INPUT_EMBED, (int64_t)Bc * ctx->n[0], st);
+        if (tc) tc_input_embed(g, in.lb[0], in.pin, in.ub[0], ctx->mu[0], M(0), R(0), st, lc);
+        else simt_input_embed(g, in.lb[0], in.pin, in.ub[0], ctx->mu[0], R(0), st, lc);
     }
-    TRY(snap_img(ctx, "mu0_embed", ctx->mu[0], rows0, false, st));
+    TRY(snap_img(ctx, "mu0_embed", ctx->mu[0], 0, Bc, false, st));
 
     for (int t = 0; t < g.T; ++t) {
         const bool last = (t == g.T - 1);
         // forward sweep
         for (int k = 1; k <= L; ++k) {
-            const int64_t rows = (int64_t)Bc * ctx->n[k];
+            const int64_t rows = R(k), nodes = (int64_t)Bc * ctx->n[k];
             {
-                ProfScope ps(ctx, GNNB_K_PROP_FWD, rows, st);
+                ProfScope ps(ctx, GNNB_K_PROP_FWD, nodes, st);
                 if (tc) prop_tc_run(ctx->plan_fwd[k - 1], ctx->mu[k - 1], ctx->nb, Bc, st, lc);
                 else prop_forward(ctx->layers[k - 1], ctx->mu[k - 1], ctx->nb, Bc, st, lc);
             }
-            TRY(snap_img(ctx, name("t%d_fwd_nb%d", t, k), ctx->nb, rows, true, st));
+            TRY(snap_img(ctx, name("t%d_fwd_nb%d", t, k), ctx->nb, k, Bc, true, st));
             {
-                ProfScope ps(ctx, GNNB_K_UPDATE_FWD, rows, st);
-                if (tc) tc_update(g, false, in.lb[k], in.ub[k], ctx->nb, ctx->relax_f[k], ctx->amb_base[k], ctx->mu[k], nullptr, ctx->n[k], 0, 0, rows, ctx->d_nan, st, lc);
+                ProfScope ps(ctx, GNNB_K_UPDATE_FWD, nodes, st);
+                if (tc) tc_update(g, false, in.lb[k], in.ub[k], ctx->nb, ctx->relax_f[k], ctx->amb_base[k], ctx->mu[k], nullptr, M(k), 0, 0, rows, ctx->d_nan, st, lc);
                 else simt_update(g, false, in.lb[k], in.ub[k], ctx->nb, ctx->relax_f[k], ctx->mu[k], nullptr, ctx->n[k], 0, 0, rows, ctx->d_nan, st, lc);
             }
-            TRY(snap_img(ctx, name("t%d_fwd_mu%d", t, k), ctx->mu[k], rows, false, st));
+            TRY(snap_img(ctx, name("t%d_fwd_mu%d", t, k), ctx->mu[k], k, Bc, false, st));
         }
         {
             ProfScope ps(ctx, GNNB_K_OUTPUT, Bc, st);
-            output_node(g, in.wp, in.bp, ctx->mu[L], tc, in.lb[L + 1], in.ub[L + 1], in.pout, ctx->mu[L + 1], ctx->n[L], Bc, st, lc);
+            output_node(g, in.wp, in.bp, ctx->mu[L], tc, tc ? ctx->rowmap[L].nslots : ctx->n[L], in.lb[L + 1], in.ub[L + 1], in.pout,
+                        ctx->mu[L + 1], ctx->n[L], Bc, st, lc);
         }
         TRY(snap(ctx, name("t%d_mu_out", t, 0), ctx->mu[L + 1], (int64_t)Bc * P, st));
         // backward sweep
         for (int k = L; k >= 1; --k) {
-            const int64_t rows = (int64_t)Bc * ctx->n[k];
+            const int64_t rows = R(k), nodes = (int64_t)Bc * ctx->n[k];
             {
-                ProfScope ps(ctx, GNNB_K_PROP_BWD, rows, st);
-                if (k == L && tc) prop_tc_property_backward(in.wp, ctx->mu[L + 1], ctx->nb, ctx->n[L], Bc, st, lc);
+                ProfScope ps(ctx, GNNB_K_PROP_BWD, nodes, st);
+                if (k == L && tc) prop_tc_property_backward(in.wp, ctx->mu[L + 1], ctx->nb, ctx->n[L], ctx->rowmap[L].nslots, Bc, st, lc);
                 else if (k == L) prop_property_backward(in.wp, ctx->mu[L + 1], ctx->nb, ctx->n[L], Bc, st, lc);
                 else if (tc) prop_tc_run(ctx->plan_bwd[k], ctx->mu[k + 1], ctx->nb, Bc, st, lc);
                 else prop_backward(ctx->layers[k], ctx->mu[k + 1], ctx->nb, Bc, true, st, lc);
             }
-            TRY(snap_img(ctx, name("t%d_bwd_nb%d", t, k), ctx->nb, rows, true, st));
+            TRY(snap_img(ctx, name("t%d_bwd_nb%d", t, k), ctx->nb, k, Bc, true, st));
             float* sc = last ? scores : nullptr;
             {
-                ProfScope ps(ctx, last ? GNNB_K_UPDATE_BWD_SCORE : GNNB_K_UPDATE_BWD, rows, st);
-                if (tc) tc_update(g, true, in.lb[k], in.ub[k], ctx->nb, ctx->relax_b[k], ctx->amb_base[k], ctx->mu[k], sc, ctx->n[k], ctx->n_hidden, ctx->hidden_off[k], rows, ctx->d_nan, st, lc);
+                ProfScope ps(ctx, last ? GNNB_K_UPDATE_BWD_SCORE : GNNB_K_UPDATE_BWD, nodes, st);
+                if (tc) tc_update(g, true, in.lb[k], in.ub[k], ctx->nb, ctx->relax_b[k], ctx->amb_base[k], ctx->mu[k], sc, M(k), ctx->n_hidden, ctx->hidden_off[k], rows, ctx->d_nan, st, lc);
                 else simt_update(g, true, in.lb[k], in.ub[k], ctx->nb, ctx->relax_b[k], ctx->mu[k], sc, ctx->n[k], ctx->n_hidden, ctx->hidden_off[k], rows, ctx->d_nan, st, lc);
             }
-            TRY(snap_img(ctx, name("t%d_bwd_mu%d", t, k), ctx->mu[k], rows, false, st));
+            TRY(snap_img(ctx, name("t%d_bwd_mu%d", t, k), ctx->mu[k], k, Bc, false, st));
         }
         // input layer: feeds the next round only (dead on the last round)
         if (!last) {
             {
-                ProfScope ps(ctx, GNNB_K_PROP_BWD, rows0, st);
+                ProfScope ps(ctx, GNNB_K_PROP_BWD, (int64_t)Bc * ctx->n[0], st);
                 if (tc) prop_tc_run(ctx->plan_bwd[0], ctx->mu[1], ctx->nb, Bc, st, lc);
                 else prop_backward(ctx->layers[0], ctx->mu[1], ctx->nb, Bc, false, st, lc);
             }
             {
-                ProfScope ps(ctx, GNNB_K_INPUT_UPDATE, rows0, st);
-                if (tc) tc_input_update(g, in.lb[0], in.ub[0], ctx->nb, ctx->mu[0], rows0, st, lc);
-                else simt_input_update(g, in.lb[0], in.ub[0], ctx->nb, ctx->mu[0], rows0, st, lc);
+                ProfScope ps(ctx, GNNB_K_INPUT_UPDATE, (int64_t)Bc * ctx->n[0], st);
+                if (tc) tc_input_update(g, in.lb[0], in.ub[0], ctx->nb, ctx->mu[0], M(0), R(0), st, lc);
+                else simt_input_update(g, in.lb[0], in.ub[0], ctx->nb, ctx->mu[0], R(0), st, lc);
             }
-            TRY(snap_img(ctx, name("t%d_mu0", t, 0), ctx->mu[0], rows0, false, st));
+            TRY(snap_img(ctx, name("t%d_mu0", t, 0), ctx->mu[0], 0, Bc, false, st));
         }
     }
     {
@@ -380,6 +393,7 @@ void gnnb_destroy(gnnb_ctx* ctx) {
     if (ctx->d_gnn) cudaFree(ctx->d_gnn);
     if (ctx->d_tc) cudaFree(ctx->d_tc);
     if (ctx->d_net) cudaFree(ctx->d_net);
+    if (ctx->d_maps) cudaFree(ctx->d_maps);
     if (ctx->d_nan) cudaFree(ctx->d_nan);
     for (PropPlan* p : ctx->plan_fwd) prop_plan_free(p);
     for (PropPlan* p : ctx->plan_bwd) prop_plan_free(p);
@@ -544,10 +558,31 @@ int gnnb_set_network(gnnb_ctx* ctx, const gnnb_layer_desc* layers, int n_layers,
     for (PropPlan* p : ctx->plan_bwd) prop_plan_free(p);
     ctx->plan_fwd.assign(n_layers, nullptr);
     ctx->plan_bwd.assign(n_layers, nullptr);
+    // slot order of layers 0..L (gnnb_common.cuh) and the device copies of the slot -> node maps
+    ctx->tiling.assign(n_layers + 1, LayerTiling());
+    ctx->tiling[0] = make_tiling(c0, h0, w0);
+    for (int k = 0; k < n_layers; ++k)
+        ctx->tiling[k + 1] = devs[k].kind == GNNB_LAYER_CONV ? make_tiling(devs[k].c_out, devs[k].h_out, devs[k].w_out)
+                                                            : make_tiling(devs[k].n_out, 1, 1);
+    {
+        size_t total_slots = 0;
+        for (const LayerTiling& t : ctx->tiling) total_slots += t.node_of_slot.size();
+        if (ctx->d_maps) cudaFree(ctx->d_maps);
+        ctx->d_maps = nullptr;
+        CU(cudaMalloc(&ctx->d_maps, total_slots * sizeof(int32_t)));
+        ctx->rowmap.assign(n_layers + 1, RowMap{nullptr, 0, 0});
+        size_t off = 0;
+        for (int k = 0; k <= n_layers; ++k) {
+            const LayerTiling& t = ctx->tiling[k];
+            CU(cudaMemcpy(ctx->d_maps + off, t.node_of_slot.data(), t.node_of_slot.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+            ctx->rowmap[k] = RowMap{ctx->d_maps + off, n[k], (int)t.node_of_slot.size()};
+            off += t.node_of_slot.size();
+        }
+    }
     for (int k = 0; k < n_layers; ++k) {
         // layer 0's transpose feeds the input nodes and is not normalised (graph_conv.py:361-372); the others are (:299-318)
-        ctx->plan_fwd[k] = prop_plan_build(devs[k], layers[k].weight, false, false);
-        ctx->plan_bwd[k] = prop_plan_build(devs[k], layers[k].weight, true, k > 0);
+        ctx->plan_fwd[k] = prop_plan_build(devs[k], layers[k].weight, false, false, ctx->tiling[k + 1], ctx->tiling[k]);
+        ctx->plan_bwd[k] = prop_plan_build(devs[k], layers[k].weight, true, k > 0, ctx->tiling[k], ctx->tiling[k + 1]);
         if (!ctx->plan_fwd[k] || !ctx->plan_bwd[k]) return fail(ctx, GNNB_ERR_CUDA, "building the propagation plans failed");
     }
     ctx->layers = devs;

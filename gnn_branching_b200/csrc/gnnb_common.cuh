@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "../../include/gnnb.h"
 
 namespace gnnb {
@@ -59,7 +61,30 @@ struct LayerDev {
     const float* bias_node;   // [n_out] bias of the layer expanded per node (graph_conv.py:122-124, 133)
 };
 
-// Per-row (node) inputs of one hidden layer for one chunk of subdomains; rows = Bc * n.
+// Row order of the tensor-core path's private tensors ("slot order").  The nodes of a layer are grouped into tiles of
+// <= 128 nodes that share inputs in the propagation plans (all channels of a spatial patch; 128 consecutive nodes for
+// flat layers), each padded to 128 slots; a subdomain owns nslots consecutive rows, global row = b * nslots + slot.
+// A propagation tile is therefore exactly one tile of the node kernels, and tiles never straddle subdomains.  The
+// caller's arrays stay in the reference's NCHW-flat node order and are reached through node_of_slot.
+struct RowMap {
+    const int32_t* node_of_slot;   // [nslots] node of each slot, -1 = padding
+    int n;                         // nodes per subdomain
+    int nslots;                    // slots per subdomain (multiple of 128)
+};
+// index into a caller array [B, n] of global slot row `grow`, -1 for padding slots
+__device__ __forceinline__ int64_t natural_row(const RowMap& m, int64_t grow) {
+    const int64_t b = grow / m.nslots;
+    const int node = __ldg(m.node_of_slot + (grow - b * m.nslots));
+    return node < 0 ? -1 : b * m.n + node;
+}
+struct LayerTiling {               // host side of a RowMap
+    std::vector<int32_t> node_of_slot, slot_of_node;
+    int ntiles = 0;
+};
+LayerTiling make_tiling(int C, int H, int W);      // conv-shaped layer; H = W = 1: flat layer of C nodes
+
+// Per-row (node) inputs of one hidden layer for one chunk of subdomains.  SIMT path: rows = Bc * n in node order;
+// tensor-core path: rows = Bc * map.nslots in slot order, the arrays below are reached through `map`.
 struct NodeInputs {
     const float* lb;          // [rows]
     const float* ub;          // [rows]
@@ -73,6 +98,7 @@ struct NodeInputs {
     // graph_conv.py:161, 293), compacted in row order by amb_compact()
     const int32_t* amb_rows;  // [amb_base[ntiles]] global row of each compacted slot
     const int32_t* amb_base;  // [ntiles + 1] first slot of each tile of 128 rows; amb_base[ntiles] = number of ambiguous rows
+    RowMap map;
 };
 
 // ---- launchers (each enqueues on `st` and bumps *launches) -------------------------------------
@@ -91,15 +117,15 @@ int simt_init();  // opt-in shared memory sizes; returns cudaError_t
 // tcgen05 node kernels (gnnb_tc.cu) — same contracts as the SIMT ones
 void tc_relax(const GnnParams& g, const NodeInputs& in, float* relax_f, float* relax_b, cudaStream_t st, int64_t* launches);
 void tc_update(const GnnParams& g, bool backward, const float* lb, const float* ub, const float* nb, const float* relax,
-               const int32_t* amb_base, float* mu_out, float* scores, int n, int64_t score_stride, int64_t score_off, int64_t rows,
+               const int32_t* amb_base, float* mu_out, float* scores, RowMap map, int64_t score_stride, int64_t score_off, int64_t rows,
                unsigned long long* nan_count, cudaStream_t st, int64_t* launches);
 // slot of every ambiguous row of a layer, in row order: amb_base[tile] (+ the rank inside the tile), amb_rows[slot] = row;
 // cnt is scratch of ntiles + 1 ints (three small launches: count per tile, scan, fill)
-void amb_compact(const float* lb, const float* ub, int64_t rows, int32_t* cnt, int32_t* amb_base, int32_t* amb_rows,
+void amb_compact(const float* lb, const float* ub, RowMap map, int64_t rows, int32_t* cnt, int32_t* amb_base, int32_t* amb_rows,
                  cudaStream_t st, int64_t* launches);
-void tc_input_embed(const GnnParams& g, const float* lb0, const float* x, const float* ub0, float* mu0, int64_t rows,
+void tc_input_embed(const GnnParams& g, const float* lb0, const float* x, const float* ub0, float* mu0, RowMap map, int64_t rows,
                     cudaStream_t st, int64_t* launches);
-void tc_input_update(const GnnParams& g, const float* lb0, const float* ub0, const float* nb, float* mu0, int64_t rows,
+void tc_input_update(const GnnParams& g, const float* lb0, const float* ub0, const float* nb, float* mu0, RowMap map, int64_t rows,
                      cudaStream_t st, int64_t* launches);
 // repack one nn.Linear weight [64][K] (host) into the tensor-core plane layout; returns elements written
 int64_t tc_pack_weight(const float* w_host, int K, uint16_t* dst_host);
@@ -107,14 +133,14 @@ int64_t tc_packed_elems(int K);
 int tc_init();   // opt-in shared memory sizes; returns cudaError_t
 bool tc_available();
 // tile image (gnnb_umma.cuh: mu = swizzled, nb = piece-major) -> fp32 [rows][64]; debugging snapshots
-void tc_unpack_tile_image(const float* img, float* out, int64_t rows, bool piece_major, cudaStream_t st);
+void tc_unpack_tile_image(const float* img, float* out, RowMap map, int64_t rows, bool piece_major, cudaStream_t st);   // out: node order
 
 // propagation through the verified network and the small kernels (gnnb_prop.cu)
 int prop_init(int max_smem_bytes);
 void prop_forward(const LayerDev& L, const float* mu_prev, float* nb, int Bc, cudaStream_t st, int64_t* launches);
 void prop_backward(const LayerDev& L, const float* mu_next, float* nb, int Bc, bool normalise, cudaStream_t st, int64_t* launches);
 void prop_property_backward(const float* wp, const float* mu_out, float* nb, int nL, int Bc, cudaStream_t st, int64_t* launches);
-void output_node(const GnnParams& g, const float* wp, const float* bp, const float* mu_L, bool mu_image, const float* lb_out,
+void output_node(const GnnParams& g, const float* wp, const float* bp, const float* mu_L, bool mu_image, int mu_stride, const float* lb_out,
                  const float* ub_out, const float* prim_out, float* mu_out, int nL, int Bc, cudaStream_t st, int64_t* launches);
 void masked_argmax(const float* scores, const float* mask, int n_hidden, int Bc, float* best_score, int32_t* best_idx,
                    cudaStream_t st, int64_t* launches);
@@ -122,11 +148,12 @@ void masked_argmax(const float* scores, const float* mask, int n_hidden, int Bc,
 // tensor-core propagation (gnnb_prop_tc.cu): block plans built once per network, gather-GEMM kernel
 struct PropPlan;
 int prop_tc_init();
-PropPlan* prop_plan_build(const LayerDev& L, const float* host_weight, bool backward, bool normalise);
+PropPlan* prop_plan_build(const LayerDev& L, const float* host_weight, bool backward, bool normalise, const LayerTiling& out,
+                          const LayerTiling& in);
 void prop_plan_free(PropPlan* p);
 double prop_plan_density(const PropPlan* p);
 void prop_tc_run(const PropPlan* plan, const float* mu_in, float* nb_img, int Bc, cudaStream_t st, int64_t* launches);
-void prop_tc_property_backward(const float* wp, const float* mu_out, float* nb_img, int nL, int Bc, cudaStream_t st, int64_t* launches);
+void prop_tc_property_backward(const float* wp, const float* mu_out, float* nb_img, int nL, int nslots, int Bc, cudaStream_t st, int64_t* launches);
 
 // ---- device helpers ---------------------------------------------------------------------------
 // compute_ratio of graph_conv.py:499-514 in the reference's operation order (IEEE division, no fast-math)

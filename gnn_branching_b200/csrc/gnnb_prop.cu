@@ -199,14 +199,14 @@ __device__ __forceinline__ float mu_at(const float* __restrict__ mu, int mu_imag
 
 // one 64-thread block per subdomain
 __global__ void __launch_bounds__(64) k_output_node(GnnParams g, const float* __restrict__ wp, const float* __restrict__ bp,
-                                                    const float* __restrict__ mu_L, int mu_image, const float* __restrict__ lb_out,
+                                                    const float* __restrict__ mu_L, int mu_image, int mu_stride, const float* __restrict__ lb_out,
                                                     const float* __restrict__ ub_out, const float* __restrict__ prim_out,
                                                     float* __restrict__ mu_out, int nL) {
     __shared__ float cat[2 * P];
     __shared__ float h2[P];
     const int b = blockIdx.x, c = threadIdx.x;
     float nbv = 0.f;                                       // prop.weight @ mu[L]  (graph_conv.py:196)
-    for (int n = 0; n < nL; ++n) nbv = fmaf(wp[(int64_t)b * nL + n], mu_at(mu_L, mu_image, (int64_t)b * nL + n, c), nbv);
+    for (int n = 0; n < nL; ++n) nbv = fmaf(wp[(int64_t)b * nL + n], mu_at(mu_L, mu_image, (int64_t)b * mu_stride + n, c), nbv);
     const float feat[4] = {lb_out[b], ub_out[b], prim_out[b], bp[b]};   // graph_conv.py:202-205
     float h = g.bias[OUT1][c];
 #pragma unroll
@@ -310,9 +310,9 @@ void prop_property_backward(const float* wp, const float* mu_out, float* nb, int
     ++*launches;
 }
 
-void output_node(const GnnParams& g, const float* wp, const float* bp, const float* mu_L, bool mu_image, const float* lb_out,
+void output_node(const GnnParams& g, const float* wp, const float* bp, const float* mu_L, bool mu_image, int mu_stride, const float* lb_out,
                  const float* ub_out, const float* prim_out, float* mu_out, int nL, int Bc, cudaStream_t st, int64_t* launches) {
-    k_output_node<<<Bc, 64, 0, st>>>(g, wp, bp, mu_L, mu_image ? 1 : 0, lb_out, ub_out, prim_out, mu_out, nL);
+    k_output_node<<<Bc, 64, 0, st>>>(g, wp, bp, mu_L, mu_image ? 1 : 0, mu_stride, lb_out, ub_out, prim_out, mu_out, nL);
     ++*launches;
 }
 

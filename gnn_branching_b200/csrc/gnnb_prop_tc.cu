@@ -22,12 +22,12 @@ namespace gnnb {
 using namespace tcx;
 
 struct PropPlanDev {
-    const int32_t* out_rows;      // [ntiles][128] output node of each tile row, -1 = unused
-    const int32_t* in_rows;       // [nchunks][64] input node of each K row, -1 = zero row
+    const int32_t* in_rows;       // [nchunks][64] input slot of each K row, -1 = zero row
     const uint16_t* a_planes;     // [nchunks][2][128 * 64] hi plane then lo plane, 32 KB per chunk
     const int32_t* tile_chunk0;   // [ntiles + 1] first chunk of each tile
     const int32_t* ksteps;        // [nchunks] K = 16 steps that hold data (1..4)
-    int ntiles, n_in, n_out;
+    int ntiles;                   // tiles of the output layer = its slots / 128
+    int nslots_in, nslots_out;    // rows per subdomain of the input / output layer (slot order, gnnb_common.cuh)
 };
 
 struct PropPlan {
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(PROP_THREADS, 1) k_tc_prop(PropPlanDev plan, c
             const int tile = (int)(item % plan.ntiles);
             const int d = (int)(item / plan.ntiles) * PD + g;
             const bool dom_ok = d < Bc;
-            const int64_t drow = (int64_t)d * plan.n_in;
+            const int64_t drow = (int64_t)d * plan.nslots_in;
             const int ch0 = plan.tile_chunk0[tile], ch1 = plan.tile_chunk0[tile + 1];
             for (int ch = ch0; ch < ch1; ++ch) {
                 const int nks = plan.ksteps[ch];
@@ -193,31 +193,30 @@ __global__ void __launch_bounds__(PROP_THREADS, 1) k_tc_prop(PropPlanDev plan, c
             if ((int)(it & 1u) != ew) continue;
             const int tile = (int)(item % plan.ntiles);
             const int d0 = (int)(item / plan.ntiles) * PD;
-            const int orow = __ldg(plan.out_rows + (size_t)tile * TILE + m);
             mbar_wait(full, aph);
             aph ^= 1u;
             tc_fence_after();
 #pragma unroll 1
             for (int dom = 0; dom < PD; ++dom) {
                 if (d0 + dom >= Bc) break;
-                const int64_t grow = (int64_t)(d0 + dom) * plan.n_out + (orow >= 0 ? orow : 0);
-                unsigned char* img = reinterpret_cast<unsigned char*>(nb_img) + (grow >> 7) * (int64_t)ABUF + (uint32_t)(grow & (TILE - 1)) * 16u;
+                // slot order: the tile's 128 rows are one tile image of the output layer; thread = row, so a warp's store
+                // instruction writes 512 contiguous bytes of a piece
+                unsigned char* img = reinterpret_cast<unsigned char*>(nb_img) +
+                                     ((int64_t)(d0 + dom) * plan.ntiles + tile) * (int64_t)ABUF + (uint32_t)m * 16u;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     float x[16];
                     tmem_ld16_sync(tmem + (uint32_t)(dom * 64 + q * 16), x);
-                    if (orow >= 0) {
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            uint4 hi, lo;
-                            split2(x[h * 8 + 0], x[h * 8 + 1], hi.x, lo.x);
-                            split2(x[h * 8 + 2], x[h * 8 + 3], hi.y, lo.y);
-                            split2(x[h * 8 + 4], x[h * 8 + 5], hi.z, lo.z);
-                            split2(x[h * 8 + 6], x[h * 8 + 7], hi.w, lo.w);
-                            const uint32_t off = (uint32_t)(q * 2 + h) * NB_PIECE;
-                            *reinterpret_cast<uint4*>(img + off) = hi;
-                            *reinterpret_cast<uint4*>(img + APLANE + off) = lo;
-                        }
+                    for (int h = 0; h < 2; ++h) {
+                        uint4 hi, lo;
+                        split2(x[h * 8 + 0], x[h * 8 + 1], hi.x, lo.x);
+                        split2(x[h * 8 + 2], x[h * 8 + 3], hi.y, lo.y);
+                        split2(x[h * 8 + 4], x[h * 8 + 5], hi.z, lo.z);
+                        split2(x[h * 8 + 6], x[h * 8 + 7], hi.w, lo.w);
+                        const uint32_t off = (uint32_t)(q * 2 + h) * NB_PIECE;
+                        *reinterpret_cast<uint4*>(img + off) = hi;
+                        *reinterpret_cast<uint4*>(img + APLANE + off) = lo;
                     }
                 }
             }
@@ -269,19 +268,21 @@ std::vector<std::vector<int>> range_tiles(int n) {
     return tiles;
 }
 
-PropPlan* build_plan(const std::vector<std::vector<int>>& tiles, const EdgeFn& edges, int n_in, int n_out) {
-    std::vector<int32_t> out_rows, in_rows, tile_chunk0, ksteps;
+PropPlan* build_plan(const LayerTiling& out, const LayerTiling& in, const EdgeFn& edges) {
+    std::vector<int32_t> in_rows, tile_chunk0, ksteps;
     std::vector<uint16_t> planes;
     std::vector<Edge> ev;
     double useful = 0.0, issued = 0.0;
-    for (const auto& rows : tiles) {
-        std::vector<std::vector<Edge>> row_edges(rows.size());
-        std::map<int, int> col;                     // input node -> K index (sorted by node)
-        for (size_t m = 0; m < rows.size(); ++m) {
+    for (int t = 0; t < out.ntiles; ++t) {
+        const int32_t* rows = &out.node_of_slot[(size_t)t * TILE];       // -1 = padding slot
+        std::vector<std::vector<Edge>> row_edges(TILE);
+        std::map<int, int> col;                     // input SLOT -> K index (sorted by slot: neighbouring K rows are neighbouring rows of the mu image)
+        for (int m = 0; m < TILE; ++m) {
+            if (rows[m] < 0) continue;
             ev.clear();
             edges(rows[m], ev);
+            for (Edge& e : ev) { e.in = in.slot_of_node[e.in]; col[e.in] = 0; }
             row_edges[m] = ev;
-            for (const Edge& e : ev) col[e.in] = 0;
             useful += (double)ev.size();
         }
         int K = 0;
@@ -299,11 +300,11 @@ PropPlan* build_plan(const std::vector<std::vector<int>>& tiles, const EdgeFn& e
         planes.resize((chunk_base + nch) * (size_t)(2 * TILE * 64), 0);
         const int Kp = nch * 64;
         std::vector<float> dense((size_t)TILE * Kp, 0.f);
-        for (size_t m = 0; m < rows.size(); ++m)
-            for (const Edge& e : row_edges[m]) dense[m * Kp + col[e.in]] += e.w;
-        for (size_t m = 0; m < rows.size(); ++m)
+        for (int m = 0; m < TILE; ++m)
+            for (const Edge& e : row_edges[m]) dense[(size_t)m * Kp + col[e.in]] += e.w;
+        for (int m = 0; m < TILE; ++m)
             for (int k = 0; k < K; ++k) {
-                const float x = dense[m * Kp + k];
+                const float x = dense[(size_t)m * Kp + k];
                 if (x == 0.f) continue;
                 const int c = k / 64, kk = k % 64;
                 uint16_t hi, lo;
@@ -313,16 +314,15 @@ PropPlan* build_plan(const std::vector<std::vector<int>>& tiles, const EdgeFn& e
                 planes[cb + el] = hi;
                 planes[cb + TILE * 64 + el] = lo;
             }
-        for (int m = 0; m < TILE; ++m) out_rows.push_back(m < (int)rows.size() ? rows[m] : -1);
     }
     tile_chunk0.push_back((int32_t)ksteps.size());
     PropPlan* p = new PropPlan();
     p->nchunks = (int)ksteps.size();
     p->density = issued > 0 ? useful / issued : 0.0;
-    const size_t b_planes = planes.size() * sizeof(uint16_t), b_out = out_rows.size() * 4, b_in = in_rows.size() * 4,
+    const size_t b_planes = planes.size() * sizeof(uint16_t), b_in = in_rows.size() * 4,
                  b_tc = tile_chunk0.size() * 4, b_ks = ksteps.size() * 4;
     auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
-    const size_t total = up(b_planes) + up(b_out) + up(b_in) + up(b_tc) + up(b_ks);
+    const size_t total = up(b_planes) + up(b_in) + up(b_tc) + up(b_ks);
     if (cudaMalloc(&p->blob, total) != cudaSuccess) { delete p; return nullptr; }
     unsigned char* d = reinterpret_cast<unsigned char*>(p->blob);
     size_t off = 0;
@@ -333,18 +333,31 @@ PropPlan* build_plan(const std::vector<std::vector<int>>& tiles, const EdgeFn& e
         return dst;
     };
     p->dev.a_planes = reinterpret_cast<const uint16_t*>(put(planes.data(), b_planes));
-    p->dev.out_rows = reinterpret_cast<const int32_t*>(put(out_rows.data(), b_out));
     p->dev.in_rows = reinterpret_cast<const int32_t*>(put(in_rows.data(), b_in));
     p->dev.tile_chunk0 = reinterpret_cast<const int32_t*>(put(tile_chunk0.data(), b_tc));
     p->dev.ksteps = reinterpret_cast<const int32_t*>(put(ksteps.data(), b_ks));
-    p->dev.ntiles = (int)tiles.size();
-    p->dev.n_in = n_in;
-    p->dev.n_out = n_out;
+    p->dev.ntiles = out.ntiles;
+    p->dev.nslots_in = (int)in.node_of_slot.size();
+    p->dev.nslots_out = (int)out.node_of_slot.size();
     if (cudaGetLastError() != cudaSuccess) { cudaFree(p->blob); delete p; return nullptr; }
     return p;
 }
 
 }  // namespace
+
+LayerTiling make_tiling(int C, int H, int W) {
+    const std::vector<std::vector<int>> tiles = (H == 1 && W == 1) ? range_tiles(C) : grid_tiles(C, H, W);
+    LayerTiling t;
+    t.ntiles = (int)tiles.size();
+    t.node_of_slot.assign((size_t)t.ntiles * TILE, -1);
+    t.slot_of_node.assign((size_t)C * H * W, -1);
+    for (int i = 0; i < t.ntiles; ++i)
+        for (size_t m = 0; m < tiles[i].size(); ++m) {
+            t.node_of_slot[(size_t)i * TILE + m] = tiles[i][m];
+            t.slot_of_node[tiles[i][m]] = i * TILE + (int)m;
+        }
+    return t;
+}
 
 int prop_tc_init() {
     return cudaFuncSetAttribute(k_tc_prop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PROP_SMEM);
@@ -352,7 +365,8 @@ int prop_tc_init() {
 
 // plan for  nb = A_k(mu)  (forward) or  nb = A_k^T(mu) [/ freq]  (backward) of one verified-network layer;
 // `w` is the layer's HOST weight (conv [co,ci,k,k] / linear [out,in])
-PropPlan* prop_plan_build(const LayerDev& L, const float* w, bool backward, bool normalise) {
+PropPlan* prop_plan_build(const LayerDev& L, const float* w, bool backward, bool normalise, const LayerTiling& out,
+                          const LayerTiling& in) {
     const int k = L.ksize, s = L.stride, p = L.pad;
     if (L.kind == GNNB_LAYER_CONV) {
         const int hw_in = L.h_in * L.w_in, hw_out = L.h_out * L.w_out;
@@ -370,7 +384,7 @@ PropPlan* prop_plan_build(const LayerDev& L, const float* w, bool backward, bool
                         }
                     }
             };
-            return build_plan(grid_tiles(L.c_out, L.h_out, L.w_out), f, L.n_in, L.n_out);
+            return build_plan(out, in, f);
         }
         EdgeFn f = [=](int node, std::vector<Edge>& ev) {
             const int ci = node / hw_in, yi = (node % hw_in) / L.w_in, xi = node % L.w_in;
@@ -390,18 +404,18 @@ PropPlan* prop_plan_build(const LayerDev& L, const float* w, bool backward, bool
             if (normalise && taps > 0)      // conv_transpose2d(.) / freq, freq = tap count (graph_conv.py:306-312)
                 for (size_t i = first; i < ev.size(); ++i) ev[i].w = ev[i].w / (float)taps;
         };
-        return build_plan(grid_tiles(L.c_in, L.h_in, L.w_in), f, L.n_out, L.n_in);
+        return build_plan(out, in, f);
     }
     if (!backward) {
         EdgeFn f = [=](int node, std::vector<Edge>& ev) {
             for (int i = 0; i < L.n_in; ++i) ev.push_back({i, w[(size_t)node * L.n_in + i]});
         };
-        return build_plan(range_tiles(L.n_out), f, L.n_in, L.n_out);
+        return build_plan(out, in, f);
     }
     EdgeFn f = [=](int node, std::vector<Edge>& ev) {
         for (int o = 0; o < L.n_out; ++o) ev.push_back({o, w[(size_t)o * L.n_in + node]});
     };
-    return build_plan(range_tiles(L.n_in), f, L.n_out, L.n_in);
+    return build_plan(out, in, f);
 }
 
 void prop_plan_free(PropPlan* p) {
@@ -423,12 +437,13 @@ void prop_tc_run(const PropPlan* plan, const float* mu_img, float* nb_img, int B
 // nb[b, n, :] = Wp[b, n] * mu[L+1][b, :] (graph_conv.py:324-326) written as the fp16 tile image
 namespace {
 __global__ void k_property_backward_img(const float* __restrict__ wp, const float* __restrict__ mu_out,
-                                        uint16_t* __restrict__ nb_img, int nL, int64_t total8) {
+                                        uint16_t* __restrict__ nb_img, int nL, int nslots, int64_t total8) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
         const int chunk = (int)(i & 7);
-        const int64_t row = i >> 3;              // b * nL + n
-        const int64_t b = row / nL;
-        const float w = wp[row] * ASCALE;
+        const int64_t row = i >> 3;              // b * nslots + slot; the last hidden layer is flat: slot = node
+        const int64_t b = row / nslots;
+        const int node = (int)(row - b * nslots);
+        const float w = node < nL ? wp[b * nL + node] * ASCALE : 0.f;
         const float4 m0 = *reinterpret_cast<const float4*>(mu_out + b * P + chunk * 8);
         const float4 m1 = *reinterpret_cast<const float4*>(mu_out + b * P + chunk * 8 + 4);
         uint4 hi, lo;
@@ -444,11 +459,11 @@ __global__ void k_property_backward_img(const float* __restrict__ wp, const floa
 }
 }  // namespace
 
-void prop_tc_property_backward(const float* wp, const float* mu_out, float* nb_img, int nL, int Bc, cudaStream_t st, int64_t* launches) {
-    const int64_t total8 = (int64_t)Bc * nL * 8;
+void prop_tc_property_backward(const float* wp, const float* mu_out, float* nb_img, int nL, int nslots, int Bc, cudaStream_t st, int64_t* launches) {
+    const int64_t total8 = (int64_t)Bc * nslots * 8;
     const int64_t blocks = (total8 + 255) / 256;
     k_property_backward_img<<<(unsigned)(blocks < 1 ? 1 : (blocks < 148 * 16 ? blocks : 148 * 16)), 256, 0, st>>>(
-        wp, mu_out, reinterpret_cast<uint16_t*>(nb_img), nL, total8);
+        wp, mu_out, reinterpret_cast<uint16_t*>(nb_img), nL, nslots, total8);
     ++*launches;
 }
 

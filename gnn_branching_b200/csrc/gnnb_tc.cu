@@ -208,7 +208,7 @@ __device__ __forceinline__ void first_layer_to_a(const WG& c, const float (&feat
 // TO_A: the same values also become the next A operand (score head).  Returns true on NaN in a valid row.
 template <bool TO_A>
 __device__ __forceinline__ bool epilogue_to_mu(const WG& c, uint32_t dcol, const float* __restrict__ bias_s, float rowscale,
-                                               int64_t row0, int64_t rows) {
+                                               bool valid) {
     bool bad = false;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -233,7 +233,7 @@ __device__ __forceinline__ bool epilogue_to_mu(const WG& c, uint32_t dcol, const
         }
         if (TO_A) tmem_st16(c.tmem + ACOL + 16 * q, w);
     }
-    return bad && (row0 + c.t < rows);
+    return bad && valid;
 }
 // the staged tile image -> global with one bulk store; then (optionally) the next tile's nb image into the same buffer
 __device__ __forceinline__ void commit_tile(const WG& c, void* dst_tile, const void* next_nb) {
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_update(GnnParams g, int bac
                                                             const float* __restrict__ ub, const uint16_t* __restrict__ nb_img,
                                                             const float* __restrict__ rlx, const int32_t* __restrict__ amb_base,
                                                             uint16_t* __restrict__ mu_out,
-                                                            float* __restrict__ scores, int n, int64_t score_stride,
+                                                            float* __restrict__ scores, RowMap map, int64_t score_stride,
                                                             int64_t score_off, int64_t rows, unsigned long long* nan_count) {
     const int l3 = backward ? BC3 : FC3, l4b = backward ? BC4_1 : FC4_2, lc = backward ? T_BWD_C : T_FWD_C;
     const uint16_t* const wsrc[4] = {g.tc[l3], g.tcx_w[lc], g.tc[l4b], g.tc[FNODE]};
@@ -367,12 +367,13 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_update(GnnParams g, int bac
         const int64_t row0 = tile * TILE, grow = row0 + c.t;
         const bool has_next = tile + tile_step < ntiles;
         float l = 0.f, u = 1.f;
-        if (grow < rows) { l = ldg1_now(lb + grow); u = ldg1_now(ub + grow); }
+        const int64_t nrow = natural_row(map, grow);           // index into the caller's [B, n] arrays, -1 = padding slot
+        if (nrow >= 0) { l = ldg1_now(lb + nrow); u = ldg1_now(ub + nrow); }
         const int slot0 = __ldg(amb_base + tile);
         const Ratio q = compute_ratio(l, u);
         const float gate = (q.r0 != 0.0f) ? 1.0f : 0.0f;
         // slot of this row's relax' = first slot of the tile + number of ambiguous rows before it (amb_compact keeps row order)
-        const bool amb = (q.amb != 0.0f) && grow < rows;
+        const bool amb = (q.amb != 0.0f) && nrow >= 0;
         const unsigned bal = __ballot_sync(0xffffffffu, amb);
         if ((c.t & 31) == 0) tl.wcnt[c.wg][c.t >> 5] = __popc(bal);
         GNNB_TR(0);
@@ -434,10 +435,10 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_update(GnnParams g, int bac
         GNNB_TR(5);
         const void* next_nb = has_next ? nb_img + (size_t)(tile + tile_step) * (ABUF / 2) : nullptr;
         if (scores == nullptr) {
-            bad |= epilogue_to_mu<false>(c, DCOL, tl.bias[2], gate, row0, rows);
+            bad |= epilogue_to_mu<false>(c, DCOL, tl.bias[2], gate, nrow >= 0);
             commit_tile(c, mu_out + (size_t)tile * (ABUF / 2), next_nb);
         } else {      // score head on the new embeddings (graph_conv.py:448-449)
-            bad |= epilogue_to_mu<true>(c, DCOL, tl.bias[2], gate, row0, rows);
+            bad |= epilogue_to_mu<true>(c, DCOL, tl.bias[2], gate, nrow >= 0);
             commit_tile(c, mu_out + (size_t)tile * (ABUF / 2), next_nb);
             gemm_ts(c, W + UPD_FN, W + UPD_FN + WPLANE, 64, DCOL);
             float sc = 0.f;
@@ -450,7 +451,7 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_update(GnnParams g, int bac
 #pragma unroll
                 for (int j = 0; j < 16; ++j) sc = fmaf(relu_nan(v[j] + bb[j]), ww[j], sc);
             }
-            if (grow < rows) scores[(grow / n) * score_stride + score_off + (grow % n)] = fmaf(sc, AINV, bscore);
+            if (nrow >= 0) scores[(nrow / map.n) * score_stride + score_off + (nrow % map.n)] = fmaf(sc, AINV, bscore);
         }
         GNNB_TR(6);
         GNNB_TR_NEXT();
@@ -487,11 +488,11 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_relax(GnnParams g, NodeInpu
         const int64_t slot = tile * TILE + c.t;
         float l = 0.f, u = 1.f, d1 = 0.f, d2 = 0.f, pp = 0.f, po = 0.f, bs = 0.f;
         if (slot < namb) {
-            const int64_t grow = __ldg(in.amb_rows + slot);
+            const int64_t grow = natural_row(in.map, __ldg(in.amb_rows + slot));      // ambiguous rows are never padding
             l = in.lb[grow]; u = in.ub[grow];
             d1 = in.dual[grow * 3 + 1]; d2 = in.dual[grow * 3 + 2];
             pp = in.prim_pre[grow]; po = in.prim_post[grow];
-            bs = in.bias_node[grow % in.n];
+            bs = in.bias_node[grow % in.map.n];
         }
         const Ratio q = compute_ratio(l, u);
         // forward: relax' = amb * (Wr relu(fc1([beta, l, u, d1-d2, x_pre, x_post, bias])) + br)   (graph_conv.py:153-161, :176)
@@ -553,7 +554,7 @@ constexpr uint32_t EMB_WBYTES = 2 * WPLANE;
 
 __global__ void __launch_bounds__(128 * NWG, 1) k_tc_input_embed(GnnParams g, const float* __restrict__ lb0,
                                                                  const float* __restrict__ x, const float* __restrict__ ub0,
-                                                                 uint16_t* __restrict__ mu0, int64_t rows) {
+                                                                 uint16_t* __restrict__ mu0, RowMap map, int64_t rows) {
     const uint16_t* const wsrc[1] = {g.tc[INP_F_1]};
     const uint32_t woff[1] = {0};
     const uint32_t wlen[1] = {2 * WPLANE};
@@ -567,11 +568,12 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_input_embed(GnnParams g, co
     for (int64_t tile = (int64_t)blockIdx.x * NWG + c.wg; tile < ntiles; tile += (int64_t)gridDim.x * NWG) {
         const int64_t row0 = tile * TILE, grow = row0 + c.t;
         float feat[3] = {0.f, 0.f, 0.f};
-        if (grow < rows) { feat[0] = lb0[grow]; feat[1] = x[grow]; feat[2] = ub0[grow]; }
+        const int64_t nrow = grow < rows ? natural_row(map, grow) : -1;
+        if (nrow >= 0) { feat[0] = lb0[nrow]; feat[1] = x[nrow]; feat[2] = ub0[nrow]; }
         first_layer_to_a<3>(c, feat, tl.w_small[0], tl.bias[5]);
         if (c.t == 0) bulk_wait_read();          // the previous tile's bulk store has read the staging buffer
         gemm_ts(c, s.w, s.w + WPLANE, 64, DCOL);
-        epilogue_to_mu<false>(c, DCOL, tl.bias[0], 1.0f, row0, rows);
+        epilogue_to_mu<false>(c, DCOL, tl.bias[0], 1.0f, nrow >= 0);
         commit_tile(c, mu0 + (size_t)tile * (ABUF / 2), nullptr);
     }
     if (c.t == 0) bulk_wait_all();
@@ -584,7 +586,7 @@ constexpr uint32_t INU_WI = 0, INU_WN = 2 * WPLANE, INU_B22 = 4 * WPLANE, INU_WB
 
 __global__ void __launch_bounds__(128 * NWG, 1) k_tc_input_update(GnnParams g, const float* __restrict__ lb0,
                                                                   const float* __restrict__ ub0, const uint16_t* __restrict__ nb_img,
-                                                                  uint16_t* __restrict__ mu0, int64_t rows) {
+                                                                  uint16_t* __restrict__ mu0, RowMap map, int64_t rows) {
     const uint16_t* const wsrc[3] = {g.tcx_w[T_INP_C], g.tcx_w[T_INP_NB], g.tc[INP_B2_2]};
     const uint32_t woff[3] = {INU_WI, INU_WN, INU_B22};
     const uint32_t wlen[3] = {2 * WPLANE, 2 * WPLANE, 2 * WPLANE};
@@ -603,7 +605,8 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_input_update(GnnParams g, c
     for (; tile < ntiles; tile += tile_step) {
         const int64_t row0 = tile * TILE, grow = row0 + c.t;
         float feat[2] = {0.f, 0.f};
-        if (grow < rows) { feat[0] = lb0[grow]; feat[1] = ub0[grow]; }
+        const int64_t nrow = grow < rows ? natural_row(map, grow) : -1;
+        if (nrow >= 0) { feat[0] = lb0[nrow]; feat[1] = ub0[nrow]; }
         first_layer_to_a<2>(c, feat, tl.w_small[0], tl.bias[5]);
         // D = Wi relu(inp_b(.)) + Wn nb: both products into the one accumulator, one commit
         gemm_sync(c);
@@ -620,7 +623,7 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_input_update(GnnParams g, c
         if (has_next && c.t == 0) prefetch_l2(nb_img + (size_t)(tile + tile_step) * (ABUF / 2), ABUF);
         epilogue_to_a<true>(c, DCOL, tl.bias[0]);
         gemm_ts(c, W + INU_B22, W + INU_B22 + WPLANE, 64, DCOL);
-        epilogue_to_mu<false>(c, DCOL, tl.bias[1], 1.0f, row0, rows);
+        epilogue_to_mu<false>(c, DCOL, tl.bias[1], 1.0f, nrow >= 0);
         commit_tile(c, mu0 + (size_t)tile * (ABUF / 2), has_next ? nb_img + (size_t)(tile + tile_step) * (ABUF / 2) : nullptr);
     }
     if (c.t == 0) bulk_wait_all();
@@ -635,24 +638,32 @@ int grid_for(int64_t rows) {
 }
 
 // tile images (hi + lo planes, scaled domain) -> fp32 [rows][64]; debugging snapshots and the output-node kernel's view
-__global__ void k_unpack_tile_image(const uint16_t* __restrict__ img, float* __restrict__ out, int64_t rows, int piece_major) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // one thread per (row, 8-channel chunk)
+__global__ void k_unpack_tile_image(const uint16_t* __restrict__ img, float* __restrict__ out, RowMap map, int64_t rows,
+                                    int piece_major) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // one thread per (slot row, 8-channel chunk)
     if (i >= rows * 8) return;
     const int64_t row = i >> 3;
+    const int64_t nrow = natural_row(map, row);
+    if (nrow < 0) return;
     const int chunk = (int)(i & 7);
     const int64_t tile = row / TILE;
     const uint32_t r = (uint32_t)(row % TILE);
     const uint32_t off = piece_major ? (uint32_t)chunk * NB_PIECE + r * 16u : swz(r, (uint32_t)chunk);
     const __half* hi = reinterpret_cast<const __half*>(img) + tile * (ABUF / 2) + off / 2;
     const __half* lo = hi + APLANE / 2;
-    for (int j = 0; j < 8; ++j) out[row * P + chunk * 8 + j] = (__half2float(hi[j]) + __half2float(lo[j])) * AINV;
+    for (int j = 0; j < 8; ++j) out[nrow * P + chunk * 8 + j] = (__half2float(hi[j]) + __half2float(lo[j])) * AINV;
 }
 
 // ---- compaction of the ambiguous rows (three small launches per layer and chunk) ---------------------------------
-__global__ void __launch_bounds__(TILE) k_amb_count(const float* __restrict__ lb, const float* __restrict__ ub, int64_t rows,
-                                                    int32_t* __restrict__ cnt) {
+__device__ __forceinline__ bool row_is_ambiguous(const float* __restrict__ lb, const float* __restrict__ ub, const RowMap& map,
+                                                 int64_t row, int64_t rows) {
+    const int64_t nrow = row < rows ? natural_row(map, row) : -1;
+    return nrow >= 0 && compute_ratio(lb[nrow], ub[nrow]).amb != 0.0f;
+}
+__global__ void __launch_bounds__(TILE) k_amb_count(const float* __restrict__ lb, const float* __restrict__ ub, RowMap map,
+                                                    int64_t rows, int32_t* __restrict__ cnt) {
     const int64_t row = (int64_t)blockIdx.x * TILE + threadIdx.x;
-    const bool amb = row < rows && compute_ratio(lb[row], ub[row]).amb != 0.0f;
+    const bool amb = row_is_ambiguous(lb, ub, map, row, rows);
     const int total = __syncthreads_count(amb);
     if (threadIdx.x == 0) cnt[blockIdx.x] = total;
 }
@@ -674,11 +685,11 @@ __global__ void __launch_bounds__(1024) k_amb_scan(const int32_t* __restrict__ c
     for (int i = lo; i < hi; ++i) { base[i] = run; run += cnt[i]; }
     if (threadIdx.x == 1023) base[n] = part[1023];
 }
-__global__ void __launch_bounds__(TILE) k_amb_fill(const float* __restrict__ lb, const float* __restrict__ ub, int64_t rows,
-                                                   const int32_t* __restrict__ base, int32_t* __restrict__ amb_rows) {
+__global__ void __launch_bounds__(TILE) k_amb_fill(const float* __restrict__ lb, const float* __restrict__ ub, RowMap map,
+                                                   int64_t rows, const int32_t* __restrict__ base, int32_t* __restrict__ amb_rows) {
     __shared__ int32_t wc[4];
     const int64_t row = (int64_t)blockIdx.x * TILE + threadIdx.x;
-    const bool amb = row < rows && compute_ratio(lb[row], ub[row]).amb != 0.0f;
+    const bool amb = row_is_ambiguous(lb, ub, map, row, rows);
     const unsigned bal = __ballot_sync(0xffffffffu, amb);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) wc[warp] = __popc(bal);
@@ -690,12 +701,12 @@ __global__ void __launch_bounds__(TILE) k_amb_fill(const float* __restrict__ lb,
 
 }  // namespace
 
-void amb_compact(const float* lb, const float* ub, int64_t rows, int32_t* cnt, int32_t* amb_base, int32_t* amb_rows,
+void amb_compact(const float* lb, const float* ub, RowMap map, int64_t rows, int32_t* cnt, int32_t* amb_base, int32_t* amb_rows,
                  cudaStream_t st, int64_t* launches) {
     const int ntiles = (int)((rows + TILE - 1) / TILE);
-    k_amb_count<<<ntiles, TILE, 0, st>>>(lb, ub, rows, cnt);
+    k_amb_count<<<ntiles, TILE, 0, st>>>(lb, ub, map, rows, cnt);
     k_amb_scan<<<1, 1024, 0, st>>>(cnt, amb_base, ntiles);
-    k_amb_fill<<<ntiles, TILE, 0, st>>>(lb, ub, rows, amb_base, amb_rows);
+    k_amb_fill<<<ntiles, TILE, 0, st>>>(lb, ub, map, rows, amb_base, amb_rows);
     *launches += 3;
 }
 
@@ -735,30 +746,30 @@ void tc_relax(const GnnParams& g, const NodeInputs& in, float* relax_f, float* r
 }
 
 void tc_update(const GnnParams& g, bool backward, const float* lb, const float* ub, const float* nb, const float* relax,
-               const int32_t* amb_base, float* mu_out, float* scores, int n, int64_t score_stride, int64_t score_off, int64_t rows,
+               const int32_t* amb_base, float* mu_out, float* scores, RowMap map, int64_t score_stride, int64_t score_off, int64_t rows,
                unsigned long long* nan_count, cudaStream_t st, int64_t* launches) {
     k_tc_update<<<grid_for(rows), 128 * NWG, smem_bytes(UPD_WBYTES, true), st>>>(
-        g, backward ? 1 : 0, lb, ub, reinterpret_cast<const uint16_t*>(nb), relax, amb_base, reinterpret_cast<uint16_t*>(mu_out), scores, n,
+        g, backward ? 1 : 0, lb, ub, reinterpret_cast<const uint16_t*>(nb), relax, amb_base, reinterpret_cast<uint16_t*>(mu_out), scores, map,
         score_stride, score_off, rows, nan_count);
     ++*launches;
 }
 
-void tc_input_embed(const GnnParams& g, const float* lb0, const float* x, const float* ub0, float* mu0, int64_t rows,
+void tc_input_embed(const GnnParams& g, const float* lb0, const float* x, const float* ub0, float* mu0, RowMap map, int64_t rows,
                     cudaStream_t st, int64_t* launches) {
-    k_tc_input_embed<<<grid_for(rows), 128 * NWG, smem_bytes(EMB_WBYTES, true), st>>>(g, lb0, x, ub0, reinterpret_cast<uint16_t*>(mu0), rows);
+    k_tc_input_embed<<<grid_for(rows), 128 * NWG, smem_bytes(EMB_WBYTES, true), st>>>(g, lb0, x, ub0, reinterpret_cast<uint16_t*>(mu0), map, rows);
     ++*launches;
 }
 
-void tc_input_update(const GnnParams& g, const float* lb0, const float* ub0, const float* nb, float* mu0, int64_t rows,
+void tc_input_update(const GnnParams& g, const float* lb0, const float* ub0, const float* nb, float* mu0, RowMap map, int64_t rows,
                      cudaStream_t st, int64_t* launches) {
     k_tc_input_update<<<grid_for(rows), 128 * NWG, smem_bytes(INU_WBYTES, true), st>>>(
-        g, lb0, ub0, reinterpret_cast<const uint16_t*>(nb), reinterpret_cast<uint16_t*>(mu0), rows);
+        g, lb0, ub0, reinterpret_cast<const uint16_t*>(nb), reinterpret_cast<uint16_t*>(mu0), map, rows);
     ++*launches;
 }
 
-void tc_unpack_tile_image(const float* img, float* out, int64_t rows, bool piece_major, cudaStream_t st) {
+void tc_unpack_tile_image(const float* img, float* out, RowMap map, int64_t rows, bool piece_major, cudaStream_t st) {
     const int64_t n = rows * 8;
-    k_unpack_tile_image<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(img), out, rows, piece_major ? 1 : 0);
+    k_unpack_tile_image<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(img), out, map, rows, piece_major ? 1 : 0);
 }
 
 }  // namespace gnnb
