@@ -41,6 +41,7 @@ def parse():
     ap.add_argument('--weights', default='random', choices=['random', 'shipped'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--opt', action='append', default=[], help='library option key=value (e.g. fuse=0, prop_share=40)')
     return ap.parse_args()
 
 
@@ -174,15 +175,30 @@ def kernel_rooflines(net, fr, prof, n_domains, T, peak_tf, peak_gbs, p=64):
     flop['input'] = net.n0 * 2 * ((3 * p + p * p) + (T - 1) * (2 * p + 4 * p * p))
     byts['input'] = net.n0 * ((12 + row) + (T - 1) * (8 + 2 * row))
     groups = {'update': ['update_fwd', 'update_bwd', 'update_bwd_score'], 'prop': ['prop_fwd', 'prop_bwd'],
-              'relax': ['relax'], 'input': ['input_embed', 'input_update']}
-    names = {'update': 'k_tc_update (node update MLP chain, forward / backward / + score head)',
+              'relax': ['relax'], 'input': ['input_embed', 'input_update'],
+              'layer': ['layer_fwd', 'layer_bwd', 'layer_bwd_score']}
+    fused_ms = sum(prof[m]['ms'] for m in groups['layer'] if m in prof)
+    if fused_ms > 0:
+        # fused launches (propagation + update of a layer): everything except the property layer's back-propagation and the
+        # input-layer propagation; their nb hand-off goes through L2 and is not compulsory HBM traffic
+        node_bytes = [nk * (row + 8 + row * am) for nk, am in zip(n, amb)]          # mu written + l, u + relax' per sweep
+        fwd = sum(n_all[k] * row + node_bytes[k] for k in range(L))                # layer k+1 gathers layer k
+        bwd = sum(n_all[k + 2] * row + node_bytes[k] for k in range(L - 1))        # layer k+1 gathers layer k+2
+        byts['layer'] = T * (fwd + bwd) + 4 * sum(n[:-1])
+        flop['layer'] = flop['update'] + flop['prop'] - 2 * p * (T - 1) * mac[0] - n[-1] * (T * upd_f + 2 * (p * p + p))
+        flop['update'] = n[-1] * (T * upd_f + 2 * (p * p + p))                     # last hidden layer, backward sweeps
+        byts['update'] = T * (n[-1] * row + node_bytes[-1]) + 4 * n[-1]
+        flop['prop'] = 2 * p * (T - 1) * mac[0]                                    # input-layer propagation + property rank-1
+        byts['prop'] = row * (T * n[-1] + (T - 1) * (n_all[1] + n_all[0]))
+    names = {'layer': 'k_tc_layer (fused propagation gather-GEMM + node update chain of one layer)',
+             'update': 'k_tc_update (node update MLP chain, forward / backward / + score head)',
              'prop': 'k_tc_prop (embedding propagation through the verified network, gather-GEMM)',
              'relax': 'k_tc_relax (+ ambiguous-row compaction)', 'input': 'k_tc_input_embed / k_tc_input_update'}
     total_ms = sum(v['ms'] for v in prof.values()) or 1.0
     classes = {}
     for gname, members in groups.items():
-        ms = sum(prof[m]['ms'] for m in members)
-        launches = sum(prof[m]['launches'] for m in members)
+        ms = sum(prof[m]['ms'] for m in members if m in prof)
+        launches = sum(prof[m]['launches'] for m in members if m in prof)
         if ms <= 0:
             continue
         gbs = byts[gname] * n_domains / (ms * 1e-3) / 1e9
@@ -232,6 +248,9 @@ def main():
     # two different frontiers used alternately: with the workspace they exceed the 126 MB L2 several times over
     fronts = [synthetic_frontier(net, lbs, ubs, wp, bp, B, seed=1000 * (7 + rank) + i, device=dev) for i in range(2)]
     scorer = model.scorer(local)
+    for kv in args.opt:
+        key, val = kv.split('=')
+        scorer.set_option(key, int(val))
     math_mode = {0: 'tc', 1: 'simt'}[scorer.get_option('math')]
 
     def step(i):

@@ -12,7 +12,7 @@ LAYER_CONV, LAYER_LINEAR = 0, 1
 MEM_DEVICE, MEM_HOST = 0, 1
 MATH_TC_FP16X3, MATH_SIMT_FP32 = 0, 1
 KERNEL_CLASSES = ['relax', 'update_fwd', 'update_bwd', 'update_bwd_score', 'input_embed', 'input_update', 'prop_fwd',
-                  'prop_bwd', 'output', 'argmax']
+                  'prop_bwd', 'output', 'argmax', 'layer_fwd', 'layer_bwd', 'layer_bwd_score']
 
 EXPORTS = ['gnnb_create', 'gnnb_destroy', 'gnnb_set_gnn_weights', 'gnnb_set_network', 'gnnb_set_option',
            'gnnb_get_option', 'gnnb_score', 'gnnb_check', 'gnnb_launch_count', 'gnnb_last_error',

@@ -30,6 +30,10 @@ struct gnnb_ctx {
     int math = GNNB_MATH_TC_FP16X3;
     int chunk = 0;
     int snapshot = 0;
+    int fuse = 1;                   // propagation + node update of a layer in one launch (tensor-core mode)
+    int prop_share = 0;             // % of a fused launch's CTAs that propagate; 0 = cost model
+    int32_t* d_flags = nullptr;     // per-item publication flags of the fused launches; value = epoch of the launch
+    int32_t epoch = 0;
     // GNN parameters
     bool have_gnn = false;
     float* d_gnn = nullptr;
@@ -130,6 +134,12 @@ int ensure_workspace(gnnb_ctx* ctx, int Bc, bool host_staging) {
     size_t nb_rows = 0;
     for (int k = 0; k <= L; ++k) nb_rows = wrows(k) > nb_rows ? wrows(k) : nb_rows;
     const size_t o_nb = take(nb_rows * P);
+    size_t max_items = 0;
+    for (int k = 0; k <= L; ++k) {
+        const size_t items = (size_t)(ctx->rowmap[k].nslots / 128) * ((Bc + 3) / 4);
+        max_items = items > max_items ? items : max_items;
+    }
+    const size_t o_flags = take(max_items);
     const size_t o_sc = take((size_t)Bc * ctx->n_hidden);
     const size_t o_best = take(Bc), o_idx = take(Bc);
     struct StgOff { std::vector<size_t> lb, ub, du, pr, po; size_t pout, pin, wp, bp, mask, best, idx, sc; } so[2];
@@ -159,6 +169,9 @@ int ensure_workspace(gnnb_ctx* ctx, int Bc, bool host_staging) {
         ctx->amb_base[k] = reinterpret_cast<int32_t*>(base + o_ab[k]);
         ctx->amb_rows[k] = reinterpret_cast<int32_t*>(base + o_ar[k]);
     }
+    ctx->d_flags = reinterpret_cast<int32_t*>(base + o_flags);
+    CU(cudaMemset(ctx->d_flags, 0, max_items * sizeof(int32_t)));
+    ctx->epoch = 0;
     ctx->nb = base + o_nb; ctx->ws_scores = base + o_sc; ctx->ws_best = base + o_best;
     ctx->ws_idx = reinterpret_cast<int32_t*>(base + o_idx);
     if (host_staging) {
@@ -266,6 +279,7 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
     auto R = [&](int k) { return (int64_t)Bc * (tc ? ctx->rowmap[k].nslots : ctx->n[k]); };
     const RowMap nomap{nullptr, 0, 0};
     auto M = [&](int k) { return tc ? ctx->rowmap[k] : nomap; };
+    const bool fused = tc && ctx->fuse;
 
     // round-independent relaxation features of every hidden layer
     for (int k = 1; k <= L; ++k) {
@@ -293,13 +307,17 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
         // forward sweep
         for (int k = 1; k <= L; ++k) {
             const int64_t rows = R(k), nodes = (int64_t)Bc * ctx->n[k];
-            {
+            if (fused) {
+                ProfScope ps(ctx, GNNB_K_LAYER_FWD, nodes, st);
+                tc_layer(g, ctx->plan_fwd[k - 1], ctx->mu[k - 1], false, in.lb[k], in.ub[k], ctx->nb, ctx->relax_f[k], ctx->amb_base[k],
+                         ctx->mu[k], nullptr, M(k), 0, 0, rows, ctx->d_nan, ctx->d_flags, ++ctx->epoch, ctx->prop_share, st, lc);
+            } else {
                 ProfScope ps(ctx, GNNB_K_PROP_FWD, nodes, st);
                 if (tc) prop_tc_run(ctx->plan_fwd[k - 1], ctx->mu[k - 1], ctx->nb, Bc, st, lc);
                 else prop_forward(ctx->layers[k - 1], ctx->mu[k - 1], ctx->nb, Bc, st, lc);
             }
             TRY(snap_img(ctx, name("t%d_fwd_nb%d", t, k), ctx->nb, k, Bc, true, st));
-            {
+            if (!fused) {
                 ProfScope ps(ctx, GNNB_K_UPDATE_FWD, nodes, st);
                 if (tc) tc_update(g, false, in.lb[k], in.ub[k], ctx->nb, ctx->relax_f[k], ctx->amb_base[k], ctx->mu[k], nullptr, M(k), 0, 0, rows, ctx->d_nan, st, lc);
                 else simt_update(g, false, in.lb[k], in.ub[k], ctx->nb, ctx->relax_f[k], ctx->mu[k], nullptr, ctx->n[k], 0, 0, rows, ctx->d_nan, st, lc);
@@ -315,7 +333,14 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
         // backward sweep
         for (int k = L; k >= 1; --k) {
             const int64_t rows = R(k), nodes = (int64_t)Bc * ctx->n[k];
-            {
+            float* sc = last ? scores : nullptr;
+            const bool fused_k = fused && k < L;           // the property layer's rank-1 back-propagation is a separate small kernel
+            if (fused_k) {
+                ProfScope ps(ctx, last ? GNNB_K_LAYER_BWD_SCORE : GNNB_K_LAYER_BWD, nodes, st);
+                tc_layer(g, ctx->plan_bwd[k], ctx->mu[k + 1], true, in.lb[k], in.ub[k], ctx->nb, ctx->relax_b[k], ctx->amb_base[k],
+                         ctx->mu[k], sc, M(k), ctx->n_hidden, ctx->hidden_off[k], rows, ctx->d_nan, ctx->d_flags, ++ctx->epoch,
+                         ctx->prop_share, st, lc);
+            } else {
                 ProfScope ps(ctx, GNNB_K_PROP_BWD, nodes, st);
                 if (k == L && tc) prop_tc_property_backward(in.wp, ctx->mu[L + 1], ctx->nb, ctx->n[L], ctx->rowmap[L].nslots, Bc, st, lc);
                 else if (k == L) prop_property_backward(in.wp, ctx->mu[L + 1], ctx->nb, ctx->n[L], Bc, st, lc);
@@ -323,8 +348,7 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
                 else prop_backward(ctx->layers[k], ctx->mu[k + 1], ctx->nb, Bc, true, st, lc);
             }
             TRY(snap_img(ctx, name("t%d_bwd_nb%d", t, k), ctx->nb, k, Bc, true, st));
-            float* sc = last ? scores : nullptr;
-            {
+            if (!fused_k) {
                 ProfScope ps(ctx, last ? GNNB_K_UPDATE_BWD_SCORE : GNNB_K_UPDATE_BWD, nodes, st);
                 if (tc) tc_update(g, true, in.lb[k], in.ub[k], ctx->nb, ctx->relax_b[k], ctx->amb_base[k], ctx->mu[k], sc, M(k), ctx->n_hidden, ctx->hidden_off[k], rows, ctx->d_nan, st, lc);
                 else simt_update(g, true, in.lb[k], in.ub[k], ctx->nb, ctx->relax_b[k], ctx->mu[k], sc, ctx->n[k], ctx->n_hidden, ctx->hidden_off[k], rows, ctx->d_nan, st, lc);
@@ -605,6 +629,11 @@ int gnnb_set_option(gnnb_ctx* ctx, const char* key, int64_t value) {
     } else if (k == "chunk") {
         if (value < 0) return fail(ctx, GNNB_ERR_INVALID, "chunk must be >= 0");
         ctx->chunk = (int)value;
+    } else if (k == "fuse") {
+        ctx->fuse = value ? 1 : 0;
+    } else if (k == "prop_share") {
+        if (value < 0 || value > 99) return fail(ctx, GNNB_ERR_INVALID, "prop_share is a percentage in [0, 99]");
+        ctx->prop_share = (int)value;
     } else if (k == "snapshot") {
         ctx->snapshot = value ? 1 : 0;
     } else if (k == "profile") {
@@ -621,6 +650,8 @@ int64_t gnnb_get_option(gnnb_ctx* ctx, const char* key) {
     if (k == "math") return ctx->math;
     if (k == "chunk") return ctx->chunk;
     if (k == "snapshot") return ctx->snapshot;
+    if (k == "fuse") return ctx->fuse;
+    if (k == "prop_share") return ctx->prop_share;
     if (k == "profile") return ctx->profile;
     if (k == "n_hidden") return ctx->n_hidden;
     if (k == "workspace_domains") return ctx->ws_cap;

@@ -15,20 +15,9 @@
 #include <map>
 #include <vector>
 
-#include "gnnb_umma.cuh"
+#include "gnnb_prop_body.cuh"
 
 namespace gnnb {
-
-using namespace tcx;
-
-struct PropPlanDev {
-    const int32_t* in_rows;       // [nchunks][64] input slot of each K row, -1 = zero row
-    const uint16_t* a_planes;     // [nchunks][2][128 * 64] hi plane then lo plane, 32 KB per chunk
-    const int32_t* tile_chunk0;   // [ntiles + 1] first chunk of each tile
-    const int32_t* ksteps;        // [nchunks] K = 16 steps that hold data (1..4)
-    int ntiles;                   // tiles of the output layer = its slots / 128
-    int nslots_in, nslots_out;    // rows per subdomain of the input / output layer (slot order, gnnb_common.cuh)
-};
 
 struct PropPlan {
     PropPlanDev dev{};
@@ -39,194 +28,10 @@ struct PropPlan {
 
 namespace {
 
-// ---- the gather-GEMM kernel ---------------------------------------------------------------------------------
-// A persistent CTA (1 per SM) walks items = (tile of 128 output nodes, group of PD = 4 subdomains); per K chunk
-//   D[128 nodes x (4 subdomains x 64 channels)] += Wblock[128 x 64] * Mu[64 input nodes x (4 x 64)]
-// as tcgen05.mma M = 128, N = 256, K = 16, three passes for the fp16 hi/lo split (Wh Mh + Wl Mh + Wh Ml).
-// Warp roles (14 warps), decoupled by mbarrier rings:
-//   warp 0      TMA: the chunk's 32 KB weight block (hi, lo plane; K-major SWIZZLE_128B)      -> W ring, 3 stages
-//   warp 1      MMA issue + tcgen05.commit (frees ring stages, publishes accumulators)
-//   warps 2-5   gather, one subdomain each: the chunk's input-node rows are copied with 16-byte cp.async straight
-//               from the mu tile images (already fp16 hi/lo, scaled) into the MN-major SWIZZLE_128B B operand — no
-//               registers, no conversion; half a chunk (32 rows x 4 subdomains x 2 planes = 32 KB) per stage, 4 stages
-//   warps 6-13  two epilogue warpgroups, alternating items on a double-buffered accumulator (2 x 256 TMEM columns):
-//               tcgen05.ld -> fp16 hi/lo split -> piece-major nb tile image (consecutive rows = consecutive 16 bytes)
-constexpr int PD = 4;
-constexpr int W_STAGES = 3, B_STAGES = 4;
-constexpr uint32_t W_STAGE_BYTES = 2 * APLANE;            // 32 KB
-constexpr uint32_t B_ROWS = 32;                           // input nodes per B stage (half a chunk = 2 K steps)
-constexpr uint32_t B_DOM_BYTES = B_ROWS * 128;            // 4 KB: one plane of one subdomain
-constexpr uint32_t B_PLANE_BYTES = PD * B_DOM_BYTES;      // 16 KB
-constexpr uint32_t B_STAGE_BYTES = 2 * B_PLANE_BYTES;     // 32 KB
-constexpr int PROP_WARPS = 14, PROP_THREADS = PROP_WARPS * 32;
-constexpr int GATHER_WARP0 = 2, EPI_WARP0 = 6;
-
-struct PropTail {
-    uint64_t w_full[W_STAGES], w_empty[W_STAGES], b_full[B_STAGES], b_empty[B_STAGES], acc_full[2], acc_empty[2];
-    uint32_t tmem_slot;
-};
-constexpr size_t PROP_SMEM = 1024 + W_STAGES * W_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + sizeof(PropTail);
-
-__global__ void __launch_bounds__(PROP_THREADS, 1) k_tc_prop(PropPlanDev plan, const uint16_t* __restrict__ mu_img,
-                                                             uint16_t* __restrict__ nb_img, int Bc) {
+__global__ void __launch_bounds__(prop::PROP_THREADS, 1) k_tc_prop(PropPlanDev plan, const uint16_t* __restrict__ mu_img,
+                                                                   uint16_t* __restrict__ nb_img, int Bc) {
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
-    const uint32_t w_ring = smem_u32(base), b_ring = w_ring + W_STAGES * W_STAGE_BYTES;
-    PropTail* tail = reinterpret_cast<PropTail*>(base + W_STAGES * W_STAGE_BYTES + B_STAGES * B_STAGE_BYTES);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < W_STAGES; ++i) { mbar_init(smem_u32(&tail->w_full[i]), 1); mbar_init(smem_u32(&tail->w_empty[i]), 1); }
-        for (int i = 0; i < B_STAGES; ++i) { mbar_init(smem_u32(&tail->b_full[i]), PD * 32); mbar_init(smem_u32(&tail->b_empty[i]), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tail->acc_full[i]), 1); mbar_init(smem_u32(&tail->acc_empty[i]), 128); }
-        fence_mbar_init();
-    }
-    __syncwarp();
-    if (warp == 0) tmem_alloc(smem_u32(&tail->tmem_slot), 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = tail->tmem_slot;
-
-    const int ngroups = (Bc + PD - 1) / PD;
-    const int64_t nitems = (int64_t)plan.ntiles * ngroups;       // item = group * ntiles + tile
-
-    if (warp == 0) {
-        // ---- weight blocks ----
-        if (lane == 0) {
-            uint32_t ws = 0, wph = 0;
-            for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
-                const int tile = (int)(item % plan.ntiles);
-                const int ch0 = plan.tile_chunk0[tile], ch1 = plan.tile_chunk0[tile + 1];
-                for (int ch = ch0; ch < ch1; ++ch) {
-                    mbar_wait(smem_u32(&tail->w_empty[ws]), wph ^ 1u);
-                    const uint32_t full = smem_u32(&tail->w_full[ws]);
-                    mbar_expect_tx(full, W_STAGE_BYTES);
-                    bulk_g2s(w_ring + ws * W_STAGE_BYTES, plan.a_planes + (size_t)ch * (W_STAGE_BYTES / 2), W_STAGE_BYTES, full);
-                    if (++ws == W_STAGES) { ws = 0; wph ^= 1u; }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ---- MMA issue ----
-        if (lane == 0) {
-            // D fp32, A fp16 K-major, B fp16 MN-major (bit 16), M = 128, N = 256
-            const uint32_t idesc = (1u << 4) | (1u << 16) | ((uint32_t)(PD * 64 >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
-            uint32_t ws = 0, wph = 0, bs = 0, bph = 0, it = 0;
-            for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
-                const int tile = (int)(item % plan.ntiles);
-                const int ch0 = plan.tile_chunk0[tile], ch1 = plan.tile_chunk0[tile + 1];
-                const uint32_t a = it & 1u, aph = (it >> 1) & 1u;
-                mbar_wait(smem_u32(&tail->acc_empty[a]), aph ^ 1u);      // the epilogue has drained this accumulator
-                tc_fence_after();
-                const uint32_t d = (tmem_base & 0x0000FFFFu) + a * 256u;
-                uint32_t first = 1;
-                for (int ch = ch0; ch < ch1; ++ch) {
-                    mbar_wait(smem_u32(&tail->w_full[ws]), wph);
-                    const int nks = plan.ksteps[ch];
-                    const uint32_t wa = w_ring + ws * W_STAGE_BYTES;
-                    for (int h = 0; 2 * h < nks; ++h) {
-                        mbar_wait(smem_u32(&tail->b_full[bs]), bph);
-                        tc_fence_after();
-                        const uint32_t ba = b_ring + bs * B_STAGE_BYTES;
-                        const int kc = (nks - 2 * h) < 2 ? (nks - 2 * h) : 2;
-#pragma unroll
-                        for (int pass = 0; pass < 3; ++pass) {
-                            const uint64_t ad = make_desc(pass == 1 ? wa + APLANE : wa);
-                            const uint64_t bd = make_desc_mn(pass == 2 ? ba + B_PLANE_BYTES : ba, B_DOM_BYTES);
-                            for (int kk = 0; kk < kc; ++kk) {
-                                umma(d, ad + 2 * (2 * h + kk), bd + 128 * kk, idesc, first ? 0u : 1u);
-                                first = 0;
-                            }
-                        }
-                        umma_commit(smem_u32(&tail->b_empty[bs]));
-                        if (++bs == B_STAGES) { bs = 0; bph ^= 1u; }
-                    }
-                    umma_commit(smem_u32(&tail->w_empty[ws]));
-                    if (++ws == W_STAGES) { ws = 0; wph ^= 1u; }
-                }
-                umma_commit(smem_u32(&tail->acc_full[a]));
-            }
-        }
-    } else if (warp < EPI_WARP0) {
-        // ---- gather: warp g copies the rows of subdomain d0 + g ----
-        const int g = warp - GATHER_WARP0;
-        const unsigned char* mu_bytes = reinterpret_cast<const unsigned char*>(mu_img);
-        uint32_t bs = 0, bph = 0;
-        for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
-            const int tile = (int)(item % plan.ntiles);
-            const int d = (int)(item / plan.ntiles) * PD + g;
-            const bool dom_ok = d < Bc;
-            const int64_t drow = (int64_t)d * plan.nslots_in;
-            const int ch0 = plan.tile_chunk0[tile], ch1 = plan.tile_chunk0[tile + 1];
-            for (int ch = ch0; ch < ch1; ++ch) {
-                const int nks = plan.ksteps[ch];
-                for (int h = 0; 2 * h < nks; ++h) {
-                    const int idx = __ldg(plan.in_rows + (size_t)ch * 64 + h * B_ROWS + lane);
-                    mbar_wait(smem_u32(&tail->b_empty[bs]), bph ^ 1u);
-                    const uint32_t dst0 = b_ring + bs * B_STAGE_BYTES + (uint32_t)g * B_DOM_BYTES;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int k = i * 4 + (lane >> 3);               // row of the stage: 4 rows x 8 chunks per instruction
-                        const int node = __shfl_sync(0xffffffffu, idx, k);
-                        const bool ok = dom_ok && node >= 0;
-                        const int64_t grow = ok ? drow + node : 0;
-                        const uint32_t r = (uint32_t)(grow & (TILE - 1));
-                        const uint32_t jp = (uint32_t)(lane & 7);       // physical 16-byte chunk of the row in the mu image
-                        const unsigned char* src = mu_bytes + (grow >> 7) * (int64_t)ABUF + (r >> 3) * 1024u + (r & 7u) * 128u + jp * 16u;
-                        const uint32_t dst = dst0 + swz((uint32_t)k, jp ^ (r & 7u));   // logical chunk = physical ^ (row & 7)
-                        cp_async16(dst, src, ok);
-                        cp_async16(dst + B_PLANE_BYTES, src + APLANE, ok);
-                    }
-                    cp_async_arrive(smem_u32(&tail->b_full[bs]));
-                    if (++bs == B_STAGES) { bs = 0; bph ^= 1u; }
-                }
-            }
-        }
-    } else {
-        // ---- epilogue: warpgroup ew takes the items it & 1 == ew ----
-        const int ew = (warp - EPI_WARP0) >> 2;
-        const int m = (warp & 3) * 32 + lane;                      // TMEM lane = tile row (a warp reaches lanes 32 * (warp % 4) ..)
-        const uint32_t tmem = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)ew * 256u;
-        const uint32_t full = smem_u32(&tail->acc_full[ew]), empty = smem_u32(&tail->acc_empty[ew]);
-        uint32_t aph = 0, it = 0;
-        for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
-            if ((int)(it & 1u) != ew) continue;
-            const int tile = (int)(item % plan.ntiles);
-            const int d0 = (int)(item / plan.ntiles) * PD;
-            mbar_wait(full, aph);
-            aph ^= 1u;
-            tc_fence_after();
-#pragma unroll 1
-            for (int dom = 0; dom < PD; ++dom) {
-                if (d0 + dom >= Bc) break;
-                // slot order: the tile's 128 rows are one tile image of the output layer; thread = row, so a warp's store
-                // instruction writes 512 contiguous bytes of a piece
-                unsigned char* img = reinterpret_cast<unsigned char*>(nb_img) +
-                                     ((int64_t)(d0 + dom) * plan.ntiles + tile) * (int64_t)ABUF + (uint32_t)m * 16u;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float x[16];
-                    tmem_ld16_sync(tmem + (uint32_t)(dom * 64 + q * 16), x);
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        uint4 hi, lo;
-                        split2(x[h * 8 + 0], x[h * 8 + 1], hi.x, lo.x);
-                        split2(x[h * 8 + 2], x[h * 8 + 3], hi.y, lo.y);
-                        split2(x[h * 8 + 4], x[h * 8 + 5], hi.z, lo.z);
-                        split2(x[h * 8 + 6], x[h * 8 + 7], hi.w, lo.w);
-                        const uint32_t off = (uint32_t)(q * 2 + h) * NB_PIECE;
-                        *reinterpret_cast<uint4*>(img + off) = hi;
-                        *reinterpret_cast<uint4*>(img + APLANE + off) = lo;
-                    }
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(empty);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, 512);
+    prop::prop_body(plan, mu_img, nb_img, Bc, smem_raw, (int)blockIdx.x, (int)gridDim.x, nullptr, 0);
 }
 
 // ---- host-side plan construction ------------------------------------------------------------------------
@@ -360,7 +165,7 @@ LayerTiling make_tiling(int C, int H, int W) {
 }
 
 int prop_tc_init() {
-    return cudaFuncSetAttribute(k_tc_prop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PROP_SMEM);
+    return cudaFuncSetAttribute(k_tc_prop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop::PROP_SMEM);
 }
 
 // plan for  nb = A_k(mu)  (forward) or  nb = A_k^T(mu) [/ freq]  (backward) of one verified-network layer;
@@ -425,11 +230,13 @@ void prop_plan_free(PropPlan* p) {
 }
 
 double prop_plan_density(const PropPlan* p) { return p ? p->density : 0.0; }
+const PropPlanDev& prop_plan_dev(const PropPlan* p) { return p->dev; }
+double prop_plan_chunks_per_tile(const PropPlan* p) { return p->dev.ntiles > 0 ? (double)p->nchunks / p->dev.ntiles : 1.0; }
 
 void prop_tc_run(const PropPlan* plan, const float* mu_img, float* nb_img, int Bc, cudaStream_t st, int64_t* launches) {
-    const int64_t nitems = (int64_t)plan->dev.ntiles * ((Bc + PD - 1) / PD);
+    const int64_t nitems = (int64_t)plan->dev.ntiles * ((Bc + prop::PD - 1) / prop::PD);
     const int grid = (int)(nitems < 1 ? 1 : (nitems < 148 ? nitems : 148));
-    k_tc_prop<<<grid, PROP_THREADS, PROP_SMEM, st>>>(plan->dev, reinterpret_cast<const uint16_t*>(mu_img),
+    k_tc_prop<<<grid, prop::PROP_THREADS, prop::PROP_SMEM, st>>>(plan->dev, reinterpret_cast<const uint16_t*>(mu_img),
                                                      reinterpret_cast<uint16_t*>(nb_img), Bc);
     ++*launches;
 }

@@ -37,7 +37,7 @@
 //   nb       per tile of 128 consecutive rows: the A-operand image itself, [hi plane 16 KB][lo plane 16 KB], scaled by
 //            ASCALE — written by the propagation kernels, loaded with one 32 KB cp.async.bulk;
 //   relax'   [tile][16 channel quads][128 rows][4] fp32 (scaled domain), so that thread = row reads are coalesced.
-#include "gnnb_umma.cuh"
+#include "gnnb_prop_body.cuh"
 
 namespace gnnb {
 namespace {
@@ -235,17 +235,23 @@ __device__ __forceinline__ bool epilogue_to_mu(const WG& c, uint32_t dcol, const
     }
     return bad && valid;
 }
-// the staged tile image -> global with one bulk store; then (optionally) the next tile's nb image into the same buffer
-__device__ __forceinline__ void commit_tile(const WG& c, void* dst_tile, const void* next_nb) {
+// the staged tile image -> global with one bulk store (the landing buffer is busy until bulk_wait_read)
+__device__ __forceinline__ void commit_tile(const WG& c, void* dst_tile) {
     fence_proxy_async();                 // the staging stores are generic-proxy writes, the bulk store reads through the async proxy
     wg_barrier(c);
+    if (c.t == 0) bulk_s2g(dst_tile, c.land, ABUF);
+}
+// request a tile's nb image into the landing buffer (one thread): after the previous tile's bulk store has read the
+// buffer and — in a fused launch — after the propagation CTA that produces the item has published it
+__device__ __forceinline__ void request_nb(const WG& c, const void* src, const int32_t* flag, int32_t epoch) {
     if (c.t == 0) {
-        bulk_s2g(dst_tile, c.land, ABUF);
-        if (next_nb != nullptr) {
-            bulk_wait_read();            // the store has read the buffer: it may be overwritten
-            mbar_expect_tx(c.mbar_tma, ABUF);
-            bulk_g2s(c.land, next_nb, ABUF, c.mbar_tma);
+        bulk_wait_read();
+        if (flag != nullptr) {
+            while (flag_acquire(flag) != epoch) __nanosleep(100);
+            fence_proxy_async();         // the image was written with generic-proxy stores by another SM; the bulk copy reads it through the async proxy
         }
+        mbar_expect_tx(c.mbar_tma, ABUF);
+        bulk_g2s(c.land, src, ABUF, c.mbar_tma);
     }
 }
 
@@ -284,12 +290,16 @@ struct CtaSetup {
     uint32_t tmem_base;
 };
 
+__device__ __forceinline__ unsigned char* smem_dyn() {
+    extern __shared__ unsigned char smem_raw_[];
+    return smem_raw_;
+}
+
 // common prologue: carve shared memory, allocate TMEM, init mbarriers, TMA the weight planes in.
 // LAND: the kernel has a 32 KB landing buffer per warpgroup after the weights.
 template <bool LAND, int NW>
-__device__ __forceinline__ CtaSetup cta_setup(uint32_t wbytes, const uint16_t* const (&wsrc)[NW], const uint32_t (&woff)[NW],
-                                              const uint32_t (&wlen)[NW]) {
-    extern __shared__ unsigned char smem_raw[];
+__device__ __forceinline__ CtaSetup cta_setup(unsigned char* smem_raw, uint32_t wbytes, const uint16_t* const (&wsrc)[NW],
+                                              const uint32_t (&woff)[NW], const uint32_t (&wlen)[NW]) {
     CtaSetup s;
     s.base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // pointer arithmetic keeps the shared address space
     s.w = smem_u32(s.base);
@@ -338,17 +348,42 @@ __device__ __forceinline__ void copy_vec(float* dst, const float* __restrict__ s
 // ---- update: 3 GEMMs per tile (see the header) [+ score head] ---------------------------------------------
 constexpr uint32_t UPD_W3 = 0, UPD_WC = 4 * WPLANE, UPD_W42 = 6 * WPLANE, UPD_FN = 8 * WPLANE, UPD_WBYTES = 10 * WPLANE;   // 80 KB
 
-__global__ void __launch_bounds__(128 * NWG, 1) k_tc_update(GnnParams g, int backward, const float* __restrict__ lb,
-                                                            const float* __restrict__ ub, const uint16_t* __restrict__ nb_img,
-                                                            const float* __restrict__ rlx, const int32_t* __restrict__ amb_base,
-                                                            uint16_t* __restrict__ mu_out,
-                                                            float* __restrict__ scores, RowMap map, int64_t score_stride,
-                                                            int64_t score_off, int64_t rows, unsigned long long* nan_count) {
+struct UpdArgs {
+    GnnParams g;
+    int backward;
+    const float *lb, *ub;
+    const uint16_t* nb_img;
+    const float* rlx;
+    const int32_t* amb_base;
+    uint16_t* mu_out;
+    float* scores;
+    RowMap map;
+    int64_t score_stride, score_off;
+    int Bc;
+    unsigned long long* nan_count;
+};
+
+// One CTA's share of a node-update launch.  Work items are the propagation's: item = group of 4 subdomains x tile, taken
+// rank, rank + nranks, ...; warpgroup w updates the tile of subdomain 4 * group + w.  `flags` (may be null): the item's nb
+// images are produced by a propagation CTA of the same launch; wait for flags[item] == epoch before loading them.
+__device__ __forceinline__ void update_body(const UpdArgs& a, unsigned char* smem_raw, int rank, int nranks, const int32_t* flags,
+                                            int32_t epoch) {
+    const GnnParams& g = a.g;
+    const int backward = a.backward;
+    const float* __restrict__ lb = a.lb;
+    const float* __restrict__ ub = a.ub;
+    const uint16_t* __restrict__ nb_img = a.nb_img;
+    const float* __restrict__ rlx = a.rlx;
+    const int32_t* __restrict__ amb_base = a.amb_base;
+    uint16_t* __restrict__ mu_out = a.mu_out;
+    float* __restrict__ scores = a.scores;
+    const RowMap map = a.map;
+    const int64_t score_stride = a.score_stride, score_off = a.score_off;
     const int l3 = backward ? BC3 : FC3, l4b = backward ? BC4_1 : FC4_2, lc = backward ? T_BWD_C : T_FWD_C;
     const uint16_t* const wsrc[4] = {g.tc[l3], g.tcx_w[lc], g.tc[l4b], g.tc[FNODE]};
     const uint32_t woff[4] = {UPD_W3, UPD_WC, UPD_W42, UPD_FN};
     const uint32_t wlen[4] = {4 * WPLANE, 2 * WPLANE, 2 * WPLANE, 2 * WPLANE};
-    CtaSetup s = cta_setup<true, 4>(UPD_WBYTES, wsrc, woff, wlen);
+    CtaSetup s = cta_setup<true, 4>(smem_raw, UPD_WBYTES, wsrc, woff, wlen);
     Tail& tl = *s.tail;
     copy_vec(tl.bias[0], g.bias[l3], P); copy_vec(tl.bias[1], g.tcx_b[lc], P); copy_vec(tl.bias[2], g.bias[l4b], P);
     copy_vec(tl.bias[3], g.bias[FNODE], P); copy_vec(tl.vec, g.wt[FSCORE], P, 1.0f);
@@ -357,15 +392,16 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_update(GnnParams g, int bac
     mbar_wait(smem_u32(&tl.mbar[0]), 0);                      // weight planes have landed
     WG c = make_wg(s, UPD_WBYTES);
     const uint32_t W = s.w;
-    const int64_t ntiles = (rows + TILE - 1) / TILE;
+    const int tiles_per_dom = map.nslots / TILE;
+    const int64_t nitems = (int64_t)tiles_per_dom * ((a.Bc + NWG - 1) / NWG);
     bool bad = false;
     GNNB_TR_DECL;
-    const int64_t tile_step = (int64_t)gridDim.x * NWG;
-    int64_t tile = (int64_t)blockIdx.x * NWG + c.wg;
-    if (tile < ntiles) tma_tile(c, nb_img + (size_t)tile * (ABUF / 2));      // first tile's nb image
-    for (; tile < ntiles; tile += tile_step) {
+    for (int64_t item = rank; item < nitems; item += nranks) {
+        const int dom = (int)(item / tiles_per_dom) * NWG + c.wg;
+        if (dom >= a.Bc) continue;
+        const int64_t tile = (int64_t)dom * tiles_per_dom + item % tiles_per_dom;
         const int64_t row0 = tile * TILE, grow = row0 + c.t;
-        const bool has_next = tile + tile_step < ntiles;
+        request_nb(c, nb_img + (size_t)tile * (ABUF / 2), flags ? flags + item : nullptr, epoch);
         float l = 0.f, u = 1.f;
         const int64_t nrow = natural_row(map, grow);           // index into the caller's [B, n] arrays, -1 = padding slot
         if (nrow >= 0) { l = ldg1_now(lb + nrow); u = ldg1_now(ub + nrow); }
@@ -380,9 +416,6 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_update(GnnParams g, int bac
         // D[0:128) = nb [W3a; W3b]^T
         gemm_ss(c, W + UPD_W3, W + UPD_W3 + 2 * WPLANE, 128, 0);
         GNNB_TR(1);
-        // the next tile's nb image moves towards L2 while this tile runs its chain (it lands in shared memory after this
-        // tile's results have left the landing buffer, see commit_tile)
-        if (has_next && c.t == 0) prefetch_l2(nb_img + (size_t)(tile + tile_step) * (ABUF / 2), ABUF);
         int slot = slot0 + __popc(bal & ((1u << (c.t & 31)) - 1u));
 #pragma unroll
         for (int w = 0; w < 3; ++w) slot += (w < (c.t >> 5)) ? tl.wcnt[c.wg][w] : 0;
@@ -433,13 +466,12 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_update(GnnParams g, int bac
         // D[64:128) = g W4_2^T;  mu = (D + b) * (r0 != 0) -> global
         gemm_ts(c, W + UPD_W42, W + UPD_W42 + WPLANE, 64, DCOL);
         GNNB_TR(5);
-        const void* next_nb = has_next ? nb_img + (size_t)(tile + tile_step) * (ABUF / 2) : nullptr;
         if (scores == nullptr) {
             bad |= epilogue_to_mu<false>(c, DCOL, tl.bias[2], gate, nrow >= 0);
-            commit_tile(c, mu_out + (size_t)tile * (ABUF / 2), next_nb);
+            commit_tile(c, mu_out + (size_t)tile * (ABUF / 2));
         } else {      // score head on the new embeddings (graph_conv.py:448-449)
             bad |= epilogue_to_mu<true>(c, DCOL, tl.bias[2], gate, nrow >= 0);
-            commit_tile(c, mu_out + (size_t)tile * (ABUF / 2), next_nb);
+            commit_tile(c, mu_out + (size_t)tile * (ABUF / 2));
             gemm_ts(c, W + UPD_FN, W + UPD_FN + WPLANE, 64, DCOL);
             float sc = 0.f;
 #pragma unroll
@@ -457,9 +489,25 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_update(GnnParams g, int bac
         GNNB_TR_NEXT();
     }
     GNNB_TR_PRINT("update[top gemm1 epi1 gemm2 epi2 gemm3 epi3]", 7);
-    if (bad) atomicAdd(nan_count, 1ULL);
+    if (bad) atomicAdd(a.nan_count, 1ULL);
     if (c.t == 0) bulk_wait_all();       // the last tile's bulk store still reads this CTA's shared memory
     cta_teardown(s);
+}
+
+__global__ void __launch_bounds__(128 * NWG, 1) k_tc_update(UpdArgs a) {
+    update_body(a, smem_dyn(), (int)blockIdx.x, (int)gridDim.x, nullptr, 0);
+}
+
+// Propagation and node update of one layer in ONE launch: CTAs [0, n_prop) run the gather-GEMM, the others the update
+// chain; both walk the same (4 subdomains x tile) items, and an update CTA starts an item when the propagation CTA
+// that produces it has published its nb images (acquire / release flag per item) — the images are then still in L2, so
+// the nb round trip costs no HBM reads.  Propagation CTAs never wait for update CTAs and have the lowest block indices.
+__global__ void __launch_bounds__(128 * NWG, 1) k_tc_layer(PropPlanDev plan, const uint16_t* __restrict__ mu_in, UpdArgs a, int n_prop,
+                                                           int32_t* flags, int32_t epoch) {
+    if ((int)blockIdx.x < n_prop)
+        prop::prop_body(plan, mu_in, const_cast<uint16_t*>(a.nb_img), a.Bc, smem_dyn(), (int)blockIdx.x, n_prop, flags, epoch);
+    else
+        update_body(a, smem_dyn(), (int)blockIdx.x - n_prop, (int)gridDim.x - n_prop, flags, epoch);
 }
 
 // ---- relax: round-independent part of the fc4 / bc4 pre-activation of a hidden layer --------------------------
@@ -471,7 +519,7 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_relax(GnnParams g, NodeInpu
     const uint16_t* const wsrc[5] = {g.tcx_w[T_FWD_R], g.tc[BC1_1], g.tc[BC1_2], g.tc[BC2], g.tcx_w[T_BWD_R]};
     const uint32_t woff[5] = {RLX_FR, RLX_BC11, RLX_BC12, RLX_BC2, RLX_BR};
     const uint32_t wlen[5] = {2 * WPLANE, 2 * WPLANE, 2 * WPLANE, 6 * WPLANE, 2 * WPLANE};
-    CtaSetup s = cta_setup<false, 5>(RLX_WBYTES, wsrc, woff, wlen);
+    CtaSetup s = cta_setup<false, 5>(smem_dyn(), RLX_WBYTES, wsrc, woff, wlen);
     Tail& tl = *s.tail;
     copy_vec(tl.bias[0], g.tcx_b[T_FWD_R], P); copy_vec(tl.bias[1], g.bias[BC1_1], P); copy_vec(tl.bias[2], g.bias[BC1_2], P);
     copy_vec(tl.bias[3], g.bias[BC2], P); copy_vec(tl.bias[4], g.tcx_b[T_BWD_R], P);
@@ -558,7 +606,7 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_input_embed(GnnParams g, co
     const uint16_t* const wsrc[1] = {g.tc[INP_F_1]};
     const uint32_t woff[1] = {0};
     const uint32_t wlen[1] = {2 * WPLANE};
-    CtaSetup s = cta_setup<true, 1>(EMB_WBYTES, wsrc, woff, wlen);
+    CtaSetup s = cta_setup<true, 1>(smem_dyn(), EMB_WBYTES, wsrc, woff, wlen);
     Tail& tl = *s.tail;
     copy_vec(tl.bias[0], g.bias[INP_F_1], P); copy_vec(tl.bias[5], g.bias[INP_F], P); copy_vec(tl.w_small[0], g.wt[INP_F], 3 * P);
     __syncthreads();
@@ -574,7 +622,7 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_input_embed(GnnParams g, co
         if (c.t == 0) bulk_wait_read();          // the previous tile's bulk store has read the staging buffer
         gemm_ts(c, s.w, s.w + WPLANE, 64, DCOL);
         epilogue_to_mu<false>(c, DCOL, tl.bias[0], 1.0f, nrow >= 0);
-        commit_tile(c, mu0 + (size_t)tile * (ABUF / 2), nullptr);
+        commit_tile(c, mu0 + (size_t)tile * (ABUF / 2));
     }
     if (c.t == 0) bulk_wait_all();
     cta_teardown(s);
@@ -590,7 +638,7 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_input_update(GnnParams g, c
     const uint16_t* const wsrc[3] = {g.tcx_w[T_INP_C], g.tcx_w[T_INP_NB], g.tc[INP_B2_2]};
     const uint32_t woff[3] = {INU_WI, INU_WN, INU_B22};
     const uint32_t wlen[3] = {2 * WPLANE, 2 * WPLANE, 2 * WPLANE};
-    CtaSetup s = cta_setup<true, 3>(INU_WBYTES, wsrc, woff, wlen);
+    CtaSetup s = cta_setup<true, 3>(smem_dyn(), INU_WBYTES, wsrc, woff, wlen);
     Tail& tl = *s.tail;
     copy_vec(tl.bias[0], g.tcx_b[T_INP_C], P); copy_vec(tl.bias[1], g.bias[INP_B2_2], P);
     copy_vec(tl.bias[5], g.bias[INP_B], P); copy_vec(tl.w_small[0], g.wt[INP_B], 2 * P);
@@ -600,10 +648,9 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_input_update(GnnParams g, c
     const uint32_t W = s.w;
     const int64_t ntiles = (rows + TILE - 1) / TILE;
     const int64_t tile_step = (int64_t)gridDim.x * NWG;
-    int64_t tile = (int64_t)blockIdx.x * NWG + c.wg;
-    if (tile < ntiles) tma_tile(c, nb_img + (size_t)tile * (ABUF / 2));
-    for (; tile < ntiles; tile += tile_step) {
+    for (int64_t tile = (int64_t)blockIdx.x * NWG + c.wg; tile < ntiles; tile += tile_step) {
         const int64_t row0 = tile * TILE, grow = row0 + c.t;
+        request_nb(c, nb_img + (size_t)tile * (ABUF / 2), nullptr, 0);
         float feat[2] = {0.f, 0.f};
         const int64_t nrow = grow < rows ? natural_row(map, grow) : -1;
         if (nrow >= 0) { feat[0] = lb0[nrow]; feat[1] = ub0[nrow]; }
@@ -619,18 +666,17 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_input_update(GnnParams g, c
         }
         c.ph_tma ^= 1u;
         gemm_finish(c);
-        const bool has_next = tile + tile_step < ntiles;
-        if (has_next && c.t == 0) prefetch_l2(nb_img + (size_t)(tile + tile_step) * (ABUF / 2), ABUF);
         epilogue_to_a<true>(c, DCOL, tl.bias[0]);
         gemm_ts(c, W + INU_B22, W + INU_B22 + WPLANE, 64, DCOL);
         epilogue_to_mu<false>(c, DCOL, tl.bias[1], 1.0f, nrow >= 0);
-        commit_tile(c, mu0 + (size_t)tile * (ABUF / 2), has_next ? nb_img + (size_t)(tile + tile_step) * (ABUF / 2) : nullptr);
+        commit_tile(c, mu0 + (size_t)tile * (ABUF / 2));
     }
     if (c.t == 0) bulk_wait_all();
     cta_teardown(s);
 }
 
 constexpr size_t smem_bytes(uint32_t wbytes, bool land) { return 1024 + wbytes + (land ? NWG * ABUF : 0) + sizeof(Tail); }
+constexpr size_t LAYER_SMEM = prop::PROP_SMEM > smem_bytes(UPD_WBYTES, true) ? prop::PROP_SMEM : smem_bytes(UPD_WBYTES, true);
 
 int grid_for(int64_t rows) {
     const int64_t tiles = (rows + TILE - 1) / TILE, ctas = (tiles + NWG - 1) / NWG;
@@ -715,6 +761,7 @@ bool tc_available() { return true; }
 int tc_init() {
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(k_tc_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(UPD_WBYTES, true))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_tc_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LAYER_SMEM)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_tc_relax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(RLX_WBYTES, false))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_tc_input_embed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(EMB_WBYTES, true))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_tc_input_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(INU_WBYTES, true))) != cudaSuccess) return e;
@@ -745,12 +792,43 @@ void tc_relax(const GnnParams& g, const NodeInputs& in, float* relax_f, float* r
     ++*launches;
 }
 
+namespace {
+UpdArgs make_upd_args(const GnnParams& g, bool backward, const float* lb, const float* ub, const float* nb, const float* relax,
+                      const int32_t* amb_base, float* mu_out, float* scores, RowMap map, int64_t score_stride, int64_t score_off,
+                      int64_t rows, unsigned long long* nan_count) {
+    UpdArgs a;
+    a.g = g; a.backward = backward ? 1 : 0; a.lb = lb; a.ub = ub; a.nb_img = reinterpret_cast<const uint16_t*>(nb); a.rlx = relax;
+    a.amb_base = amb_base; a.mu_out = reinterpret_cast<uint16_t*>(mu_out); a.scores = scores; a.map = map;
+    a.score_stride = score_stride; a.score_off = score_off; a.Bc = (int)(rows / map.nslots); a.nan_count = nan_count;
+    return a;
+}
+}  // namespace
+
 void tc_update(const GnnParams& g, bool backward, const float* lb, const float* ub, const float* nb, const float* relax,
                const int32_t* amb_base, float* mu_out, float* scores, RowMap map, int64_t score_stride, int64_t score_off, int64_t rows,
                unsigned long long* nan_count, cudaStream_t st, int64_t* launches) {
-    k_tc_update<<<grid_for(rows), 128 * NWG, smem_bytes(UPD_WBYTES, true), st>>>(
-        g, backward ? 1 : 0, lb, ub, reinterpret_cast<const uint16_t*>(nb), relax, amb_base, reinterpret_cast<uint16_t*>(mu_out), scores, map,
-        score_stride, score_off, rows, nan_count);
+    const UpdArgs a = make_upd_args(g, backward, lb, ub, nb, relax, amb_base, mu_out, scores, map, score_stride, score_off, rows, nan_count);
+    const int64_t nitems = (int64_t)(map.nslots / TILE) * ((a.Bc + NWG - 1) / NWG);
+    k_tc_update<<<(int)(nitems < 1 ? 1 : (nitems < 148 ? nitems : 148)), 128 * NWG, smem_bytes(UPD_WBYTES, true), st>>>(a);
+    ++*launches;
+}
+
+void tc_layer(const GnnParams& g, const PropPlan* plan, const float* mu_in, bool backward, const float* lb, const float* ub,
+              float* nb, const float* relax, const int32_t* amb_base, float* mu_out, float* scores, RowMap map, int64_t score_stride,
+              int64_t score_off, int64_t rows, unsigned long long* nan_count, int32_t* flags, int32_t epoch, int prop_share_pct,
+              cudaStream_t st, int64_t* launches) {
+    const UpdArgs a = make_upd_args(g, backward, lb, ub, nb, relax, amb_base, mu_out, scores, map, score_stride, score_off, rows, nan_count);
+    const int64_t nitems = (int64_t)(map.nslots / TILE) * ((a.Bc + NWG - 1) / NWG);
+    // split of the 148 CTAs by a cost model in units of one propagation K chunk (fitted to stand-alone kernel times)
+    const double cp = prop_plan_chunks_per_tile(plan) + 8.5, cu = scores ? 19.0 : 16.7;
+    double share = prop_share_pct > 0 ? prop_share_pct / 100.0 : cp / (cp + cu);
+    int n_prop = (int)(148 * share + 0.5);
+    n_prop = n_prop < 4 ? 4 : (n_prop > 144 ? 144 : n_prop);
+    int n_upd = 148 - n_prop;
+    if (nitems < n_prop) n_prop = (int)nitems;
+    if (nitems < n_upd) n_upd = (int)nitems;
+    k_tc_layer<<<n_prop + n_upd, 128 * NWG, LAYER_SMEM, st>>>(prop_plan_dev(plan), reinterpret_cast<const uint16_t*>(mu_in), a, n_prop,
+                                                             flags, epoch);
     ++*launches;
 }
 

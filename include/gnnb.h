@@ -53,6 +53,9 @@ enum gnnb_kernel_class {
     GNNB_K_PROP_BWD,           /* embeddings through A_k^T (transposed conv / linear / property rank-1) */
     GNNB_K_OUTPUT,             /* output node */
     GNNB_K_ARGMAX,             /* masked argmax per subdomain */
+    GNNB_K_LAYER_FWD,          /* fused launch: propagation through A_k + forward node update (option "fuse") */
+    GNNB_K_LAYER_BWD,          /* fused launch: propagation through A_{k+1}^T + backward node update */
+    GNNB_K_LAYER_BWD_SCORE,    /* the same on the last backward sweep, with the score head */
     GNNB_K_COUNT
 };
 
@@ -102,7 +105,9 @@ int gnnb_set_gnn_weights(gnnb_ctx* ctx, const float* const* tensors, const int64
  * (graph_conv.py:107-137, 222-249). */
 int gnnb_set_network(gnnb_ctx* ctx, const gnnb_layer_desc* layers, int n_layers, int c0, int h0, int w0);
 
-/* Options: "math" (gnnb_math_mode), "chunk" (subdomains per wave; 0 = auto), "snapshot" (0/1: keep
+/* Options: "math" (gnnb_math_mode), "chunk" (subdomains per wave; 0 = auto), "fuse" (0/1, default 1: propagation and
+ * node update of a layer in one launch, tensor-core mode), "prop_share" (0 = cost model, else the percentage of the
+ * CTAs of a fused launch that run the propagation), "snapshot" (0/1: keep
  * per-stage copies for gnnb_debug_snapshot; debugging only), "profile" (0/1: time every stage launch with
  * CUDA events for gnnb_profile_read). */
 int gnnb_set_option(gnnb_ctx* ctx, const char* key, int64_t value);
