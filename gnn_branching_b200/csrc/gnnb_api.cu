@@ -30,10 +30,12 @@ struct gnnb_ctx {
     int math = GNNB_MATH_TC_FP16X3;
     int chunk = 0;
     int snapshot = 0;
-    int fuse = 1;                   // propagation + node update of a layer in one launch (tensor-core mode)
+    int fuse = 0;                   // propagation + node update of a layer in one launch (tensor-core mode); measured 3-4 % slower than two launches
     int prop_share = 0;             // % of a fused launch's CTAs that propagate; 0 = cost model
     int32_t* d_flags = nullptr;     // per-item publication flags of the fused launches; value = epoch of the launch
     int32_t epoch = 0;
+    int32_t consumed_base = 0;      // host mirror of the device progress counter d_flags[-1] at the next fused launch
+    int lead = 256;                 // items the propagation side of a fused launch may run ahead (nb images in flight: lead * 128 KB)
     // GNN parameters
     bool have_gnn = false;
     float* d_gnn = nullptr;
@@ -139,7 +141,7 @@ int ensure_workspace(gnnb_ctx* ctx, int Bc, bool host_staging) {
         const size_t items = (size_t)(ctx->rowmap[k].nslots / 128) * ((Bc + 3) / 4);
         max_items = items > max_items ? items : max_items;
     }
-    const size_t o_flags = take(max_items);
+    const size_t o_flags = take(max_items + 1);          // + the progress counter
     const size_t o_sc = take((size_t)Bc * ctx->n_hidden);
     const size_t o_best = take(Bc), o_idx = take(Bc);
     struct StgOff { std::vector<size_t> lb, ub, du, pr, po; size_t pout, pin, wp, bp, mask, best, idx, sc; } so[2];
@@ -170,8 +172,10 @@ int ensure_workspace(gnnb_ctx* ctx, int Bc, bool host_staging) {
         ctx->amb_rows[k] = reinterpret_cast<int32_t*>(base + o_ar[k]);
     }
     ctx->d_flags = reinterpret_cast<int32_t*>(base + o_flags);
-    CU(cudaMemset(ctx->d_flags, 0, max_items * sizeof(int32_t)));
+    CU(cudaMemset(ctx->d_flags, 0, (max_items + 1) * sizeof(int32_t)));
+    ctx->d_flags += 1;                                   // d_flags[-1] is the counter
     ctx->epoch = 0;
+    ctx->consumed_base = 0;
     ctx->nb = base + o_nb; ctx->ws_scores = base + o_sc; ctx->ws_best = base + o_best;
     ctx->ws_idx = reinterpret_cast<int32_t*>(base + o_idx);
     if (host_staging) {
@@ -310,7 +314,8 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
             if (fused) {
                 ProfScope ps(ctx, GNNB_K_LAYER_FWD, nodes, st);
                 tc_layer(g, ctx->plan_fwd[k - 1], ctx->mu[k - 1], false, in.lb[k], in.ub[k], ctx->nb, ctx->relax_f[k], ctx->amb_base[k],
-                         ctx->mu[k], nullptr, M(k), 0, 0, rows, ctx->d_nan, ctx->d_flags, ++ctx->epoch, ctx->prop_share, st, lc);
+                         ctx->mu[k], nullptr, M(k), 0, 0, rows, ctx->d_nan, ctx->d_flags, ++ctx->epoch, ctx->prop_share,
+                         ctx->d_flags - 1, &ctx->consumed_base, ctx->lead, st, lc);
             } else {
                 ProfScope ps(ctx, GNNB_K_PROP_FWD, nodes, st);
                 if (tc) prop_tc_run(ctx->plan_fwd[k - 1], ctx->mu[k - 1], ctx->nb, Bc, st, lc);
@@ -339,7 +344,7 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
                 ProfScope ps(ctx, last ? GNNB_K_LAYER_BWD_SCORE : GNNB_K_LAYER_BWD, nodes, st);
                 tc_layer(g, ctx->plan_bwd[k], ctx->mu[k + 1], true, in.lb[k], in.ub[k], ctx->nb, ctx->relax_b[k], ctx->amb_base[k],
                          ctx->mu[k], sc, M(k), ctx->n_hidden, ctx->hidden_off[k], rows, ctx->d_nan, ctx->d_flags, ++ctx->epoch,
-                         ctx->prop_share, st, lc);
+                         ctx->prop_share, ctx->d_flags - 1, &ctx->consumed_base, ctx->lead, st, lc);
             } else {
                 ProfScope ps(ctx, GNNB_K_PROP_BWD, nodes, st);
                 if (k == L && tc) prop_tc_property_backward(in.wp, ctx->mu[L + 1], ctx->nb, ctx->n[L], ctx->rowmap[L].nslots, Bc, st, lc);
@@ -634,6 +639,9 @@ int gnnb_set_option(gnnb_ctx* ctx, const char* key, int64_t value) {
     } else if (k == "prop_share") {
         if (value < 0 || value > 99) return fail(ctx, GNNB_ERR_INVALID, "prop_share is a percentage in [0, 99]");
         ctx->prop_share = (int)value;
+    } else if (k == "lead") {
+        if (value < 0) return fail(ctx, GNNB_ERR_INVALID, "lead must be >= 0");
+        ctx->lead = (int)value;
     } else if (k == "snapshot") {
         ctx->snapshot = value ? 1 : 0;
     } else if (k == "profile") {
@@ -652,6 +660,7 @@ int64_t gnnb_get_option(gnnb_ctx* ctx, const char* key) {
     if (k == "snapshot") return ctx->snapshot;
     if (k == "fuse") return ctx->fuse;
     if (k == "prop_share") return ctx->prop_share;
+    if (k == "lead") return ctx->lead;
     if (k == "profile") return ctx->profile;
     if (k == "n_hidden") return ctx->n_hidden;
     if (k == "workspace_domains") return ctx->ws_cap;

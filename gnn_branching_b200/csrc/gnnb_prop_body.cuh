@@ -63,9 +63,10 @@ constexpr size_t PROP_SMEM = 1024 + W_STAGES * W_STAGE_BYTES + B_STAGES * B_STAG
 
 // One CTA's share of a propagation launch: items rank, rank + nranks, ...  `flags` (may be null): after the nb tile images
 // of an item are written, flags[item] = epoch is released at GPU scope, for node-update CTAs of the same launch that
-// wait for exactly this item (gnnb_tc.cu, k_tc_layer).  All threads of the block must call it (block-wide barriers).
+// wait for exactly this item (gnnb_tc.cu, k_tc_layer); `consumed` (may be null) is their progress counter.  All threads of the block must call it (block-wide barriers).
 __device__ __forceinline__ void prop_body(const PropPlanDev& plan, const uint16_t* __restrict__ mu_img, uint16_t* __restrict__ nb_img,
-                                          int Bc, unsigned char* smem_raw, int rank, int nranks, int32_t* flags, int32_t epoch) {
+                                          int Bc, unsigned char* smem_raw, int rank, int nranks, int32_t* flags, int32_t epoch,
+                                          const int32_t* consumed = nullptr, int32_t consumed_base = 0, int lead = 0) {
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
     const uint32_t w_ring = smem_u32(base), b_ring = w_ring + W_STAGES * W_STAGE_BYTES;
     PropTail* tail = reinterpret_cast<PropTail*>(base + W_STAGES * W_STAGE_BYTES + B_STAGES * B_STAGE_BYTES);
@@ -149,6 +150,12 @@ __device__ __forceinline__ void prop_body(const PropPlanDev& plan, const uint16_
         const unsigned char* mu_bytes = reinterpret_cast<const unsigned char*>(mu_img);
         uint32_t bs = 0, bph = 0;
         for (int64_t item = rank; item < nitems; item += nranks) {
+            if (consumed != nullptr && item >= lead) {
+                // back-pressure of a fused launch: stay at most `lead` items ahead of the node-update CTAs, so that the
+                // nb images are still in L2 when they are read (every item is consumed by exactly 4 warpgroup-items)
+                const int32_t target = consumed_base + 4 * (int32_t)(item - lead);
+                while ((int32_t)(flag_acquire(consumed) - target) < 0) __nanosleep(200);
+            }
             const int tile = (int)(item % plan.ntiles);
             const int d = (int)(item / plan.ntiles) * PD + g;
             const bool dom_ok = d < Bc;

@@ -361,6 +361,7 @@ struct UpdArgs {
     int64_t score_stride, score_off;
     int Bc;
     unsigned long long* nan_count;
+    int32_t* consumed;          // fused launches: progress counter of the node-update side (+1 per warpgroup-item), or null
 };
 
 // One CTA's share of a node-update launch.  Work items are the propagation's: item = group of 4 subdomains x tile, taken
@@ -398,7 +399,10 @@ __device__ __forceinline__ void update_body(const UpdArgs& a, unsigned char* sme
     GNNB_TR_DECL;
     for (int64_t item = rank; item < nitems; item += nranks) {
         const int dom = (int)(item / tiles_per_dom) * NWG + c.wg;
-        if (dom >= a.Bc) continue;
+        if (dom >= a.Bc) {
+            if (a.consumed != nullptr && c.t == 0) atomicAdd(a.consumed, 1);
+            continue;
+        }
         const int64_t tile = (int64_t)dom * tiles_per_dom + item % tiles_per_dom;
         const int64_t row0 = tile * TILE, grow = row0 + c.t;
         request_nb(c, nb_img + (size_t)tile * (ABUF / 2), flags ? flags + item : nullptr, epoch);
@@ -415,10 +419,23 @@ __device__ __forceinline__ void update_body(const UpdArgs& a, unsigned char* sme
         GNNB_TR(0);
         // D[0:128) = nb [W3a; W3b]^T
         gemm_ss(c, W + UPD_W3, W + UPD_W3 + 2 * WPLANE, 128, 0);
+        if (a.consumed != nullptr && c.t == 0) atomicAdd(a.consumed, 1);      // this tile's nb image has been read
         GNNB_TR(1);
+        // towards L2 while this tile runs its chain: the next tile's nb image (stand-alone launches: it was written by an
+        // earlier kernel) and this row's relax' pieces
+        if (flags == nullptr && c.t == 0 && item + nranks < nitems) {
+            const int64_t nitem = item + nranks;
+            const int ndom = (int)(nitem / tiles_per_dom) * NWG + c.wg;
+            if (ndom < a.Bc) prefetch_l2(nb_img + (size_t)((int64_t)ndom * tiles_per_dom + nitem % tiles_per_dom) * (ABUF / 2), ABUF);
+        }
         int slot = slot0 + __popc(bal & ((1u << (c.t & 31)) - 1u));
 #pragma unroll
         for (int w = 0; w < 3; ++w) slot += (w < (c.t >> 5)) ? tl.wcnt[c.wg][w] : 0;
+        const float* rt = rlx + (size_t)(slot >> 7) * (TILE * P) + (size_t)(slot & (TILE - 1)) * 4;
+        if (amb) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(rt + (size_t)i * (TILE * 4)));
+        }
         // h3 = relu(r0 * D[0:64) + r1 * D[64:128) + b3) -> A, in place over the consumed columns (graph_conv.py:169-170 / 331-336)
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
@@ -440,7 +457,6 @@ __device__ __forceinline__ void update_body(const UpdArgs& a, unsigned char* sme
         gemm_ts_start(c, W + UPD_WC, W + UPD_WC + WPLANE, 64, DCOL);
         float4 rx[16];
         {
-            const float* rt = rlx + (size_t)(slot >> 7) * (TILE * P) + (size_t)(slot & (TILE - 1)) * 4;
 #pragma unroll
             for (int i = 0; i < 16; ++i) rx[i] = amb ? ldg4_now(rt + (size_t)i * (TILE * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -503,9 +519,10 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_update(UpdArgs a) {
 // that produces it has published its nb images (acquire / release flag per item) — the images are then still in L2, so
 // the nb round trip costs no HBM reads.  Propagation CTAs never wait for update CTAs and have the lowest block indices.
 __global__ void __launch_bounds__(128 * NWG, 1) k_tc_layer(PropPlanDev plan, const uint16_t* __restrict__ mu_in, UpdArgs a, int n_prop,
-                                                           int32_t* flags, int32_t epoch) {
+                                                           int32_t* flags, int32_t epoch, int32_t consumed_base, int lead) {
     if ((int)blockIdx.x < n_prop)
-        prop::prop_body(plan, mu_in, const_cast<uint16_t*>(a.nb_img), a.Bc, smem_dyn(), (int)blockIdx.x, n_prop, flags, epoch);
+        prop::prop_body(plan, mu_in, const_cast<uint16_t*>(a.nb_img), a.Bc, smem_dyn(), (int)blockIdx.x, n_prop, flags, epoch,
+                        a.consumed, consumed_base, lead);
     else
         update_body(a, smem_dyn(), (int)blockIdx.x - n_prop, (int)gridDim.x - n_prop, flags, epoch);
 }
@@ -800,6 +817,7 @@ UpdArgs make_upd_args(const GnnParams& g, bool backward, const float* lb, const 
     a.g = g; a.backward = backward ? 1 : 0; a.lb = lb; a.ub = ub; a.nb_img = reinterpret_cast<const uint16_t*>(nb); a.rlx = relax;
     a.amb_base = amb_base; a.mu_out = reinterpret_cast<uint16_t*>(mu_out); a.scores = scores; a.map = map;
     a.score_stride = score_stride; a.score_off = score_off; a.Bc = (int)(rows / map.nslots); a.nan_count = nan_count;
+    a.consumed = nullptr;
     return a;
 }
 }  // namespace
@@ -816,8 +834,8 @@ void tc_update(const GnnParams& g, bool backward, const float* lb, const float* 
 void tc_layer(const GnnParams& g, const PropPlan* plan, const float* mu_in, bool backward, const float* lb, const float* ub,
               float* nb, const float* relax, const int32_t* amb_base, float* mu_out, float* scores, RowMap map, int64_t score_stride,
               int64_t score_off, int64_t rows, unsigned long long* nan_count, int32_t* flags, int32_t epoch, int prop_share_pct,
-              cudaStream_t st, int64_t* launches) {
-    const UpdArgs a = make_upd_args(g, backward, lb, ub, nb, relax, amb_base, mu_out, scores, map, score_stride, score_off, rows, nan_count);
+              int32_t* consumed, int32_t* consumed_base, int lead, cudaStream_t st, int64_t* launches) {
+    UpdArgs a = make_upd_args(g, backward, lb, ub, nb, relax, amb_base, mu_out, scores, map, score_stride, score_off, rows, nan_count);
     const int64_t nitems = (int64_t)(map.nslots / TILE) * ((a.Bc + NWG - 1) / NWG);
     // split of the 148 CTAs by a cost model in units of one propagation K chunk (fitted to stand-alone kernel times)
     const double cp = prop_plan_chunks_per_tile(plan) + 8.5, cu = scores ? 19.0 : 16.7;
@@ -827,8 +845,10 @@ void tc_layer(const GnnParams& g, const PropPlan* plan, const float* mu_in, bool
     int n_upd = 148 - n_prop;
     if (nitems < n_prop) n_prop = (int)nitems;
     if (nitems < n_upd) n_upd = (int)nitems;
+    a.consumed = lead > 0 ? consumed : nullptr;
     k_tc_layer<<<n_prop + n_upd, 128 * NWG, LAYER_SMEM, st>>>(prop_plan_dev(plan), reinterpret_cast<const uint16_t*>(mu_in), a, n_prop,
-                                                             flags, epoch);
+                                                             flags, epoch, *consumed_base, lead);
+    if (lead > 0) *consumed_base += (int32_t)(4 * nitems);        // the counter runs on across launches (wrap-safe comparisons)
     ++*launches;
 }
 

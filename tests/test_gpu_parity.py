@@ -213,3 +213,28 @@ def test_frontier_of_65536_subdomains():
     _, i3, s3 = model.score_frontier(fr.slice(B - 2, B).contiguous())
     rep = O.parity_report(s3.cpu(), s_or, sl.mask, i3.cpu(), rtol=RTOL['tc'])
     assert rep['ok'], rep
+
+
+@pytest.mark.parametrize('arch', ARCHS)
+def test_fused_layer_launches_match_reference(arch):
+    """Option fuse = 1 (propagation CTAs + node-update CTAs of a layer in one launch, item-granular hand-off) gives the
+    same scores as two launches, bit for bit, and matches the reference's committed outputs."""
+    fr, ref = load_case(arch, 'fr')
+    model = _model('random', 'tc')
+    sc = model.scorer(0)
+    b0, i0, s0 = model.score_frontier(fr.to('cuda'))
+    sc.set_option('fuse', 1)
+    for share in (0, 30, 70):
+        sc.set_option('prop_share', share)
+        b1, i1, s1 = model.score_frontier(fr.to('cuda'))
+        assert torch.equal(s0, s1) and torch.equal(i0, i1) and torch.equal(b0, b1)
+    rep = O.parity_report(s1.cpu(), ref['scores_random'], fr.mask, i1.cpu(), rtol=RTOL['tc'])
+    assert rep['ok'], rep
+    net, lbs, ubs, wp, bp = load_root(arch)
+    big = synthetic_frontier(net, lbs, ubs, wp, bp, 301, seed=77, device='cuda')     # several items per CTA, a ragged last group
+    sc.set_option('fuse', 0)
+    b2, i2, s2 = model.score_frontier(big)
+    sc.set_option('fuse', 1)
+    sc.set_option('prop_share', 0)
+    b3, i3, s3 = model.score_frontier(big)
+    assert torch.equal(s2, s3) and torch.equal(i2, i3) and torch.equal(b2, b3)
