@@ -338,8 +338,10 @@ def main():
                               'frac_of_bf16_peak': value / world * flops_dom / 1e12 / peak_tf,
                               'hbm_bytes_per_subdomain': roofline.pop('_bytes_per_subdomain'),
                               'note': 'fp32 accuracy needs 3 fp16 MMA passes per product: the tensor ceiling is 1/3 of the bf16 peak'}
-    try:
-        roofline['traffic'] = json.load(open(os.path.join(ROOT, 'profiles', 'kernel_traffic.json')))[roofline['kernel_class']]
+    try:      # DRAM bytes per launch of that kernel class from the committed ncu --set full capture, scaled to this run's wave size
+        kt = json.load(open(os.path.join(ROOT, 'profiles', 'kernel_traffic.json')))
+        roofline['traffic'] = kt[roofline['kernel_class']]['dram_bytes_per_launch_per_subdomain'] * min(B, scorer.get_option('workspace_domains'))
+        roofline['traffic_source'] = kt['_source']
     except (OSError, ValueError, KeyError):
         roofline['traffic'] = None
 

@@ -109,20 +109,35 @@ __device__ __forceinline__ void prop_body(const PropPlanDev& plan, const uint16_
             // D fp32, A fp16 K-major, B fp16 MN-major (bit 16), M = 128, N = 256
             const uint32_t idesc = (1u << 4) | (1u << 16) | ((uint32_t)(PD * 64 >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
             uint32_t ws = 0, wph = 0, bs = 0, bph = 0, it = 0;
+#ifdef GNNB_TRACE
+            long long t_acc = 0, t_w = 0, t_b = 0, t_all = clock64(), t0_;
+            int n_chunks = 0;
+#define PTR_BEGIN() t0_ = clock64()
+#define PTR_END(x) x += clock64() - t0_
+#else
+#define PTR_BEGIN()
+#define PTR_END(x)
+#endif
             for (int64_t item = rank; item < nitems; item += nranks, ++it) {
                 const int tile = (int)(item % plan.ntiles);
                 const int ch0 = plan.tile_chunk0[tile], ch1 = plan.tile_chunk0[tile + 1];
                 const uint32_t a = it & 1u, aph = (it >> 1) & 1u;
+                PTR_BEGIN();
                 mbar_wait(smem_u32(&tail->acc_empty[a]), aph ^ 1u);      // the epilogue has drained this accumulator
+                PTR_END(t_acc);
                 tc_fence_after();
                 const uint32_t d = (tmem_base & 0x0000FFFFu) + a * 256u;
                 uint32_t first = 1;
                 for (int ch = ch0; ch < ch1; ++ch) {
+                    PTR_BEGIN();
                     mbar_wait(smem_u32(&tail->w_full[ws]), wph);
+                    PTR_END(t_w);
                     const int nks = plan.ksteps[ch];
                     const uint32_t wa = w_ring + ws * W_STAGE_BYTES;
                     for (int h = 0; 2 * h < nks; ++h) {
+                        PTR_BEGIN();
                         mbar_wait(smem_u32(&tail->b_full[bs]), bph);
+                        PTR_END(t_b);
                         tc_fence_after();
                         const uint32_t ba = b_ring + bs * B_STAGE_BYTES;
                         const int kc = (nks - 2 * h) < 2 ? (nks - 2 * h) : 2;
@@ -142,13 +157,23 @@ __device__ __forceinline__ void prop_body(const PropPlanDev& plan, const uint16_
                     if (++ws == W_STAGES) { ws = 0; wph ^= 1u; }
                 }
                 umma_commit(smem_u32(&tail->acc_full[a]));
+#ifdef GNNB_TRACE
+                n_chunks += ch1 - ch0;
+#endif
             }
+#ifdef GNNB_TRACE
+            if (rank == 1) printf("TRACE prop-mma: items %u chunks %d total %lld | wait acc_empty %lld, w_full %lld, b_full %lld\n", it, n_chunks,
+                                  clock64() - t_all, t_acc, t_w, t_b);
+#endif
         }
     } else if (warp < EPI_WARP0) {
         // ---- gather: warp g copies the rows of subdomain d0 + g ----
         const int g = warp - GATHER_WARP0;
         const unsigned char* mu_bytes = reinterpret_cast<const unsigned char*>(mu_img);
         uint32_t bs = 0, bph = 0;
+#ifdef GNNB_TRACE
+        long long g_wait = 0, g_all = clock64(), g0_;
+#endif
         for (int64_t item = rank; item < nitems; item += nranks) {
             if (consumed != nullptr && item >= lead) {
                 // back-pressure of a fused launch: stay at most `lead` items ahead of the node-update CTAs, so that the
@@ -165,7 +190,13 @@ __device__ __forceinline__ void prop_body(const PropPlanDev& plan, const uint16_
                 const int nks = plan.ksteps[ch];
                 for (int h = 0; 2 * h < nks; ++h) {
                     const int idx = __ldg(plan.in_rows + (size_t)ch * 64 + h * B_ROWS + lane);
+#ifdef GNNB_TRACE
+                    g0_ = clock64();
+#endif
                     mbar_wait(smem_u32(&tail->b_empty[bs]), bph ^ 1u);
+#ifdef GNNB_TRACE
+                    g_wait += clock64() - g0_;
+#endif
                     const uint32_t dst0 = b_ring + bs * B_STAGE_BYTES + (uint32_t)g * B_DOM_BYTES;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -185,6 +216,9 @@ __device__ __forceinline__ void prop_body(const PropPlanDev& plan, const uint16_
                 }
             }
         }
+#ifdef GNNB_TRACE
+        if (rank == 1 && g == 0 && lane == 0) printf("TRACE prop-gather: total %lld, wait b_empty %lld\n", clock64() - g_all, g_wait);
+#endif
     } else if (warp < EPI_WARP0 + 8) {
         // ---- epilogue: warpgroup ew takes the items it & 1 == ew ----
         const int ew = (warp - EPI_WARP0) >> 2;
@@ -192,13 +226,22 @@ __device__ __forceinline__ void prop_body(const PropPlanDev& plan, const uint16_
         const uint32_t tmem = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)ew * 256u;
         const uint32_t full = smem_u32(&tail->acc_full[ew]), empty = smem_u32(&tail->acc_empty[ew]);
         uint32_t aph = 0, it = 0;
+#ifdef GNNB_TRACE
+        long long e_wait = 0, e_work = 0, e0_;
+#endif
         for (int64_t item = rank; item < nitems; item += nranks, ++it) {
             if ((int)(it & 1u) != ew) continue;
             const int tile = (int)(item % plan.ntiles);
             const int d0 = (int)(item / plan.ntiles) * PD;
+#ifdef GNNB_TRACE
+            e0_ = clock64();
+#endif
             mbar_wait(full, aph);
             aph ^= 1u;
             tc_fence_after();
+#ifdef GNNB_TRACE
+            e_wait += clock64() - e0_; e0_ = clock64();
+#endif
 #pragma unroll 1
             for (int dom = 0; dom < PD; ++dom) {
                 if (d0 + dom >= Bc) break;
@@ -225,12 +268,18 @@ __device__ __forceinline__ void prop_body(const PropPlanDev& plan, const uint16_
             }
             tc_fence_before();
             mbar_arrive(empty);
+#ifdef GNNB_TRACE
+            e_work += clock64() - e0_;
+#endif
             if (flags != nullptr) {      // publish the item: every thread's stores, then one release store
                 __threadfence();
                 named_bar(1 + ew, 128);
                 if (m == 0) flag_release(flags + item, epoch);
             }
         }
+#ifdef GNNB_TRACE
+        if (rank == 1 && m == 0) printf("TRACE prop-epi wg %d: wait acc_full %lld, work %lld\n", ew, e_wait, e_work);
+#endif
     }
     tc_fence_before();
     __syncthreads();

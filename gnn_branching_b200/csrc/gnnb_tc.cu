@@ -63,15 +63,6 @@ struct WG {
 
 __device__ __forceinline__ void wg_barrier(const WG& c) { named_bar(1 + c.wg, 128); }
 
-// one 32 KB pre-split tile image (global) -> this warpgroup's landing buffer.  The buffer must be free: the MMAs that
-// read it have completed (it is only ever touched by the async proxy: TMA writes, tensor-core reads)
-__device__ __forceinline__ void tma_tile(const WG& c, const void* src) {
-    if (c.t == 0) {
-        mbar_expect_tx(c.mbar_tma, ABUF);
-        bulk_g2s(c.land, src, ABUF, c.mbar_tma);
-    }
-}
-
 // 3 passes x 4 K steps with the A operand in tensor memory (issued by one thread)
 __device__ __forceinline__ void issue_ts(const WG& c, uint32_t b_hi, uint32_t b_lo, uint32_t N, uint32_t dcol, bool accumulate) {
     const uint32_t idesc = make_idesc(N);

@@ -10,7 +10,7 @@ def f(x):
     except ValueError: return float('nan')
 print(f"{'id':>3} {'kernel':16s} {'grid':>4} {'us':>8} {'dramR_MB':>9} {'dramW_MB':>9} {'dram%':>6} {'l2%':>6} {'tensor%':>7} {'issue%':>6} {'smem%':>6} {'regs':>4}")
 for r in rows[2:]:
-    name = g(r, 'Kernel Name').split('::')[-1].split('(')[0][:16]
+    name = g(r, "Kernel Name").split("(")[0].split("::")[-1][:16]
     print(f"{g(r,'ID'):>3} {name:16s} {g(r,'launch__grid_size'):>4} {f(g(r,'gpu__time_duration.sum')):8.1f} {f(g(r,'dram__bytes_read.sum')):9.1f} {f(g(r,'dram__bytes_write.sum')):9.1f} "
           f"{f(g(r,'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')):6.1f} {f(g(r,'lts__throughput.avg.pct_of_peak_sustained_elapsed')):6.1f} "
           f"{f(g(r,'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active')):7.1f} {f(g(r,'sm__inst_issued.avg.pct_of_peak_sustained_active')):6.1f} "
