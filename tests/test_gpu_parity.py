@@ -238,3 +238,50 @@ def test_fused_layer_launches_match_reference(arch):
     sc.set_option('prop_share', 0)
     b3, i3, s3 = model.score_frontier(big)
     assert torch.equal(s2, s3) and torch.equal(i2, i3) and torch.equal(b2, b3)
+
+
+def _custom_frontier(layers, input_shape, B, seed):
+    from torch import nn
+    from gnn_branching_b200 import netspec_from_modules
+    from gnn_branching_b200.frontier import interval_root_bounds
+    g = torch.Generator().manual_seed(seed)
+    for m in layers:
+        for q in m.parameters():
+            q.data = torch.randn(q.shape, generator=g) * (0.3 if q.dim() > 1 else 0.1)
+    net = netspec_from_modules(layers, input_shape, name='custom')
+    x = torch.randn(input_shape, generator=g)
+    wp = torch.randn(net.hidden_sizes[-1], generator=g) * 0.3
+    lbs, ubs = interval_root_bounds(net, x.reshape(-1), 0.05, wp, 0.1)
+    return synthetic_frontier(net, lbs, ubs, wp, 0.1, B, seed=seed, max_splits=4)
+
+
+@pytest.mark.parametrize('math', MODES)
+@pytest.mark.parametrize('case', ['odd_shapes', 'wide_channels', 'deep_narrow'])
+def test_other_network_shapes_match_oracle(case, math):
+    """Networks that are not the three CIFAR ones: odd spatial sizes and channel counts (padding slots in every tile),
+    more than 128 channels (channel-blocked tiles), 3x3 / 5x5 kernels, stride 1 and 2 — against the oracle."""
+    from torch import nn
+    from gnn_branching_b200 import Flatten
+    if case == 'odd_shapes':
+        layers = [nn.Conv2d(2, 5, 3, stride=1, padding=1), nn.ReLU(), nn.Conv2d(5, 6, 3, stride=2, padding=1), nn.ReLU(),
+                  Flatten(), nn.Linear(6 * 5 * 4, 37), nn.ReLU()]
+        shape, B = (2, 9, 7), 7
+    elif case == 'wide_channels':
+        layers = [nn.Conv2d(3, 130, 3, stride=1, padding=1), nn.ReLU(), Flatten(), nn.Linear(130 * 4 * 4, 20), nn.ReLU()]
+        shape, B = (3, 4, 4), 5
+    else:
+        layers = [nn.Conv2d(1, 4, 5, stride=1, padding=2), nn.ReLU(), nn.Conv2d(4, 4, 3, stride=1, padding=1), nn.ReLU(),
+                  nn.Conv2d(4, 3, 4, stride=2, padding=1), nn.ReLU(), Flatten(), nn.Linear(3 * 6 * 6, 150), nn.ReLU(),
+                  nn.Linear(150, 9), nn.ReLU()]
+        shape, B = (1, 12, 12), 6
+    fr = _custom_frontier(layers, shape, B, seed=11)
+    sd = load_gnn('random')
+    s_or, _ = O.gnn_forward(sd, fr)
+    model = _model('random', math)
+    best, idx, scores = model.score_frontier(fr.to('cuda'))
+    rep = O.parity_report(scores.cpu(), s_or, fr.mask, idx.cpu(), rtol=RTOL[math])
+    assert rep['ok'], rep
+    if math == 'tc':
+        model.scorer(0).set_option('fuse', 1)
+        b1, i1, s1 = model.score_frontier(fr.to('cuda'))
+        assert torch.equal(s1, scores) and torch.equal(i1, idx)
