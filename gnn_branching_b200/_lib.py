@@ -16,7 +16,7 @@ KERNEL_CLASSES = ['relax', 'update_fwd', 'update_bwd', 'update_bwd_score', 'inpu
 
 EXPORTS = ['gnnb_create', 'gnnb_destroy', 'gnnb_set_gnn_weights', 'gnnb_set_network', 'gnnb_set_option',
            'gnnb_get_option', 'gnnb_score', 'gnnb_check', 'gnnb_launch_count', 'gnnb_last_error',
-           'gnnb_debug_snapshot', 'gnnb_abi_version', 'gnnb_profile_read', 'gnnb_profile_reset']
+           'gnnb_debug_snapshot', 'gnnb_abi_version', 'gnnb_profile_read', 'gnnb_profile_reset', 'gnnb_babsr']
 
 _fp = C.POINTER(C.c_float)
 _fpp = C.POINTER(_fp)
@@ -64,6 +64,8 @@ def load() -> C.CDLL:
     lib.gnnb_get_option.argtypes = [vp, C.c_char_p]
     lib.gnnb_get_option.restype = C.c_int64
     lib.gnnb_score.argtypes = [vp, C.POINTER(FrontierDesc), _fp, C.POINTER(C.c_int32), _fp, vp]
+    _ip = C.POINTER(C.c_int32)
+    lib.gnnb_babsr.argtypes = [vp, C.POINTER(FrontierDesc), C.c_int32, C.c_float, _ip, _ip, _ip, _ip, _ip, _fp, vp]
     lib.gnnb_check.argtypes = [vp, vp, C.POINTER(C.c_int64)]
     lib.gnnb_launch_count.argtypes = [vp]
     lib.gnnb_launch_count.restype = C.c_int64

@@ -51,6 +51,11 @@ struct gnnb_ctx {
     std::vector<LayerTiling> tiling;
     std::vector<RowMap> rowmap;
     int32_t* d_maps = nullptr;
+    // BaBSR heuristic: device copies of the layer table, hidden offsets, preference order and the per-call pointer tables
+    LayerDev* d_layers = nullptr;
+    int32_t* d_hidden_off = nullptr;
+    int32_t* d_random_order = nullptr;
+    const float** d_ptrs = nullptr;   // [2 * (L + 2)] lb pointers then ub pointers
     std::vector<int> hidden_off;    // offset of layer k (1-based) in the flat ReLU index
     int n_hidden = 0;
     // workspace
@@ -423,6 +428,10 @@ void gnnb_destroy(gnnb_ctx* ctx) {
     if (ctx->d_tc) cudaFree(ctx->d_tc);
     if (ctx->d_net) cudaFree(ctx->d_net);
     if (ctx->d_maps) cudaFree(ctx->d_maps);
+    if (ctx->d_layers) cudaFree(ctx->d_layers);
+    if (ctx->d_hidden_off) cudaFree(ctx->d_hidden_off);
+    if (ctx->d_random_order) cudaFree(ctx->d_random_order);
+    if (ctx->d_ptrs) cudaFree(ctx->d_ptrs);
     if (ctx->d_nan) cudaFree(ctx->d_nan);
     for (PropPlan* p : ctx->plan_fwd) prop_plan_free(p);
     for (PropPlan* p : ctx->plan_bwd) prop_plan_free(p);
@@ -620,6 +629,18 @@ int gnnb_set_network(gnnb_ctx* ctx, const gnnb_layer_desc* layers, int n_layers,
     int off = 0;
     for (int k = 1; k <= n_layers; ++k) { ctx->hidden_off[k] = off; off += n[k]; }
     ctx->n_hidden = off;
+    // tables of the BaBSR kernel
+    if (ctx->d_layers) cudaFree(ctx->d_layers);
+    if (ctx->d_hidden_off) cudaFree(ctx->d_hidden_off);
+    if (ctx->d_random_order) cudaFree(ctx->d_random_order);
+    if (ctx->d_ptrs) cudaFree(ctx->d_ptrs);
+    ctx->d_layers = nullptr; ctx->d_hidden_off = nullptr; ctx->d_random_order = nullptr; ctx->d_ptrs = nullptr;
+    CU(cudaMalloc(&ctx->d_layers, n_layers * sizeof(LayerDev)));
+    CU(cudaMemcpy(ctx->d_layers, devs.data(), n_layers * sizeof(LayerDev), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&ctx->d_hidden_off, (n_layers + 1) * sizeof(int32_t)));
+    CU(cudaMemcpy(ctx->d_hidden_off, ctx->hidden_off.data() + 1, (n_layers + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&ctx->d_random_order, n_layers * sizeof(int32_t)));
+    CU(cudaMalloc(&ctx->d_ptrs, 2 * (n_layers + 2) * sizeof(float*)));
     ctx->have_net = true;
     return GNNB_OK;
 }
@@ -755,6 +776,82 @@ int gnnb_score(gnnb_ctx* ctx, const gnnb_frontier* in, float* best_score, int32_
         CU(cudaMemcpyAsync(best_idx, ctx->res_idx, (size_t)in->B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         return gnnb_check(ctx, stream, nullptr);
     }
+    return GNNB_OK;
+}
+
+int gnnb_babsr(gnnb_ctx* ctx, const gnnb_frontier* in, int32_t sparsest_layer, float decision_threshold,
+               const int32_t* random_order, const int32_t* icp_counter_in, int32_t* decision, int32_t* icp_counter_out,
+               int32_t* kind, float* scores, void* stream) {
+    if (!ctx || !in || !random_order || !decision || !icp_counter_out) return fail(ctx, GNNB_ERR_INVALID, "null argument");
+    if (!ctx->have_net) return fail(ctx, GNNB_ERR_STATE, "gnnb_set_network must be called first");
+    if (in->B < 0) return fail(ctx, GNNB_ERR_INVALID, "negative batch");
+    if (in->B == 0) return GNNB_OK;
+    if (!in->lb || !in->ub || !in->wp || !in->mask) return fail(ctx, GNNB_ERR_INVALID, "null frontier field");
+    const int L = (int)ctx->layers.size(), B = in->B;
+    if (L > babsr_max_layers()) return fail(ctx, GNNB_ERR_UNSUPPORTED, "too many layers for the BaBSR kernel");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool host = in->mem == GNNB_MEM_HOST;
+    const std::vector<int>& n = ctx->n;
+    int nmax = 0;
+    for (int k = 0; k <= L; ++k) nmax = n[k] > nmax ? n[k] : nmax;
+    // host buffers: one temporary device block for the inputs and results of this call (this entry is not the hot path)
+    float* tmp = nullptr;
+    std::vector<const float*> ptrs(2 * (L + 2), nullptr);
+    const float *d_wp = in->wp, *d_mask = in->mask;
+    const int32_t* d_cin = icp_counter_in;
+    int32_t *d_dec = decision, *d_cout = icp_counter_out, *d_kind = kind;
+    float* d_scores = scores;
+    if (host) {
+        size_t total = 0;
+        auto take = [&](size_t elems) { size_t o = total; total += align4(elems); return o; };
+        std::vector<size_t> o_lb(L + 2), o_ub(L + 2);
+        for (int k = 1; k <= L; ++k) { o_lb[k] = take((size_t)B * n[k]); o_ub[k] = take((size_t)B * n[k]); }
+        const size_t o_wp = take((size_t)B * n[L]), o_mask = take((size_t)B * ctx->n_hidden), o_cin = take(B), o_dec = take(2 * (size_t)B),
+                     o_cout = take(B), o_kind = take(B), o_sc = take(scores ? (size_t)B * ctx->n_hidden : 0);
+        CU(cudaMalloc(&tmp, total * sizeof(float)));
+        auto up = [&](size_t off, const void* src, size_t elems) {
+            cudaMemcpyAsync(tmp + off, src, elems * sizeof(float), cudaMemcpyHostToDevice, st);
+            return tmp + off;
+        };
+        for (int k = 1; k <= L; ++k) {
+            if (!in->lb[k] || !in->ub[k]) { cudaFree(tmp); return fail(ctx, GNNB_ERR_INVALID, "null bound array"); }
+            ptrs[k] = up(o_lb[k], in->lb[k], (size_t)B * n[k]);
+            ptrs[L + 2 + k] = up(o_ub[k], in->ub[k], (size_t)B * n[k]);
+        }
+        d_wp = up(o_wp, in->wp, (size_t)B * n[L]);
+        d_mask = up(o_mask, in->mask, (size_t)B * ctx->n_hidden);
+        d_cin = icp_counter_in ? reinterpret_cast<const int32_t*>(up(o_cin, icp_counter_in, B)) : nullptr;
+        d_dec = reinterpret_cast<int32_t*>(tmp + o_dec); d_cout = reinterpret_cast<int32_t*>(tmp + o_cout);
+        d_kind = kind ? reinterpret_cast<int32_t*>(tmp + o_kind) : nullptr;
+        d_scores = scores ? tmp + o_sc : nullptr;
+    } else {
+        for (int k = 1; k <= L; ++k) {
+            if (!in->lb[k] || !in->ub[k]) return fail(ctx, GNNB_ERR_INVALID, "null bound array");
+            ptrs[k] = in->lb[k];
+            ptrs[L + 2 + k] = in->ub[k];
+        }
+    }
+    // the pointer table and the preference order change per call: stream-ordered copies from pageable memory return
+    // after the source has been read, so the local vectors may go out of scope
+    cudaError_t e = cudaMemcpyAsync(ctx->d_ptrs, ptrs.data(), ptrs.size() * sizeof(float*), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_random_order, random_order, L * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+    int rc = 0;
+    if (e == cudaSuccess)
+        rc = babsr_run(ctx->d_layers, L, ctx->n_hidden, nmax, ctx->d_ptrs, ctx->d_ptrs + (L + 2), d_wp, d_mask, ctx->d_hidden_off,
+                       ctx->d_random_order, d_cin, sparsest_layer, decision_threshold, d_dec, d_cout, d_kind, d_scores, B, st,
+                       &ctx->launches);
+    if (e == cudaSuccess && rc == 0 && host) {
+        cudaMemcpyAsync(decision, d_dec, 2 * (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(icp_counter_out, d_cout, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+        if (kind) cudaMemcpyAsync(kind, d_kind, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+        if (scores) cudaMemcpyAsync(scores, d_scores, (size_t)B * ctx->n_hidden * sizeof(float), cudaMemcpyDeviceToHost, st);
+        e = cudaStreamSynchronize(st);
+    }
+    if (tmp) { cudaStreamSynchronize(st); cudaFree(tmp); }
+    if (e != cudaSuccess) return fail(ctx, GNNB_ERR_CUDA, std::string("gnnb_babsr: ") + cudaGetErrorString(e));
+    if (rc != 0) return fail(ctx, GNNB_ERR_UNSUPPORTED, "a layer is too large for the BaBSR kernel's shared-memory buffers");
+    CU(cudaGetLastError());
     return GNNB_OK;
 }
 

@@ -164,6 +164,13 @@ double prop_plan_density(const PropPlan* p);
 void prop_tc_run(const PropPlan* plan, const float* mu_in, float* nb_img, int Bc, cudaStream_t st, int64_t* launches);
 void prop_tc_property_backward(const float* wp, const float* mu_out, float* nb_img, int nL, int nslots, int Bc, cudaStream_t st, int64_t* launches);
 
+// BaBSR / KW heuristic (gnnb_babsr.cu); every pointer is a device pointer; returns -1 when the network does not fit
+int babsr_max_layers();
+int babsr_run(const LayerDev* d_layers, int L, int n_hidden, int nmax, const float* const* d_lb, const float* const* d_ub,
+              const float* wp, const float* mask, const int32_t* d_hidden_off, const int32_t* d_random_order,
+              const int32_t* counter_in, int sparsest_layer, float threshold, int32_t* decision, int32_t* counter_out,
+              int32_t* kind, float* scores, int B, cudaStream_t st, int64_t* launches);
+
 // ---- device helpers ---------------------------------------------------------------------------
 // compute_ratio of graph_conv.py:499-514 in the reference's operation order (IEEE division, no fast-math)
 struct Ratio { float r0, r1, beta, amb; };

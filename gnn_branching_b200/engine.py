@@ -168,6 +168,48 @@ class Scorer:
                 self.check()
         return best, idx, scores
 
+    def babsr(self, fr: Frontier, icp_score_counter=None, random_order=None, sparsest_layer: int = 0,
+              decision_threshold: float = 0.001, return_scores: bool = False):
+        """BaBSR / KW heuristic decisions for every subdomain of ``fr`` (plnn/kw_score_conv.py:41-156, batched).
+
+        Returns (decision [B, 2] i32 = (layer, index in layer), counters [B] i32, kind [B] i32, scores or None);
+        tensors live where ``fr`` lives."""
+        if self.net is None:
+            raise RuntimeError('set_network first')
+        net, B = self.net, fr.B
+        L = net.L
+        host = fr.device.type == 'cpu'
+        sizes = [net.n0] + net.hidden_sizes + [1]
+        lb = [self._as_f32(fr.lb[k], (B, sizes[k])) for k in range(L + 2)]
+        ub = [self._as_f32(fr.ub[k], (B, sizes[k])) for k in range(L + 2)]
+        wp, mask = self._as_f32(fr.Wp, (B, sizes[L])), self._as_f32(fr.mask, (B, net.n_hidden))
+        dev = fr.device
+        if random_order is None:                                  # relu_conv_gnnkwthreshold.py:98-101
+            random_order = [sparsest_layer] + [k for k in range(L) if k != sparsest_layer] if sparsest_layer >= 0 else list(range(L))
+        order = (C.c_int32 * L)(*[int(k) for k in random_order])
+        cin = None
+        if icp_score_counter is not None:
+            cin = torch.as_tensor(icp_score_counter, dtype=torch.int32).to(dev).contiguous()
+        dec = torch.empty(B, 2, dtype=torch.int32, device=dev)
+        cout = torch.empty(B, dtype=torch.int32, device=dev)
+        kind = torch.empty(B, dtype=torch.int32, device=dev)
+        scores = torch.empty(B, net.n_hidden, dtype=torch.float32, device=dev) if return_scores else None
+        if B == 0:
+            return dec, cout, kind, scores
+        d = _lib.FrontierDesc()
+        d.B, d.mem = B, (_lib.MEM_HOST if host else _lib.MEM_DEVICE)
+        plb, k1 = _lib.fptr_array(lb)
+        pub, k2 = _lib.fptr_array(ub)
+        d.lb, d.ub, d.wp, d.mask = plb, pub, _lib.fptr(wp), _lib.fptr(mask)
+        ip = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_int32)) if t is not None else None
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            self._ok(self.lib.gnnb_babsr(self.h, C.byref(d), int(sparsest_layer), float(decision_threshold), order, ip(cin),
+                                         ip(dec), ip(cout), ip(kind), _lib.fptr(scores) if scores is not None else None,
+                                         C.c_void_p(stream)))
+        del k1, k2
+        return dec, cout, kind, scores
+
     def check(self) -> None:
         """Synchronise and raise if a NaN appeared in an embedding (the reference drops into pdb there)."""
         n = C.c_int64(0)

@@ -125,6 +125,22 @@ int64_t gnnb_get_option(gnnb_ctx* ctx, const char* key);
 int gnnb_score(gnnb_ctx* ctx, const gnnb_frontier* in, float* best_score, int32_t* best_idx, float* scores,
                void* stream);
 
+/* BaBSR / KW branching heuristic for B subdomains at once.  Replaces choose_node_conv (plnn/kw_score_conv.py:41-156),
+ * the hand-written score the reference falls back to when the GNN decision did not improve the bound
+ * (plnn/relu_conv_gnnkwthreshold.py:155-157).  Uses `in->lb`, `in->ub` (hidden layers), `in->wp`, `in->mask` and
+ * `in->mem`; the other frontier fields may be NULL.
+ *   random_order      [L] HOST: layer preference of the last fallback, most preferred last (relu_conv_gnnkwthreshold.py:98-101)
+ *   icp_counter_in    [B] or NULL (= zeros): the caller's icp_score_counter per subdomain
+ *   decision          [B, 2] (layer, index within the layer); (-1, -1) when the subdomain has no candidate
+ *   icp_counter_out   [B] updated counters
+ *   kind              [B] or NULL: 0 = score decision, 1 = intercept score, 2 = preference order, -1 = no candidate
+ *   scores            [B, sum n_k] or NULL: the masked |score| of every hidden ReLU (the reference's gt=True output)
+ * Arrays other than random_order live in the memory space `in->mem`; with HOST buffers the call returns after the
+ * results have landed, with DEVICE buffers it only enqueues on `stream`. */
+int gnnb_babsr(gnnb_ctx* ctx, const gnnb_frontier* in, int32_t sparsest_layer, float decision_threshold,
+               const int32_t* random_order, const int32_t* icp_counter_in, int32_t* decision, int32_t* icp_counter_out,
+               int32_t* kind, float* scores, void* stream);
+
 /* Synchronise `stream` and report sticky device-side errors of earlier gnnb_score calls
  * (GNNB_ERR_NAN with the NaN count in *nan_count, may be NULL).  Clears the flag. */
 int gnnb_check(gnnb_ctx* ctx, void* stream, int64_t* nan_count);

@@ -285,3 +285,59 @@ def test_other_network_shapes_match_oracle(case, math):
         model.scorer(0).set_option('fuse', 1)
         b1, i1, s1 = model.score_frontier(fr.to('cuda'))
         assert torch.equal(s1, scores) and torch.equal(i1, idx)
+
+
+# ---- BaBSR / KW heuristic -------------------------------------------------------------------
+@pytest.mark.parametrize('case', ['fr', 'root'])
+@pytest.mark.parametrize('arch', ARCHS)
+def test_babsr_matches_reference(arch, case):
+    """gnnb_babsr against the reference's choose_node_conv outputs: scores to 1e-5 of the largest score, decisions and
+    counters exactly, in the three branches of the decision rule; device and host buffers agree."""
+    import numpy as np
+    from golden_io import GOLDEN
+    from gnn_branching_b200 import babsr_frontier
+    z = dict(np.load(os.path.join(GOLDEN, f'babsr_{arch}.npz')))
+    fr, _ = load_case(arch, case)
+    order = [0] + [k for k in range(fr.net.L) if k != 0]
+    ref = torch.from_numpy(z[f'{case}_scores'])
+    for name, (thr, cnt) in {'score': (0.001, 0), 'intercept': (1e9, 0), 'order': (1e9, 2)}.items():
+        dec, cout, kind, scores = babsr_frontier(fr.to('cuda'), [cnt] * fr.B, order, 0, thr, return_scores=True)
+        assert float((scores.cpu() - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+        assert dec.cpu().tolist() == z[f'{case}_{name}_decisions'].tolist()
+        assert cout.cpu().tolist() == z[f'{case}_{name}_counters'].tolist()
+        assert kind.cpu().tolist() == [{'score': 0, 'intercept': 1, 'order': 2}[name]] * fr.B
+        d2, c2, k2, s2 = babsr_frontier(fr.contiguous(), [cnt] * fr.B, order, 0, thr, return_scores=True)
+        assert not d2.is_cuda and torch.equal(d2, dec.cpu()) and torch.equal(c2, cout.cpu()) and torch.equal(s2, scores.cpu())
+
+
+@pytest.mark.parametrize('arch,B', [('base', 1024), ('deep', 257)])
+def test_babsr_frontier_matches_oracle(arch, B):
+    """A whole synthetic frontier: scores against the oracle, decisions equal wherever the oracle's top-2 margin
+    exceeds the tolerance; the reference-signature wrapper agrees on single subdomains."""
+    from gnn_branching_b200 import babsr_frontier, choose_node_conv
+    from oracle import babsr_oracle as BO
+    net, lbs, ubs, wp, bp = load_root(arch)
+    fr = synthetic_frontier(net, lbs, ubs, wp, bp, B, seed=31, device='cuda')
+    order = [0] + [k for k in range(net.L) if k != 0]
+    dec, cout, kind, scores = babsr_frontier(fr, None, order, 0, 0.001, return_scores=True)
+    fc = fr.cpu().contiguous()
+    sc, ic = BO.babsr_scores(fc)
+    tol = 1e-5 * float(sc.abs().max())
+    assert float((scores.cpu() - sc).abs().max()) <= tol
+    d_or, c_or, k_or = BO.babsr_decide(sc, ic, fc.mask, net.hidden_sizes, [0] * B, order, 0, 0.001)
+    top2 = sc.topk(2, dim=1).values
+    safe = (top2[:, 0] - top2[:, 1]) > 2 * tol
+    assert int(safe.sum()) > B // 2
+    assert torch.equal(dec.cpu()[safe].long(), d_or[safe]) and torch.equal(cout.cpu()[safe].long(), c_or[safe])
+    # reference-signature call, B = 1
+    one = fc.slice(3, 4)
+    lbs1, ubs1, _, _, _, layers, masks = one.to_reference_args()
+    modules = layers['fixed_layers'] + [layers['prop_layers'][0]]
+    pre_relu = list(range(1, net.L + 1))
+    init_mask, off = [], 0
+    for n in net.hidden_sizes:
+        m = masks[0, off:off + n]
+        init_mask.append(torch.where(m != 0, torch.full_like(m, -1), torch.ones_like(m)).int())
+        off += n
+    d1, c1 = choose_node_conv([t[0] for t in lbs1], [t[0] for t in ubs1], init_mask, modules, pre_relu, 0, order, 0)
+    assert d1 == dec[3].tolist() and c1 == int(cout[3])

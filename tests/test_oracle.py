@@ -71,3 +71,32 @@ def test_compute_ratio_cases():
     assert beta.tolist() == [0.5, 0.0, 0.0, 0.0, 0.0]
     r0, _, _, _ = O.compute_ratio(torch.zeros(1), torch.zeros(1))
     assert torch.isnan(r0).all()          # l = u = 0 is 0/0 in the reference too
+
+
+# ---- BaBSR / KW heuristic -------------------------------------------------------------------
+BABSR_SCENARIOS = {'score': (0.001, 0), 'intercept': (1e9, 0), 'order': (1e9, 2)}
+
+
+def _babsr_golden(arch):
+    import numpy as np
+    import os
+    from golden_io import GOLDEN
+    return dict(np.load(os.path.join(GOLDEN, f'babsr_{arch}.npz')))
+
+
+@pytest.mark.parametrize('case', ['fr', 'root'])
+@pytest.mark.parametrize('arch', ARCHS)
+def test_babsr_oracle_matches_reference(arch, case):
+    """oracle/babsr_oracle.py against the reference's choose_node_conv outputs (tests/golden/make_golden_babsr.py):
+    scores to 1e-6, decisions and intercept counters exactly, in the three branches of the decision rule."""
+    from oracle import babsr_oracle as BO
+    z = _babsr_golden(arch)
+    fr, _ = load_case(arch, case)
+    sc, ic = BO.babsr_scores(fr)
+    ref = torch.from_numpy(z[f'{case}_scores'])
+    assert float((sc - ref).abs().max()) <= 1e-6 * max(1.0, float(ref.abs().max()))
+    order = [0] + [k for k in range(fr.net.L) if k != 0]
+    for name, (thr, cnt) in BABSR_SCENARIOS.items():
+        d, c, _ = BO.babsr_decide(sc, ic, fr.mask, fr.net.hidden_sizes, [cnt] * fr.B, order, 0, thr)
+        assert d.tolist() == z[f'{case}_{name}_decisions'].tolist()
+        assert c.tolist() == z[f'{case}_{name}_counters'].tolist()
