@@ -41,6 +41,7 @@ def parse():
     ap.add_argument('--weights', default='random', choices=['random', 'shipped'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-babsr', action='store_true')
     ap.add_argument('--opt', action='append', default=[], help='library option key=value (e.g. fuse=0, prop_share=40)')
     return ap.parse_args()
 
@@ -58,7 +59,7 @@ def load_weights(which):
 
 # ---------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms during the timed region."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
@@ -69,7 +70,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-lms', '200', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          '-lms', '50', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -345,6 +346,37 @@ def main():
     except (OSError, ValueError, KeyError):
         roofline['traffic'] = None
 
+    # ---- the BaBSR / KW heuristic on the same frontier (secondary line, not the headline metric) ----
+    babsr = None
+    if world == 1 and not args.no_babsr:
+        from gnn_branching_b200 import babsr_frontier
+        fr0 = fronts[0]
+        for _ in range(3):
+            babsr_frontier(fr0, scorer=scorer)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(20):
+            babsr_frontier(fronts[i % 2], scorer=scorer)
+        e1.record()
+        torch.cuda.synchronize()
+        bms = e0.elapsed_time(e1) / 20
+        bbytes = B * (sum(net.hidden_sizes) * 12 + net.hidden_sizes[-1] * 4 + 16)      # l, u, mask per ReLU; Wp; outputs
+        babsr = {'value': B / (bms * 1e-3), 'unit': UNIT, 'ms_per_call': bms, 'subdomains': B,
+                 'roofline': {'bound': 'hbm', 'achieved': bbytes / (bms * 1e-3) / 1e9, 'peak': peak_gbs, 'unit': 'GB/s',
+                              'frac': bbytes / (bms * 1e-3) / 1e9 / peak_gbs},
+                 'note': 'choose_node_conv (plnn/kw_score_conv.py:41-156) batched, one thread block per subdomain, device-resident inputs'}
+        if not args.no_cpu_baseline:
+            from oracle import babsr_oracle as BO
+            fc = fr0.slice(0, 64).cpu().contiguous()
+            order = [0] + list(range(1, net.L))
+            t0 = time.perf_counter()
+            for _ in range(3):
+                sc_, ic_ = BO.babsr_scores(fc)
+                BO.babsr_decide(sc_, ic_, fc.mask, net.hidden_sizes, [0] * 64, order, 0)
+            babsr['cpu_baseline'] = {'value': 3 * 64 / (time.perf_counter() - t0), 'unit': UNIT, 'kind': 'port', 'cores': os.cpu_count(),
+                                     'sample': '64 subdomains x 3 passes, oracle/babsr_oracle.py (batched scores, per-domain decision rule)'}
+
     cb = None
     if not args.no_cpu_baseline and world == 1:
         cb, _ = cpu_baseline(args.workload, args.weights)
@@ -357,7 +389,8 @@ def main():
                        'chunk': scorer.get_option('workspace_domains'),
                        'l2': 'two alternating frontiers; inputs + per-chunk workspace exceed the 126 MB L2',
                        'sharding': f'{world} ranks x {B} subdomains, winners all-gathered (8 B/subdomain)'},
-            'clocks': clk.summary(), 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cb}
+            'clocks': clk.summary(), 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cb,
+            'babsr': babsr}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -135,26 +135,42 @@ __global__ void __launch_bounds__(BT) k_babsr(BabsrArgs a) {
         const int n_in = Lk.n_in;
         if (Lk.kind == GNNB_LAYER_CONV) {
             const int hw_in = Lk.h_in * Lk.w_in, hw_out = Lk.h_out * Lk.w_out, ks = Lk.ksize, s = Lk.stride, p = Lk.pad;
+            const int wstride = Lk.c_in * ks * ks;                       // between output channels of the weight tensor
             for (int j = t; j < n_in; j += BT) {
                 const int ci = j / hw_in, yi = (j % hw_in) / Lk.w_in, xi = j % Lk.w_in;
                 float acc = 0.f;
-                for (int co = 0; co < Lk.c_out; ++co)
-                    for (int ky = 0; ky < ks; ++ky) {
-                        const int ty = yi + p - ky;
-                        if (ty < 0 || ty % s != 0 || ty / s >= Lk.h_out) continue;
-                        for (int kx = 0; kx < ks; ++kx) {
-                            const int tx = xi + p - kx;
-                            if (tx < 0 || tx % s != 0 || tx / s >= Lk.w_out) continue;
-                            acc = fmaf(Lk.weight[((co * Lk.c_in + ci) * ks + ky) * ks + kx], ratio[co * hw_out + (ty / s) * Lk.w_out + tx / s], acc);
-                        }
+                for (int ky = 0; ky < ks; ++ky) {                          // taps first: their validity does not depend on co
+                    const int ty = yi + p - ky;
+                    if (ty < 0 || ty % s != 0 || ty / s >= Lk.h_out) continue;
+                    for (int kx = 0; kx < ks; ++kx) {
+                        const int tx = xi + p - kx;
+                        if (tx < 0 || tx % s != 0 || tx / s >= Lk.w_out) continue;
+                        const float* w = Lk.weight + (ci * ks + ky) * ks + kx;
+                        const float* r = ratio + (ty / s) * Lk.w_out + tx / s;
+#pragma unroll 4
+                        for (int co = 0; co < Lk.c_out; ++co) acc = fmaf(__ldg(w + co * wstride), r[co * hw_out], acc);
                     }
+                }
                 next[j] = acc;
             }
         } else {
-            for (int j = t; j < n_in; j += BT) {
-                float acc = 0.f;
-                for (int o = 0; o < n; ++o) acc = fmaf(Lk.weight[(int64_t)o * n_in + j], ratio[o], acc);
-                next[j] = acc;
+            // W^T @ ratio: each thread owns up to 8 input nodes (BT apart, so a warp reads 128 contiguous bytes of a weight
+            // row) and walks the rows with 8 independent loads in flight per row, 4 rows unrolled
+            for (int j0 = 0; j0 < n_in; j0 += BT * 8) {
+                float acc[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+#pragma unroll 4
+                for (int o = 0; o < n; ++o) {
+                    const float r = ratio[o];
+                    const float* wrow = Lk.weight + (int64_t)o * n_in + j0 + t;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (j0 + t + q * BT < n_in) acc[q] = fmaf(__ldg(wrow + q * BT), r, acc[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (j0 + t + q * BT < n_in) next[j0 + t + q * BT] = acc[q];
             }
         }
         __syncthreads();

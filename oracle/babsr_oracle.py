@@ -1,6 +1,6 @@
 """ORACLE — TEST INFRASTRUCTURE ONLY.  CPU restatement of the BaBSR / KW branching heuristic.
 
-Only ``tests/`` may import this module, as the checker.  What it restates: ``choose_node_conv`` of
+Only ``tests/`` and ``bench.py``'s cpu_baseline leg may import this module, as the checker / the timed CPU baseline.  What it restates: ``choose_node_conv`` of
 oval-group/GNN_branching (plnn/kw_score_conv.py:41-156; ``compute_ratio`` :23-37), the hand-written score the
 reference falls back to when the GNN decision did not improve the bound enough
 (plnn/relu_conv_gnnkwthreshold.py:155-157) — SURVEY §8f rank 1.  Batched over subdomains; the reference runs
