@@ -708,7 +708,7 @@ int gnnb_score(gnnb_ctx* ctx, const gnnb_frontier* in, float* best_score, int32_
     const bool host = in->mem == GNNB_MEM_HOST;
     // subdomains per wave: large waves amortise launches and tails; with host buffers smaller waves let the copies of
     // wave i + 1 (copy stream, second staging set) run under the kernels of wave i
-    int chunk = ctx->chunk > 0 ? ctx->chunk : (host ? 512 : 1024);
+    int chunk = ctx->chunk > 0 ? ctx->chunk : 1024;
     if (chunk > in->B) chunk = in->B;
     TRY(ensure_workspace(ctx, chunk, host));
     const std::vector<int>& n = ctx->n;
@@ -723,10 +723,12 @@ int gnnb_score(gnnb_ctx* ctx, const gnnb_frontier* in, float* best_score, int32_
 
     // host buffers: the first waves are small so that the kernels start after a short copy, then the wave size doubles
     // up to `chunk` (the copy engine outruns the kernels, so later waves always find their inputs staged)
-    int wave = 0, ramp = host ? (chunk / 4 > 64 ? chunk / 4 : (chunk < 64 ? chunk : 64)) : chunk;
+    // (the copy engine moves a subdomain's inputs ~1.8x faster than the kernels score it, and small waves cost a fixed
+    // ~0.25 ms of launches: 64, 256, 1024, 1024, ... keeps every copy shorter than the compute it hides behind)
+    int wave = 0, ramp = host ? (chunk < 64 ? chunk : 64) : chunk;
     for (int c0 = 0, Bc = 0; c0 < in->B; c0 += Bc, ++wave) {
         Bc = (in->B - c0) < ramp ? (in->B - c0) : ramp;
-        ramp = ramp * 2 > chunk ? chunk : ramp * 2;
+        ramp = ramp * 4 > chunk ? chunk : ramp * 4;
         gnnb_ctx::Staging& sg = ctx->stg[wave & 1];
         cudaStream_t cs = host ? ctx->copy_stream : st;
         if (host && wave >= 2) CU(cudaStreamWaitEvent(cs, ctx->ev_free[wave & 1], 0));   // this staging set's previous wave is done
