@@ -344,11 +344,13 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
         for (int k = L; k >= 1; --k) {
             const int64_t rows = R(k), nodes = (int64_t)Bc * ctx->n[k];
             float* sc = last ? scores : nullptr;
+            // the last sweep's embeddings of the first hidden layer feed only the (dead) last input-layer update: not stored
+            float* mu_k = (last && k == 1 && tc && !ctx->snapshot) ? nullptr : ctx->mu[k];
             const bool fused_k = fused && k < L;           // the property layer's rank-1 back-propagation is a separate small kernel
             if (fused_k) {
                 ProfScope ps(ctx, last ? GNNB_K_LAYER_BWD_SCORE : GNNB_K_LAYER_BWD, nodes, st);
                 tc_layer(g, ctx->plan_bwd[k], ctx->mu[k + 1], true, in.lb[k], in.ub[k], ctx->nb, ctx->relax_b[k], ctx->amb_base[k],
-                         ctx->mu[k], sc, M(k), ctx->n_hidden, ctx->hidden_off[k], rows, ctx->d_nan, ctx->d_flags, ++ctx->epoch,
+                         mu_k, sc, M(k), ctx->n_hidden, ctx->hidden_off[k], rows, ctx->d_nan, ctx->d_flags, ++ctx->epoch,
                          ctx->prop_share, ctx->d_flags - 1, &ctx->consumed_base, ctx->lead, st, lc);
             } else {
                 ProfScope ps(ctx, GNNB_K_PROP_BWD, nodes, st);
@@ -360,7 +362,7 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
             TRY(snap_img(ctx, name("t%d_bwd_nb%d", t, k), ctx->nb, k, Bc, true, st));
             if (!fused_k) {
                 ProfScope ps(ctx, last ? GNNB_K_UPDATE_BWD_SCORE : GNNB_K_UPDATE_BWD, nodes, st);
-                if (tc) tc_update(g, true, in.lb[k], in.ub[k], ctx->nb, ctx->relax_b[k], ctx->amb_base[k], ctx->mu[k], sc, M(k), ctx->n_hidden, ctx->hidden_off[k], rows, ctx->d_nan, st, lc);
+                if (tc) tc_update(g, true, in.lb[k], in.ub[k], ctx->nb, ctx->relax_b[k], ctx->amb_base[k], mu_k, sc, M(k), ctx->n_hidden, ctx->hidden_off[k], rows, ctx->d_nan, st, lc);
                 else simt_update(g, true, in.lb[k], in.ub[k], ctx->nb, ctx->relax_b[k], ctx->mu[k], sc, ctx->n[k], ctx->n_hidden, ctx->hidden_off[k], rows, ctx->d_nan, st, lc);
             }
             TRY(snap_img(ctx, name("t%d_bwd_mu%d", t, k), ctx->mu[k], k, Bc, false, st));

@@ -199,7 +199,7 @@ __device__ __forceinline__ void first_layer_to_a(const WG& c, const float (&feat
 // TO_A: the same values also become the next A operand (score head).  Returns true on NaN in a valid row.
 template <bool TO_A>
 __device__ __forceinline__ bool epilogue_to_mu(const WG& c, uint32_t dcol, const float* __restrict__ bias_s, float rowscale,
-                                               bool valid) {
+                                               bool valid, bool stage = true) {
     bool bad = false;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -215,7 +215,7 @@ __device__ __forceinline__ bool epilogue_to_mu(const WG& c, uint32_t dcol, const
 #pragma unroll
         for (int i = 0; i < 8; ++i) split2(v[2 * i], v[2 * i + 1], w[i], w[8 + i]);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < 2 && stage; ++h) {
             const uint32_t off = swz((uint32_t)c.t, (uint32_t)(q * 2 + h));
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(c.land + off), "r"(w[4 * h]), "r"(w[4 * h + 1]),
                          "r"(w[4 * h + 2]), "r"(w[4 * h + 3]) : "memory");
@@ -477,8 +477,10 @@ __device__ __forceinline__ void update_body(const UpdArgs& a, unsigned char* sme
             bad |= epilogue_to_mu<false>(c, DCOL, tl.bias[2], gate, nrow >= 0);
             commit_tile(c, mu_out + (size_t)tile * (ABUF / 2));
         } else {      // score head on the new embeddings (graph_conv.py:448-449)
-            bad |= epilogue_to_mu<true>(c, DCOL, tl.bias[2], gate, nrow >= 0);
-            commit_tile(c, mu_out + (size_t)tile * (ABUF / 2));
+            bad |= epilogue_to_mu<true>(c, DCOL, tl.bias[2], gate, nrow >= 0, mu_out != nullptr);
+            // mu_out == null: nothing reads these embeddings (first hidden layer on the last backward sweep: its only
+            // consumer would be the input-layer update, which is dead on the last round) — the scores are all that is kept
+            if (mu_out != nullptr) commit_tile(c, mu_out + (size_t)tile * (ABUF / 2));
             gemm_ts(c, W + UPD_FN, W + UPD_FN + WPLANE, 64, DCOL);
             float sc = 0.f;
 #pragma unroll
