@@ -388,19 +388,36 @@ __device__ __forceinline__ void update_body(const UpdArgs& a, unsigned char* sme
     const int64_t nitems = (int64_t)tiles_per_dom * ((a.Bc + NWG - 1) / NWG);
     bool bad = false;
     GNNB_TR_DECL;
+    // this row's bounds are fetched one item ahead (two dependent 4-byte gathers from HBM would otherwise stall the
+    // warpgroup at the top of every tile)
+    int64_t nrow_n = -1;
+    float l_n = 0.f, u_n = 1.f;
+    int slot0_n = 0;
+    auto fetch_row = [&](int64_t it) {
+        nrow_n = -1; l_n = 0.f; u_n = 1.f; slot0_n = 0;
+        if (it >= nitems) return;
+        const int d = (int)(it / tiles_per_dom) * NWG + c.wg;
+        if (d >= a.Bc) return;
+        const int64_t tl_ = (int64_t)d * tiles_per_dom + it % tiles_per_dom;
+        nrow_n = natural_row(map, tl_ * TILE + c.t);           // index into the caller's [B, n] arrays, -1 = padding slot
+        if (nrow_n >= 0) { l_n = ldg1_now(lb + nrow_n); u_n = ldg1_now(ub + nrow_n); }
+        slot0_n = __ldg(amb_base + tl_);
+    };
+    fetch_row(rank);
     for (int64_t item = rank; item < nitems; item += nranks) {
         const int dom = (int)(item / tiles_per_dom) * NWG + c.wg;
+        const int64_t nrow = nrow_n;
+        const float l = l_n, u = u_n;
+        const int slot0 = slot0_n;
         if (dom >= a.Bc) {
             if (a.consumed != nullptr && c.t == 0) atomicAdd(a.consumed, 1);
+            fetch_row(item + nranks);
             continue;
         }
         const int64_t tile = (int64_t)dom * tiles_per_dom + item % tiles_per_dom;
         const int64_t row0 = tile * TILE, grow = row0 + c.t;
         request_nb(c, nb_img + (size_t)tile * (ABUF / 2), flags ? flags + item : nullptr, epoch);
-        float l = 0.f, u = 1.f;
-        const int64_t nrow = natural_row(map, grow);           // index into the caller's [B, n] arrays, -1 = padding slot
-        if (nrow >= 0) { l = ldg1_now(lb + nrow); u = ldg1_now(ub + nrow); }
-        const int slot0 = __ldg(amb_base + tile);
+        fetch_row(item + nranks);
         const Ratio q = compute_ratio(l, u);
         const float gate = (q.r0 != 0.0f) ? 1.0f : 0.0f;
         // slot of this row's relax' = first slot of the tile + number of ambiguous rows before it (amb_compact keeps row order)
