@@ -16,27 +16,31 @@
 //       D = nb [W3a; W3b]^T (N = 128) -> h3 = relu(r0 Da + r1 Db + b3) -> D = h3 Wc^T -> g = relu(D + relax' + bc)
 //       -> D = g W4_2^T -> mu = (D + b4_2) (r0 != 0)   [-> score head on the last backward sweep];
 //   * row scalings of GEMM *inputs* move to the epilogue by linearity: [nb r0, nb r1] W3^T is one
-//     N = 128 MMA, bc2's [s1, -d2 s1, d1 s1] input one N = 192 MMA.
+//     N = 128 MMA, bc2's [s1, -d2 s1, d1 s1] input three N = 64 MMAs that share one A operand (summed in registers).
 //
-// Structure of a CTA (1 per SM, persistent over tiles): 4 warpgroups of 128 threads; the stage's weights sit in shared
-// memory for the CTA's lifetime as fp16 hi/lo planes in the UMMA K-major SWIZZLE_128B image (repacked once on the host,
-// landed with one cp.async.bulk per linear); each warpgroup owns one 128-node tile at a time with 128 tensor-memory
-// columns, a 32 KB shared-memory landing buffer for the tile's nb image and two mbarriers, and walks the chain of its
-// tile sequentially:
+// Rows are in slot order (gnnb_common.cuh RowMap): a tile is 128 slots of one subdomain = one tile of the propagation
+// plans; the caller's node-order arrays (bounds, duals, primals, scores) are reached through node_of_slot.
+//
+// Structure of a CTA (1 per SM, persistent over work items = 4 subdomains x tile, one tile per warpgroup): 4 warpgroups
+// of 128 threads; the stage's weights sit in shared memory for the CTA's lifetime as fp16 hi/lo planes in the UMMA
+// K-major SWIZZLE_128B image (repacked once on the host, landed with one cp.async.bulk per linear); each warpgroup
+// owns one 128-slot tile at a time with 128 tensor-memory columns, a 32 KB shared-memory buffer and two mbarriers, and
+// walks the chain of its tile sequentially:
 //   GEMM (one thread issues 3 x 4 tcgen05.mma + tcgen05.commit) -> everyone waits on the mbarrier -> tcgen05.ld ->
-//   bias / ReLU / row scaling in registers (thread = node row = TMEM lane) -> fp16 hi/lo split -> tcgen05.st of the next
+//   bias / ReLU / row scaling in registers (thread = row = TMEM lane) -> fp16 hi/lo split -> tcgen05.st of the next
 //   A operand straight back into tensor memory -> tcgen05.wait::st + fence + warpgroup barrier -> next GEMM ...
-// Only the first GEMM of the update chain reads its A operand from shared memory (the TMA'd nb image); every chained
-// GEMM takes A from tensor memory (the ".ts" form of tcgen05.mma), so intermediate activations never touch shared
-// memory: no generic-proxy stores, no proxy fences, and the tensor core's shared-memory reads are the weights only.
-// The landing buffer is free as soon as the first GEMM has completed, so the next tile's image (and an L2 prefetch of
-// its relax' tile) is in flight during the whole rest of the chain.  The warpgroups are independent, so one tile's
-// epilogue overlaps the others' MMAs and loads.
+// Only the first GEMM of the update chain reads its A operand from shared memory (the nb tile image, one 32 KB
+// cp.async.bulk, used as a no-swizzle K-major operand); every chained GEMM takes A from tensor memory (the ".ts" form
+// of tcgen05.mma), so intermediate activations never touch shared memory.  The same 32 KB buffer then stages the
+// tile's result as the mu image (conflict-free swizzled 16-byte stores) and leaves with one bulk store; the next
+// tile's nb image is requested once the store has read the buffer (it was prefetched to L2 a tile earlier, as are the
+// row's relax' pieces and bounds).  The warpgroups are independent, so one tile's epilogue overlaps the others' MMAs.
 //
-// Private workspace layouts (produced and consumed only by the tensor-core kernels):
-//   nb       per tile of 128 consecutive rows: the A-operand image itself, [hi plane 16 KB][lo plane 16 KB], scaled by
-//            ASCALE — written by the propagation kernels, loaded with one 32 KB cp.async.bulk;
-//   relax'   [tile][16 channel quads][128 rows][4] fp32 (scaled domain), so that thread = row reads are coalesced.
+// Private workspace layouts (produced and consumed only by the tensor-core kernels; gnnb_umma.cuh):
+//   nb       per tile the A-operand image itself, [hi plane 16 KB][lo plane 16 KB] piece-major, scaled by ASCALE —
+//            written by the propagation kernel, loaded with one 32 KB cp.async.bulk;
+//   mu       per tile [hi plane][lo plane] K-major SWIZZLE_128B (a row's 64 channels = 128 contiguous bytes), bulk-stored;
+//   relax'   ambiguous rows only, compacted in row order: [tile][16 channel quads][128 slots][4] fp32 (scaled domain).
 #include "gnnb_prop_body.cuh"
 
 namespace gnnb {
