@@ -16,7 +16,8 @@ KERNEL_CLASSES = ['relax', 'update_fwd', 'update_bwd', 'update_bwd_score', 'inpu
 
 EXPORTS = ['gnnb_create', 'gnnb_destroy', 'gnnb_set_gnn_weights', 'gnnb_set_network', 'gnnb_set_option',
            'gnnb_get_option', 'gnnb_score', 'gnnb_check', 'gnnb_launch_count', 'gnnb_last_error',
-           'gnnb_debug_snapshot', 'gnnb_abi_version', 'gnnb_profile_read', 'gnnb_profile_reset', 'gnnb_babsr']
+           'gnnb_debug_snapshot', 'gnnb_abi_version', 'gnnb_profile_read', 'gnnb_profile_reset', 'gnnb_babsr',
+           'gnnb_score_grad', 'gnnb_get_gradients', 'gnnb_get_gnn_weights', 'gnnb_adam_step', 'gnnb_adam_reset']
 
 _fp = C.POINTER(C.c_float)
 _fpp = C.POINTER(_fp)
@@ -66,6 +67,11 @@ def load() -> C.CDLL:
     lib.gnnb_score.argtypes = [vp, C.POINTER(FrontierDesc), _fp, C.POINTER(C.c_int32), _fp, vp]
     _ip = C.POINTER(C.c_int32)
     lib.gnnb_babsr.argtypes = [vp, C.POINTER(FrontierDesc), C.c_int32, C.c_float, _ip, _ip, _ip, _ip, _ip, _fp, vp]
+    lib.gnnb_score_grad.argtypes = [vp, C.POINTER(FrontierDesc), C.c_int32, _ip, _ip, _fp, _fp, vp]
+    lib.gnnb_get_gradients.argtypes = [vp, _fpp, C.POINTER(C.c_int64), C.c_int]
+    lib.gnnb_get_gnn_weights.argtypes = [vp, _fpp, C.POINTER(C.c_int64), C.c_int]
+    lib.gnnb_adam_step.argtypes = [vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp]
+    lib.gnnb_adam_reset.argtypes = [vp]
     lib.gnnb_check.argtypes = [vp, vp, C.POINTER(C.c_int64)]
     lib.gnnb_launch_count.argtypes = [vp]
     lib.gnnb_launch_count.restype = C.c_int64

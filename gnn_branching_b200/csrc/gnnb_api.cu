@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "gnnb_common.cuh"
+#include "gnnb_train.cuh"
 
 using namespace gnnb;
 
@@ -41,6 +42,12 @@ struct gnnb_ctx {
     float* d_gnn = nullptr;
     uint16_t* d_tc = nullptr;
     GnnParams gp{};
+    // online fine-tuning (gnnb_train.cu): master parameters in nn.Linear layout, gradients and Adam moments, one block of
+    // 4 * n_params floats [master | grad | exp_avg | exp_avg_sq]; offsets of weight / bias of each linear inside a quarter
+    float* d_train = nullptr;
+    int64_t n_params = 0;
+    size_t po_w[N_LIN] = {0}, po_b[N_LIN] = {0};
+    int adam_steps = 0;
     // verified network
     bool have_net = false;
     float* d_net = nullptr;
@@ -390,72 +397,9 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
     return GNNB_OK;
 }
 
-}  // namespace
-
-extern "C" {
-
-int gnnb_abi_version(void) { return 1; }
-
-int gnnb_create(gnnb_ctx** out, int device) {
-    if (!out) return GNNB_ERR_INVALID;
-    *out = nullptr;
-    gnnb_ctx* ctx = new gnnb_ctx();
-    ctx->device = device;
-    cudaError_t e = cudaSetDevice(device);
-    if (e != cudaSuccess) { delete ctx; return GNNB_ERR_CUDA; }
-    cudaDeviceProp prop;
-    e = cudaGetDeviceProperties(&prop, device);
-    if (e != cudaSuccess) { delete ctx; return GNNB_ERR_CUDA; }
-    if (prop.major != 10) {   // sm_100a cubins only; there is no other code path
-        fprintf(stderr, "libgnnb: device %d is sm_%d%d; this library is built for sm_100a (B200) only\n", device, prop.major, prop.minor);
-        delete ctx;
-        return GNNB_ERR_UNSUPPORTED;
-    }
-    if (cudaMalloc(&ctx->d_nan, sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMemset(ctx->d_nan, 0, sizeof(unsigned long long)) != cudaSuccess ||
-        simt_init() != 0 || prop_init(64 * 1024) != 0 || tc_init() != 0 || prop_tc_init() != 0) {
-        fprintf(stderr, "libgnnb: initialisation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
-        delete ctx;
-        return GNNB_ERR_CUDA;
-    }
-    *out = ctx;
-    return GNNB_OK;
-}
-
-void gnnb_destroy(gnnb_ctx* ctx) {
-    if (!ctx) return;
-    cudaSetDevice(ctx->device);
-    free_workspace(ctx);
-    if (ctx->d_gnn) cudaFree(ctx->d_gnn);
-    if (ctx->d_tc) cudaFree(ctx->d_tc);
-    if (ctx->d_net) cudaFree(ctx->d_net);
-    if (ctx->d_maps) cudaFree(ctx->d_maps);
-    if (ctx->d_layers) cudaFree(ctx->d_layers);
-    if (ctx->d_hidden_off) cudaFree(ctx->d_hidden_off);
-    if (ctx->d_random_order) cudaFree(ctx->d_random_order);
-    if (ctx->d_ptrs) cudaFree(ctx->d_ptrs);
-    if (ctx->d_nan) cudaFree(ctx->d_nan);
-    for (PropPlan* p : ctx->plan_fwd) prop_plan_free(p);
-    for (PropPlan* p : ctx->plan_bwd) prop_plan_free(p);
-    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-    if (ctx->res_best) cudaFree(ctx->res_best);
-    if (ctx->res_idx) cudaFree(ctx->res_idx);
-    for (int i = 0; i < 2; ++i) { if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]); if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]); }
-    for (auto& p : ctx->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
-    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
-    delete ctx;
-}
-
-int gnnb_set_gnn_weights(gnnb_ctx* ctx, const float* const* tensors, const int64_t* numels, int n_tensors, int T, int p) {
-    if (!ctx || !tensors || !numels) return fail(ctx, GNNB_ERR_INVALID, "null argument");
-    if (p != P) return fail(ctx, GNNB_ERR_UNSUPPORTED, "embedding size p must be 64");
-    if (T < 1) return fail(ctx, GNNB_ERR_INVALID, "T must be >= 1");
-    if (n_tensors != 2 * N_LIN) return fail(ctx, GNNB_ERR_INVALID, "expected 52 tensors (weight, bias of 26 linears)");
-    for (int l = 0; l < N_LIN; ++l) {
-        if (numels[2 * l] != (int64_t)lin_in(l) * lin_out(l) || numels[2 * l + 1] != lin_out(l))
-            return fail(ctx, GNNB_ERR_INVALID, "tensor " + std::to_string(2 * l) + " has the wrong number of elements");
-    }
-    CU(cudaSetDevice(ctx->device));
+// upload the 52 host tensors in every form the kernels read: transposed fp32, composed linears, tensor-core planes, and
+// the nn.Linear-layout master copy of the fine-tuning path (its gradient and Adam buffers are kept when they exist)
+int upload_gnn(gnnb_ctx* ctx, const float* const* tensors, int T) {
     // fp32 blob: transposed weights + biases
     std::vector<size_t> o_w(N_LIN), o_b(N_LIN);
     size_t total = 0;
@@ -530,8 +474,127 @@ int gnnb_set_gnn_weights(gnnb_ctx* ctx, const float* const* tensors, const int64
         ctx->gp.tcx_b[i] = ctx->d_gnn + o_cb + (size_t)i * P;
     }
     ctx->gp.T = T;
+    // master copy (nn.Linear layout, state_dict order); the gradient / Adam quarters survive a re-upload
+    if (!ctx->d_train) {
+        size_t np = 0;
+        for (int l = 0; l < N_LIN; ++l) {
+            ctx->po_w[l] = np; np += align4((size_t)lin_in(l) * lin_out(l));
+            ctx->po_b[l] = np; np += align4(lin_out(l));
+        }
+        ctx->n_params = (int64_t)np;
+        CU(cudaMalloc(&ctx->d_train, 4 * np * sizeof(float)));
+        CU(cudaMemset(ctx->d_train, 0, 4 * np * sizeof(float)));
+        ctx->adam_steps = 0;
+    }
+    {
+        std::vector<float> master((size_t)ctx->n_params, 0.f);
+        for (int l = 0; l < N_LIN; ++l) {
+            memcpy(&master[ctx->po_w[l]], tensors[2 * l], sizeof(float) * lin_in(l) * lin_out(l));
+            memcpy(&master[ctx->po_b[l]], tensors[2 * l + 1], sizeof(float) * lin_out(l));
+        }
+        CU(cudaMemcpy(ctx->d_train, master.data(), master.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
     ctx->have_gnn = true;
     return GNNB_OK;
+}
+
+TrainParams train_params(gnnb_ctx* ctx) {
+    TrainParams tp;
+    float* grad = ctx->d_train + ctx->n_params;
+    for (int l = 0; l < N_LIN; ++l) {
+        tp.w[l] = ctx->d_train + ctx->po_w[l]; tp.b[l] = ctx->d_train + ctx->po_b[l];
+        tp.dw[l] = grad + ctx->po_w[l]; tp.db[l] = grad + ctx->po_b[l];
+    }
+    return tp;
+}
+
+// copy one quarter of the training block (0 = parameters, 1 = gradients) to 52 host tensors in state_dict order
+int download_quarter(gnnb_ctx* ctx, int quarter, float* const* tensors, const int64_t* numels, int n_tensors) {
+    if (!ctx || !tensors || !numels) return fail(ctx, GNNB_ERR_INVALID, "null argument");
+    if (!ctx->have_gnn) return fail(ctx, GNNB_ERR_STATE, "gnnb_set_gnn_weights must be called first");
+    if (n_tensors != 2 * N_LIN) return fail(ctx, GNNB_ERR_INVALID, "expected 52 tensors (weight, bias of 26 linears)");
+    for (int l = 0; l < N_LIN; ++l)
+        if (numels[2 * l] != (int64_t)lin_in(l) * lin_out(l) || numels[2 * l + 1] != lin_out(l))
+            return fail(ctx, GNNB_ERR_INVALID, "tensor " + std::to_string(2 * l) + " has the wrong number of elements");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    std::vector<float> host((size_t)ctx->n_params);
+    CU(cudaMemcpy(host.data(), ctx->d_train + (size_t)quarter * ctx->n_params, host.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int l = 0; l < N_LIN; ++l) {
+        memcpy(tensors[2 * l], &host[ctx->po_w[l]], sizeof(float) * lin_in(l) * lin_out(l));
+        memcpy(tensors[2 * l + 1], &host[ctx->po_b[l]], sizeof(float) * lin_out(l));
+    }
+    return GNNB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gnnb_abi_version(void) { return 1; }
+
+int gnnb_create(gnnb_ctx** out, int device) {
+    if (!out) return GNNB_ERR_INVALID;
+    *out = nullptr;
+    gnnb_ctx* ctx = new gnnb_ctx();
+    ctx->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { delete ctx; return GNNB_ERR_CUDA; }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { delete ctx; return GNNB_ERR_CUDA; }
+    if (prop.major != 10) {   // sm_100a cubins only; there is no other code path
+        fprintf(stderr, "libgnnb: device %d is sm_%d%d; this library is built for sm_100a (B200) only\n", device, prop.major, prop.minor);
+        delete ctx;
+        return GNNB_ERR_UNSUPPORTED;
+    }
+    if (cudaMalloc(&ctx->d_nan, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(ctx->d_nan, 0, sizeof(unsigned long long)) != cudaSuccess ||
+        simt_init() != 0 || prop_init(64 * 1024) != 0 || tc_init() != 0 || prop_tc_init() != 0 || train_init() != 0) {
+        fprintf(stderr, "libgnnb: initialisation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+        delete ctx;
+        return GNNB_ERR_CUDA;
+    }
+    *out = ctx;
+    return GNNB_OK;
+}
+
+void gnnb_destroy(gnnb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    free_workspace(ctx);
+    if (ctx->d_gnn) cudaFree(ctx->d_gnn);
+    if (ctx->d_tc) cudaFree(ctx->d_tc);
+    if (ctx->d_train) cudaFree(ctx->d_train);
+    if (ctx->d_net) cudaFree(ctx->d_net);
+    if (ctx->d_maps) cudaFree(ctx->d_maps);
+    if (ctx->d_layers) cudaFree(ctx->d_layers);
+    if (ctx->d_hidden_off) cudaFree(ctx->d_hidden_off);
+    if (ctx->d_random_order) cudaFree(ctx->d_random_order);
+    if (ctx->d_ptrs) cudaFree(ctx->d_ptrs);
+    if (ctx->d_nan) cudaFree(ctx->d_nan);
+    for (PropPlan* p : ctx->plan_fwd) prop_plan_free(p);
+    for (PropPlan* p : ctx->plan_bwd) prop_plan_free(p);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->res_best) cudaFree(ctx->res_best);
+    if (ctx->res_idx) cudaFree(ctx->res_idx);
+    for (int i = 0; i < 2; ++i) { if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]); if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]); }
+    for (auto& p : ctx->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    delete ctx;
+}
+
+int gnnb_set_gnn_weights(gnnb_ctx* ctx, const float* const* tensors, const int64_t* numels, int n_tensors, int T, int p) {
+    if (!ctx || !tensors || !numels) return fail(ctx, GNNB_ERR_INVALID, "null argument");
+    if (p != P) return fail(ctx, GNNB_ERR_UNSUPPORTED, "embedding size p must be 64");
+    if (T < 1) return fail(ctx, GNNB_ERR_INVALID, "T must be >= 1");
+    if (n_tensors != 2 * N_LIN) return fail(ctx, GNNB_ERR_INVALID, "expected 52 tensors (weight, bias of 26 linears)");
+    for (int l = 0; l < N_LIN; ++l) {
+        if (numels[2 * l] != (int64_t)lin_in(l) * lin_out(l) || numels[2 * l + 1] != lin_out(l))
+            return fail(ctx, GNNB_ERR_INVALID, "tensor " + std::to_string(2 * l) + " has the wrong number of elements");
+    }
+    CU(cudaSetDevice(ctx->device));
+    return upload_gnn(ctx, tensors, T);
 }
 
 int gnnb_set_network(gnnb_ctx* ctx, const gnnb_layer_desc* layers, int n_layers, int c0, int h0, int w0) {
@@ -856,6 +919,101 @@ int gnnb_babsr(gnnb_ctx* ctx, const gnnb_frontier* in, int32_t sparsest_layer, f
     if (e != cudaSuccess) return fail(ctx, GNNB_ERR_CUDA, std::string("gnnb_babsr: ") + cudaGetErrorString(e));
     if (rc != 0) return fail(ctx, GNNB_ERR_UNSUPPORTED, "a layer is too large for the BaBSR kernel's shared-memory buffers");
     CU(cudaGetLastError());
+    return GNNB_OK;
+}
+
+int gnnb_score_grad(gnnb_ctx* ctx, const gnnb_frontier* in, int32_t n_terms, const int32_t* term_domain, const int32_t* term_index,
+                    const float* term_coeff, float* term_scores, void* stream) {
+    if (!ctx || !in || !term_domain || !term_index || !term_coeff) return fail(ctx, GNNB_ERR_INVALID, "null argument");
+    if (!ctx->have_gnn || !ctx->have_net) return fail(ctx, GNNB_ERR_STATE, "gnnb_set_gnn_weights and gnnb_set_network must be called first");
+    if (in->B < 1 || n_terms < 1) return fail(ctx, GNNB_ERR_INVALID, "need at least one subdomain and one term");
+    if (!in->lb || !in->ub || !in->dual || !in->prim_pre || !in->prim_post || !in->prim_out || !in->primal_input || !in->wp || !in->bp)
+        return fail(ctx, GNNB_ERR_INVALID, "null frontier field");
+    for (int i = 0; i < n_terms; ++i)
+        if (term_domain[i] < 0 || term_domain[i] >= in->B || term_index[i] < 0 || term_index[i] >= ctx->n_hidden)
+            return fail(ctx, GNNB_ERR_INVALID, "term " + std::to_string(i) + " is out of range");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int L = (int)ctx->layers.size(), B = in->B;
+    const std::vector<int>& n = ctx->n;
+    const bool host = in->mem == GNNB_MEM_HOST;
+    float* tmp = nullptr;
+    TrainInputs ti;
+    ti.lb.resize(L + 2); ti.ub.resize(L + 2); ti.dual.resize(L); ti.pre.resize(L); ti.post.resize(L);
+    size_t total = 0;
+    auto take = [&](size_t elems) { size_t o = total; total += align4(elems); return o; };
+    if (host) {
+        for (int k = 0; k <= L + 1; ++k) total += 2 * align4((size_t)B * n[k]);
+        for (int k = 0; k < L; ++k) total += align4((size_t)B * n[k + 1] * 3) + 2 * align4((size_t)B * n[k + 1]);
+        total += 2 * align4(B) + align4((size_t)B * n[0]) + align4((size_t)B * n[L]);
+        CU(cudaMalloc(&tmp, total * sizeof(float)));
+        total = 0;
+    }
+    auto stage = [&](const float* src, size_t elems) -> const float* {
+        if (!host) return src;
+        float* dst = tmp + take(elems);
+        cudaMemcpyAsync(dst, src, elems * sizeof(float), cudaMemcpyHostToDevice, st);
+        return dst;
+    };
+    bool bad = false;
+    for (int k = 0; k <= L + 1; ++k) {
+        if (!in->lb[k] || !in->ub[k]) { bad = true; break; }
+        ti.lb[k] = stage(in->lb[k], (size_t)B * n[k]);
+        ti.ub[k] = stage(in->ub[k], (size_t)B * n[k]);
+    }
+    for (int k = 0; k < L && !bad; ++k) {
+        if (!in->dual[k] || !in->prim_pre[k] || !in->prim_post[k]) { bad = true; break; }
+        ti.dual[k] = stage(in->dual[k], (size_t)B * n[k + 1] * 3);
+        ti.pre[k] = stage(in->prim_pre[k], (size_t)B * n[k + 1]);
+        ti.post[k] = stage(in->prim_post[k], (size_t)B * n[k + 1]);
+    }
+    if (bad) { if (tmp) { cudaStreamSynchronize(st); cudaFree(tmp); } return fail(ctx, GNNB_ERR_INVALID, "null bound / dual / primal array"); }
+    ti.pout = stage(in->prim_out, B); ti.pin = stage(in->primal_input, (size_t)B * n[0]);
+    ti.wp = stage(in->wp, (size_t)B * n[L]); ti.bp = stage(in->bp, B);
+    // optimizer.zero_grad() (graph_score_online.py:73), then loss.backward()
+    cudaMemsetAsync(ctx->d_train + ctx->n_params, 0, (size_t)ctx->n_params * sizeof(float), st);
+    std::string err;
+    const int rc = train_backward(ctx->gp, train_params(ctx), ctx->layers, ctx->n, ctx->hidden_off, ti, B, n_terms, term_domain, term_index,
+                                  term_coeff, term_scores, st, &ctx->launches, &err);
+    if (tmp) { cudaStreamSynchronize(st); cudaFree(tmp); }
+    if (rc != GNNB_OK) return fail(ctx, rc, err);
+    return GNNB_OK;
+}
+
+int gnnb_get_gradients(gnnb_ctx* ctx, float* const* tensors, const int64_t* numels, int n_tensors) {
+    return download_quarter(ctx, 1, tensors, numels, n_tensors);
+}
+
+int gnnb_get_gnn_weights(gnnb_ctx* ctx, float* const* tensors, const int64_t* numels, int n_tensors) {
+    return download_quarter(ctx, 0, tensors, numels, n_tensors);
+}
+
+int gnnb_adam_step(gnnb_ctx* ctx, float lr, float beta1, float beta2, float eps, float weight_decay, void* stream) {
+    if (!ctx) return GNNB_ERR_INVALID;
+    if (!ctx->have_gnn) return fail(ctx, GNNB_ERR_STATE, "gnnb_set_gnn_weights must be called first");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t np = (size_t)ctx->n_params;
+    ++ctx->adam_steps;
+    adam_step(ctx->d_train, ctx->d_train + np, ctx->d_train + 2 * np, ctx->d_train + 3 * np, ctx->n_params, lr, beta1, beta2, eps,
+              weight_decay, ctx->adam_steps, st, &ctx->launches);
+    // every derived form of the parameters (transposed, composed, tensor-core planes) is rebuilt from the new master copy
+    std::vector<float> host(np);
+    CU(cudaMemcpyAsync(host.data(), ctx->d_train, np * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    std::vector<const float*> tensors(2 * N_LIN);
+    for (int l = 0; l < N_LIN; ++l) { tensors[2 * l] = &host[ctx->po_w[l]]; tensors[2 * l + 1] = &host[ctx->po_b[l]]; }
+    CU(cudaDeviceSynchronize());          // no kernel may still read the parameter blobs that upload_gnn replaces
+    return upload_gnn(ctx, tensors.data(), ctx->gp.T);
+}
+
+int gnnb_adam_reset(gnnb_ctx* ctx) {
+    if (!ctx) return GNNB_ERR_INVALID;
+    ctx->adam_steps = 0;
+    if (ctx->d_train) {
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaMemset(ctx->d_train + 2 * (size_t)ctx->n_params, 0, 2 * (size_t)ctx->n_params * sizeof(float)));
+    }
     return GNNB_OK;
 }
 

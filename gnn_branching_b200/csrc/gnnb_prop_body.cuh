@@ -70,7 +70,7 @@ __device__ __forceinline__ void prop_body(const PropPlanDev& plan, const uint16_
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
     const uint32_t w_ring = smem_u32(base), b_ring = w_ring + W_STAGES * W_STAGE_BYTES;
     PropTail* tail = reinterpret_cast<PropTail*>(base + W_STAGES * W_STAGE_BYTES + B_STAGES * B_STAGE_BYTES);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform((int)(threadIdx.x >> 5)), lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int i = 0; i < W_STAGES; ++i) { mbar_init(smem_u32(&tail->w_full[i]), 1); mbar_init(smem_u32(&tail->w_empty[i]), 1); }
         for (int i = 0; i < B_STAGES; ++i) { mbar_init(smem_u32(&tail->b_full[i]), PD * 32); mbar_init(smem_u32(&tail->b_empty[i]), 1); }
@@ -104,68 +104,72 @@ __device__ __forceinline__ void prop_body(const PropPlanDev& plan, const uint16_
             }
         }
     } else if (warp == 1) {
-        // ---- MMA issue ----
-        if (lane == 0) {
-            // D fp32, A fp16 K-major, B fp16 MN-major (bit 16), M = 128, N = 256
-            const uint32_t idesc = (1u << 4) | (1u << 16) | ((uint32_t)(PD * 64 >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
-            uint32_t ws = 0, wph = 0, bs = 0, bph = 0, it = 0;
+        // ---- MMA issue: the whole warp walks the loop (uniform control and operands), one elected lane issues ----
+        // D fp32, A fp16 K-major, B fp16 MN-major (bit 16), M = 128, N = 256
+        const uint32_t idesc = (1u << 4) | (1u << 16) | ((uint32_t)(PD * 64 >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+        uint32_t ws = 0, wph = 0, bs = 0, bph = 0, it = 0;
 #ifdef GNNB_TRACE
-            long long t_acc = 0, t_w = 0, t_b = 0, t_all = clock64(), t0_;
-            int n_chunks = 0;
+        long long t_acc = 0, t_w = 0, t_b = 0, t_all = clock64(), t0_;
+        int n_chunks = 0;
 #define PTR_BEGIN() t0_ = clock64()
 #define PTR_END(x) x += clock64() - t0_
 #else
 #define PTR_BEGIN()
 #define PTR_END(x)
 #endif
-            for (int64_t item = rank; item < nitems; item += nranks, ++it) {
-                const int tile = (int)(item % plan.ntiles);
-                const int ch0 = plan.tile_chunk0[tile], ch1 = plan.tile_chunk0[tile + 1];
-                const uint32_t a = it & 1u, aph = (it >> 1) & 1u;
+        for (int64_t item = rank; item < nitems; item += nranks, ++it) {
+            const int tile = (int)(item % plan.ntiles);
+            const int ch0 = uniform(plan.tile_chunk0[tile]), ch1 = uniform(plan.tile_chunk0[tile + 1]);
+            const uint32_t a = it & 1u, aph = (it >> 1) & 1u;
+            PTR_BEGIN();
+            mbar_wait(smem_u32(&tail->acc_empty[a]), aph ^ 1u);      // the epilogue has drained this accumulator
+            PTR_END(t_acc);
+            tc_fence_after();
+            const uint32_t d = (tmem_base & 0x0000FFFFu) + a * 256u;
+            uint32_t accum = 0;
+            for (int ch = ch0; ch < ch1; ++ch) {
                 PTR_BEGIN();
-                mbar_wait(smem_u32(&tail->acc_empty[a]), aph ^ 1u);      // the epilogue has drained this accumulator
-                PTR_END(t_acc);
-                tc_fence_after();
-                const uint32_t d = (tmem_base & 0x0000FFFFu) + a * 256u;
-                uint32_t first = 1;
-                for (int ch = ch0; ch < ch1; ++ch) {
+                mbar_wait(smem_u32(&tail->w_full[ws]), wph);
+                PTR_END(t_w);
+                const int nks = uniform(plan.ksteps[ch]);
+                const uint32_t wa = w_ring + ws * W_STAGE_BYTES;
+                const uint64_t a_hi = make_desc(wa), a_lo = make_desc(wa + APLANE);
+                for (int h = 0; 2 * h < nks; ++h) {
                     PTR_BEGIN();
-                    mbar_wait(smem_u32(&tail->w_full[ws]), wph);
-                    PTR_END(t_w);
-                    const int nks = plan.ksteps[ch];
-                    const uint32_t wa = w_ring + ws * W_STAGE_BYTES;
-                    for (int h = 0; 2 * h < nks; ++h) {
-                        PTR_BEGIN();
-                        mbar_wait(smem_u32(&tail->b_full[bs]), bph);
-                        PTR_END(t_b);
-                        tc_fence_after();
-                        const uint32_t ba = b_ring + bs * B_STAGE_BYTES;
-                        const int kc = (nks - 2 * h) < 2 ? (nks - 2 * h) : 2;
-#pragma unroll
-                        for (int pass = 0; pass < 3; ++pass) {
-                            const uint64_t ad = make_desc(pass == 1 ? wa + APLANE : wa);
-                            const uint64_t bd = make_desc_mn(pass == 2 ? ba + B_PLANE_BYTES : ba, B_DOM_BYTES);
-                            for (int kk = 0; kk < kc; ++kk) {
-                                umma(d, ad + 2 * (2 * h + kk), bd + 128 * kk, idesc, first ? 0u : 1u);
-                                first = 0;
-                            }
-                        }
+                    mbar_wait(smem_u32(&tail->b_full[bs]), bph);
+                    PTR_END(t_b);
+                    tc_fence_after();
+                    const uint32_t ba = b_ring + bs * B_STAGE_BYTES;
+                    const uint64_t b_hi = make_desc_mn(ba, B_DOM_BYTES), b_lo = make_desc_mn(ba + B_PLANE_BYTES, B_DOM_BYTES);
+                    const bool two = nks - 2 * h >= 2;             // K steps of this half chunk that hold data: 1 or 2
+                    const uint64_t ah0 = a_hi + (uint64_t)(4 * h), al0 = a_lo + (uint64_t)(4 * h);
+                    if (elect_one()) {
+                        umma(d, ah0, b_hi, idesc, accum);                      // Wh Mh
+                        if (two) umma(d, ah0 + 2, b_hi + 128, idesc, 1u);
+                        umma(d, al0, b_hi, idesc, 1u);                         // Wl Mh
+                        if (two) umma(d, al0 + 2, b_hi + 128, idesc, 1u);
+                        umma(d, ah0, b_lo, idesc, 1u);                         // Wh Ml
+                        if (two) umma(d, ah0 + 2, b_lo + 128, idesc, 1u);
                         umma_commit(smem_u32(&tail->b_empty[bs]));
-                        if (++bs == B_STAGES) { bs = 0; bph ^= 1u; }
                     }
-                    umma_commit(smem_u32(&tail->w_empty[ws]));
-                    if (++ws == W_STAGES) { ws = 0; wph ^= 1u; }
+                    __syncwarp();
+                    accum = 1u;
+                    if (++bs == B_STAGES) { bs = 0; bph ^= 1u; }
                 }
-                umma_commit(smem_u32(&tail->acc_full[a]));
-#ifdef GNNB_TRACE
-                n_chunks += ch1 - ch0;
-#endif
+                if (elect_one()) umma_commit(smem_u32(&tail->w_empty[ws]));
+                __syncwarp();
+                if (++ws == W_STAGES) { ws = 0; wph ^= 1u; }
             }
+            if (elect_one()) umma_commit(smem_u32(&tail->acc_full[a]));
+            __syncwarp();
 #ifdef GNNB_TRACE
-            if (rank == 1) printf("TRACE prop-mma: items %u chunks %d total %lld | wait acc_empty %lld, w_full %lld, b_full %lld\n", it, n_chunks,
-                                  clock64() - t_all, t_acc, t_w, t_b);
+            n_chunks += ch1 - ch0;
 #endif
         }
+#ifdef GNNB_TRACE
+        if (rank == 1 && lane == 0) printf("TRACE prop-mma: items %u chunks %d total %lld | wait acc_empty %lld, w_full %lld, b_full %lld\n", it, n_chunks,
+                                           clock64() - t_all, t_acc, t_w, t_b);
+#endif
     } else if (warp < EPI_WARP0) {
         // ---- gather: warp g copies the rows of subdomain d0 + g ----
         const int g = warp - GATHER_WARP0;

@@ -63,6 +63,7 @@ struct WG {
     uint32_t tmem0;             // lane 0, first column of this warpgroup (MMA operand / accumulator addresses)
     int t;                      // thread index within the warpgroup = row of the tile this thread owns
     int wg;
+    bool lead_warp;             // first warp of the warpgroup (warp-uniform): it issues the warpgroup's MMAs, one elected lane
 };
 
 __device__ __forceinline__ void wg_barrier(const WG& c) { named_bar(1 + c.wg, 128); }
@@ -107,10 +108,13 @@ __device__ __forceinline__ void gemm_finish(WG& c) {
 // D[dcol, dcol + N) = A(tmem) W^T
 __device__ __forceinline__ void gemm_ts_start(WG& c, uint32_t b_hi, uint32_t b_lo, uint32_t N, uint32_t dcol, bool accumulate = false) {
     gemm_sync(c);
-    if (c.t == 0) {
+    if (c.lead_warp) {          // uniform operands + one elected lane: 12 back-to-back UTCHMMA (gnnb_umma.cuh, elect_one)
         tc_fence_after();
-        issue_ts(c, b_hi, b_lo, N, dcol, accumulate);
-        umma_commit(c.mbar_mma);
+        if (elect_one()) {
+            issue_ts(c, b_hi, b_lo, N, dcol, accumulate);
+            umma_commit(c.mbar_mma);
+        }
+        __syncwarp();
     }
 }
 __device__ __forceinline__ void gemm_ts(WG& c, uint32_t b_hi, uint32_t b_lo, uint32_t N, uint32_t dcol, bool accumulate = false) {
@@ -120,11 +124,14 @@ __device__ __forceinline__ void gemm_ts(WG& c, uint32_t b_hi, uint32_t b_lo, uin
 // D[dcol, dcol + N) = A(landing buffer, after its TMA has completed) W^T
 __device__ __forceinline__ void gemm_ss(WG& c, uint32_t b_hi, uint32_t b_lo, uint32_t N, uint32_t dcol, bool accumulate = false) {
     gemm_sync(c);
-    if (c.t == 0) {
+    if (c.lead_warp) {
         tc_fence_after();
         mbar_wait(c.mbar_tma, c.ph_tma);
-        issue_ss(c, b_hi, b_lo, N, dcol, accumulate);
-        umma_commit(c.mbar_mma);
+        if (elect_one()) {
+            issue_ss(c, b_hi, b_lo, N, dcol, accumulate);
+            umma_commit(c.mbar_mma);
+        }
+        __syncwarp();
     }
     c.ph_tma ^= 1u;
     gemm_finish(c);
@@ -320,14 +327,15 @@ __device__ __forceinline__ CtaSetup cta_setup(unsigned char* smem_raw, uint32_t 
 }
 __device__ __forceinline__ WG make_wg(const CtaSetup& s, uint32_t wbytes) {
     WG c;
-    c.wg = threadIdx.x >> 7;
+    c.wg = uniform((int)(threadIdx.x >> 7));
+    c.lead_warp = (uniform((int)(threadIdx.x >> 5)) & 3) == 0;
     c.t = threadIdx.x & 127;
     c.land = s.w + wbytes + (uint32_t)c.wg * ABUF;
     c.mbar_mma = smem_u32(&s.tail->mbar[1 + 2 * c.wg]);
     c.mbar_tma = smem_u32(&s.tail->mbar[2 + 2 * c.wg]);
     c.ph_mma = 0;
     c.ph_tma = 0;
-    c.tmem0 = (s.tmem_base & 0x0000FFFFu) + (uint32_t)c.wg * WG_COLS;
+    c.tmem0 = ((uint32_t)uniform((int)s.tmem_base) & 0x0000FFFFu) + (uint32_t)c.wg * WG_COLS;
     c.tmem = s.tmem_base + ((uint32_t)((c.t >> 5) * 32) << 16) + (uint32_t)c.wg * WG_COLS;
     return c;
 }
@@ -688,12 +696,16 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_input_update(GnnParams g, c
         first_layer_to_a<2>(c, feat, tl.w_small[0], tl.bias[5]);
         // D = Wi relu(inp_b(.)) + Wn nb: both products into the one accumulator, one commit
         gemm_sync(c);
-        if (c.t == 0) {
+        if (c.lead_warp) {
             tc_fence_after();
-            issue_ts(c, W + INU_WI, W + INU_WI + WPLANE, 64, DCOL, false);
+            if (elect_one()) issue_ts(c, W + INU_WI, W + INU_WI + WPLANE, 64, DCOL, false);
+            __syncwarp();
             mbar_wait(c.mbar_tma, c.ph_tma);
-            issue_ss(c, W + INU_WN, W + INU_WN + WPLANE, 64, DCOL, true);
-            umma_commit(c.mbar_mma);
+            if (elect_one()) {
+                issue_ss(c, W + INU_WN, W + INU_WN + WPLANE, 64, DCOL, true);
+                umma_commit(c.mbar_mma);
+            }
+            __syncwarp();
         }
         c.ph_tma ^= 1u;
         gemm_finish(c);

@@ -197,6 +197,19 @@ __device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
 }
 
+// Issuing tcgen05.mma / tcgen05.commit from warp-uniform code: every lane of the warp walks the (uniform) loop and one
+// elected lane executes the instruction.  With operands that are uniform by data flow the compiler keeps descriptors in
+// uniform registers and emits one UTCHMMA per MMA; a `if (lane == 0)` region instead makes every MMA a ~30-instruction
+// sequence (per-thread 64-bit descriptor arithmetic, 5 R2UR, an ELECT / BRA.U.ANY loop), i.e. 150-220 cycles of issue per
+// MMA against 32-128 cycles of tensor time (scripts/micro/mma_rate.cu).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\nselp.u32 %0, 1, 0, q;\n}" : "=r"(p));
+    return p != 0;
+}
+// a value every lane holds identically, in a form the compiler can prove uniform (loaded data, threadIdx-derived warp ids)
+__device__ __forceinline__ int uniform(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (bits [4,6) = 1), A/B fp16 (format 0), both K-major, M = 128
 __device__ __forceinline__ uint32_t make_idesc(uint32_t N) {
     return (1u << 4) | ((N >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);

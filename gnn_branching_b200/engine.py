@@ -20,6 +20,9 @@ STATE_DICT_KEYS = ([f'EmbedUpdates.update.{n}.{s}' for n in UPDATE_LINEARS for s
                    + [f'ComputeFinalScore.{n}.{s}' for n in SCORE_LINEARS for s in ('weight', 'bias')])
 
 _MATH = {'tc': _lib.MATH_TC_FP16X3, 'simt': _lib.MATH_SIMT_FP32}
+# nn.Linear shapes of the 26 linears, same order (graph_conv.py:36-74, 431-432)
+_LIN_IN = [3, 64, 2, 64, 128, 64, 7, 64, 128, 64, 128, 64, 4, 128, 64, 7, 64, 64, 192, 64, 128, 64, 128, 64, 64, 64]
+_LIN_OUT = [64] * 25 + [1]
 
 
 class Scorer:
@@ -209,6 +212,77 @@ class Scorer:
                                          C.c_void_p(stream)))
         del k1, k2
         return dec, cout, kind, scores
+
+    # ---- online fine-tuning (graph_score_online.py:62-77) ----
+    def _frontier_desc(self, fr: Frontier):
+        """gnnb_frontier of ``fr`` (the fields the GNN reads) + the objects that keep its arrays alive."""
+        net, B, L = self.net, fr.B, self.net.L
+        sizes = [net.n0] + net.hidden_sizes + [1]
+        lb = [self._as_f32(fr.lb[k], (B, sizes[k])) for k in range(L + 2)]
+        ub = [self._as_f32(fr.ub[k], (B, sizes[k])) for k in range(L + 2)]
+        dual = [self._as_f32(fr.dual[k], (B, sizes[k + 1], 3)) for k in range(L)]
+        pre = [self._as_f32(fr.prim_pre[k], (B, sizes[k + 1])) for k in range(L)]
+        post = [self._as_f32(fr.prim_post[k], (B, sizes[k + 1])) for k in range(L)]
+        flat = [self._as_f32(fr.prim_out, (B,)), self._as_f32(fr.primal_input, (B, net.n0)),
+                self._as_f32(fr.Wp, (B, sizes[L])), self._as_f32(fr.bp, (B,)), self._as_f32(fr.mask, (B, net.n_hidden))]
+        d = _lib.FrontierDesc()
+        d.B, d.mem = B, (_lib.MEM_HOST if fr.device.type == 'cpu' else _lib.MEM_DEVICE)
+        keep = [lb, ub, dual, pre, post, flat]
+        for name, arrs in (('lb', lb), ('ub', ub), ('dual', dual), ('prim_pre', pre), ('prim_post', post)):
+            p, k = _lib.fptr_array(arrs)
+            setattr(d, name, p)
+            keep.append(k)
+        d.prim_out, d.primal_input, d.wp, d.bp, d.mask = map(_lib.fptr, flat)
+        return d, keep
+
+    def score_grad(self, fr: Frontier, terms) -> torch.Tensor:
+        """Back-propagate ``sum_i coeff_i * score[domain_i][flat_index_i]`` into the gradient buffers of the context
+        (zeroed first, like ``optimizer.zero_grad(); loss.backward()``).  ``terms``: iterable of (domain, flat index,
+        coeff).  Returns the terms' scores (fp32, CPU)."""
+        if self.net is None:
+            raise RuntimeError('set_network first')
+        terms = list(terms)
+        nt = len(terms)
+        dom = (C.c_int32 * nt)(*[int(t[0]) for t in terms])
+        idx = (C.c_int32 * nt)(*[int(t[1]) for t in terms])
+        coeff = (C.c_float * nt)(*[float(t[2]) for t in terms])
+        out = (C.c_float * nt)()
+        d, keep = self._frontier_desc(fr)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            self._ok(self.lib.gnnb_score_grad(self.h, C.byref(d), nt, dom, idx, coeff, out, C.c_void_p(stream)))
+        del keep
+        return torch.tensor(list(out), dtype=torch.float32)
+
+    def _download(self, fn) -> Dict[str, torch.Tensor]:
+        shapes = []
+        for l in range(len(_LIN_IN)):
+            shapes += [(_LIN_OUT[l], _LIN_IN[l]), (_LIN_OUT[l],)]
+        host = [torch.empty(s, dtype=torch.float32) for s in shapes]
+        ptrs, keep = _lib.fptr_array(host)
+        numels = (C.c_int64 * len(host))(*[t.numel() for t in host])
+        self._ok(fn(self.h, ptrs, numels, len(host)))
+        del keep
+        return dict(zip(STATE_DICT_KEYS, host))
+
+    def gradients(self) -> Dict[str, torch.Tensor]:
+        """The reference's ``p.grad`` after ``loss.backward()``, keyed like the state_dict (CPU tensors)."""
+        return self._download(self.lib.gnnb_get_gradients)
+
+    def weights(self) -> Dict[str, torch.Tensor]:
+        """The parameters the context currently scores with (the reference's ``model.state_dict()``)."""
+        return self._download(self.lib.gnnb_get_gnn_weights)
+
+    def adam_step(self, lr: float, weight_decay: float = 0.0, betas=(0.9, 0.999), eps: float = 1e-8):
+        """One ``torch.optim.Adam`` step on the device with the gradients of the last ``score_grad``."""
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            self._ok(self.lib.gnnb_adam_step(self.h, float(lr), float(betas[0]), float(betas[1]), float(eps),
+                                             float(weight_decay), C.c_void_p(stream)))
+        self._gnn_key = None
+
+    def adam_reset(self):
+        self._ok(self.lib.gnnb_adam_reset(self.h))
 
     def check(self) -> None:
         """Synchronise and raise if a NaN appeared in an embedding (the reference drops into pdb there)."""

@@ -87,6 +87,15 @@ class GraphNet(nn.Module):
         self._scorer.set_gnn(self.state_dict(), self.T, self.p, key=key)
         return self._scorer
 
+    def adopt_weights(self, sc: Scorer) -> None:
+        """After a device-side optimiser step: copy the context's parameters into this module (so ``state_dict()`` and
+        checkpoints follow the fine-tuning) without triggering a re-upload."""
+        new = sc.weights()
+        with torch.no_grad():
+            for k, q in self.state_dict().items():
+                q.copy_(new[k])
+        sc._gnn_key = tuple((q.data_ptr(), q._version) for q in self.parameters())
+
     def score_frontier(self, fr: Frontier, return_scores: bool = True):
         """Batched entry (addition to the reference API): (best_score [B], best_idx [B], scores [B, sum n_k])."""
         sc = self.scorer(fr.device.index if fr.device.type == 'cuda' else None)

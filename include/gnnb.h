@@ -141,6 +141,34 @@ int gnnb_babsr(gnnb_ctx* ctx, const gnnb_frontier* in, int32_t sparsest_layer, f
                const int32_t* random_order, const int32_t* icp_counter_in, int32_t* decision, int32_t* icp_counter_out,
                int32_t* kind, float* scores, void* stream);
 
+/* ---- online fine-tuning (the reference's `--bab_online` variant) ------------------------------------------------------
+ * Replaces loss.backward() + optimizer.step() of GraphChoice.online_learning (graphnet/graph_score_online.py:62-77, called
+ * from plnn/relu_conv_online.py:198-211): the reference differentiates `gnn_score - kw_score + improvement` through
+ * GraphNet.forward with PyTorch autograd and applies torch.optim.Adam(lr, weight_decay) (graph_score_online.py:15).
+ *
+ * gnnb_score_grad: zeroes the gradient buffers (optimizer.zero_grad, :73), runs an exact-fp32 forward pass of the
+ * subdomains of `in` that keeps the activations, and back-propagates
+ *     loss = sum_i term_coeff[i] * score[term_domain[i]][term_index[i]]
+ * (term_index = flat index into the concatenated hidden layers) into d loss / d parameter for all 52 tensors.  The
+ * reference's loss is the two terms (+1, argmax index), (-1, index of the KW decision); `improvement` is a constant and
+ * has no gradient.  term_* are HOST arrays; term_scores [n_terms] (HOST, may be NULL) receives the terms' fp32 scores.
+ * Frontier pointers live in `in->mem`; `in->mask` is not read.  Returns after the gradients are complete. */
+int gnnb_score_grad(gnnb_ctx* ctx, const gnnb_frontier* in, int32_t n_terms, const int32_t* term_domain,
+                    const int32_t* term_index, const float* term_coeff, float* term_scores, void* stream);
+
+/* Copy the gradients of the last gnnb_score_grad (the reference's `p.grad`) / the current parameters (the reference's
+ * `model.state_dict()`) into 52 HOST tensors in the order of gnnb_set_gnn_weights. */
+int gnnb_get_gradients(gnnb_ctx* ctx, float* const* tensors, const int64_t* numels, int n_tensors);
+int gnnb_get_gnn_weights(gnnb_ctx* ctx, float* const* tensors, const int64_t* numels, int n_tensors);
+
+/* One torch.optim.Adam step (amsgrad off) on all 52 tensors with the gradients of the last gnnb_score_grad:
+ * g += weight_decay * p; m = lerp(m, g, 1 - beta1); v = beta2 v + (1 - beta2) g^2;
+ * p -= lr / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps).  The moments and the step count t live in the context
+ * (they survive gnnb_set_gnn_weights, as the reference's optimizer survives load_state_dict) until gnnb_adam_reset.
+ * Every packed form of the parameters used by gnnb_score is rebuilt before the call returns. */
+int gnnb_adam_step(gnnb_ctx* ctx, float lr, float beta1, float beta2, float eps, float weight_decay, void* stream);
+int gnnb_adam_reset(gnnb_ctx* ctx);
+
 /* Synchronise `stream` and report sticky device-side errors of earlier gnnb_score calls
  * (GNNB_ERR_NAN with the NaN count in *nan_count, may be NULL).  Clears the flag. */
 int gnnb_check(gnnb_ctx* ctx, void* stream, int64_t* nan_count);

@@ -45,8 +45,9 @@ def compute_ratio(l: torch.Tensor, u: torch.Tensor):
 
 
 class _Params:
-    def __init__(self, sd: Dict[str, torch.Tensor]):
-        self.sd = {k: v.detach().float().cpu() for k, v in sd.items()}
+    def __init__(self, sd: Dict[str, torch.Tensor], keep_graph: bool = False):
+        # keep_graph: use the tensors as given (fp32 CPU leaves that require grad) so that autograd reaches them
+        self.sd = dict(sd) if keep_graph else {k: v.detach().float().cpu() for k, v in sd.items()}
 
     def lin(self, name: str, x: torch.Tensor) -> torch.Tensor:
         pre = 'ComputeFinalScore.' if name in SCORE_LINEARS else 'EmbedUpdates.update.'
@@ -88,7 +89,7 @@ def _bias_per_node(a) -> torch.Tensor:
 
 
 def gnn_forward(state_dict: Dict[str, torch.Tensor], fr, T: int = 2, p: int = 64,
-                stages: Optional[dict] = None, dead_input_update: bool = False):
+                stages: Optional[dict] = None, dead_input_update: bool = False, keep_graph: bool = False):
     """Batched restatement of GraphNet.forward (graph_conv.py:479-483).
 
     ``fr`` is a ``gnn_branching_b200.frontier.Frontier`` on the CPU.  Returns
@@ -96,7 +97,7 @@ def gnn_forward(state_dict: Dict[str, torch.Tensor], fr, T: int = 2, p: int = 64
     mask; the reference evaluates the head only on rows with mask != 0, graph_conv.py:445-450).
     ``stages`` (optional dict) receives named intermediates for kernel-by-kernel debugging.
     """
-    P = _Params(state_dict)
+    P = _Params(state_dict, keep_graph)
     net = fr.net
     L, B = net.L, fr.B
     rec = (lambda k, v: stages.__setitem__(k, v.clone())) if stages is not None else (lambda k, v: None)

@@ -73,3 +73,8 @@ def load_case(arch: str, name: str):
     ref = {k[len(name) + 1:]: torch.from_numpy(v.copy()) for k, v in z.items()
            if k.startswith(name + '_scores') or k.startswith(name + '_decisions')}
     return fr, ref
+
+
+def load_online():
+    """tests/golden/online_base.npz (make_golden_online.py): the reference's online fine-tuning steps on the base case."""
+    return _npz('online_base.npz')

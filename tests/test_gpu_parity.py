@@ -341,3 +341,136 @@ def test_babsr_frontier_matches_oracle(arch, B):
         off += n
     d1, c1 = choose_node_conv([t[0] for t in lbs1], [t[0] for t in ubs1], init_mask, modules, pre_relu, 0, order, 0)
     assert d1 == dec[3].tolist() and c1 == int(cout[3])
+
+
+# ---- online fine-tuning -----------------------------------------------------------------------
+# per tensor: max|g - g_ref| <= GRAD_RTOL * max|g_ref| + GRAD_ATOL.  Both sides are fp32 sums over thousands of rows in
+# different orders; the absolute floor (5 ulp of the O(1) scores being differentiated) covers tensors at the end of the
+# longest chains (inp_f on the 5-layer net: |g| ~ 1e-4 after cancellation, observed difference 1.3e-7)
+GRAD_RTOL, GRAD_ATOL = 1e-4, 3e-7
+
+
+def _bab_mask(fr, b):
+    out, off = [], 0
+    for n in fr.net.hidden_sizes:
+        m = fr.mask[b, off:off + n]
+        out.append(torch.where(m != 0, torch.full_like(m, -1), torch.ones_like(m)).int())
+        off += n
+    return out
+
+
+def _flat(fr, dec):
+    return sum(fr.net.hidden_sizes[:dec[0]]) + dec[1]
+
+
+def _assert_grads(got, ref, rtol=GRAD_RTOL):
+    for k, r in ref.items():
+        err, scale = float((got[k] - r).abs().max()), float(r.abs().max())
+        assert err <= rtol * scale + GRAD_ATOL, (k, err, scale)
+
+
+@pytest.mark.parametrize('weights', ['random', 'shipped'])
+def test_score_gradients_match_reference(weights):
+    """gnnb_score_grad against the reference's own p.grad after loss.backward() (graph_score_online.py:74-75)."""
+    from golden_io import load_online
+    z = load_online()
+    fr, _ = load_case('base', 'fr')
+    one = fr.slice(0, 1).to('cuda')
+    model = _model(weights, 'tc')
+    sc = model.scorer(0)
+    sc.set_network(fr.net, key=fr.net.key)
+    gnn, kw = _flat(fr, z[f'{weights}_dec0'].tolist()), _flat(fr, z[f'{weights}_kw0'].tolist())
+    vals = sc.score_grad(one, [(0, gnn, 1.0), (0, kw, -1.0)])
+    assert abs(float(vals[0]) - float(z[f'{weights}_gnn_score0'])) <= 1e-5 * abs(float(z[f'{weights}_gnn_score0']))
+    assert abs(float(vals[1]) - float(z[f'{weights}_kw_score0'])) <= 1e-5 * max(1.0, abs(float(z[f'{weights}_kw_score0'])))
+    ref = {k: torch.from_numpy(z[f'{weights}_grad0_{k}']) for k in sc.gradients()}
+    _assert_grads(sc.gradients(), ref)
+
+
+@pytest.mark.parametrize('arch,B', [('deep', 2), ('wide', 2), ('base', 3)])
+def test_score_gradients_match_oracle_batched(arch, B):
+    """Several subdomains and terms at once, other network shapes (3x3 stride-1 convs, 5 hidden layers), host buffers.
+
+    Tolerance 2e-2 per tensor: a gradient through ~30 ReLU layers is a discontinuous function of the fp32 rounding of the
+    forward pass — a pre-activation within one ulp of zero gives a different ReLU mask in two equally valid fp32
+    evaluations, and one flipped unit moves the gradients behind it by 1e-3 .. 1e-2 of their size.  scripts/grad_diag.py
+    measures it against an fp64 autograd oracle: where no unit flips the CUDA path is within 1e-6..3e-6 of fp64 (like
+    torch's own fp32 autograd); on deep x 1 torch-fp32 itself is 6.8e-3 away from fp64; on deep x 2 the CUDA path is 5e-3
+    away and torch-fp32 2e-6.  The tight bound (1e-4) is held by test_score_gradients_match_reference."""
+    from oracle import online_oracle as OO
+    fr, _ = load_case(arch, 'fr')
+    fr = fr.slice(0, B)
+    sd = load_gnn('random')
+    terms = []
+    for b in range(B):
+        cand = fr.mask[b].nonzero().view(-1).tolist()
+        terms += [(b, cand[0], 1.0), (b, cand[len(cand) // 2], -0.5 - b), (b, cand[-1], 0.25)]
+    ref, vals_ref = OO.score_grads(sd, fr, terms)
+    model = _model('random', 'tc')
+    sc = model.scorer(0)
+    sc.set_network(fr.net, key=fr.net.key)
+    for dev in ('cuda', 'cpu'):
+        vals = sc.score_grad(fr.to(dev), terms)
+        assert float((vals - vals_ref).abs().max()) <= 1e-5 * float(vals_ref.abs().max())
+        _assert_grads(sc.gradients(), ref, rtol=2e-2)
+
+
+def test_online_learning_matches_reference(tmp_path):
+    """graph_score_online.GraphChoice used exactly like plnn/relu_conv_online.py uses the reference: decision, online_learning
+    against a KW decision, twice; decisions equal the reference's, the parameters after two Adam steps agree to a small
+    fraction of one step (Adam's step is lr * m / (sqrt(v) + eps): O(lr) per element whatever the gradient's size)."""
+    from golden_io import load_online
+    from gnn_branching_b200.graph_score_online import GraphChoice as OnlineChoice
+    z = load_online()
+    lr, wd = float(z['lr']), float(z['wd'])
+    fr, _ = load_case('base', 'fr')
+    ckpt = os.path.join(tmp_path, 'gnn.pt')
+    torch.save(load_gnn('random'), ckpt)
+    gc = OnlineChoice(_bab_mask(fr, 0), ckpt, lr=lr, wd=wd)
+    for step in (0, 1):
+        one = fr.slice(step, step + 1)
+        lbs, ubs, duals, primals, pin, layers, _ = one.to_reference_args()
+        dec = gc.decision(lbs, ubs, duals, pin, [q.tolist() for q in primals], layers, _bab_mask(fr, step))
+        assert dec == z[f'random_dec{step}'].tolist()
+        assert abs(gc.gnn_score - float(z[f'random_gnn_score{step}'])) <= 1e-4 * abs(float(z[f'random_gnn_score{step}']))
+        loss = gc.online_learning(z[f'random_kw{step}'].tolist(), 1)
+        ref_loss = float(z[f'random_gnn_score{step}']) - float(z[f'random_kw_score{step}']) + 1.0
+        assert abs(loss - ref_loss) <= 1e-4 * abs(ref_loss)
+        gc.del_score()
+    sd = gc.model.state_dict()
+    worst = 0.0
+    for k, v in sd.items():
+        ref = torch.from_numpy(z[f'random_sd2_{k}'])
+        worst = max(worst, float((v.cpu() - ref).abs().max()))
+    assert worst <= 0.05 * lr, worst
+    # the module and the device context hold the same parameters, and scoring uses them
+    dev = gc.model.scorer(0).weights()
+    for k, v in sd.items():
+        assert torch.equal(v.cpu(), dev[k])
+    s_new, _ = O.gnn_forward({k: v.cpu() for k, v in sd.items()}, fr)
+    _, idx, scores = gc.model.score_frontier(fr.to('cuda'))
+    rep = O.parity_report(scores.cpu(), s_new, fr.mask, idx.cpu(), rtol=1e-4)
+    assert rep['ok'], rep
+
+
+def test_adam_step_matches_torch():
+    """gnnb_adam_step against torch.optim.Adam on identical gradients, three steps (bias correction, weight decay)."""
+    fr, _ = load_case('base', 'fr')
+    one = fr.slice(0, 1).to('cuda')
+    model = _model('random', 'tc')
+    sc = model.scorer(0)
+    sc.set_network(fr.net, key=fr.net.key)
+    params = {k: torch.nn.Parameter(v.clone()) for k, v in load_gnn('random').items()}
+    opt = torch.optim.Adam(list(params.values()), lr=3e-4, weight_decay=1e-3)
+    cand = fr.mask[0].nonzero().view(-1).tolist()
+    for step in range(3):
+        sc.score_grad(one, [(0, cand[step], 1.0), (0, cand[-1 - step], -1.0)])
+        g = sc.gradients()
+        for k, q in params.items():
+            q.grad = g[k].clone()
+        opt.step()
+        sc.adam_step(3e-4, weight_decay=1e-3)
+        w = sc.weights()
+        for k, q in params.items():
+            assert float((w[k] - q.detach()).abs().max()) <= 2e-7 + 1e-3 * 3e-4, k
+            q.data.copy_(w[k])          # keep the two trajectories on the same parameters

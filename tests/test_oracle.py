@@ -100,3 +100,34 @@ def test_babsr_oracle_matches_reference(arch, case):
         d, c, _ = BO.babsr_decide(sc, ic, fr.mask, fr.net.hidden_sizes, [cnt] * fr.B, order, 0, thr)
         assert d.tolist() == z[f'{case}_{name}_decisions'].tolist()
         assert c.tolist() == z[f'{case}_{name}_counters'].tolist()
+
+
+# ---- online fine-tuning -----------------------------------------------------------------------
+def test_online_oracle_matches_reference():
+    """oracle/online_oracle.py against the reference's own online_learning (tests/golden/make_golden_online.py): same
+    decisions, same loss terms, gradients of the first step to 2e-5 of each tensor's largest entry (autograd over a
+    batched restatement re-associates sums), parameters after two Adam steps to 2 % of one step (lr)."""
+    from golden_io import load_online
+    from oracle.online_oracle import OnlineOracle, kw_flat_index
+    z = load_online()
+    fr, _ = load_case('base', 'fr')
+    lr, wd = float(z['lr']), float(z['wd'])
+    for w in ('random', 'shipped'):
+        oo = OnlineOracle(load_gnn(w), lr=lr, wd=wd)
+        for step in ((0, 1) if w == 'random' else (0,)):
+            one = fr.slice(step, step + 1)
+            flat, dec = oo.decision(one)
+            assert dec == z[f'{w}_dec{step}'].tolist()
+            kw = z[f'{w}_kw{step}'].tolist()
+            grads, loss = oo.online_learning(one, flat, kw, 1.0)
+            ref_loss = float(z[f'{w}_gnn_score{step}']) - float(z[f'{w}_kw_score{step}']) + 1.0
+            assert abs(loss - ref_loss) <= 1e-5 * max(1.0, abs(ref_loss))
+            assert kw_flat_index(one.mask[0], fr.net.hidden_sizes, kw) == sum(fr.net.hidden_sizes[:kw[0]]) + kw[1]
+            if step == 0:
+                for k, g in grads.items():
+                    ref = torch.from_numpy(z[f'{w}_grad0_{k}'])
+                    assert float((g - ref).abs().max()) <= 2e-5 * float(ref.abs().max()) + 1e-12, k
+        if w == 'random':
+            for k, v in oo.state_dict().items():
+                ref = torch.from_numpy(z[f'{w}_sd2_{k}'])
+                assert float((v - ref).abs().max()) <= 0.02 * lr, k
