@@ -42,6 +42,7 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-babsr', action='store_true')
+    ap.add_argument('--no-online', action='store_true')
     ap.add_argument('--opt', action='append', default=[], help='library option key=value (e.g. fuse=0, prop_share=40)')
     return ap.parse_args()
 
@@ -59,15 +60,54 @@ def load_weights(which):
 
 # ---------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 50 ms during the timed region."""
+    """SM clock / throttle reasons of one GPU sampled DURING the timed region: NVML (nvidia_ml_py) polled every 5 ms from a
+    thread — a 50 ms timed region still gets ~10 samples — with `nvidia-smi -lms 50` as the fallback."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
+    BITS = {'sw_power_cap': 0x4, 'hw_slowdown': 0x8, 'sw_thermal_slowdown': 0x20, 'hw_thermal_slowdown': 0x40}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nv, self.h, self.stop = index, [], None, None, None, False
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(('GPU-' + uuid) if not uuid.startswith('GPU-') else uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                except Exception:
+                    pw = 0.0
+                self.samples.append((sm, mask, pw))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def __enter__(self):
+        self.samples = []
+        if self.nv is not None:
+            self.stop = False
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return self
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
                                           '-lms', '50', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
@@ -82,12 +122,24 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(',')])
 
     def __exit__(self, *a):
-        if self.proc:
+        if self.nv is not None:
+            self.stop = True
+            self.t.join(timeout=2)
+        elif self.proc:
             time.sleep(0.25)
             self.proc.terminate()
             self.t.join(timeout=2)
 
+    def count(self):
+        return len(self.samples) if self.nv is not None else len(self.rows)
+
     def summary(self):
+        if self.nv is not None and self.samples:
+            sm = [q[0] for q in self.samples]
+            reasons = sorted(n for n, bit in self.BITS.items() if any(q[1] & bit for q in self.samples))
+            return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': self.max_mhz, 'reasons': reasons,
+                    'power_w_max': max(q[2] for q in self.samples), 'samples': len(sm),
+                    'source': 'nvml polled every 5 ms over the timed region (+ identical untimed steps until 8 samples)'}
         sm, mx, reasons, power = [], [], set(), []
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         for r in self.rows:
@@ -101,7 +153,7 @@ class ClockSampler:
         if not sm:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
         return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': max(mx), 'reasons': sorted(reasons),
-                'power_w_max': max(power), 'samples': len(sm)}
+                'power_w_max': max(power), 'samples': len(sm), 'source': 'nvidia-smi -lms 50'}
 
 
 def cpu_baseline(workload, weights, threads=None, reps=3):
@@ -274,8 +326,6 @@ def main():
     scorer.check()
     barrier()
     launches0 = scorer.launches
-    scorer.set_option('profile', 1)
-    scorer.profile_reset()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         barrier()
@@ -284,9 +334,26 @@ def main():
             step(i)
         ev1.record()
         barrier()
+        launches = scorer.launches - launches0
+        # a short timed region (K x 5 ms) may end before NVML has answered a handful of times: keep the identical load
+        # running, untimed, until there are enough samples of the clocks under it
+        extra = 0
+        while clk.count() < 8 and extra < 400:
+            step(extra)
+            extra += 1
+            if extra % 4 == 0:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
     scorer.check()
     ms = ev0.elapsed_time(ev1)
-    launches = scorer.launches - launches0
+    # per-kernel-class durations: a second pass of K identical steps with CUDA events around every launch (on the launching
+    # stream).  The events serialise consecutive launches (no programmatic overlap of a kernel's prologue with its
+    # predecessor's tail), so the headline `value` above is measured without them
+    scorer.set_option('profile', 1)
+    scorer.profile_reset()
+    for i in range(K):
+        step(i)
+    scorer.check()
     prof = scorer.profile_read()
     scorer.set_option('profile', 0)
     if world > 1:
@@ -334,6 +401,8 @@ def main():
         'B200_PROFILING.md fallback 6.65 TB/s / 1.4 PF sustained (of fallback)'
     roofline = kernel_rooflines(net, fronts[0], prof, K * B, T=2, peak_tf=peak_tf, peak_gbs=peak_gbs)
     roofline['peak_source'] = peak_src
+    roofline['timing'] = (f'CUDA events around every launch on the launching stream, over a second pass of the same {K} steps '
+                          '(the events serialise launches, so `value` is timed without them)')
     flops_dom = net.flops_per_domain()
     roofline['whole_path'] = {'flop_per_subdomain': flops_dom, 'achieved_tflops': value / world * flops_dom / 1e12,
                               'frac_of_bf16_peak': value / world * flops_dom / 1e12 / peak_tf,
@@ -377,6 +446,40 @@ def main():
             babsr['cpu_baseline'] = {'value': 3 * 64 / (time.perf_counter() - t0), 'unit': UNIT, 'kind': 'port', 'cores': os.cpu_count(),
                                      'sample': '64 subdomains x 3 passes, oracle/babsr_oracle.py (batched scores, per-domain decision rule)'}
 
+    # ---- one online fine-tuning step (secondary line): gradient of gnn_score - kw_score + Adam, B = 1 ----
+    online = None
+    if world == 1 and not args.no_online:
+        one = fronts[0].slice(0, 1)
+        cand = one.mask[0].nonzero().view(-1).tolist()
+        if len(cand) >= 2:
+            terms = [(0, cand[0], 1.0), (0, cand[-1], -1.0)]
+            saved = scorer.weights()
+            for _ in range(2):
+                scorer.score_grad(one, terms)
+                scorer.adam_step(1e-4, weight_decay=1e-4)
+            torch.cuda.synchronize()
+            l0, t0 = scorer.launches, time.perf_counter()
+            for _ in range(10):
+                scorer.score_grad(one, terms)
+                scorer.adam_step(1e-4, weight_decay=1e-4)
+            torch.cuda.synchronize()
+            oms = (time.perf_counter() - t0) / 10 * 1e3
+            online = {'ms_per_step': oms, 'steps_per_s': 1e3 / oms, 'launches_per_step': (scorer.launches - l0) // 10,
+                      'note': 'GraphChoice.online_learning (graph_score_online.py:62-77): fp32 forward with tape + backward + Adam + '
+                              'repack of the tensor-core weight planes, one subdomain, wall clock around the C-ABI calls'}
+            scorer.adam_reset()
+            scorer.set_gnn(saved, key=None)       # the headline numbers above were measured before; restore anyway
+            if not args.no_cpu_baseline:
+                from oracle.online_oracle import OnlineOracle
+                oo = OnlineOracle(load_weights(args.weights))
+                oc = one.cpu().contiguous()
+                oo.online_learning(oc, cand[0], [0, 0], 1.0)
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    oo.online_learning(oc, cand[0], [0, 0], 1.0)
+                online['cpu_baseline'] = {'ms_per_step': (time.perf_counter() - t0) / 3 * 1e3, 'kind': 'port', 'cores': os.cpu_count(),
+                                          'sample': '3 steps, oracle/online_oracle.py (torch autograd + torch.optim.Adam on the host cores)'}
+
     cb = None
     if not args.no_cpu_baseline and world == 1:
         cb, _ = cpu_baseline(args.workload, args.weights)
@@ -390,7 +493,7 @@ def main():
                        'l2': 'two alternating frontiers; inputs + per-chunk workspace exceed the 126 MB L2',
                        'sharding': f'{world} ranks x {B} subdomains, winners all-gathered (8 B/subdomain)'},
             'clocks': clk.summary(), 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cb,
-            'babsr': babsr}
+            'babsr': babsr, 'online': online}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

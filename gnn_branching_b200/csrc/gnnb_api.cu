@@ -48,6 +48,8 @@ struct gnnb_ctx {
     int64_t n_params = 0;
     size_t po_w[N_LIN] = {0}, po_b[N_LIN] = {0};
     int adam_steps = 0;
+    float* train_ws = nullptr;      // activation tape + gradient temporaries of gnnb_score_grad (grow-only)
+    size_t train_ws_cap = 0;
     // verified network
     bool have_net = false;
     float* d_net = nullptr;
@@ -457,12 +459,12 @@ int upload_gnn(gnnb_ctx* ctx, const float* const* tensors, int T) {
     total += cb.size();
     blob.resize(total, 0.f);
     memcpy(&blob[o_cb], cb.data(), cb.size() * sizeof(float));
-    if (ctx->d_gnn) cudaFree(ctx->d_gnn);
-    if (ctx->d_tc) cudaFree(ctx->d_tc);
-    ctx->d_gnn = nullptr; ctx->d_tc = nullptr;
-    CU(cudaMalloc(&ctx->d_gnn, total * sizeof(float)));
+    // the blobs have fixed sizes (p = 64): allocated once, overwritten by later uploads (an Adam step re-uploads every time);
+    // no kernel of an earlier call may still be reading them
+    CU(cudaDeviceSynchronize());
+    if (!ctx->d_gnn) CU(cudaMalloc(&ctx->d_gnn, total * sizeof(float)));
+    if (!ctx->d_tc) CU(cudaMalloc(&ctx->d_tc, tcblob.size() * sizeof(uint16_t)));
     CU(cudaMemcpy(ctx->d_gnn, blob.data(), total * sizeof(float), cudaMemcpyHostToDevice));
-    CU(cudaMalloc(&ctx->d_tc, tcblob.size() * sizeof(uint16_t)));
     CU(cudaMemcpy(ctx->d_tc, tcblob.data(), tcblob.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     for (int l = 0; l < N_LIN; ++l) {
         ctx->gp.wt[l] = ctx->d_gnn + o_w[l];
@@ -566,6 +568,7 @@ void gnnb_destroy(gnnb_ctx* ctx) {
     if (ctx->d_gnn) cudaFree(ctx->d_gnn);
     if (ctx->d_tc) cudaFree(ctx->d_tc);
     if (ctx->d_train) cudaFree(ctx->d_train);
+    if (ctx->train_ws) cudaFree(ctx->train_ws);
     if (ctx->d_net) cudaFree(ctx->d_net);
     if (ctx->d_maps) cudaFree(ctx->d_maps);
     if (ctx->d_layers) cudaFree(ctx->d_layers);
@@ -974,7 +977,7 @@ int gnnb_score_grad(gnnb_ctx* ctx, const gnnb_frontier* in, int32_t n_terms, con
     cudaMemsetAsync(ctx->d_train + ctx->n_params, 0, (size_t)ctx->n_params * sizeof(float), st);
     std::string err;
     const int rc = train_backward(ctx->gp, train_params(ctx), ctx->layers, ctx->n, ctx->hidden_off, ti, B, n_terms, term_domain, term_index,
-                                  term_coeff, term_scores, st, &ctx->launches, &err);
+                                  term_coeff, term_scores, &ctx->train_ws, &ctx->train_ws_cap, st, &ctx->launches, &err);
     if (tmp) { cudaStreamSynchronize(st); cudaFree(tmp); }
     if (rc != GNNB_OK) return fail(ctx, rc, err);
     return GNNB_OK;
@@ -1003,7 +1006,6 @@ int gnnb_adam_step(gnnb_ctx* ctx, float lr, float beta1, float beta2, float eps,
     CU(cudaStreamSynchronize(st));
     std::vector<const float*> tensors(2 * N_LIN);
     for (int l = 0; l < N_LIN; ++l) { tensors[2 * l] = &host[ctx->po_w[l]]; tensors[2 * l + 1] = &host[ctx->po_b[l]]; }
-    CU(cudaDeviceSynchronize());          // no kernel may still read the parameter blobs that upload_gnn replaces
     return upload_gnn(ctx, tensors.data(), ctx->gp.T);
 }
 

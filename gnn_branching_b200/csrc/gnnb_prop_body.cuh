@@ -66,7 +66,7 @@ constexpr size_t PROP_SMEM = 1024 + W_STAGES * W_STAGE_BYTES + B_STAGES * B_STAG
 // wait for exactly this item (gnnb_tc.cu, k_tc_layer); `consumed` (may be null) is their progress counter.  All threads of the block must call it (block-wide barriers).
 __device__ __forceinline__ void prop_body(const PropPlanDev& plan, const uint16_t* __restrict__ mu_img, uint16_t* __restrict__ nb_img,
                                           int Bc, unsigned char* smem_raw, int rank, int nranks, int32_t* flags, int32_t epoch,
-                                          const int32_t* consumed = nullptr, int32_t consumed_base = 0, int lead = 0) {
+                                          const int32_t* consumed = nullptr, int32_t consumed_base = 0, int lead = 0, bool pdl = false) {
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
     const uint32_t w_ring = smem_u32(base), b_ring = w_ring + W_STAGES * W_STAGE_BYTES;
     PropTail* tail = reinterpret_cast<PropTail*>(base + W_STAGES * W_STAGE_BYTES + B_STAGES * B_STAGE_BYTES);
@@ -83,6 +83,7 @@ __device__ __forceinline__ void prop_body(const PropPlanDev& plan, const uint16_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tail->tmem_slot;
+    if (pdl) { pdl_trigger(); pdl_wait(); }     // prologue done; the mu images are the predecessor's output
 
     const int ngroups = (Bc + PD - 1) / PD;
     const int64_t nitems = (int64_t)plan.ntiles * ngroups;       // item = group * ntiles + tile

@@ -31,7 +31,7 @@ namespace {
 __global__ void __launch_bounds__(prop::PROP_THREADS, 1) k_tc_prop(PropPlanDev plan, const uint16_t* __restrict__ mu_img,
                                                                    uint16_t* __restrict__ nb_img, int Bc) {
     extern __shared__ unsigned char smem_raw[];
-    prop::prop_body(plan, mu_img, nb_img, Bc, smem_raw, (int)blockIdx.x, (int)gridDim.x, nullptr, 0);
+    prop::prop_body(plan, mu_img, nb_img, Bc, smem_raw, (int)blockIdx.x, (int)gridDim.x, nullptr, 0, nullptr, 0, 0, true);
 }
 
 // ---- host-side plan construction ------------------------------------------------------------------------
@@ -236,8 +236,8 @@ double prop_plan_chunks_per_tile(const PropPlan* p) { return p->dev.ntiles > 0 ?
 void prop_tc_run(const PropPlan* plan, const float* mu_img, float* nb_img, int Bc, cudaStream_t st, int64_t* launches) {
     const int64_t nitems = (int64_t)plan->dev.ntiles * ((Bc + prop::PD - 1) / prop::PD);
     const int grid = (int)(nitems < 1 ? 1 : (nitems < 148 ? nitems : 148));
-    k_tc_prop<<<grid, prop::PROP_THREADS, prop::PROP_SMEM, st>>>(plan->dev, reinterpret_cast<const uint16_t*>(mu_img),
-                                                     reinterpret_cast<uint16_t*>(nb_img), Bc);
+    launch_pdl(k_tc_prop, grid, prop::PROP_THREADS, prop::PROP_SMEM, st, plan->dev, reinterpret_cast<const uint16_t*>(mu_img),
+               reinterpret_cast<uint16_t*>(nb_img), Bc);
     ++*launches;
 }
 

@@ -371,7 +371,7 @@ struct UpdArgs {
 // rank, rank + nranks, ...; warpgroup w updates the tile of subdomain 4 * group + w.  `flags` (may be null): the item's nb
 // images are produced by a propagation CTA of the same launch; wait for flags[item] == epoch before loading them.
 __device__ __forceinline__ void update_body(const UpdArgs& a, unsigned char* smem_raw, int rank, int nranks, const int32_t* flags,
-                                            int32_t epoch) {
+                                            int32_t epoch, bool pdl = false) {
     const GnnParams& g = a.g;
     const int backward = a.backward;
     const float* __restrict__ lb = a.lb;
@@ -394,6 +394,7 @@ __device__ __forceinline__ void update_body(const UpdArgs& a, unsigned char* sme
     const float bscore = g.bias[FSCORE][0];
     __syncthreads();
     mbar_wait(smem_u32(&tl.mbar[0]), 0);                      // weight planes have landed
+    if (pdl) { pdl_trigger(); pdl_wait(); }                   // everything above read constant parameters only
     WG c = make_wg(s, UPD_WBYTES);
     const uint32_t W = s.w;
     const int tiles_per_dom = map.nslots / TILE;
@@ -533,7 +534,7 @@ __device__ __forceinline__ void update_body(const UpdArgs& a, unsigned char* sme
 }
 
 __global__ void __launch_bounds__(128 * NWG, 1) k_tc_update(UpdArgs a) {
-    update_body(a, smem_dyn(), (int)blockIdx.x, (int)gridDim.x, nullptr, 0);
+    update_body(a, smem_dyn(), (int)blockIdx.x, (int)gridDim.x, nullptr, 0, true);
 }
 
 // Propagation and node update of one layer in ONE launch: CTAs [0, n_prop) run the gather-GEMM, the others the update
@@ -566,6 +567,7 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_relax(GnnParams g, NodeInpu
     copy_vec(tl.bias[5], g.bias[FC1], P); copy_vec(tl.vec, g.bias[BC1], P);
     __syncthreads();
     mbar_wait(smem_u32(&tl.mbar[0]), 0);
+    pdl_trigger(); pdl_wait();
     WG c = make_wg(s, RLX_WBYTES);
     const uint32_t W = s.w;
     // only the ambiguous rows have non-zero relaxation features: walk them in compacted order (slot = tile * 128 + t)
@@ -650,6 +652,7 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_input_embed(GnnParams g, co
     copy_vec(tl.bias[0], g.bias[INP_F_1], P); copy_vec(tl.bias[5], g.bias[INP_F], P); copy_vec(tl.w_small[0], g.wt[INP_F], 3 * P);
     __syncthreads();
     mbar_wait(smem_u32(&tl.mbar[0]), 0);
+    pdl_trigger(); pdl_wait();
     WG c = make_wg(s, EMB_WBYTES);
     const int64_t ntiles = (rows + TILE - 1) / TILE;
     for (int64_t tile = (int64_t)blockIdx.x * NWG + c.wg; tile < ntiles; tile += (int64_t)gridDim.x * NWG) {
@@ -683,6 +686,7 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_input_update(GnnParams g, c
     copy_vec(tl.bias[5], g.bias[INP_B], P); copy_vec(tl.w_small[0], g.wt[INP_B], 2 * P);
     __syncthreads();
     mbar_wait(smem_u32(&tl.mbar[0]), 0);
+    pdl_trigger(); pdl_wait();
     WG c = make_wg(s, INU_WBYTES);
     const uint32_t W = s.w;
     const int64_t ntiles = (rows + TILE - 1) / TILE;
@@ -831,7 +835,7 @@ int64_t tc_pack_weight(const float* w, int K, uint16_t* dst) {
 }
 
 void tc_relax(const GnnParams& g, const NodeInputs& in, float* relax_f, float* relax_b, cudaStream_t st, int64_t* launches) {
-    k_tc_relax<<<grid_for(in.rows), 128 * NWG, smem_bytes(RLX_WBYTES, false), st>>>(g, in, relax_f, relax_b);
+    launch_pdl(k_tc_relax, grid_for(in.rows), 128 * NWG, smem_bytes(RLX_WBYTES, false), st, g, in, relax_f, relax_b);
     ++*launches;
 }
 
@@ -853,7 +857,7 @@ void tc_update(const GnnParams& g, bool backward, const float* lb, const float* 
                unsigned long long* nan_count, cudaStream_t st, int64_t* launches) {
     const UpdArgs a = make_upd_args(g, backward, lb, ub, nb, relax, amb_base, mu_out, scores, map, score_stride, score_off, rows, nan_count);
     const int64_t nitems = (int64_t)(map.nslots / TILE) * ((a.Bc + NWG - 1) / NWG);
-    k_tc_update<<<(int)(nitems < 1 ? 1 : (nitems < 148 ? nitems : 148)), 128 * NWG, smem_bytes(UPD_WBYTES, true), st>>>(a);
+    launch_pdl(k_tc_update, (int)(nitems < 1 ? 1 : (nitems < 148 ? nitems : 148)), 128 * NWG, smem_bytes(UPD_WBYTES, true), st, a);
     ++*launches;
 }
 
@@ -880,14 +884,14 @@ void tc_layer(const GnnParams& g, const PropPlan* plan, const float* mu_in, bool
 
 void tc_input_embed(const GnnParams& g, const float* lb0, const float* x, const float* ub0, float* mu0, RowMap map, int64_t rows,
                     cudaStream_t st, int64_t* launches) {
-    k_tc_input_embed<<<grid_for(rows), 128 * NWG, smem_bytes(EMB_WBYTES, true), st>>>(g, lb0, x, ub0, reinterpret_cast<uint16_t*>(mu0), map, rows);
+    launch_pdl(k_tc_input_embed, grid_for(rows), 128 * NWG, smem_bytes(EMB_WBYTES, true), st, g, lb0, x, ub0, reinterpret_cast<uint16_t*>(mu0), map, rows);
     ++*launches;
 }
 
 void tc_input_update(const GnnParams& g, const float* lb0, const float* ub0, const float* nb, float* mu0, RowMap map, int64_t rows,
                      cudaStream_t st, int64_t* launches) {
-    k_tc_input_update<<<grid_for(rows), 128 * NWG, smem_bytes(INU_WBYTES, true), st>>>(
-        g, lb0, ub0, reinterpret_cast<const uint16_t*>(nb), reinterpret_cast<uint16_t*>(mu0), map, rows);
+    launch_pdl(k_tc_input_update, grid_for(rows), 128 * NWG, smem_bytes(INU_WBYTES, true), st,
+               g, lb0, ub0, reinterpret_cast<const uint16_t*>(nb), reinterpret_cast<uint16_t*>(mu0), map, (int64_t)rows);
     ++*launches;
 }
 

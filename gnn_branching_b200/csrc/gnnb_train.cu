@@ -426,8 +426,8 @@ int train_init() {
 
 int train_backward(const GnnParams& g, const TrainParams& tp, const std::vector<LayerDev>& layers, const std::vector<int>& n,
                    const std::vector<int>& hidden_off, const TrainInputs& in, int B, int n_terms, const int32_t* term_domain,
-                   const int32_t* term_index, const float* term_coeff, float* term_scores_host, cudaStream_t st,
-                   int64_t* launches, std::string* err) {
+                   const int32_t* term_index, const float* term_coeff, float* term_scores_host, float** arena, size_t* arena_cap,
+                   cudaStream_t st, int64_t* launches, std::string* err) {
     const int L = (int)layers.size(), T = g.T;
     auto R = [&](int k) { return (int64_t)B * n[k]; };
     int64_t rmax = 0;
@@ -463,9 +463,15 @@ int train_backward(const GnnParams& g, const TrainParams& tp, const std::vector<
     const size_t o_dout = take((int64_t)B * P), o_dsm = take(4 * (int64_t)B * P);
     const size_t o_bufA = take(rmax * P), o_bufB = take(rmax * P), o_bufC = take(rmax * P), o_bufD = take(rmax * P);
     const size_t o_tsc = take(n_terms), o_tco = take(n_terms), o_tptr = take(4 * (int64_t)n_terms + 8);
-    float* base = nullptr;
-    cudaError_t ce = cudaMalloc(&base, total * sizeof(float));
-    if (ce != cudaSuccess) { *err = std::string("training workspace: ") + cudaGetErrorString(ce); return GNNB_ERR_CUDA; }
+    cudaError_t ce = cudaSuccess;
+    if (*arena_cap < total) {           // the tape arena lives in the context and only grows
+        if (*arena) { cudaStreamSynchronize(st); cudaFree(*arena); }
+        *arena = nullptr; *arena_cap = 0;
+        ce = cudaMalloc(arena, total * sizeof(float));
+        if (ce != cudaSuccess) { *err = std::string("training workspace: ") + cudaGetErrorString(ce); return GNNB_ERR_CUDA; }
+        *arena_cap = total;
+    }
+    float* base = *arena;
     auto Pp = [&](size_t off) { return base + off; };
     Ctx c{g, tp, st, launches};
     unsigned long long nan_dummy = 0; (void)nan_dummy;
@@ -635,7 +641,6 @@ int train_backward(const GnnParams& g, const TrainParams& tp, const std::vector<
     }
     ce = cudaStreamSynchronize(st);
     if (ce == cudaSuccess) ce = cudaGetLastError();
-    cudaFree(base);
     if (ce != cudaSuccess) { *err = std::string("training pass: ") + cudaGetErrorString(ce); return GNNB_ERR_CUDA; }
     return GNNB_OK;
 }

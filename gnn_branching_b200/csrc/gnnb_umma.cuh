@@ -210,6 +210,30 @@ __device__ __forceinline__ bool elect_one() {
 // a value every lane holds identically, in a form the compiler can prove uniform (loaded data, threadIdx-derived warp ids)
 __device__ __forceinline__ int uniform(int v) { return __shfl_sync(0xffffffffu, v, 0); }
 
+// ---- programmatic dependent launch -----------------------------------------------------------------------------------
+// The big kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization (launch_pdl below): a kernel may be
+// scheduled while its predecessor in the stream is still draining, so its prologue (barrier init, tensor-memory allocation,
+// the bulk loads of the constant weight planes) overlaps the predecessor's tail.  pdl_wait() blocks until the predecessor
+// grid has completed and its writes are visible: NOTHING but constant parameters may be touched before it.  pdl_trigger()
+// lets the successor be scheduled as soon as every CTA of this (single-wave) grid has started.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (bits [4,6) = 1), A/B fp16 (format 0), both K-major, M = 128
 __device__ __forceinline__ uint32_t make_idesc(uint32_t N) {
     return (1u << 4) | ((N >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
