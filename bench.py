@@ -43,6 +43,7 @@ def parse():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-babsr', action='store_true')
     ap.add_argument('--no-online', action='store_true')
+    ap.add_argument('--no-queue', action='store_true')
     ap.add_argument('--opt', action='append', default=[], help='library option key=value (e.g. fuse=0, prop_share=40)')
     return ap.parse_args()
 
@@ -480,6 +481,32 @@ def main():
                 online['cpu_baseline'] = {'ms_per_step': (time.perf_counter() - t0) / 3 * 1e3, 'kind': 'port', 'cores': os.cpu_count(),
                                           'sample': '3 steps, oracle/online_oracle.py (torch autograd + torch.optim.Adam on the host cores)'}
 
+    # ---- the device-resident domain queue (secondary line): add / pick of whole frontiers ----
+    queue = None
+    if world == 1 and not args.no_queue:
+        from gnn_branching_b200 import DomainQueue, DomainBatch
+        f0 = fronts[0]
+        Bq = min(B, 1024)
+        g = torch.Generator(device='cpu').manual_seed(3)
+        batch = DomainBatch((torch.randn(Bq, generator=g) - 1.0).to(dev), torch.zeros(Bq, device=dev), [t[:Bq] for t in f0.lb],
+                            [t[:Bq] for t in f0.ub], (f0.mask[:Bq] * -1).to(torch.int8), torch.zeros(Bq, 2, dtype=torch.int32, device=dev))
+        q = DomainQueue(scorer, capacity=4 * Bq)
+        for _ in range(2):
+            q.add(batch); q.pick(Bq, float('inf'))
+        torch.cuda.synchronize()
+        reps, t_add, t_pick = 10, 0.0, 0.0
+        for _ in range(reps):
+            t0 = time.perf_counter(); q.add(batch); torch.cuda.synchronize(); t_add += time.perf_counter() - t0
+            t0 = time.perf_counter(); out = q.pick(Bq, float('inf')); torch.cuda.synchronize(); t_pick += time.perf_counter() - t0
+        row_bytes = 2 * 4 * (net.n0 + net.n_hidden + 1) + net.n_hidden + 16
+        queue = {'domains': Bq, 'add_domains_per_s': Bq * reps / t_add, 'pick_domains_per_s': Bq * reps / t_pick,
+                 'payload_bytes_per_domain': row_bytes,
+                 'add_gbs': 2 * row_bytes * Bq * reps / t_add / 1e9, 'pick_gbs': 2 * row_bytes * Bq * reps / t_pick / 1e9, 'peak_gbs': peak_gbs,
+                 'note': 'add_domain / pick_out of plnn/branch_and_bound.py:159-184 for a whole frontier per call: payload rows copied '
+                         'once into / out of the device pool (read + write counted), order kept by a radix sort of (key, slot) pairs; '
+                         'wall clock around the C-ABI calls, which read one count back per call'}
+        del q, out
+
     cb = None
     if not args.no_cpu_baseline and world == 1:
         cb, _ = cpu_baseline(args.workload, args.weights)
@@ -493,7 +520,7 @@ def main():
                        'l2': 'two alternating frontiers; inputs + per-chunk workspace exceed the 126 MB L2',
                        'sharding': f'{world} ranks x {B} subdomains, winners all-gathered (8 B/subdomain)'},
             'clocks': clk.summary(), 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cb,
-            'babsr': babsr, 'online': online}
+            'babsr': babsr, 'online': online, 'queue': queue}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -17,7 +17,8 @@ KERNEL_CLASSES = ['relax', 'update_fwd', 'update_bwd', 'update_bwd_score', 'inpu
 EXPORTS = ['gnnb_create', 'gnnb_destroy', 'gnnb_set_gnn_weights', 'gnnb_set_network', 'gnnb_set_option',
            'gnnb_get_option', 'gnnb_score', 'gnnb_check', 'gnnb_launch_count', 'gnnb_last_error',
            'gnnb_debug_snapshot', 'gnnb_abi_version', 'gnnb_profile_read', 'gnnb_profile_reset', 'gnnb_babsr',
-           'gnnb_score_grad', 'gnnb_get_gradients', 'gnnb_get_gnn_weights', 'gnnb_adam_step', 'gnnb_adam_reset']
+           'gnnb_score_grad', 'gnnb_get_gradients', 'gnnb_get_gnn_weights', 'gnnb_adam_step', 'gnnb_adam_reset',
+           'gnnb_queue_create', 'gnnb_queue_destroy', 'gnnb_queue_add', 'gnnb_queue_pick', 'gnnb_queue_prune', 'gnnb_queue_stats']
 
 _fp = C.POINTER(C.c_float)
 _fpp = C.POINTER(_fp)
@@ -34,6 +35,11 @@ class FrontierDesc(C.Structure):
     _fields_ = [('B', C.c_int32), ('mem', C.c_int32),
                 ('lb', _fpp), ('ub', _fpp), ('dual', _fpp), ('prim_pre', _fpp), ('prim_post', _fpp),
                 ('prim_out', _fp), ('primal_input', _fp), ('wp', _fp), ('bp', _fp), ('mask', _fp)]
+
+
+class DomainsDesc(C.Structure):
+    _fields_ = [('B', C.c_int32), ('mem', C.c_int32), ('lower_bound', _fp), ('upper_bound', _fp), ('lb', _fpp), ('ub', _fpp),
+                ('mask', C.POINTER(C.c_int8)), ('decision', C.POINTER(C.c_int32))]
 
 
 class GnnbError(RuntimeError):
@@ -72,6 +78,13 @@ def load() -> C.CDLL:
     lib.gnnb_get_gnn_weights.argtypes = [vp, _fpp, C.POINTER(C.c_int64), C.c_int]
     lib.gnnb_adam_step.argtypes = [vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp]
     lib.gnnb_adam_reset.argtypes = [vp]
+    lib.gnnb_queue_create.argtypes = [vp, C.c_int64, C.POINTER(vp)]
+    lib.gnnb_queue_destroy.argtypes = [vp]
+    lib.gnnb_queue_destroy.restype = None
+    lib.gnnb_queue_add.argtypes = [vp, C.POINTER(DomainsDesc), C.POINTER(C.c_uint8), _ip, vp]
+    lib.gnnb_queue_pick.argtypes = [vp, C.c_float, C.c_int32, C.POINTER(DomainsDesc), _ip, vp]
+    lib.gnnb_queue_prune.argtypes = [vp, C.c_float, vp]
+    lib.gnnb_queue_stats.argtypes = [vp, C.POINTER(C.c_int64), _fp, vp]
     lib.gnnb_check.argtypes = [vp, vp, C.POINTER(C.c_int64)]
     lib.gnnb_launch_count.argtypes = [vp]
     lib.gnnb_launch_count.restype = C.c_int64

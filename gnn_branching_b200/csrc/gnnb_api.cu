@@ -299,13 +299,25 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
     auto M = [&](int k) { return tc ? ctx->rowmap[k] : nomap; };
     const bool fused = tc && ctx->fuse;
 
+    // ambiguous rows of every hidden layer, compacted (three launches for the wave)
+    const bool amb_all = tc && L <= AMB_MAX_LAYERS;
+    if (amb_all) {
+        ProfScope ps(ctx, GNNB_K_RELAX, 0, st);
+        AmbLayers al{};
+        al.n = L;
+        for (int k = 1; k <= L; ++k) {
+            al.lb[k - 1] = in.lb[k]; al.ub[k - 1] = in.ub[k]; al.map[k - 1] = M(k); al.rows[k - 1] = R(k);
+            al.cnt[k - 1] = ctx->amb_cnt[k]; al.base[k - 1] = ctx->amb_base[k]; al.out_rows[k - 1] = ctx->amb_rows[k];
+        }
+        amb_compact_all(al, st, lc);
+    }
     // round-independent relaxation features of every hidden layer
     for (int k = 1; k <= L; ++k) {
         NodeInputs ni{in.lb[k], in.ub[k], in.dual[k - 1], in.pre[k - 1], in.post[k - 1], ctx->layers[k - 1].bias_node,
                       ctx->n[k], R(k), ctx->amb_rows[k], ctx->amb_base[k], M(k)};
         {
             ProfScope ps(ctx, GNNB_K_RELAX, (int64_t)Bc * ctx->n[k], st);
-            if (tc) amb_compact(in.lb[k], in.ub[k], M(k), ni.rows, ctx->amb_cnt[k], ctx->amb_base[k], ctx->amb_rows[k], st, lc);
+            if (tc && !amb_all) amb_compact(in.lb[k], in.ub[k], M(k), ni.rows, ctx->amb_cnt[k], ctx->amb_base[k], ctx->amb_rows[k], st, lc);
             if (tc) tc_relax(g, ni, ctx->relax_f[k], ctx->relax_b[k], st, lc);
             else simt_relax(g, ni, ctx->relax_f[k], ctx->relax_b[k], st, lc);
         }
@@ -1015,6 +1027,148 @@ int gnnb_adam_reset(gnnb_ctx* ctx) {
     if (ctx->d_train) {
         CU(cudaSetDevice(ctx->device));
         CU(cudaMemset(ctx->d_train + 2 * (size_t)ctx->n_params, 0, 2 * (size_t)ctx->n_params * sizeof(float)));
+    }
+    return GNNB_OK;
+}
+
+struct gnnb_queue {
+    gnnb_ctx* ctx;
+    DomainQueue* q;
+};
+
+int gnnb_queue_create(gnnb_ctx* ctx, int64_t capacity, gnnb_queue** out) {
+    if (!ctx || !out || capacity < 1) return fail(ctx, GNNB_ERR_INVALID, "bad argument");
+    *out = nullptr;
+    if (!ctx->have_net) return fail(ctx, GNNB_ERR_STATE, "gnnb_set_network must be called first");
+    if (capacity > 0x7fffffff) return fail(ctx, GNNB_ERR_INVALID, "capacity must fit 31 bits");
+    std::string err;
+    DomainQueue* q = nullptr;
+    const int rc = queue_create(ctx->device, ctx->n, ctx->n_hidden, capacity, &q, &err);
+    if (rc != GNNB_OK) return fail(ctx, rc, err);
+    *out = new gnnb_queue{ctx, q};
+    return GNNB_OK;
+}
+
+void gnnb_queue_destroy(gnnb_queue* q) {
+    if (!q) return;
+    queue_destroy(q->q);
+    delete q;
+}
+
+namespace {
+// device views of a gnnb_domains batch: the caller's pointers (DEVICE) or a staged copy (HOST; `to_device` copies in)
+struct DomView {
+    std::vector<float*> lb, ub;
+    float *lower = nullptr, *upper = nullptr;
+    int8_t* mask = nullptr;
+    int32_t* dec = nullptr;
+    uint8_t* keep = nullptr;
+};
+int view_domains(gnnb_queue* q, const gnnb_domains* d, const uint8_t* keep, bool to_device, DomView* v, cudaStream_t st) {
+    gnnb_ctx* ctx = q->ctx;
+    const int L = (int)ctx->layers.size(), B = d->B;
+    v->lb.assign(L + 2, nullptr); v->ub.assign(L + 2, nullptr);
+    if (d->mem != GNNB_MEM_HOST) {
+        for (int k = 0; k <= L + 1; ++k) { v->lb[k] = d->lb ? d->lb[k] : nullptr; v->ub[k] = d->ub ? d->ub[k] : nullptr; }
+        v->lower = d->lower_bound; v->upper = d->upper_bound; v->mask = d->mask; v->dec = d->decision; v->keep = const_cast<uint8_t*>(keep);
+        return GNNB_OK;
+    }
+    size_t floats = 0;
+    for (int k = 0; k <= L + 1; ++k) floats += 2 * align4((size_t)B * ctx->n[k]);
+    floats += 2 * align4(B) + align4(2 * (size_t)B) + align4(((size_t)B * ctx->n_hidden + 3) / 4) + align4(((size_t)B + 3) / 4);
+    float* base = queue_stage(q->q, floats * sizeof(float));
+    if (!base) return fail(ctx, GNNB_ERR_CUDA, queue_error(q->q));
+    size_t o = 0;
+    auto take = [&](size_t elems) { float* p = base + o; o += align4(elems); return p; };
+    auto up = [&](void* dst, const void* src, size_t bytes) { if (to_device && src) cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st); };
+    for (int k = 0; k <= L + 1; ++k) {
+        v->lb[k] = take((size_t)B * ctx->n[k]); v->ub[k] = take((size_t)B * ctx->n[k]);
+        up(v->lb[k], d->lb ? d->lb[k] : nullptr, (size_t)B * ctx->n[k] * sizeof(float));
+        up(v->ub[k], d->ub ? d->ub[k] : nullptr, (size_t)B * ctx->n[k] * sizeof(float));
+    }
+    v->lower = take(B); v->upper = take(B);
+    up(v->lower, d->lower_bound, B * sizeof(float)); up(v->upper, d->upper_bound, B * sizeof(float));
+    v->dec = reinterpret_cast<int32_t*>(take(2 * (size_t)B));
+    if (to_device && !d->decision) v->dec = nullptr; else up(v->dec, d->decision, 2 * (size_t)B * sizeof(int32_t));
+    v->mask = reinterpret_cast<int8_t*>(take(((size_t)B * ctx->n_hidden + 3) / 4));
+    up(v->mask, d->mask, (size_t)B * ctx->n_hidden);
+    v->keep = nullptr;
+    if (keep) { v->keep = reinterpret_cast<uint8_t*>(take(((size_t)B + 3) / 4)); up(v->keep, keep, B); }
+    return GNNB_OK;
+}
+}  // namespace
+
+int gnnb_queue_add(gnnb_queue* q, const gnnb_domains* d, const uint8_t* keep, int32_t* added, void* stream) {
+    if (!q || !d || !added) return GNNB_ERR_INVALID;
+    gnnb_ctx* ctx = q->ctx;
+    *added = 0;
+    if (d->B < 0) return fail(ctx, GNNB_ERR_INVALID, "negative batch");
+    if (d->B == 0) return GNNB_OK;
+    if (!d->lower_bound || !d->upper_bound || !d->lb || !d->ub || !d->mask) return fail(ctx, GNNB_ERR_INVALID, "null domain field");
+    const int L = (int)ctx->layers.size();
+    for (int k = 0; k <= L + 1; ++k) if (!d->lb[k] || !d->ub[k]) return fail(ctx, GNNB_ERR_INVALID, "null bound array");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    DomView v;
+    TRY(view_domains(q, d, keep, true, &v, st));
+    const int rc = queue_add(q->q, d->B, v.lower, v.upper, v.lb.data(), v.ub.data(), v.mask, v.dec, v.keep, added, st, &ctx->launches);
+    if (rc != GNNB_OK) return fail(ctx, rc, queue_error(q->q));
+    if (d->mem == GNNB_MEM_HOST) CU(cudaStreamSynchronize(st));      // the staging block is reused by the next call
+    return GNNB_OK;
+}
+
+int gnnb_queue_pick(gnnb_queue* q, float threshold, int32_t discard_rest, gnnb_domains* out, int32_t* picked, void* stream) {
+    if (!q || !out || !picked) return GNNB_ERR_INVALID;
+    gnnb_ctx* ctx = q->ctx;
+    *picked = 0;
+    if (out->B < 0) return fail(ctx, GNNB_ERR_INVALID, "negative batch");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int L = (int)ctx->layers.size();
+    DomView v;
+    TRY(view_domains(q, out, nullptr, false, &v, st));
+    const bool host = out->mem == GNNB_MEM_HOST;
+    if (host) {      // only the fields the caller asked for
+        if (!out->lower_bound) v.lower = nullptr;
+        if (!out->upper_bound) v.upper = nullptr;
+        if (!out->mask) v.mask = nullptr;
+        if (!out->decision) v.dec = nullptr;
+        for (int k = 0; k <= L + 1; ++k) { if (!out->lb || !out->lb[k]) v.lb[k] = nullptr; if (!out->ub || !out->ub[k]) v.ub[k] = nullptr; }
+    }
+    const int rc = queue_pick(q->q, out->B, threshold, discard_rest != 0, picked, v.lower, v.upper, v.lb.data(), v.ub.data(), v.mask, v.dec, st,
+                              &ctx->launches);
+    if (rc != GNNB_OK) return fail(ctx, rc, queue_error(q->q));
+    if (host && *picked > 0) {
+        const size_t n = (size_t)*picked;
+        auto down = [&](void* dst, const void* src, size_t bytes) { if (dst && src) cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st); };
+        for (int k = 0; k <= L + 1; ++k) {
+            down(out->lb ? out->lb[k] : nullptr, v.lb[k], n * ctx->n[k] * sizeof(float));
+            down(out->ub ? out->ub[k] : nullptr, v.ub[k], n * ctx->n[k] * sizeof(float));
+        }
+        down(out->lower_bound, v.lower, n * sizeof(float)); down(out->upper_bound, v.upper, n * sizeof(float));
+        down(out->mask, v.mask, n * ctx->n_hidden); down(out->decision, v.dec, 2 * n * sizeof(int32_t));
+        CU(cudaStreamSynchronize(st));
+    }
+    return GNNB_OK;
+}
+
+int gnnb_queue_prune(gnnb_queue* q, float threshold, void* stream) {
+    if (!q) return GNNB_ERR_INVALID;
+    gnnb_ctx* ctx = q->ctx;
+    CU(cudaSetDevice(ctx->device));
+    const int rc = queue_prune(q->q, threshold, (cudaStream_t)stream, &ctx->launches);
+    if (rc != GNNB_OK) return fail(ctx, rc, queue_error(q->q));
+    return GNNB_OK;
+}
+
+int gnnb_queue_stats(gnnb_queue* q, int64_t* size, float* global_lb, void* stream) {
+    if (!q) return GNNB_ERR_INVALID;
+    gnnb_ctx* ctx = q->ctx;
+    if (size) *size = queue_size(q->q);
+    if (global_lb && queue_size(q->q) > 0) {
+        CU(cudaSetDevice(ctx->device));
+        const int rc = queue_global_lb(q->q, global_lb, (cudaStream_t)stream);
+        if (rc != GNNB_OK) return fail(ctx, rc, queue_error(q->q));
     }
     return GNNB_OK;
 }

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <string>
 #include <vector>
 
 #include "../../include/gnnb.h"
@@ -132,6 +133,20 @@ void tc_layer(const GnnParams& g, const PropPlan* plan, const float* mu_in, bool
 // cnt is scratch of ntiles + 1 ints (three small launches: count per tile, scan, fill)
 void amb_compact(const float* lb, const float* ub, RowMap map, int64_t rows, int32_t* cnt, int32_t* amb_base, int32_t* amb_rows,
                  cudaStream_t st, int64_t* launches);
+// the same for up to AMB_MAX_LAYERS hidden layers of a wave in three launches
+constexpr int AMB_MAX_LAYERS = 16;
+struct AmbLayers {
+    const float* lb[AMB_MAX_LAYERS];
+    const float* ub[AMB_MAX_LAYERS];
+    RowMap map[AMB_MAX_LAYERS];
+    int64_t rows[AMB_MAX_LAYERS];
+    int32_t* cnt[AMB_MAX_LAYERS];
+    int32_t* base[AMB_MAX_LAYERS];
+    int32_t* out_rows[AMB_MAX_LAYERS];
+    int tile0[AMB_MAX_LAYERS + 1];      // filled by amb_compact_all
+    int n;
+};
+void amb_compact_all(AmbLayers a, cudaStream_t st, int64_t* launches);
 void tc_input_embed(const GnnParams& g, const float* lb0, const float* x, const float* ub0, float* mu0, RowMap map, int64_t rows,
                     cudaStream_t st, int64_t* launches);
 void tc_input_update(const GnnParams& g, const float* lb0, const float* ub0, const float* nb, float* mu0, RowMap map, int64_t rows,
@@ -170,6 +185,21 @@ int babsr_run(const LayerDev* d_layers, int L, int n_hidden, int nmax, const flo
               const float* wp, const float* mask, const int32_t* d_hidden_off, const int32_t* d_random_order,
               const int32_t* counter_in, int sparsest_layer, float threshold, int32_t* decision, int32_t* counter_out,
               int32_t* kind, float* scores, int B, cudaStream_t st, int64_t* launches);
+
+// device-resident domain queue (gnnb_queue.cu); every data pointer is a device pointer
+struct DomainQueue;
+int queue_create(int device, const std::vector<int>& n, int n_hidden, int64_t capacity, DomainQueue** out, std::string* err);
+void queue_destroy(DomainQueue* q);
+const std::string& queue_error(const DomainQueue* q);
+int64_t queue_size(const DomainQueue* q);
+int64_t queue_capacity(const DomainQueue* q);
+int queue_global_lb(DomainQueue* q, float* out, cudaStream_t st);
+int queue_add(DomainQueue* q, int B, const float* lower, const float* upper, const float* const* lb, const float* const* ub,
+              const int8_t* mask, const int32_t* decision, const uint8_t* keep, int32_t* added, cudaStream_t st, int64_t* launches);
+int queue_pick(DomainQueue* q, int max_B, float threshold, bool discard, int32_t* picked, float* lower, float* upper, float* const* lb,
+               float* const* ub, int8_t* mask, int32_t* decision, cudaStream_t st, int64_t* launches);
+int queue_prune(DomainQueue* q, float threshold, cudaStream_t st, int64_t* launches);
+float* queue_stage(DomainQueue* q, size_t bytes);
 
 // ---- device helpers ---------------------------------------------------------------------------
 // compute_ratio of graph_conv.py:499-514 in the reference's operation order (IEEE division, no fast-math)

@@ -197,27 +197,34 @@ __device__ __forceinline__ float mu_at(const float* __restrict__ mu, int mu_imag
     return (__half2float(hi) + __half2float(lo)) * 8.0f;
 }
 
-// one 64-thread block per subdomain
-__global__ void __launch_bounds__(64) k_output_node(GnnParams g, const float* __restrict__ wp, const float* __restrict__ bp,
-                                                    const float* __restrict__ mu_L, int mu_image, int mu_stride, const float* __restrict__ lb_out,
-                                                    const float* __restrict__ ub_out, const float* __restrict__ prim_out,
-                                                    float* __restrict__ mu_out, int nL) {
+// one 256-thread block per subdomain: thread (part, c) sums every 4th node of channel c, so that four independent
+// chains of loads are in flight per channel (the sum over the last hidden layer is latency-bound otherwise)
+__global__ void __launch_bounds__(256) k_output_node(GnnParams g, const float* __restrict__ wp, const float* __restrict__ bp,
+                                                     const float* __restrict__ mu_L, int mu_image, int mu_stride, const float* __restrict__ lb_out,
+                                                     const float* __restrict__ ub_out, const float* __restrict__ prim_out,
+                                                     float* __restrict__ mu_out, int nL) {
+    __shared__ float part_s[4][P];
     __shared__ float cat[2 * P];
     __shared__ float h2[P];
-    const int b = blockIdx.x, c = threadIdx.x;
+    const int b = blockIdx.x, c = threadIdx.x & 63, part = threadIdx.x >> 6;
     float nbv = 0.f;                                       // prop.weight @ mu[L]  (graph_conv.py:196)
-    for (int n = 0; n < nL; ++n) nbv = fmaf(wp[(int64_t)b * nL + n], mu_at(mu_L, mu_image, (int64_t)b * mu_stride + n, c), nbv);
+#pragma unroll 4
+    for (int n = part; n < nL; n += 4) nbv = fmaf(wp[(int64_t)b * nL + n], mu_at(mu_L, mu_image, (int64_t)b * mu_stride + n, c), nbv);
+    part_s[part][c] = nbv;
+    __syncthreads();
+    if (part != 0) return;
+    nbv = (part_s[0][c] + part_s[1][c]) + (part_s[2][c] + part_s[3][c]);
     const float feat[4] = {lb_out[b], ub_out[b], prim_out[b], bp[b]};   // graph_conv.py:202-205
     float h = g.bias[OUT1][c];
 #pragma unroll
     for (int k = 0; k < 4; ++k) h = fmaf(feat[k], g.wt[OUT1][k * P + c], h);
     cat[c] = (h != h) ? h : fmaxf(h, 0.f);
     cat[P + c] = nbv;
-    __syncthreads();
+    asm volatile("bar.sync 1, 64;" ::: "memory");
     float a = g.bias[OUT2][c];
     for (int k = 0; k < 2 * P; ++k) a = fmaf(cat[k], g.wt[OUT2][k * P + c], a);
     h2[c] = (a != a) ? a : fmaxf(a, 0.f);
-    __syncthreads();
+    asm volatile("bar.sync 1, 64;" ::: "memory");
     float o = g.bias[OUT3][c];
     for (int k = 0; k < P; ++k) o = fmaf(h2[k], g.wt[OUT3][k * P + c], o);
     mu_out[(int64_t)b * P + c] = o;
@@ -312,7 +319,7 @@ void prop_property_backward(const float* wp, const float* mu_out, float* nb, int
 
 void output_node(const GnnParams& g, const float* wp, const float* bp, const float* mu_L, bool mu_image, int mu_stride, const float* lb_out,
                  const float* ub_out, const float* prim_out, float* mu_out, int nL, int Bc, cudaStream_t st, int64_t* launches) {
-    k_output_node<<<Bc, 64, 0, st>>>(g, wp, bp, mu_L, mu_image ? 1 : 0, mu_stride, lb_out, ub_out, prim_out, mu_out, nL);
+    k_output_node<<<Bc, 256, 0, st>>>(g, wp, bp, mu_L, mu_image ? 1 : 0, mu_stride, lb_out, ub_out, prim_out, mu_out, nL);
     ++*launches;
 }
 

@@ -792,7 +792,63 @@ __global__ void __launch_bounds__(TILE) k_amb_fill(const float* __restrict__ lb,
     if (amb) amb_rows[slot] = (int32_t)row;
 }
 
+// the same three steps for every hidden layer of a wave in three launches (a block finds its layer from the tile offsets)
+__device__ __forceinline__ int amb_layer_of(const AmbLayers& a, int tile) {
+    int k = 0;
+    while (k + 1 < a.n && tile >= a.tile0[k + 1]) ++k;
+    return k;
+}
+__global__ void __launch_bounds__(TILE) k_amb_count_all(AmbLayers a) {
+    const int k = amb_layer_of(a, (int)blockIdx.x), tile = (int)blockIdx.x - a.tile0[k];
+    const int64_t row = (int64_t)tile * TILE + threadIdx.x;
+    const bool amb = row_is_ambiguous(a.lb[k], a.ub[k], a.map[k], row, a.rows[k]);
+    const int total = __syncthreads_count(amb);
+    if (threadIdx.x == 0) a.cnt[k][tile] = total;
+}
+__global__ void __launch_bounds__(1024) k_amb_scan_all(AmbLayers a) {
+    __shared__ int32_t part[1024];
+    const int k = blockIdx.x, n = a.tile0[k + 1] - a.tile0[k];
+    const int32_t* __restrict__ cnt = a.cnt[k];
+    int32_t* __restrict__ base = a.base[k];
+    const int per = (n + 1023) / 1024, lo = threadIdx.x * per, hi = min(n, lo + per);
+    int32_t sum = 0;
+    for (int i = lo; i < hi; ++i) sum += cnt[i];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        const int32_t v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int32_t run = part[threadIdx.x] - sum;
+    for (int i = lo; i < hi; ++i) { base[i] = run; run += cnt[i]; }
+    if (threadIdx.x == 1023) base[n] = part[1023];
+}
+__global__ void __launch_bounds__(TILE) k_amb_fill_all(AmbLayers a) {
+    __shared__ int32_t wc[4];
+    const int k = amb_layer_of(a, (int)blockIdx.x), tile = (int)blockIdx.x - a.tile0[k];
+    const int64_t row = (int64_t)tile * TILE + threadIdx.x;
+    const bool amb = row_is_ambiguous(a.lb[k], a.ub[k], a.map[k], row, a.rows[k]);
+    const unsigned bal = __ballot_sync(0xffffffffu, amb);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) wc[warp] = __popc(bal);
+    __syncthreads();
+    int slot = a.base[k][tile] + __popc(bal & ((1u << lane) - 1u));
+    for (int w = 0; w < warp; ++w) slot += wc[w];
+    if (amb) a.out_rows[k][slot] = (int32_t)row;
+}
+
 }  // namespace
+
+void amb_compact_all(AmbLayers a, cudaStream_t st, int64_t* launches) {
+    a.tile0[0] = 0;
+    for (int k = 0; k < a.n; ++k) a.tile0[k + 1] = a.tile0[k] + (int)((a.rows[k] + TILE - 1) / TILE);
+    k_amb_count_all<<<a.tile0[a.n], TILE, 0, st>>>(a);
+    k_amb_scan_all<<<a.n, 1024, 0, st>>>(a);
+    k_amb_fill_all<<<a.tile0[a.n], TILE, 0, st>>>(a);
+    *launches += 3;
+}
 
 void amb_compact(const float* lb, const float* ub, RowMap map, int64_t rows, int32_t* cnt, int32_t* amb_base, int32_t* amb_rows,
                  cudaStream_t st, int64_t* launches) {

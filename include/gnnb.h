@@ -169,6 +169,48 @@ int gnnb_get_gnn_weights(gnnb_ctx* ctx, float* const* tensors, const int64_t* nu
 int gnnb_adam_step(gnnb_ctx* ctx, float lr, float beta1, float beta2, float eps, float weight_decay, void* stream);
 int gnnb_adam_reset(gnnb_ctx* ctx);
 
+/* ---- device-resident domain queue of the branch-and-bound loop -------------------------------------------------------
+ * Replaces the sorted Python list `domains` of ReLUDomain objects (plnn/relu_conv_gnnkwthreshold.py:20-53: mask, lower /
+ * upper bound, every layer's bounds, the stored GNN decision) and the functions that work on it:
+ *   add_domain(candidate, domains)      bisect.insort_left by lower bound          plnn/branch_and_bound.py:159-164
+ *   pick_out(domains, threshold)        pop the front until lower_bound < threshold                          :167-184
+ *   prune_domains(domains, threshold)   keep the prefix with lower_bound < threshold                         :264-281
+ *   len(domains), domains[0].lower_bound                              plnn/relu_conv_gnnkwthreshold.py:236-244
+ * A domain's payload (bounds of layers 0..L+1 in the gnnb_frontier layout, mask, bounds, decision) stays in a device pool;
+ * the order is a sorted (key, slot) array on the device.  Equal lower bounds: the newest domain first (insort_left). */
+typedef struct gnnb_queue gnnb_queue;
+
+typedef struct {
+    int32_t B;                           /* domains in this batch (capacity of the arrays for gnnb_queue_pick) */
+    int32_t mem;                         /* gnnb_mem_kind of every pointer below */
+    float* lower_bound;                  /* [B]  ReLUDomain.lower_bound (the sort key) */
+    float* upper_bound;                  /* [B]  ReLUDomain.upper_bound */
+    float* const* lb;                    /* L+2 arrays [B, n_k]: ReLUDomain.lower_all at the layers the GNN reads */
+    float* const* ub;                    /* L+2 arrays [B, n_k]: ReLUDomain.upper_all */
+    int8_t* mask;                        /* [B, sum n_k]  -1 undecided, 0 / 1 fixed (ReLUDomain.mask, concatenated) */
+    int32_t* decision;                   /* [B, 2] (layer, index) or NULL: ReLUDomain.gnn_decision */
+} gnnb_domains;
+
+/* A queue for the network of `ctx` (gnnb_set_network first) with room for `capacity` domains. */
+int gnnb_queue_create(gnnb_ctx* ctx, int64_t capacity, gnnb_queue** out);
+void gnnb_queue_destroy(gnnb_queue* q);
+
+/* add_domain for every domain b of `d` with keep[b] != 0 (keep: [B] bytes in d->mem, NULL = all; the reference adds a child
+ * only when its lower bound is below the decision bound, relu_conv_gnnkwthreshold.py:217, 226).  *added = how many. */
+int gnnb_queue_add(gnnb_queue* q, const gnnb_domains* d, const uint8_t* keep, int32_t* added, void* stream);
+
+/* pick_out(domains, threshold) repeated until out->B domains are picked or the front of the queue is not below the
+ * threshold; the picked domains are written to `out` in pick order (fields may be NULL) and leave the queue.
+ * discard_rest != 0 mirrors the reference exactly: a pick_out that finds no domain below the threshold has popped (dropped)
+ * every remaining domain; 0 keeps them for gnnb_queue_prune.  *picked = how many (HOST). */
+int gnnb_queue_pick(gnnb_queue* q, float threshold, int32_t discard_rest, gnnb_domains* out, int32_t* picked, void* stream);
+
+/* prune_domains(domains, threshold). */
+int gnnb_queue_prune(gnnb_queue* q, float threshold, void* stream);
+
+/* len(domains) and domains[0].lower_bound (global_lb is written only when the queue is not empty; either may be NULL). */
+int gnnb_queue_stats(gnnb_queue* q, int64_t* size, float* global_lb, void* stream);
+
 /* Synchronise `stream` and report sticky device-side errors of earlier gnnb_score calls
  * (GNNB_ERR_NAN with the NaN count in *nan_count, may be NULL).  Clears the flag. */
 int gnnb_check(gnnb_ctx* ctx, void* stream, int64_t* nan_count);

@@ -11,7 +11,7 @@ for w in base wide deep; do
   python bench.py --workload $w --steps 10 --warmup 3 > $O/${TAG}_bench_$w.json 2> $O/${TAG}_bench_$w.err; echo "bench $w rc=$?"
 done
 python bench.py --impl reference --steps 3 --warmup 1 > $O/${TAG}_bench_ref.json 2>&1
-CMD="python bench.py --domains 256 --chunk 256 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e"
+CMD="python bench.py --domains 256 --chunk 256 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-babsr --no-online --no-queue"
 $CMD > $O/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -s 33 -c 40 --csv --log-file $O/${TAG}_launches.csv $CMD > $O/${TAG}_ncu_launches.log 2>&1
 $CMD > $O/${TAG}_plain2.log 2>&1 &&

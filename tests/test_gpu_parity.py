@@ -474,3 +474,135 @@ def test_adam_step_matches_torch():
         for k, q in params.items():
             assert float((w[k] - q.detach()).abs().max()) <= 2e-7 + 1e-3 * 3e-4, k
             q.data.copy_(w[k])          # keep the two trajectories on the same parameters
+
+
+# ---- device-resident domain queue ---------------------------------------------------------------
+def _queue_batch(net, lbs, ids, device='cuda'):
+    """Domains whose payload encodes their id: bounds row = id + layer/column pattern, mask = id % 3 - 1, decision = (id, 2 id)."""
+    from gnn_branching_b200 import DomainBatch
+    B = len(lbs)
+    ids_t = torch.tensor(ids, dtype=torch.float32)
+    sizes = [net.n0] + net.hidden_sizes + [1]
+    lb = [ids_t.reshape(B, 1) + 0.001 * k + 1e-6 * torch.arange(n).reshape(1, n) for k, n in enumerate(sizes)]
+    ub = [t + 0.5 for t in lb]
+    mask = ((torch.tensor(ids).reshape(B, 1) + torch.arange(net.n_hidden).reshape(1, -1)) % 3 - 1).to(torch.int8)
+    dec = torch.tensor([[i % 7, 2 * i] for i in ids], dtype=torch.int32)
+    return DomainBatch(torch.tensor(lbs, dtype=torch.float32), torch.tensor(lbs, dtype=torch.float32) + 1.0, lb, ub, mask, dec).to(device)
+
+
+def _check_payload(net, b, ids):
+    ref = _queue_batch(net, [float(x) for x in b.lower_bound.cpu()], ids, device='cpu')
+    got = b.to('cpu')
+    assert torch.equal(got.upper_bound, ref.upper_bound)
+    for k in range(len(ref.lb)):
+        assert torch.equal(got.lb[k], ref.lb[k]) and torch.equal(got.ub[k], ref.ub[k])
+    assert torch.equal(got.mask, ref.mask) and torch.equal(got.decision, ref.decision)
+
+
+@pytest.mark.parametrize('host', [False, True])
+def test_domain_queue_replays_reference_traces(host):
+    """gnnb_queue_* on the reference's own traces (tests/golden/queue_traces.npz): every pick returns the domain the
+    reference's pick_out returned, with its payload intact; the list left at the end is the reference's, in order."""
+    import numpy as np
+    from golden_io import GOLDEN
+    from gnn_branching_b200 import DomainQueue
+    z = dict(np.load(os.path.join(GOLDEN, 'queue_traces.npz')))
+    fr, _ = load_case('base', 'fr')
+    sc = Scorer(0)
+    sc.set_network(fr.net, key=fr.net.key)
+    dev = 'cpu' if host else 'cuda'
+    for t in range(6):
+        ops = z[f't{t}_ops']
+        if host and len(ops) > 500:
+            continue
+        q = DomainQueue(sc, capacity=1024)
+        picked = []
+        for kind, value, ident in ops:
+            kind = int(kind)
+            if kind == 0:
+                assert q.add(_queue_batch(fr.net, [float(value)], [int(ident)], device=dev)) == 1
+            elif kind == 1:
+                if len(q) == 0:
+                    picked.append(-1)
+                    continue
+                b = q.pick(1, float(value), device=dev, discard_rest=True)
+                if b.B == 0:
+                    picked.append(-1)
+                    assert len(q) == 0
+                else:
+                    ident_got = int(b.decision[0, 1]) // 2
+                    picked.append(ident_got)
+                    _check_payload(fr.net, b, [ident_got])
+            else:
+                q.prune(float(value))
+        assert picked == z[f't{t}_picked'].tolist()
+        left = z[f't{t}_left'].tolist()
+        assert len(q) == len(left)
+        if left:
+            rest = q.pick(len(left), float('inf'), device=dev)
+            assert [int(x) // 2 for x in rest.decision[:, 1].cpu()] == left
+            _check_payload(fr.net, rest, left)
+
+
+def test_domain_queue_batched_ops_match_oracle():
+    """Batched adds (with a keep mask), picks of many domains at once and prunes against the oracle; more adds than the
+    capacity raise; slots are recycled."""
+    from oracle.queue_oracle import QueueOracle
+    from gnn_branching_b200 import DomainQueue
+    fr, _ = load_case('base', 'fr')
+    sc = Scorer(0)
+    sc.set_network(fr.net, key=fr.net.key)
+    q, o = DomainQueue(sc, capacity=600), QueueOracle()
+    g = torch.Generator().manual_seed(5)
+    nid = 0
+    for rnd in range(12):
+        B = 150
+        lbs = (torch.round(torch.randn(B, generator=g) * 8) / 8 - 1.0).tolist()
+        keep = (torch.rand(B, generator=g) < 0.7)
+        ids = list(range(nid, nid + B)); nid += B
+        added = q.add(_queue_batch(fr.net, lbs, ids), keep=keep.cuda())
+        for b in range(B):
+            if keep[b]:
+                o.add(lbs[b], ids[b])
+        assert added == int(keep.sum()) and len(q) == len(o.domains)
+        assert q.global_lb == o.domains[0].lower_bound
+        thr = float(torch.randn(1, generator=g)) * 0.5 - 0.8
+        want = []
+        for _ in range(90):                          # pick(90) == 90 x pick_out while domains below the threshold remain
+            if not o.domains or o.domains[0].lower_bound >= thr:
+                break
+            want.append(o.pick(thr))
+        b = q.pick(90, thr)
+        assert [int(x) // 2 for x in b.decision[:, 1].cpu()] == want
+        _check_payload(fr.net, b, want)
+        if rnd % 3 == 2:
+            pt = float(torch.randn(1, generator=g)) * 0.5
+            q.prune(pt); o.prune(pt)
+        assert len(q) == len(o.domains)
+    rest = q.pick(len(q), float('inf'))
+    assert [int(x) // 2 for x in rest.decision[:, 1].cpu()] == [i for _, i in o.state()]
+    with pytest.raises(_lib.GnnbError):
+        q.add(_queue_batch(fr.net, [0.0] * 601, list(range(601))))
+
+
+def test_domain_queue_reference_function_api():
+    """add_domain / pick_out / prune_domains / domains[0].lower_bound called like plnn/relu_conv_gnnkwthreshold.py:126-244."""
+    from gnn_branching_b200.domain_queue import DomainQueue, ReLUDomain, add_domain, pick_out, prune_domains
+    fr, _ = load_case('base', 'fr')
+    sc = Scorer(0)
+    sc.set_network(fr.net, key=fr.net.key)
+    domains = DomainQueue(sc, capacity=16)
+    lbs, ubs, _, _, _, _, _ = fr.slice(0, 1).to_reference_args()
+    mask = _bab_mask(fr, 0)
+    for lb, dec in ((-0.5, [1, 7]), (-2.0, [0, 3]), (-0.5, [2, 9]), (0.3, [0, 0])):
+        add_domain(ReLUDomain(mask, lb=lb, ub=1.0, lb_all=[t[0] for t in lbs], up_all=[t[0] for t in ubs], gnn_decision=dec), domains)
+    assert len(domains) == 4 and domains[0].lower_bound == -2.0
+    d = pick_out(domains, 0.0)
+    assert d.lower_bound == -2.0 and d.gnn_decision == [0, 3] and d.upper_bound == 1.0
+    assert all(torch.equal(a.cpu(), b[0]) for a, b in zip(d.lower_all, lbs)) and all(torch.equal(a.cpu(), m) for a, m in zip(d.mask, mask))
+    assert pick_out(domains, 0.0).gnn_decision == [2, 9]          # equal lower bounds: the newest first (insort_left)
+    domains = prune_domains(domains, 0.0)
+    assert len(domains) == 1 and domains[0].lower_bound == -0.5
+    assert pick_out(domains, 0.0).gnn_decision == [1, 7]
+    with pytest.raises(AssertionError):
+        pick_out(domains, 0.0)

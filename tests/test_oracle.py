@@ -131,3 +131,18 @@ def test_online_oracle_matches_reference():
             for k, v in oo.state_dict().items():
                 ref = torch.from_numpy(z[f'{w}_sd2_{k}'])
                 assert float((v - ref).abs().max()) <= 0.02 * lr, k
+
+
+# ---- domain queue -------------------------------------------------------------------------------
+def test_queue_oracle_matches_reference_traces():
+    """oracle/queue_oracle.py against the reference's own add_domain / pick_out / prune_domains on seeded traces
+    (tests/golden/make_golden_queue.py): the same domain from every pick (ties, signed zeros, empty picks), the same list left."""
+    import numpy as np
+    import os
+    from golden_io import GOLDEN
+    from oracle import queue_oracle as QO
+    z = dict(np.load(os.path.join(GOLDEN, 'queue_traces.npz')))
+    for t in range(6):
+        picked, left = QO.replay(z[f't{t}_ops'])
+        assert picked == z[f't{t}_picked'].tolist()
+        assert left == z[f't{t}_left'].tolist()
