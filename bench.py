@@ -157,6 +157,31 @@ class ClockSampler:
                 'power_w_max': max(power), 'samples': len(sm), 'source': 'nvidia-smi -lms 50'}
 
 
+def run_timed(step, local_step, K, barrier, record0, record1, clock_samples, sync, min_samples=8, max_extra=400):
+    """The timed region: barrier, K steps between the two event records, barrier.  `step` may contain collectives (every
+    rank calls it exactly K times); afterwards the identical load is kept running with `local_step` — rank-LOCAL work only,
+    because every rank runs a different number of these — until the clock sampler has `min_samples` samples under load
+    (a K x 5 ms region can end before NVML has answered a handful of times)."""
+    barrier()
+    record0()
+    for i in range(K):
+        step(i)
+    record1()
+    barrier()
+    extra = 0
+    while clock_samples() < min_samples and extra < max_extra:
+        local_step(extra)
+        extra += 1
+        if extra % 4 == 0:
+            sync()
+    sync()
+    run_timed.extra = extra
+    return extra
+
+
+run_timed.extra = 0
+
+
 def cpu_baseline(workload, weights, threads=None, reps=3):
     """The reference algorithm (oracle port, fp32 PyTorch-CPU like the reference itself) on the host cores."""
     import torch
@@ -329,22 +354,8 @@ def main():
     launches0 = scorer.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
-        barrier()
-        ev0.record()
-        for i in range(K):
-            step(i)
-        ev1.record()
-        barrier()
-        launches = scorer.launches - launches0
-        # a short timed region (K x 5 ms) may end before NVML has answered a handful of times: keep the identical load
-        # running, untimed, until there are enough samples of the clocks under it
-        extra = 0
-        while clk.count() < 8 and extra < 400:
-            step(extra)
-            extra += 1
-            if extra % 4 == 0:
-                torch.cuda.synchronize()
-        torch.cuda.synchronize()
+        run_timed(step, lambda i: scorer_score(fronts[i % 2]), K, barrier, ev0.record, ev1.record, clk.count, torch.cuda.synchronize)
+        launches = (scorer.launches - launches0) * K // (K + run_timed.extra)      # every step issues the same launches
     scorer.check()
     ms = ev0.elapsed_time(ev1)
     # per-kernel-class durations: a second pass of K identical steps with CUDA events around every launch (on the launching

@@ -62,3 +62,48 @@ def test_gather_winners_two_ranks_gloo():
         for p in procs:
             p.join(timeout=60)
         assert all(ok for _, ok in res), res
+
+
+def _timed_worker(rank, world, port, q):
+    """bench.run_timed with a step that holds a collective and clock samplers that fill at different speeds per rank: every
+    rank must issue the same collectives (a rank-dependent number of extra steps with a collective inside deadlocked the
+    8-GPU bench once)."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    calls = {'step': 0, 'local': 0, 'samples': 0}
+
+    def step(i):
+        t = torch.ones(1)
+        dist.all_reduce(t)
+        calls['step'] += 1
+
+    def local_step(i):
+        calls['local'] += 1
+        calls['samples'] += 1 + rank           # rank 1's sampler fills twice as fast: different numbers of extra steps
+
+    extra = bench.run_timed(step, local_step, 5, dist.barrier, lambda: None, lambda: None, lambda: calls['samples'], lambda: None)
+    t = torch.tensor([float(extra)])
+    dist.all_reduce(t)                          # the collective sequence after the region still lines up
+    q.put((rank, calls['step'], calls['local'], float(t.item())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_timed_region_keeps_collectives_aligned_gloo():
+    port = _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_timed_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[1] for r in res] == [5, 5]                       # exactly K collective steps on every rank
+    assert res[0][2] == 8 and res[1][2] == 4                   # different numbers of rank-local extra steps
+    assert res[0][3] == res[1][3] == 12.0
