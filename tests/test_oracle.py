@@ -4,6 +4,8 @@ The goldens were produced by the unmodified reference GraphNet / GraphChoice in 
 (tests/golden/make_golden.py).  Tolerance: the oracle restates the same fp32 PyTorch-CPU arithmetic in
 batched form, so only fp32 re-association noise is allowed: 2e-6 * max|s| (observed <= 5e-7).
 """
+import os
+
 import pytest
 import torch
 
@@ -146,3 +148,46 @@ def test_queue_oracle_matches_reference_traces():
         picked, left = QO.replay(z[f't{t}_ops'])
         assert picked == z[f't{t}_picked'].tolist()
         assert left == z[f't{t}_left'].tolist()
+
+
+# ---- KW intermediate bounds (oracle and pins only, no CUDA implementation yet) ---------------------
+def _kw_err(a, b):
+    return float((a.reshape(-1) - b.reshape(-1)).abs().max()) / max(1.0, float(b.abs().max()))
+
+
+@pytest.mark.parametrize('arch', ARCHS)
+def test_kw_bounds_oracle_matches_reference_root_bounds(arch):
+    """oracle/kw_bounds_oracle.py against the reference's own DualNetwork on the root domain of the three CIFAR nets
+    (tests/golden/nets.npz, written by make_golden.py with convex_adversarial.DualNetwork): every layer's pre-ReLU bounds and
+    the output bounds to 2e-5 of the largest bound (fp32 sums over up to 3 072 + |I| columns in a different order)."""
+    import numpy as np
+    from golden_io import GOLDEN, load_root
+    from oracle import kw_bounds_oracle as KW
+    net, lbs, ubs, wp, bp = load_root(arch)
+    x = torch.from_numpy(np.load(os.path.join(GOLDEN, 'nets.npz'))[f'{arch}_x'].copy()).reshape(-1)
+    got_l, got_u = KW.kw_bounds(net, x, 0.145, wp, bp)
+    for k in range(net.L + 2):
+        assert _kw_err(got_l[k], lbs[k]) <= 2e-5 and _kw_err(got_u[k], ubs[k]) <= 2e-5, k
+        assert bool((got_l[k] <= got_u[k] + 1e-6).all())
+
+
+@pytest.mark.parametrize('arch', ['base', 'deep'])
+def test_kw_bounds_oracle_matches_reference_children(arch):
+    """Child domains: one ambiguous ReLU of the root fixed to blocked / passing, bounds recomputed with the parent's bounds
+    provided (tests/golden/make_golden_kw.py, the DualNetwork(provided_zl, provided_zu) path of init_kw_bounds)."""
+    import numpy as np
+    from golden_io import GOLDEN, load_root
+    from oracle import kw_bounds_oracle as KW
+    z = dict(np.load(os.path.join(GOLDEN, 'kw_children.npz')))
+    net, lbs, ubs, wp, bp = load_root(arch)
+    x = torch.from_numpy(np.load(os.path.join(GOLDEN, 'nets.npz'))[f'{arch}_x'].copy()).reshape(-1)
+    for c in range(int(z[f'{arch}_ncases'])):
+        lay, idx, choice = z[f'{arch}_c{c}_decision'].tolist()
+        plb, pub = KW.split_bounds(lbs, ubs, (lay, idx), choice)
+        got_l, got_u = KW.kw_bounds(net, x, 0.145, wp, bp, plb, pub)
+        got_l[-1], got_u[-1] = torch.max(got_l[-1], lbs[-1]), torch.min(got_u[-1], ubs[-1])     # init_kw_bounds :285-286
+        for k in range(1, net.L + 2):
+            rl, ru = torch.from_numpy(z[f'{arch}_c{c}_lb{k}']), torch.from_numpy(z[f'{arch}_c{c}_ub{k}'])
+            assert _kw_err(got_l[k], rl) <= 2e-5 and _kw_err(got_u[k], ru) <= 2e-5, (c, k)
+        fixed_l, fixed_u = got_l[lay + 1][idx], got_u[lay + 1][idx]
+        assert (float(fixed_u) == 0.0) if choice == 0 else (float(fixed_l) == 0.0)
