@@ -33,6 +33,7 @@ struct gnnb_ctx {
     int snapshot = 0;
     int fuse = 0;                   // propagation + node update of a layer in one launch (tensor-core mode); measured 3-4 % slower than two launches
     int prop_share = 0;             // % of a fused launch's CTAs that propagate; 0 = cost model
+    int gather_prefetch = 0;        // propagation kernel variant that fetches the gather indices one chunk ahead (not validated on a GPU yet)
     int32_t* d_flags = nullptr;     // per-item publication flags of the fused launches; value = epoch of the launch
     int32_t epoch = 0;
     int32_t consumed_base = 0;      // host mirror of the device progress counter d_flags[-1] at the next fused launch
@@ -344,7 +345,7 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
                          ctx->d_flags - 1, &ctx->consumed_base, ctx->lead, st, lc);
             } else {
                 ProfScope ps(ctx, GNNB_K_PROP_FWD, nodes, st);
-                if (tc) prop_tc_run(ctx->plan_fwd[k - 1], ctx->mu[k - 1], ctx->nb, Bc, st, lc);
+                if (tc) prop_tc_run(ctx->plan_fwd[k - 1], ctx->mu[k - 1], ctx->nb, Bc, st, lc, ctx->gather_prefetch != 0);
                 else prop_forward(ctx->layers[k - 1], ctx->mu[k - 1], ctx->nb, Bc, st, lc);
             }
             TRY(snap_img(ctx, name("t%d_fwd_nb%d", t, k), ctx->nb, k, Bc, true, st));
@@ -377,7 +378,7 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
                 ProfScope ps(ctx, GNNB_K_PROP_BWD, nodes, st);
                 if (k == L && tc) prop_tc_property_backward(in.wp, ctx->mu[L + 1], ctx->nb, ctx->n[L], ctx->rowmap[L].nslots, Bc, st, lc);
                 else if (k == L) prop_property_backward(in.wp, ctx->mu[L + 1], ctx->nb, ctx->n[L], Bc, st, lc);
-                else if (tc) prop_tc_run(ctx->plan_bwd[k], ctx->mu[k + 1], ctx->nb, Bc, st, lc);
+                else if (tc) prop_tc_run(ctx->plan_bwd[k], ctx->mu[k + 1], ctx->nb, Bc, st, lc, ctx->gather_prefetch != 0);
                 else prop_backward(ctx->layers[k], ctx->mu[k + 1], ctx->nb, Bc, true, st, lc);
             }
             TRY(snap_img(ctx, name("t%d_bwd_nb%d", t, k), ctx->nb, k, Bc, true, st));
@@ -392,7 +393,7 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
         if (!last) {
             {
                 ProfScope ps(ctx, GNNB_K_PROP_BWD, (int64_t)Bc * ctx->n[0], st);
-                if (tc) prop_tc_run(ctx->plan_bwd[0], ctx->mu[1], ctx->nb, Bc, st, lc);
+                if (tc) prop_tc_run(ctx->plan_bwd[0], ctx->mu[1], ctx->nb, Bc, st, lc, ctx->gather_prefetch != 0);
                 else prop_backward(ctx->layers[0], ctx->mu[1], ctx->nb, Bc, false, st, lc);
             }
             {
@@ -737,6 +738,8 @@ int gnnb_set_option(gnnb_ctx* ctx, const char* key, int64_t value) {
         ctx->chunk = (int)value;
     } else if (k == "fuse") {
         ctx->fuse = value ? 1 : 0;
+    } else if (k == "gather_prefetch") {
+        ctx->gather_prefetch = value ? 1 : 0;
     } else if (k == "prop_share") {
         if (value < 0 || value > 99) return fail(ctx, GNNB_ERR_INVALID, "prop_share is a percentage in [0, 99]");
         ctx->prop_share = (int)value;
@@ -761,6 +764,7 @@ int64_t gnnb_get_option(gnnb_ctx* ctx, const char* key) {
     if (k == "snapshot") return ctx->snapshot;
     if (k == "fuse") return ctx->fuse;
     if (k == "prop_share") return ctx->prop_share;
+    if (k == "gather_prefetch") return ctx->gather_prefetch;
     if (k == "lead") return ctx->lead;
     if (k == "profile") return ctx->profile;
     if (k == "n_hidden") return ctx->n_hidden;

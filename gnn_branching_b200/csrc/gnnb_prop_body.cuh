@@ -64,6 +64,7 @@ constexpr size_t PROP_SMEM = 1024 + W_STAGES * W_STAGE_BYTES + B_STAGES * B_STAG
 // One CTA's share of a propagation launch: items rank, rank + nranks, ...  `flags` (may be null): after the nb tile images
 // of an item are written, flags[item] = epoch is released at GPU scope, for node-update CTAs of the same launch that
 // wait for exactly this item (gnnb_tc.cu, k_tc_layer); `consumed` (may be null) is their progress counter.  All threads of the block must call it (block-wide barriers).
+template <bool GATHER_PREFETCH = false>
 __device__ __forceinline__ void prop_body(const PropPlanDev& plan, const uint16_t* __restrict__ mu_img, uint16_t* __restrict__ nb_img,
                                           int Bc, unsigned char* smem_raw, int rank, int nranks, int32_t* flags, int32_t epoch,
                                           const int32_t* consumed = nullptr, int32_t consumed_base = 0, int lead = 0, bool pdl = false) {
@@ -171,6 +172,62 @@ __device__ __forceinline__ void prop_body(const PropPlanDev& plan, const uint16_
         if (rank == 1 && lane == 0) printf("TRACE prop-mma: items %u chunks %d total %lld | wait acc_empty %lld, w_full %lld, b_full %lld\n", it, n_chunks,
                                            clock64() - t_all, t_acc, t_w, t_b);
 #endif
+    } else if (warp < EPI_WARP0 && GATHER_PREFETCH) {
+        // ---- gather with the row indices fetched one chunk ahead (option "gather_prefetch"; NOT the default yet) ----
+        // ncu's source page puts 57 % of the gather warps' samples on the first shuffle of `idx` below, i.e. on the latency of
+        // the index load that precedes every stage (profiles/r01s): here the 64 indices and the K-step count of
+        // the next chunk (of this item or of the CTA's next item) are in registers before the current chunk is copied.
+        const int g = warp - GATHER_WARP0;
+        const unsigned char* mu_bytes = reinterpret_cast<const unsigned char*>(mu_img);
+        uint32_t bs = 0, bph = 0;
+        int64_t item = rank;
+        if (item < nitems) {
+            int ch = plan.tile_chunk0[(int)(item % plan.ntiles)], ch1 = plan.tile_chunk0[(int)(item % plan.ntiles) + 1];
+            int i0 = __ldg(plan.in_rows + (size_t)ch * 64 + lane), i1 = __ldg(plan.in_rows + (size_t)ch * 64 + B_ROWS + lane);
+            int nks = __ldg(plan.ksteps + ch);
+            while (true) {
+                int64_t nitem = item;
+                int nch = ch + 1, nch1 = ch1;
+                if (nch >= ch1) {
+                    nitem = item + nranks;
+                    if (nitem < nitems) {
+                        const int nt = (int)(nitem % plan.ntiles);
+                        nch = plan.tile_chunk0[nt]; nch1 = plan.tile_chunk0[nt + 1];
+                    }
+                }
+                const bool has_next = nitem < nitems;
+                int n0 = -1, n1 = -1, nnks = 0;
+                if (has_next) {
+                    n0 = __ldg(plan.in_rows + (size_t)nch * 64 + lane); n1 = __ldg(plan.in_rows + (size_t)nch * 64 + B_ROWS + lane);
+                    nnks = __ldg(plan.ksteps + nch);
+                }
+                const int d = (int)(item / plan.ntiles) * PD + g;
+                const bool dom_ok = d < Bc;
+                const int64_t drow = (int64_t)d * plan.nslots_in;
+                for (int h = 0; 2 * h < nks; ++h) {
+                    const int idx = h ? i1 : i0;
+                    mbar_wait(smem_u32(&tail->b_empty[bs]), bph ^ 1u);
+                    const uint32_t dst0 = b_ring + bs * B_STAGE_BYTES + (uint32_t)g * B_DOM_BYTES;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int k = i * 4 + (lane >> 3);
+                        const int node = __shfl_sync(0xffffffffu, idx, k);
+                        const bool ok = dom_ok && node >= 0;
+                        const int64_t grow = ok ? drow + node : 0;
+                        const uint32_t r = (uint32_t)(grow & (TILE - 1));
+                        const uint32_t jp = (uint32_t)(lane & 7);
+                        const unsigned char* src = mu_bytes + (grow >> 7) * (int64_t)ABUF + (r >> 3) * 1024u + (r & 7u) * 128u + jp * 16u;
+                        const uint32_t dst = dst0 + swz((uint32_t)k, jp ^ (r & 7u));
+                        cp_async16(dst, src, ok);
+                        cp_async16(dst + B_PLANE_BYTES, src + APLANE, ok);
+                    }
+                    cp_async_arrive(smem_u32(&tail->b_full[bs]));
+                    if (++bs == B_STAGES) { bs = 0; bph ^= 1u; }
+                }
+                if (!has_next) break;
+                item = nitem; ch = nch; ch1 = nch1; i0 = n0; i1 = n1; nks = nnks;
+            }
+        }
     } else if (warp < EPI_WARP0) {
         // ---- gather: warp g copies the rows of subdomain d0 + g ----
         const int g = warp - GATHER_WARP0;
