@@ -608,19 +608,18 @@ def test_domain_queue_reference_function_api():
         pick_out(domains, 0.0)
 
 
+def _run_isolated(what, arg, timeout=240):
+    """Run a check of code that has never executed on a GPU in its own process (its own CUDA context) with a timeout: a hang
+    or a sticky CUDA error there cannot take the rest of the suite with it."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, os.path.join(here, 'gpu_isolated.py'), what, arg], capture_output=True, text=True, timeout=timeout)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+
+
 @pytest.mark.xfail(reason='option "gather_prefetch" (propagation kernel variant with the gather indices fetched one chunk ahead) was '
                           'written after the GPU budget of round 1 was spent: off by default, first validated by this test', strict=False)
 @pytest.mark.parametrize('arch', ARCHS)
 def test_gather_prefetch_variant_is_bit_identical(arch):
-    fr, ref = load_case(arch, 'fr')
-    model = _model('random', 'tc')
-    b0, i0, s0 = model.score_frontier(fr.to('cuda'))
-    model.scorer(0).set_option('gather_prefetch', 1)
-    b1, i1, s1 = model.score_frontier(fr.to('cuda'))
-    model.scorer(0).set_option('gather_prefetch', 0)
-    assert torch.equal(s0, s1) and torch.equal(i0, i1) and torch.equal(b0, b1)
-    big = synthetic_frontier(*load_root(arch), 37, seed=5, device='cuda')
-    b0, i0, s0 = model.score_frontier(big)
-    model.scorer(0).set_option('gather_prefetch', 1)
-    b1, i1, s1 = model.score_frontier(big)
-    assert torch.equal(s0, s1) and torch.equal(i0, i1)
+    _run_isolated('gather_prefetch', arch)
