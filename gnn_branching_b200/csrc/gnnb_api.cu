@@ -51,6 +51,8 @@ struct gnnb_ctx {
     int adam_steps = 0;
     float* train_ws = nullptr;      // activation tape + gradient temporaries of gnnb_score_grad (grow-only)
     size_t train_ws_cap = 0;
+    float* kw_ws = nullptr;         // column buffers of gnnb_kw_bounds (grow-only)
+    size_t kw_ws_cap = 0;
     // verified network
     bool have_net = false;
     float* d_net = nullptr;
@@ -582,6 +584,7 @@ void gnnb_destroy(gnnb_ctx* ctx) {
     if (ctx->d_tc) cudaFree(ctx->d_tc);
     if (ctx->d_train) cudaFree(ctx->d_train);
     if (ctx->train_ws) cudaFree(ctx->train_ws);
+    if (ctx->kw_ws) cudaFree(ctx->kw_ws);
     if (ctx->d_net) cudaFree(ctx->d_net);
     if (ctx->d_maps) cudaFree(ctx->d_maps);
     if (ctx->d_layers) cudaFree(ctx->d_layers);
@@ -1174,6 +1177,24 @@ int gnnb_queue_stats(gnnb_queue* q, int64_t* size, float* global_lb, void* strea
         const int rc = queue_global_lb(q->q, global_lb, (cudaStream_t)stream);
         if (rc != GNNB_OK) return fail(ctx, rc, queue_error(q->q));
     }
+    return GNNB_OK;
+}
+
+int gnnb_kw_bounds(gnnb_ctx* ctx, int32_t B, const float* x, float eps, const float* wp, const float* bp, const float* const* provided_lb,
+                   const float* const* provided_ub, float* const* out_lb, float* const* out_ub, void* stream) {
+    if (!ctx || !x || !wp || !bp || !out_lb || !out_ub) return fail(ctx, GNNB_ERR_INVALID, "null argument");
+    if (!ctx->have_net) return fail(ctx, GNNB_ERR_STATE, "gnnb_set_network must be called first");
+    if (B < 1) return fail(ctx, GNNB_ERR_INVALID, "need at least one domain");
+    if ((provided_lb == nullptr) != (provided_ub == nullptr)) return fail(ctx, GNNB_ERR_INVALID, "provide both lower and upper bounds or neither");
+    const int L = (int)ctx->layers.size();
+    for (int k = 0; k <= L + 1; ++k) if (!out_lb[k] || !out_ub[k]) return fail(ctx, GNNB_ERR_INVALID, "null output array");
+    if (provided_lb)
+        for (int k = 0; k < L; ++k) if (!provided_lb[k] || !provided_ub[k]) return fail(ctx, GNNB_ERR_INVALID, "null provided-bounds array");
+    CU(cudaSetDevice(ctx->device));
+    std::string err;
+    const int rc = kw_bounds(ctx->layers, ctx->n, B, x, eps, wp, bp, provided_lb, provided_ub, out_lb, out_ub, &ctx->kw_ws, &ctx->kw_ws_cap,
+                             (cudaStream_t)stream, &ctx->launches, &err);
+    if (rc != GNNB_OK) return fail(ctx, rc, err);
     return GNNB_OK;
 }
 

@@ -202,6 +202,11 @@ int queue_pick(DomainQueue* q, int max_B, float threshold, bool discard, int32_t
 int queue_prune(DomainQueue* q, float threshold, cudaStream_t st, int64_t* launches);
 float* queue_stage(DomainQueue* q, size_t bytes);
 
+// batched KW intermediate bounds (gnnb_kw.cu); every pointer is a device pointer
+int kw_bounds(const std::vector<LayerDev>& layers, const std::vector<int>& n, int B, const float* x, float eps, const float* wp, const float* bp,
+              const float* const* prov_lb, const float* const* prov_ub, float* const* out_lb, float* const* out_ub, float** ws,
+              size_t* ws_cap, cudaStream_t st, int64_t* launches, std::string* err);
+
 // ---- device helpers ---------------------------------------------------------------------------
 // compute_ratio of graph_conv.py:499-514 in the reference's operation order (IEEE division, no fast-math)
 struct Ratio { float r0, r1, beta, amb; };

@@ -284,6 +284,41 @@ class Scorer:
     def adam_reset(self):
         self._ok(self.lib.gnnb_adam_reset(self.h))
 
+    # ---- batched KW bounds (NOT validated on a GPU yet: gnnb_kw.cu) ----
+    def kw_bounds(self, x: torch.Tensor, eps: float, Wp: torch.Tensor, bp: torch.Tensor, provided_lb=None, provided_ub=None):
+        """KW intermediate bounds of B domains (init_kw_bounds of the reference, batched).  ``x`` [B, n0] (or [n0], shared),
+        ``Wp`` [B, n_L], ``bp`` [B]; ``provided_lb`` / ``provided_ub``: L tensors [B, n_k] (the parent's pre-ReLU bounds with
+        the split applied) or None.  Returns (lbs, ubs): L + 2 CUDA tensors [B, n_k] each."""
+        if self.net is None:
+            raise RuntimeError('set_network first')
+        net, L = self.net, self.net.L
+        dev = torch.device('cuda', self.device)
+        sizes = [net.n0] + net.hidden_sizes + [1]
+        Wp = Wp.to(dev, torch.float32).reshape(-1, sizes[L]).contiguous()
+        B = int(Wp.shape[0])
+        x = x.to(dev, torch.float32).reshape(-1, net.n0)
+        x = (x.expand(B, net.n0) if x.shape[0] == 1 else x).contiguous()
+        bp = bp.to(dev, torch.float32).reshape(B).contiguous()
+        lbs = [torch.empty(B, n, dtype=torch.float32, device=dev) for n in sizes]
+        ubs = [torch.empty(B, n, dtype=torch.float32, device=dev) for n in sizes]
+        plb = pub = None
+        keep = []
+        if provided_lb is not None:
+            pl = [self._as_f32(t.to(dev), (B, sizes[k + 1])) for k, t in enumerate(provided_lb)]
+            pu = [self._as_f32(t.to(dev), (B, sizes[k + 1])) for k, t in enumerate(provided_ub)]
+            plb, k1 = _lib.fptr_array(pl)
+            pub, k2 = _lib.fptr_array(pu)
+            keep += [pl, pu, k1, k2]
+        olb, k3 = _lib.fptr_array(lbs)
+        oub, k4 = _lib.fptr_array(ubs)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            self._ok(self.lib.gnnb_kw_bounds(self.h, B, _lib.fptr(x), float(eps), _lib.fptr(Wp), _lib.fptr(bp), plb, pub, olb, oub,
+                                             C.c_void_p(stream)))
+            torch.cuda.synchronize()
+        del keep, k3, k4
+        return lbs, ubs
+
     def check(self) -> None:
         """Synchronise and raise if a NaN appeared in an embedding (the reference drops into pdb there)."""
         n = C.c_int64(0)

@@ -212,6 +212,18 @@ int gnnb_queue_prune(gnnb_queue* q, float threshold, void* stream);
 /* len(domains) and domains[0].lower_bound (global_lb is written only when the queue is not empty; either may be NULL). */
 int gnnb_queue_stats(gnnb_queue* q, int64_t* size, float* global_lb, void* stream);
 
+/* ---- batched KW intermediate bounds (the bound producer in front of the scoring path) ---------------------------------
+ * NOT VALIDATED ON A GPU YET (written after the GPU budget of round 1 was spent).
+ * Replaces DualNetwork(net, x, eps, bounded_input=False[, provided_zl, provided_zu]) of the reference's vendored
+ * convex_adversarial as called by init_kw_bounds (plnn/dual_network_linear_approximation.py:205-288) for B domains at once:
+ * pre-ReLU bounds of the L hidden layers (DualReLU.zl / zu), each intersected with the provided bounds when given (the
+ * parent's bounds with one ReLU fixed, :313-319), the input box, and the bounds of the property output (dual(+-1)).
+ * Every pointer is a DEVICE pointer: x [B, n_0], wp [B, n_L], bp [B]; provided_lb / provided_ub: L arrays [B, n_k],
+ * k = 1..L, or both NULL; out_lb / out_ub: L + 2 arrays [B, n_k], k = 0..L+1.  Work is enqueued on `stream`. */
+int gnnb_kw_bounds(gnnb_ctx* ctx, int32_t B, const float* x, float eps, const float* wp, const float* bp,
+                   const float* const* provided_lb, const float* const* provided_ub, float* const* out_lb,
+                   float* const* out_ub, void* stream);
+
 /* Synchronise `stream` and report sticky device-side errors of earlier gnnb_score calls
  * (GNNB_ERR_NAN with the NaN count in *nan_count, may be NULL).  Clears the flag. */
 int gnnb_check(gnnb_ctx* ctx, void* stream, int64_t* nan_count);

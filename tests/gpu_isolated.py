@@ -29,6 +29,45 @@ def check_gather_prefetch(arch):
         assert torch.equal(s0, s1) and torch.equal(i0, i1) and torch.equal(b0, b1), 'gather_prefetch changes the results'
 
 
+def check_kw_bounds(arch):
+    """gnnb_kw_bounds against the reference's own DualNetwork: root bounds of the net (tests/golden/nets.npz) and child domains
+    with one ReLU fixed, all children in one batched call (tests/golden/kw_children.npz); 5e-5 of the largest bound."""
+    import numpy as np
+    from golden_io import GOLDEN
+    from gnn_branching_b200 import Scorer
+    from oracle import kw_bounds_oracle as KW
+    net, lbs, ubs, wp, bp = load_root(arch)
+    x = torch.from_numpy(np.load(os.path.join(GOLDEN, 'nets.npz'))[f'{arch}_x'].copy()).reshape(1, -1)
+    sc = Scorer(0)
+    sc.set_network(net, key=net.key)
+
+    def err(a, b):
+        return float((a.reshape(-1).cpu() - b.reshape(-1)).abs().max()) / max(1.0, float(b.abs().max()))
+
+    gl, gu = sc.kw_bounds(x, 0.145, wp.reshape(1, -1), torch.tensor([bp]))
+    for k in range(net.L + 2):
+        assert err(gl[k], lbs[k]) <= 5e-5 and err(gu[k], ubs[k]) <= 5e-5, ('root', k, err(gl[k], lbs[k]), err(gu[k], ubs[k]))
+    if arch == 'wide':
+        return
+    z = dict(np.load(os.path.join(GOLDEN, 'kw_children.npz')))
+    nc = int(z[f'{arch}_ncases'])
+    plbs, pubs = [], []
+    for c in range(nc):
+        lay, idx, choice = z[f'{arch}_c{c}_decision'].tolist()
+        a, b = KW.split_bounds(lbs, ubs, (lay, idx), choice)
+        plbs.append(a); pubs.append(b)
+    plb = [torch.stack([plbs[c][k] for c in range(nc)]) for k in range(net.L)]
+    pub = [torch.stack([pubs[c][k] for c in range(nc)]) for k in range(net.L)]
+    gl, gu = sc.kw_bounds(x, 0.145, wp.reshape(1, -1).repeat(nc, 1), torch.full((nc,), float(bp)), plb, pub)
+    for c in range(nc):
+        for k in range(1, net.L + 2):
+            rl, ru = torch.from_numpy(z[f'{arch}_c{c}_lb{k}']), torch.from_numpy(z[f'{arch}_c{c}_ub{k}'])
+            l, u = gl[k][c].cpu(), gu[k][c].cpu()
+            if k == net.L + 1:                     # init_kw_bounds :285-286 intersects the output bounds with the parent's
+                l, u = torch.max(l, lbs[-1]), torch.min(u, ubs[-1])
+            assert err(l, rl) <= 5e-5 and err(u, ru) <= 5e-5, ('child', c, k, err(l, rl), err(u, ru))
+
+
 if __name__ == '__main__':
-    {'gather_prefetch': check_gather_prefetch}[sys.argv[1]](sys.argv[2])
+    {'gather_prefetch': check_gather_prefetch, 'kw_bounds': check_kw_bounds}[sys.argv[1]](sys.argv[2])
     print('ok')

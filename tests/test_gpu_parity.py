@@ -623,3 +623,11 @@ def _run_isolated(what, arg, timeout=240):
 @pytest.mark.parametrize('arch', ARCHS)
 def test_gather_prefetch_variant_is_bit_identical(arch):
     _run_isolated('gather_prefetch', arch)
+
+
+@pytest.mark.xfail(reason='gnnb_kw_bounds (batched KW bound producer, SURVEY 8f rank 3) was written after the GPU budget of round 1 was '
+                          'spent; its algorithm is checked on the CPU (scripts/kw_transposed_check.py), its kernels first run here',
+                   strict=False)
+@pytest.mark.parametrize('arch', ARCHS)
+def test_kw_bounds_match_reference(arch):
+    _run_isolated('kw_bounds', arch, timeout=600)
