@@ -45,9 +45,10 @@ def compute_ratio(l: torch.Tensor, u: torch.Tensor):
 
 
 class _Params:
-    def __init__(self, sd: Dict[str, torch.Tensor], keep_graph: bool = False):
+    def __init__(self, sd: Dict[str, torch.Tensor], keep_graph: bool = False, device='cpu'):
         # keep_graph: use the tensors as given (fp32 CPU leaves that require grad) so that autograd reaches them
-        self.sd = dict(sd) if keep_graph else {k: v.detach().float().cpu() for k, v in sd.items()}
+        # device: 'cpu' everywhere except bench.py's "eager PyTorch on the GPU" baseline leg
+        self.sd = dict(sd) if keep_graph else {k: v.detach().float().to(device) for k, v in sd.items()}
 
     def lin(self, name: str, x: torch.Tensor) -> torch.Tensor:
         pre = 'ComputeFinalScore.' if name in SCORE_LINEARS else 'EmbedUpdates.update.'
@@ -75,7 +76,7 @@ def _conv_backward(a, mu_next: torch.Tensor, normalise: bool) -> torch.Tensor:
         raise NotImplementedError('conv_transpose2d output does not match the layer input (output_padding needed)')
     if normalise:
         kh, kw = a.weight.shape[2:]
-        freq = F.conv_transpose2d(torch.ones(1, 1, *a.out_shape[1:]), torch.ones(1, 1, kh, kw), None,
+        freq = F.conv_transpose2d(torch.ones(1, 1, *a.out_shape[1:], device=y.device), torch.ones(1, 1, kh, kw, device=y.device), None,
                                   stride=a.stride, padding=a.padding)
         y = y / freq
     return y.reshape(B, p, -1).permute(0, 2, 1)
@@ -97,14 +98,14 @@ def gnn_forward(state_dict: Dict[str, torch.Tensor], fr, T: int = 2, p: int = 64
     mask; the reference evaluates the head only on rows with mask != 0, graph_conv.py:445-450).
     ``stages`` (optional dict) receives named intermediates for kernel-by-kernel debugging.
     """
-    P = _Params(state_dict, keep_graph)
+    P = _Params(state_dict, keep_graph, device=fr.lb[0].device)
     net = fr.net
     L, B = net.L, fr.B
     rec = (lambda k, v: stages.__setitem__(k, v.clone())) if stages is not None else (lambda k, v: None)
 
     # init_mu (graph_conv.py:487-496)
     sizes = [net.n0] + net.hidden_sizes + [1]
-    mu: List[torch.Tensor] = [torch.zeros(B, n, p) for n in sizes]
+    mu: List[torch.Tensor] = [torch.zeros(B, n, p, device=fr.lb[0].device) for n in sizes]
     l0, u0 = fr.lb[0], fr.ub[0]
 
     for t in range(T):
