@@ -111,3 +111,30 @@ def test_synthetic_frontier_is_well_formed():
     again = synthetic_frontier(net, lbs, ubs, wp, bp, 16, seed=3)
     assert torch.equal(again.lb[1], fr.lb[1]) and torch.equal(again.dual[0], fr.dual[0])
     assert fr.input_bytes() // 16 == 4 * (2 * (3072 + 3172 + 1) + 3 * 3172 + 2 * 3172 + 1 + 3072 + 100 + 1 + 3172)
+
+
+def test_ctypes_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors of gnnb_layer_desc / gnnb_frontier / gnnb_domains against the C compiler's view of include/gnnb.h
+    (sizes and field offsets), and the header compiles as plain C."""
+    import ctypes as C
+    import subprocess
+    src = os.path.join(tmp_path, 'layout.c')
+    fields = {'gnnb_layer_desc': [f[0] for f in _lib.LayerDesc._fields_], 'gnnb_frontier': [f[0] for f in _lib.FrontierDesc._fields_],
+              'gnnb_domains': [f[0] for f in _lib.DomainsDesc._fields_]}
+    with open(src, 'w') as f:
+        f.write('#include <stdio.h>\n#include <stddef.h>\n#include "gnnb.h"\nint main(void) {\n')
+        for s, names in fields.items():
+            f.write(f'  printf("{s} %zu", sizeof({s}));\n')
+            for n in names:
+                f.write(f'  printf(" %zu", offsetof({s}, {n}));\n')
+            f.write('  printf("\\n");\n')
+        f.write('  return 0;\n}\n')
+    exe = os.path.join(tmp_path, 'layout')
+    subprocess.check_call(['gcc', '-std=c99', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'), src, '-o', exe])
+    out = subprocess.check_output([exe], text=True).strip().splitlines()
+    mirrors = {'gnnb_layer_desc': _lib.LayerDesc, 'gnnb_frontier': _lib.FrontierDesc, 'gnnb_domains': _lib.DomainsDesc}
+    for line in out:
+        parts = line.split()
+        cls = mirrors[parts[0]]
+        assert int(parts[1]) == C.sizeof(cls), parts[0]
+        assert [int(x) for x in parts[2:]] == [getattr(cls, n).offset for n, _ in cls._fields_], parts[0]
