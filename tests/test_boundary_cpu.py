@@ -138,3 +138,16 @@ def test_ctypes_struct_layouts_match_the_header(tmp_path):
         cls = mirrors[parts[0]]
         assert int(parts[1]) == C.sizeof(cls), parts[0]
         assert [int(x) for x in parts[2:]] == [getattr(cls, n).offset for n, _ in cls._fields_], parts[0]
+
+
+def test_plain_c_client_links_and_fails_loudly_without_a_gpu(tmp_path):
+    """tests/c/abi_client.c built with gcc against include/gnnb.h and libgnnb.so: the ABI is plain C, and without a B200
+    gnnb_create returns a status code and no context (with one, the context works)."""
+    import subprocess
+    lib_dir = os.path.dirname(_lib.LIB_PATH)
+    exe = os.path.join(tmp_path, 'abi_client')
+    subprocess.check_call(['gcc', '-std=c99', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'), os.path.join(ROOT, 'tests', 'c', 'abi_client.c'),
+                           '-L', lib_dir, '-lgnnb', '-Wl,-rpath,' + lib_dir, '-o', exe])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert r.stdout.startswith('abi 1 create ')
