@@ -39,7 +39,8 @@ namespace prop {
 // as tcgen05.mma M = 128, N = 256, K = 16, three passes for the fp16 hi/lo split (Wh Mh + Wl Mh + Wh Ml).
 // Warp roles (14 warps), decoupled by mbarrier rings:
 //   warp 0      TMA: the chunk's 32 KB weight block (hi, lo plane; K-major SWIZZLE_128B)      -> W ring, 3 stages
-//   warp 1      MMA issue + tcgen05.commit (frees ring stages, publishes accumulators)
+//   warp 1      MMA issue + tcgen05.commit (frees ring stages, publishes accumulators): all 32 lanes walk the loop with
+//               uniform operands, one elected lane issues (6 back-to-back UTCHMMA per half chunk)
 //   warps 2-5   gather, one subdomain each: the chunk's input-node rows are copied with 16-byte cp.async straight
 //               from the mu tile images (already fp16 hi/lo, scaled) into the MN-major SWIZZLE_128B B operand — no
 //               registers, no conversion; half a chunk (32 rows x 4 subdomains x 2 planes = 32 KB) per stage, 4 stages

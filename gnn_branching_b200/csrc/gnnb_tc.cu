@@ -21,12 +21,16 @@
 // Rows are in slot order (gnnb_common.cuh RowMap): a tile is 128 slots of one subdomain = one tile of the propagation
 // plans; the caller's node-order arrays (bounds, duals, primals, scores) are reached through node_of_slot.
 //
+// Launch: programmatic dependent launch (gnnb_umma.cuh launch_pdl): the prologue (barriers, tensor memory, weight planes) of a
+// kernel overlaps the tail of its predecessor; pdl_wait() precedes the first access to anything a predecessor wrote.
+//
 // Structure of a CTA (1 per SM, persistent over work items = 4 subdomains x tile, one tile per warpgroup): 4 warpgroups
 // of 128 threads; the stage's weights sit in shared memory for the CTA's lifetime as fp16 hi/lo planes in the UMMA
 // K-major SWIZZLE_128B image (repacked once on the host, landed with one cp.async.bulk per linear); each warpgroup
 // owns one 128-slot tile at a time with 128 tensor-memory columns, a 32 KB shared-memory buffer and two mbarriers, and
 // walks the chain of its tile sequentially:
-//   GEMM (one thread issues 3 x 4 tcgen05.mma + tcgen05.commit) -> everyone waits on the mbarrier -> tcgen05.ld ->
+//   GEMM (the warpgroup's first warp walks the issue code uniformly, one elected lane issues 3 x 4 tcgen05.mma +
+//   tcgen05.commit: 12 back-to-back UTCHMMA, gnnb_umma.cuh elect_one) -> everyone waits on the mbarrier -> tcgen05.ld ->
 //   bias / ReLU / row scaling in registers (thread = row = TMEM lane) -> fp16 hi/lo split -> tcgen05.st of the next
 //   A operand straight back into tensor memory -> tcgen05.wait::st + fence + warpgroup barrier -> next GEMM ...
 // Only the first GEMM of the update chain reads its A operand from shared memory (the nb tile image, one 32 KB
