@@ -347,7 +347,7 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
                          ctx->d_flags - 1, &ctx->consumed_base, ctx->lead, st, lc);
             } else {
                 ProfScope ps(ctx, GNNB_K_PROP_FWD, nodes, st);
-                if (tc) prop_tc_run(ctx->plan_fwd[k - 1], ctx->mu[k - 1], ctx->nb, Bc, st, lc, ctx->gather_prefetch != 0);
+                if (tc) prop_tc_run(ctx->plan_fwd[k - 1], ctx->mu[k - 1], ctx->nb, Bc, st, lc, ctx->gather_prefetch);
                 else prop_forward(ctx->layers[k - 1], ctx->mu[k - 1], ctx->nb, Bc, st, lc);
             }
             TRY(snap_img(ctx, name("t%d_fwd_nb%d", t, k), ctx->nb, k, Bc, true, st));
@@ -380,7 +380,7 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
                 ProfScope ps(ctx, GNNB_K_PROP_BWD, nodes, st);
                 if (k == L && tc) prop_tc_property_backward(in.wp, ctx->mu[L + 1], ctx->nb, ctx->n[L], ctx->rowmap[L].nslots, Bc, st, lc);
                 else if (k == L) prop_property_backward(in.wp, ctx->mu[L + 1], ctx->nb, ctx->n[L], Bc, st, lc);
-                else if (tc) prop_tc_run(ctx->plan_bwd[k], ctx->mu[k + 1], ctx->nb, Bc, st, lc, ctx->gather_prefetch != 0);
+                else if (tc) prop_tc_run(ctx->plan_bwd[k], ctx->mu[k + 1], ctx->nb, Bc, st, lc, ctx->gather_prefetch);
                 else prop_backward(ctx->layers[k], ctx->mu[k + 1], ctx->nb, Bc, true, st, lc);
             }
             TRY(snap_img(ctx, name("t%d_bwd_nb%d", t, k), ctx->nb, k, Bc, true, st));
@@ -395,7 +395,7 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
         if (!last) {
             {
                 ProfScope ps(ctx, GNNB_K_PROP_BWD, (int64_t)Bc * ctx->n[0], st);
-                if (tc) prop_tc_run(ctx->plan_bwd[0], ctx->mu[1], ctx->nb, Bc, st, lc, ctx->gather_prefetch != 0);
+                if (tc) prop_tc_run(ctx->plan_bwd[0], ctx->mu[1], ctx->nb, Bc, st, lc, ctx->gather_prefetch);
                 else prop_backward(ctx->layers[0], ctx->mu[1], ctx->nb, Bc, false, st, lc);
             }
             {
@@ -742,7 +742,8 @@ int gnnb_set_option(gnnb_ctx* ctx, const char* key, int64_t value) {
     } else if (k == "fuse") {
         ctx->fuse = value ? 1 : 0;
     } else if (k == "gather_prefetch") {
-        ctx->gather_prefetch = value ? 1 : 0;
+        if (value < 0 || value > 2) return fail(ctx, GNNB_ERR_INVALID, "gather_prefetch is 0, 1 or 2");
+        ctx->gather_prefetch = (int)value;
     } else if (k == "prop_share") {
         if (value < 0 || value > 99) return fail(ctx, GNNB_ERR_INVALID, "prop_share is a percentage in [0, 99]");
         ctx->prop_share = (int)value;

@@ -177,7 +177,7 @@ PropPlan* prop_plan_build(const LayerDev& L, const float* host_weight, bool back
 void prop_plan_free(PropPlan* p);
 double prop_plan_density(const PropPlan* p);
 void prop_tc_run(const PropPlan* plan, const float* mu_in, float* nb_img, int Bc, cudaStream_t st, int64_t* launches,
-                 bool gather_prefetch = false);
+                 int gather_prefetch = 0);
 void prop_tc_property_backward(const float* wp, const float* mu_out, float* nb_img, int nL, int nslots, int Bc, cudaStream_t st, int64_t* launches);
 
 // BaBSR / KW heuristic (gnnb_babsr.cu); every pointer is a device pointer; returns -1 when the network does not fit

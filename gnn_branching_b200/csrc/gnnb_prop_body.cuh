@@ -56,26 +56,30 @@ constexpr uint32_t B_STAGE_BYTES = 2 * B_PLANE_BYTES;     // 32 KB
 constexpr int PROP_WARPS = 14, PROP_THREADS = PROP_WARPS * 32;
 constexpr int GATHER_WARP0 = 2, EPI_WARP0 = 6;
 
-struct PropTail {
-    uint64_t w_full[W_STAGES], w_empty[W_STAGES], b_full[B_STAGES], b_empty[B_STAGES], acc_full[2], acc_empty[2];
+template <int WS, int BS>
+struct PropTailT {
+    uint64_t w_full[WS], w_empty[WS], b_full[BS], b_empty[BS], acc_full[2], acc_empty[2];
     uint32_t tmem_slot;
 };
+using PropTail = PropTailT<W_STAGES, B_STAGES>;
+static_assert(sizeof(PropTailT<2, 5>) == sizeof(PropTail), "the 2 + 5 stage variant uses the same shared memory");
 constexpr size_t PROP_SMEM = 1024 + W_STAGES * W_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + sizeof(PropTail);
 
 // One CTA's share of a propagation launch: items rank, rank + nranks, ...  `flags` (may be null): after the nb tile images
 // of an item are written, flags[item] = epoch is released at GPU scope, for node-update CTAs of the same launch that
 // wait for exactly this item (gnnb_tc.cu, k_tc_layer); `consumed` (may be null) is their progress counter.  All threads of the block must call it (block-wide barriers).
-template <bool GATHER_PREFETCH = false>
+template <bool GATHER_PREFETCH = false, int WS = W_STAGES, int BS = B_STAGES>
 __device__ __forceinline__ void prop_body(const PropPlanDev& plan, const uint16_t* __restrict__ mu_img, uint16_t* __restrict__ nb_img,
                                           int Bc, unsigned char* smem_raw, int rank, int nranks, int32_t* flags, int32_t epoch,
                                           const int32_t* consumed = nullptr, int32_t consumed_base = 0, int lead = 0, bool pdl = false) {
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
-    const uint32_t w_ring = smem_u32(base), b_ring = w_ring + W_STAGES * W_STAGE_BYTES;
-    PropTail* tail = reinterpret_cast<PropTail*>(base + W_STAGES * W_STAGE_BYTES + B_STAGES * B_STAGE_BYTES);
+    const uint32_t w_ring = smem_u32(base), b_ring = w_ring + WS * W_STAGE_BYTES;
+    using Tail = PropTailT<WS, BS>;
+    Tail* tail = reinterpret_cast<Tail*>(base + WS * W_STAGE_BYTES + BS * B_STAGE_BYTES);
     const int warp = uniform((int)(threadIdx.x >> 5)), lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < W_STAGES; ++i) { mbar_init(smem_u32(&tail->w_full[i]), 1); mbar_init(smem_u32(&tail->w_empty[i]), 1); }
-        for (int i = 0; i < B_STAGES; ++i) { mbar_init(smem_u32(&tail->b_full[i]), PD * 32); mbar_init(smem_u32(&tail->b_empty[i]), 1); }
+        for (int i = 0; i < WS; ++i) { mbar_init(smem_u32(&tail->w_full[i]), 1); mbar_init(smem_u32(&tail->w_empty[i]), 1); }
+        for (int i = 0; i < BS; ++i) { mbar_init(smem_u32(&tail->b_full[i]), PD * 32); mbar_init(smem_u32(&tail->b_empty[i]), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tail->acc_full[i]), 1); mbar_init(smem_u32(&tail->acc_empty[i]), 128); }
         fence_mbar_init();
     }
@@ -102,7 +106,7 @@ __device__ __forceinline__ void prop_body(const PropPlanDev& plan, const uint16_
                     const uint32_t full = smem_u32(&tail->w_full[ws]);
                     mbar_expect_tx(full, W_STAGE_BYTES);
                     bulk_g2s(w_ring + ws * W_STAGE_BYTES, plan.a_planes + (size_t)ch * (W_STAGE_BYTES / 2), W_STAGE_BYTES, full);
-                    if (++ws == W_STAGES) { ws = 0; wph ^= 1u; }
+                    if (++ws == WS) { ws = 0; wph ^= 1u; }
                 }
             }
         }
@@ -157,11 +161,11 @@ __device__ __forceinline__ void prop_body(const PropPlanDev& plan, const uint16_
                     }
                     __syncwarp();
                     accum = 1u;
-                    if (++bs == B_STAGES) { bs = 0; bph ^= 1u; }
+                    if (++bs == BS) { bs = 0; bph ^= 1u; }
                 }
                 if (elect_one()) umma_commit(smem_u32(&tail->w_empty[ws]));
                 __syncwarp();
-                if (++ws == W_STAGES) { ws = 0; wph ^= 1u; }
+                if (++ws == WS) { ws = 0; wph ^= 1u; }
             }
             if (elect_one()) umma_commit(smem_u32(&tail->acc_full[a]));
             __syncwarp();
@@ -223,7 +227,7 @@ __device__ __forceinline__ void prop_body(const PropPlanDev& plan, const uint16_
                         cp_async16(dst + B_PLANE_BYTES, src + APLANE, ok);
                     }
                     cp_async_arrive(smem_u32(&tail->b_full[bs]));
-                    if (++bs == B_STAGES) { bs = 0; bph ^= 1u; }
+                    if (++bs == BS) { bs = 0; bph ^= 1u; }
                 }
                 if (!has_next) break;
                 item = nitem; ch = nch; ch1 = nch1; i0 = n0; i1 = n1; nks = nnks;
@@ -275,7 +279,7 @@ __device__ __forceinline__ void prop_body(const PropPlanDev& plan, const uint16_
                         cp_async16(dst + B_PLANE_BYTES, src + APLANE, ok);
                     }
                     cp_async_arrive(smem_u32(&tail->b_full[bs]));
-                    if (++bs == B_STAGES) { bs = 0; bph ^= 1u; }
+                    if (++bs == BS) { bs = 0; bph ^= 1u; }
                 }
             }
         }

@@ -172,10 +172,19 @@ LayerTiling make_tiling(int C, int H, int W) {
     return t;
 }
 
+// prefetched indices + 2 weight stages / 5 gather stages (the same shared memory): more gathered rows in flight, the weight
+// ring is rarely what the MMA warp waits for (option "gather_prefetch" = 2; not validated on a GPU yet either)
+__global__ void __launch_bounds__(prop::PROP_THREADS, 1) k_tc_prop_pf25(PropPlanDev plan, const uint16_t* __restrict__ mu_img,
+                                                                        uint16_t* __restrict__ nb_img, int Bc) {
+    extern __shared__ unsigned char smem_raw[];
+    prop::prop_body<true, 2, 5>(plan, mu_img, nb_img, Bc, smem_raw, (int)blockIdx.x, (int)gridDim.x, nullptr, 0, nullptr, 0, 0, true);
+}
+
 int prop_tc_init() {
     cudaError_t e = cudaFuncSetAttribute(k_tc_prop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop::PROP_SMEM);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_tc_prop_pf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop::PROP_SMEM);
+    if ((e = cudaFuncSetAttribute(k_tc_prop_pf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop::PROP_SMEM)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_tc_prop_pf25, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop::PROP_SMEM);
 }
 
 // plan for  nb = A_k(mu)  (forward) or  nb = A_k^T(mu) [/ freq]  (backward) of one verified-network layer;
@@ -243,10 +252,10 @@ double prop_plan_density(const PropPlan* p) { return p ? p->density : 0.0; }
 const PropPlanDev& prop_plan_dev(const PropPlan* p) { return p->dev; }
 double prop_plan_chunks_per_tile(const PropPlan* p) { return p->dev.ntiles > 0 ? (double)p->nchunks / p->dev.ntiles : 1.0; }
 
-void prop_tc_run(const PropPlan* plan, const float* mu_img, float* nb_img, int Bc, cudaStream_t st, int64_t* launches, bool gather_prefetch) {
+void prop_tc_run(const PropPlan* plan, const float* mu_img, float* nb_img, int Bc, cudaStream_t st, int64_t* launches, int gather_prefetch) {
     const int64_t nitems = (int64_t)plan->dev.ntiles * ((Bc + prop::PD - 1) / prop::PD);
     const int grid = (int)(nitems < 1 ? 1 : (nitems < 148 ? nitems : 148));
-    launch_pdl(gather_prefetch ? k_tc_prop_pf : k_tc_prop, grid, prop::PROP_THREADS, prop::PROP_SMEM, st, plan->dev,
+    launch_pdl(gather_prefetch == 2 ? k_tc_prop_pf25 : gather_prefetch == 1 ? k_tc_prop_pf : k_tc_prop, grid, prop::PROP_THREADS, prop::PROP_SMEM, st, plan->dev,
                reinterpret_cast<const uint16_t*>(mu_img), reinterpret_cast<uint16_t*>(nb_img), Bc);
     ++*launches;
 }

@@ -105,8 +105,8 @@ int gnnb_set_gnn_weights(gnnb_ctx* ctx, const float* const* tensors, const int64
  * (graph_conv.py:107-137, 222-249). */
 int gnnb_set_network(gnnb_ctx* ctx, const gnnb_layer_desc* layers, int n_layers, int c0, int h0, int w0);
 
-/* Options: "math" (gnnb_math_mode), "chunk" (subdomains per wave; 0 = auto), "gather_prefetch" (0/1, default 0: propagation
- * kernel variant that fetches its gather indices one chunk ahead), "fuse" (0/1, default 0: propagation and
+/* Options: "math" (gnnb_math_mode), "chunk" (subdomains per wave; 0 = auto), "gather_prefetch" (0/1/2, default 0: propagation
+ * kernel variants that fetch their gather indices one chunk ahead; 2 also trades one weight stage for a gather stage), "fuse" (0/1, default 0: propagation and
  * node update of a layer in one launch, tensor-core mode), "prop_share" (0 = cost model, else the percentage of the
  * CTAs of a fused launch that run the propagation), "snapshot" (0/1: keep
  * per-stage copies for gnnb_debug_snapshot; debugging only), "profile" (0/1: time every stage launch with

@@ -14,7 +14,7 @@ for a in base deep wide; do
   done
 done
 # 3. the propagation variant with prefetched gather indices against the default
-for pf in 0 1; do
+for pf in 0 1 2; do
   python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --no-babsr --no-online --no-queue --opt gather_prefetch=$pf \
       > $O/${TAG}_bench_base_pf$pf.json 2> $O/${TAG}_bench_base_pf$pf.err; echo "bench pf=$pf rc=$?"
 done

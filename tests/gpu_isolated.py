@@ -15,7 +15,8 @@ from gnn_branching_b200 import GraphNet, synthetic_frontier      # noqa: E402
 
 
 def check_gather_prefetch(arch):
-    """The propagation kernel variant k_tc_prop_pf must give bit-identical scores, winners and indices."""
+    """The propagation kernel variants k_tc_prop_pf (option value 1) and k_tc_prop_pf25 (2) must give bit-identical scores,
+    winners and indices."""
     fr, _ = load_case(arch, 'fr')
     model = GraphNet(2, 64, math='tc')
     model.load_state_dict(load_gnn('random'))
@@ -23,10 +24,11 @@ def check_gather_prefetch(arch):
     for f in (fr.to('cuda'), synthetic_frontier(*load_root(arch), 37, seed=5, device='cuda')):
         model.scorer(0).set_option('gather_prefetch', 0)
         b0, i0, s0 = model.score_frontier(f)
-        model.scorer(0).set_option('gather_prefetch', 1)
-        b1, i1, s1 = model.score_frontier(f)
-        torch.cuda.synchronize()
-        assert torch.equal(s0, s1) and torch.equal(i0, i1) and torch.equal(b0, b1), 'gather_prefetch changes the results'
+        for variant in (1, 2):
+            model.scorer(0).set_option('gather_prefetch', variant)
+            b1, i1, s1 = model.score_frontier(f)
+            torch.cuda.synchronize()
+            assert torch.equal(s0, s1) and torch.equal(i0, i1) and torch.equal(b0, b1), f'gather_prefetch={variant} changes the results'
 
 
 def check_kw_bounds(arch):
