@@ -84,7 +84,8 @@ class GraphNet(nn.Module):
         if self._scorer is None or self._scorer.device != device_index:
             self._scorer = Scorer(device_index, math=self._math, chunk=self._chunk)
         key = tuple((q.data_ptr(), q._version) for q in self.parameters())
-        self._scorer.set_gnn(self.state_dict(), self.T, self.p, key=key)
+        if self._scorer._gnn_key != key:          # state_dict() costs ~0.2 ms: only when a parameter changed
+            self._scorer.set_gnn(self.state_dict(), self.T, self.p, key=key)
         return self._scorer
 
     def adopt_weights(self, sc: Scorer) -> None:
