@@ -324,6 +324,9 @@ def main():
     model = GraphNet(2, 64, math=args.math, chunk=args.chunk)
     model.load_state_dict(sd)
     model = model.eval().to(dev)
+    if world > 1:      # the GNN parameters are broadcast once from rank 0, outside the timed region
+        from gnn_branching_b200.dist import broadcast_gnn_weights
+        broadcast_gnn_weights(model, src=0)
     # two different frontiers used alternately: with the workspace they exceed the 126 MB L2 several times over
     fronts = [synthetic_frontier(net, lbs, ubs, wp, bp, B, seed=1000 * (7 + rank) + i, device=dev) for i in range(2)]
     scorer = model.scorer(local)

@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from gnn_branching_b200.dist import gather_winners, pack_winners, shard_range, unpack_winners
+from gnn_branching_b200.dist import broadcast_gnn_weights, gather_winners, pack_winners, shard_range, unpack_winners
 
 
 def _free_port():
@@ -107,3 +107,38 @@ def test_timed_region_keeps_collectives_aligned_gloo():
     assert [r[1] for r in res] == [5, 5]                       # exactly K collective steps on every rank
     assert res[0][2] == 8 and res[1][2] == 4                   # different numbers of rank-local extra steps
     assert res[0][3] == res[1][3] == 12.0
+
+
+def _bcast_worker(rank, world, port, q):
+    from gnn_branching_b200 import GraphNet
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)                       # every rank starts from different parameters
+    model = GraphNet(2, 64)
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    n = broadcast_gnn_weights(model, src=0)
+    ref = [torch.zeros_like(v) for v in model.state_dict().values()]
+    if rank == 0:
+        ref = [v.clone() for v in before.values()]
+    for t in ref:
+        dist.broadcast(t, src=0)
+    same = all(torch.equal(a, b) for a, b in zip(model.state_dict().values(), ref))
+    changed = any(not torch.equal(a, b) for a, b in zip(model.state_dict().values(), before.values()))
+    q.put((rank, n, bool(same), bool(changed)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_weights_are_broadcast_once_from_rank_0_gloo():
+    port = _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bcast_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == 117825 and r[2] for r in res), res
+    assert not res[0][3] and res[1][3]                  # rank 0 keeps its parameters, rank 1 received them
