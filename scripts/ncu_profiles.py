@@ -3,6 +3,7 @@
      <tag>_ncu_launches.csv        the launch list (copied)
      <tag>_ncu_launch_shares.txt   share of the step per kernel
      <tag>_ncu_summary.txt         per-launch DRAM bytes / %, L2 %, tensor-pipe %, issue-slot % (from --set full)
+     <tag>_ncu_source_{prop,update}.txt   source page: stall reasons and hottest SASS lines of the two big kernels
      kernel_traffic.json           measured DRAM bytes per launch and subdomain per kernel class (bench.py's roofline.traffic)
    Usage: python scripts/ncu_profiles.py <tag> <domains in the capture>"""
 import csv, io, json, os, subprocess, sys
@@ -62,5 +63,15 @@ kt = {c: {'launches_per_step': a[0], 'dram_bytes_per_launch_per_subdomain': a[1]
 kt['_source'] = (f'ncu --set full, profiles/{tag}_ncu_summary.txt: bench.py --domains {domains} --chunk {domains} --steps 1 --warmup 1, second step '
                  '(dram__bytes_read.sum + dram__bytes_write.sum)')
 json.dump(kt, open(os.path.join(P, 'kernel_traffic.json'), 'w'), indent=1)
+# ---- source page of the two big kernels: stall reasons and hottest SASS lines ----
+for kern, short in (('k_tc_prop', 'prop'), ('k_tc_update', 'update')):
+    src = subprocess.run(['ncu', '-i', os.path.join(O, f'{tag}_prof.ncu-rep'), '--page', 'source', '--csv', '--kernel-name', f'regex:{kern}$',
+                          '--launch-skip', '0', '--launch-count', '1'], capture_output=True, text=True).stdout
+    tmp = os.path.join(O, f'{tag}_src_{short}.csv')
+    open(tmp, 'w').write(src)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'scripts', 'ncu_src_summary.py'), tmp, '20'], capture_output=True, text=True).stdout
+    with open(os.path.join(P, f'{tag}_ncu_source_{short}.txt'), 'w') as f:
+        f.write(f'# ncu --page source of {tag}_prof.ncu-rep, first launch of {kern}: stall reasons and hottest SASS lines\n')
+        f.write(out)
 print(open(os.path.join(P, f'{tag}_ncu_launch_shares.txt')).read())
 print(json.dumps({k: v for k, v in kt.items() if k != '_source'}, indent=1))
