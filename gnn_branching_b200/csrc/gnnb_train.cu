@@ -474,7 +474,6 @@ int train_backward(const GnnParams& g, const TrainParams& tp, const std::vector<
     float* base = *arena;
     auto Pp = [&](size_t off) { return base + off; };
     Ctx c{g, tp, st, launches};
-    unsigned long long nan_dummy = 0; (void)nan_dummy;
 
     // ---- forward with tape ----
     for (int k = 1; k <= L; ++k) {
