@@ -26,6 +26,7 @@ METRIC = 'gnn_subdomains_scored_per_sec'
 UNIT = 'subdomains/s'
 DEFAULT_DOMAINS = {'base': 1024, 'wide': 4096, 'deep': 4096}
 CPU_SAMPLE = 32          # subdomains per CPU-baseline pass (the reference's CPU rate is flat from B = 4)
+FRONTIER_TOTAL = 65536   # BASELINE configs[4]: the base frontier sharded over N > 1 GPUs
 
 
 def parse():
@@ -44,6 +45,7 @@ def parse():
     ap.add_argument('--no-babsr', action='store_true')
     ap.add_argument('--no-online', action='store_true')
     ap.add_argument('--no-queue', action='store_true')
+    ap.add_argument('--no-secondary', action='store_true', help='skip the wide / deep x 4096 secondary objects of the default line')
     ap.add_argument('--opt', action='append', default=[], help='library option key=value (e.g. fuse=0, prop_share=40)')
     return ap.parse_args()
 
@@ -182,12 +184,43 @@ def run_timed(step, local_step, K, barrier, record0, record1, clock_samples, syn
 run_timed.extra = 0
 
 
-def cpu_baseline(workload, weights, threads=None, reps=3):
-    """The reference algorithm (oracle port, fp32 PyTorch-CPU like the reference itself) on the host cores."""
+def _run_ref_runner(device, workload, weights, batches, reps, warmup=1, timeout=900):
+    """oracle/ref_runner.py in its own process (CPU runs must not see a GPU).  Returns its JSON or None."""
+    from oracle import ref_runner
+    if not ref_runner.available():
+        return None
+    env = dict(os.environ)
+    if device == 'cpu':
+        env['CUDA_VISIBLE_DEVICES'] = ''
+    for k in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE', 'MASTER_ADDR', 'MASTER_PORT'):
+        env.pop(k, None)
+    cmd = [sys.executable, os.path.join(ROOT, 'oracle', 'ref_runner.py'), '--device', device, '--workload', workload, '--weights', weights,
+           '--batches', ','.join(str(b) for b in batches), '--reps', str(reps), '--warmup', str(warmup)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+        if r.returncode != 0:
+            return {'error': (r.stderr or r.stdout)[-300:]}
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:          # a baseline must never take the bench line down
+        return {'error': repr(e)[:300]}
+
+
+def cpu_baseline(workload, weights, threads=None, reps=3, warmup=1):
+    """The reference GNN forward on the host cores: the UNMODIFIED graphnet/graph_conv.py staged in oracle/_ref (kind
+    "reference") when it is there, else the oracle port (kind "port").  B = 1 latency (the reference's native usage) and the
+    best rate over B in {1, 8, 32} (its CPU rate is flat from B = 4)."""
+    threads = threads or os.cpu_count()
+    ref = _run_ref_runner('cpu', workload, weights, (1, 8, CPU_SAMPLE), reps, warmup)
+    if ref and 'error' not in ref:
+        pb = ref['per_batch']
+        times = pb[str(CPU_SAMPLE)]['times_s']
+        return {'value': ref['value'], 'unit': UNIT, 'cores': ref['cores'], 'kind': 'reference', 'best_batch': ref['best_batch'],
+                'b1_latency_ms': ref['b1_latency_ms'], 'rate_by_batch': {k: v['rate'] for k, v in pb.items()},
+                'sample': f'unmodified graphnet/graph_conv.py GraphNet.forward (oracle/_ref, own process without a GPU), cifar_{workload}_kw, '
+                          f'B in (1, 8, {CPU_SAMPLE}) x {reps} passes each, best pass of the best batch size'}, times
     import torch
     from gnn_branching_b200 import synthetic_frontier
     from oracle import graphnet_oracle as O
-    threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
     net, lbs, ubs, wp, bp = load_problem(workload)
     fr = synthetic_frontier(net, lbs, ubs, wp, bp, CPU_SAMPLE, seed=99)
@@ -204,19 +237,19 @@ def cpu_baseline(workload, weights, threads=None, reps=3):
         O.gnn_forward(sd, fr.slice(0, 1))
         lat1 = time.perf_counter() - t0
     best = min(times)
-    return {'value': CPU_SAMPLE / best, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-            'sample': f'{CPU_SAMPLE} cifar_{workload}_kw subdomains x {reps} passes, best pass; oracle/graphnet_oracle.py '
-                      f'(fp32 torch-CPU restatement of graphnet/graph_conv.py); B=1 latency {lat1 * 1e3:.1f} ms',
+    return {'value': CPU_SAMPLE / best, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'b1_latency_ms': lat1 * 1e3,
+            'sample': f'{CPU_SAMPLE} cifar_{workload}_kw subdomains x {reps} passes, best pass; oracle/graphnet_oracle.py (fp32 torch-CPU '
+                      f'restatement of graphnet/graph_conv.py) because oracle/_ref is not staged' + (f' ({ref["error"]})' if ref else ''),
             'median_value': CPU_SAMPLE / statistics.median(times)}, times
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm on this box's host cores (oracle port)."""
+    """--impl reference: the reference's own GNN forward (oracle/_ref, unmodified; else the oracle port) on this box's host
+    cores, every step one pass over a CPU_SAMPLE-subdomain sample of the workload."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cb, times = cpu_baseline(args.workload, args.weights, reps=max(1, args.steps + args.warmup))
-    times = times[args.warmup:] or times
+    cb, times = cpu_baseline(args.workload, args.weights, reps=max(1, args.steps), warmup=max(1, args.warmup))
     per = sum(times) / len(times)
     line = {'impl': 'reference', 'metric': METRIC, 'value': CPU_SAMPLE / per, 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': len(times), 'warmup': args.warmup, 'ms_per_step': per * 1e3, 'higher_is_better': True,
@@ -269,7 +302,7 @@ def kernel_rooflines(net, fr, prof, n_domains, T, peak_tf, peak_gbs, p=64):
         byts['update'] = T * (n[-1] * row + node_bytes[-1]) + 4 * n[-1]
         flop['prop'] = 2 * p * (T - 1) * mac[0]                                    # input-layer propagation + property rank-1
         byts['prop'] = row * (T * n[-1] + (T - 1) * (n_all[1] + n_all[0]))
-    names = {'layer': 'k_tc_layer (fused propagation gather-GEMM + node update chain of one layer)',
+    names = {'layer': 'k_tc_fused (propagation gather-GEMM -> tensor memory -> node update chain of one layer, one kernel)',
              'update': 'k_tc_update (node update MLP chain, forward / backward / + score head)',
              'prop': 'k_tc_prop (embedding propagation through the verified network, gather-GEMM)',
              'relax': 'k_tc_relax (+ ambiguous-row compaction)', 'input': 'k_tc_input_embed / k_tc_input_update'}
@@ -297,6 +330,121 @@ def kernel_rooflines(net, fr, prof, n_domains, T, peak_tf, peak_gbs, p=64):
             '_bytes_per_subdomain': sum(byts.values())}
 
 
+def measure_device(scorer, fronts, B, K, W, world, dev, local, gather):
+    """Device-resident rate of one workload: W warm-up steps, K timed steps between CUDA events (barrier + synchronize on both
+    sides, max over ranks), clocks sampled during the timed region, then a second pass of K steps with events around every
+    launch for the per-kernel-class times."""
+    import torch
+    import torch.distributed as dist
+
+    def score(fr):
+        scorer.set_network(fr.net, key=fr.net.key)
+        return scorer.score(fr, return_scores=False, check=False)
+
+    def step(i):
+        best, idx, _ = score(fronts[i % len(fronts)])
+        if world > 1:
+            best, idx = gather(best, idx, B * world)
+        return best, idx
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        step(i)
+    scorer.check()
+    barrier()
+    launches0 = scorer.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        run_timed(step, lambda i: score(fronts[i % len(fronts)]), K, barrier, ev0.record, ev1.record, clk.count, torch.cuda.synchronize)
+        launches = (scorer.launches - launches0) * K // (K + run_timed.extra)      # every step issues the same launches
+    scorer.check()
+    ms = ev0.elapsed_time(ev1)
+    # per-kernel-class durations: a second pass of K identical steps with CUDA events around every launch (on the launching
+    # stream).  The events serialise consecutive launches (no programmatic overlap of a kernel's prologue with its
+    # predecessor's tail), so the headline `value` above is measured without them
+    scorer.set_option('profile', 1)
+    scorer.profile_reset()
+    for i in range(K):
+        step(i)
+    scorer.check()
+    prof = scorer.profile_read()
+    scorer.set_option('profile', 0)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {'value': B * world * K / (ms * 1e-3), 'ms': ms, 'launches': launches, 'prof': prof, 'clocks': clk.summary()}
+
+
+def measure_e2e(model, host_fronts, B, K, W, world, dev, gather):
+    """The same metric through the public API with pinned HOST buffers: host->device copies of every step's inputs and the
+    device->host read of the winners are inside the timed region (wall clock between barriers, max over ranks)."""
+    import torch
+    import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(min(W, 2)):
+        model.score_frontier(host_fronts[i % len(host_fronts)], return_scores=False)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        hb, hi, _ = model.score_frontier(host_fronts[i % len(host_fronts)], return_scores=False)
+        if world > 1:
+            gather(hb.to(dev), hi.to(dev), B * world)
+    barrier()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    return {'value': B * world * K / dt, 'unit': UNIT, 'h2d_bytes_per_step': host_fronts[0].input_bytes(),
+            'd2h_bytes_per_step': B * 8, 'api': 'GraphNet.score_frontier(pinned host Frontier)'}
+
+
+def load_peaks():
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except (OSError, ValueError):
+        pass
+    # a short timed region runs at burst clocks, a long one under the power cap (profiling recipe): bf16 burst / sustained
+    return {'tf_sustained': peaks.get('bf16_tflops_sustained', 1400.0), 'tf_burst': peaks.get('bf16_tflops', 1650.0),
+            'gbs': peaks.get('hbm_gbs', 6650.0),
+            'source': 'MEASURED_PEAKS.json hbm_gbs / bf16_tflops (burst) / bf16_tflops_sustained (of measured)' if peaks else
+                      'B200_PROFILING.md fallback 6.65 TB/s / 1.65 PF burst / 1.4 PF sustained (of fallback)'}
+
+
+def roofline_of(net, fr, m, n_domains, world, scorer, peaks):
+    """roofline object of one measured workload (dominant kernel class, live CUDA-event times, whole-path figures)."""
+    timed_s = m['ms'] * 1e-3
+    peak_tf = peaks['tf_burst'] if timed_s < 0.25 else peaks['tf_sustained']        # which bf16 peak applies to this timed region
+    r = kernel_rooflines(net, fr, m['prof'], n_domains, T=2, peak_tf=peak_tf, peak_gbs=peaks['gbs'])
+    r['peak_source'] = peaks['source'] + (' - tensor peak: burst (timed region %.0f ms)' % (timed_s * 1e3) if timed_s < 0.25
+                                          else ' - tensor peak: sustained (timed region %.0f ms)' % (timed_s * 1e3))
+    r['timing'] = ('CUDA events around every launch on the launching stream, over a second pass of the same steps '
+                   '(the events serialise launches, so `value` is timed without them)')
+    flops_dom = net.flops_per_domain()
+    r['whole_path'] = {'flop_per_subdomain': flops_dom, 'achieved_tflops': m['value'] / world * flops_dom / 1e12,
+                       'frac_of_bf16_peak': m['value'] / world * flops_dom / 1e12 / peak_tf, 'bf16_peak_used': peak_tf,
+                       'hbm_bytes_per_subdomain': r.pop('_bytes_per_subdomain'),
+                       'note': 'fp32 accuracy needs 3 fp16 MMA passes per product: the tensor ceiling is 1/3 of the bf16 peak'}
+    try:      # DRAM bytes per launch of that kernel class from the committed ncu --set full capture, scaled to this run's wave size
+        kt = json.load(open(os.path.join(ROOT, 'profiles', 'kernel_traffic.json')))
+        r['traffic'] = kt[r['kernel_class']]['dram_bytes_per_launch_per_subdomain'] * min(fr.B, scorer.get_option('workspace_domains'))
+        r['traffic_source'] = kt['_source']
+    except (OSError, ValueError, KeyError):
+        r['traffic'] = None
+    return r
+
+
 def main():
     args = parse()
     if args.impl == 'reference':
@@ -316,7 +464,10 @@ def main():
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    B = args.domains or DEFAULT_DOMAINS[args.workload]
+    # N = 1: BASELINE configs[1..3] (base x 1 024, or --workload wide / deep x 4 096).  N > 1: BASELINE configs[4], the 65 536-
+    # subdomain base frontier sharded contiguously over the N GPUs (strong scaling: the total is fixed)
+    strong = world > 1 and not args.domains and args.workload == 'base'
+    B = args.domains or (FRONTIER_TOTAL // world if strong else DEFAULT_DOMAINS[args.workload])
     K, W = args.steps, max(args.warmup, 0)
 
     net, lbs, ubs, wp, bp = load_problem(args.workload)
@@ -327,76 +478,24 @@ def main():
     if world > 1:      # the GNN parameters are broadcast once from rank 0, outside the timed region
         from gnn_branching_b200.dist import broadcast_gnn_weights
         broadcast_gnn_weights(model, src=0)
-    # two different frontiers used alternately: with the workspace they exceed the 126 MB L2 several times over
-    fronts = [synthetic_frontier(net, lbs, ubs, wp, bp, B, seed=1000 * (7 + rank) + i, device=dev) for i in range(2)]
+    # two different frontiers used alternately: with the workspace they exceed the 126 MB L2 several times over (a frontier of
+    # more than 8 192 subdomains is > 1 GB of inputs on its own: one is enough)
+    n_fronts = 2 if B <= 8192 else 1
+    fronts = [synthetic_frontier(net, lbs, ubs, wp, bp, B, seed=1000 * (7 + rank) + i, device=dev) for i in range(n_fronts)]
     scorer = model.scorer(local)
     for kv in args.opt:
         key, val = kv.split('=')
         scorer.set_option(key, int(val))
     math_mode = {0: 'tc', 1: 'simt'}[scorer.get_option('math')]
 
-    def step(i):
-        best, idx, _ = scorer_score(fronts[i % 2])
-        if world > 1:
-            best, idx = gather_winners(best, idx, B * world)
-        return best, idx
-
-    def scorer_score(fr):
-        scorer.set_network(fr.net, key=fr.net.key)
-        return scorer.score(fr, return_scores=False, check=False)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for i in range(W):
-        step(i)
-    scorer.check()
-    barrier()
-    launches0 = scorer.launches
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
-        run_timed(step, lambda i: scorer_score(fronts[i % 2]), K, barrier, ev0.record, ev1.record, clk.count, torch.cuda.synchronize)
-        launches = (scorer.launches - launches0) * K // (K + run_timed.extra)      # every step issues the same launches
-    scorer.check()
-    ms = ev0.elapsed_time(ev1)
-    # per-kernel-class durations: a second pass of K identical steps with CUDA events around every launch (on the launching
-    # stream).  The events serialise consecutive launches (no programmatic overlap of a kernel's prologue with its
-    # predecessor's tail), so the headline `value` above is measured without them
-    scorer.set_option('profile', 1)
-    scorer.profile_reset()
-    for i in range(K):
-        step(i)
-    scorer.check()
-    prof = scorer.profile_read()
-    scorer.set_option('profile', 0)
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    value = B * world * K / (ms * 1e-3)
+    m = measure_device(scorer, fronts, B, K, W, world, dev, local, gather_winners)
+    value, ms, launches, clocks = m['value'], m['ms'], m['launches'], m['clocks']
 
     # ---- end to end through the public API with pinned HOST buffers (copies inside the timed region) ----
     e2e = None
     if not args.no_e2e:
         host_fronts = [f.cpu().pin() for f in fronts]
-        for i in range(min(W, 2)):
-            model.score_frontier(host_fronts[i % 2], return_scores=False)
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(K):
-            hb, hi, _ = model.score_frontier(host_fronts[i % 2], return_scores=False)
-            if world > 1:
-                gather_winners(hb.to(dev), hi.to(dev), B * world)
-        barrier()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {'value': B * world * K / dt, 'unit': UNIT, 'h2d_bytes_per_step': host_fronts[0].input_bytes(),
-               'd2h_bytes_per_step': B * 8, 'api': 'GraphNet.score_frontier(pinned host Frontier)'}
+        e2e = measure_e2e(model, host_fronts, B, K, W, world, dev, gather_winners)
         del host_fronts
 
     if rank != 0:
@@ -404,31 +503,56 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel class, from live CUDA-event timings on the launching stream ----
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-    except (OSError, ValueError):
-        pass
-    peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
-    peak_gbs = peaks.get('hbm_gbs', 6650.0)
-    peak_src = 'MEASURED_PEAKS.json hbm_gbs / bf16_tflops_sustained (of measured)' if peaks else \
-        'B200_PROFILING.md fallback 6.65 TB/s / 1.4 PF sustained (of fallback)'
-    roofline = kernel_rooflines(net, fronts[0], prof, K * B, T=2, peak_tf=peak_tf, peak_gbs=peak_gbs)
-    roofline['peak_source'] = peak_src
-    roofline['timing'] = (f'CUDA events around every launch on the launching stream, over a second pass of the same {K} steps '
-                          '(the events serialise launches, so `value` is timed without them)')
-    flops_dom = net.flops_per_domain()
-    roofline['whole_path'] = {'flop_per_subdomain': flops_dom, 'achieved_tflops': value / world * flops_dom / 1e12,
-                              'frac_of_bf16_peak': value / world * flops_dom / 1e12 / peak_tf,
-                              'hbm_bytes_per_subdomain': roofline.pop('_bytes_per_subdomain'),
-                              'note': 'fp32 accuracy needs 3 fp16 MMA passes per product: the tensor ceiling is 1/3 of the bf16 peak'}
-    try:      # DRAM bytes per launch of that kernel class from the committed ncu --set full capture, scaled to this run's wave size
-        kt = json.load(open(os.path.join(ROOT, 'profiles', 'kernel_traffic.json')))
-        roofline['traffic'] = kt[roofline['kernel_class']]['dram_bytes_per_launch_per_subdomain'] * min(B, scorer.get_option('workspace_domains'))
-        roofline['traffic_source'] = kt['_source']
-    except (OSError, ValueError, KeyError):
-        roofline['traffic'] = None
+    peaks = load_peaks()
+    peak_gbs = peaks['gbs']
+    roofline = roofline_of(net, fronts[0], m, K * B, world, scorer, peaks)
+
+    # ---- B = 1 latency (the reference's native usage: one subdomain per call, plnn/relu_conv_gnnkwthreshold.py:117) ----
+    b1 = None
+    if world == 1:
+        one = fronts[0].slice(0, 1).contiguous()
+        one_host = one.cpu().pin()
+        for _ in range(5):
+            scorer.score(one, return_scores=False, check=False)
+            model.score_frontier(one_host, return_scores=False)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            scorer.score(one, return_scores=False, check=False)
+        e1.record()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(50):
+            model.score_frontier(one_host, return_scores=False)
+        torch.cuda.synchronize()
+        b1 = {'device_ms': e0.elapsed_time(e1) / 50, 'e2e_ms': (time.perf_counter() - t0) / 50 * 1e3,
+              'note': 'one subdomain per call; device_ms: inputs resident, CUDA events; e2e_ms: pinned host inputs, winners read back'}
+        del one, one_host
+
+    # ---- BASELINE configs[2] and [3] (wide / deep x 4 096) as secondary objects of the default line ----
+    others = {}
+    if world == 1 and args.workload == 'base' and not args.domains and not args.no_secondary:
+        del fronts
+        torch.cuda.empty_cache()
+        for wl in ('wide', 'deep'):
+            try:
+                net2, lbs2, ubs2, wp2, bp2 = load_problem(wl)
+                B2 = DEFAULT_DOMAINS[wl]
+                fr2 = [synthetic_frontier(net2, lbs2, ubs2, wp2, bp2, B2, seed=1000 * (17 + i) + len(wl), device=dev) for i in range(2)]
+                m2 = measure_device(scorer, fr2, B2, 20, 3, 1, dev, local, gather_winners)
+                hf2 = [fr2[0].cpu().pin()]
+                e2 = measure_e2e(model, hf2, B2, 3, 1, 1, dev, gather_winners)
+                del hf2
+                others[wl] = {'value': m2['value'], 'unit': UNIT, 'ms_per_step': m2['ms'] / 20, 'steps': 20, 'warmup': 3,
+                              'workload': f'cifar_{wl}_kw x {B2} synthetic subdomains per step', 'gpu_launches': m2['launches'],
+                              'clocks': m2['clocks'], 'e2e': e2, 'roofline': roofline_of(net2, fr2[0], m2, 20 * B2, 1, scorer, peaks)}
+                del fr2
+                torch.cuda.empty_cache()
+            except Exception as e:          # a secondary object must never take the headline down
+                others[wl] = {'error': repr(e)[:300]}
+        fronts = [synthetic_frontier(net, lbs, ubs, wp, bp, B, seed=1000 * (7 + rank) + i, device=dev) for i in range(n_fronts)]
+        scorer.set_network(net, key=net.key)
 
     # ---- the BaBSR / KW heuristic on the same frontier (secondary line, not the headline metric) ----
     babsr = None
@@ -524,40 +648,28 @@ def main():
     cb = None
     if not args.no_cpu_baseline and world == 1:
         cb, _ = cpu_baseline(args.workload, args.weights)
-        # the reference's native deployment is eager PyTorch on the GPU (graph_score.py:13): the same restatement with CUDA
-        # tensors, B = 1 (its native usage) and B = 32 — library kernels, a reported baseline like the CPU figure
-        try:
-            from oracle import graphnet_oracle as O
-            sdg = {k: v.to(dev) for k, v in load_weights(args.weights).items()}
-            f1, f32 = fronts[0].slice(0, 1).to(dev), fronts[0].slice(0, min(32, B)).to(dev)
-            with torch.no_grad():
-                for f in (f1, f32):
-                    O.gnn_forward(sdg, f)
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                for _ in range(3):
-                    O.gnn_forward(sdg, f1)
-                torch.cuda.synchronize()
-                lat1 = (time.perf_counter() - t0) / 3
-                t0 = time.perf_counter()
-                for _ in range(3):
-                    O.gnn_forward(sdg, f32)
-                torch.cuda.synchronize()
-                t32 = (time.perf_counter() - t0) / 3
-            cb['eager_pytorch_on_gpu'] = {'value': f32.B / t32, 'unit': UNIT, 'batch': f32.B, 'b1_latency_ms': lat1 * 1e3,
-                                          'note': 'oracle/graphnet_oracle.py with CUDA tensors (torch eager: cuDNN / cuBLAS kernels)'}
-        except Exception as e:          # a baseline must never take the bench line down
-            cb['eager_pytorch_on_gpu'] = {'error': repr(e)[:300]}
+        # the reference's native deployment is eager PyTorch on the GPU (graph_score.py:13): the unmodified module (oracle/_ref)
+        # with CUDA tensors at B = 1 (its native usage), 32 and 1 024 — library kernels, a reported baseline like the CPU figure
+        eg = _run_ref_runner('cuda', args.workload, args.weights, (1, 32, 1024), 3, 1, timeout=600)
+        if eg and 'error' not in eg:
+            cb['eager_pytorch_on_gpu'] = {'value': eg['value'], 'unit': UNIT, 'best_batch': eg['best_batch'], 'b1_latency_ms': eg['b1_latency_ms'],
+                                          'rate_by_batch': {k: v['rate'] for k, v in eg['per_batch'].items()}, 'kind': 'reference',
+                                          'note': 'unmodified graphnet/graph_conv.py GraphNet.forward (oracle/_ref) on this B200, torch eager '
+                                                  '(cuDNN / cuBLAS kernels), own process'}
+        else:
+            cb['eager_pytorch_on_gpu'] = eg or {'error': 'oracle/_ref is not staged'}
 
+    wl_name = (f'cifar_base_kw frontier of {B * world} synthetic subdomains sharded across {world} GPUs ({B} per GPU per step)' if strong
+               else f'cifar_{args.workload}_kw x {B} synthetic subdomains per GPU per step')
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
-            'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'strong' if strong else 'weak', 'vs_baseline': None,
             'dtype': 'fp16x3 (fp32 accumulate)' if math_mode == 'tc' else 'f32', 'data': 'synthetic',
-            'config': {'workload': f'cifar_{args.workload}_kw x {B} synthetic subdomains per GPU per step',
-                       'gnn': 'GraphNet(T=2,p=64)', 'weights': args.weights, 'math': math_mode,
-                       'chunk': scorer.get_option('workspace_domains'),
-                       'l2': 'two alternating frontiers; inputs + per-chunk workspace exceed the 126 MB L2',
+            'config': {'workload': wl_name, 'gnn': 'GraphNet(T=2,p=64)', 'weights': args.weights, 'math': math_mode,
+                       'chunk': scorer.get_option('workspace_domains'), 'fuse': scorer.get_option('fuse'),
+                       'l2': f'{n_fronts} frontier(s) of {B} subdomains used alternately; inputs + per-wave workspace exceed the 126 MB L2',
                        'sharding': f'{world} ranks x {B} subdomains, winners all-gathered (8 B/subdomain)'},
-            'clocks': clk.summary(), 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cb,
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cb,
+            'b1_latency_ms': b1, 'wide': others.get('wide'), 'deep': others.get('deep'),
             'babsr': babsr, 'online': online, 'queue': queue}
     print(json.dumps(line))
     if world > 1:

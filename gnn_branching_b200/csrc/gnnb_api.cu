@@ -31,13 +31,8 @@ struct gnnb_ctx {
     int math = GNNB_MATH_TC_FP16X3;
     int chunk = 0;
     int snapshot = 0;
-    int fuse = 0;                   // propagation + node update of a layer in one launch (tensor-core mode); measured 3-4 % slower than two launches
-    int prop_share = 0;             // % of a fused launch's CTAs that propagate; 0 = cost model
+    int fuse = 1;                   // propagation + node update of a layer in one launch, nb handed over in tensor memory (k_tc_fused); 0 = two launches
     int gather_prefetch = 0;        // propagation kernel variant that fetches the gather indices one chunk ahead (not validated on a GPU yet)
-    int32_t* d_flags = nullptr;     // per-item publication flags of the fused launches; value = epoch of the launch
-    int32_t epoch = 0;
-    int32_t consumed_base = 0;      // host mirror of the device progress counter d_flags[-1] at the next fused launch
-    int lead = 256;                 // items the propagation side of a fused launch may run ahead (nb images in flight: lead * 128 KB)
     // GNN parameters
     bool have_gnn = false;
     float* d_gnn = nullptr;
@@ -70,6 +65,7 @@ struct gnnb_ctx {
     const float** d_ptrs = nullptr;   // [2 * (L + 2)] lb pointers then ub pointers
     std::vector<int> hidden_off;    // offset of layer k (1-based) in the flat ReLU index
     int n_hidden = 0;
+    std::vector<struct gnnb_queue*> queues;      // live gnnb_queue objects: they were sized for the current network
     // workspace
     int ws_cap = 0;                 // subdomains the workspace can hold
     bool ws_host_staging = false;
@@ -107,6 +103,11 @@ struct gnnb_ctx {
     int64_t prof_rows[GNNB_K_COUNT] = {0};
 };
 
+struct gnnb_queue {
+    gnnb_ctx* ctx;                  // null once the context has been destroyed (the queue's own device memory stays valid)
+    DomainQueue* q;
+};
+
 namespace {
 
 int fail(gnnb_ctx* c, int status, const std::string& msg) {
@@ -138,7 +139,7 @@ int ensure_workspace(gnnb_ctx* ctx, int Bc, bool host_staging) {
     int nmax = 0;
     for (int k = 0; k <= L; ++k) nmax = ctx->n[k] > nmax ? ctx->n[k] : nmax;
     size_t total = 0;
-    auto take = [&](size_t elems) { size_t off = total; total += align4(elems) + 64; return off; };
+    auto take = [&](size_t elems) { size_t off = total; total += (elems + 63) & ~size_t(63); return off; };      // 256-byte aligned (32-byte sector stores, bulk copies)
     std::vector<size_t> o_mu(L + 2), o_rf(L + 1), o_rb(L + 1), o_lb(L + 2), o_ub(L + 2), o_du(L), o_pr(L), o_po(L);
     // mu, nb and relax' are stored per tile of 128 rows by the tensor-core kernels: round the row counts up
     // rows of a layer in the workspace: slots (multiple of 128 per subdomain) >= nodes, so the SIMT path's node-order rows fit too
@@ -153,12 +154,6 @@ int ensure_workspace(gnnb_ctx* ctx, int Bc, bool host_staging) {
     size_t nb_rows = 0;
     for (int k = 0; k <= L; ++k) nb_rows = wrows(k) > nb_rows ? wrows(k) : nb_rows;
     const size_t o_nb = take(nb_rows * P);
-    size_t max_items = 0;
-    for (int k = 0; k <= L; ++k) {
-        const size_t items = (size_t)(ctx->rowmap[k].nslots / 128) * ((Bc + 3) / 4);
-        max_items = items > max_items ? items : max_items;
-    }
-    const size_t o_flags = take(max_items + 1);          // + the progress counter
     const size_t o_sc = take((size_t)Bc * ctx->n_hidden);
     const size_t o_best = take(Bc), o_idx = take(Bc);
     struct StgOff { std::vector<size_t> lb, ub, du, pr, po; size_t pout, pin, wp, bp, mask, best, idx, sc; } so[2];
@@ -188,11 +183,6 @@ int ensure_workspace(gnnb_ctx* ctx, int Bc, bool host_staging) {
         ctx->amb_base[k] = reinterpret_cast<int32_t*>(base + o_ab[k]);
         ctx->amb_rows[k] = reinterpret_cast<int32_t*>(base + o_ar[k]);
     }
-    ctx->d_flags = reinterpret_cast<int32_t*>(base + o_flags);
-    CU(cudaMemset(ctx->d_flags, 0, (max_items + 1) * sizeof(int32_t)));
-    ctx->d_flags += 1;                                   // d_flags[-1] is the counter
-    ctx->epoch = 0;
-    ctx->consumed_base = 0;
     ctx->nb = base + o_nb; ctx->ws_scores = base + o_sc; ctx->ws_best = base + o_best;
     ctx->ws_idx = reinterpret_cast<int32_t*>(base + o_idx);
     if (host_staging) {
@@ -342,9 +332,8 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
             const int64_t rows = R(k), nodes = (int64_t)Bc * ctx->n[k];
             if (fused) {
                 ProfScope ps(ctx, GNNB_K_LAYER_FWD, nodes, st);
-                tc_layer(g, ctx->plan_fwd[k - 1], ctx->mu[k - 1], false, in.lb[k], in.ub[k], ctx->nb, ctx->relax_f[k], ctx->amb_base[k],
-                         ctx->mu[k], nullptr, M(k), 0, 0, rows, ctx->d_nan, ctx->d_flags, ++ctx->epoch, ctx->prop_share,
-                         ctx->d_flags - 1, &ctx->consumed_base, ctx->lead, st, lc);
+                tc_fused(g, ctx->plan_fwd[k - 1], ctx->mu[k - 1], false, in.lb[k], in.ub[k], ctx->relax_f[k], ctx->amb_base[k],
+                         ctx->mu[k], nullptr, M(k), 0, 0, rows, ctx->d_nan, ctx->snapshot ? ctx->nb : nullptr, st, lc);
             } else {
                 ProfScope ps(ctx, GNNB_K_PROP_FWD, nodes, st);
                 if (tc) prop_tc_run(ctx->plan_fwd[k - 1], ctx->mu[k - 1], ctx->nb, Bc, st, lc, ctx->gather_prefetch);
@@ -373,9 +362,8 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
             const bool fused_k = fused && k < L;           // the property layer's rank-1 back-propagation is a separate small kernel
             if (fused_k) {
                 ProfScope ps(ctx, last ? GNNB_K_LAYER_BWD_SCORE : GNNB_K_LAYER_BWD, nodes, st);
-                tc_layer(g, ctx->plan_bwd[k], ctx->mu[k + 1], true, in.lb[k], in.ub[k], ctx->nb, ctx->relax_b[k], ctx->amb_base[k],
-                         mu_k, sc, M(k), ctx->n_hidden, ctx->hidden_off[k], rows, ctx->d_nan, ctx->d_flags, ++ctx->epoch,
-                         ctx->prop_share, ctx->d_flags - 1, &ctx->consumed_base, ctx->lead, st, lc);
+                tc_fused(g, ctx->plan_bwd[k], ctx->mu[k + 1], true, in.lb[k], in.ub[k], ctx->relax_b[k], ctx->amb_base[k],
+                         mu_k, sc, M(k), ctx->n_hidden, ctx->hidden_off[k], rows, ctx->d_nan, ctx->snapshot ? ctx->nb : nullptr, st, lc);
             } else {
                 ProfScope ps(ctx, GNNB_K_PROP_BWD, nodes, st);
                 if (k == L && tc) prop_tc_property_backward(in.wp, ctx->mu[L + 1], ctx->nb, ctx->n[L], ctx->rowmap[L].nslots, Bc, st, lc);
@@ -569,6 +557,7 @@ int gnnb_create(gnnb_ctx** out, int device) {
         cudaMemset(ctx->d_nan, 0, sizeof(unsigned long long)) != cudaSuccess ||
         simt_init() != 0 || prop_init(64 * 1024) != 0 || tc_init() != 0 || prop_tc_init() != 0 || train_init() != 0) {
         fprintf(stderr, "libgnnb: initialisation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+        if (ctx->d_nan) cudaFree(ctx->d_nan);
         delete ctx;
         return GNNB_ERR_CUDA;
     }
@@ -600,6 +589,7 @@ void gnnb_destroy(gnnb_ctx* ctx) {
     for (int i = 0; i < 2; ++i) { if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]); if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]); }
     for (auto& p : ctx->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    for (gnnb_queue* q : ctx->queues) q->ctx = nullptr;
     delete ctx;
 }
 
@@ -618,6 +608,7 @@ int gnnb_set_gnn_weights(gnnb_ctx* ctx, const float* const* tensors, const int64
 
 int gnnb_set_network(gnnb_ctx* ctx, const gnnb_layer_desc* layers, int n_layers, int c0, int h0, int w0) {
     if (!ctx || !layers || n_layers < 1) return fail(ctx, GNNB_ERR_INVALID, "null argument");
+    if (!ctx->queues.empty()) return fail(ctx, GNNB_ERR_STATE, "gnnb_set_network while domain queues of the previous network exist");
     CU(cudaSetDevice(ctx->device));
     std::vector<LayerDev> devs(n_layers);
     std::vector<int> n(n_layers + 2);
@@ -670,61 +661,89 @@ int gnnb_set_network(gnnb_ctx* ctx, const gnnb_layer_desc* layers, int n_layers,
         const int per = d.kind == GNNB_LAYER_CONV ? d.h_out * d.w_out : 1;     // graph_conv.py:122-124
         for (int j = 0; j < L.n_out; ++j) blob[o_b[k] + j] = d.bias[j / per];
     }
-    free_workspace(ctx);
-    if (ctx->d_net) cudaFree(ctx->d_net);
-    ctx->d_net = nullptr;
-    CU(cudaMalloc(&ctx->d_net, total * sizeof(float)));
-    CU(cudaMemcpy(ctx->d_net, blob.data(), total * sizeof(float), cudaMemcpyHostToDevice));
-    for (int k = 0; k < n_layers; ++k) { devs[k].weight = ctx->d_net + o_w[k]; devs[k].bias_node = ctx->d_net + o_b[k]; }
-    for (PropPlan* p : ctx->plan_fwd) prop_plan_free(p);
-    for (PropPlan* p : ctx->plan_bwd) prop_plan_free(p);
-    ctx->plan_fwd.assign(n_layers, nullptr);
-    ctx->plan_bwd.assign(n_layers, nullptr);
+    // Transactional: everything the new network needs is built into locals first; the context is only touched once every
+    // allocation, copy and plan has succeeded, so a failure leaves the previous network (if any) fully usable.
+    struct Staged {
+        float* d_net = nullptr;
+        int32_t* d_maps = nullptr;
+        LayerDev* d_layers = nullptr;
+        int32_t *d_hidden_off = nullptr, *d_random_order = nullptr;
+        const float** d_ptrs = nullptr;
+        std::vector<PropPlan*> plan_fwd, plan_bwd;
+        bool keep = false;
+        ~Staged() {
+            if (keep) return;
+            if (d_net) cudaFree(d_net);
+            if (d_maps) cudaFree(d_maps);
+            if (d_layers) cudaFree(d_layers);
+            if (d_hidden_off) cudaFree(d_hidden_off);
+            if (d_random_order) cudaFree(d_random_order);
+            if (d_ptrs) cudaFree(d_ptrs);
+            for (PropPlan* p : plan_fwd) prop_plan_free(p);
+            for (PropPlan* p : plan_bwd) prop_plan_free(p);
+        }
+    } sg;
+    CU(cudaMalloc(&sg.d_net, total * sizeof(float)));
+    CU(cudaMemcpy(sg.d_net, blob.data(), total * sizeof(float), cudaMemcpyHostToDevice));
+    for (int k = 0; k < n_layers; ++k) { devs[k].weight = sg.d_net + o_w[k]; devs[k].bias_node = sg.d_net + o_b[k]; }
+    sg.plan_fwd.assign(n_layers, nullptr);
+    sg.plan_bwd.assign(n_layers, nullptr);
     // slot order of layers 0..L (gnnb_common.cuh) and the device copies of the slot -> node maps
-    ctx->tiling.assign(n_layers + 1, LayerTiling());
-    ctx->tiling[0] = make_tiling(c0, h0, w0);
+    std::vector<LayerTiling> tiling(n_layers + 1);
+    std::vector<RowMap> rowmap(n_layers + 1, RowMap{nullptr, 0, 0});
+    tiling[0] = make_tiling(c0, h0, w0);
     for (int k = 0; k < n_layers; ++k)
-        ctx->tiling[k + 1] = devs[k].kind == GNNB_LAYER_CONV ? make_tiling(devs[k].c_out, devs[k].h_out, devs[k].w_out)
-                                                            : make_tiling(devs[k].n_out, 1, 1);
+        tiling[k + 1] = devs[k].kind == GNNB_LAYER_CONV ? make_tiling(devs[k].c_out, devs[k].h_out, devs[k].w_out)
+                                                       : make_tiling(devs[k].n_out, 1, 1);
     {
         size_t total_slots = 0;
-        for (const LayerTiling& t : ctx->tiling) total_slots += t.node_of_slot.size();
-        if (ctx->d_maps) cudaFree(ctx->d_maps);
-        ctx->d_maps = nullptr;
-        CU(cudaMalloc(&ctx->d_maps, total_slots * sizeof(int32_t)));
-        ctx->rowmap.assign(n_layers + 1, RowMap{nullptr, 0, 0});
+        for (const LayerTiling& t : tiling) total_slots += t.node_of_slot.size();
+        CU(cudaMalloc(&sg.d_maps, total_slots * sizeof(int32_t)));
         size_t off = 0;
         for (int k = 0; k <= n_layers; ++k) {
-            const LayerTiling& t = ctx->tiling[k];
-            CU(cudaMemcpy(ctx->d_maps + off, t.node_of_slot.data(), t.node_of_slot.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-            ctx->rowmap[k] = RowMap{ctx->d_maps + off, n[k], (int)t.node_of_slot.size()};
+            const LayerTiling& t = tiling[k];
+            CU(cudaMemcpy(sg.d_maps + off, t.node_of_slot.data(), t.node_of_slot.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+            rowmap[k] = RowMap{sg.d_maps + off, n[k], (int)t.node_of_slot.size()};
             off += t.node_of_slot.size();
         }
     }
     for (int k = 0; k < n_layers; ++k) {
         // layer 0's transpose feeds the input nodes and is not normalised (graph_conv.py:361-372); the others are (:299-318)
-        ctx->plan_fwd[k] = prop_plan_build(devs[k], layers[k].weight, false, false, ctx->tiling[k + 1], ctx->tiling[k]);
-        ctx->plan_bwd[k] = prop_plan_build(devs[k], layers[k].weight, true, k > 0, ctx->tiling[k], ctx->tiling[k + 1]);
-        if (!ctx->plan_fwd[k] || !ctx->plan_bwd[k]) return fail(ctx, GNNB_ERR_CUDA, "building the propagation plans failed");
+        sg.plan_fwd[k] = prop_plan_build(devs[k], layers[k].weight, false, false, tiling[k + 1], tiling[k]);
+        sg.plan_bwd[k] = prop_plan_build(devs[k], layers[k].weight, true, k > 0, tiling[k], tiling[k + 1]);
+        if (!sg.plan_fwd[k] || !sg.plan_bwd[k]) return fail(ctx, GNNB_ERR_CUDA, "building the propagation plans failed");
     }
-    ctx->layers = devs;
-    ctx->n = n;
-    ctx->hidden_off.assign(n_layers + 2, 0);
-    int off = 0;
-    for (int k = 1; k <= n_layers; ++k) { ctx->hidden_off[k] = off; off += n[k]; }
-    ctx->n_hidden = off;
+    std::vector<int> hidden_off(n_layers + 2, 0);
+    int n_hidden = 0;
+    for (int k = 1; k <= n_layers; ++k) { hidden_off[k] = n_hidden; n_hidden += n[k]; }
     // tables of the BaBSR kernel
+    CU(cudaMalloc(&sg.d_layers, n_layers * sizeof(LayerDev)));
+    CU(cudaMemcpy(sg.d_layers, devs.data(), n_layers * sizeof(LayerDev), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&sg.d_hidden_off, (n_layers + 1) * sizeof(int32_t)));
+    CU(cudaMemcpy(sg.d_hidden_off, hidden_off.data() + 1, (n_layers + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&sg.d_random_order, n_layers * sizeof(int32_t)));
+    CU(cudaMalloc(&sg.d_ptrs, 2 * (n_layers + 2) * sizeof(float*)));
+    // ---- commit: nothing below can fail ----
+    CU(cudaDeviceSynchronize());                 // no kernel of an earlier call may still read the old tables
+    ctx->have_net = false;
+    free_workspace(ctx);
+    if (ctx->d_net) cudaFree(ctx->d_net);
+    if (ctx->d_maps) cudaFree(ctx->d_maps);
     if (ctx->d_layers) cudaFree(ctx->d_layers);
     if (ctx->d_hidden_off) cudaFree(ctx->d_hidden_off);
     if (ctx->d_random_order) cudaFree(ctx->d_random_order);
     if (ctx->d_ptrs) cudaFree(ctx->d_ptrs);
-    ctx->d_layers = nullptr; ctx->d_hidden_off = nullptr; ctx->d_random_order = nullptr; ctx->d_ptrs = nullptr;
-    CU(cudaMalloc(&ctx->d_layers, n_layers * sizeof(LayerDev)));
-    CU(cudaMemcpy(ctx->d_layers, devs.data(), n_layers * sizeof(LayerDev), cudaMemcpyHostToDevice));
-    CU(cudaMalloc(&ctx->d_hidden_off, (n_layers + 1) * sizeof(int32_t)));
-    CU(cudaMemcpy(ctx->d_hidden_off, ctx->hidden_off.data() + 1, (n_layers + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
-    CU(cudaMalloc(&ctx->d_random_order, n_layers * sizeof(int32_t)));
-    CU(cudaMalloc(&ctx->d_ptrs, 2 * (n_layers + 2) * sizeof(float*)));
+    for (PropPlan* p : ctx->plan_fwd) prop_plan_free(p);
+    for (PropPlan* p : ctx->plan_bwd) prop_plan_free(p);
+    sg.keep = true;
+    ctx->d_net = sg.d_net; ctx->d_maps = sg.d_maps; ctx->d_layers = sg.d_layers; ctx->d_hidden_off = sg.d_hidden_off;
+    ctx->d_random_order = sg.d_random_order; ctx->d_ptrs = sg.d_ptrs;
+    ctx->plan_fwd = sg.plan_fwd; ctx->plan_bwd = sg.plan_bwd;
+    ctx->tiling = tiling; ctx->rowmap = rowmap;
+    ctx->layers = devs;
+    ctx->n = n;
+    ctx->hidden_off = hidden_off;
+    ctx->n_hidden = n_hidden;
     ctx->have_net = true;
     return GNNB_OK;
 }
@@ -744,12 +763,6 @@ int gnnb_set_option(gnnb_ctx* ctx, const char* key, int64_t value) {
     } else if (k == "gather_prefetch") {
         if (value < 0 || value > 2) return fail(ctx, GNNB_ERR_INVALID, "gather_prefetch is 0, 1 or 2");
         ctx->gather_prefetch = (int)value;
-    } else if (k == "prop_share") {
-        if (value < 0 || value > 99) return fail(ctx, GNNB_ERR_INVALID, "prop_share is a percentage in [0, 99]");
-        ctx->prop_share = (int)value;
-    } else if (k == "lead") {
-        if (value < 0) return fail(ctx, GNNB_ERR_INVALID, "lead must be >= 0");
-        ctx->lead = (int)value;
     } else if (k == "snapshot") {
         ctx->snapshot = value ? 1 : 0;
     } else if (k == "profile") {
@@ -767,9 +780,7 @@ int64_t gnnb_get_option(gnnb_ctx* ctx, const char* key) {
     if (k == "chunk") return ctx->chunk;
     if (k == "snapshot") return ctx->snapshot;
     if (k == "fuse") return ctx->fuse;
-    if (k == "prop_share") return ctx->prop_share;
     if (k == "gather_prefetch") return ctx->gather_prefetch;
-    if (k == "lead") return ctx->lead;
     if (k == "profile") return ctx->profile;
     if (k == "n_hidden") return ctx->n_hidden;
     if (k == "workspace_domains") return ctx->ws_cap;
@@ -1039,10 +1050,6 @@ int gnnb_adam_reset(gnnb_ctx* ctx) {
     return GNNB_OK;
 }
 
-struct gnnb_queue {
-    gnnb_ctx* ctx;
-    DomainQueue* q;
-};
 
 int gnnb_queue_create(gnnb_ctx* ctx, int64_t capacity, gnnb_queue** out) {
     if (!ctx || !out || capacity < 1) return fail(ctx, GNNB_ERR_INVALID, "bad argument");
@@ -1054,12 +1061,17 @@ int gnnb_queue_create(gnnb_ctx* ctx, int64_t capacity, gnnb_queue** out) {
     const int rc = queue_create(ctx->device, ctx->n, ctx->n_hidden, capacity, &q, &err);
     if (rc != GNNB_OK) return fail(ctx, rc, err);
     *out = new gnnb_queue{ctx, q};
+    ctx->queues.push_back(*out);
     return GNNB_OK;
 }
 
 void gnnb_queue_destroy(gnnb_queue* q) {
     if (!q) return;
     queue_destroy(q->q);
+    if (q->ctx) {
+        auto& v = q->ctx->queues;
+        for (size_t i = 0; i < v.size(); ++i) if (v[i] == q) { v.erase(v.begin() + i); break; }
+    }
     delete q;
 }
 
@@ -1107,7 +1119,7 @@ int view_domains(gnnb_queue* q, const gnnb_domains* d, const uint8_t* keep, bool
 }  // namespace
 
 int gnnb_queue_add(gnnb_queue* q, const gnnb_domains* d, const uint8_t* keep, int32_t* added, void* stream) {
-    if (!q || !d || !added) return GNNB_ERR_INVALID;
+    if (!q || !d || !added || !q->ctx) return GNNB_ERR_INVALID;
     gnnb_ctx* ctx = q->ctx;
     *added = 0;
     if (d->B < 0) return fail(ctx, GNNB_ERR_INVALID, "negative batch");
@@ -1126,7 +1138,7 @@ int gnnb_queue_add(gnnb_queue* q, const gnnb_domains* d, const uint8_t* keep, in
 }
 
 int gnnb_queue_pick(gnnb_queue* q, float threshold, int32_t discard_rest, gnnb_domains* out, int32_t* picked, void* stream) {
-    if (!q || !out || !picked) return GNNB_ERR_INVALID;
+    if (!q || !out || !picked || !q->ctx) return GNNB_ERR_INVALID;
     gnnb_ctx* ctx = q->ctx;
     *picked = 0;
     if (out->B < 0) return fail(ctx, GNNB_ERR_INVALID, "negative batch");
@@ -1161,7 +1173,7 @@ int gnnb_queue_pick(gnnb_queue* q, float threshold, int32_t discard_rest, gnnb_d
 }
 
 int gnnb_queue_prune(gnnb_queue* q, float threshold, void* stream) {
-    if (!q) return GNNB_ERR_INVALID;
+    if (!q || !q->ctx) return GNNB_ERR_INVALID;
     gnnb_ctx* ctx = q->ctx;
     CU(cudaSetDevice(ctx->device));
     const int rc = queue_prune(q->q, threshold, (cudaStream_t)stream, &ctx->launches);
@@ -1170,7 +1182,7 @@ int gnnb_queue_prune(gnnb_queue* q, float threshold, void* stream) {
 }
 
 int gnnb_queue_stats(gnnb_queue* q, int64_t* size, float* global_lb, void* stream) {
-    if (!q) return GNNB_ERR_INVALID;
+    if (!q || !q->ctx) return GNNB_ERR_INVALID;
     gnnb_ctx* ctx = q->ctx;
     if (size) *size = queue_size(q->q);
     if (global_lb && queue_size(q->q) > 0) {

@@ -120,15 +120,12 @@ void tc_relax(const GnnParams& g, const NodeInputs& in, float* relax_f, float* r
 void tc_update(const GnnParams& g, bool backward, const float* lb, const float* ub, const float* nb, const float* relax,
                const int32_t* amb_base, float* mu_out, float* scores, RowMap map, int64_t score_stride, int64_t score_off, int64_t rows,
                unsigned long long* nan_count, cudaStream_t st, int64_t* launches);
-// propagation (plan) + node update of one layer in one launch; flags: >= tiles * ceil(Bc / 4) ints owned by the caller,
-// epoch: a value no earlier launch used with this flag buffer; prop_share_pct: 0 = cost model, else % of the CTAs that propagate;
-// consumed / consumed_base / lead: device progress counter of the update side, its expected value at launch (advanced by the
-// call), and how many items the propagation may run ahead (0 = unbounded)
+// propagation (plan) + node update of one layer in ONE launch: the neighbour embeddings go from the propagation accumulator
+// to the update chain through tensor memory and are never written (k_tc_fused); nb_dbg: the nb tile images for snapshots, or null
 struct PropPlan;
-void tc_layer(const GnnParams& g, const PropPlan* plan, const float* mu_in, bool backward, const float* lb, const float* ub,
-              float* nb, const float* relax, const int32_t* amb_base, float* mu_out, float* scores, RowMap map, int64_t score_stride,
-              int64_t score_off, int64_t rows, unsigned long long* nan_count, int32_t* flags, int32_t epoch, int prop_share_pct,
-              int32_t* consumed, int32_t* consumed_base, int lead, cudaStream_t st, int64_t* launches);
+void tc_fused(const GnnParams& g, const PropPlan* plan, const float* mu_in, bool backward, const float* lb, const float* ub,
+              const float* relax, const int32_t* amb_base, float* mu_out, float* scores, RowMap map, int64_t score_stride, int64_t score_off,
+              int64_t rows, unsigned long long* nan_count, float* nb_dbg, cudaStream_t st, int64_t* launches);
 // slot of every ambiguous row of a layer, in row order: amb_base[tile] (+ the rank inside the tile), amb_rows[slot] = row;
 // cnt is scratch of ntiles + 1 ints (three small launches: count per tile, scan, fill)
 void amb_compact(const float* lb, const float* ub, RowMap map, int64_t rows, int32_t* cnt, int32_t* amb_base, int32_t* amb_rows,

@@ -1,5 +1,5 @@
-// Device side of the tensor-core propagation (gather-GEMM), shared by the stand-alone kernel (gnnb_prop_tc.cu) and the
-// fused propagation + node-update launch (gnnb_tc.cu).
+// Device side of the stand-alone tensor-core propagation (gather-GEMM, gnnb_prop_tc.cu) and the plan format it shares with
+// the fused propagation + node-update kernel (gnnb_tc.cu, k_tc_fused).
 #pragma once
 
 #include "gnnb_umma.cuh"
@@ -21,15 +21,6 @@ struct PropPlanDev {
 struct PropPlan;
 const PropPlanDev& prop_plan_dev(const PropPlan* p);
 double prop_plan_chunks_per_tile(const PropPlan* p);
-
-__device__ __forceinline__ void flag_release(int32_t* f, int32_t v) {
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(f), "r"(v) : "memory");
-}
-__device__ __forceinline__ int32_t flag_acquire(const int32_t* f) {
-    int32_t v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-    return v;
-}
 
 namespace prop {
 
@@ -65,13 +56,11 @@ using PropTail = PropTailT<W_STAGES, B_STAGES>;
 static_assert(sizeof(PropTailT<2, 5>) == sizeof(PropTail), "the 2 + 5 stage variant uses the same shared memory");
 constexpr size_t PROP_SMEM = 1024 + W_STAGES * W_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + sizeof(PropTail);
 
-// One CTA's share of a propagation launch: items rank, rank + nranks, ...  `flags` (may be null): after the nb tile images
-// of an item are written, flags[item] = epoch is released at GPU scope, for node-update CTAs of the same launch that
-// wait for exactly this item (gnnb_tc.cu, k_tc_layer); `consumed` (may be null) is their progress counter.  All threads of the block must call it (block-wide barriers).
+// One CTA's share of a propagation launch: items rank, rank + nranks, ...  All threads of the block must call it (block-wide
+// barriers).
 template <bool GATHER_PREFETCH = false, int WS = W_STAGES, int BS = B_STAGES>
 __device__ __forceinline__ void prop_body(const PropPlanDev& plan, const uint16_t* __restrict__ mu_img, uint16_t* __restrict__ nb_img,
-                                          int Bc, unsigned char* smem_raw, int rank, int nranks, int32_t* flags, int32_t epoch,
-                                          const int32_t* consumed = nullptr, int32_t consumed_base = 0, int lead = 0, bool pdl = false) {
+                                          int Bc, unsigned char* smem_raw, int rank, int nranks, bool pdl = false) {
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
     const uint32_t w_ring = smem_u32(base), b_ring = w_ring + WS * W_STAGE_BYTES;
     using Tail = PropTailT<WS, BS>;
@@ -242,12 +231,6 @@ __device__ __forceinline__ void prop_body(const PropPlanDev& plan, const uint16_
         long long g_wait = 0, g_all = clock64(), g0_;
 #endif
         for (int64_t item = rank; item < nitems; item += nranks) {
-            if (consumed != nullptr && item >= lead) {
-                // back-pressure of a fused launch: stay at most `lead` items ahead of the node-update CTAs, so that the
-                // nb images are still in L2 when they are read (every item is consumed by exactly 4 warpgroup-items)
-                const int32_t target = consumed_base + 4 * (int32_t)(item - lead);
-                while ((int32_t)(flag_acquire(consumed) - target) < 0) __nanosleep(200);
-            }
             const int tile = (int)(item % plan.ntiles);
             const int d = (int)(item / plan.ntiles) * PD + g;
             const bool dom_ok = d < Bc;
@@ -338,11 +321,6 @@ __device__ __forceinline__ void prop_body(const PropPlanDev& plan, const uint16_
 #ifdef GNNB_TRACE
             e_work += clock64() - e0_;
 #endif
-            if (flags != nullptr) {      // publish the item: every thread's stores, then one release store
-                __threadfence();
-                named_bar(1 + ew, 128);
-                if (m == 0) flag_release(flags + item, epoch);
-            }
         }
 #ifdef GNNB_TRACE
         if (rank == 1 && m == 0) printf("TRACE prop-epi wg %d: wait acc_full %lld, work %lld\n", ew, e_wait, e_work);

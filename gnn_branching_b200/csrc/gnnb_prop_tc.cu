@@ -31,7 +31,7 @@ namespace {
 __global__ void __launch_bounds__(prop::PROP_THREADS, 1) k_tc_prop(PropPlanDev plan, const uint16_t* __restrict__ mu_img,
                                                                    uint16_t* __restrict__ nb_img, int Bc) {
     extern __shared__ unsigned char smem_raw[];
-    prop::prop_body<false>(plan, mu_img, nb_img, Bc, smem_raw, (int)blockIdx.x, (int)gridDim.x, nullptr, 0, nullptr, 0, 0, true);
+    prop::prop_body<false>(plan, mu_img, nb_img, Bc, smem_raw, (int)blockIdx.x, (int)gridDim.x, true);
 }
 
 // the same kernel with the gather indices fetched one chunk ahead (option "gather_prefetch", off by default until it has been
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(prop::PROP_THREADS, 1) k_tc_prop(PropPlanDev p
 __global__ void __launch_bounds__(prop::PROP_THREADS, 1) k_tc_prop_pf(PropPlanDev plan, const uint16_t* __restrict__ mu_img,
                                                                       uint16_t* __restrict__ nb_img, int Bc) {
     extern __shared__ unsigned char smem_raw[];
-    prop::prop_body<true>(plan, mu_img, nb_img, Bc, smem_raw, (int)blockIdx.x, (int)gridDim.x, nullptr, 0, nullptr, 0, 0, true);
+    prop::prop_body<true>(plan, mu_img, nb_img, Bc, smem_raw, (int)blockIdx.x, (int)gridDim.x, true);
 }
 
 // ---- host-side plan construction ------------------------------------------------------------------------
@@ -177,7 +177,7 @@ LayerTiling make_tiling(int C, int H, int W) {
 __global__ void __launch_bounds__(prop::PROP_THREADS, 1) k_tc_prop_pf25(PropPlanDev plan, const uint16_t* __restrict__ mu_img,
                                                                         uint16_t* __restrict__ nb_img, int Bc) {
     extern __shared__ unsigned char smem_raw[];
-    prop::prop_body<true, 2, 5>(plan, mu_img, nb_img, Bc, smem_raw, (int)blockIdx.x, (int)gridDim.x, nullptr, 0, nullptr, 0, 0, true);
+    prop::prop_body<true, 2, 5>(plan, mu_img, nb_img, Bc, smem_raw, (int)blockIdx.x, (int)gridDim.x, true);
 }
 
 int prop_tc_init() {

@@ -65,6 +65,7 @@ struct WG {
     uint32_t ph_mma, ph_tma;
     uint32_t tmem;              // TMEM address: lane base of this warp, first column of this warpgroup
     uint32_t tmem0;             // lane 0, first column of this warpgroup (MMA operand / accumulator addresses)
+    uint32_t acol;              // first column of the A operand of the chained GEMMs, relative to tmem / tmem0
     int t;                      // thread index within the warpgroup = row of the tile this thread owns
     int wg;
     bool lead_warp;             // first warp of the warpgroup (warp-uniform): it issues the warpgroup's MMAs, one elected lane
@@ -75,7 +76,7 @@ __device__ __forceinline__ void wg_barrier(const WG& c) { named_bar(1 + c.wg, 12
 // 3 passes x 4 K steps with the A operand in tensor memory (issued by one thread)
 __device__ __forceinline__ void issue_ts(const WG& c, uint32_t b_hi, uint32_t b_lo, uint32_t N, uint32_t dcol, bool accumulate) {
     const uint32_t idesc = make_idesc(N);
-    const uint32_t d = c.tmem0 + dcol, a = c.tmem0 + ACOL;
+    const uint32_t d = c.tmem0 + dcol, a = c.tmem0 + c.acol;
 #pragma unroll
     for (int pass = 0; pass < 3; ++pass) {
         const uint64_t bd = make_desc(pass == 2 ? b_lo : b_hi);
@@ -146,7 +147,7 @@ __device__ __forceinline__ void a_store16(const WG& c, int ks, const float (&v)[
     uint32_t w[16];
 #pragma unroll
     for (int i = 0; i < 8; ++i) split2(v[2 * i], v[2 * i + 1], w[i], w[8 + i]);
-    tmem_st16(c.tmem + ACOL + 16 * ks, w);
+    tmem_st16(c.tmem + c.acol + 16 * ks, w);
 }
 
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -237,7 +238,7 @@ __device__ __forceinline__ bool epilogue_to_mu(const WG& c, uint32_t dcol, const
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(c.land + APLANE + off), "r"(w[8 + 4 * h]),
                          "r"(w[8 + 4 * h + 1]), "r"(w[8 + 4 * h + 2]), "r"(w[8 + 4 * h + 3]) : "memory");
         }
-        if (TO_A) tmem_st16(c.tmem + ACOL + 16 * q, w);
+        if (TO_A) tmem_st16(c.tmem + c.acol + 16 * q, w);
     }
     return bad && valid;
 }
@@ -247,15 +248,10 @@ __device__ __forceinline__ void commit_tile(const WG& c, void* dst_tile) {
     wg_barrier(c);
     if (c.t == 0) bulk_s2g(dst_tile, c.land, ABUF);
 }
-// request a tile's nb image into the landing buffer (one thread): after the previous tile's bulk store has read the
-// buffer and — in a fused launch — after the propagation CTA that produces the item has published it
-__device__ __forceinline__ void request_nb(const WG& c, const void* src, const int32_t* flag, int32_t epoch) {
+// request a tile's nb image into the landing buffer (one thread), after the previous tile's bulk store has read the buffer
+__device__ __forceinline__ void request_nb(const WG& c, const void* src) {
     if (c.t == 0) {
         bulk_wait_read();
-        if (flag != nullptr) {
-            while (flag_acquire(flag) != epoch) __nanosleep(100);
-            fence_proxy_async();         // the image was written with generic-proxy stores by another SM; the bulk copy reads it through the async proxy
-        }
         mbar_expect_tx(c.mbar_tma, ABUF);
         bulk_g2s(c.land, src, ABUF, c.mbar_tma);
     }
@@ -339,6 +335,7 @@ __device__ __forceinline__ WG make_wg(const CtaSetup& s, uint32_t wbytes) {
     c.mbar_tma = smem_u32(&s.tail->mbar[2 + 2 * c.wg]);
     c.ph_mma = 0;
     c.ph_tma = 0;
+    c.acol = ACOL;
     c.tmem0 = ((uint32_t)uniform((int)s.tmem_base) & 0x0000FFFFu) + (uint32_t)c.wg * WG_COLS;
     c.tmem = s.tmem_base + ((uint32_t)((c.t >> 5) * 32) << 16) + (uint32_t)c.wg * WG_COLS;
     return c;
@@ -368,14 +365,11 @@ struct UpdArgs {
     int64_t score_stride, score_off;
     int Bc;
     unsigned long long* nan_count;
-    int32_t* consumed;          // fused launches: progress counter of the node-update side (+1 per warpgroup-item), or null
 };
 
 // One CTA's share of a node-update launch.  Work items are the propagation's: item = group of 4 subdomains x tile, taken
-// rank, rank + nranks, ...; warpgroup w updates the tile of subdomain 4 * group + w.  `flags` (may be null): the item's nb
-// images are produced by a propagation CTA of the same launch; wait for flags[item] == epoch before loading them.
-__device__ __forceinline__ void update_body(const UpdArgs& a, unsigned char* smem_raw, int rank, int nranks, const int32_t* flags,
-                                            int32_t epoch, bool pdl = false) {
+// rank, rank + nranks, ...; warpgroup w updates the tile of subdomain 4 * group + w.
+__device__ __forceinline__ void update_body(const UpdArgs& a, unsigned char* smem_raw, int rank, int nranks, bool pdl = false) {
     const GnnParams& g = a.g;
     const int backward = a.backward;
     const float* __restrict__ lb = a.lb;
@@ -427,13 +421,12 @@ __device__ __forceinline__ void update_body(const UpdArgs& a, unsigned char* sme
         const float l = l_n, u = u_n;
         const int slot0 = slot0_n;
         if (dom >= a.Bc) {
-            if (a.consumed != nullptr && c.t == 0) atomicAdd(a.consumed, 1);
             fetch_row(item + nranks);
             continue;
         }
         const int64_t tile = (int64_t)dom * tiles_per_dom + item % tiles_per_dom;
         const int64_t row0 = tile * TILE, grow = row0 + c.t;
-        request_nb(c, nb_img + (size_t)tile * (ABUF / 2), flags ? flags + item : nullptr, epoch);
+        request_nb(c, nb_img + (size_t)tile * (ABUF / 2));
         fetch_row(item + nranks);
         const Ratio q = compute_ratio(l, u);
         const float gate = (q.r0 != 0.0f) ? 1.0f : 0.0f;
@@ -444,11 +437,9 @@ __device__ __forceinline__ void update_body(const UpdArgs& a, unsigned char* sme
         GNNB_TR(0);
         // D[0:128) = nb [W3a; W3b]^T
         gemm_ss(c, W + UPD_W3, W + UPD_W3 + 2 * WPLANE, 128, 0);
-        if (a.consumed != nullptr && c.t == 0) atomicAdd(a.consumed, 1);      // this tile's nb image has been read
         GNNB_TR(1);
-        // towards L2 while this tile runs its chain: the next tile's nb image (stand-alone launches: it was written by an
-        // earlier kernel) and this row's relax' pieces
-        if (flags == nullptr && c.t == 0 && item + nranks < nitems) {
+        // towards L2 while this tile runs its chain: the next tile's nb image and this row's relax' pieces
+        if (c.t == 0 && item + nranks < nitems) {
             const int64_t nitem = item + nranks;
             const int ndom = (int)(nitem / tiles_per_dom) * NWG + c.wg;
             if (ndom < a.Bc) prefetch_l2(nb_img + (size_t)((int64_t)ndom * tiles_per_dom + nitem % tiles_per_dom) * (ABUF / 2), ABUF);
@@ -538,20 +529,541 @@ __device__ __forceinline__ void update_body(const UpdArgs& a, unsigned char* sme
 }
 
 __global__ void __launch_bounds__(128 * NWG, 1) k_tc_update(UpdArgs a) {
-    update_body(a, smem_dyn(), (int)blockIdx.x, (int)gridDim.x, nullptr, 0, true);
+    update_body(a, smem_dyn(), (int)blockIdx.x, (int)gridDim.x, true);
 }
 
-// Propagation and node update of one layer in ONE launch: CTAs [0, n_prop) run the gather-GEMM, the others the update
-// chain; both walk the same (4 subdomains x tile) items, and an update CTA starts an item when the propagation CTA
-// that produces it has published its nb images (acquire / release flag per item) — the images are then still in L2, so
-// the nb round trip costs no HBM reads.  Propagation CTAs never wait for update CTAs and have the lowest block indices.
-__global__ void __launch_bounds__(128 * NWG, 1) k_tc_layer(PropPlanDev plan, const uint16_t* __restrict__ mu_in, UpdArgs a, int n_prop,
-                                                           int32_t* flags, int32_t epoch, int32_t consumed_base, int lead) {
-    if ((int)blockIdx.x < n_prop)
-        prop::prop_body(plan, mu_in, const_cast<uint16_t*>(a.nb_img), a.Bc, smem_dyn(), (int)blockIdx.x, n_prop, flags, epoch,
-                        a.consumed, consumed_base, lead);
-    else
-        update_body(a, smem_dyn(), (int)blockIdx.x - n_prop, (int)gridDim.x - n_prop, flags, epoch);
+// ---- fused layer: propagation gather-GEMM -> tensor memory -> node-update chain ------------------------------------------
+// One launch per (layer, sweep): the neighbour embeddings nb = A(mu) of a tile never leave the SM.  A persistent CTA (1 per
+// SM, 16 warps) walks items = (tile of 128 nodes) x (pair of subdomains); the propagation of item i + 1 runs while the two
+// chains of item i run (the propagation accumulator is double-buffered in tensor memory):
+//   warp 0      bulk copies of the item's propagation weight blocks (32 KB per 64-row K chunk)          -> W ring, 2 stages
+//   warps 2-5   gather: warp g copies 8 of the K step's 16 input-node rows of subdomain g & 1 with 16-byte cp.async from the
+//               mu images into the MN-major SWIZZLE_128B B operand (the row indices of the next chunk are fetched one chunk
+//               ahead)                                   -> B ring, 6 - 8 stages of one K step (16 rows x 2 subdomains x hi / lo)
+//   warp 1      tcgen05.mma M = 128, N = 128 (2 subdomains x 64 channels), K = 16, three fp16 hi / lo passes, into accumulator
+//               it & 1 (tensor-memory columns [128 (it & 1), +128)); tcgen05.commit frees ring stages and publishes it
+//   warps 8-15  two chain warpgroups (thread = row of the tile = TMEM lane); warpgroup j takes subdomain j of every item:
+//               tcgen05.ld of its 64 accumulator columns -> fp16 hi / lo split -> tcgen05.st back IN PLACE as the A operand
+//               of the chain (the same split the stand-alone propagation kernel writes to its nb image); then the update
+//               chain of k_tc_update with every GEMM in the TS form (A from tensor memory) and the warpgroup's 128 accumulator
+//               columns at [256 + 128 j, +128).  The new embeddings are staged per WARP (32 rows x 128 B of one plane = 4 KB,
+//               contiguous in the swizzled mu image) and leave with one bulk store per warp and plane — no warpgroup barrier,
+//               and the drain of 4 KB is short.
+// Tensor memory: 2 x 128 (propagation accumulators = the chains' A operands) + 2 x 128 (chain accumulators) = 512 columns.
+// Shared memory: chain weights 64 KB (80 KB with the score head) + W ring 64 KB + staging 32 KB + B ring 64 KB (48 KB).
+// Accumulator b is free for item i + 2 when both chains of item i have completed their last GEMM that reads its A columns
+// (acc_empty[b], 2 arrivals).
+namespace fz {
+constexpr int PD = 2;                               // subdomains per item = accumulator columns / 64
+constexpr int CW = 2;                               // chain warpgroups = PD
+constexpr int WS = 2;                               // weight ring stages
+constexpr int BS_MAX = 8;
+constexpr uint32_t W_STAGE = 2 * APLANE;            // 32 KB: one 64-row K chunk of the weight block, hi + lo plane
+constexpr uint32_t B_ROWS = 16;                     // input nodes per B stage = one K step
+constexpr uint32_t B_DOM = B_ROWS * 128;            // 2 KB: one plane of one subdomain
+constexpr uint32_t B_PLANE = PD * B_DOM;            // 4 KB
+constexpr uint32_t B_STAGE = 2 * B_PLANE;           // 8 KB
+constexpr uint32_t STG_WARP = 32 * 128;             // 4 KB: 32 rows of one plane of a mu tile image
+constexpr uint32_t STG_BYTES = CW * 4 * STG_WARP;   // 32 KB
+constexpr int THREADS = 512;
+constexpr int GATHER_WARP0 = 2, GATHER_WARPS = 4, CHAIN_WARP0 = 8;
+constexpr uint32_t ACC_COL = 0, ACC_WIN = PD * 64, D_COL = 256, D_WIN = 128;
+
+struct Tail {
+    float bias[4][P];           // pre-scaled by ASCALE
+    float vec[P];
+    uint64_t wts, w_full[WS], w_empty[WS], b_full[BS_MAX], b_empty[BS_MAX], acc_full[2], acc_empty[2], mma[CW];
+    uint32_t tmem_slot;
+    int32_t wcnt[CW][4];
+};
+constexpr size_t smem_for(uint32_t wbytes, int nb_stages) {
+    return 1024 + wbytes + WS * W_STAGE + STG_BYTES + (size_t)nb_stages * B_STAGE + sizeof(Tail);
+}
+constexpr size_t SMEM_MAX = 232448;                 // 227 KB: the per-block opt-in limit of sm_100
+}  // namespace fz
+
+struct FusedArgs {
+    UpdArgs u;                  // u.nb_img is unused
+    PropPlanDev plan;
+    const uint16_t* mu_in;      // mu images of the layer the propagation reads
+    uint16_t* nb_dbg;           // snapshots only: the nb tile images the two-launch path would have written, or null
+    int nb_stages;
+};
+
+// two 16-column tensor-memory loads in flight, then both -> fp32
+__device__ __forceinline__ void tmem_ld32_sync(uint32_t taddr, float (&v0)[16], float (&v1)[16]) {
+    uint32_t r0[16], r1[16];
+    tmem_ld16(taddr, r0);
+    tmem_ld16(taddr + 16, r1);
+    tmem_wait16(r0, v0);
+    tmem_wait16(r1, v1);
+}
+
+// 16 fp32 -> 8 hi + 8 lo packed fp16x2 words (element 2i at the lower half of word i)
+__device__ __forceinline__ void split16(const float (&v)[16], uint32_t (&w)[16]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split2(v[2 * i], v[2 * i + 1], w[i], w[8 + i]);
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// (accumulator columns [dcol, dcol+64) + bias) * rowscale -> this thread's row of the mu tile image (fp16 hi / lo planes,
+// K-major SWIZZLE_128B, scaled domain).  A warp's 32 rows of one plane are 4 KB contiguous in the image: the hi plane is staged
+// in the warp's 4 KB buffer (conflict-free swizzled 16-byte stores) and leaves with one bulk store, then the lo plane (kept in
+// registers meanwhile) the same way.  TO_A: the values also become the next A operand (score head).  img: the tile image in
+// global memory or null (nothing is stored).  Returns true on NaN in a valid row.  Warp-synchronous: all 32 lanes call it.
+template <bool TO_A>
+__device__ __forceinline__ bool epilogue_to_mu_warp(const WG& c, uint32_t dcol, const float* __restrict__ bias_s, float rowscale,
+                                                    bool valid, unsigned char* img, uint32_t stage) {
+    bool bad = false;
+    const uint32_t rl = (uint32_t)c.t & 31u;                       // row within the warp's 32 rows
+    const bool lane0 = rl == 0;
+    unsigned char* dst = img + ((uint32_t)c.t >> 5) * fz::STG_WARP;
+    uint32_t lo[32];
+    if (img != nullptr) {
+        if (lane0) bulk_wait_read();                                // the previous tile's lo-plane store has read the buffer
+        __syncwarp();
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float v0[16], v1[16];
+        tmem_ld32_sync(c.tmem + dcol + h * 32, v0, v1);
+#pragma unroll
+        for (int qq = 0; qq < 2; ++qq) {
+            float (&v)[16] = qq ? v1 : v0;
+            const int q = h * 2 + qq;
+            float bb[16];
+            lds16(bias_s + q * 16, bb);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                v[j] = (v[j] + bb[j]) * rowscale;
+                bad |= (v[j] != v[j]);
+            }
+            uint32_t w[16];
+            split16(v, w);
+            if (img != nullptr) {
+                sts128(stage + swz(rl, (uint32_t)(2 * q)), w[0], w[1], w[2], w[3]);
+                sts128(stage + swz(rl, (uint32_t)(2 * q + 1)), w[4], w[5], w[6], w[7]);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) lo[q * 8 + i] = w[8 + i];
+            if (TO_A) tmem_st16(c.tmem + c.acol + 16 * q, w);
+        }
+    }
+    if (img != nullptr) {
+        fence_proxy_async();             // the staging stores are generic-proxy writes, the bulk store reads through the async proxy
+        __syncwarp();
+        if (lane0) { bulk_s2g(dst, stage, fz::STG_WARP); bulk_wait_read(); }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            sts128(stage + swz(rl, (uint32_t)(2 * q)), lo[q * 8], lo[q * 8 + 1], lo[q * 8 + 2], lo[q * 8 + 3]);
+            sts128(stage + swz(rl, (uint32_t)(2 * q + 1)), lo[q * 8 + 4], lo[q * 8 + 5], lo[q * 8 + 6], lo[q * 8 + 7]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane0) bulk_s2g(dst + APLANE, stage, fz::STG_WARP);
+    }
+    return bad && valid;
+}
+
+__global__ void __launch_bounds__(fz::THREADS, 1) k_tc_fused(FusedArgs fa) {
+    using namespace fz;
+    const UpdArgs& a = fa.u;
+    const GnnParams& g = a.g;
+    const PropPlanDev& plan = fa.plan;
+    const bool with_score = a.scores != nullptr;
+    const uint32_t wbytes = with_score ? UPD_WBYTES : UPD_FN;          // the fnode planes are only needed by the score head
+    const int NB = fa.nb_stages;
+    unsigned char* base = smem_dyn();
+    base += (1024u - (smem_u32(base) & 1023u)) & 1023u;
+    const uint32_t W = smem_u32(base), w_ring = W + wbytes, stg = w_ring + WS * W_STAGE, b_ring = stg + STG_BYTES;
+    fz::Tail* tl = reinterpret_cast<fz::Tail*>(base + wbytes + WS * W_STAGE + STG_BYTES + (size_t)NB * B_STAGE);
+    const int warp = uniform((int)(threadIdx.x >> 5)), lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(&tl->wts), 1);
+        for (int i = 0; i < WS; ++i) { mbar_init(smem_u32(&tl->w_full[i]), 1); mbar_init(smem_u32(&tl->w_empty[i]), 1); }
+        for (int i = 0; i < NB; ++i) { mbar_init(smem_u32(&tl->b_full[i]), GATHER_WARPS * 32); mbar_init(smem_u32(&tl->b_empty[i]), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tl->acc_full[i]), 1); mbar_init(smem_u32(&tl->acc_empty[i]), PD); }
+        for (int i = 0; i < CW; ++i) mbar_init(smem_u32(&tl->mma[i]), 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (warp == 0) tmem_alloc(smem_u32(&tl->tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tl->tmem_slot;
+    const int l3 = a.backward ? BC3 : FC3, l4b = a.backward ? BC4_1 : FC4_2, lc = a.backward ? T_BWD_C : T_FWD_C;
+    if (threadIdx.x == 0) {
+        const uint32_t mb = smem_u32(&tl->wts);
+        mbar_expect_tx(mb, wbytes);
+        bulk_g2s(W + UPD_W3, g.tc[l3], 4 * WPLANE, mb);
+        bulk_g2s(W + UPD_WC, g.tcx_w[lc], 2 * WPLANE, mb);
+        bulk_g2s(W + UPD_W42, g.tc[l4b], 2 * WPLANE, mb);
+        if (with_score) bulk_g2s(W + UPD_FN, g.tc[FNODE], 2 * WPLANE, mb);
+    }
+    copy_vec(tl->bias[0], g.bias[l3], P); copy_vec(tl->bias[1], g.tcx_b[lc], P); copy_vec(tl->bias[2], g.bias[l4b], P);
+    copy_vec(tl->bias[3], g.bias[FNODE], P); copy_vec(tl->vec, g.wt[FSCORE], P, 1.0f);
+    __syncthreads();
+    pdl_trigger(); pdl_wait();                    // everything above read constant parameters only
+
+    const int ntiles = plan.ntiles;
+    const int64_t nitems = (int64_t)ntiles * ((a.Bc + PD - 1) / PD);      // item = pair * ntiles + tile
+    const int rank = (int)blockIdx.x, nranks = (int)gridDim.x;
+
+    if (warp == 0) {
+        // ---- propagation weight blocks ----
+        if (lane == 0) {
+            uint32_t ws = 0, wph = 0;
+            for (int64_t item = rank; item < nitems; item += nranks) {
+                const int tile = (int)(item % ntiles);
+                const int ch0 = plan.tile_chunk0[tile], ch1 = plan.tile_chunk0[tile + 1];
+                for (int ch = ch0; ch < ch1; ++ch) {
+                    mbar_wait(smem_u32(&tl->w_empty[ws]), wph ^ 1u);
+                    const uint32_t full = smem_u32(&tl->w_full[ws]);
+                    mbar_expect_tx(full, W_STAGE);
+                    bulk_g2s(w_ring + ws * W_STAGE, plan.a_planes + (size_t)ch * (W_STAGE / 2), W_STAGE, full);
+                    if (++ws == WS) { ws = 0; wph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---- propagation MMAs: the whole warp walks the loop (uniform control and operands), one elected lane issues ----
+        // D fp32, A fp16 K-major, B fp16 MN-major (bit 16), M = 128, N = 128
+        const uint32_t idesc = (1u << 4) | (1u << 16) | ((uint32_t)(PD * 64 >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+        uint32_t ws = 0, wph = 0, bs = 0, bph = 0, it = 0;
+#ifdef GNNB_TRACE
+        long long t_acc = 0, t_w = 0, t_b = 0, t_all = clock64(), t0_;
+        int n_ks = 0;
+#define FTR_BEGIN() t0_ = clock64()
+#define FTR_END(x) x += clock64() - t0_
+#else
+#define FTR_BEGIN()
+#define FTR_END(x)
+#endif
+        for (int64_t item = rank; item < nitems; item += nranks, ++it) {
+            const int tile = (int)(item % ntiles);
+            const int ch0 = uniform(plan.tile_chunk0[tile]), ch1 = uniform(plan.tile_chunk0[tile + 1]);
+            const uint32_t buf = it & 1u, bufph = (it >> 1) & 1u;
+            FTR_BEGIN();
+            mbar_wait(smem_u32(&tl->acc_empty[buf]), bufph ^ 1u);     // the chains of item it - 2 no longer read these A columns
+            FTR_END(t_acc);
+            tc_fence_after();
+            const uint32_t d = (tmem_base & 0x0000FFFFu) + ACC_COL + buf * ACC_WIN;
+            uint32_t accum = 0;
+            for (int ch = ch0; ch < ch1; ++ch) {
+                FTR_BEGIN();
+                mbar_wait(smem_u32(&tl->w_full[ws]), wph);
+                FTR_END(t_w);
+                const int nks = uniform(plan.ksteps[ch]);
+                const uint32_t wa = w_ring + ws * W_STAGE;
+                const uint64_t a_hi = make_desc(wa), a_lo = make_desc(wa + APLANE);
+#ifdef GNNB_TRACE
+                n_ks += nks;
+#endif
+                for (int ks = 0; ks < nks; ++ks) {
+                    FTR_BEGIN();
+                    mbar_wait(smem_u32(&tl->b_full[bs]), bph);
+                    FTR_END(t_b);
+                    tc_fence_after();
+                    const uint32_t ba = b_ring + bs * B_STAGE;
+                    const uint64_t b_hi = make_desc_mn(ba, B_DOM), b_lo = make_desc_mn(ba + B_PLANE, B_DOM);
+                    const uint64_t ah = a_hi + (uint64_t)(2 * ks), al = a_lo + (uint64_t)(2 * ks);
+                    if (elect_one()) {
+                        umma(d, ah, b_hi, idesc, accum);               // Wh Mh
+                        umma(d, al, b_hi, idesc, 1u);                  // Wl Mh
+                        umma(d, ah, b_lo, idesc, 1u);                  // Wh Ml
+                        umma_commit(smem_u32(&tl->b_empty[bs]));
+                    }
+                    __syncwarp();
+                    accum = 1u;
+                    if (++bs == (uint32_t)NB) { bs = 0; bph ^= 1u; }
+                }
+                if (elect_one()) umma_commit(smem_u32(&tl->w_empty[ws]));
+                __syncwarp();
+                if (++ws == WS) { ws = 0; wph ^= 1u; }
+            }
+            if (elect_one()) umma_commit(smem_u32(&tl->acc_full[buf]));
+            __syncwarp();
+        }
+#ifdef GNNB_TRACE
+        if (rank == 1 && lane == 0) printf("TRACE fused-mma: items %u ksteps %d total %lld | wait acc_empty %lld, w_full %lld, b_full %lld\n", it, n_ks,
+                                           clock64() - t_all, t_acc, t_w, t_b);
+#endif
+    } else if (warp >= GATHER_WARP0 && warp < GATHER_WARP0 + GATHER_WARPS) {
+        // ---- gather: warp gw copies rows [8 (gw >> 1), +8) of the K step for subdomain 2 * pair + (gw & 1); the 64 row indices
+        //      and the K-step count of the next chunk (of this item or of the CTA's next item) are in registers before the
+        //      current chunk is copied ----
+        const int gw = warp - GATHER_WARP0, gs = gw & 1, gh = gw >> 1;
+        const unsigned char* mu_bytes = reinterpret_cast<const unsigned char*>(fa.mu_in);
+        uint32_t bs = 0, bph = 0;
+        int64_t item = rank;
+#ifdef GNNB_TRACE
+        long long g_wait = 0, g_all = clock64();
+#endif
+        if (item < nitems) {
+            int ch = __ldg(plan.tile_chunk0 + (int)(item % ntiles)), ch1 = __ldg(plan.tile_chunk0 + (int)(item % ntiles) + 1);
+            int i0 = __ldg(plan.in_rows + (size_t)ch * 64 + lane), i1 = __ldg(plan.in_rows + (size_t)ch * 64 + 32 + lane);
+            int nks = __ldg(plan.ksteps + ch);
+            while (true) {
+                int64_t nitem = item;
+                int nch = ch + 1, nch1 = ch1;
+                if (nch >= ch1) {
+                    nitem = item + nranks;
+                    if (nitem < nitems) {
+                        const int nt = (int)(nitem % ntiles);
+                        nch = __ldg(plan.tile_chunk0 + nt); nch1 = __ldg(plan.tile_chunk0 + nt + 1);
+                    }
+                }
+                const bool has_next = nitem < nitems;
+                int n0 = -1, n1 = -1, nnks = 0;
+                if (has_next) {
+                    n0 = __ldg(plan.in_rows + (size_t)nch * 64 + lane); n1 = __ldg(plan.in_rows + (size_t)nch * 64 + 32 + lane);
+                    nnks = __ldg(plan.ksteps + nch);
+                }
+                const int dm = (int)(item / ntiles) * PD + gs;
+                const bool dom_ok = dm < a.Bc;
+                const int64_t drow = (int64_t)dm * plan.nslots_in;
+                for (int ks = 0; ks < nks; ++ks) {
+                    const int idx = (ks & 2) ? i1 : i0;
+#ifdef GNNB_TRACE
+                    const long long g0_ = clock64();
+#endif
+                    mbar_wait(smem_u32(&tl->b_empty[bs]), bph ^ 1u);
+#ifdef GNNB_TRACE
+                    g_wait += clock64() - g0_;
+#endif
+                    const uint32_t dst0 = b_ring + bs * B_STAGE + (uint32_t)gs * B_DOM;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int k = gh * 8 + i * 4 + (lane >> 3);      // row of the stage: 4 rows x 8 chunks per instruction
+                        const int node = __shfl_sync(0xffffffffu, idx, (ks & 1) * 16 + k);
+                        const bool ok = dom_ok && node >= 0;
+                        const int64_t grow = ok ? drow + node : 0;
+                        const uint32_t r = (uint32_t)(grow & (TILE - 1));
+                        const uint32_t jp = (uint32_t)(lane & 7);       // physical 16-byte chunk of the row in the mu image
+                        const unsigned char* src = mu_bytes + (grow >> 7) * (int64_t)ABUF + (r >> 3) * 1024u + (r & 7u) * 128u + jp * 16u;
+                        const uint32_t dst = dst0 + swz((uint32_t)k, jp ^ (r & 7u));   // logical chunk = physical ^ (row & 7)
+                        cp_async16(dst, src, ok);
+                        cp_async16(dst + B_PLANE, src + APLANE, ok);
+                    }
+                    cp_async_arrive(smem_u32(&tl->b_full[bs]));
+                    if (++bs == (uint32_t)NB) { bs = 0; bph ^= 1u; }
+                }
+                if (!has_next) break;
+                item = nitem; ch = nch; ch1 = nch1; i0 = n0; i1 = n1; nks = nnks;
+            }
+        }
+#ifdef GNNB_TRACE
+        if (rank == 1 && gw == 0 && lane == 0) printf("TRACE fused-gather: total %lld, wait b_empty %lld\n", clock64() - g_all, g_wait);
+#endif
+    } else if (warp >= CHAIN_WARP0) {
+        // ---- node-update chains ----
+        const float* __restrict__ lb = a.lb;
+        const float* __restrict__ ub = a.ub;
+        const float* __restrict__ rlx = a.rlx;
+        const int32_t* __restrict__ amb_base = a.amb_base;
+        float* __restrict__ scores = a.scores;
+        const RowMap map = a.map;
+        const float bscore = g.bias[FSCORE][0];
+        WG c;
+        c.wg = uniform((warp - CHAIN_WARP0) >> 2);
+        c.lead_warp = ((warp - CHAIN_WARP0) & 3) == 0;
+        c.t = threadIdx.x & 127;
+        c.land = 0;
+        c.mbar_mma = smem_u32(&tl->mma[c.wg]);
+        c.mbar_tma = 0;
+        c.ph_mma = 0;
+        c.ph_tma = 0;
+        c.acol = ACC_COL;
+        c.tmem0 = (uint32_t)uniform((int)tmem_base) & 0x0000FFFFu;
+        c.tmem = tmem_base + ((uint32_t)((c.t >> 5) * 32) << 16);
+        const int j = c.wg;
+        const uint32_t D = D_COL + D_WIN * (uint32_t)j;          // this warpgroup's accumulator window [D, D + 128)
+        const uint32_t stage = stg + (uint32_t)(warp - CHAIN_WARP0) * STG_WARP;      // this warp's 4 KB staging buffer
+        mbar_wait(smem_u32(&tl->wts), 0);                        // chain weights have landed
+        bool bad = false;
+        // this row's bounds are fetched one item ahead (two dependent 4-byte gathers from HBM)
+        int64_t nrow_n = -1;
+        float l_n = 0.f, u_n = 1.f;
+        int slot0_n = 0;
+        auto fetch_row = [&](int64_t it_) {
+            nrow_n = -1; l_n = 0.f; u_n = 1.f; slot0_n = 0;
+            if (it_ >= nitems) return;
+            const int d_ = (int)(it_ / ntiles) * PD + j;
+            if (d_ >= a.Bc) return;
+            const int64_t tl_ = (int64_t)d_ * ntiles + it_ % ntiles;
+            nrow_n = natural_row(map, tl_ * TILE + c.t);           // index into the caller's [B, n] arrays, -1 = padding slot
+            if (nrow_n >= 0) { l_n = ldg1_now(lb + nrow_n); u_n = ldg1_now(ub + nrow_n); }
+            slot0_n = __ldg(amb_base + tl_);
+        };
+        fetch_row(rank);
+        uint32_t it = 0;
+#ifdef GNNB_TRACE
+        long long c_wait = 0, c_ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, c_all = clock64(), c0_;
+        int c_tiles = 0;
+#define CTR(i) do { const long long n_ = clock64(); c_ph[i] += n_ - c0_; c0_ = n_; } while (0)
+#else
+#define CTR(i) do {} while (0)
+#endif
+        for (int64_t item = rank; item < nitems; item += nranks, ++it) {
+            const uint32_t buf = it & 1u, bufph = (it >> 1) & 1u;
+            const uint32_t acc_full = smem_u32(&tl->acc_full[buf]), acc_empty = smem_u32(&tl->acc_empty[buf]);
+            const int dom = (int)(item / ntiles) * PD + j;
+            const int64_t nrow = nrow_n;
+            const float l = l_n, u = u_n;
+            const int slot0 = slot0_n;
+            fetch_row(item + nranks);
+#ifdef GNNB_TRACE
+            c0_ = clock64();
+#endif
+            mbar_wait(acc_full, bufph);                           // the item's nb = A(mu) is complete in tensor memory
+#ifdef GNNB_TRACE
+            c_wait += clock64() - c0_;
+#endif
+            tc_fence_after();
+            if (dom >= a.Bc) {                                    // odd batch: the last pair has one subdomain
+                if (c.t == 0) mbar_arrive(acc_empty);
+                continue;
+            }
+            const int64_t tile = (int64_t)dom * ntiles + item % ntiles;
+            c.acol = ACC_COL + buf * ACC_WIN + 64u * (uint32_t)j;
+#ifdef GNNB_TRACE
+            c0_ = clock64(); ++c_tiles;
+#endif
+            const Ratio q = compute_ratio(l, u);
+            const float gate = (q.r0 != 0.0f) ? 1.0f : 0.0f;
+            const bool amb = (q.amb != 0.0f) && nrow >= 0;
+            const unsigned bal = __ballot_sync(0xffffffffu, amb);
+            if ((c.t & 31) == 0) tl->wcnt[j][c.t >> 5] = __popc(bal);
+            // nb: accumulator columns -> fp16 hi / lo A operand, in place (K step qd = channels [16 qd, 16 qd + 16))
+            {
+                unsigned char* dbg = fa.nb_dbg ? reinterpret_cast<unsigned char*>(fa.nb_dbg) + tile * (int64_t)ABUF + (uint32_t)c.t * 16u : nullptr;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float v0[16], v1[16];
+                    tmem_ld32_sync(c.tmem + c.acol + h * 32, v0, v1);
+#pragma unroll
+                    for (int qq = 0; qq < 2; ++qq) {
+                        const int qd = h * 2 + qq;
+                        uint32_t w[16];
+                        split16(qq ? v1 : v0, w);
+                        tmem_st16(c.tmem + c.acol + 16 * qd, w);
+                        if (dbg != nullptr) {      // piece-major nb image of the two-launch path (snapshots)
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {
+                                const uint32_t off = (uint32_t)(qd * 2 + hh) * NB_PIECE;
+                                *reinterpret_cast<uint4*>(dbg + off) = make_uint4(w[4 * hh], w[4 * hh + 1], w[4 * hh + 2], w[4 * hh + 3]);
+                                *reinterpret_cast<uint4*>(dbg + APLANE + off) = make_uint4(w[8 + 4 * hh], w[8 + 4 * hh + 1], w[8 + 4 * hh + 2], w[8 + 4 * hh + 3]);
+                            }
+                        }
+                    }
+                }
+            }
+            CTR(0);
+            // D[0:128) = nb [W3a; W3b]^T
+            gemm_ts(c, W + UPD_W3, W + UPD_W3 + 2 * WPLANE, 128, D);
+            CTR(1);
+            // slot of this row's relax' = first slot of the tile + number of ambiguous rows before it
+            int slot = slot0 + __popc(bal & ((1u << (c.t & 31)) - 1u));
+#pragma unroll
+            for (int w = 0; w < 3; ++w) slot += (w < (c.t >> 5)) ? tl->wcnt[j][w] : 0;
+            const float* rt = rlx + (size_t)(slot >> 7) * (TILE * P) + (size_t)(slot & (TILE - 1)) * 4;
+            if (amb) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(rt + (size_t)i * (TILE * 4)));
+            }
+            // h3 = relu(r0 * D[0:64) + r1 * D[64:128) + b3) -> A (graph_conv.py:169-170 / 331-336)
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {
+                float x[16], y[16], bb[16];
+                {
+                    uint32_t ra[16], rb[16];
+                    tmem_ld16(c.tmem + D + qd * 16, ra);
+                    tmem_ld16(c.tmem + D + 64 + qd * 16, rb);
+                    tmem_wait16(ra, x);
+                    tmem_wait16(rb, y);
+                }
+                lds16(tl->bias[0] + qd * 16, bb);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) x[i] = relu_nan(fmaf(q.r0, x[i], fmaf(q.r1, y[i], bb[i])));
+                a_store16(c, qd, x);
+            }
+            CTR(2);
+            // D[0:64) = h3 Wc^T; meanwhile fetch this row's relax'
+            gemm_ts_start(c, W + UPD_WC, W + UPD_WC + WPLANE, 64, D);
+            float4 rx[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) rx[i] = amb ? ldg4_now(rt + (size_t)i * (TILE * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            gemm_finish(c);
+            CTR(3);
+            // g = relu(D + relax' + bc) -> A
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float v0[16], v1[16];
+                tmem_ld32_sync(c.tmem + D + h * 32, v0, v1);
+#pragma unroll
+                for (int qq = 0; qq < 2; ++qq) {
+                    float (&v)[16] = qq ? v1 : v0;
+                    const int qd = h * 2 + qq;
+                    float bb[16];
+                    lds16(tl->bias[1] + qd * 16, bb);
+#pragma unroll
+                    for (int hh = 0; hh < 4; ++hh) {
+                        const float4 x = rx[qd * 4 + hh];
+                        v[hh * 4 + 0] = relu_nan(v[hh * 4 + 0] + x.x + bb[hh * 4 + 0]);
+                        v[hh * 4 + 1] = relu_nan(v[hh * 4 + 1] + x.y + bb[hh * 4 + 1]);
+                        v[hh * 4 + 2] = relu_nan(v[hh * 4 + 2] + x.z + bb[hh * 4 + 2]);
+                        v[hh * 4 + 3] = relu_nan(v[hh * 4 + 3] + x.w + bb[hh * 4 + 3]);
+                    }
+                    a_store16(c, qd, v);
+                }
+            }
+            CTR(4);
+            // D[0:64) = g W4_2^T;  mu = (D + b) * (r0 != 0) -> global
+            gemm_ts(c, W + UPD_W42, W + UPD_W42 + WPLANE, 64, D);
+            CTR(5);
+            unsigned char* img = a.mu_out ? reinterpret_cast<unsigned char*>(a.mu_out) + tile * (int64_t)ABUF : nullptr;
+            if (!with_score) {
+                if (c.t == 0) mbar_arrive(acc_empty);              // the last GEMM that reads this subdomain's A columns has completed
+                bad |= epilogue_to_mu_warp<false>(c, D, tl->bias[2], gate, nrow >= 0, img, stage);
+            } else {      // score head on the new embeddings (graph_conv.py:448-449)
+                bad |= epilogue_to_mu_warp<true>(c, D, tl->bias[2], gate, nrow >= 0, img, stage);
+                gemm_ts(c, W + UPD_FN, W + UPD_FN + WPLANE, 64, D);
+                if (c.t == 0) mbar_arrive(acc_empty);
+                float sc = 0.f;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float v0[16], v1[16];
+                    tmem_ld32_sync(c.tmem + D + h * 32, v0, v1);
+#pragma unroll
+                    for (int qq = 0; qq < 2; ++qq) {
+                        const int qd = h * 2 + qq;
+                        float bb[16], ww[16];
+                        lds16(tl->bias[3] + qd * 16, bb);
+                        lds16(tl->vec + qd * 16, ww);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) sc = fmaf(relu_nan((qq ? v1 : v0)[i] + bb[i]), ww[i], sc);
+                    }
+                }
+                if (nrow >= 0) scores[(nrow / map.n) * a.score_stride + a.score_off + (nrow % map.n)] = fmaf(sc, AINV, bscore);
+            }
+            CTR(6);
+        }
+#ifdef GNNB_TRACE
+        if (rank == 1 && threadIdx.x == CHAIN_WARP0 * 32)
+            printf("TRACE fused-chain wg0: tiles %d total %lld | wait acc_full %lld | per tile: convert %lld gemm1 %lld epi1 %lld gemm2 %lld epi2 %lld gemm3 %lld epi3 %lld\n",
+                   c_tiles, clock64() - c_all, c_wait, c_ph[0] / max(c_tiles, 1), c_ph[1] / max(c_tiles, 1), c_ph[2] / max(c_tiles, 1), c_ph[3] / max(c_tiles, 1),
+                   c_ph[4] / max(c_tiles, 1), c_ph[5] / max(c_tiles, 1), c_ph[6] / max(c_tiles, 1));
+#endif
+        if (bad) atomicAdd(a.nan_count, 1ULL);
+        if ((c.t & 31) == 0) bulk_wait_all();        // this warp's last bulk stores still read its staging buffer
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
 // ---- relax: round-independent part of the fc4 / bc4 pre-activation of a hidden layer --------------------------
@@ -697,7 +1209,7 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_input_update(GnnParams g, c
     const int64_t tile_step = (int64_t)gridDim.x * NWG;
     for (int64_t tile = (int64_t)blockIdx.x * NWG + c.wg; tile < ntiles; tile += tile_step) {
         const int64_t row0 = tile * TILE, grow = row0 + c.t;
-        request_nb(c, nb_img + (size_t)tile * (ABUF / 2), nullptr, 0);
+        request_nb(c, nb_img + (size_t)tile * (ABUF / 2));
         float feat[2] = {0.f, 0.f};
         const int64_t nrow = grow < rows ? natural_row(map, grow) : -1;
         if (nrow >= 0) { feat[0] = lb0[nrow]; feat[1] = ub0[nrow]; }
@@ -727,7 +1239,6 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_input_update(GnnParams g, c
 }
 
 constexpr size_t smem_bytes(uint32_t wbytes, bool land) { return 1024 + wbytes + (land ? NWG * ABUF : 0) + sizeof(Tail); }
-constexpr size_t LAYER_SMEM = prop::PROP_SMEM > smem_bytes(UPD_WBYTES, true) ? prop::PROP_SMEM : smem_bytes(UPD_WBYTES, true);
 
 int grid_for(int64_t rows) {
     const int64_t tiles = (rows + TILE - 1) / TILE, ctas = (tiles + NWG - 1) / NWG;
@@ -868,7 +1379,7 @@ bool tc_available() { return true; }
 int tc_init() {
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(k_tc_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(UPD_WBYTES, true))) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_tc_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LAYER_SMEM)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_tc_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz::SMEM_MAX)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_tc_relax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(RLX_WBYTES, false))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_tc_input_embed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(EMB_WBYTES, true))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_tc_input_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(INU_WBYTES, true))) != cudaSuccess) return e;
@@ -907,7 +1418,6 @@ UpdArgs make_upd_args(const GnnParams& g, bool backward, const float* lb, const 
     a.g = g; a.backward = backward ? 1 : 0; a.lb = lb; a.ub = ub; a.nb_img = reinterpret_cast<const uint16_t*>(nb); a.rlx = relax;
     a.amb_base = amb_base; a.mu_out = reinterpret_cast<uint16_t*>(mu_out); a.scores = scores; a.map = map;
     a.score_stride = score_stride; a.score_off = score_off; a.Bc = (int)(rows / map.nslots); a.nan_count = nan_count;
-    a.consumed = nullptr;
     return a;
 }
 }  // namespace
@@ -921,24 +1431,19 @@ void tc_update(const GnnParams& g, bool backward, const float* lb, const float* 
     ++*launches;
 }
 
-void tc_layer(const GnnParams& g, const PropPlan* plan, const float* mu_in, bool backward, const float* lb, const float* ub,
-              float* nb, const float* relax, const int32_t* amb_base, float* mu_out, float* scores, RowMap map, int64_t score_stride,
-              int64_t score_off, int64_t rows, unsigned long long* nan_count, int32_t* flags, int32_t epoch, int prop_share_pct,
-              int32_t* consumed, int32_t* consumed_base, int lead, cudaStream_t st, int64_t* launches) {
-    UpdArgs a = make_upd_args(g, backward, lb, ub, nb, relax, amb_base, mu_out, scores, map, score_stride, score_off, rows, nan_count);
-    const int64_t nitems = (int64_t)(map.nslots / TILE) * ((a.Bc + NWG - 1) / NWG);
-    // split of the 148 CTAs by a cost model in units of one propagation K chunk (fitted to stand-alone kernel times)
-    const double cp = prop_plan_chunks_per_tile(plan) + 8.5, cu = scores ? 19.0 : 16.7;
-    double share = prop_share_pct > 0 ? prop_share_pct / 100.0 : cp / (cp + cu);
-    int n_prop = (int)(148 * share + 0.5);
-    n_prop = n_prop < 4 ? 4 : (n_prop > 144 ? 144 : n_prop);
-    int n_upd = 148 - n_prop;
-    if (nitems < n_prop) n_prop = (int)nitems;
-    if (nitems < n_upd) n_upd = (int)nitems;
-    a.consumed = lead > 0 ? consumed : nullptr;
-    k_tc_layer<<<n_prop + n_upd, 128 * NWG, LAYER_SMEM, st>>>(prop_plan_dev(plan), reinterpret_cast<const uint16_t*>(mu_in), a, n_prop,
-                                                             flags, epoch, *consumed_base, lead);
-    if (lead > 0) *consumed_base += (int32_t)(4 * nitems);        // the counter runs on across launches (wrap-safe comparisons)
+void tc_fused(const GnnParams& g, const PropPlan* plan, const float* mu_in, bool backward, const float* lb, const float* ub,
+              const float* relax, const int32_t* amb_base, float* mu_out, float* scores, RowMap map, int64_t score_stride, int64_t score_off,
+              int64_t rows, unsigned long long* nan_count, float* nb_dbg, cudaStream_t st, int64_t* launches) {
+    FusedArgs fa;
+    fa.u = make_upd_args(g, backward, lb, ub, nullptr, relax, amb_base, mu_out, scores, map, score_stride, score_off, rows, nan_count);
+    fa.plan = prop_plan_dev(plan);
+    fa.mu_in = reinterpret_cast<const uint16_t*>(mu_in);
+    fa.nb_dbg = reinterpret_cast<uint16_t*>(nb_dbg);
+    const uint32_t wbytes = scores ? UPD_WBYTES : UPD_FN;
+    int nb = (int)((fz::SMEM_MAX - fz::smem_for(wbytes, 0)) / fz::B_STAGE);
+    fa.nb_stages = nb > fz::BS_MAX ? fz::BS_MAX : nb;
+    const int64_t nitems = (int64_t)fa.plan.ntiles * ((fa.u.Bc + fz::PD - 1) / fz::PD);
+    launch_pdl(k_tc_fused, (int)(nitems < 1 ? 1 : (nitems < 148 ? nitems : 148)), fz::THREADS, fz::smem_for(wbytes, fa.nb_stages), st, fa);
     ++*launches;
 }
 

@@ -1,5 +1,5 @@
-"""Checks of GPU code paths that have not run on a GPU yet, executed in their own process by tests/test_gpu_parity.py
-(`_run_isolated`): exit code 0 = pass.  Usage: python tests/gpu_isolated.py <check> <arg>"""
+"""Checks executed in their own process (own CUDA context, time-out) by tests/test_gpu_parity.py (`_run_isolated`):
+exit code 0 = pass.  Usage: python tests/gpu_isolated.py <check> <arg>"""
 import os
 import sys
 
@@ -21,6 +21,7 @@ def check_gather_prefetch(arch):
     model = GraphNet(2, 64, math='tc')
     model.load_state_dict(load_gnn('random'))
     model = model.eval().cuda()
+    model.scorer(0).set_option('fuse', 0)          # the variants belong to the stand-alone propagation kernel
     for f in (fr.to('cuda'), synthetic_frontier(*load_root(arch), 37, seed=5, device='cuda')):
         model.scorer(0).set_option('gather_prefetch', 0)
         b0, i0, s0 = model.score_frontier(f)
@@ -29,6 +30,38 @@ def check_gather_prefetch(arch):
             b1, i1, s1 = model.score_frontier(f)
             torch.cuda.synchronize()
             assert torch.equal(s0, s1) and torch.equal(i0, i1) and torch.equal(b0, b1), f'gather_prefetch={variant} changes the results'
+
+
+def check_fused(arch):
+    """k_tc_fused (default) against the two-launch path: both split the same fp32 propagation accumulator into the same fp16
+    hi / lo operand, but the first chain GEMM reads it from tensor memory instead of shared memory and the hardware's
+    accumulation order differs (measured 1.3e-6 of the largest score) — held to 1e-5, winners equal wherever the top-2 margin
+    exceeds that; B chosen so that CTAs walk several items, the last group of 4 subdomains is ragged, and (B = 1) most of the
+    grid is idle."""
+    model = GraphNet(2, 64, math='tc')
+    model.load_state_dict(load_gnn('random'))
+    model = model.eval().cuda()
+    sc = model.scorer(0)
+    for B in (3, 1, 301, 1024):
+        f = synthetic_frontier(*load_root(arch), B, seed=5 + B, device='cuda')
+        sc.set_option('fuse', 1)
+        b1, i1, s1 = model.score_frontier(f)
+        torch.cuda.synchronize()
+        sc.set_option('fuse', 0)
+        b0, i0, s0 = model.score_frontier(f)
+        torch.cuda.synchronize()
+        _close(s0, s1, i0, i1, f.mask, f'fused {arch} B={B}')
+
+
+def _close(s0, s1, i0, i1, mask, what, rtol=1e-5):
+    scale = float(s0.abs().max())
+    err = float((s0 - s1).abs().max()) / scale
+    masked = torch.where(mask != 0, s0, torch.full_like(s0, float('-inf')))
+    top2 = masked.topk(2, dim=1).values
+    safe = (top2[:, 0] - top2[:, 1]) > 2 * rtol * scale
+    print(f'{what}: identical={torch.equal(s0, s1)} max rel diff {err:.3e}, winners compared {int(safe.sum())}/{len(safe)}', flush=True)
+    assert err <= rtol, f'{what}: scores differ by {err:.3e} of the largest score'
+    assert torch.equal(i0[safe], i1[safe]), f'{what}: winners differ'
 
 
 def check_kw_bounds(arch):
@@ -71,5 +104,5 @@ def check_kw_bounds(arch):
 
 
 if __name__ == '__main__':
-    {'gather_prefetch': check_gather_prefetch, 'kw_bounds': check_kw_bounds}[sys.argv[1]](sys.argv[2])
+    {'gather_prefetch': check_gather_prefetch, 'kw_bounds': check_kw_bounds, 'fused': check_fused}[sys.argv[1]](sys.argv[2])
     print('ok')

@@ -216,28 +216,29 @@ def test_frontier_of_65536_subdomains():
 
 
 @pytest.mark.parametrize('arch', ARCHS)
-def test_fused_layer_launches_match_reference(arch):
-    """Option fuse = 1 (propagation CTAs + node-update CTAs of a layer in one launch, item-granular hand-off) gives the
-    same scores as two launches, bit for bit, and matches the reference's committed outputs."""
+def test_fused_layer_kernel_matches_two_launches(arch):
+    """The default path (option fuse = 1: propagation gather-GEMM and node-update chain of a layer in one kernel, nb handed
+    over in tensor memory) against the two-launch path (fuse = 0, nb through HBM): both split the same fp32 accumulator into
+    the same fp16 hi / lo operand; the first chain GEMM reads it from tensor memory instead of shared memory, which changes the
+    hardware's accumulation order (1.3e-6 of the largest score measured) — held to 1e-5 — and both match the reference."""
+    from gpu_isolated import _close
     fr, ref = load_case(arch, 'fr')
     model = _model('random', 'tc')
     sc = model.scorer(0)
+    assert sc.get_option('fuse') == 1
+    b1, i1, s1 = model.score_frontier(fr.to('cuda'))
+    sc.set_option('fuse', 0)
     b0, i0, s0 = model.score_frontier(fr.to('cuda'))
-    sc.set_option('fuse', 1)
-    for share in (0, 30, 70):
-        sc.set_option('prop_share', share)
-        b1, i1, s1 = model.score_frontier(fr.to('cuda'))
-        assert torch.equal(s0, s1) and torch.equal(i0, i1) and torch.equal(b0, b1)
-    rep = O.parity_report(s1.cpu(), ref['scores_random'], fr.mask, i1.cpu(), rtol=RTOL['tc'])
-    assert rep['ok'], rep
+    _close(s0, s1, i0, i1, fr.mask.cuda(), f'{arch} golden frontier')
+    for s_, i_ in ((s0, i0), (s1, i1)):
+        rep = O.parity_report(s_.cpu(), ref['scores_random'], fr.mask, i_.cpu(), rtol=RTOL['tc'])
+        assert rep['ok'], rep
     net, lbs, ubs, wp, bp = load_root(arch)
     big = synthetic_frontier(net, lbs, ubs, wp, bp, 301, seed=77, device='cuda')     # several items per CTA, a ragged last group
-    sc.set_option('fuse', 0)
     b2, i2, s2 = model.score_frontier(big)
     sc.set_option('fuse', 1)
-    sc.set_option('prop_share', 0)
     b3, i3, s3 = model.score_frontier(big)
-    assert torch.equal(s2, s3) and torch.equal(i2, i3) and torch.equal(b2, b3)
+    _close(s2, s3, i2, i3, big.mask, f'{arch} x 301')
 
 
 def _custom_frontier(layers, input_shape, B, seed):
@@ -282,9 +283,10 @@ def test_other_network_shapes_match_oracle(case, math):
     rep = O.parity_report(scores.cpu(), s_or, fr.mask, idx.cpu(), rtol=RTOL[math])
     assert rep['ok'], rep
     if math == 'tc':
-        model.scorer(0).set_option('fuse', 1)
+        from gpu_isolated import _close
+        model.scorer(0).set_option('fuse', 0)
         b1, i1, s1 = model.score_frontier(fr.to('cuda'))
-        assert torch.equal(s1, scores) and torch.equal(i1, idx)
+        _close(s1, scores, i1, idx, fr.mask.cuda(), case)
 
 
 # ---- BaBSR / KW heuristic -------------------------------------------------------------------
@@ -612,13 +614,12 @@ _ISO_TIMED_OUT = set()
 
 
 def _run_isolated(what, arg, timeout=120):
-    """Run a check of code that has never executed on a GPU in its own process (its own CUDA context) with a timeout: a hang
-    or a sticky CUDA error there cannot take the rest of the suite with it.  After one time-out of a kind of check the others
-    of that kind are not started (a hang does not depend on the network)."""
+    """Run a check in its own process (its own CUDA context) with a timeout: a hang or a sticky CUDA error there cannot take
+    the rest of the suite with it.  After one time-out of a kind of check the others of that kind fail at once."""
     import subprocess
     import sys
     if what in _ISO_TIMED_OUT:
-        pytest.xfail(f'{what}: an earlier isolated check timed out')
+        pytest.fail(f'{what}: an earlier isolated check timed out')
     here = os.path.dirname(os.path.abspath(__file__))
     try:
         r = subprocess.run([sys.executable, os.path.join(here, 'gpu_isolated.py'), what, arg], capture_output=True, text=True, timeout=timeout)
@@ -628,16 +629,11 @@ def _run_isolated(what, arg, timeout=120):
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
 
 
-@pytest.mark.xfail(reason='option "gather_prefetch" (propagation kernel variant with the gather indices fetched one chunk ahead) was '
-                          'written after the GPU budget of round 1 was spent: off by default, first validated by this test', strict=False)
 @pytest.mark.parametrize('arch', ARCHS)
 def test_gather_prefetch_variant_is_bit_identical(arch):
     _run_isolated('gather_prefetch', arch)
 
 
-@pytest.mark.xfail(reason='gnnb_kw_bounds (batched KW bound producer, SURVEY 8f rank 3) was written after the GPU budget of round 1 was '
-                          'spent; its algorithm is checked on the CPU (scripts/kw_transposed_check.py), its kernels first run here',
-                   strict=False)
 @pytest.mark.parametrize('arch', ARCHS)
 def test_kw_bounds_match_reference(arch):
     _run_isolated('kw_bounds', arch, timeout=180)
