@@ -279,7 +279,7 @@ struct ChunkPtrs {
 
 // the stage schedule for one chunk; every pointer is a device pointer
 int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* best_score, int32_t* best_idx,
-              cudaStream_t st) {
+              gnnb_winner* winners, cudaStream_t st) {
     const int L = (int)ctx->layers.size();
     const GnnParams& g = ctx->gp;
     const bool tc = ctx->math == GNNB_MATH_TC_FP16X3;
@@ -396,7 +396,7 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
     }
     {
         ProfScope ps(ctx, GNNB_K_ARGMAX, Bc, st);
-        masked_argmax(scores, in.mask, ctx->n_hidden, Bc, best_score, best_idx, st, lc);
+        masked_argmax(scores, in.mask, ctx->n_hidden, Bc, best_score, best_idx, winners, st, lc);
     }
     CU(cudaGetLastError());
     return GNNB_OK;
@@ -793,8 +793,9 @@ int64_t gnnb_get_option(gnnb_ctx* ctx, const char* key) {
     return -1;
 }
 
-int gnnb_score(gnnb_ctx* ctx, const gnnb_frontier* in, float* best_score, int32_t* best_idx, float* scores, void* stream) {
-    if (!ctx || !in || !best_score || !best_idx) return fail(ctx, GNNB_ERR_INVALID, "null argument");
+static int score_impl(gnnb_ctx* ctx, const gnnb_frontier* in, float* best_score, int32_t* best_idx, gnnb_winner* winners, float* scores,
+                      void* stream) {
+    if (!ctx || !in || ((!best_score || !best_idx) && !winners)) return fail(ctx, GNNB_ERR_INVALID, "null argument");
     if (!ctx->have_gnn || !ctx->have_net) return fail(ctx, GNNB_ERR_STATE, "gnnb_set_gnn_weights and gnnb_set_network must be called first");
     if (in->B < 0) return fail(ctx, GNNB_ERR_INVALID, "negative batch");
     if (in->B == 0) return GNNB_OK;
@@ -805,13 +806,18 @@ int gnnb_score(gnnb_ctx* ctx, const gnnb_frontier* in, float* best_score, int32_
     cudaStream_t st = (cudaStream_t)stream;
     const int L = (int)ctx->layers.size();
     const bool host = in->mem == GNNB_MEM_HOST;
+    // every array pointer is checked before anything is enqueued: an error return never leaves copies in flight
+    for (int k = 0; k <= L + 1; ++k)
+        if (!in->lb[k] || !in->ub[k]) return fail(ctx, GNNB_ERR_INVALID, "null bound array");
+    for (int k = 0; k < L; ++k)
+        if (!in->dual[k] || !in->prim_pre[k] || !in->prim_post[k]) return fail(ctx, GNNB_ERR_INVALID, "null dual/primal array");
     // subdomains per wave: large waves amortise launches and tails; with host buffers smaller waves let the copies of
     // wave i + 1 (copy stream, second staging set) run under the kernels of wave i
     int chunk = ctx->chunk > 0 ? ctx->chunk : 1024;
     if (chunk > in->B) chunk = in->B;
     TRY(ensure_workspace(ctx, chunk, host));
     const std::vector<int>& n = ctx->n;
-    if (host && ctx->res_cap < in->B) {
+    if (host && !winners && ctx->res_cap < in->B) {
         if (ctx->res_best) cudaFree(ctx->res_best);
         if (ctx->res_idx) cudaFree(ctx->res_idx);
         ctx->res_best = nullptr; ctx->res_idx = nullptr; ctx->res_cap = 0;
@@ -830,7 +836,9 @@ int gnnb_score(gnnb_ctx* ctx, const gnnb_frontier* in, float* best_score, int32_
         ramp = ramp * 4 > chunk ? chunk : ramp * 4;
         gnnb_ctx::Staging& sg = ctx->stg[wave & 1];
         cudaStream_t cs = host ? ctx->copy_stream : st;
-        if (host && wave >= 2) CU(cudaStreamWaitEvent(cs, ctx->ev_free[wave & 1], 0));   // this staging set's previous wave is done
+        // this staging set's previous user (an earlier wave of this call, or the last waves of an earlier call — possibly on
+        // another stream, or one that ended in an error) is done; an event that was never recorded is a no-op
+        if (host) CU(cudaStreamWaitEvent(cs, ctx->ev_free[wave & 1], 0));
         ChunkPtrs cp;
         cp.lb.resize(L + 2); cp.ub.resize(L + 2); cp.dual.resize(L); cp.pre.resize(L); cp.post.resize(L);
         auto stage = [&](const float* src, float* dst, size_t per_domain) -> const float* {
@@ -840,12 +848,10 @@ int gnnb_score(gnnb_ctx* ctx, const gnnb_frontier* in, float* best_score, int32_
             return dst;
         };
         for (int k = 0; k <= L + 1; ++k) {
-            if (!in->lb[k] || !in->ub[k]) return fail(ctx, GNNB_ERR_INVALID, "null bound array");
             cp.lb[k] = stage(in->lb[k], host ? sg.lb[k] : nullptr, n[k]);
             cp.ub[k] = stage(in->ub[k], host ? sg.ub[k] : nullptr, n[k]);
         }
         for (int k = 0; k < L; ++k) {
-            if (!in->dual[k] || !in->prim_pre[k] || !in->prim_post[k]) return fail(ctx, GNNB_ERR_INVALID, "null dual/primal array");
             cp.dual[k] = stage(in->dual[k], host ? sg.dual[k] : nullptr, (size_t)n[k + 1] * 3);
             cp.pre[k] = stage(in->prim_pre[k], host ? sg.pre[k] : nullptr, n[k + 1]);
             cp.post[k] = stage(in->prim_post[k], host ? sg.post[k] : nullptr, n[k + 1]);
@@ -862,9 +868,16 @@ int gnnb_score(gnnb_ctx* ctx, const gnnb_frontier* in, float* best_score, int32_
         }
 
         float* d_scores = host ? sg.scores : (scores ? scores + (size_t)c0 * ctx->n_hidden : ctx->ws_scores);
-        float* d_best = host ? ctx->res_best + c0 : best_score + c0;
-        int32_t* d_idx = host ? ctx->res_idx + c0 : best_idx + c0;
-        TRY(run_chunk(ctx, cp, Bc, d_scores, d_best, d_idx, st));
+        float* d_best = winners ? nullptr : (host ? ctx->res_best + c0 : best_score + c0);
+        int32_t* d_idx = winners ? nullptr : (host ? ctx->res_idx + c0 : best_idx + c0);
+        {
+            const int rc = run_chunk(ctx, cp, Bc, d_scores, d_best, d_idx, winners ? winners + c0 : nullptr, st);
+            if (rc != GNNB_OK) {      // nothing of this call may still be touching the caller's buffers or the staging sets
+                if (host) cudaStreamSynchronize(ctx->copy_stream);
+                cudaStreamSynchronize(st);
+                return rc;
+            }
+        }
         if (host) {
             if (scores)
                 CU(cudaMemcpyAsync(scores + (size_t)c0 * ctx->n_hidden, d_scores, (size_t)Bc * ctx->n_hidden * sizeof(float),
@@ -873,11 +886,24 @@ int gnnb_score(gnnb_ctx* ctx, const gnnb_frontier* in, float* best_score, int32_
         }
     }
     if (host) {
-        CU(cudaMemcpyAsync(best_score, ctx->res_best, (size_t)in->B * sizeof(float), cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(best_idx, ctx->res_idx, (size_t)in->B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        if (!winners) {
+            CU(cudaMemcpyAsync(best_score, ctx->res_best, (size_t)in->B * sizeof(float), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(best_idx, ctx->res_idx, (size_t)in->B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        }
         return gnnb_check(ctx, stream, nullptr);
     }
     return GNNB_OK;
+}
+
+int gnnb_score(gnnb_ctx* ctx, const gnnb_frontier* in, float* best_score, int32_t* best_idx, float* scores, void* stream) {
+    if (!best_score || !best_idx) return fail(ctx, GNNB_ERR_INVALID, "null argument");
+    return score_impl(ctx, in, best_score, best_idx, nullptr, scores, stream);
+}
+
+int gnnb_score_winners(gnnb_ctx* ctx, const gnnb_frontier* in, gnnb_winner* winners, float* scores, void* stream) {
+    if (!winners) return fail(ctx, GNNB_ERR_INVALID, "null argument");
+    if (in && in->mem == GNNB_MEM_HOST && scores) return fail(ctx, GNNB_ERR_INVALID, "dense scores of a HOST frontier: use gnnb_score");
+    return score_impl(ctx, in, nullptr, nullptr, winners, scores, stream);
 }
 
 int gnnb_babsr(gnnb_ctx* ctx, const gnnb_frontier* in, int32_t sparsest_layer, float decision_threshold,

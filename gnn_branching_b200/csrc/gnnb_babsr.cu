@@ -181,9 +181,12 @@ __global__ void __launch_bounds__(BT) k_babsr(BabsrArgs a) {
         bool any = false;
         for (int k = 0; k < a.L; ++k) any |= sfirst[k] >= 0;
         if (any) {
+            // max(max_info) compares (value, index) tuples (kw_score_conv.py:123-124): on equal maxima the layer whose in-layer
+            // argmax index is larger wins, and max_info.index() returns the first layer among fully equal pairs
             int best = 0;
             for (int k = 1; k < a.L; ++k)
-                if (smax[k].v > smax[best].v || (smax[k].v != smax[k].v && smax[best].v == smax[best].v)) best = k;
+                if (smax[k].v > smax[best].v || (smax[k].v == smax[best].v && smax[k].i > smax[best].i) ||
+                    (smax[k].v != smax[k].v && smax[best].v == smax[best].v)) best = k;
             if (best != a.sparsest_layer && smax[best].v > a.threshold) {
                 dl = best; di = smax[best].i; kind = 0;
             } else {

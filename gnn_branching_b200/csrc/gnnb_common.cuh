@@ -163,8 +163,9 @@ void prop_backward(const LayerDev& L, const float* mu_next, float* nb, int Bc, b
 void prop_property_backward(const float* wp, const float* mu_out, float* nb, int nL, int Bc, cudaStream_t st, int64_t* launches);
 void output_node(const GnnParams& g, const float* wp, const float* bp, const float* mu_L, bool mu_image, int mu_stride, const float* lb_out,
                  const float* ub_out, const float* prim_out, float* mu_out, int nL, int Bc, cudaStream_t st, int64_t* launches);
+// best_score / best_idx (both or neither) and / or packed winner records
 void masked_argmax(const float* scores, const float* mask, int n_hidden, int Bc, float* best_score, int32_t* best_idx,
-                   cudaStream_t st, int64_t* launches);
+                   gnnb_winner* winners, cudaStream_t st, int64_t* launches);
 
 // tensor-core propagation (gnnb_prop_tc.cu): block plans built once per network, gather-GEMM kernel
 struct PropPlan;

@@ -241,7 +241,7 @@ __device__ __forceinline__ bool better(float a, int ia, float b, int ib) {
 // one block per subdomain: max over rows with mask != 0, lowest index on ties
 __global__ void __launch_bounds__(256) k_masked_argmax(const float* __restrict__ scores, const float* __restrict__ mask,
                                                        int n_hidden, float* __restrict__ best_score,
-                                                       int32_t* __restrict__ best_idx) {
+                                                       int32_t* __restrict__ best_idx, gnnb_winner* __restrict__ winners) {
     __shared__ float sv[8];
     __shared__ int si[8];
     const int b = blockIdx.x;
@@ -269,7 +269,14 @@ __global__ void __launch_bounds__(256) k_masked_argmax(const float* __restrict__
             const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
             if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
         }
-        if (lane == 0) { best_score[b] = bi < 0 ? -INFINITY : bv; best_idx[b] = bi; }
+        if (lane == 0) {
+            const float v = bi < 0 ? -INFINITY : bv;
+            if (best_score != nullptr) { best_score[b] = v; best_idx[b] = bi; }
+            if (winners != nullptr) {      // one 8-byte store: the record the winner all-gather sends (gnn_branching_b200/dist.py)
+                gnnb_winner w; w.score = v; w.index = bi;
+                winners[b] = w;
+            }
+        }
     }
 }
 
@@ -324,8 +331,8 @@ void output_node(const GnnParams& g, const float* wp, const float* bp, const flo
 }
 
 void masked_argmax(const float* scores, const float* mask, int n_hidden, int Bc, float* best_score, int32_t* best_idx,
-                   cudaStream_t st, int64_t* launches) {
-    k_masked_argmax<<<Bc, 256, 0, st>>>(scores, mask, n_hidden, best_score, best_idx);
+                   gnnb_winner* winners, cudaStream_t st, int64_t* launches) {
+    k_masked_argmax<<<Bc, 256, 0, st>>>(scores, mask, n_hidden, best_score, best_idx, winners);
     ++*launches;
 }
 

@@ -557,14 +557,15 @@ namespace fz {
 constexpr int PD = 2;                               // subdomains per item = accumulator columns / 64
 constexpr int CW = 2;                               // chain warpgroups = PD
 constexpr int WS = 2;                               // weight ring stages
-constexpr int BS_MAX = 8;
+constexpr int BS_MAX = 12;
 constexpr uint32_t W_STAGE = 2 * APLANE;            // 32 KB: one 64-row K chunk of the weight block, hi + lo plane
 constexpr uint32_t B_ROWS = 16;                     // input nodes per B stage = one K step
 constexpr uint32_t B_DOM = B_ROWS * 128;            // 2 KB: one plane of one subdomain
 constexpr uint32_t B_PLANE = PD * B_DOM;            // 4 KB
 constexpr uint32_t B_STAGE = 2 * B_PLANE;           // 8 KB
-constexpr uint32_t STG_WARP = 32 * 128;             // 4 KB: 32 rows of one plane of a mu tile image
-constexpr uint32_t STG_BYTES = CW * 4 * STG_WARP;   // 32 KB
+constexpr uint32_t STG_PLANE = 32 * 128;            // 4 KB: a warp's 32 rows of one plane of a mu tile image
+constexpr uint32_t STG_WARP = 2 * STG_PLANE;        // 8 KB: hi + lo
+constexpr uint32_t STG_BYTES = CW * 4 * STG_WARP;   // 64 KB, only in launches that store embeddings
 constexpr int THREADS = 512;
 constexpr int GATHER_WARP0 = 2, GATHER_WARPS = 4, CHAIN_WARP0 = 8;
 constexpr uint32_t ACC_COL = 0, ACC_WIN = PD * 64, D_COL = 256, D_WIN = 128;
@@ -576,8 +577,8 @@ struct Tail {
     uint32_t tmem_slot;
     int32_t wcnt[CW][4];
 };
-constexpr size_t smem_for(uint32_t wbytes, int nb_stages) {
-    return 1024 + wbytes + WS * W_STAGE + STG_BYTES + (size_t)nb_stages * B_STAGE + sizeof(Tail);
+constexpr size_t smem_for(uint32_t wbytes, bool staging, int nb_stages) {
+    return 1024 + wbytes + WS * W_STAGE + (staging ? STG_BYTES : 0) + (size_t)nb_stages * B_STAGE + sizeof(Tail);
 }
 constexpr size_t SMEM_MAX = 232448;                 // 227 KB: the per-block opt-in limit of sm_100
 }  // namespace fz
@@ -609,20 +610,21 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 }
 
 // (accumulator columns [dcol, dcol+64) + bias) * rowscale -> this thread's row of the mu tile image (fp16 hi / lo planes,
-// K-major SWIZZLE_128B, scaled domain).  A warp's 32 rows of one plane are 4 KB contiguous in the image: the hi plane is staged
-// in the warp's 4 KB buffer (conflict-free swizzled 16-byte stores) and leaves with one bulk store, then the lo plane (kept in
-// registers meanwhile) the same way.  TO_A: the values also become the next A operand (score head).  img: the tile image in
-// global memory or null (nothing is stored).  Returns true on NaN in a valid row.  Warp-synchronous: all 32 lanes call it.
+// K-major SWIZZLE_128B, scaled domain).  A warp's 32 rows of one plane are 4 KB contiguous in the image: both planes are
+// staged in the warp's 8 KB buffer (conflict-free swizzled 16-byte stores) and leave with one bulk store per plane, issued by
+// the warp itself — no warpgroup barrier; the stores drain while the warp runs its next tile (the SMs of a launch walk their
+// tiles in lock step, so the tiles of a wave are written in bursts that take ~4 000 cycles to drain: a synchronous store of
+// any kind — 32-byte direct stores, coalesced 16-byte stores, a bulk store waited for — puts that on the chain's path
+// [measured, profiles/r02_fused_phase_trace.log]).  TO_A: the values also become the next A operand (score head).  img: the
+// tile image in global memory or null (nothing is stored).  Returns true on NaN in a valid row.  Warp-synchronous.
 template <bool TO_A>
 __device__ __forceinline__ bool epilogue_to_mu_warp(const WG& c, uint32_t dcol, const float* __restrict__ bias_s, float rowscale,
                                                     bool valid, unsigned char* img, uint32_t stage) {
     bool bad = false;
-    const uint32_t rl = (uint32_t)c.t & 31u;                       // row within the warp's 32 rows
-    const bool lane0 = rl == 0;
-    unsigned char* dst = img + ((uint32_t)c.t >> 5) * fz::STG_WARP;
-    uint32_t lo[32];
+    const uint32_t rl = (uint32_t)c.t & 31u;                       // row within the warp's 32 rows = lane
+    unsigned char* dst = img + ((uint32_t)c.t >> 5) * fz::STG_PLANE;
     if (img != nullptr) {
-        if (lane0) bulk_wait_read();                                // the previous tile's lo-plane store has read the buffer
+        if (rl == 0) bulk_wait_read();                              // the previous tile's bulk stores have read the buffer
         __syncwarp();
     }
 #pragma unroll
@@ -643,27 +645,23 @@ __device__ __forceinline__ bool epilogue_to_mu_warp(const WG& c, uint32_t dcol, 
             uint32_t w[16];
             split16(v, w);
             if (img != nullptr) {
-                sts128(stage + swz(rl, (uint32_t)(2 * q)), w[0], w[1], w[2], w[3]);
-                sts128(stage + swz(rl, (uint32_t)(2 * q + 1)), w[4], w[5], w[6], w[7]);
+                const uint32_t o0 = stage + swz(rl, (uint32_t)(2 * q)), o1 = stage + swz(rl, (uint32_t)(2 * q + 1));
+                sts128(o0, w[0], w[1], w[2], w[3]);
+                sts128(o1, w[4], w[5], w[6], w[7]);
+                sts128(o0 + fz::STG_PLANE, w[8], w[9], w[10], w[11]);
+                sts128(o1 + fz::STG_PLANE, w[12], w[13], w[14], w[15]);
             }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) lo[q * 8 + i] = w[8 + i];
             if (TO_A) tmem_st16(c.tmem + c.acol + 16 * q, w);
         }
     }
     if (img != nullptr) {
-        fence_proxy_async();             // the staging stores are generic-proxy writes, the bulk store reads through the async proxy
+        fence_proxy_async();             // the staging stores are generic-proxy writes, the bulk stores read through the async proxy
         __syncwarp();
-        if (lane0) { bulk_s2g(dst, stage, fz::STG_WARP); bulk_wait_read(); }
-        __syncwarp();
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            sts128(stage + swz(rl, (uint32_t)(2 * q)), lo[q * 8], lo[q * 8 + 1], lo[q * 8 + 2], lo[q * 8 + 3]);
-            sts128(stage + swz(rl, (uint32_t)(2 * q + 1)), lo[q * 8 + 4], lo[q * 8 + 5], lo[q * 8 + 6], lo[q * 8 + 7]);
+        if (rl == 0) {
+            bulk_s2g_nocommit(dst, stage, fz::STG_PLANE);
+            bulk_s2g_nocommit(dst + APLANE, stage + fz::STG_PLANE, fz::STG_PLANE);
+            bulk_commit();
         }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane0) bulk_s2g(dst + APLANE, stage, fz::STG_WARP);
     }
     return bad && valid;
 }
@@ -678,8 +676,9 @@ __global__ void __launch_bounds__(fz::THREADS, 1) k_tc_fused(FusedArgs fa) {
     const int NB = fa.nb_stages;
     unsigned char* base = smem_dyn();
     base += (1024u - (smem_u32(base) & 1023u)) & 1023u;
-    const uint32_t W = smem_u32(base), w_ring = W + wbytes, stg = w_ring + WS * W_STAGE, b_ring = stg + STG_BYTES;
-    fz::Tail* tl = reinterpret_cast<fz::Tail*>(base + wbytes + WS * W_STAGE + STG_BYTES + (size_t)NB * B_STAGE);
+    const uint32_t stg_bytes = a.mu_out != nullptr ? STG_BYTES : 0u;
+    const uint32_t W = smem_u32(base), w_ring = W + wbytes, stg = w_ring + WS * W_STAGE, b_ring = stg + stg_bytes;
+    fz::Tail* tl = reinterpret_cast<fz::Tail*>(base + wbytes + WS * W_STAGE + stg_bytes + (size_t)NB * B_STAGE);
     const int warp = uniform((int)(threadIdx.x >> 5)), lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         mbar_init(smem_u32(&tl->wts), 1);
@@ -885,21 +884,27 @@ __global__ void __launch_bounds__(fz::THREADS, 1) k_tc_fused(FusedArgs fa) {
         const uint32_t stage = stg + (uint32_t)(warp - CHAIN_WARP0) * STG_WARP;      // this warp's 4 KB staging buffer
         mbar_wait(smem_u32(&tl->wts), 0);                        // chain weights have landed
         bool bad = false;
-        // this row's bounds are fetched one item ahead (two dependent 4-byte gathers from HBM)
-        int64_t nrow_n = -1;
+        // this row's inputs are two dependent 4-byte gathers (slot -> node, node -> bounds): the node index is fetched two
+        // items ahead and the bounds one item ahead, so neither latency is on the chain's path
+        int64_t nrow_n = -1, nrow_nn = -1;
         float l_n = 0.f, u_n = 1.f;
         int slot0_n = 0;
-        auto fetch_row = [&](int64_t it_) {
-            nrow_n = -1; l_n = 0.f; u_n = 1.f; slot0_n = 0;
-            if (it_ >= nitems) return;
+        auto fetch_node = [&](int64_t it_) -> int64_t {          // index into the caller's [B, n] arrays, -1 = padding slot / no item
+            if (it_ >= nitems) return -1;
             const int d_ = (int)(it_ / ntiles) * PD + j;
-            if (d_ >= a.Bc) return;
-            const int64_t tl_ = (int64_t)d_ * ntiles + it_ % ntiles;
-            nrow_n = natural_row(map, tl_ * TILE + c.t);           // index into the caller's [B, n] arrays, -1 = padding slot
-            if (nrow_n >= 0) { l_n = ldg1_now(lb + nrow_n); u_n = ldg1_now(ub + nrow_n); }
-            slot0_n = __ldg(amb_base + tl_);
+            if (d_ >= a.Bc) return -1;
+            return natural_row(map, ((int64_t)d_ * ntiles + it_ % ntiles) * TILE + c.t);
         };
-        fetch_row(rank);
+        auto fetch_bounds = [&](int64_t it_, int64_t nrow_) {
+            nrow_n = nrow_; l_n = 0.f; u_n = 1.f; slot0_n = 0;
+            if (nrow_ >= 0) { l_n = ldg1_now(lb + nrow_); u_n = ldg1_now(ub + nrow_); }
+            if (it_ < nitems) {
+                const int d_ = (int)(it_ / ntiles) * PD + j;
+                if (d_ < a.Bc) slot0_n = __ldg(amb_base + (int64_t)d_ * ntiles + it_ % ntiles);
+            }
+        };
+        fetch_bounds(rank, fetch_node(rank));
+        nrow_nn = fetch_node((int64_t)rank + nranks);
         uint32_t it = 0;
 #ifdef GNNB_TRACE
         long long c_wait = 0, c_ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, c_all = clock64(), c0_;
@@ -915,7 +920,8 @@ __global__ void __launch_bounds__(fz::THREADS, 1) k_tc_fused(FusedArgs fa) {
             const int64_t nrow = nrow_n;
             const float l = l_n, u = u_n;
             const int slot0 = slot0_n;
-            fetch_row(item + nranks);
+            fetch_bounds(item + nranks, nrow_nn);
+            nrow_nn = fetch_node(item + 2 * (int64_t)nranks);
 #ifdef GNNB_TRACE
             c0_ = clock64();
 #endif
@@ -1440,10 +1446,11 @@ void tc_fused(const GnnParams& g, const PropPlan* plan, const float* mu_in, bool
     fa.mu_in = reinterpret_cast<const uint16_t*>(mu_in);
     fa.nb_dbg = reinterpret_cast<uint16_t*>(nb_dbg);
     const uint32_t wbytes = scores ? UPD_WBYTES : UPD_FN;
-    int nb = (int)((fz::SMEM_MAX - fz::smem_for(wbytes, 0)) / fz::B_STAGE);
+    const bool staging = mu_out != nullptr;
+    int nb = (int)((fz::SMEM_MAX - fz::smem_for(wbytes, staging, 0)) / fz::B_STAGE);
     fa.nb_stages = nb > fz::BS_MAX ? fz::BS_MAX : nb;
     const int64_t nitems = (int64_t)fa.plan.ntiles * ((fa.u.Bc + fz::PD - 1) / fz::PD);
-    launch_pdl(k_tc_fused, (int)(nitems < 1 ? 1 : (nitems < 148 ? nitems : 148)), fz::THREADS, fz::smem_for(wbytes, fa.nb_stages), st, fa);
+    launch_pdl(k_tc_fused, (int)(nitems < 1 ? 1 : (nitems < 148 ? nitems : 148)), fz::THREADS, fz::smem_for(wbytes, staging, fa.nb_stages), st, fa);
     ++*launches;
 }
 

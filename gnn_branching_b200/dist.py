@@ -45,6 +45,31 @@ def gather_winners(best: torch.Tensor, idx: torch.Tensor, B_total: int, group=No
     return unpack_winners(torch.cat(parts, 0))
 
 
+_GATHER_BUF = {}
+
+
+def gather_winner_records(records: torch.Tensor, B_total: int, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """All-gather of the packed winner records ``[n, 2]`` int32 (``Scorer.score_winners``: the argmax kernel wrote them) of
+    every rank's shard into frontier order.  With equal shards (B_total divisible by the world size — the 65 536-subdomain
+    frontier on 2 / 4 / 8 GPUs) the collective reads the records and writes the persistent result buffer directly: no pack,
+    pad or concatenate pass; ragged shards go through ``gather_winners``.  Returns (best_score [B_total] f32, best_idx i32)
+    as views of the gathered buffer."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return unpack_winners(records)
+    if B_total % world != 0:
+        return gather_winners(*unpack_winners(records), B_total, group=group)
+    n = B_total // world
+    if records.shape[0] != n:
+        raise ValueError(f'rank shard has {records.shape[0]} records, expected {n}')
+    key = (B_total, world, records.device, id(group))
+    out = _GATHER_BUF.get(key)
+    if out is None:
+        out = _GATHER_BUF[key] = torch.empty(B_total, 2, dtype=torch.int32, device=records.device)
+    dist.all_gather_into_tensor(out, records.contiguous(), group=group)
+    return out[:, 0].view(torch.float32), out[:, 1]
+
+
 def broadcast_gnn_weights(model: torch.nn.Module, src: int = 0, group=None) -> int:
     """Rank ``src``'s GNN parameters to every rank, once, as one flat blob (117 825 floats = 471 KB for GraphNet(2, 64)): one
     collective instead of 52.  Returns the number of elements broadcast.  Every rank must call it."""

@@ -75,9 +75,14 @@ class Scorer:
         return int(self.lib.gnnb_launch_count(self.h))
 
     # ---- parameters ----
-    def set_gnn(self, state_dict: Dict[str, torch.Tensor], T: int = 2, p: int = 64, key=None):
-        """Upload the 52 GNN tensors (models/cifar_trained_gnn/*.pt loads unchanged)."""
-        if key is not None and key == self._gnn_key:
+    def set_gnn(self, state_dict: Dict[str, torch.Tensor], T: int = 2, p: int = 64, key=None, force: bool = False):
+        """Upload the 52 GNN tensors (models/cifar_trained_gnn/*.pt loads unchanged).
+
+        Caching contract: with a ``key`` the upload is skipped when the key equals the one of the last upload.  Callers
+        derive keys from (data_ptr, _version) of the tensors, which does NOT see writes that bypass the version counter
+        (``p.data.copy_()``, writes through a numpy view, some custom optimizers): after such writes pass ``force=True``
+        (or call ``invalidate()``)."""
+        if not force and key is not None and key == self._gnn_key:
             return
         missing = [k for k in STATE_DICT_KEYS if k not in state_dict]
         if missing:
@@ -89,8 +94,14 @@ class Scorer:
         self._gnn_key = key
         del keep
 
-    def set_network(self, net: NetSpec, key=None):
-        if key is not None and key == self._net_key:
+    def invalidate(self):
+        """Forget the cache keys: the next set_gnn / set_network uploads again whatever its key."""
+        self._gnn_key = None
+        self._net_key = None
+
+    def set_network(self, net: NetSpec, key=None, force: bool = False):
+        """Upload the verified network (same caching contract as ``set_gnn``)."""
+        if not force and key is not None and key == self._net_key:
             return
         descs = (_lib.LayerDesc * net.L)()
         keep = []
@@ -171,6 +182,25 @@ class Scorer:
                 self.check()
         return best, idx, scores
 
+    def score_winners(self, fr: Frontier, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Score every subdomain of ``fr`` (CUDA or pinned CPU) and return the winners as packed records on the GPU:
+        int32 ``[B, 2]`` = (bit pattern of the fp32 score, flat index) — the buffer the multi-GPU winner all-gather sends
+        (``dist.gather_winner_records``); ``out``: a preallocated ``[>= B, 2]`` int32 CUDA tensor to write into."""
+        if self.net is None:
+            raise RuntimeError('set_network first')
+        d, keep = self._frontier_desc(fr)
+        dev = torch.device('cuda', self.device)
+        if out is None:
+            out = torch.empty(fr.B, 2, dtype=torch.int32, device=dev)
+        if out.dtype != torch.int32 or not out.is_cuda or not out.is_contiguous() or out.shape[0] < fr.B or out.shape[1:] != (2,):
+            raise ValueError('out must be a contiguous int32 CUDA tensor [>= B, 2]')
+        if fr.B:
+            with torch.cuda.device(self.device):
+                stream = torch.cuda.current_stream().cuda_stream
+                self._ok(self.lib.gnnb_score_winners(self.h, C.byref(d), C.c_void_p(out.data_ptr()), None, C.c_void_p(stream)))
+        del keep
+        return out[:fr.B]
+
     def babsr(self, fr: Frontier, icp_score_counter=None, random_order=None, sparsest_layer: int = 0,
               decision_threshold: float = 0.001, return_scores: bool = False):
         """BaBSR / KW heuristic decisions for every subdomain of ``fr`` (plnn/kw_score_conv.py:41-156, batched).
@@ -189,7 +219,10 @@ class Scorer:
         dev = fr.device
         if random_order is None:                                  # relu_conv_gnnkwthreshold.py:98-101
             random_order = [sparsest_layer] + [k for k in range(L) if k != sparsest_layer] if sparsest_layer >= 0 else list(range(L))
-        order = (C.c_int32 * L)(*[int(k) for k in random_order])
+        random_order = [int(k) for k in random_order]
+        if sorted(random_order) != list(range(L)):                # a short list would be zero-padded silently, a long one overflow
+            raise ValueError(f'random_order must be a permutation of range({L}), got {random_order}')
+        order = (C.c_int32 * L)(*random_order)
         cin = None
         if icp_score_counter is not None:
             cin = torch.as_tensor(icp_score_counter, dtype=torch.int32).to(dev).contiguous()

@@ -126,6 +126,19 @@ int64_t gnnb_get_option(gnnb_ctx* ctx, const char* key);
 int gnnb_score(gnnb_ctx* ctx, const gnnb_frontier* in, float* best_score, int32_t* best_idx, float* scores,
                void* stream);
 
+/* The same scoring pass with the winners written as packed 8-byte records straight into a buffer a collective can send:
+ * the multi-GPU frontier (one context per GPU, contiguous shards) all-gathers exactly these records over NCCL / NVLink
+ * (SURVEY 8e), so no pack / pad / concatenate pass runs between the argmax kernel and the collective.
+ *   winners    [B] DEVICE records (score, index) — always device memory, also when `in->mem` is HOST (inputs are then
+ *              staged host -> device inside the call as in gnnb_score, the records stay on the GPU that scored them)
+ * Replaces the same reference lines as gnnb_score (graph_score.py:32-56).  Returns without synchronising when
+ * `in->mem` is DEVICE; with HOST inputs it returns after the staged copies and kernels have completed. */
+typedef struct gnnb_winner {
+    float score;                         /* -inf when the subdomain has no candidate */
+    int32_t index;                       /* flat index into the concatenated hidden layers, -1 when none */
+} gnnb_winner;
+int gnnb_score_winners(gnnb_ctx* ctx, const gnnb_frontier* in, gnnb_winner* winners, float* scores, void* stream);
+
 /* BaBSR / KW branching heuristic for B subdomains at once.  Replaces choose_node_conv (plnn/kw_score_conv.py:41-156),
  * the hand-written score the reference falls back to when the GNN decision did not improve the bound
  * (plnn/relu_conv_gnnkwthreshold.py:155-157).  Uses `in->lb`, `in->ub` (hidden layers), `in->wp`, `in->mask` and

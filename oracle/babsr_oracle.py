@@ -83,10 +83,11 @@ def babsr_decide(score: torch.Tensor, intercept: torch.Tensor, mask: torch.Tenso
         ic = [intercept[b, offs[k]:offs[k + 1]] for k in range(len(hidden_sizes))]
         mk = [mask[b, offs[k]:offs[k + 1]] for k in range(len(hidden_sizes))]
         max_info = [torch.max(s, 0) for s in sc]
-        # `max(max_info)` compares (value, index) tuples and `.index` returns the first equal entry: the first layer
-        # holding the largest maximum (exact ties between layers do not occur on real data)
+        # `max(max_info)` compares (value, index) tuples and `.index` returns the first equal entry: on equal maxima the
+        # layer whose in-layer argmax index is larger wins, the first layer among fully equal pairs
         vals = [float(v) for v, _ in max_info]
-        decision_layer = vals.index(max(vals))
+        pairs = [(float(v), int(i)) for v, i in max_info]
+        decision_layer = pairs.index(max(pairs))
         decision_index = int(max_info[decision_layer][1])
         if decision_layer != sparsest_layer and vals[decision_layer] > decision_threshold:
             decision, kind = [decision_layer, decision_index], 0

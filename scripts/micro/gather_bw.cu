@@ -3,7 +3,9 @@
 //   mode 1  cp.async.bulk.tensor.2d ... tile::gather4 (4 rows per instruction, SWIZZLE_128B), one issuing thread
 //   mode 2  cp.async.bulk (linear) of one 128-byte row per instruction, one issuing thread
 // Rows are 64 fp16 = 128 B; a "stage" is 64 rows (8 KB, one K step of the fused kernel: 16 rows x 2 subdomains x 2 planes);
-// a ring of NST stages is kept in flight.  Row indices: runs of `run` consecutive rows at random places of the table.
+// a ring of NST stages is kept in flight.  Row indices: runs of `run` consecutive rows at random places of a window of the
+// table that slides forward with the iteration (argv[4] MB, 0 = the whole table: TLB-hostile), like a wave of subdomains.
+// usage: gather_bw [rows] [iters] [box_rows 1|4] [window_MB]
 // Prints bytes / cycle / SM and checks the landed data (row id in the first word of every 16-byte chunk).
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o build/gather_bw scripts/micro/gather_bw.cu -lcuda
 #include <cuda.h>
@@ -47,7 +49,7 @@ __global__ void __launch_bounds__(160, 1) k(int mode, int nst, int iters, const 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const long long t0 = clock64();
+    long long t0 = clock64();
     if (mode == 0) {
         if (warp < 4) {      // warp w copies rows [16 w, 16 w + 16) of every stage: 4 rows x 8 chunks per instruction
             for (int it = 0; it < iters + nst; ++it) {
@@ -66,8 +68,11 @@ __global__ void __launch_bounds__(160, 1) k(int mode, int nst, int iters, const 
                     cp_async_arrive(smem_u32(&full[s]));
                 }
             }
+            if (threadIdx.x == 0) out[blockIdx.x] = clock64() - t0;      // timed by a thread that walked the loop
         }
-    } else if (threadIdx.x == 128) {
+    } else if (warp == 4) {
+      if (lane == 0) {
+        t0 = clock64();
         for (int it = 0; it < iters + nst; ++it) {
             const int s = it % nst;
             if (it >= nst) mbar_wait(smem_u32(&full[s]), ((it / nst) - 1) & 1);
@@ -83,10 +88,11 @@ __global__ void __launch_bounds__(160, 1) k(int mode, int nst, int iters, const 
                 }
             }
         }
+        out[blockIdx.x] = clock64() - t0;
+      }
+      __syncwarp();
     }
     __syncthreads();
-    const long long t1 = clock64();
-    if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
     // check the last stage that landed (iteration iters - 1)
     const int s = (iters - 1) % nst;
     int bad = 0;
@@ -103,6 +109,8 @@ __global__ void __launch_bounds__(160, 1) k(int mode, int nst, int iters, const 
 int main(int argc, char** argv) {
     const long long nrows = argc > 1 ? atoll(argv[1]) : (8ll << 20);       // 8 Mi rows = 1 GiB
     const int iters = argc > 2 ? atoi(argv[2]) : 2000;
+    const int boxrows_arg = argc > 3 ? atoi(argv[3]) : 1;
+    const long long window_rows = (argc > 4 ? atoll(argv[4]) : 32) * 8192ll;          // MB -> rows of 128 B
     CK(cudaSetDevice(0));
     unsigned char* table;
     CK(cudaMalloc(&table, (size_t)nrows * 128));
@@ -119,7 +127,7 @@ int main(int argc, char** argv) {
     int* drows;
     CK(cudaMalloc(&drows, (size_t)grid * iters * ROWS_PER_STAGE * sizeof(int)));
     CUtensorMap tm;
-    for (int boxrows : {1, 4}) {
+    for (int boxrows : {boxrows_arg}) {
         const cuuint64_t dims[2] = {64, (cuuint64_t)nrows};
         const cuuint64_t strides[1] = {128};
         const cuuint32_t box[2] = {64, (cuuint32_t)boxrows};
@@ -133,17 +141,24 @@ int main(int argc, char** argv) {
             uint64_t st = 88172645463325252ull;
             for (size_t i = 0; i < h.size(); i += run) {
                 st ^= st << 13; st ^= st >> 7; st ^= st << 17;
-                const long long r0 = (long long)(st % (uint64_t)(nrows - run));
+                long long r0 = (long long)(st % (uint64_t)(nrows - run));
+                if (window_rows > 0) {      // window start moves with the iteration index (same for every CTA)
+                    const long long itn = (long long)((i / ROWS_PER_STAGE) % iters);
+                    const long long w0 = (nrows - window_rows - run) * itn / iters;
+                    r0 = w0 + (long long)(st % (uint64_t)window_rows);
+                }
                 for (int j = 0; j < run && i + j < h.size(); ++j) h[i + j] = (int)(r0 + j);
             }
             CK(cudaMemcpy(drows, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
             for (int mode = 0; mode < 3; ++mode)
                 for (int nst : {4, 8, 16}) {
-                    if (boxrows == 4 && mode != 1) continue;                // the tensor map only matters for mode 1
+                    if (boxrows != 1 && mode != 1) continue;                // the tensor map only matters for mode 1
                     CK(cudaMemset(errs, 0, sizeof(int)));
                     const size_t smem = 1024 + (size_t)nst * STAGE_BYTES;
                     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    CK(cudaMemset(out, 0, grid * sizeof(long long)));
                     k<<<grid, 160, smem>>>(mode, nst, iters, tm, table, drows, out, errs);
+                    CK(cudaGetLastError());
                     cudaError_t e = cudaDeviceSynchronize();
                     if (e != cudaSuccess) { printf("mode %d nst %d run %d box %d: %s\n", mode, nst, run, boxrows, cudaGetErrorString(e)); return 1; }
                     std::vector<long long> cyc(grid);

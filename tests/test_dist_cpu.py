@@ -142,3 +142,38 @@ def test_weights_are_broadcast_once_from_rank_0_gloo():
         p.join(timeout=60)
     assert all(r[1] == 117825 and r[2] for r in res), res
     assert not res[0][3] and res[1][3]                  # rank 0 keeps its parameters, rank 1 received them
+
+
+def _records_worker(rank, world, port, B, q):
+    from gnn_branching_b200.dist import gather_winner_records
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(1)
+    score = torch.randn(B, generator=g)
+    score[1] = float('-inf')
+    idx = torch.randint(-1, 3172, (B,), generator=g, dtype=torch.int32)
+    s, e = shard_range(B, rank, world)
+    ok = True
+    for _ in range(2):          # the second call reuses the persistent result buffer
+        best, flat = gather_winner_records(pack_winners(score[s:e], idx[s:e]), B)
+        ok = ok and torch.equal(best.view(torch.int32), score.view(torch.int32)) and torch.equal(flat, idx)
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_winner_records_two_ranks_gloo():
+    """The packed (score, index) records the argmax kernel writes are all-gathered as they are (equal shards) or through
+    the padded path (ragged shards)."""
+    for B in (8, 7):
+        port = _free_port()
+        ctx = mp.get_context('spawn')
+        q = ctx.Queue()
+        procs = [ctx.Process(target=_records_worker, args=(r, 2, port, B, q)) for r in range(2)]
+        for p in procs:
+            p.start()
+        res = [q.get(timeout=120) for _ in procs]
+        for p in procs:
+            p.join(timeout=60)
+        assert all(ok for _, ok in res), res
