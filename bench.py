@@ -341,10 +341,14 @@ def measure_device(scorer, fronts, B, K, W, world, dev, local, gather):
         scorer.set_network(fr.net, key=fr.net.key)
         return scorer.score(fr, return_scores=False, check=False)
 
+    rec = torch.empty(B, 2, dtype=torch.int32, device=dev) if world > 1 else None
+
     def step(i):
-        best, idx, _ = score(fronts[i % len(fronts)])
-        if world > 1:
-            best, idx = gather(best, idx, B * world)
+        fr = fronts[i % len(fronts)]
+        if world > 1:      # the argmax kernel writes the packed (score, index) records the all-gather sends
+            scorer.set_network(fr.net, key=fr.net.key)
+            return gather(scorer.score_winners(fr, out=rec), B * world)
+        best, idx, _ = score(fr)
         return best, idx
 
     def barrier():
@@ -391,14 +395,24 @@ def measure_e2e(model, host_fronts, B, K, W, world, dev, gather):
             dist.barrier()
         torch.cuda.synchronize()
 
+    scorer = model.scorer(dev.index)
+    rec = torch.empty(B, 2, dtype=torch.int32, device=dev) if world > 1 else None
+
+    def step(i):
+        fr = host_fronts[i % len(host_fronts)]
+        if world == 1:
+            return model.score_frontier(fr, return_scores=False)
+        # inputs staged host -> device inside the call, records stay on the GPU, all-gather, then the whole frontier's winners are
+        # read back by every rank (the device -> host read of the step's result)
+        best, idx = gather(scorer.score_winners(fr, out=rec), B * world)
+        return best.cpu(), idx.cpu()
+
     for i in range(min(W, 2)):
-        model.score_frontier(host_fronts[i % len(host_fronts)], return_scores=False)
+        step(i)
     barrier()
     t0 = time.perf_counter()
     for i in range(K):
-        hb, hi, _ = model.score_frontier(host_fronts[i % len(host_fronts)], return_scores=False)
-        if world > 1:
-            gather(hb.to(dev), hi.to(dev), B * world)
+        step(i)
     barrier()
     dt = time.perf_counter() - t0
     if world > 1:
@@ -406,7 +420,9 @@ def measure_e2e(model, host_fronts, B, K, W, world, dev, gather):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     return {'value': B * world * K / dt, 'unit': UNIT, 'h2d_bytes_per_step': host_fronts[0].input_bytes(),
-            'd2h_bytes_per_step': B * 8, 'api': 'GraphNet.score_frontier(pinned host Frontier)'}
+            'd2h_bytes_per_step': B * world * 8 if world > 1 else B * 8,
+            'api': 'GraphNet.score_frontier(pinned host Frontier)' if world == 1 else
+                   'Scorer.score_winners(pinned host Frontier) + dist.gather_winner_records + read-back of all winners'}
 
 
 def load_peaks():
@@ -453,7 +469,7 @@ def main():
     import torch
     import torch.distributed as dist
     from gnn_branching_b200 import GraphNet, synthetic_frontier
-    from gnn_branching_b200.dist import gather_winners
+    from gnn_branching_b200.dist import gather_winner_records
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -488,14 +504,14 @@ def main():
         scorer.set_option(key, int(val))
     math_mode = {0: 'tc', 1: 'simt'}[scorer.get_option('math')]
 
-    m = measure_device(scorer, fronts, B, K, W, world, dev, local, gather_winners)
+    m = measure_device(scorer, fronts, B, K, W, world, dev, local, gather_winner_records)
     value, ms, launches, clocks = m['value'], m['ms'], m['launches'], m['clocks']
 
     # ---- end to end through the public API with pinned HOST buffers (copies inside the timed region) ----
     e2e = None
     if not args.no_e2e:
         host_fronts = [f.cpu().pin() for f in fronts]
-        e2e = measure_e2e(model, host_fronts, B, K, W, world, dev, gather_winners)
+        e2e = measure_e2e(model, host_fronts, B, K, W, world, dev, gather_winner_records)
         del host_fronts
 
     if rank != 0:
@@ -540,9 +556,9 @@ def main():
                 net2, lbs2, ubs2, wp2, bp2 = load_problem(wl)
                 B2 = DEFAULT_DOMAINS[wl]
                 fr2 = [synthetic_frontier(net2, lbs2, ubs2, wp2, bp2, B2, seed=1000 * (17 + i) + len(wl), device=dev) for i in range(2)]
-                m2 = measure_device(scorer, fr2, B2, 20, 3, 1, dev, local, gather_winners)
+                m2 = measure_device(scorer, fr2, B2, 20, 3, 1, dev, local, gather_winner_records)
                 hf2 = [fr2[0].cpu().pin()]
-                e2 = measure_e2e(model, hf2, B2, 3, 1, 1, dev, gather_winners)
+                e2 = measure_e2e(model, hf2, B2, 3, 1, 1, dev, gather_winner_records)
                 del hf2
                 others[wl] = {'value': m2['value'], 'unit': UNIT, 'ms_per_step': m2['ms'] / 20, 'steps': 20, 'warmup': 3,
                               'workload': f'cifar_{wl}_kw x {B2} synthetic subdomains per step', 'gpu_launches': m2['launches'],

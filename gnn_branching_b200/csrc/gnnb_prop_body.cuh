@@ -13,6 +13,11 @@ struct PropPlanDev {
     const uint16_t* a_planes;     // [nchunks][2][128 * 64] hi plane then lo plane, 32 KB per chunk
     const int32_t* tile_chunk0;   // [ntiles + 1] first chunk of each tile
     const int32_t* ksteps;        // [nchunks] K = 16 steps that hold data (1..4)
+    // the same plan per K step (16 input rows), for the fused kernel (gnnb_tc.cu, k_tc_fused): the steps that hold data only
+    const int32_t* tile_ks0;      // [ntiles + 1] first K step of each tile
+    const int32_t* ks_rows;       // [nksteps][16] input slot of each K row, -1 = zero row
+    const uint16_t* ks_w;         // [nksteps] 8 KB weight blocks: [hi plane 4 KB][lo plane 4 KB], each 128 x 16 fp16 K-major without
+                                  // swizzle, "piece-major": the 16-byte piece p (K 8p .. 8p + 7) of row m at p * 2048 + m * 16
     int ntiles;                   // tiles of the output layer = its slots / 128
     int nslots_in, nslots_out;    // rows per subdomain of the input / output layer (slot order, gnnb_common.cuh)
 };
@@ -21,6 +26,7 @@ struct PropPlanDev {
 struct PropPlan;
 const PropPlanDev& prop_plan_dev(const PropPlan* p);
 double prop_plan_chunks_per_tile(const PropPlan* p);
+double prop_plan_ksteps_per_tile(const PropPlan* p);
 
 namespace prop {
 

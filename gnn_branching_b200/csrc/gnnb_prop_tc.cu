@@ -22,7 +22,7 @@ namespace gnnb {
 struct PropPlan {
     PropPlanDev dev{};
     void* blob = nullptr;
-    int nchunks = 0;
+    int nchunks = 0, nksteps = 0;
     double density = 0.0;         // useful MACs / issued MACs
 };
 
@@ -82,8 +82,8 @@ std::vector<std::vector<int>> range_tiles(int n) {
 }
 
 PropPlan* build_plan(const LayerTiling& out, const LayerTiling& in, const EdgeFn& edges) {
-    std::vector<int32_t> in_rows, tile_chunk0, ksteps;
-    std::vector<uint16_t> planes;
+    std::vector<int32_t> in_rows, tile_chunk0, ksteps, tile_ks0, ks_rows;
+    std::vector<uint16_t> planes, ks_w;
     std::vector<Edge> ev;
     double useful = 0.0, issued = 0.0;
     for (int t = 0; t < out.ntiles; ++t) {
@@ -115,6 +115,26 @@ PropPlan* build_plan(const LayerTiling& out, const LayerTiling& in, const EdgeFn
         std::vector<float> dense((size_t)TILE * Kp, 0.f);
         for (int m = 0; m < TILE; ++m)
             for (const Edge& e : row_edges[m]) dense[(size_t)m * Kp + col[e.in]] += e.w;
+        // per-K-step form (fused kernel): K steps [0, ceil(K / 16)) of this tile, at least one
+        tile_ks0.push_back((int32_t)(ks_rows.size() / 16));
+        {
+            const int nks = std::max(1, (K + 15) / 16);
+            const size_t r0 = ks_rows.size(), w0 = ks_w.size();
+            ks_rows.resize(r0 + (size_t)nks * 16, -1);
+            for (const auto& kv : col) ks_rows[r0 + kv.second] = kv.first;
+            ks_w.resize(w0 + (size_t)nks * 4096, 0);                        // 8 KB = 4096 fp16 per K step
+            for (int m = 0; m < TILE; ++m)
+                for (int k = 0; k < K; ++k) {
+                    const float x = dense[(size_t)m * Kp + k];
+                    if (x == 0.f) continue;
+                    uint16_t hi, lo;
+                    split_host(x, hi, lo);
+                    const int j = k / 16, pce = (k % 16) / 8, e = k % 8;
+                    const size_t el = w0 + (size_t)j * 4096 + (size_t)pce * 1024 + (size_t)m * 8 + e;      // fp16 elements: piece 2 KB = 1024
+                    ks_w[el] = hi;
+                    ks_w[el + 2048] = lo;                                                                  // lo plane 4 KB further
+                }
+        }
         for (int m = 0; m < TILE; ++m)
             for (int k = 0; k < K; ++k) {
                 const float x = dense[(size_t)m * Kp + k];
@@ -129,13 +149,16 @@ PropPlan* build_plan(const LayerTiling& out, const LayerTiling& in, const EdgeFn
             }
     }
     tile_chunk0.push_back((int32_t)ksteps.size());
+    tile_ks0.push_back((int32_t)(ks_rows.size() / 16));
     PropPlan* p = new PropPlan();
     p->nchunks = (int)ksteps.size();
+    p->nksteps = (int)(ks_rows.size() / 16);
     p->density = issued > 0 ? useful / issued : 0.0;
     const size_t b_planes = planes.size() * sizeof(uint16_t), b_in = in_rows.size() * 4,
-                 b_tc = tile_chunk0.size() * 4, b_ks = ksteps.size() * 4;
+                 b_tc = tile_chunk0.size() * 4, b_ks = ksteps.size() * 4, b_tk = tile_ks0.size() * 4, b_kr = ks_rows.size() * 4,
+                 b_kw = ks_w.size() * sizeof(uint16_t);
     auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
-    const size_t total = up(b_planes) + up(b_in) + up(b_tc) + up(b_ks);
+    const size_t total = up(b_planes) + up(b_in) + up(b_tc) + up(b_ks) + up(b_tk) + up(b_kr) + up(b_kw);
     if (cudaMalloc(&p->blob, total) != cudaSuccess) { delete p; return nullptr; }
     unsigned char* d = reinterpret_cast<unsigned char*>(p->blob);
     size_t off = 0;
@@ -149,6 +172,9 @@ PropPlan* build_plan(const LayerTiling& out, const LayerTiling& in, const EdgeFn
     p->dev.in_rows = reinterpret_cast<const int32_t*>(put(in_rows.data(), b_in));
     p->dev.tile_chunk0 = reinterpret_cast<const int32_t*>(put(tile_chunk0.data(), b_tc));
     p->dev.ksteps = reinterpret_cast<const int32_t*>(put(ksteps.data(), b_ks));
+    p->dev.ks_w = reinterpret_cast<const uint16_t*>(put(ks_w.data(), b_kw));
+    p->dev.tile_ks0 = reinterpret_cast<const int32_t*>(put(tile_ks0.data(), b_tk));
+    p->dev.ks_rows = reinterpret_cast<const int32_t*>(put(ks_rows.data(), b_kr));
     p->dev.ntiles = out.ntiles;
     p->dev.nslots_in = (int)in.node_of_slot.size();
     p->dev.nslots_out = (int)out.node_of_slot.size();
@@ -250,6 +276,7 @@ void prop_plan_free(PropPlan* p) {
 
 double prop_plan_density(const PropPlan* p) { return p ? p->density : 0.0; }
 const PropPlanDev& prop_plan_dev(const PropPlan* p) { return p->dev; }
+double prop_plan_ksteps_per_tile(const PropPlan* p) { return p->dev.ntiles > 0 ? (double)p->nksteps / p->dev.ntiles : 1.0; }
 double prop_plan_chunks_per_tile(const PropPlan* p) { return p->dev.ntiles > 0 ? (double)p->nchunks / p->dev.ntiles : 1.0; }
 
 void prop_tc_run(const PropPlan* plan, const float* mu_img, float* nb_img, int Bc, cudaStream_t st, int64_t* launches, int gather_prefetch) {

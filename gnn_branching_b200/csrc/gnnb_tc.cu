@@ -556,29 +556,30 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_update(UpdArgs a) {
 namespace fz {
 constexpr int PD = 2;                               // subdomains per item = accumulator columns / 64
 constexpr int CW = 2;                               // chain warpgroups = PD
-constexpr int WS = 2;                               // weight ring stages
-constexpr int BS_MAX = 12;
-constexpr uint32_t W_STAGE = 2 * APLANE;            // 32 KB: one 64-row K chunk of the weight block, hi + lo plane
-constexpr uint32_t B_ROWS = 16;                     // input nodes per B stage = one K step
+constexpr int NS_MAX = 8;                           // ring stages (one K step each)
+constexpr uint32_t W_KS = 8192;                     // weight block of one K step: [hi 128 x 16][lo 128 x 16] fp16, no swizzle
+constexpr uint32_t B_ROWS = 16;                     // input nodes per stage = one K step
 constexpr uint32_t B_DOM = B_ROWS * 128;            // 2 KB: one plane of one subdomain
 constexpr uint32_t B_PLANE = PD * B_DOM;            // 4 KB
 constexpr uint32_t B_STAGE = 2 * B_PLANE;           // 8 KB
+constexpr uint32_t STAGE = W_KS + B_STAGE;          // 16 KB: everything the three MMAs of a K step read
 constexpr uint32_t STG_PLANE = 32 * 128;            // 4 KB: a warp's 32 rows of one plane of a mu tile image
 constexpr uint32_t STG_WARP = 2 * STG_PLANE;        // 8 KB: hi + lo
 constexpr uint32_t STG_BYTES = CW * 4 * STG_WARP;   // 64 KB, only in launches that store embeddings
 constexpr int THREADS = 512;
-constexpr int GATHER_WARP0 = 2, GATHER_WARPS = 4, CHAIN_WARP0 = 8;
+constexpr int GATHER_WARP0 = 2, GATHER_WARPS = 6, CHAIN_WARP0 = 8;
 constexpr uint32_t ACC_COL = 0, ACC_WIN = PD * 64, D_COL = 256, D_WIN = 128;
 
 struct Tail {
     float bias[4][P];           // pre-scaled by ASCALE
     float vec[P];
-    uint64_t wts, w_full[WS], w_empty[WS], b_full[BS_MAX], b_empty[BS_MAX], acc_full[2], acc_empty[2], mma[CW];
+    uint64_t wts, full[NS_MAX], empty[NS_MAX], acc_full[2], acc_empty[2], mma[CW];
     uint32_t tmem_slot;
     int32_t wcnt[CW][4];
 };
-constexpr size_t smem_for(uint32_t wbytes, bool staging, int nb_stages) {
-    return 1024 + wbytes + WS * W_STAGE + (staging ? STG_BYTES : 0) + (size_t)nb_stages * B_STAGE + sizeof(Tail);
+// staging: 0 = none (nothing stored), 1 = one plane per warp (score-head launches), 2 = both planes
+constexpr size_t smem_for(uint32_t wbytes, int staging, int n_stages) {
+    return 1024 + wbytes + (size_t)staging * (STG_BYTES / 2) + (size_t)n_stages * STAGE + sizeof(Tail);
 }
 constexpr size_t SMEM_MAX = 232448;                 // 227 KB: the per-block opt-in limit of sm_100
 }  // namespace fz
@@ -588,7 +589,8 @@ struct FusedArgs {
     PropPlanDev plan;
     const uint16_t* mu_in;      // mu images of the layer the propagation reads
     uint16_t* nb_dbg;           // snapshots only: the nb tile images the two-launch path would have written, or null
-    int nb_stages;
+    int n_stages;               // ring stages that fit beside the chain weights and the staging buffers (6 .. 8)
+    int mma_group;              // K steps the propagation issues per pass of its loop (1 .. 4)
 };
 
 // two 16-column tensor-memory loads in flight, then both -> fp32
@@ -617,12 +619,15 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 // any kind — 32-byte direct stores, coalesced 16-byte stores, a bulk store waited for — puts that on the chain's path
 // [measured, profiles/r02_fused_phase_trace.log]).  TO_A: the values also become the next A operand (score head).  img: the
 // tile image in global memory or null (nothing is stored).  Returns true on NaN in a valid row.  Warp-synchronous.
+// TO_A (score head launches, which need 16 KB more weights): the buffer is 4 KB — the hi plane leaves first, the lo plane
+// (kept in registers) follows once the first bulk store has read the buffer.
 template <bool TO_A>
 __device__ __forceinline__ bool epilogue_to_mu_warp(const WG& c, uint32_t dcol, const float* __restrict__ bias_s, float rowscale,
                                                     bool valid, unsigned char* img, uint32_t stage) {
     bool bad = false;
     const uint32_t rl = (uint32_t)c.t & 31u;                       // row within the warp's 32 rows = lane
     unsigned char* dst = img + ((uint32_t)c.t >> 5) * fz::STG_PLANE;
+    uint32_t lo[TO_A ? 32 : 1];
     if (img != nullptr) {
         if (rl == 0) bulk_wait_read();                              // the previous tile's bulk stores have read the buffer
         __syncwarp();
@@ -648,19 +653,38 @@ __device__ __forceinline__ bool epilogue_to_mu_warp(const WG& c, uint32_t dcol, 
                 const uint32_t o0 = stage + swz(rl, (uint32_t)(2 * q)), o1 = stage + swz(rl, (uint32_t)(2 * q + 1));
                 sts128(o0, w[0], w[1], w[2], w[3]);
                 sts128(o1, w[4], w[5], w[6], w[7]);
-                sts128(o0 + fz::STG_PLANE, w[8], w[9], w[10], w[11]);
-                sts128(o1 + fz::STG_PLANE, w[12], w[13], w[14], w[15]);
+                if (!TO_A) {
+                    sts128(o0 + fz::STG_PLANE, w[8], w[9], w[10], w[11]);
+                    sts128(o1 + fz::STG_PLANE, w[12], w[13], w[14], w[15]);
+                }
             }
-            if (TO_A) tmem_st16(c.tmem + c.acol + 16 * q, w);
+            if (TO_A) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) lo[q * 8 + i] = w[8 + i];
+                tmem_st16(c.tmem + c.acol + 16 * q, w);
+            }
         }
     }
     if (img != nullptr) {
         fence_proxy_async();             // the staging stores are generic-proxy writes, the bulk stores read through the async proxy
         __syncwarp();
-        if (rl == 0) {
-            bulk_s2g_nocommit(dst, stage, fz::STG_PLANE);
-            bulk_s2g_nocommit(dst + APLANE, stage + fz::STG_PLANE, fz::STG_PLANE);
-            bulk_commit();
+        if (!TO_A) {
+            if (rl == 0) {
+                bulk_s2g_nocommit(dst, stage, fz::STG_PLANE);
+                bulk_s2g_nocommit(dst + APLANE, stage + fz::STG_PLANE, fz::STG_PLANE);
+                bulk_commit();
+            }
+        } else {
+            if (rl == 0) { bulk_s2g(dst, stage, fz::STG_PLANE); bulk_wait_read(); }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                sts128(stage + swz(rl, (uint32_t)(2 * q)), lo[q * 8], lo[q * 8 + 1], lo[q * 8 + 2], lo[q * 8 + 3]);
+                sts128(stage + swz(rl, (uint32_t)(2 * q + 1)), lo[q * 8 + 4], lo[q * 8 + 5], lo[q * 8 + 6], lo[q * 8 + 7]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (rl == 0) bulk_s2g(dst + APLANE, stage, fz::STG_PLANE);
         }
     }
     return bad && valid;
@@ -673,17 +697,18 @@ __global__ void __launch_bounds__(fz::THREADS, 1) k_tc_fused(FusedArgs fa) {
     const PropPlanDev& plan = fa.plan;
     const bool with_score = a.scores != nullptr;
     const uint32_t wbytes = with_score ? UPD_WBYTES : UPD_FN;          // the fnode planes are only needed by the score head
-    const int NB = fa.nb_stages;
+    const int NS = fa.n_stages;
     unsigned char* base = smem_dyn();
     base += (1024u - (smem_u32(base) & 1023u)) & 1023u;
-    const uint32_t stg_bytes = a.mu_out != nullptr ? STG_BYTES : 0u;
-    const uint32_t W = smem_u32(base), w_ring = W + wbytes, stg = w_ring + WS * W_STAGE, b_ring = stg + stg_bytes;
-    fz::Tail* tl = reinterpret_cast<fz::Tail*>(base + wbytes + WS * W_STAGE + stg_bytes + (size_t)NB * B_STAGE);
+    const uint32_t stg_warp = a.mu_out == nullptr ? 0u : (with_score ? STG_PLANE : STG_WARP), stg_bytes = CW * 4 * stg_warp;
+    const uint32_t W = smem_u32(base), stg = W + wbytes, ring = stg + stg_bytes;
+    fz::Tail* tl = reinterpret_cast<fz::Tail*>(base + wbytes + stg_bytes + (size_t)NS * STAGE);
     const int warp = uniform((int)(threadIdx.x >> 5)), lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         mbar_init(smem_u32(&tl->wts), 1);
-        for (int i = 0; i < WS; ++i) { mbar_init(smem_u32(&tl->w_full[i]), 1); mbar_init(smem_u32(&tl->w_empty[i]), 1); }
-        for (int i = 0; i < NB; ++i) { mbar_init(smem_u32(&tl->b_full[i]), GATHER_WARPS * 32); mbar_init(smem_u32(&tl->b_empty[i]), 1); }
+        // a stage is full when its weight block has landed (1 arrival + its bytes) and the 32 lanes of the gather warp that owns
+        // it have seen their copies land; it is empty again when the step's MMAs have completed (tcgen05.commit)
+        for (int i = 0; i < NS; ++i) { mbar_init(smem_u32(&tl->full[i]), 1 + 32); mbar_init(smem_u32(&tl->empty[i]), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tl->acc_full[i]), 1); mbar_init(smem_u32(&tl->acc_empty[i]), PD); }
         for (int i = 0; i < CW; ++i) mbar_init(smem_u32(&tl->mma[i]), 1);
         fence_mbar_init();
@@ -713,29 +738,31 @@ __global__ void __launch_bounds__(fz::THREADS, 1) k_tc_fused(FusedArgs fa) {
     const int rank = (int)blockIdx.x, nranks = (int)gridDim.x;
 
     if (warp == 0) {
-        // ---- propagation weight blocks ----
+        // ---- propagation weight blocks: 8 KB per K step into the W half of the step's ring stage ----
         if (lane == 0) {
-            uint32_t ws = 0, wph = 0;
+            uint32_t t = 0;
             for (int64_t item = rank; item < nitems; item += nranks) {
                 const int tile = (int)(item % ntiles);
-                const int ch0 = plan.tile_chunk0[tile], ch1 = plan.tile_chunk0[tile + 1];
-                for (int ch = ch0; ch < ch1; ++ch) {
-                    mbar_wait(smem_u32(&tl->w_empty[ws]), wph ^ 1u);
-                    const uint32_t full = smem_u32(&tl->w_full[ws]);
-                    mbar_expect_tx(full, W_STAGE);
-                    bulk_g2s(w_ring + ws * W_STAGE, plan.a_planes + (size_t)ch * (W_STAGE / 2), W_STAGE, full);
-                    if (++ws == WS) { ws = 0; wph ^= 1u; }
+                const int ks0 = plan.tile_ks0[tile], ks1 = plan.tile_ks0[tile + 1];
+                for (int ks = ks0; ks < ks1; ++ks, ++t) {
+                    const uint32_t slot = t % (uint32_t)NS, ph = (t / (uint32_t)NS) & 1u;
+                    mbar_wait(smem_u32(&tl->empty[slot]), ph ^ 1u);
+                    const uint32_t full = smem_u32(&tl->full[slot]);
+                    mbar_expect_tx(full, W_KS);
+                    bulk_g2s(ring + slot * STAGE, plan.ks_w + (size_t)ks * (W_KS / 2), W_KS, full);
                 }
             }
         }
     } else if (warp == 1) {
         // ---- propagation MMAs: the whole warp walks the loop (uniform control and operands), one elected lane issues ----
-        // D fp32, A fp16 K-major, B fp16 MN-major (bit 16), M = 128, N = 128
+        // D fp32, A fp16 K-major (no swizzle), B fp16 MN-major SWIZZLE_128B (bit 16), M = 128, N = 128
         const uint32_t idesc = (1u << 4) | (1u << 16) | ((uint32_t)(PD * 64 >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
-        uint32_t ws = 0, wph = 0, bs = 0, bph = 0, it = 0;
+        uint32_t t = 0, it = 0;
+        const int group = fa.mma_group;
+        uint32_t lag_slot0 = 0, lag_slot1 = 0, lag_ph0 = 0, lag_ph1 = 0;       // last step of the group before the previous one / of the previous one
+        bool have_lag = false, have_prev = false;
 #ifdef GNNB_TRACE
-        long long t_acc = 0, t_w = 0, t_b = 0, t_all = clock64(), t0_;
-        int n_ks = 0;
+        long long t_acc = 0, t_b = 0, t_lag = 0, t_all = clock64(), t0_;
 #define FTR_BEGIN() t0_ = clock64()
 #define FTR_END(x) x += clock64() - t0_
 #else
@@ -744,7 +771,7 @@ __global__ void __launch_bounds__(fz::THREADS, 1) k_tc_fused(FusedArgs fa) {
 #endif
         for (int64_t item = rank; item < nitems; item += nranks, ++it) {
             const int tile = (int)(item % ntiles);
-            const int ch0 = uniform(plan.tile_chunk0[tile]), ch1 = uniform(plan.tile_chunk0[tile + 1]);
+            const int ks0 = uniform(plan.tile_ks0[tile]), ks1 = uniform(plan.tile_ks0[tile + 1]);
             const uint32_t buf = it & 1u, bufph = (it >> 1) & 1u;
             FTR_BEGIN();
             mbar_wait(smem_u32(&tl->acc_empty[buf]), bufph ^ 1u);     // the chains of item it - 2 no longer read these A columns
@@ -752,111 +779,93 @@ __global__ void __launch_bounds__(fz::THREADS, 1) k_tc_fused(FusedArgs fa) {
             tc_fence_after();
             const uint32_t d = (tmem_base & 0x0000FFFFu) + ACC_COL + buf * ACC_WIN;
             uint32_t accum = 0;
-            for (int ch = ch0; ch < ch1; ++ch) {
+            // K steps are issued in groups of up to GROUP: one pass through the loop costs ~350 cycles of waits, fences and
+            // descriptor arithmetic whatever it issues, a K step's three N = 128 MMAs 192 cycles of tensor time.  The tensor pipe
+            // executes MMAs in issue order, so a group is only issued when the group before the previous one has completed: a
+            // chain GEMM issued meanwhile waits for at most two groups.
+            for (int ks = ks0; ks < ks1;) {
+                const int n = ks1 - ks < group ? ks1 - ks : group;
                 FTR_BEGIN();
-                mbar_wait(smem_u32(&tl->w_full[ws]), wph);
-                FTR_END(t_w);
-                const int nks = uniform(plan.ksteps[ch]);
-                const uint32_t wa = w_ring + ws * W_STAGE;
-                const uint64_t a_hi = make_desc(wa), a_lo = make_desc(wa + APLANE);
-#ifdef GNNB_TRACE
-                n_ks += nks;
-#endif
-                for (int ks = 0; ks < nks; ++ks) {
+                if (have_lag) mbar_wait(smem_u32(&tl->empty[lag_slot0]), lag_ph0);
+                FTR_END(t_lag);
+                lag_slot0 = lag_slot1; lag_ph0 = lag_ph1; have_lag = have_prev;
+                for (int i = 0; i < n; ++i, ++t) {
+                    const uint32_t slot = t % (uint32_t)NS, ph = (t / (uint32_t)NS) & 1u;
                     FTR_BEGIN();
-                    mbar_wait(smem_u32(&tl->b_full[bs]), bph);
+                    mbar_wait(smem_u32(&tl->full[slot]), ph);
                     FTR_END(t_b);
                     tc_fence_after();
-                    const uint32_t ba = b_ring + bs * B_STAGE;
-                    const uint64_t b_hi = make_desc_mn(ba, B_DOM), b_lo = make_desc_mn(ba + B_PLANE, B_DOM);
-                    const uint64_t ah = a_hi + (uint64_t)(2 * ks), al = a_lo + (uint64_t)(2 * ks);
+                    const uint32_t sa = ring + slot * STAGE, sb = sa + W_KS;
+                    const uint64_t a_hi = make_desc_nosw(sa, NB_PIECE, 128u), a_lo = make_desc_nosw(sa + W_KS / 2, NB_PIECE, 128u);
+                    const uint64_t b_hi = make_desc_mn(sb, B_DOM), b_lo = make_desc_mn(sb + B_PLANE, B_DOM);
                     if (elect_one()) {
-                        umma(d, ah, b_hi, idesc, accum);               // Wh Mh
-                        umma(d, al, b_hi, idesc, 1u);                  // Wl Mh
-                        umma(d, ah, b_lo, idesc, 1u);                  // Wh Ml
-                        umma_commit(smem_u32(&tl->b_empty[bs]));
+                        umma(d, a_hi, b_hi, idesc, accum);               // Wh Mh
+                        umma(d, a_lo, b_hi, idesc, 1u);                  // Wl Mh
+                        umma(d, a_hi, b_lo, idesc, 1u);                  // Wh Ml
+                        umma_commit(smem_u32(&tl->empty[slot]));
                     }
                     __syncwarp();
                     accum = 1u;
-                    if (++bs == (uint32_t)NB) { bs = 0; bph ^= 1u; }
+                    lag_slot1 = slot; lag_ph1 = ph;                      // the group's last step completes last
                 }
-                if (elect_one()) umma_commit(smem_u32(&tl->w_empty[ws]));
-                __syncwarp();
-                if (++ws == WS) { ws = 0; wph ^= 1u; }
+                have_prev = true;
+                ks += n;
             }
             if (elect_one()) umma_commit(smem_u32(&tl->acc_full[buf]));
             __syncwarp();
         }
 #ifdef GNNB_TRACE
-        if (rank == 1 && lane == 0) printf("TRACE fused-mma: items %u ksteps %d total %lld | wait acc_empty %lld, w_full %lld, b_full %lld\n", it, n_ks,
-                                           clock64() - t_all, t_acc, t_w, t_b);
+        if (rank == 1 && lane == 0) printf("TRACE fused-mma: items %u ksteps %u total %lld | wait acc_empty %lld, lag %lld, stage full %lld\n", it, t,
+                                           clock64() - t_all, t_acc, t_lag, t_b);
 #endif
     } else if (warp >= GATHER_WARP0 && warp < GATHER_WARP0 + GATHER_WARPS) {
-        // ---- gather: warp gw copies rows [8 (gw >> 1), +8) of the K step for subdomain 2 * pair + (gw & 1); the 64 row indices
-        //      and the K-step count of the next chunk (of this item or of the CTA's next item) are in registers before the
-        //      current chunk is copied ----
-        const int gw = warp - GATHER_WARP0, gs = gw & 1, gh = gw >> 1;
+        // ---- gather: warp gw owns the K steps t = gw, gw + 6, ... of the CTA's sequence and copies the step's 16 input-node rows
+        //      of both subdomains (hi + lo plane: 8 KB, 16 x 16-byte cp.async per lane) from the mu images into the MN-major
+        //      SWIZZLE_128B B half of the step's stage.  A warp keeps ~8 KB of cp.async misses in flight whatever it does
+        //      (scripts/micro/gather_bw2.cu: 5 B / cycle / warp from DRAM with 2, 4 or 8 stages per warp, arrive- or
+        //      commit-group-tracked; L2 prefetches share the budget; the rate scales with the number of warps), so the six warps
+        //      work on six different stages: 48 KB in flight ----
+        const int gw = warp - GATHER_WARP0;
         const unsigned char* mu_bytes = reinterpret_cast<const unsigned char*>(fa.mu_in);
-        uint32_t bs = 0, bph = 0;
-        int64_t item = rank;
 #ifdef GNNB_TRACE
         long long g_wait = 0, g_all = clock64();
 #endif
-        if (item < nitems) {
-            int ch = __ldg(plan.tile_chunk0 + (int)(item % ntiles)), ch1 = __ldg(plan.tile_chunk0 + (int)(item % ntiles) + 1);
-            int i0 = __ldg(plan.in_rows + (size_t)ch * 64 + lane), i1 = __ldg(plan.in_rows + (size_t)ch * 64 + 32 + lane);
-            int nks = __ldg(plan.ksteps + ch);
-            while (true) {
-                int64_t nitem = item;
-                int nch = ch + 1, nch1 = ch1;
-                if (nch >= ch1) {
-                    nitem = item + nranks;
-                    if (nitem < nitems) {
-                        const int nt = (int)(nitem % ntiles);
-                        nch = __ldg(plan.tile_chunk0 + nt); nch1 = __ldg(plan.tile_chunk0 + nt + 1);
-                    }
-                }
-                const bool has_next = nitem < nitems;
-                int n0 = -1, n1 = -1, nnks = 0;
-                if (has_next) {
-                    n0 = __ldg(plan.in_rows + (size_t)nch * 64 + lane); n1 = __ldg(plan.in_rows + (size_t)nch * 64 + 32 + lane);
-                    nnks = __ldg(plan.ksteps + nch);
-                }
-                const int dm = (int)(item / ntiles) * PD + gs;
-                const bool dom_ok = dm < a.Bc;
-                const int64_t drow = (int64_t)dm * plan.nslots_in;
-                for (int ks = 0; ks < nks; ++ks) {
-                    const int idx = (ks & 2) ? i1 : i0;
+        uint32_t t = 0;
+        for (int64_t item = rank; item < nitems; item += nranks) {
+            const int tile = (int)(item % ntiles);
+            const int ks0 = __ldg(plan.tile_ks0 + tile), ks1 = __ldg(plan.tile_ks0 + tile + 1);
+            const int dm0 = (int)(item / ntiles) * PD;
+            for (int ks = ks0; ks < ks1; ++ks, ++t) {
+                if ((int)(t % (uint32_t)GATHER_WARPS) != gw) continue;
+                const uint32_t slot = t % (uint32_t)NS, ph = (t / (uint32_t)NS) & 1u;
+                const int idx = __ldg(plan.ks_rows + (size_t)ks * 16 + (lane & 15));      // issued before the wait below
 #ifdef GNNB_TRACE
-                    const long long g0_ = clock64();
+                const long long g0_ = clock64();
 #endif
-                    mbar_wait(smem_u32(&tl->b_empty[bs]), bph ^ 1u);
+                mbar_wait(smem_u32(&tl->empty[slot]), ph ^ 1u);
 #ifdef GNNB_TRACE
-                    g_wait += clock64() - g0_;
+                g_wait += clock64() - g0_;
 #endif
-                    const uint32_t dst0 = b_ring + bs * B_STAGE + (uint32_t)gs * B_DOM;
+                const uint32_t dst0 = ring + slot * STAGE + W_KS;
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const int k = gh * 8 + i * 4 + (lane >> 3);      // row of the stage: 4 rows x 8 chunks per instruction
-                        const int node = __shfl_sync(0xffffffffu, idx, (ks & 1) * 16 + k);
-                        const bool ok = dom_ok && node >= 0;
-                        const int64_t grow = ok ? drow + node : 0;
-                        const uint32_t r = (uint32_t)(grow & (TILE - 1));
-                        const uint32_t jp = (uint32_t)(lane & 7);       // physical 16-byte chunk of the row in the mu image
-                        const unsigned char* src = mu_bytes + (grow >> 7) * (int64_t)ABUF + (r >> 3) * 1024u + (r & 7u) * 128u + jp * 16u;
-                        const uint32_t dst = dst0 + swz((uint32_t)k, jp ^ (r & 7u));   // logical chunk = physical ^ (row & 7)
-                        cp_async16(dst, src, ok);
-                        cp_async16(dst + B_PLANE, src + APLANE, ok);
-                    }
-                    cp_async_arrive(smem_u32(&tl->b_full[bs]));
-                    if (++bs == (uint32_t)NB) { bs = 0; bph ^= 1u; }
+                for (int i = 0; i < 8; ++i) {
+                    const int sub = i >> 2;
+                    const int k = (i & 3) * 4 + (lane >> 3);             // row of the stage: 4 rows x 8 chunks per instruction
+                    const int node = __shfl_sync(0xffffffffu, idx, k);
+                    const bool ok = node >= 0 && dm0 + sub < a.Bc;
+                    const int64_t grow = ok ? (int64_t)(dm0 + sub) * plan.nslots_in + node : 0;
+                    const uint32_t r = (uint32_t)(grow & (TILE - 1));
+                    const uint32_t jp = (uint32_t)(lane & 7);           // physical 16-byte chunk of the row in the mu image
+                    const unsigned char* src = mu_bytes + (grow >> 7) * (int64_t)ABUF + (r >> 3) * 1024u + (r & 7u) * 128u + jp * 16u;
+                    const uint32_t dst = dst0 + (uint32_t)sub * B_DOM + swz((uint32_t)k, jp ^ (r & 7u));   // logical chunk = physical ^ (row & 7)
+                    cp_async16(dst, src, ok);
+                    cp_async16(dst + B_PLANE, src + APLANE, ok);
                 }
-                if (!has_next) break;
-                item = nitem; ch = nch; ch1 = nch1; i0 = n0; i1 = n1; nks = nnks;
+                cp_async_arrive(smem_u32(&tl->full[slot]));
             }
         }
 #ifdef GNNB_TRACE
-        if (rank == 1 && gw == 0 && lane == 0) printf("TRACE fused-gather: total %lld, wait b_empty %lld\n", clock64() - g_all, g_wait);
+        if (rank == 1 && gw == 0 && lane == 0) printf("TRACE fused-gather: total %lld, wait stage empty %lld\n", clock64() - g_all, g_wait);
 #endif
     } else if (warp >= CHAIN_WARP0) {
         // ---- node-update chains ----
@@ -881,7 +890,7 @@ __global__ void __launch_bounds__(fz::THREADS, 1) k_tc_fused(FusedArgs fa) {
         c.tmem = tmem_base + ((uint32_t)((c.t >> 5) * 32) << 16);
         const int j = c.wg;
         const uint32_t D = D_COL + D_WIN * (uint32_t)j;          // this warpgroup's accumulator window [D, D + 128)
-        const uint32_t stage = stg + (uint32_t)(warp - CHAIN_WARP0) * STG_WARP;      // this warp's 4 KB staging buffer
+        const uint32_t stage = stg + (uint32_t)(warp - CHAIN_WARP0) * stg_warp;      // this warp's 8 KB (4 KB with the score head) staging buffer
         mbar_wait(smem_u32(&tl->wts), 0);                        // chain weights have landed
         bool bad = false;
         // this row's inputs are two dependent 4-byte gathers (slot -> node, node -> bounds): the node index is fetched two
@@ -1446,11 +1455,15 @@ void tc_fused(const GnnParams& g, const PropPlan* plan, const float* mu_in, bool
     fa.mu_in = reinterpret_cast<const uint16_t*>(mu_in);
     fa.nb_dbg = reinterpret_cast<uint16_t*>(nb_dbg);
     const uint32_t wbytes = scores ? UPD_WBYTES : UPD_FN;
-    const bool staging = mu_out != nullptr;
-    int nb = (int)((fz::SMEM_MAX - fz::smem_for(wbytes, staging, 0)) / fz::B_STAGE);
-    fa.nb_stages = nb > fz::BS_MAX ? fz::BS_MAX : nb;
+    const int staging = mu_out == nullptr ? 0 : (scores ? 1 : 2);
+    const int ns = (int)((fz::SMEM_MAX - fz::smem_for(wbytes, staging, 0)) / fz::STAGE);
+    fa.n_stages = ns > fz::NS_MAX ? fz::NS_MAX : ns;
+    // layers with long K loops are bound by the propagation's issue loop, layers with short ones by the chains, whose GEMMs queue
+    // behind whatever the propagation has issued: groups of 4 K steps for the former, single steps for the latter
+    fa.mma_group = prop_plan_ksteps_per_tile(plan) >= 12.0 ? 4 : (prop_plan_ksteps_per_tile(plan) >= 6.0 ? 2 : 1);
+    if (fa.mma_group > fa.n_stages / 2) fa.mma_group = fa.n_stages / 2;
     const int64_t nitems = (int64_t)fa.plan.ntiles * ((fa.u.Bc + fz::PD - 1) / fz::PD);
-    launch_pdl(k_tc_fused, (int)(nitems < 1 ? 1 : (nitems < 148 ? nitems : 148)), fz::THREADS, fz::smem_for(wbytes, staging, fa.nb_stages), st, fa);
+    launch_pdl(k_tc_fused, (int)(nitems < 1 ? 1 : (nitems < 148 ? nitems : 148)), fz::THREADS, fz::smem_for(wbytes, staging, fa.n_stages), st, fa);
     ++*launches;
 }
 

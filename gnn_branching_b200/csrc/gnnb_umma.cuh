@@ -198,6 +198,20 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool v
 __device__ __forceinline__ void cp_async_arrive(uint32_t mbar) {      // arrives when this thread's earlier cp.async have landed
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(mbar) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// wait until at most n (0 .. 7) of this thread's committed cp.async groups are pending (the instruction takes an immediate)
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {
+    switch (n) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+        case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+    }
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
 }

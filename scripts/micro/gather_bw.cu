@@ -2,6 +2,8 @@
 //   mode 0  cp.async (LDGSTS) 16 B per lane, 4 warps                     — what the propagation gather does today
 //   mode 1  cp.async.bulk.tensor.2d ... tile::gather4 (4 rows per instruction, SWIZZLE_128B), one issuing thread
 //   mode 2  cp.async.bulk (linear) of one 128-byte row per instruction, one issuing thread
+//   mode 3+ cp.async.bulk.tensor.2d tile (box) loads of R = 8 << (mode - 3) consecutive rows per instruction (R = 8 .. 64,
+//           1 .. 8 KB), SWIZZLE_128B, one issuing thread: how the per-instruction cost of the TMA unit amortises
 // Rows are 64 fp16 = 128 B; a "stage" is 64 rows (8 KB, one K step of the fused kernel: 16 rows x 2 subdomains x 2 planes);
 // a ring of NST stages is kept in flight.  Row indices: runs of `run` consecutive rows at random places of a window of the
 // table that slides forward with the iteration (argv[4] MB, 0 = the whole table: TLB-hostile), like a wave of subdomains.
@@ -30,13 +32,18 @@ __device__ __forceinline__ void gather4(uint32_t dst, const CUtensorMap* tm, uin
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
                  ::"r"(dst), "l"(tm), "r"(mbar), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
 }
+__device__ __forceinline__ void box2d(uint32_t dst, const CUtensorMap* tm, uint32_t mbar, int c0, int r0) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(tm), "r"(mbar), "r"(c0), "r"(r0) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
 __device__ __forceinline__ void cp_async_arrive(uint32_t mbar) { asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(mbar) : "memory"); }
 
-__global__ void __launch_bounds__(160, 1) k(int mode, int nst, int iters, const __grid_constant__ CUtensorMap tm, const unsigned char* table,
+__global__ void __launch_bounds__(160, 1) k(int mode, int nst, int iters, const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmbox,
+                                            const unsigned char* table,
                                             const int* rows /* [grid][iters][64] */, long long* out, int* errs) {
     extern __shared__ unsigned char raw[];
     unsigned char* base = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
@@ -83,6 +90,9 @@ __global__ void __launch_bounds__(160, 1) k(int mode, int nst, int iters, const 
                 if (mode == 1) {
                     for (int g4 = 0; g4 < ROWS_PER_STAGE / 4; ++g4)
                         gather4(ring + s * STAGE_BYTES + g4 * 512, &tm, mb, 0, rr[4 * g4], rr[4 * g4 + 1], rr[4 * g4 + 2], rr[4 * g4 + 3]);
+                } else if (mode >= 3) {
+                    const int R = 8 << (mode - 3);
+                    for (int r = 0; r < ROWS_PER_STAGE; r += R) box2d(ring + s * STAGE_BYTES + r * 128, &tmbox, mb, 0, rr[r]);
                 } else {
                     for (int r = 0; r < ROWS_PER_STAGE; ++r) bulk_g2s(ring + s * STAGE_BYTES + r * 128, table + (size_t)rr[r] * 128, 128, mb);
                 }
@@ -99,7 +109,7 @@ __global__ void __launch_bounds__(160, 1) k(int mode, int nst, int iters, const 
     for (int i = threadIdx.x; i < ROWS_PER_STAGE * 8; i += blockDim.x) {
         const int kr = i >> 3, c = i & 7;
         const int want_row = myrows[(iters - 1) * ROWS_PER_STAGE + kr];
-        const int pos = (mode == 2) ? c : (c ^ (kr & 7));          // modes 0 / 1 land SWIZZLE_128B
+        const int pos = (mode == 2) ? c : (c ^ (kr & 7));          // every mode but 2 lands SWIZZLE_128B
         const uint32_t* p = reinterpret_cast<const uint32_t*>(base + s * STAGE_BYTES + kr * 128 + pos * 16);
         if (p[0] != (uint32_t)want_row || p[1] != (uint32_t)c) ++bad;
     }
@@ -136,7 +146,7 @@ int main(int argc, char** argv) {
                                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         printf("cuTensorMapEncodeTiled(box rows %d) -> %d\n", boxrows, (int)r);
         if (r != CUDA_SUCCESS) continue;
-        for (int run : {1, 4, 16}) {
+        for (int run : {1, 16, 64}) {
             std::vector<int> h((size_t)grid * iters * ROWS_PER_STAGE);
             uint64_t st = 88172645463325252ull;
             for (size_t i = 0; i < h.size(); i += run) {
@@ -150,14 +160,22 @@ int main(int argc, char** argv) {
                 for (int j = 0; j < run && i + j < h.size(); ++j) h[i + j] = (int)(r0 + j);
             }
             CK(cudaMemcpy(drows, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
-            for (int mode = 0; mode < 3; ++mode)
-                for (int nst : {4, 8, 16}) {
+            for (int mode = 0; mode < 7; ++mode)
+                for (int nst : {4, 16}) {
                     if (boxrows != 1 && mode != 1) continue;                // the tensor map only matters for mode 1
+                    if (mode >= 3 && run < (8 << (mode - 3))) continue;     // box loads need runs of at least R consecutive rows
+                    CUtensorMap tmb = tm;
+                    if (mode >= 3) {
+                        const cuuint32_t bb[2] = {64, (cuuint32_t)(8 << (mode - 3))};
+                        CUresult rb = cuTensorMapEncodeTiled(&tmb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, table, dims, strides, bb, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        if (rb != CUDA_SUCCESS) { printf("box map R=%d -> %d\n", 8 << (mode - 3), (int)rb); continue; }
+                    }
                     CK(cudaMemset(errs, 0, sizeof(int)));
                     const size_t smem = 1024 + (size_t)nst * STAGE_BYTES;
                     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                     CK(cudaMemset(out, 0, grid * sizeof(long long)));
-                    k<<<grid, 160, smem>>>(mode, nst, iters, tm, table, drows, out, errs);
+                    k<<<grid, 160, smem>>>(mode, nst, iters, tm, tmb, table, drows, out, errs);
                     CK(cudaGetLastError());
                     cudaError_t e = cudaDeviceSynchronize();
                     if (e != cudaSuccess) { printf("mode %d nst %d run %d box %d: %s\n", mode, nst, run, boxrows, cudaGetErrorString(e)); return 1; }
@@ -168,7 +186,8 @@ int main(int argc, char** argv) {
                     long long mx = 0;
                     for (long long c : cyc) mx = c > mx ? c : mx;
                     printf("box %d  mode %d (%s)  run %2d  stages %2d (%3d KB in flight): %6.2f B/cycle/SM  (%.0f cycles/stage)  data errors %d\n", boxrows, mode,
-                           mode == 0 ? "cp.async 16B x 4 warps" : mode == 1 ? "TMA gather4          " : "bulk 128 B per row   ", run, nst, nst * STAGE_BYTES / 1024,
+                           mode == 0 ? "cp.async 16B x 4 warps" : mode == 1 ? "TMA gather4          " : mode == 2 ? "bulk 128 B per row   " :
+                           mode == 3 ? "TMA box  8 rows 1 KB " : mode == 4 ? "TMA box 16 rows 2 KB " : mode == 5 ? "TMA box 32 rows 4 KB " : "TMA box 64 rows 8 KB ", run, nst, nst * STAGE_BYTES / 1024,
                            (double)iters * STAGE_BYTES / mx, (double)mx / iters, herr);
                 }
         }

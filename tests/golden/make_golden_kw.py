@@ -60,7 +60,7 @@ def modules_of(net, wp, bp):
 def main():
     nets = dict(np.load(os.path.join(HERE, 'nets.npz')))
     out = {}
-    for arch in ('base', 'deep'):
+    for arch in ('base', 'deep', 'wide'):
         net, lbs, ubs, wp, bp = load_root(arch)
         x = torch.from_numpy(nets[f'{arch}_x'].copy())
         seq = modules_of(net, wp, bp)

@@ -82,8 +82,6 @@ def check_kw_bounds(arch):
     gl, gu = sc.kw_bounds(x, 0.145, wp.reshape(1, -1), torch.tensor([bp]))
     for k in range(net.L + 2):
         assert err(gl[k], lbs[k]) <= 5e-5 and err(gu[k], ubs[k]) <= 5e-5, ('root', k, err(gl[k], lbs[k]), err(gu[k], ubs[k]))
-    if arch == 'wide':
-        return
     z = dict(np.load(os.path.join(GOLDEN, 'kw_children.npz')))
     nc = int(z[f'{arch}_ncases'])
     plbs, pubs = [], []

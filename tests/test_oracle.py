@@ -171,7 +171,7 @@ def test_kw_bounds_oracle_matches_reference_root_bounds(arch):
         assert bool((got_l[k] <= got_u[k] + 1e-6).all())
 
 
-@pytest.mark.parametrize('arch', ['base', 'deep'])
+@pytest.mark.parametrize('arch', ['base', 'deep', 'wide'])
 def test_kw_bounds_oracle_matches_reference_children(arch):
     """Child domains: one ambiguous ReLU of the root fixed to blocked / passing, bounds recomputed with the parent's bounds
     provided (tests/golden/make_golden_kw.py, the DualNetwork(provided_zl, provided_zu) path of init_kw_bounds)."""
