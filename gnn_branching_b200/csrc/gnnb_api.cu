@@ -333,7 +333,7 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
             if (fused) {
                 ProfScope ps(ctx, GNNB_K_LAYER_FWD, nodes, st);
                 tc_fused(g, ctx->plan_fwd[k - 1], ctx->mu[k - 1], false, in.lb[k], in.ub[k], ctx->relax_f[k], ctx->amb_base[k],
-                         ctx->mu[k], nullptr, M(k), 0, 0, rows, ctx->d_nan, ctx->snapshot ? ctx->nb : nullptr, st, lc);
+                         ctx->mu[k], nullptr, M(k), 0, 0, rows, ctx->d_nan, ctx->snapshot ? ctx->nb : nullptr, false, st, lc);
             } else {
                 ProfScope ps(ctx, GNNB_K_PROP_FWD, nodes, st);
                 if (tc) prop_tc_run(ctx->plan_fwd[k - 1], ctx->mu[k - 1], ctx->nb, Bc, st, lc, ctx->gather_prefetch);
@@ -363,7 +363,7 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
             if (fused_k) {
                 ProfScope ps(ctx, last ? GNNB_K_LAYER_BWD_SCORE : GNNB_K_LAYER_BWD, nodes, st);
                 tc_fused(g, ctx->plan_bwd[k], ctx->mu[k + 1], true, in.lb[k], in.ub[k], ctx->relax_b[k], ctx->amb_base[k],
-                         mu_k, sc, M(k), ctx->n_hidden, ctx->hidden_off[k], rows, ctx->d_nan, ctx->snapshot ? ctx->nb : nullptr, st, lc);
+                         mu_k, sc, M(k), ctx->n_hidden, ctx->hidden_off[k], rows, ctx->d_nan, ctx->snapshot ? ctx->nb : nullptr, false, st, lc);
             } else {
                 ProfScope ps(ctx, GNNB_K_PROP_BWD, nodes, st);
                 if (k == L && tc) prop_tc_property_backward(in.wp, ctx->mu[L + 1], ctx->nb, ctx->n[L], ctx->rowmap[L].nslots, Bc, st, lc);
@@ -380,7 +380,12 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
             TRY(snap_img(ctx, name("t%d_bwd_mu%d", t, k), ctx->mu[k], k, Bc, false, st));
         }
         // input layer: feeds the next round only (dead on the last round)
-        if (!last) {
+        if (!last && fused) {
+            ProfScope ps(ctx, GNNB_K_INPUT_UPDATE, (int64_t)Bc * ctx->n[0], st);
+            tc_fused(g, ctx->plan_bwd[0], ctx->mu[1], true, in.lb[0], in.ub[0], nullptr, nullptr, ctx->mu[0], nullptr, M(0), 0, 0, R(0),
+                     ctx->d_nan, nullptr, true, st, lc);
+            TRY(snap_img(ctx, name("t%d_mu0", t, 0), ctx->mu[0], 0, Bc, false, st));
+        } else if (!last) {
             {
                 ProfScope ps(ctx, GNNB_K_PROP_BWD, (int64_t)Bc * ctx->n[0], st);
                 if (tc) prop_tc_run(ctx->plan_bwd[0], ctx->mu[1], ctx->nb, Bc, st, lc, ctx->gather_prefetch);

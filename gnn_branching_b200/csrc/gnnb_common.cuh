@@ -121,11 +121,12 @@ void tc_update(const GnnParams& g, bool backward, const float* lb, const float* 
                const int32_t* amb_base, float* mu_out, float* scores, RowMap map, int64_t score_stride, int64_t score_off, int64_t rows,
                unsigned long long* nan_count, cudaStream_t st, int64_t* launches);
 // propagation (plan) + node update of one layer in ONE launch: the neighbour embeddings go from the propagation accumulator
-// to the update chain through tensor memory and are never written (k_tc_fused); nb_dbg: the nb tile images for snapshots, or null
+// to the update chain through tensor memory and are never written (k_tc_fused); nb_dbg: the nb tile images for snapshots, or null;
+// input_layer: the chain is the input-layer update (lb / ub = input bounds; backward, relax, amb_base, scores unused)
 struct PropPlan;
 void tc_fused(const GnnParams& g, const PropPlan* plan, const float* mu_in, bool backward, const float* lb, const float* ub,
               const float* relax, const int32_t* amb_base, float* mu_out, float* scores, RowMap map, int64_t score_stride, int64_t score_off,
-              int64_t rows, unsigned long long* nan_count, float* nb_dbg, cudaStream_t st, int64_t* launches);
+              int64_t rows, unsigned long long* nan_count, float* nb_dbg, bool input_layer, cudaStream_t st, int64_t* launches);
 // slot of every ambiguous row of a layer, in row order: amb_base[tile] (+ the rank inside the tile), amb_rows[slot] = row;
 // cnt is scratch of ntiles + 1 ints (three small launches: count per tile, scan, fill)
 void amb_compact(const float* lb, const float* ub, RowMap map, int64_t rows, int32_t* cnt, int32_t* amb_base, int32_t* amb_rows,

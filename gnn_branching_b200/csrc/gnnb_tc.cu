@@ -67,11 +67,12 @@ struct WG {
     uint32_t tmem0;             // lane 0, first column of this warpgroup (MMA operand / accumulator addresses)
     uint32_t acol;              // first column of the A operand of the chained GEMMs, relative to tmem / tmem0
     int t;                      // thread index within the warpgroup = row of the tile this thread owns
+    int bar_threads;            // threads that walk the chain of one tile together: 128 (one warpgroup) or 256 (k_tc_fused: two, half the columns each)
     int wg;
     bool lead_warp;             // first warp of the warpgroup (warp-uniform): it issues the warpgroup's MMAs, one elected lane
 };
 
-__device__ __forceinline__ void wg_barrier(const WG& c) { named_bar(1 + c.wg, 128); }
+__device__ __forceinline__ void wg_barrier(const WG& c) { named_bar(1 + c.wg, c.bar_threads); }
 
 // 3 passes x 4 K steps with the A operand in tensor memory (issued by one thread)
 __device__ __forceinline__ void issue_ts(const WG& c, uint32_t b_hi, uint32_t b_lo, uint32_t N, uint32_t dcol, bool accumulate) {
@@ -336,6 +337,7 @@ __device__ __forceinline__ WG make_wg(const CtaSetup& s, uint32_t wbytes) {
     c.ph_mma = 0;
     c.ph_tma = 0;
     c.acol = ACOL;
+    c.bar_threads = 128;
     c.tmem0 = ((uint32_t)uniform((int)s.tmem_base) & 0x0000FFFFu) + (uint32_t)c.wg * WG_COLS;
     c.tmem = s.tmem_base + ((uint32_t)((c.t >> 5) * 32) << 16) + (uint32_t)c.wg * WG_COLS;
     return c;
@@ -534,23 +536,25 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_update(UpdArgs a) {
 
 // ---- fused layer: propagation gather-GEMM -> tensor memory -> node-update chain ------------------------------------------
 // One launch per (layer, sweep): the neighbour embeddings nb = A(mu) of a tile never leave the SM.  A persistent CTA (1 per
-// SM, 16 warps) walks items = (tile of 128 nodes) x (pair of subdomains); the propagation of item i + 1 runs while the two
-// chains of item i run (the propagation accumulator is double-buffered in tensor memory):
-//   warp 0      bulk copies of the item's propagation weight blocks (32 KB per 64-row K chunk)          -> W ring, 2 stages
-//   warps 2-5   gather: warp g copies 8 of the K step's 16 input-node rows of subdomain g & 1 with 16-byte cp.async from the
-//               mu images into the MN-major SWIZZLE_128B B operand (the row indices of the next chunk are fetched one chunk
-//               ahead)                                   -> B ring, 6 - 8 stages of one K step (16 rows x 2 subdomains x hi / lo)
+// SM, 24 warps) walks items = (tile of 128 nodes) x (pair of subdomains); the propagation of item i + 1 runs while the two
+// chains of item i run (the propagation accumulator is double-buffered in tensor memory).  One ring of 6 - 8 stages, one K
+// step (16 input nodes) each: [8 KB weight block | 8 KB gathered rows] = everything the step's three MMAs read.
+//   warp 0      one bulk copy per K step: the step's weight block (plan.ks_w: 128 x 16 fp16 hi + lo, K-major without swizzle)
+//   warps 2-7   gather: warp g owns the steps g, g + 6, ... and copies the step's 16 input-node rows of both subdomains with
+//               16-byte cp.async from the mu images into the MN-major SWIZZLE_128B B operand (16 instructions per lane = 8 KB,
+//               which is what one warp can keep in flight: scripts/micro/gather_bw2.cu)
 //   warp 1      tcgen05.mma M = 128, N = 128 (2 subdomains x 64 channels), K = 16, three fp16 hi / lo passes, into accumulator
-//               it & 1 (tensor-memory columns [128 (it & 1), +128)); tcgen05.commit frees ring stages and publishes it
-//   warps 8-15  two chain warpgroups (thread = row of the tile = TMEM lane); warpgroup j takes subdomain j of every item:
-//               tcgen05.ld of its 64 accumulator columns -> fp16 hi / lo split -> tcgen05.st back IN PLACE as the A operand
-//               of the chain (the same split the stand-alone propagation kernel writes to its nb image); then the update
-//               chain of k_tc_update with every GEMM in the TS form (A from tensor memory) and the warpgroup's 128 accumulator
-//               columns at [256 + 128 j, +128).  The new embeddings are staged per WARP (32 rows x 128 B of one plane = 4 KB,
-//               contiguous in the swizzled mu image) and leave with one bulk store per warp and plane — no warpgroup barrier,
-//               and the drain of 4 KB is short.
+//               it & 1 (tensor-memory columns [128 (it & 1), +128)); tcgen05.commit frees the stage and publishes the accumulator
+//   warps 8-23  four chain warpgroups: subdomain j of every item is walked by two of them, h = 0 / 1 owning channels [32 h, +32)
+//               of every epilogue (thread = row of the tile = TMEM lane): tcgen05.ld of the accumulator columns -> fp16 hi / lo
+//               split -> tcgen05.st back IN PLACE as the A operand of the chain (the same split the stand-alone propagation
+//               kernel writes to its nb image); then the update chain of k_tc_update with every GEMM in the TS form (A from
+//               tensor memory) and the chain's 128 accumulator columns at [256 + 128 j, +128).  The new embeddings are staged
+//               per pair of warps (32 rows x 128 B of one plane = 4 KB, contiguous in the swizzled mu image) and leave with one
+//               bulk store per plane.
+// Registers: 768 threads x 80; with half a row's channels per thread the chain fits (no setmaxnreg needed).
 // Tensor memory: 2 x 128 (propagation accumulators = the chains' A operands) + 2 x 128 (chain accumulators) = 512 columns.
-// Shared memory: chain weights 64 KB (80 KB with the score head) + W ring 64 KB + staging 32 KB + B ring 64 KB (48 KB).
+// Shared memory: chain weights 64 KB (80 KB with the score head) + staging 64 KB (32 KB) + ring 96 KB (112 KB) — all of it.
 // Accumulator b is free for item i + 2 when both chains of item i have completed their last GEMM that reads its A columns
 // (acc_empty[b], 2 arrivals).
 namespace fz {
@@ -566,7 +570,8 @@ constexpr uint32_t STAGE = W_KS + B_STAGE;          // 16 KB: everything the thr
 constexpr uint32_t STG_PLANE = 32 * 128;            // 4 KB: a warp's 32 rows of one plane of a mu tile image
 constexpr uint32_t STG_WARP = 2 * STG_PLANE;        // 8 KB: hi + lo
 constexpr uint32_t STG_BYTES = CW * 4 * STG_WARP;   // 64 KB, only in launches that store embeddings
-constexpr int THREADS = 512;
+constexpr uint32_t INF_WN = 0, INF_WI = 2 * WPLANE, INF_B22 = 4 * WPLANE;      // chain weights of the input-layer variant
+constexpr int THREADS = 768;                        // 8 producer warps + 4 chain warpgroups
 constexpr int GATHER_WARP0 = 2, GATHER_WARPS = 6, CHAIN_WARP0 = 8;
 constexpr uint32_t ACC_COL = 0, ACC_WIN = PD * 64, D_COL = 256, D_WIN = 128;
 
@@ -575,7 +580,7 @@ struct Tail {
     float vec[P];
     uint64_t wts, full[NS_MAX], empty[NS_MAX], acc_full[2], acc_empty[2], mma[CW];
     uint32_t tmem_slot;
-    int32_t wcnt[CW][4];
+    int32_t wcnt[2 * CW][4];
 };
 // staging: 0 = none (nothing stored), 1 = one plane per warp (score-head launches), 2 = both planes
 constexpr size_t smem_for(uint32_t wbytes, int staging, int n_stages) {
@@ -591,6 +596,8 @@ struct FusedArgs {
     uint16_t* nb_dbg;           // snapshots only: the nb tile images the two-launch path would have written, or null
     int n_stages;               // ring stages that fit beside the chain weights and the staging buffers (6 .. 8)
     int mma_group;              // K steps the propagation issues per pass of its loop (1 .. 4)
+    int input_layer;            // 1: the chain is the input-layer update (graph_conv.py:360-385; u.lb / u.ub are the input bounds, no
+                                // relaxation term, no gate), 0: a hidden layer's forward / backward update
 };
 
 // two 16-column tensor-memory loads in flight, then both -> fp32
@@ -611,35 +618,46 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// (accumulator columns [dcol, dcol+64) + bias) * rowscale -> this thread's row of the mu tile image (fp16 hi / lo planes,
-// K-major SWIZZLE_128B, scaled domain).  A warp's 32 rows of one plane are 4 KB contiguous in the image: both planes are
-// staged in the warp's 8 KB buffer (conflict-free swizzled 16-byte stores) and leave with one bulk store per plane, issued by
-// the warp itself — no warpgroup barrier; the stores drain while the warp runs its next tile (the SMs of a launch walk their
-// tiles in lock step, so the tiles of a wave are written in bursts that take ~4 000 cycles to drain: a synchronous store of
-// any kind — 32-byte direct stores, coalesced 16-byte stores, a bulk store waited for — puts that on the chain's path
-// [measured, profiles/r02_fused_phase_trace.log]).  TO_A: the values also become the next A operand (score head).  img: the
-// tile image in global memory or null (nothing is stored).  Returns true on NaN in a valid row.  Warp-synchronous.
-// TO_A (score head launches, which need 16 KB more weights): the buffer is 4 KB — the hi plane leaves first, the lo plane
-// (kept in registers) follows once the first bulk store has read the buffer.
+// (accumulator columns [dcol + 32 h, +32) + bias) * rowscale -> channels [32 h, 32 h + 32) of this thread's row of the mu tile
+// image (fp16 hi / lo planes, K-major SWIZZLE_128B, scaled domain).  The two warps that hold the same 32 rows (one per column
+// half) share an 8 KB staging buffer: a warp's 32 rows of one plane are 4 KB contiguous in the image, both planes are staged
+// (conflict-free swizzled 16-byte stores) and leave with one bulk store per plane issued by the h = 0 warp — no warpgroup
+// barrier, only the 64-thread barrier `pair_bar` of the two warps; the stores drain while the warps run their next tile (a
+// synchronous store of any kind — 32-byte direct stores, coalesced 16-byte stores, a bulk store waited for — costs the chain
+// 2 500 - 4 000 cycles per tile [measured, profiles/r02*_fused_phase_trace.log]).  TO_A (score-head launches, which need
+// 16 KB more weights): the values also become the next A operand, and the buffer is 4 KB — the hi plane leaves first, the lo
+// plane (kept in registers) follows once the first bulk store has read the buffer.  img: the tile image in global memory or
+// null (nothing is stored).  Returns true on NaN in a valid row.  Both warps of the pair call it.
+#ifdef GNNB_TRACE
+__device__ long long g_e3_trace[4];          // e3 sub-phases of the tracing thread: wait for the previous stores, compute + stage, fence + issue
+#define E3TR(i) do { if (blockIdx.x == 1 && threadIdx.x == fz::CHAIN_WARP0 * 32) { const long long n_ = clock64(); g_e3_trace[i] += n_ - e3t_; e3t_ = n_; } } while (0)
+#else
+#define E3TR(i) do {} while (0)
+#endif
 template <bool TO_A>
-__device__ __forceinline__ bool epilogue_to_mu_warp(const WG& c, uint32_t dcol, const float* __restrict__ bias_s, float rowscale,
-                                                    bool valid, unsigned char* img, uint32_t stage) {
+__device__ __forceinline__ bool epilogue_to_mu_pair(const WG& c, int h, int pair_bar, uint32_t dcol, const float* __restrict__ bias_s,
+                                                    float rowscale, bool valid, unsigned char* img, uint32_t stage) {
     bool bad = false;
+#ifdef GNNB_TRACE
+    long long e3t_ = clock64();
+#endif
     const uint32_t rl = (uint32_t)c.t & 31u;                       // row within the warp's 32 rows = lane
+    const bool issuer = h == 0 && rl == 0;
     unsigned char* dst = img + ((uint32_t)c.t >> 5) * fz::STG_PLANE;
-    uint32_t lo[TO_A ? 32 : 1];
+    uint32_t lo[TO_A ? 16 : 1];
     if (img != nullptr) {
-        if (rl == 0) bulk_wait_read();                              // the previous tile's bulk stores have read the buffer
-        __syncwarp();
+        if (issuer) bulk_wait_read();                               // the previous tile's bulk stores have read the buffer
+        named_bar(pair_bar, 64);
     }
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    E3TR(0);
+    {
         float v0[16], v1[16];
         tmem_ld32_sync(c.tmem + dcol + h * 32, v0, v1);
+        E3TR(1);
 #pragma unroll
         for (int qq = 0; qq < 2; ++qq) {
             float (&v)[16] = qq ? v1 : v0;
-            const int q = h * 2 + qq;
+            const int q = 2 * h + qq;
             float bb[16];
             lds16(bias_s + q * 16, bb);
 #pragma unroll
@@ -660,35 +678,51 @@ __device__ __forceinline__ bool epilogue_to_mu_warp(const WG& c, uint32_t dcol, 
             }
             if (TO_A) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) lo[q * 8 + i] = w[8 + i];
+                for (int i = 0; i < 8; ++i) lo[qq * 8 + i] = w[8 + i];
                 tmem_st16(c.tmem + c.acol + 16 * q, w);
             }
         }
     }
+    E3TR(2);
     if (img != nullptr) {
         fence_proxy_async();             // the staging stores are generic-proxy writes, the bulk stores read through the async proxy
-        __syncwarp();
+        named_bar(pair_bar, 64);
         if (!TO_A) {
-            if (rl == 0) {
+            if (issuer) {
                 bulk_s2g_nocommit(dst, stage, fz::STG_PLANE);
                 bulk_s2g_nocommit(dst + APLANE, stage + fz::STG_PLANE, fz::STG_PLANE);
                 bulk_commit();
             }
         } else {
-            if (rl == 0) { bulk_s2g(dst, stage, fz::STG_PLANE); bulk_wait_read(); }
-            __syncwarp();
+            if (issuer) { bulk_s2g(dst, stage, fz::STG_PLANE); bulk_wait_read(); }
+            named_bar(pair_bar, 64);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                sts128(stage + swz(rl, (uint32_t)(2 * q)), lo[q * 8], lo[q * 8 + 1], lo[q * 8 + 2], lo[q * 8 + 3]);
-                sts128(stage + swz(rl, (uint32_t)(2 * q + 1)), lo[q * 8 + 4], lo[q * 8 + 5], lo[q * 8 + 6], lo[q * 8 + 7]);
+            for (int qq = 0; qq < 2; ++qq) {
+                const int q = 2 * h + qq;
+                sts128(stage + swz(rl, (uint32_t)(2 * q)), lo[qq * 8], lo[qq * 8 + 1], lo[qq * 8 + 2], lo[qq * 8 + 3]);
+                sts128(stage + swz(rl, (uint32_t)(2 * q + 1)), lo[qq * 8 + 4], lo[qq * 8 + 5], lo[qq * 8 + 6], lo[qq * 8 + 7]);
             }
             fence_proxy_async();
-            __syncwarp();
-            if (rl == 0) bulk_s2g(dst + APLANE, stage, fz::STG_PLANE);
+            named_bar(pair_bar, 64);
+            if (issuer) bulk_s2g(dst + APLANE, stage, fz::STG_PLANE);
         }
     }
+    E3TR(3);
     return bad && valid;
 }
+
+// The CTA's item sequence rank, rank + nranks, ... as (pair of subdomains, tile) with item = pair * ntiles + tile, advanced
+// without divisions (a 64-bit division by a run-time value is ~100 instructions; the roles walk the sequence once per item).
+struct ItemCursor {
+    int pair, tile, dq, dr, ntiles, npairs;
+    __device__ __forceinline__ ItemCursor(int rank, int nranks, int ntiles_, int npairs_)
+        : pair(rank / ntiles_), tile(rank % ntiles_), dq(nranks / ntiles_), dr(nranks % ntiles_), ntiles(ntiles_), npairs(npairs_) {}
+    __device__ __forceinline__ bool valid() const { return pair < npairs; }
+    __device__ __forceinline__ void next() {
+        tile += dr; pair += dq;
+        if (tile >= ntiles) { tile -= ntiles; ++pair; }
+    }
+};
 
 __global__ void __launch_bounds__(fz::THREADS, 1) k_tc_fused(FusedArgs fa) {
     using namespace fz;
@@ -720,36 +754,47 @@ __global__ void __launch_bounds__(fz::THREADS, 1) k_tc_fused(FusedArgs fa) {
     tc_fence_after();
     const uint32_t tmem_base = tl->tmem_slot;
     const int l3 = a.backward ? BC3 : FC3, l4b = a.backward ? BC4_1 : FC4_2, lc = a.backward ? T_BWD_C : T_FWD_C;
+    const bool inp = fa.input_layer != 0;
     if (threadIdx.x == 0) {
         const uint32_t mb = smem_u32(&tl->wts);
-        mbar_expect_tx(mb, wbytes);
-        bulk_g2s(W + UPD_W3, g.tc[l3], 4 * WPLANE, mb);
-        bulk_g2s(W + UPD_WC, g.tcx_w[lc], 2 * WPLANE, mb);
-        bulk_g2s(W + UPD_W42, g.tc[l4b], 2 * WPLANE, mb);
-        if (with_score) bulk_g2s(W + UPD_FN, g.tc[FNODE], 2 * WPLANE, mb);
+        if (!inp) {
+            mbar_expect_tx(mb, wbytes);
+            bulk_g2s(W + UPD_W3, g.tc[l3], 4 * WPLANE, mb);
+            bulk_g2s(W + UPD_WC, g.tcx_w[lc], 2 * WPLANE, mb);
+            bulk_g2s(W + UPD_W42, g.tc[l4b], 2 * WPLANE, mb);
+            if (with_score) bulk_g2s(W + UPD_FN, g.tc[FNODE], 2 * WPLANE, mb);
+        } else {      // mu0 = inp_b2_2(relu(Wi relu(inp_b([l0, u0])) + Wn nb + bi)),  Wi = W_b2[:, :64] W_b1,  Wn = W_b2[:, 64:]
+            mbar_expect_tx(mb, 6 * WPLANE);
+            bulk_g2s(W + INF_WN, g.tcx_w[T_INP_NB], 2 * WPLANE, mb);
+            bulk_g2s(W + INF_WI, g.tcx_w[T_INP_C], 2 * WPLANE, mb);
+            bulk_g2s(W + INF_B22, g.tc[INP_B2_2], 2 * WPLANE, mb);
+        }
     }
-    copy_vec(tl->bias[0], g.bias[l3], P); copy_vec(tl->bias[1], g.tcx_b[lc], P); copy_vec(tl->bias[2], g.bias[l4b], P);
-    copy_vec(tl->bias[3], g.bias[FNODE], P); copy_vec(tl->vec, g.wt[FSCORE], P, 1.0f);
+    if (!inp) {
+        copy_vec(tl->bias[0], g.bias[l3], P); copy_vec(tl->bias[1], g.tcx_b[lc], P); copy_vec(tl->bias[2], g.bias[l4b], P);
+        copy_vec(tl->bias[3], g.bias[FNODE], P); copy_vec(tl->vec, g.wt[FSCORE], P, 1.0f);
+    } else {
+        copy_vec(tl->bias[0], g.tcx_b[T_INP_C], P); copy_vec(tl->bias[1], g.bias[INP_B2_2], P); copy_vec(tl->bias[2], g.bias[INP_B], P);
+        copy_vec(tl->bias[3], g.wt[INP_B], 2 * P);          // [2][64] transposed first-layer weight: fills bias[3] and vec (adjacent)
+    }
     __syncthreads();
     pdl_trigger(); pdl_wait();                    // everything above read constant parameters only
 
-    const int ntiles = plan.ntiles;
-    const int64_t nitems = (int64_t)ntiles * ((a.Bc + PD - 1) / PD);      // item = pair * ntiles + tile
+    const int ntiles = plan.ntiles, npairs = (a.Bc + PD - 1) / PD;       // item = pair * ntiles + tile
     const int rank = (int)blockIdx.x, nranks = (int)gridDim.x;
 
     if (warp == 0) {
         // ---- propagation weight blocks: 8 KB per K step into the W half of the step's ring stage ----
         if (lane == 0) {
-            uint32_t t = 0;
-            for (int64_t item = rank; item < nitems; item += nranks) {
-                const int tile = (int)(item % ntiles);
-                const int ks0 = plan.tile_ks0[tile], ks1 = plan.tile_ks0[tile + 1];
-                for (int ks = ks0; ks < ks1; ++ks, ++t) {
-                    const uint32_t slot = t % (uint32_t)NS, ph = (t / (uint32_t)NS) & 1u;
+            uint32_t slot = 0, ph = 0;
+            for (ItemCursor cur(rank, nranks, ntiles, npairs); cur.valid(); cur.next()) {
+                const int ks0 = plan.tile_ks0[cur.tile], ks1 = plan.tile_ks0[cur.tile + 1];
+                for (int ks = ks0; ks < ks1; ++ks) {
                     mbar_wait(smem_u32(&tl->empty[slot]), ph ^ 1u);
                     const uint32_t full = smem_u32(&tl->full[slot]);
                     mbar_expect_tx(full, W_KS);
                     bulk_g2s(ring + slot * STAGE, plan.ks_w + (size_t)ks * (W_KS / 2), W_KS, full);
+                    if (++slot == (uint32_t)NS) { slot = 0; ph ^= 1u; }
                 }
             }
         }
@@ -757,7 +802,7 @@ __global__ void __launch_bounds__(fz::THREADS, 1) k_tc_fused(FusedArgs fa) {
         // ---- propagation MMAs: the whole warp walks the loop (uniform control and operands), one elected lane issues ----
         // D fp32, A fp16 K-major (no swizzle), B fp16 MN-major SWIZZLE_128B (bit 16), M = 128, N = 128
         const uint32_t idesc = (1u << 4) | (1u << 16) | ((uint32_t)(PD * 64 >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
-        uint32_t t = 0, it = 0;
+        uint32_t t = 0, it = 0, slot = 0, ph = 0;
         const int group = fa.mma_group;
         uint32_t lag_slot0 = 0, lag_slot1 = 0, lag_ph0 = 0, lag_ph1 = 0;       // last step of the group before the previous one / of the previous one
         bool have_lag = false, have_prev = false;
@@ -769,9 +814,8 @@ __global__ void __launch_bounds__(fz::THREADS, 1) k_tc_fused(FusedArgs fa) {
 #define FTR_BEGIN()
 #define FTR_END(x)
 #endif
-        for (int64_t item = rank; item < nitems; item += nranks, ++it) {
-            const int tile = (int)(item % ntiles);
-            const int ks0 = uniform(plan.tile_ks0[tile]), ks1 = uniform(plan.tile_ks0[tile + 1]);
+        for (ItemCursor cur(rank, nranks, ntiles, npairs); cur.valid(); cur.next(), ++it) {
+            const int ks0 = uniform(plan.tile_ks0[cur.tile]), ks1 = uniform(plan.tile_ks0[cur.tile + 1]);
             const uint32_t buf = it & 1u, bufph = (it >> 1) & 1u;
             FTR_BEGIN();
             mbar_wait(smem_u32(&tl->acc_empty[buf]), bufph ^ 1u);     // the chains of item it - 2 no longer read these A columns
@@ -790,7 +834,6 @@ __global__ void __launch_bounds__(fz::THREADS, 1) k_tc_fused(FusedArgs fa) {
                 FTR_END(t_lag);
                 lag_slot0 = lag_slot1; lag_ph0 = lag_ph1; have_lag = have_prev;
                 for (int i = 0; i < n; ++i, ++t) {
-                    const uint32_t slot = t % (uint32_t)NS, ph = (t / (uint32_t)NS) & 1u;
                     FTR_BEGIN();
                     mbar_wait(smem_u32(&tl->full[slot]), ph);
                     FTR_END(t_b);
@@ -807,6 +850,7 @@ __global__ void __launch_bounds__(fz::THREADS, 1) k_tc_fused(FusedArgs fa) {
                     __syncwarp();
                     accum = 1u;
                     lag_slot1 = slot; lag_ph1 = ph;                      // the group's last step completes last
+                    if (++slot == (uint32_t)NS) { slot = 0; ph ^= 1u; }
                 }
                 have_prev = true;
                 ks += n;
@@ -830,23 +874,26 @@ __global__ void __launch_bounds__(fz::THREADS, 1) k_tc_fused(FusedArgs fa) {
 #ifdef GNNB_TRACE
         long long g_wait = 0, g_all = clock64();
 #endif
-        uint32_t t = 0;
-        for (int64_t item = rank; item < nitems; item += nranks) {
-            const int tile = (int)(item % ntiles);
-            const int ks0 = __ldg(plan.tile_ks0 + tile), ks1 = __ldg(plan.tile_ks0 + tile + 1);
-            const int dm0 = (int)(item / ntiles) * PD;
-            for (int ks = ks0; ks < ks1; ++ks, ++t) {
-                if ((int)(t % (uint32_t)GATHER_WARPS) != gw) continue;
-                const uint32_t slot = t % (uint32_t)NS, ph = (t / (uint32_t)NS) & 1u;
+        uint32_t slot = 0, ph = 0;
+        int turn = 0;                                   // stage counter modulo the number of gather warps
+        for (ItemCursor cur(rank, nranks, ntiles, npairs); cur.valid(); cur.next()) {
+            const int ks0 = __ldg(plan.tile_ks0 + cur.tile), ks1 = __ldg(plan.tile_ks0 + cur.tile + 1);
+            const int dm0 = cur.pair * PD;
+            for (int ks = ks0; ks < ks1; ++ks) {
+                const uint32_t slot_ = slot, ph_ = ph;
+                const bool mine = turn == gw;
+                if (++slot == (uint32_t)NS) { slot = 0; ph ^= 1u; }
+                if (++turn == GATHER_WARPS) turn = 0;
+                if (!mine) continue;
                 const int idx = __ldg(plan.ks_rows + (size_t)ks * 16 + (lane & 15));      // issued before the wait below
 #ifdef GNNB_TRACE
                 const long long g0_ = clock64();
 #endif
-                mbar_wait(smem_u32(&tl->empty[slot]), ph ^ 1u);
+                mbar_wait(smem_u32(&tl->empty[slot_]), ph_ ^ 1u);
 #ifdef GNNB_TRACE
                 g_wait += clock64() - g0_;
 #endif
-                const uint32_t dst0 = ring + slot * STAGE + W_KS;
+                const uint32_t dst0 = ring + slot_ * STAGE + W_KS;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int sub = i >> 2;
@@ -861,14 +908,16 @@ __global__ void __launch_bounds__(fz::THREADS, 1) k_tc_fused(FusedArgs fa) {
                     cp_async16(dst, src, ok);
                     cp_async16(dst + B_PLANE, src + APLANE, ok);
                 }
-                cp_async_arrive(smem_u32(&tl->full[slot]));
+                cp_async_arrive(smem_u32(&tl->full[slot_]));
             }
         }
 #ifdef GNNB_TRACE
         if (rank == 1 && gw == 0 && lane == 0) printf("TRACE fused-gather: total %lld, wait stage empty %lld\n", clock64() - g_all, g_wait);
 #endif
     } else if (warp >= CHAIN_WARP0) {
-        // ---- node-update chains ----
+        // ---- node-update chains: subdomain j of every item is walked by TWO warpgroups, h = 0 / 1 owning channels [32 h, +32)
+        //      of every epilogue (thread = row of the tile = TMEM lane in both); the chain is a latency chain of three GEMMs and
+        //      four epilogues, and halving each epilogue's per-thread work shortens it more than anything else did ----
         const float* __restrict__ lb = a.lb;
         const float* __restrict__ ub = a.ub;
         const float* __restrict__ rlx = a.rlx;
@@ -876,44 +925,51 @@ __global__ void __launch_bounds__(fz::THREADS, 1) k_tc_fused(FusedArgs fa) {
         float* __restrict__ scores = a.scores;
         const RowMap map = a.map;
         const float bscore = g.bias[FSCORE][0];
+        const int cw = warp - CHAIN_WARP0;                        // 0 .. 15
+        const int j = uniform(cw >> 3), h = uniform((cw >> 2) & 1);
         WG c;
-        c.wg = uniform((warp - CHAIN_WARP0) >> 2);
-        c.lead_warp = ((warp - CHAIN_WARP0) & 3) == 0;
+        c.wg = j;                                                // named barrier 1 + j, 256 threads
+        c.bar_threads = 256;
+        c.lead_warp = (cw & 7) == 0;
         c.t = threadIdx.x & 127;
         c.land = 0;
-        c.mbar_mma = smem_u32(&tl->mma[c.wg]);
+        c.mbar_mma = smem_u32(&tl->mma[j]);
         c.mbar_tma = 0;
         c.ph_mma = 0;
         c.ph_tma = 0;
         c.acol = ACC_COL;
         c.tmem0 = (uint32_t)uniform((int)tmem_base) & 0x0000FFFFu;
         c.tmem = tmem_base + ((uint32_t)((c.t >> 5) * 32) << 16);
-        const int j = c.wg;
-        const uint32_t D = D_COL + D_WIN * (uint32_t)j;          // this warpgroup's accumulator window [D, D + 128)
-        const uint32_t stage = stg + (uint32_t)(warp - CHAIN_WARP0) * stg_warp;      // this warp's 8 KB (4 KB with the score head) staging buffer
+        const uint32_t D = D_COL + D_WIN * (uint32_t)j;          // this chain's accumulator window [D, D + 128)
+        const int pw = j * 4 + (cw & 3);                          // the pair of warps (one per half) that holds rows 32 (cw & 3) .. + 31
+        const uint32_t stage = stg + (uint32_t)pw * stg_warp;     // the pair's 8 KB (4 KB with the score head) staging buffer
+        const int pair_bar = 3 + pw;                              // named barriers 3 .. 10, 64 threads
+        const int Q0 = 2 * h;                                     // this half's K steps / 16-channel groups: Q0, Q0 + 1
         mbar_wait(smem_u32(&tl->wts), 0);                        // chain weights have landed
         bool bad = false;
-        // this row's inputs are two dependent 4-byte gathers (slot -> node, node -> bounds): the node index is fetched two
-        // items ahead and the bounds one item ahead, so neither latency is on the chain's path
-        int64_t nrow_n = -1, nrow_nn = -1;
+        // the node of a slot does not depend on the subdomain: node_of_slot[tile * 128 + t]; index into the caller's [B, n] arrays =
+        // dom * n + node.  Two dependent 4-byte gathers (slot -> node, node -> bounds): the node is fetched two items ahead and
+        // the bounds one item ahead, so neither latency is on the chain's path
+        int node_n = -1, node_nn = -1;
         float l_n = 0.f, u_n = 1.f;
         int slot0_n = 0;
-        auto fetch_node = [&](int64_t it_) -> int64_t {          // index into the caller's [B, n] arrays, -1 = padding slot / no item
-            if (it_ >= nitems) return -1;
-            const int d_ = (int)(it_ / ntiles) * PD + j;
-            if (d_ >= a.Bc) return -1;
-            return natural_row(map, ((int64_t)d_ * ntiles + it_ % ntiles) * TILE + c.t);
+        auto fetch_node = [&](const ItemCursor& cu) -> int {     // -1 = padding slot / no item / no such subdomain
+            if (!cu.valid() || cu.pair * PD + j >= a.Bc) return -1;
+            return __ldg(map.node_of_slot + cu.tile * TILE + c.t);
         };
-        auto fetch_bounds = [&](int64_t it_, int64_t nrow_) {
-            nrow_n = nrow_; l_n = 0.f; u_n = 1.f; slot0_n = 0;
-            if (nrow_ >= 0) { l_n = ldg1_now(lb + nrow_); u_n = ldg1_now(ub + nrow_); }
-            if (it_ < nitems) {
-                const int d_ = (int)(it_ / ntiles) * PD + j;
-                if (d_ < a.Bc) slot0_n = __ldg(amb_base + (int64_t)d_ * ntiles + it_ % ntiles);
-            }
+        auto fetch_bounds = [&](const ItemCursor& cu, int node_) {
+            node_n = node_; l_n = 0.f; u_n = 1.f; slot0_n = 0;
+            if (!cu.valid()) return;
+            const int d_ = cu.pair * PD + j;
+            if (d_ >= a.Bc) return;
+            if (node_ >= 0) { l_n = ldg1_now(lb + (int64_t)d_ * map.n + node_); u_n = ldg1_now(ub + (int64_t)d_ * map.n + node_); }
+            if (amb_base != nullptr) slot0_n = __ldg(amb_base + (int64_t)d_ * ntiles + cu.tile);
         };
-        fetch_bounds(rank, fetch_node(rank));
-        nrow_nn = fetch_node((int64_t)rank + nranks);
+        ItemCursor cur(rank, nranks, ntiles, npairs), cur1 = cur, cur2 = cur;
+        cur1.next();
+        cur2.next(); cur2.next();
+        fetch_bounds(cur, fetch_node(cur));
+        node_nn = fetch_node(cur1);
         uint32_t it = 0;
 #ifdef GNNB_TRACE
         long long c_wait = 0, c_ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, c_all = clock64(), c0_;
@@ -922,15 +978,15 @@ __global__ void __launch_bounds__(fz::THREADS, 1) k_tc_fused(FusedArgs fa) {
 #else
 #define CTR(i) do {} while (0)
 #endif
-        for (int64_t item = rank; item < nitems; item += nranks, ++it) {
+        for (; cur.valid(); cur.next(), cur1.next(), cur2.next(), ++it) {
             const uint32_t buf = it & 1u, bufph = (it >> 1) & 1u;
             const uint32_t acc_full = smem_u32(&tl->acc_full[buf]), acc_empty = smem_u32(&tl->acc_empty[buf]);
-            const int dom = (int)(item / ntiles) * PD + j;
-            const int64_t nrow = nrow_n;
+            const int dom = cur.pair * PD + j;
+            const int node = node_n;
             const float l = l_n, u = u_n;
             const int slot0 = slot0_n;
-            fetch_bounds(item + nranks, nrow_nn);
-            nrow_nn = fetch_node(item + 2 * (int64_t)nranks);
+            fetch_bounds(cur1, node_nn);
+            node_nn = fetch_node(cur2);
 #ifdef GNNB_TRACE
             c0_ = clock64();
 #endif
@@ -940,59 +996,113 @@ __global__ void __launch_bounds__(fz::THREADS, 1) k_tc_fused(FusedArgs fa) {
 #endif
             tc_fence_after();
             if (dom >= a.Bc) {                                    // odd batch: the last pair has one subdomain
-                if (c.t == 0) mbar_arrive(acc_empty);
+                if (h == 0 && c.t == 0) mbar_arrive(acc_empty);
                 continue;
             }
-            const int64_t tile = (int64_t)dom * ntiles + item % ntiles;
+            const int64_t tile = (int64_t)dom * ntiles + cur.tile;
             c.acol = ACC_COL + buf * ACC_WIN + 64u * (uint32_t)j;
 #ifdef GNNB_TRACE
             c0_ = clock64(); ++c_tiles;
 #endif
             const Ratio q = compute_ratio(l, u);
             const float gate = (q.r0 != 0.0f) ? 1.0f : 0.0f;
-            const bool amb = (q.amb != 0.0f) && nrow >= 0;
+            const bool amb = (q.amb != 0.0f) && node >= 0;
             const unsigned bal = __ballot_sync(0xffffffffu, amb);
-            if ((c.t & 31) == 0) tl->wcnt[j][c.t >> 5] = __popc(bal);
+            if ((c.t & 31) == 0) tl->wcnt[j * 2 + h][c.t >> 5] = __popc(bal);
             // nb: accumulator columns -> fp16 hi / lo A operand, in place (K step qd = channels [16 qd, 16 qd + 16))
             {
                 unsigned char* dbg = fa.nb_dbg ? reinterpret_cast<unsigned char*>(fa.nb_dbg) + tile * (int64_t)ABUF + (uint32_t)c.t * 16u : nullptr;
+                float v0[16], v1[16];
+                tmem_ld32_sync(c.tmem + c.acol + h * 32, v0, v1);
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float v0[16], v1[16];
-                    tmem_ld32_sync(c.tmem + c.acol + h * 32, v0, v1);
+                for (int qq = 0; qq < 2; ++qq) {
+                    const int qd = Q0 + qq;
+                    uint32_t w[16];
+                    split16(qq ? v1 : v0, w);
+                    tmem_st16(c.tmem + c.acol + 16 * qd, w);
+                    if (dbg != nullptr) {      // piece-major nb image of the two-launch path (snapshots)
 #pragma unroll
-                    for (int qq = 0; qq < 2; ++qq) {
-                        const int qd = h * 2 + qq;
-                        uint32_t w[16];
-                        split16(qq ? v1 : v0, w);
-                        tmem_st16(c.tmem + c.acol + 16 * qd, w);
-                        if (dbg != nullptr) {      // piece-major nb image of the two-launch path (snapshots)
-#pragma unroll
-                            for (int hh = 0; hh < 2; ++hh) {
-                                const uint32_t off = (uint32_t)(qd * 2 + hh) * NB_PIECE;
-                                *reinterpret_cast<uint4*>(dbg + off) = make_uint4(w[4 * hh], w[4 * hh + 1], w[4 * hh + 2], w[4 * hh + 3]);
-                                *reinterpret_cast<uint4*>(dbg + APLANE + off) = make_uint4(w[8 + 4 * hh], w[8 + 4 * hh + 1], w[8 + 4 * hh + 2], w[8 + 4 * hh + 3]);
-                            }
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const uint32_t off = (uint32_t)(qd * 2 + hh) * NB_PIECE;
+                            *reinterpret_cast<uint4*>(dbg + off) = make_uint4(w[4 * hh], w[4 * hh + 1], w[4 * hh + 2], w[4 * hh + 3]);
+                            *reinterpret_cast<uint4*>(dbg + APLANE + off) = make_uint4(w[8 + 4 * hh], w[8 + 4 * hh + 1], w[8 + 4 * hh + 2], w[8 + 4 * hh + 3]);
                         }
                     }
                 }
             }
             CTR(0);
+            unsigned char* img = a.mu_out ? reinterpret_cast<unsigned char*>(a.mu_out) + tile * (int64_t)ABUF : nullptr;
+            if (inp) {
+                // ---- input-layer update (graph_conv.py:380-385): a second A operand relu(inp_b([l0, u0])) of this half's 32 channels
+                //      (K < 64 first layer on CUDA cores) goes to D[64:128); D[0:64) = nb Wn^T + that Wi^T, one commit ----
+                {
+                    const float* w0 = &tl->bias[3][0];
+#pragma unroll
+                    for (int qq = 0; qq < 2; ++qq) {
+                        const int qd = Q0 + qq;
+                        float o[16], wl[16], wu[16];
+                        lds16(tl->bias[2] + qd * 16, o);
+                        lds16(w0 + qd * 16, wl);
+                        lds16(w0 + P + qd * 16, wu);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = relu_nan(fmaf(node >= 0 ? l : 0.f, wl[i], fmaf(node >= 0 ? u : 0.f, wu[i], o[i])));
+                        uint32_t w[16];
+                        split16(o, w);
+                        tmem_st16(c.tmem + D + 64 + 16 * qd, w);
+                    }
+                }
+                gemm_sync(c);
+                if (c.lead_warp) {
+                    tc_fence_after();
+                    if (elect_one()) {
+                        WG c2 = c;
+                        c2.acol = D + 64;
+                        issue_ts(c, W + INF_WN, W + INF_WN + WPLANE, 64, D, false);
+                        issue_ts(c2, W + INF_WI, W + INF_WI + WPLANE, 64, D, true);
+                        umma_commit(c.mbar_mma);
+                    }
+                    __syncwarp();
+                }
+                gemm_finish(c);
+                CTR(1);
+                {
+                    float v0[16], v1[16];
+                    tmem_ld32_sync(c.tmem + D + h * 32, v0, v1);
+#pragma unroll
+                    for (int qq = 0; qq < 2; ++qq) {
+                        float (&v)[16] = qq ? v1 : v0;
+                        const int qd = Q0 + qq;
+                        float bb[16];
+                        lds16(tl->bias[0] + qd * 16, bb);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = relu_nan(v[i] + bb[i]);
+                        a_store16(c, qd, v);
+                    }
+                }
+                CTR(2);
+                gemm_ts(c, W + INF_B22, W + INF_B22 + WPLANE, 64, D);
+                CTR(3);
+                if (h == 0 && c.t == 0) mbar_arrive(acc_empty);
+                bad |= epilogue_to_mu_pair<false>(c, h, pair_bar, D, tl->bias[1], 1.0f, node >= 0, img, stage);
+                CTR(6);
+                continue;
+            }
             // D[0:128) = nb [W3a; W3b]^T
             gemm_ts(c, W + UPD_W3, W + UPD_W3 + 2 * WPLANE, 128, D);
             CTR(1);
             // slot of this row's relax' = first slot of the tile + number of ambiguous rows before it
             int slot = slot0 + __popc(bal & ((1u << (c.t & 31)) - 1u));
 #pragma unroll
-            for (int w = 0; w < 3; ++w) slot += (w < (c.t >> 5)) ? tl->wcnt[j][w] : 0;
-            const float* rt = rlx + (size_t)(slot >> 7) * (TILE * P) + (size_t)(slot & (TILE - 1)) * 4;
+            for (int w = 0; w < 3; ++w) slot += (w < (c.t >> 5)) ? tl->wcnt[j * 2 + h][w] : 0;
+            const float* rt = rlx + (size_t)(slot >> 7) * (TILE * P) + (size_t)(slot & (TILE - 1)) * 4 + (size_t)(8 * h) * (TILE * 4);
             if (amb) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(rt + (size_t)i * (TILE * 4)));
+                for (int i = 0; i < 8; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(rt + (size_t)i * (TILE * 4)));
             }
             // h3 = relu(r0 * D[0:64) + r1 * D[64:128) + b3) -> A (graph_conv.py:169-170 / 331-336)
 #pragma unroll
-            for (int qd = 0; qd < 4; ++qd) {
+            for (int qq = 0; qq < 2; ++qq) {
+                const int qd = Q0 + qq;
                 float x[16], y[16], bb[16];
                 {
                     uint32_t ra[16], rb[16];
@@ -1009,25 +1119,24 @@ __global__ void __launch_bounds__(fz::THREADS, 1) k_tc_fused(FusedArgs fa) {
             CTR(2);
             // D[0:64) = h3 Wc^T; meanwhile fetch this row's relax'
             gemm_ts_start(c, W + UPD_WC, W + UPD_WC + WPLANE, 64, D);
-            float4 rx[16];
+            float4 rx[8];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) rx[i] = amb ? ldg4_now(rt + (size_t)i * (TILE * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < 8; ++i) rx[i] = amb ? ldg4_now(rt + (size_t)i * (TILE * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
             gemm_finish(c);
             CTR(3);
             // g = relu(D + relax' + bc) -> A
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            {
                 float v0[16], v1[16];
                 tmem_ld32_sync(c.tmem + D + h * 32, v0, v1);
 #pragma unroll
                 for (int qq = 0; qq < 2; ++qq) {
                     float (&v)[16] = qq ? v1 : v0;
-                    const int qd = h * 2 + qq;
+                    const int qd = Q0 + qq;
                     float bb[16];
                     lds16(tl->bias[1] + qd * 16, bb);
 #pragma unroll
                     for (int hh = 0; hh < 4; ++hh) {
-                        const float4 x = rx[qd * 4 + hh];
+                        const float4 x = rx[qq * 4 + hh];
                         v[hh * 4 + 0] = relu_nan(v[hh * 4 + 0] + x.x + bb[hh * 4 + 0]);
                         v[hh * 4 + 1] = relu_nan(v[hh * 4 + 1] + x.y + bb[hh * 4 + 1]);
                         v[hh * 4 + 2] = relu_nan(v[hh * 4 + 2] + x.z + bb[hh * 4 + 2]);
@@ -1040,22 +1149,20 @@ __global__ void __launch_bounds__(fz::THREADS, 1) k_tc_fused(FusedArgs fa) {
             // D[0:64) = g W4_2^T;  mu = (D + b) * (r0 != 0) -> global
             gemm_ts(c, W + UPD_W42, W + UPD_W42 + WPLANE, 64, D);
             CTR(5);
-            unsigned char* img = a.mu_out ? reinterpret_cast<unsigned char*>(a.mu_out) + tile * (int64_t)ABUF : nullptr;
             if (!with_score) {
-                if (c.t == 0) mbar_arrive(acc_empty);              // the last GEMM that reads this subdomain's A columns has completed
-                bad |= epilogue_to_mu_warp<false>(c, D, tl->bias[2], gate, nrow >= 0, img, stage);
+                if (h == 0 && c.t == 0) mbar_arrive(acc_empty);    // the last GEMM that reads this subdomain's A columns has completed
+                bad |= epilogue_to_mu_pair<false>(c, h, pair_bar, D, tl->bias[2], gate, node >= 0, img, stage);
             } else {      // score head on the new embeddings (graph_conv.py:448-449)
-                bad |= epilogue_to_mu_warp<true>(c, D, tl->bias[2], gate, nrow >= 0, img, stage);
+                bad |= epilogue_to_mu_pair<true>(c, h, pair_bar, D, tl->bias[2], gate, node >= 0, img, stage);
                 gemm_ts(c, W + UPD_FN, W + UPD_FN + WPLANE, 64, D);
-                if (c.t == 0) mbar_arrive(acc_empty);
+                if (h == 0 && c.t == 0) mbar_arrive(acc_empty);
                 float sc = 0.f;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
+                {
                     float v0[16], v1[16];
                     tmem_ld32_sync(c.tmem + D + h * 32, v0, v1);
 #pragma unroll
                     for (int qq = 0; qq < 2; ++qq) {
-                        const int qd = h * 2 + qq;
+                        const int qd = Q0 + qq;
                         float bb[16], ww[16];
                         lds16(tl->bias[3] + qd * 16, bb);
                         lds16(tl->vec + qd * 16, ww);
@@ -1063,7 +1170,18 @@ __global__ void __launch_bounds__(fz::THREADS, 1) k_tc_fused(FusedArgs fa) {
                         for (int i = 0; i < 16; ++i) sc = fmaf(relu_nan((qq ? v1 : v0)[i] + bb[i]), ww[i], sc);
                     }
                 }
-                if (nrow >= 0) scores[(nrow / map.n) * a.score_stride + a.score_off + (nrow % map.n)] = fmaf(sc, AINV, bscore);
+                // the two halves of the dot product meet in a free tensor-memory column of the row's lane (D[64:128) is unused here)
+                if (h == 1) {
+                    tmem_st1(c.tmem + D + 64, __float_as_uint(sc));
+                    tmem_st_wait();
+                }
+                tc_fence_before();
+                wg_barrier(c);
+                tc_fence_after();
+                if (h == 0) {
+                    sc += __uint_as_float(tmem_ld1_sync(c.tmem + D + 64));
+                    if (node >= 0) scores[(int64_t)dom * a.score_stride + a.score_off + node] = fmaf(sc, AINV, bscore);
+                }
             }
             CTR(6);
         }
@@ -1072,9 +1190,13 @@ __global__ void __launch_bounds__(fz::THREADS, 1) k_tc_fused(FusedArgs fa) {
             printf("TRACE fused-chain wg0: tiles %d total %lld | wait acc_full %lld | per tile: convert %lld gemm1 %lld epi1 %lld gemm2 %lld epi2 %lld gemm3 %lld epi3 %lld\n",
                    c_tiles, clock64() - c_all, c_wait, c_ph[0] / max(c_tiles, 1), c_ph[1] / max(c_tiles, 1), c_ph[2] / max(c_tiles, 1), c_ph[3] / max(c_tiles, 1),
                    c_ph[4] / max(c_tiles, 1), c_ph[5] / max(c_tiles, 1), c_ph[6] / max(c_tiles, 1));
+        if (rank == 1 && threadIdx.x == CHAIN_WARP0 * 32) {
+            printf("TRACE fused-e3 (cumulative over launches): wait prev store %lld, tmem load %lld, compute + stage %lld, fence + issue %lld\n",
+                   g_e3_trace[0], g_e3_trace[1], g_e3_trace[2], g_e3_trace[3]);
+        }
 #endif
         if (bad) atomicAdd(a.nan_count, 1ULL);
-        if ((c.t & 31) == 0) bulk_wait_all();        // this warp's last bulk stores still read its staging buffer
+        if (h == 0 && (c.t & 31) == 0) bulk_wait_all();        // this pair's last bulk stores still read its staging buffer
     }
     tc_fence_before();
     __syncthreads();
@@ -1448,8 +1570,9 @@ void tc_update(const GnnParams& g, bool backward, const float* lb, const float* 
 
 void tc_fused(const GnnParams& g, const PropPlan* plan, const float* mu_in, bool backward, const float* lb, const float* ub,
               const float* relax, const int32_t* amb_base, float* mu_out, float* scores, RowMap map, int64_t score_stride, int64_t score_off,
-              int64_t rows, unsigned long long* nan_count, float* nb_dbg, cudaStream_t st, int64_t* launches) {
+              int64_t rows, unsigned long long* nan_count, float* nb_dbg, bool input_layer, cudaStream_t st, int64_t* launches) {
     FusedArgs fa;
+    fa.input_layer = input_layer ? 1 : 0;
     fa.u = make_upd_args(g, backward, lb, ub, nullptr, relax, amb_base, mu_out, scores, map, score_stride, score_off, rows, nan_count);
     fa.plan = prop_plan_dev(plan);
     fa.mu_in = reinterpret_cast<const uint16_t*>(mu_in);
