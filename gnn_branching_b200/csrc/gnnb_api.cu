@@ -304,19 +304,33 @@ int run_chunk(gnnb_ctx* ctx, const ChunkPtrs& in, int Bc, float* scores, float* 
         }
         amb_compact_all(al, st, lc);
     }
-    // round-independent relaxation features of every hidden layer
-    for (int k = 1; k <= L; ++k) {
-        NodeInputs ni{in.lb[k], in.ub[k], in.dual[k - 1], in.pre[k - 1], in.post[k - 1], ctx->layers[k - 1].bias_node,
-                      ctx->n[k], R(k), ctx->amb_rows[k], ctx->amb_base[k], M(k)};
-        {
-            ProfScope ps(ctx, GNNB_K_RELAX, (int64_t)Bc * ctx->n[k], st);
-            if (tc && !amb_all) amb_compact(in.lb[k], in.ub[k], M(k), ni.rows, ctx->amb_cnt[k], ctx->amb_base[k], ctx->amb_rows[k], st, lc);
-            if (tc) tc_relax(g, ni, ctx->relax_f[k], ctx->relax_b[k], st, lc);
-            else simt_relax(g, ni, ctx->relax_f[k], ctx->relax_b[k], st, lc);
+    // round-independent relaxation features of every hidden layer (tensor-core path: one launch per AMB_MAX_LAYERS layers)
+    {
+        std::vector<NodeInputs> nis(L + 1);
+        for (int k = 1; k <= L; ++k)
+            nis[k] = NodeInputs{in.lb[k], in.ub[k], in.dual[k - 1], in.pre[k - 1], in.post[k - 1], ctx->layers[k - 1].bias_node,
+                                ctx->n[k], R(k), ctx->amb_rows[k], ctx->amb_base[k], M(k)};
+        if (tc) {
+            for (int k0 = 1; k0 <= L; k0 += AMB_MAX_LAYERS) {
+                const int nl = (L - k0 + 1) < AMB_MAX_LAYERS ? (L - k0 + 1) : AMB_MAX_LAYERS;
+                int64_t nodes = 0;
+                for (int k = k0; k < k0 + nl; ++k) {
+                    nodes += (int64_t)Bc * ctx->n[k];
+                    if (!amb_all) amb_compact(in.lb[k], in.ub[k], M(k), nis[k].rows, ctx->amb_cnt[k], ctx->amb_base[k], ctx->amb_rows[k], st, lc);
+                }
+                ProfScope ps(ctx, GNNB_K_RELAX, nodes, st);
+                tc_relax(g, &nis[k0], &ctx->relax_f[k0], &ctx->relax_b[k0], nl, st, lc);
+            }
         }
-        // tensor-core mode stores relax' (pre-multiplied by fc4 / bc4's relax half, compacted, tile-transposed): not comparable 1:1
-        TRY(snap(ctx, name(tc ? "relaxp_f%d" : "relax_f%d", k, 0), ctx->relax_f[k], (int64_t)Bc * ctx->n[k] * P, st));
-        TRY(snap(ctx, name(tc ? "relaxp_b%d" : "relax_b%d", k, 0), ctx->relax_b[k], (int64_t)Bc * ctx->n[k] * P, st));
+        for (int k = 1; k <= L; ++k) {
+            if (!tc) {
+                ProfScope ps(ctx, GNNB_K_RELAX, (int64_t)Bc * ctx->n[k], st);
+                simt_relax(g, nis[k], ctx->relax_f[k], ctx->relax_b[k], st, lc);
+            }
+            // tensor-core mode stores relax' (pre-multiplied by fc4 / bc4's relax half, compacted, tile-transposed): not comparable 1:1
+            TRY(snap(ctx, name(tc ? "relaxp_f%d" : "relax_f%d", k, 0), ctx->relax_f[k], (int64_t)Bc * ctx->n[k] * P, st));
+            TRY(snap(ctx, name(tc ? "relaxp_b%d" : "relax_b%d", k, 0), ctx->relax_b[k], (int64_t)Bc * ctx->n[k] * P, st));
+        }
     }
     {
         ProfScope ps(ctx, GNNB_K_INPUT_EMBED, (int64_t)Bc * ctx->n[0], st);

@@ -116,7 +116,9 @@ void simt_input_update(const GnnParams& g, const float* lb0, const float* ub0, c
 int simt_init();  // opt-in shared memory sizes; returns cudaError_t
 
 // tcgen05 node kernels (gnnb_tc.cu) — same contracts as the SIMT ones
-void tc_relax(const GnnParams& g, const NodeInputs& in, float* relax_f, float* relax_b, cudaStream_t st, int64_t* launches);
+// relax' of n_layers <= AMB_MAX_LAYERS hidden layers in one launch (their ambiguous rows compacted by amb_compact_all)
+void tc_relax(const GnnParams& g, const NodeInputs* in, float* const* relax_f, float* const* relax_b, int n_layers, cudaStream_t st,
+              int64_t* launches);
 void tc_update(const GnnParams& g, bool backward, const float* lb, const float* ub, const float* nb, const float* relax,
                const int32_t* amb_base, float* mu_out, float* scores, RowMap map, int64_t score_stride, int64_t score_off, int64_t rows,
                unsigned long long* nan_count, cudaStream_t st, int64_t* launches);

@@ -724,7 +724,8 @@ struct ItemCursor {
     }
 };
 
-__global__ void __launch_bounds__(fz::THREADS, 1) k_tc_fused(FusedArgs fa) {
+template <bool INPUT_LAYER>
+__device__ __forceinline__ void fused_body(const FusedArgs& fa) {
     using namespace fz;
     const UpdArgs& a = fa.u;
     const GnnParams& g = a.g;
@@ -754,7 +755,7 @@ __global__ void __launch_bounds__(fz::THREADS, 1) k_tc_fused(FusedArgs fa) {
     tc_fence_after();
     const uint32_t tmem_base = tl->tmem_slot;
     const int l3 = a.backward ? BC3 : FC3, l4b = a.backward ? BC4_1 : FC4_2, lc = a.backward ? T_BWD_C : T_FWD_C;
-    const bool inp = fa.input_layer != 0;
+    constexpr bool inp = INPUT_LAYER;
     if (threadIdx.x == 0) {
         const uint32_t mb = smem_u32(&tl->wts);
         if (!inp) {
@@ -1203,12 +1204,24 @@ __global__ void __launch_bounds__(fz::THREADS, 1) k_tc_fused(FusedArgs fa) {
     if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+// hidden layers (forward / backward sweep, + score head) and the input-layer update: the same body under two kernel names, so that
+// profiles tell them apart
+__global__ void __launch_bounds__(fz::THREADS, 1) k_tc_fused(FusedArgs fa) { fused_body<false>(fa); }
+__global__ void __launch_bounds__(fz::THREADS, 1) k_tc_fused_input(FusedArgs fa) { fused_body<true>(fa); }
+
 // ---- relax: round-independent part of the fc4 / bc4 pre-activation of a hidden layer --------------------------
 constexpr uint32_t RLX_FR = 0, RLX_BC11 = 2 * WPLANE, RLX_BC12 = 4 * WPLANE, RLX_BC2 = 6 * WPLANE, RLX_BR = 12 * WPLANE;
 constexpr uint32_t RLX_WBYTES = 14 * WPLANE;
 
-__global__ void __launch_bounds__(128 * NWG, 1) k_tc_relax(GnnParams g, NodeInputs in, float* __restrict__ rlx_f,
-                                                           float* __restrict__ rlx_b) {
+// every hidden layer of a wave in one launch: the warpgroups walk the concatenation of the layers' compacted ambiguous tiles
+struct RelaxLayers {
+    NodeInputs in[AMB_MAX_LAYERS];
+    float* rlx_f[AMB_MAX_LAYERS];
+    float* rlx_b[AMB_MAX_LAYERS];
+    int n;
+};
+
+__global__ void __launch_bounds__(128 * NWG, 1) k_tc_relax(GnnParams g, const __grid_constant__ RelaxLayers rl) {
     const uint16_t* const wsrc[5] = {g.tcx_w[T_FWD_R], g.tc[BC1_1], g.tc[BC1_2], g.tc[BC2], g.tcx_w[T_BWD_R]};
     const uint32_t woff[5] = {RLX_FR, RLX_BC11, RLX_BC12, RLX_BC2, RLX_BR};
     const uint32_t wlen[5] = {2 * WPLANE, 2 * WPLANE, 2 * WPLANE, 6 * WPLANE, 2 * WPLANE};
@@ -1223,10 +1236,24 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_relax(GnnParams g, NodeInpu
     pdl_trigger(); pdl_wait();
     WG c = make_wg(s, RLX_WBYTES);
     const uint32_t W = s.w;
-    // only the ambiguous rows have non-zero relaxation features: walk them in compacted order (slot = tile * 128 + t)
-    const int64_t namb = __ldg(in.amb_base + (in.rows + TILE - 1) / TILE);
-    const int64_t ntiles = (namb + TILE - 1) / TILE;
-    for (int64_t tile = (int64_t)blockIdx.x * NWG + c.wg; tile < ntiles; tile += (int64_t)gridDim.x * NWG) {
+    // only the ambiguous rows have non-zero relaxation features: walk them in compacted order (slot = tile * 128 + t), layer
+    // after layer (tile0[k] = first global tile of layer k)
+    int tile0[AMB_MAX_LAYERS + 1];
+    tile0[0] = 0;
+#pragma unroll 1
+    for (int k = 0; k < rl.n; ++k) {
+        const int namb_k = __ldg(rl.in[k].amb_base + (rl.in[k].rows + TILE - 1) / TILE);
+        tile0[k + 1] = tile0[k] + (namb_k + TILE - 1) / TILE;
+    }
+    const int total_tiles = tile0[rl.n];
+    int k = 0;
+    for (int gt = (int)blockIdx.x * NWG + c.wg; gt < total_tiles; gt += (int)gridDim.x * NWG) {
+        while (gt >= tile0[k + 1]) ++k;
+        const NodeInputs& in = rl.in[k];
+        float* __restrict__ rlx_f = rl.rlx_f[k];
+        float* __restrict__ rlx_b = rl.rlx_b[k];
+        const int64_t tile = gt - tile0[k];
+        const int64_t namb = __ldg(in.amb_base + (in.rows + TILE - 1) / TILE);
         const int64_t slot = tile * TILE + c.t;
         float l = 0.f, u = 1.f, d1 = 0.f, d2 = 0.f, pp = 0.f, po = 0.f, bs = 0.f;
         if (slot < namb) {
@@ -1517,6 +1544,7 @@ int tc_init() {
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(k_tc_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(UPD_WBYTES, true))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_tc_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz::SMEM_MAX)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_tc_fused_input, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz::SMEM_MAX)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_tc_relax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(RLX_WBYTES, false))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_tc_input_embed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(EMB_WBYTES, true))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_tc_input_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(INU_WBYTES, true))) != cudaSuccess) return e;
@@ -1542,8 +1570,13 @@ int64_t tc_pack_weight(const float* w, int K, uint16_t* dst) {
     return tc_packed_elems(K);
 }
 
-void tc_relax(const GnnParams& g, const NodeInputs& in, float* relax_f, float* relax_b, cudaStream_t st, int64_t* launches) {
-    launch_pdl(k_tc_relax, grid_for(in.rows), 128 * NWG, smem_bytes(RLX_WBYTES, false), st, g, in, relax_f, relax_b);
+void tc_relax(const GnnParams& g, const NodeInputs* in, float* const* relax_f, float* const* relax_b, int n_layers, cudaStream_t st,
+              int64_t* launches) {
+    RelaxLayers rl;
+    rl.n = n_layers;
+    int64_t rows = 0;
+    for (int k = 0; k < n_layers; ++k) { rl.in[k] = in[k]; rl.rlx_f[k] = relax_f[k]; rl.rlx_b[k] = relax_b[k]; rows += in[k].rows; }
+    launch_pdl(k_tc_relax, grid_for(rows), 128 * NWG, smem_bytes(RLX_WBYTES, false), st, g, rl);
     ++*launches;
 }
 
@@ -1583,10 +1616,12 @@ void tc_fused(const GnnParams& g, const PropPlan* plan, const float* mu_in, bool
     fa.n_stages = ns > fz::NS_MAX ? fz::NS_MAX : ns;
     // layers with long K loops are bound by the propagation's issue loop, layers with short ones by the chains, whose GEMMs queue
     // behind whatever the propagation has issued: groups of 4 K steps for the former, single steps for the latter
-    fa.mma_group = prop_plan_ksteps_per_tile(plan) >= 12.0 ? 4 : (prop_plan_ksteps_per_tile(plan) >= 6.0 ? 2 : 1);
+    // (a chain takes ~11 000 cycles per item, a K step 192 cycles of tensor time: only K loops of 48+ steps outlast the chains)
+    fa.mma_group = prop_plan_ksteps_per_tile(plan) >= 48.0 ? 4 : (prop_plan_ksteps_per_tile(plan) >= 32.0 ? 2 : 1);
     if (fa.mma_group > fa.n_stages / 2) fa.mma_group = fa.n_stages / 2;
     const int64_t nitems = (int64_t)fa.plan.ntiles * ((fa.u.Bc + fz::PD - 1) / fz::PD);
-    launch_pdl(k_tc_fused, (int)(nitems < 1 ? 1 : (nitems < 148 ? nitems : 148)), fz::THREADS, fz::smem_for(wbytes, staging, fa.n_stages), st, fa);
+    launch_pdl(input_layer ? k_tc_fused_input : k_tc_fused, (int)(nitems < 1 ? 1 : (nitems < 148 ? nitems : 148)), fz::THREADS,
+               fz::smem_for(wbytes, staging, fa.n_stages), st, fa);
     ++*launches;
 }
 

@@ -3,7 +3,7 @@
      <tag>_ncu_launches.csv        the launch list (copied)
      <tag>_ncu_launch_shares.txt   share of the step per kernel
      <tag>_ncu_summary.txt         per-launch DRAM bytes / %, L2 %, tensor-pipe %, issue-slot % (from --set full)
-     <tag>_ncu_source_{prop,update}.txt   source page: stall reasons and hottest SASS lines of the two big kernels
+     <tag>_ncu_source_fused.txt   source page: stall reasons and hottest SASS lines of the fused layer kernel
      kernel_traffic.json           measured DRAM bytes per launch and subdomain per kernel class (bench.py's roofline.traffic)
    Usage: python scripts/ncu_profiles.py <tag> <domains in the capture>"""
 import csv, io, json, os, subprocess, sys
@@ -12,7 +12,8 @@ from collections import defaultdict
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag, domains = sys.argv[1], int(sys.argv[2])
 O, P = os.path.join(ROOT, 'gpurun_out'), os.path.join(ROOT, 'profiles')
-CLASS = {'k_tc_relax': 'relax', 'k_tc_update': 'update', 'k_tc_prop': 'prop', 'k_tc_input_embed': 'input', 'k_tc_input_update': 'input'}
+CLASS = {'k_tc_relax': 'relax', 'k_tc_update': 'update', 'k_tc_prop': 'prop', 'k_tc_input_embed': 'input', 'k_tc_input_update': 'input',
+         'k_tc_fused': 'layer', 'k_tc_fused_input': 'input'}
 
 # ---- launch list ----
 lines = [l for l in open(os.path.join(O, f'{tag}_launches.csv')) if not l.startswith('==')]
@@ -64,7 +65,7 @@ kt['_source'] = (f'ncu --set full, profiles/{tag}_ncu_summary.txt: bench.py --do
                  '(dram__bytes_read.sum + dram__bytes_write.sum)')
 json.dump(kt, open(os.path.join(P, 'kernel_traffic.json'), 'w'), indent=1)
 # ---- source page of the two big kernels: stall reasons and hottest SASS lines ----
-for kern, short in (('k_tc_prop', 'prop'), ('k_tc_update', 'update')):
+for kern, short in (('k_tc_fused', 'fused'),):
     src = subprocess.run(['ncu', '-i', os.path.join(O, f'{tag}_prof.ncu-rep'), '--page', 'source', '--csv', '--kernel-name', f'regex:{kern}$',
                           '--launch-skip', '0', '--launch-count', '1'], capture_output=True, text=True).stdout
     tmp = os.path.join(O, f'{tag}_src_{short}.csv')
