@@ -782,6 +782,8 @@ int gnnb_set_option(gnnb_ctx* ctx, const char* key, int64_t value) {
     } else if (k == "gather_prefetch") {
         if (value < 0 || value > 2) return fail(ctx, GNNB_ERR_INVALID, "gather_prefetch is 0, 1 or 2");
         ctx->gather_prefetch = (int)value;
+    } else if (k.rfind("fused_", 0) == 0) {       // experiment knobs of k_tc_fused (process-wide)
+        tc_fused_tune(k.c_str() + 6, (int)value);
     } else if (k == "snapshot") {
         ctx->snapshot = value ? 1 : 0;
     } else if (k == "profile") {

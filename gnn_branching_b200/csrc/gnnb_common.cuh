@@ -126,6 +126,7 @@ void tc_update(const GnnParams& g, bool backward, const float* lb, const float* 
 // to the update chain through tensor memory and are never written (k_tc_fused); nb_dbg: the nb tile images for snapshots, or null;
 // input_layer: the chain is the input-layer update (lb / ub = input bounds; backward, relax, amb_base, scores unused)
 struct PropPlan;
+void tc_fused_tune(const char* key, int value);
 void tc_fused(const GnnParams& g, const PropPlan* plan, const float* mu_in, bool backward, const float* lb, const float* ub,
               const float* relax, const int32_t* amb_base, float* mu_out, float* scores, RowMap map, int64_t score_stride, int64_t score_off,
               int64_t rows, unsigned long long* nan_count, float* nb_dbg, bool input_layer, cudaStream_t st, int64_t* launches);

@@ -171,6 +171,11 @@ __device__ __forceinline__ float ldg1_now(const float* p) {
     asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
 }
+__device__ __forceinline__ int ldgi_now(const int32_t* p) {
+    int v;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
 
 // accumulator columns [dcol, dcol+64) + bias (optionally ReLU) -> A operand
 template <bool RELU>
@@ -956,7 +961,7 @@ __device__ __forceinline__ void fused_body(const FusedArgs& fa) {
         int slot0_n = 0;
         auto fetch_node = [&](const ItemCursor& cu) -> int {     // -1 = padding slot / no item / no such subdomain
             if (!cu.valid() || cu.pair * PD + j >= a.Bc) return -1;
-            return __ldg(map.node_of_slot + cu.tile * TILE + c.t);
+            return ldgi_now(map.node_of_slot + cu.tile * TILE + c.t);      // issued here, not sunk to its first use an item later
         };
         auto fetch_bounds = [&](const ItemCursor& cu, int node_) {
             node_n = node_; l_n = 0.f; u_n = 1.f; slot0_n = 0;
@@ -964,7 +969,7 @@ __device__ __forceinline__ void fused_body(const FusedArgs& fa) {
             const int d_ = cu.pair * PD + j;
             if (d_ >= a.Bc) return;
             if (node_ >= 0) { l_n = ldg1_now(lb + (int64_t)d_ * map.n + node_); u_n = ldg1_now(ub + (int64_t)d_ * map.n + node_); }
-            if (amb_base != nullptr) slot0_n = __ldg(amb_base + (int64_t)d_ * ntiles + cu.tile);
+            if (amb_base != nullptr) slot0_n = ldgi_now(amb_base + (int64_t)d_ * ntiles + cu.tile);
         };
         ItemCursor cur(rank, nranks, ntiles, npairs), cur1 = cur, cur2 = cur;
         cur1.next();
@@ -1065,6 +1070,8 @@ __device__ __forceinline__ void fused_body(const FusedArgs& fa) {
                     __syncwarp();
                 }
                 gemm_finish(c);
+                if (h == 0 && c.t == 0) mbar_arrive(acc_empty);    // nb has been read: the propagation may refill this accumulator
+                c.acol = D + 64;                                  // the remaining A operands live in the consumed half of the window
                 CTR(1);
                 {
                     float v0[16], v1[16];
@@ -1081,15 +1088,21 @@ __device__ __forceinline__ void fused_body(const FusedArgs& fa) {
                     }
                 }
                 CTR(2);
-                gemm_ts(c, W + INF_B22, W + INF_B22 + WPLANE, 64, D);
+                gemm_ts_start(c, W + INF_B22, W + INF_B22 + WPLANE, 64, D);
+                gemm_finish(c);
                 CTR(3);
-                if (h == 0 && c.t == 0) mbar_arrive(acc_empty);
                 bad |= epilogue_to_mu_pair<false>(c, h, pair_bar, D, tl->bias[1], 1.0f, node >= 0, img, stage);
                 CTR(6);
                 continue;
             }
             // D[0:128) = nb [W3a; W3b]^T
-            gemm_ts(c, W + UPD_W3, W + UPD_W3 + 2 * WPLANE, 128, D);
+            gemm_ts_start(c, W + UPD_W3, W + UPD_W3 + 2 * WPLANE, 128, D);
+            gemm_finish(c);
+            // nb has been read: the propagation may refill this accumulator while the chain goes on.  The remaining A operands
+            // (h3, g, and the embeddings of the score head) live in D[64:128), each 16-column piece written by the thread that has
+            // just consumed it in the first epilogue
+            if (h == 0 && c.t == 0) mbar_arrive(acc_empty);
+            c.acol = D + 64;
             CTR(1);
             // slot of this row's relax' = first slot of the tile + number of ambiguous rows before it
             int slot = slot0 + __popc(bal & ((1u << (c.t & 31)) - 1u));
@@ -1148,15 +1161,15 @@ __device__ __forceinline__ void fused_body(const FusedArgs& fa) {
             }
             CTR(4);
             // D[0:64) = g W4_2^T;  mu = (D + b) * (r0 != 0) -> global
-            gemm_ts(c, W + UPD_W42, W + UPD_W42 + WPLANE, 64, D);
+            gemm_ts_start(c, W + UPD_W42, W + UPD_W42 + WPLANE, 64, D);
+            gemm_finish(c);
             CTR(5);
             if (!with_score) {
-                if (h == 0 && c.t == 0) mbar_arrive(acc_empty);    // the last GEMM that reads this subdomain's A columns has completed
                 bad |= epilogue_to_mu_pair<false>(c, h, pair_bar, D, tl->bias[2], gate, node >= 0, img, stage);
             } else {      // score head on the new embeddings (graph_conv.py:448-449)
                 bad |= epilogue_to_mu_pair<true>(c, h, pair_bar, D, tl->bias[2], gate, node >= 0, img, stage);
-                gemm_ts(c, W + UPD_FN, W + UPD_FN + WPLANE, 64, D);
-                if (h == 0 && c.t == 0) mbar_arrive(acc_empty);
+                gemm_ts_start(c, W + UPD_FN, W + UPD_FN + WPLANE, 64, D);
+                gemm_finish(c);
                 float sc = 0.f;
                 {
                     float v0[16], v1[16];
@@ -1601,6 +1614,17 @@ void tc_update(const GnnParams& g, bool backward, const float* lb, const float* 
     ++*launches;
 }
 
+// process-wide experiment knobs of the fused kernel (gnnb_set_option "fused_mma_group")
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+static struct { int mma_group = env_int("GNNB_FUSED_MMA_GROUP", 0); } g_fused_tune;
+void tc_fused_tune(const char* key, int value) {
+    const std::string k(key);
+    if (k == "mma_group") g_fused_tune.mma_group = value;
+}
+
 void tc_fused(const GnnParams& g, const PropPlan* plan, const float* mu_in, bool backward, const float* lb, const float* ub,
               const float* relax, const int32_t* amb_base, float* mu_out, float* scores, RowMap map, int64_t score_stride, int64_t score_off,
               int64_t rows, unsigned long long* nan_count, float* nb_dbg, bool input_layer, cudaStream_t st, int64_t* launches) {
@@ -1618,6 +1642,7 @@ void tc_fused(const GnnParams& g, const PropPlan* plan, const float* mu_in, bool
     // behind whatever the propagation has issued: groups of 4 K steps for the former, single steps for the latter
     // (a chain takes ~11 000 cycles per item, a K step 192 cycles of tensor time: only K loops of 48+ steps outlast the chains)
     fa.mma_group = prop_plan_ksteps_per_tile(plan) >= 48.0 ? 4 : (prop_plan_ksteps_per_tile(plan) >= 32.0 ? 2 : 1);
+    if (g_fused_tune.mma_group > 0) fa.mma_group = g_fused_tune.mma_group;
     if (fa.mma_group > fa.n_stages / 2) fa.mma_group = fa.n_stages / 2;
     const int64_t nitems = (int64_t)fa.plan.ntiles * ((fa.u.Bc + fz::PD - 1) / fz::PD);
     launch_pdl(input_layer ? k_tc_fused_input : k_tc_fused, (int)(nitems < 1 ? 1 : (nitems < 148 ? nitems : 148)), fz::THREADS,
