@@ -11,7 +11,8 @@ from .graph_conv import GraphNet                                # noqa: F401
 from .graph_score import GraphChoice                            # noqa: F401
 from .kw_score_conv import choose_node_conv, babsr_frontier     # noqa: F401
 from .domain_queue import DomainQueue, DomainBatch, ReLUDomain  # noqa: F401
+from .bab_step import FrontierStep, StepStats                   # noqa: F401
 
 __all__ = ['Frontier', 'synthetic_frontier', 'NetSpec', 'cifar_netspec', 'netspec_from_modules', 'Flatten', 'Scorer',
            'STATE_DICT_KEYS', 'GraphNet', 'GraphChoice', 'choose_node_conv', 'babsr_frontier', 'DomainQueue', 'DomainBatch',
-           'ReLUDomain']
+           'ReLUDomain', 'FrontierStep', 'StepStats']

@@ -1,0 +1,128 @@
+"""One batched branch-and-bound step, device-resident: pick -> split -> bound -> score -> add.
+
+The reference's loop body (plnn/relu_conv_gnnkwthreshold.py:126-244) handles ONE domain per iteration: ``pick_out`` the domain
+with the smallest lower bound, build its two children with ``net.get_lower_bound(mask, lbs, ubs, decision, choice)``
+(= ``KWConvGen.update_the_model``: intermediate bounds, then a Gurobi LP), ask the GNN for each child's branching decision
+(``graph.decision``) and ``add_domain`` the children that can still violate the property.  ``FrontierStep.step`` does the same
+for the next ``max_B`` domains of the queue at once, and nothing but four integers crosses the PCIe bus:
+
+    DomainQueue.pick(max_B)            gnnb_queue_pick       the parents' bounds, masks and stored decisions, dense [B, .]
+    split on the stored decision       (index arithmetic)    2 B children: (parent, choice 0) and (parent, choice 1)
+    Scorer.child_bounds                gnnb_child_bounds     bounds part of update_the_model for the 2 B children + BaB masks
+    GraphNet.score_frontier            gnnb_score            each child's GNN decision (argmax over its undecided ReLUs)
+    DomainQueue.add(children, keep)    gnnb_queue_add        children whose lower bound is still below the decision bound
+
+What is NOT here is the LP: Gurobi is out of scope, so the values the reference takes from the LP solution are
+SURROGATES and the step is labelled as such wherever it is reported — the child's lower bound is the lower bound of the
+property output from the KW / interval pass (valid, but looser than the LP's), its upper bound is the parent's, the GNN's
+LP features are zero duals and the activations of the ball centre as primals (the convention of the synthetic frontier
+generator).  A branch-and-bound run built from these steps is therefore a sound but weaker verifier than the
+reference's; its purpose here is the data path: the bounds the scorer reads are produced on the GPU that scores them.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List
+
+import torch
+import torch.nn.functional as F
+
+from .domain_queue import DomainBatch, DomainQueue
+from .frontier import Frontier
+from .graph_conv import GraphNet
+from .networks import NetSpec
+
+
+@dataclass
+class StepStats:
+    picked: int              # parents taken from the queue
+    children: int            # 2 * picked
+    second_pass: int         # children whose interval bounds triggered the second KW pass
+    added: int               # children put back into the queue
+    global_lb: float         # smallest lower bound left in the queue (nan when it is empty)
+
+
+class FrontierStep:
+    def __init__(self, model: GraphNet, net: NetSpec, x: torch.Tensor, eps: float, Wp: torch.Tensor, bp: float,
+                 capacity: int = 1 << 16, decision_bound: float = 0.0, device: int = 0):
+        self.model, self.net, self.eps, self.decision_bound = model, net, float(eps), float(decision_bound)
+        self.dev = torch.device('cuda', device)
+        self.scorer = model.scorer(device)
+        self.scorer.set_network(net, key=net.key)
+        self.queue = DomainQueue(self.scorer, capacity)
+        self.x = x.reshape(1, -1).to(self.dev, torch.float32)
+        self.Wp = Wp.reshape(1, -1).to(self.dev, torch.float32)
+        self.bp = torch.tensor([float(bp)], device=self.dev)
+        self.sizes = [net.n0] + net.hidden_sizes + [1]
+        self.offsets = torch.tensor([0] + list(torch.tensor(net.hidden_sizes).cumsum(0)), device=self.dev)
+        # surrogate LP primals: the activations of the ball centre (pre- and post-ReLU), shared by every domain
+        pre, post, h = [], [], self.x.reshape(1, *net.input_shape)
+        for a in net.affine:
+            w, b = a.weight.to(self.dev), a.bias.to(self.dev)
+            h = F.conv2d(h, w, b, stride=a.stride, padding=a.padding) if a.kind == 'conv' else F.linear(h.reshape(1, -1), w, b)
+            pre.append(h.reshape(1, -1))
+            h = h.clamp(min=0)
+            post.append(h.reshape(1, -1))
+        self.prim_pre, self.prim_post = pre, post
+        self.prim_out = (post[-1] @ self.Wp.t()).reshape(1) + self.bp
+        self._zeros = {}
+
+    # ---- seeding ----
+    def seed_root(self, lbs: List[torch.Tensor], ubs: List[torch.Tensor]) -> None:
+        """Put the root domain into the queue: its bounds (L + 2 flat tensors), mask from the bounds, GNN decision."""
+        lb = [t.reshape(1, -1).to(self.dev, torch.float32) for t in lbs]
+        ub = [t.reshape(1, -1).to(self.dev, torch.float32) for t in ubs]
+        mask = torch.cat([self._bab_mask(lb[k], ub[k]) for k in range(1, self.net.L + 1)], dim=1)
+        dec, ok = self._decide(lb, ub, mask)
+        self.queue.add(DomainBatch(lb[-1].reshape(1).clone(), ub[-1].reshape(1).clone(), lb, ub, mask, dec), keep=ok)
+
+    # ---- the step ----
+    def step(self, max_B: int, threshold: float = float('inf')) -> StepStats:
+        L = self.net.L
+        parents = self.queue.pick(max_B, threshold)
+        B = parents.B
+        if B == 0:
+            return StepStats(0, 0, 0, 0, float('nan'))
+        rep = lambda t: t.repeat_interleave(2, dim=0)
+        choice = torch.arange(2 * B, device=self.dev, dtype=torch.int32) & 1
+        dec = rep(parents.decision)
+        lbs, ubs, masks, second = self.scorer.child_bounds(self.x, self.eps, self.Wp.expand(2 * B, -1), self.bp.expand(2 * B),
+                                                           [rep(t) for t in parents.lb], [rep(t) for t in parents.ub],
+                                                           dec[:, 0], dec[:, 1], choice)
+        # ReLUs the ancestors fixed stay fixed (their bounds say so already); this child's own split is in `masks` too, because
+        # its bound is exactly 0 on the fixed side (conv_kwinter_gen.py:572: relu_mask[decision] = choice)
+        mask = torch.cat(masks, dim=1)
+        new_dec, ok = self._decide(lbs, ubs, mask)
+        lower = lbs[L + 1].reshape(-1)
+        keep = ok & (lower < self.decision_bound)
+        children = DomainBatch(lower.contiguous(), rep(parents.upper_bound).contiguous(), lbs, ubs, mask, new_dec)
+        added = self.queue.add(children, keep=keep)
+        glb = self.queue.global_lb if len(self.queue) else float('nan')
+        return StepStats(B, 2 * B, int(second.sum()), added, glb)
+
+    # ---- helpers ----
+    @staticmethod
+    def _bab_mask(l: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
+        """conv_kwinter_gen.py:696-713: passing 1, blocked 0, ambiguous -1."""
+        one, zero = torch.ones_like(l, dtype=torch.int8), torch.zeros_like(l, dtype=torch.int8)
+        return torch.where((l >= 0) & (u >= 0), one, torch.where((l <= 0) & (u <= 0), zero, -one))
+
+    def _decide(self, lbs, ubs, mask):
+        """GNN decision of every domain (graph_score.py:21-56 batched): [n, 2] int32 (layer, index), and which domains have
+        an undecided ReLU at all."""
+        n = int(mask.shape[0])
+        L = self.net.L
+        z = self._zeros.get(n)
+        if z is None:
+            z = [torch.zeros(n, s, 3, device=self.dev) for s in self.sizes[1:L + 1]]
+            self._zeros = {n: z}
+        ex = lambda t: t.expand(n, -1).contiguous()
+        fr = Frontier(net=self.net, lb=lbs, ub=ubs, dual=z, prim_pre=[ex(t) for t in self.prim_pre], prim_post=[ex(t) for t in self.prim_post],
+                      prim_out=self.prim_out.expand(n).contiguous(), primal_input=ex(self.x), Wp=ex(self.Wp), bp=self.bp.expand(n).contiguous(),
+                      mask=(mask == -1).float())
+        _, idx, _ = self.model.score_frontier(fr, return_scores=False)
+        ok = idx >= 0
+        flat = idx.clamp(min=0).long()
+        lay = torch.bucketize(flat, self.offsets[1:], right=True)
+        dec = torch.stack([lay, flat - self.offsets[lay]], dim=1).to(torch.int32)
+        return dec, ok

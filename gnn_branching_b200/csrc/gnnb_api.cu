@@ -48,6 +48,8 @@ struct gnnb_ctx {
     size_t train_ws_cap = 0;
     float* kw_ws = nullptr;         // column buffers of gnnb_kw_bounds (grow-only)
     size_t kw_ws_cap = 0;
+    int32_t* kw_iscratch = nullptr; // per-domain flags of gnnb_child_bounds (grow-only)
+    int kw_iscratch_cap = 0;
     // verified network
     bool have_net = false;
     float* d_net = nullptr;
@@ -593,6 +595,7 @@ void gnnb_destroy(gnnb_ctx* ctx) {
     if (ctx->d_train) cudaFree(ctx->d_train);
     if (ctx->train_ws) cudaFree(ctx->train_ws);
     if (ctx->kw_ws) cudaFree(ctx->kw_ws);
+    if (ctx->kw_iscratch) cudaFree(ctx->kw_iscratch);
     if (ctx->d_net) cudaFree(ctx->d_net);
     if (ctx->d_maps) cudaFree(ctx->d_maps);
     if (ctx->d_layers) cudaFree(ctx->d_layers);
@@ -1254,6 +1257,32 @@ int gnnb_kw_bounds(gnnb_ctx* ctx, int32_t B, const float* x, float eps, const fl
     std::string err;
     const int rc = kw_bounds(ctx->layers, ctx->n, B, x, eps, wp, bp, provided_lb, provided_ub, out_lb, out_ub, &ctx->kw_ws, &ctx->kw_ws_cap,
                              (cudaStream_t)stream, &ctx->launches, &err);
+    if (rc != GNNB_OK) return fail(ctx, rc, err);
+    return GNNB_OK;
+}
+
+int gnnb_child_bounds(gnnb_ctx* ctx, int32_t B, const float* x, float eps, const float* wp, const float* bp, const float* const* parent_lb,
+                      const float* const* parent_ub, const int32_t* dec_layer, const int32_t* dec_index, const int32_t* choice,
+                      float* const* out_lb, float* const* out_ub, int8_t* const* out_mask, int32_t* second_pass, void* stream) {
+    if (!ctx || !x || !wp || !bp || !parent_lb || !parent_ub || !dec_layer || !dec_index || !choice || !out_lb || !out_ub)
+        return fail(ctx, GNNB_ERR_INVALID, "null argument");
+    if (!ctx->have_net) return fail(ctx, GNNB_ERR_STATE, "gnnb_set_network must be called first");
+    if (B < 1) return fail(ctx, GNNB_ERR_INVALID, "need at least one domain");
+    const int L = (int)ctx->layers.size();
+    for (int k = 0; k <= L + 1; ++k)
+        if (!out_lb[k] || !out_ub[k] || !parent_lb[k] || !parent_ub[k]) return fail(ctx, GNNB_ERR_INVALID, "null bounds array");
+    if (out_mask)
+        for (int k = 0; k < L; ++k) if (!out_mask[k]) return fail(ctx, GNNB_ERR_INVALID, "null mask array");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ctx->kw_iscratch_cap < B) {
+        if (ctx->kw_iscratch) { CU(cudaStreamSynchronize(st)); cudaFree(ctx->kw_iscratch); ctx->kw_iscratch = nullptr; ctx->kw_iscratch_cap = 0; }
+        CU(cudaMalloc(&ctx->kw_iscratch, (3 * (size_t)B + 1) * sizeof(int32_t)));
+        ctx->kw_iscratch_cap = B;
+    }
+    std::string err;
+    const int rc = child_bounds(ctx->layers, ctx->n, B, x, eps, wp, bp, parent_lb, parent_ub, dec_layer, dec_index, choice, out_lb, out_ub, out_mask,
+                                second_pass, ctx->kw_iscratch, &ctx->kw_ws, &ctx->kw_ws_cap, st, &ctx->launches, &err);
     if (rc != GNNB_OK) return fail(ctx, rc, err);
     return GNNB_OK;
 }

@@ -1,9 +1,10 @@
 // Batched KW (Wong & Kolter) intermediate bounds on the GPU — the bound producer in front of the scoring path
-// (SURVEY §8f rank 3).  NOT VALIDATED ON A GPU YET: written after the GPU budget of round 1 was spent; its parity tests run
-// in their own process and are marked xfail until they have passed once.  Nothing on the scoring path calls it.
+// (SURVEY §8f rank 3): gnnb_kw_bounds (the bounds of init_kw_bounds) and gnnb_child_bounds (the bounds part of
+// update_the_model: KW pass from the parent's bounds with one ReLU fixed, interval pass, second KW pass where needed).
 //
 // Reference: DualNetwork.__init__ of the vendored convex_adversarial (dual_network.py:15-101, dual_layers.py:207-312,
-// dual_inputs.py:24-70) as called from init_kw_bounds (plnn/dual_network_linear_approximation.py:205-288).  The reference
+// dual_inputs.py:24-70) as called from init_kw_bounds / update_kw_bounds (plnn/dual_network_linear_approximation.py:205-451)
+// and KWConvGen.update_the_model (plnn/conv_kwinter_gen.py:558-660).  The reference
 // pushes x, the n0 x n0 identity, the biases and one scaled unit vector per ambiguous ReLU FORWARD through the layers; the
 // number of columns depends on the domain.  Here the same numbers are computed by the transposed recursion, whose column
 // count is fixed (one column per output neuron), so B domains x 64-column groups batch into the existing propagation
@@ -16,7 +17,8 @@
 // with d_j = [zl_j >= 0] + I_j zu_j / (zu_j - zl_j), I_j = [zl_j < 0 < zu_j] from the (already final) bounds of layer j, then
 // intersected with the provided bounds of the parent domain (dual_network.py:85-86).  A_j^T is prop_backward without the
 // tap-count normalisation (gnnb_prop.cu), 64 columns riding in the 64 "embedding channels" of a [pairs, n, 64] tensor,
-// pair = (domain, column group).
+// pair = (domain, column group).  A pass may run on a subset of the domains (dom_list) and may leave the first hidden
+// layers of a domain untouched (keep_upto: update_kw_bounds keeps the layers up to the split).
 #include <string>
 #include <vector>
 
@@ -26,6 +28,7 @@ namespace gnnb {
 namespace {
 
 constexpr int KW_COLS = P;          // columns per pair = the channel width of the propagation kernels
+constexpr int KW_MAX_LAYERS = 30;   // hidden layers a child-bounds call can handle (pointer tables passed by value)
 
 // s_k of a column group: buf[pair][node][c] = (node == g * 64 + c)
 __global__ void k_kw_onehot(float* __restrict__ buf, int n, int G, int64_t p0, int64_t total4) {
@@ -42,13 +45,15 @@ __global__ void k_kw_onehot(float* __restrict__ buf, int n, int G, int64_t p0, i
 }
 
 // t_L of the property output: column 0 = Wp[b, :], the other columns 0 (one pair per domain)
-__global__ void k_kw_wp_col(float* __restrict__ buf, const float* __restrict__ wp, int nL, int64_t b0, int64_t total4) {
+__global__ void k_kw_wp_col(float* __restrict__ buf, const float* __restrict__ wp, int nL, int64_t b0, int64_t total4,
+                            const int32_t* __restrict__ dom_list) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
     const int c4 = (int)(i & 15);
     const int64_t row = i >> 4;                      // pair_local * nL + node
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c4 == 0) v.x = wp[(b0 + row / nL) * nL + row % nL];
+    const int64_t bl = b0 + row / nL, b = dom_list ? dom_list[bl] : bl;
+    if (c4 == 0) v.x = wp[b * nL + row % nL];
     reinterpret_cast<float4*>(buf)[i] = v;
 }
 
@@ -56,9 +61,10 @@ struct KwAcc { float *cx, *l1, *bias, *low, *up; };      // [pairs][64] each
 
 // t_j -> s_j = d_j * t_j in place, and the three sums over the nodes of layer j.  One block per pair, thread = (part, column).
 __global__ void __launch_bounds__(256) k_kw_reduce_layer(float* __restrict__ t, const float* __restrict__ zl, const float* __restrict__ zu,
-                                                         const float* __restrict__ bias_node, int n, int G, int64_t p0, KwAcc acc) {
+                                                         const float* __restrict__ bias_node, int n, int G, int64_t p0, KwAcc acc,
+                                                         const int32_t* __restrict__ dom_list) {
     __shared__ float red[3][4][KW_COLS];
-    const int64_t pl = blockIdx.x, b = (p0 + pl) / G;
+    const int64_t pl = blockIdx.x, bl = (p0 + pl) / G, b = dom_list ? dom_list[bl] : bl;
     const int c = threadIdx.x & 63, part = threadIdx.x >> 6;
     float sb = 0.f, sl = 0.f, su = 0.f;
     for (int i = part; i < n; i += 4) {
@@ -84,9 +90,9 @@ __global__ void __launch_bounds__(256) k_kw_reduce_layer(float* __restrict__ t, 
 
 // t_0 . x and |t_0|_1
 __global__ void __launch_bounds__(256) k_kw_reduce_input(const float* __restrict__ t, const float* __restrict__ x, int n0, int G, int64_t p0,
-                                                         KwAcc acc) {
+                                                         KwAcc acc, const int32_t* __restrict__ dom_list) {
     __shared__ float red[2][4][KW_COLS];
-    const int64_t pl = blockIdx.x, b = (p0 + pl) / G;
+    const int64_t pl = blockIdx.x, bl = (p0 + pl) / G, b = dom_list ? dom_list[bl] : bl;
     const int c = threadIdx.x & 63, part = threadIdx.x >> 6;
     float sx = 0.f, s1 = 0.f;
     for (int i = part; i < n0; i += 4) {
@@ -104,15 +110,18 @@ __global__ void __launch_bounds__(256) k_kw_reduce_input(const float* __restrict
 }
 
 // bounds of the group's columns, intersected with the provided ones; own_bias: bias of the layer per node (hidden layers) or
-// the property bias per domain (ncols == 1)
+// the property bias per domain (ncols == 1); layer: 1-based index of the layer, left untouched for domains with
+// keep_upto[b] >= layer
 __global__ void k_kw_finish(KwAcc acc, int ncols, int G, int64_t p0, int64_t npairs, float eps, const float* __restrict__ bias_node,
-                            const float* __restrict__ bp, const float* __restrict__ prov_lb, const float* __restrict__ prov_ub,
-                            float* __restrict__ out_lb, float* __restrict__ out_ub) {
+                            const float* __restrict__ bp, const float* prov_lb, const float* prov_ub,      // may alias out_lb / out_ub
+                            float* out_lb, float* out_ub, const int32_t* __restrict__ dom_list,
+                            const int32_t* __restrict__ keep_upto, int layer) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npairs * KW_COLS) return;
-    const int64_t pl = i / KW_COLS, p = p0 + pl, b = p / G;
+    const int64_t pl = i / KW_COLS, p = p0 + pl, bl = p / G, b = dom_list ? dom_list[bl] : bl;
     const int o = (int)(p % G) * KW_COLS + (int)(i % KW_COLS);
     if (o >= ncols) return;
+    if (keep_upto && keep_upto[b] >= layer) return;
     const float own = bias_node ? bias_node[o] : bp[b];
     const float centre = acc.cx[i] + (acc.bias[i] + own);
     float zl = centre - eps * acc.l1[i] + acc.low[i];
@@ -133,19 +142,145 @@ __global__ void k_kw_input_box(const float* __restrict__ x, float eps, int64_t t
 
 unsigned blocks_of(int64_t n, int per) { return (unsigned)((n + per - 1) / per < 1 ? 1 : (n + per - 1) / per); }
 
+// ---- child domains (update_the_model) -----------------------------------------------------------------------------------
+// the split of update_kw_bounds (plnn/dual_network_linear_approximation.py:313-319): u = 0 (choice 0) or l = 0 (choice 1) at
+// the decided ReLU; keep_upto[b] = 1-based index of the decided layer (its bounds and those in front of it are final)
+struct BoundPtrs { float* lb[KW_MAX_LAYERS + 2]; float* ub[KW_MAX_LAYERS + 2]; int n[KW_MAX_LAYERS + 2]; };
+__global__ void k_child_split(BoundPtrs o, int L, int B, const int32_t* __restrict__ dec_layer, const int32_t* __restrict__ dec_index,
+                              const int32_t* __restrict__ choice, int32_t* __restrict__ keep_upto, int32_t* __restrict__ changed) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int lay = dec_layer[b], idx = dec_index[b];
+    changed[b] = 0;
+    if (lay < 0 || lay >= L || idx < 0 || idx >= o.n[lay + 1]) { keep_upto[b] = L; return; }      // no valid decision: nothing behind it to refresh
+    keep_upto[b] = lay + 1;
+    if (choice[b] == 0) o.ub[lay + 1][(int64_t)b * o.n[lay + 1] + idx] = 0.f;
+    else o.lb[lay + 1][(int64_t)b * o.n[lay + 1] + idx] = 0.f;
+}
+
+// Does an interval bound that beats the current one call for the second KW pass?  The reference repeats the pass on ANY strict
+// improvement (:630-641), which includes last-bit differences between two evaluations of the same sum: root bounds are
+// themselves KW bounds intersected with interval bounds, so wherever the interval bound was the tighter one at the root the
+// child's interval bound is the same number up to summation order.  The tighter bound is always taken; the pass is repeated
+// only for gains above rounding (1e-6 relative), whose effect on later layers is above rounding too.
+__device__ __forceinline__ bool interval_gain_counts(float better, float current) {
+    return fabsf(better - current) > 1e-6f * fmaxf(1.0f, fabsf(current));
+}
+
+// interval bounds of one layer from the post-ReLU box of the layer in front of it, intersected with the current bounds
+// (plnn/conv_kwinter_gen.py:594-641: W+ l + W- u + b / W+ u + W- l + b); only for domains whose split lies in front of the
+// layer; changed[b] is raised when a HIDDEN layer's bound moved (:652: only then the KW pass is repeated)
+__global__ void __launch_bounds__(256) k_interval_conv(LayerDev Ld, const float* __restrict__ lb_in, const float* __restrict__ ub_in,
+                                                       float* __restrict__ lb, float* __restrict__ ub, int B, int layer,
+                                                       const int32_t* __restrict__ keep_upto, int32_t* __restrict__ changed) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * Ld.n_out) return;
+    const int b = (int)(i / Ld.n_out), node = (int)(i % Ld.n_out);
+    if (keep_upto[b] >= layer) return;
+    const int hw = Ld.h_out * Ld.w_out, co = node / hw, y = (node % hw) / Ld.w_out, x = node % Ld.w_out;
+    const float* li = lb_in + (int64_t)b * Ld.n_in;
+    const float* ui = ub_in + (int64_t)b * Ld.n_in;
+    float lo = Ld.bias_node[node], hi = lo;
+    for (int ci = 0; ci < Ld.c_in; ++ci)
+        for (int ky = 0; ky < Ld.ksize; ++ky) {
+            const int yy = y * Ld.stride + ky - Ld.pad;
+            if (yy < 0 || yy >= Ld.h_in) continue;
+            for (int kx = 0; kx < Ld.ksize; ++kx) {
+                const int xx = x * Ld.stride + kx - Ld.pad;
+                if (xx < 0 || xx >= Ld.w_in) continue;
+                const float w = Ld.weight[((co * Ld.c_in + ci) * Ld.ksize + ky) * Ld.ksize + kx];
+                const int at = (ci * Ld.h_in + yy) * Ld.w_in + xx;
+                const float l = fmaxf(li[at], 0.f), u = fmaxf(ui[at], 0.f);
+                lo = fmaf(w, w > 0.f ? l : u, lo);
+                hi = fmaf(w, w > 0.f ? u : l, hi);
+            }
+        }
+    bool ch = false;
+    if (lo > lb[i]) { ch |= interval_gain_counts(lo, lb[i]); lb[i] = lo; }
+    if (hi < ub[i]) { ch |= interval_gain_counts(hi, ub[i]); ub[i] = hi; }
+    if (ch) changed[b] = 1;
+}
+
+// linear layer (and, with per-domain weights wp / bias bp, the property output): one warp per (domain, output)
+__global__ void __launch_bounds__(256) k_interval_linear(const float* __restrict__ W, const float* __restrict__ bias, int64_t w_dom_stride,
+                                                         int n_in, int n_out, const float* __restrict__ lb_in, const float* __restrict__ ub_in,
+                                                         float* __restrict__ lb, float* __restrict__ ub, int B, int layer, bool hidden,
+                                                         const int32_t* __restrict__ keep_upto, int32_t* __restrict__ changed) {
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= (int64_t)B * n_out) return;
+    const int b = (int)(wid / n_out), o = (int)(wid % n_out);
+    if (keep_upto[b] >= layer) return;
+    const float* w = W + (int64_t)b * w_dom_stride + (int64_t)o * n_in;
+    const float* li = lb_in + (int64_t)b * n_in;
+    const float* ui = ub_in + (int64_t)b * n_in;
+    float lo = 0.f, hi = 0.f;
+    for (int i = lane; i < n_in; i += 32) {
+        const float wv = w[i], l = fmaxf(li[i], 0.f), u = fmaxf(ui[i], 0.f);
+        lo = fmaf(wv, wv > 0.f ? l : u, lo);
+        hi = fmaf(wv, wv > 0.f ? u : l, hi);
+    }
+    for (int d = 16; d > 0; d >>= 1) { lo += __shfl_xor_sync(0xffffffffu, lo, d); hi += __shfl_xor_sync(0xffffffffu, hi, d); }
+    if (lane != 0) return;
+    const float bv = w_dom_stride ? bias[b] : bias[o];
+    lo += bv; hi += bv;
+    bool ch = false;
+    if (lo > lb[wid]) { ch |= interval_gain_counts(lo, lb[wid]); lb[wid] = lo; }
+    if (hi < ub[wid]) { ch |= interval_gain_counts(hi, ub[wid]); ub[wid] = hi; }
+    if (ch && hidden) changed[b] = 1;
+}
+
+// the domains whose hidden bounds moved, in index order (one block; B is a frontier batch, thousands at most)
+__global__ void __launch_bounds__(1024) k_collect_changed(const int32_t* __restrict__ changed, int B, int32_t* __restrict__ list, int32_t* __restrict__ count) {
+    __shared__ int32_t warp_tot[32];
+    __shared__ int32_t base;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < B; b0 += 1024) {
+        const int b = b0 + threadIdx.x;
+        const bool f = b < B && changed[b] != 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        if ((threadIdx.x & 31) == 0) warp_tot[threadIdx.x >> 5] = __popc(bal);
+        __syncthreads();
+        int before = base;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) before += warp_tot[w];
+        if (f) list[before + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u))] = b;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 32; ++w) t += warp_tot[w]; base += t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = base;
+}
+
+// ReLU phase of every hidden node from its pre-activation bounds, in the BaB convention (plnn/conv_kwinter_gen.py:696-713:
+// passing 1, blocked 0, ambiguous -1)
+__global__ void k_mask_from_bounds(const float* __restrict__ lb, const float* __restrict__ ub, int8_t* __restrict__ mask, int64_t total) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const float l = lb[i], u = ub[i];
+    mask[i] = (l >= 0.f && u >= 0.f) ? 1 : ((l <= 0.f && u <= 0.f) ? 0 : -1);
+}
+
 }  // namespace
 
-// every pointer is a device pointer.  x [B, n0]; wp [B, n_L]; bp [B]; prov_lb / prov_ub: L arrays [B, n_k] (k = 1..L) or null;
-// out_lb / out_ub: L + 2 arrays [B, n_k] (k = 0..L+1).  *ws / *ws_cap (floats): caller-kept scratch, grown when too small.
-int kw_bounds(const std::vector<LayerDev>& layers, const std::vector<int>& n, int B, const float* x, float eps, const float* wp, const float* bp,
-              const float* const* prov_lb, const float* const* prov_ub, float* const* out_lb, float* const* out_ub, float** ws,
-              size_t* ws_cap, cudaStream_t st, int64_t* launches, std::string* err) {
+// One KW pass.  Every pointer is a device pointer.  x [B, n0]; wp [B, n_L]; bp [B]; prov_lb / prov_ub: L + 1 arrays [B, n_k]
+// (k = 1..L+1, the last one — the property output — may be null) or null; out_lb / out_ub: L + 2 arrays [B, n_k] (k = 0..L+1),
+// may alias the provided arrays.  first_layer: first layer (1-based) whose bounds are computed (layers in front of it must
+// already be in out_*; 1 also writes the input box).  dom_list / n_dom: the pass runs on these domains only (rows of the same
+// arrays), null = all B.  keep_upto [B] or null: layers <= keep_upto[b] of domain b are left as they are.
+// *ws / *ws_cap (floats): caller-kept scratch, grown when too small.
+int kw_pass(const std::vector<LayerDev>& layers, const std::vector<int>& n, int B, const float* x, float eps, const float* wp, const float* bp,
+            const float* const* prov_lb, const float* const* prov_ub, float* const* out_lb, float* const* out_ub, int first_layer,
+            const int32_t* dom_list, int n_dom, const int32_t* keep_upto, float** ws, size_t* ws_cap, cudaStream_t st, int64_t* launches,
+            std::string* err) {
     const int L = (int)layers.size();
+    const int ND = dom_list ? n_dom : B;          // domains of this pass
+    if (ND < 1) return GNNB_OK;
     int nmax = 0;
     for (int k = 0; k <= L; ++k) nmax = n[k] > nmax ? n[k] : nmax;
     int64_t max_pairs = 0;
     for (int k = 1; k <= L; ++k) {
-        const int64_t pairs = (int64_t)B * ((n[k] + KW_COLS - 1) / KW_COLS);
+        const int64_t pairs = (int64_t)ND * ((n[k] + KW_COLS - 1) / KW_COLS);
         max_pairs = pairs > max_pairs ? pairs : max_pairs;
     }
     const int64_t PMAX = max_pairs < 1024 ? (max_pairs < 1 ? 1 : max_pairs) : 1024;      // pairs per pass: two [PMAX, nmax, 64] buffers
@@ -162,13 +297,15 @@ int kw_bounds(const std::vector<LayerDev>& layers, const std::vector<int>& n, in
     float* accp = *ws + 2 * buf_elems;
     KwAcc acc{accp, accp + acc_elems, accp + 2 * acc_elems, accp + 3 * acc_elems, accp + 4 * acc_elems};
 
-    k_kw_input_box<<<blocks_of((int64_t)B * n[0], 256), 256, 0, st>>>(x, eps, (int64_t)B * n[0], out_lb[0], out_ub[0]);
-    ++*launches;
-    for (int k = 1; k <= L + 1; ++k) {
+    if (first_layer <= 1) {
+        k_kw_input_box<<<blocks_of((int64_t)B * n[0], 256), 256, 0, st>>>(x, eps, (int64_t)B * n[0], out_lb[0], out_ub[0]);
+        ++*launches;
+    }
+    for (int k = first_layer < 1 ? 1 : first_layer; k <= L + 1; ++k) {
         const bool out_layer = k == L + 1;
         const int ncols = out_layer ? 1 : n[k];
         const int G = (ncols + KW_COLS - 1) / KW_COLS;
-        const int64_t pairs = (int64_t)B * G;
+        const int64_t pairs = (int64_t)ND * G;
         for (int64_t p0 = 0; p0 < pairs; p0 += PMAX) {
             const int64_t np = (pairs - p0) < PMAX ? (pairs - p0) : PMAX;
             cudaMemsetAsync(accp, 0, 5 * acc_elems * sizeof(float), st);
@@ -180,7 +317,7 @@ int kw_bounds(const std::vector<LayerDev>& layers, const std::vector<int>& n, in
                 ++*launches;
             } else {
                 const int64_t total4 = np * n[L] * 16;
-                k_kw_wp_col<<<blocks_of(total4, 256), 256, 0, st>>>(buf[cur], wp, n[L], p0, total4);       // t_L (G = 1: pair = domain)
+                k_kw_wp_col<<<blocks_of(total4, 256), 256, 0, st>>>(buf[cur], wp, n[L], p0, total4, dom_list);   // t_L (G = 1: pair = domain)
                 ++*launches;
             }
             // walk down: buf[cur] holds s_{j+1} (or, for the output layer's first step, already t_L)
@@ -191,20 +328,97 @@ int kw_bounds(const std::vector<LayerDev>& layers, const std::vector<int>& n, in
                     cur ^= 1;
                 }
                 have_t = false;
-                k_kw_reduce_layer<<<(unsigned)np, 256, 0, st>>>(buf[cur], out_lb[j], out_ub[j], layers[j - 1].bias_node, n[j], G, p0, acc);
+                k_kw_reduce_layer<<<(unsigned)np, 256, 0, st>>>(buf[cur], out_lb[j], out_ub[j], layers[j - 1].bias_node, n[j], G, p0, acc, dom_list);
                 ++*launches;
             }
             prop_backward(layers[0], buf[cur], buf[cur ^ 1], (int)np, false, st, launches);                  // t_0 = A_1^T s_1
             cur ^= 1;
-            k_kw_reduce_input<<<(unsigned)np, 256, 0, st>>>(buf[cur], x, n[0], G, p0, acc);
+            k_kw_reduce_input<<<(unsigned)np, 256, 0, st>>>(buf[cur], x, n[0], G, p0, acc, dom_list);
             k_kw_finish<<<blocks_of(np * KW_COLS, 256), 256, 0, st>>>(acc, ncols, G, p0, np, eps, out_layer ? nullptr : layers[k - 1].bias_node, bp,
-                                                                      (!out_layer && prov_lb) ? prov_lb[k - 1] : nullptr,
-                                                                      (!out_layer && prov_ub) ? prov_ub[k - 1] : nullptr, out_lb[k], out_ub[k]);
+                                                                      prov_lb ? prov_lb[k - 1] : nullptr, prov_ub ? prov_ub[k - 1] : nullptr,
+                                                                      out_lb[k], out_ub[k], dom_list, keep_upto, k);
             *launches += 2;
         }
     }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { *err = std::string("KW bounds: ") + cudaGetErrorString(e); return GNNB_ERR_CUDA; }
+    return GNNB_OK;
+}
+
+// init_kw_bounds for B domains: all layers, optional provided bounds of the hidden layers (L arrays)
+int kw_bounds(const std::vector<LayerDev>& layers, const std::vector<int>& n, int B, const float* x, float eps, const float* wp, const float* bp,
+              const float* const* prov_lb, const float* const* prov_ub, float* const* out_lb, float* const* out_ub, float** ws,
+              size_t* ws_cap, cudaStream_t st, int64_t* launches, std::string* err) {
+    const int L = (int)layers.size();
+    const float* pl[KW_MAX_LAYERS + 1];
+    const float* pu[KW_MAX_LAYERS + 1];
+    for (int k = 0; k <= L; ++k) { pl[k] = (prov_lb && k < L) ? prov_lb[k] : nullptr; pu[k] = (prov_ub && k < L) ? prov_ub[k] : nullptr; }
+    return kw_pass(layers, n, B, x, eps, wp, bp, prov_lb ? pl : nullptr, prov_ub ? pu : nullptr, out_lb, out_ub, 1, nullptr, 0, nullptr, ws, ws_cap,
+                   st, launches, err);
+}
+
+// Bounds part of update_the_model (plnn/conv_kwinter_gen.py:558-660) for B children at once.  parent_lb / parent_ub, out_lb /
+// out_ub: L + 2 arrays [B, n_k] (k = 0..L+1); dec_layer (0-based hidden layer) / dec_index / choice: [B]; out_mask: L arrays
+// [B, n_k] int8 or null; second_pass: [B] int32 or null (1 where the interval bounds tightened a hidden layer and the KW pass
+// was repeated).  iscratch: 3 B + 1 int32 of caller-kept device scratch.  Synchronises `st` once (the number of domains that
+// need the second pass).
+int child_bounds(const std::vector<LayerDev>& layers, const std::vector<int>& n, int B, const float* x, float eps, const float* wp, const float* bp,
+                 const float* const* parent_lb, const float* const* parent_ub, const int32_t* dec_layer, const int32_t* dec_index,
+                 const int32_t* choice, float* const* out_lb, float* const* out_ub, int8_t* const* out_mask, int32_t* second_pass,
+                 int32_t* iscratch, float** ws, size_t* ws_cap, cudaStream_t st, int64_t* launches, std::string* err) {
+    const int L = (int)layers.size();
+    if (L > KW_MAX_LAYERS) { *err = "child bounds: too many layers"; return GNNB_ERR_UNSUPPORTED; }
+    int32_t* keep = iscratch;
+    int32_t* changed = iscratch + B;
+    int32_t* list = iscratch + 2 * (size_t)B;
+    int32_t* count = iscratch + 3 * (size_t)B;
+    BoundPtrs o;
+    for (int k = 0; k <= L + 1; ++k) {
+        o.lb[k] = out_lb[k]; o.ub[k] = out_ub[k]; o.n[k] = n[k];
+        if (out_lb[k] != parent_lb[k]) cudaMemcpyAsync(out_lb[k], parent_lb[k], (size_t)B * n[k] * sizeof(float), cudaMemcpyDeviceToDevice, st);
+        if (out_ub[k] != parent_ub[k]) cudaMemcpyAsync(out_ub[k], parent_ub[k], (size_t)B * n[k] * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    }
+    k_child_split<<<blocks_of(B, 256), 256, 0, st>>>(o, L, B, dec_layer, dec_index, choice, keep, changed);
+    ++*launches;
+    // first KW pass: the children's own (parent + split) bounds are the provided ones; layer 1 depends on no ReLU and never moves
+    const float* pl[KW_MAX_LAYERS + 1];
+    const float* pu[KW_MAX_LAYERS + 1];
+    for (int k = 1; k <= L + 1; ++k) { pl[k - 1] = out_lb[k]; pu[k - 1] = out_ub[k]; }
+    int rc = kw_pass(layers, n, B, x, eps, wp, bp, pl, pu, out_lb, out_ub, 2, nullptr, 0, keep, ws, ws_cap, st, launches, err);
+    if (rc != GNNB_OK) return rc;
+    // interval pass, layer by layer behind the split
+    for (int k = 2; k <= L + 1; ++k) {
+        if (k <= L) {
+            const LayerDev& Ld = layers[k - 1];
+            if (Ld.kind == GNNB_LAYER_CONV)
+                k_interval_conv<<<blocks_of((int64_t)B * n[k], 256), 256, 0, st>>>(Ld, out_lb[k - 1], out_ub[k - 1], out_lb[k], out_ub[k], B, k, keep, changed);
+            else
+                k_interval_linear<<<blocks_of((int64_t)B * n[k] * 32, 256), 256, 0, st>>>(Ld.weight, Ld.bias_node, 0, n[k - 1], n[k], out_lb[k - 1], out_ub[k - 1],
+                                                                                           out_lb[k], out_ub[k], B, k, true, keep, changed);
+        } else {
+            k_interval_linear<<<blocks_of((int64_t)B * 32, 256), 256, 0, st>>>(wp, bp, n[L], n[L], 1, out_lb[L], out_ub[L], out_lb[k], out_ub[k], B, k, false,
+                                                                                keep, changed);
+        }
+        ++*launches;
+    }
+    k_collect_changed<<<1, 1024, 0, st>>>(changed, B, list, count);
+    ++*launches;
+    int32_t h_count = 0;
+    cudaMemcpyAsync(&h_count, count, sizeof h_count, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) { *err = std::string("child bounds: ") + cudaGetErrorString(cudaGetLastError()); return GNNB_ERR_CUDA; }
+    if (h_count > 0) {
+        rc = kw_pass(layers, n, B, x, eps, wp, bp, pl, pu, out_lb, out_ub, 2, list, h_count, keep, ws, ws_cap, st, launches, err);
+        if (rc != GNNB_OK) return rc;
+    }
+    if (second_pass) cudaMemcpyAsync(second_pass, changed, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
+    if (out_mask)
+        for (int k = 1; k <= L; ++k) {
+            const int64_t total = (int64_t)B * n[k];
+            k_mask_from_bounds<<<blocks_of(total, 256), 256, 0, st>>>(out_lb[k], out_ub[k], out_mask[k - 1], total);
+            ++*launches;
+        }
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { *err = std::string("child bounds: ") + cudaGetErrorString(e); return GNNB_ERR_CUDA; }
     return GNNB_OK;
 }
 

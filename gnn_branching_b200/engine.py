@@ -317,7 +317,7 @@ class Scorer:
     def adam_reset(self):
         self._ok(self.lib.gnnb_adam_reset(self.h))
 
-    # ---- batched KW bounds (NOT validated on a GPU yet: gnnb_kw.cu) ----
+    # ---- batched KW bounds (gnnb_kw.cu) ----
     def kw_bounds(self, x: torch.Tensor, eps: float, Wp: torch.Tensor, bp: torch.Tensor, provided_lb=None, provided_ub=None):
         """KW intermediate bounds of B domains (init_kw_bounds of the reference, batched).  ``x`` [B, n0] (or [n0], shared),
         ``Wp`` [B, n_L], ``bp`` [B]; ``provided_lb`` / ``provided_ub``: L tensors [B, n_k] (the parent's pre-ReLU bounds with
@@ -351,6 +351,46 @@ class Scorer:
             torch.cuda.synchronize()
         del keep, k3, k4
         return lbs, ubs
+
+    def child_bounds(self, x: torch.Tensor, eps: float, Wp: torch.Tensor, bp: torch.Tensor, parent_lb, parent_ub,
+                     dec_layer: torch.Tensor, dec_index: torch.Tensor, choice: torch.Tensor, with_mask: bool = True):
+        """Bounds of B child domains — the bounds part of ``KWConvGen.update_the_model`` (plnn/conv_kwinter_gen.py:558-660),
+        batched and device-resident.  ``parent_lb`` / ``parent_ub``: L + 2 tensors [B, n_k] (input box, pre-ReLU bounds,
+        property output); ``dec_layer`` (0-based hidden layer), ``dec_index``, ``choice`` (0 blocked / 1 passing): [B] ints.
+        Returns (lbs, ubs, masks, second_pass): L + 2 CUDA tensors [B, n_k] each, L int8 masks in the BaB convention
+        (or None), [B] int32 flags of the domains that took the second KW pass."""
+        if self.net is None:
+            raise RuntimeError('set_network first')
+        net, L = self.net, self.net.L
+        dev = torch.device('cuda', self.device)
+        sizes = [net.n0] + net.hidden_sizes + [1]
+        Wp = Wp.to(dev, torch.float32).reshape(-1, sizes[L]).contiguous()
+        B = int(Wp.shape[0])
+        x = x.to(dev, torch.float32).reshape(-1, net.n0)
+        x = (x.expand(B, net.n0) if x.shape[0] == 1 else x).contiguous()
+        bp = bp.to(dev, torch.float32).reshape(B).contiguous()
+        pl = [self._as_f32(t.to(dev).reshape(B, -1), (B, sizes[k])) for k, t in enumerate(parent_lb)]
+        pu = [self._as_f32(t.to(dev).reshape(B, -1), (B, sizes[k])) for k, t in enumerate(parent_ub)]
+        ints = [t.to(dev, torch.int32).reshape(B).contiguous() for t in (dec_layer, dec_index, choice)]
+        lbs = [torch.empty(B, n, dtype=torch.float32, device=dev) for n in sizes]
+        ubs = [torch.empty(B, n, dtype=torch.float32, device=dev) for n in sizes]
+        masks = [torch.empty(B, n, dtype=torch.int8, device=dev) for n in sizes[1:L + 1]] if with_mask else None
+        second = torch.empty(B, dtype=torch.int32, device=dev)
+        plb, k1 = _lib.fptr_array(pl)
+        pub, k2 = _lib.fptr_array(pu)
+        olb, k3 = _lib.fptr_array(lbs)
+        oub, k4 = _lib.fptr_array(ubs)
+        ip = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_int32))
+        mptr = None
+        if with_mask:
+            marr = (C.POINTER(C.c_int8) * L)(*[C.cast(m.data_ptr(), C.POINTER(C.c_int8)) for m in masks])
+            mptr = C.cast(marr, C.POINTER(C.POINTER(C.c_int8)))
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            self._ok(self.lib.gnnb_child_bounds(self.h, B, _lib.fptr(x), float(eps), _lib.fptr(Wp), _lib.fptr(bp), plb, pub,
+                                                ip(ints[0]), ip(ints[1]), ip(ints[2]), olb, oub, mptr, ip(second), C.c_void_p(stream)))
+        del k1, k2, k3, k4
+        return lbs, ubs, masks, second
 
     def check(self) -> None:
         """Synchronise and raise if a NaN appeared in an embedding (the reference drops into pdb there)."""

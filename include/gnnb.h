@@ -226,7 +226,6 @@ int gnnb_queue_prune(gnnb_queue* q, float threshold, void* stream);
 int gnnb_queue_stats(gnnb_queue* q, int64_t* size, float* global_lb, void* stream);
 
 /* ---- batched KW intermediate bounds (the bound producer in front of the scoring path) ---------------------------------
- * NOT VALIDATED ON A GPU YET (written after the GPU budget of round 1 was spent).
  * Replaces DualNetwork(net, x, eps, bounded_input=False[, provided_zl, provided_zu]) of the reference's vendored
  * convex_adversarial as called by init_kw_bounds (plnn/dual_network_linear_approximation.py:205-288) for B domains at once:
  * pre-ReLU bounds of the L hidden layers (DualReLU.zl / zu), each intersected with the provided bounds when given (the
@@ -236,6 +235,22 @@ int gnnb_queue_stats(gnnb_queue* q, int64_t* size, float* global_lb, void* strea
 int gnnb_kw_bounds(gnnb_ctx* ctx, int32_t B, const float* x, float eps, const float* wp, const float* bp,
                    const float* const* provided_lb, const float* const* provided_ub, float* const* out_lb,
                    float* const* out_ub, void* stream);
+
+/* Bounds of B child domains: the bounds part of KWConvGen.update_the_model(relu_mask, pre_lb_all, pre_ub_all, decision,
+ * choice) (plnn/conv_kwinter_gen.py:558-660), i.e. update_kw_bounds (plnn/dual_network_linear_approximation.py:296-439) with
+ * the decided ReLU fixed — layers up to the split keep the parent's bounds, later layers get KW bounds intersected with the
+ * parent's —, interval bounds of the layers behind the split intersected with them (:594-651), and a second KW pass for the
+ * domains where the interval bounds tightened a hidden layer (:652-656).  The LP that follows in the reference (Gurobi) is
+ * out of scope; the property-output bounds returned here are the KW / interval ones.
+ * Every pointer is a DEVICE pointer.  parent_lb / parent_ub, out_lb / out_ub: L + 2 arrays [B, n_k], k = 0..L+1 (input box,
+ * pre-ReLU bounds, property output; out may alias parent); dec_layer (0-based hidden layer) / dec_index / choice (0: blocked,
+ * u = 0; 1: passing, l = 0): [B] int32; out_mask: L arrays [B, n_k] int8 in the BaB convention (1 passing, 0 blocked,
+ * -1 ambiguous; :696-713) or NULL; second_pass: [B] int32 (1 where the second KW pass ran) or NULL.
+ * Synchronises `stream` once (the number of domains that need the second pass). */
+int gnnb_child_bounds(gnnb_ctx* ctx, int32_t B, const float* x, float eps, const float* wp, const float* bp,
+                      const float* const* parent_lb, const float* const* parent_ub, const int32_t* dec_layer,
+                      const int32_t* dec_index, const int32_t* choice, float* const* out_lb, float* const* out_ub,
+                      int8_t* const* out_mask, int32_t* second_pass, void* stream);
 
 /* Synchronise `stream` and report sticky device-side errors of earlier gnnb_score calls
  * (GNNB_ERR_NAN with the NaN count in *nan_count, may be NULL).  Clears the flag. */

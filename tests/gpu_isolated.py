@@ -101,6 +101,119 @@ def check_kw_bounds(arch):
             assert err(l, rl) <= 5e-5 and err(u, ru) <= 5e-5, ('child', c, k, err(l, rl), err(u, ru))
 
 
+def check_child_bounds(arch):
+    """gnnb_child_bounds against the UNMODIFIED reference's update_the_model (bounds part; tests/golden/child_bounds.npz): every
+    golden child in ONE batched call, each from its own parent's bounds (root, child or grandchild), different split layers in
+    the same batch; bounds within 5e-5 of the largest bound, the BaB mask from the rule of conv_kwinter_gen.py:696-713, the
+    second-KW-pass flags equal to the reference's.  Then the same batch replicated to 64 domains (several column passes)."""
+    import numpy as np
+    from golden_io import GOLDEN
+    from gnn_branching_b200 import Scorer
+    z = dict(np.load(os.path.join(GOLDEN, 'child_bounds.npz')))
+    net, _, _, wp, bp = load_root(arch)
+    x = torch.from_numpy(np.load(os.path.join(GOLDEN, 'nets.npz'))[f'{arch}_x'].copy()).reshape(1, -1)
+    L, nc = net.L, int(z[f'{arch}_ncases'])
+    sc = Scorer(0)
+    sc.set_network(net, key=net.key)
+
+    def get(c):
+        lbs = [x[0] - 0.145] + [torch.from_numpy(z[f'{arch}_c{c}_lb{k}'].copy()) for k in range(1, L + 2)]
+        ubs = [x[0] + 0.145] + [torch.from_numpy(z[f'{arch}_c{c}_ub{k}'].copy()) for k in range(1, L + 2)]
+        return lbs, ubs
+
+    def err(a, b):
+        return float((a.reshape(-1).cpu() - b.reshape(-1)).abs().max()) / max(1.0, float(b.abs().max()))
+
+    # largest interval gain on a hidden layer after the first KW pass, per case (CPU, oracle pieces)
+    from oracle import kw_bounds_oracle as KW
+    gains = {}
+    for c in range(1, nc):
+        lay, idx, choice = z[f'{arch}_c{c}_decision'].tolist()
+        lbs, ubs = get(int(z[f'{arch}_c{c}_parent']))
+        (ubs if choice == 0 else lbs)[lay + 1][idx] = 0
+        lbs, ubs = KW._kw_pass(net, x[0], 0.145, wp, bp, lbs, ubs, keep_upto=lay + 1)
+        g = 0.0
+        for k in range(lay + 2, L + 1):
+            lo, hi = KW.interval_layer(net.affine[k - 1], lbs[k - 1].clamp(min=0), ubs[k - 1].clamp(min=0))
+            g = max(g, float(((lo - lbs[k]) / lbs[k].abs().clamp(min=1)).max()), float(((ubs[k] - hi) / ubs[k].abs().clamp(min=1)).max()))
+            lbs[k], ubs[k] = torch.max(lbs[k], lo), torch.min(ubs[k], hi)
+        gains[c] = g
+    for rep in (1, 64 // (nc - 1) + 1):
+        cases = list(range(1, nc)) * rep
+        B = len(cases)
+        parents = [get(int(z[f'{arch}_c{c}_parent'])) for c in cases]
+        plb = [torch.stack([p[0][k] for p in parents]) for k in range(L + 2)]
+        pub = [torch.stack([p[1][k] for p in parents]) for k in range(L + 2)]
+        dec = torch.tensor([z[f'{arch}_c{c}_decision'].tolist() for c in cases], dtype=torch.int32)
+        gl, gu, masks, second = sc.child_bounds(x, 0.145, wp.reshape(1, -1).repeat(B, 1), torch.full((B,), float(bp)), plb, pub,
+                                                dec[:, 0], dec[:, 1], dec[:, 2])
+        torch.cuda.synchronize()
+        worst = 0.0
+        for i, c in enumerate(cases):
+            rl, ru = get(c)
+            for k in range(0, L + 2):
+                e = max(err(gl[k][i], rl[k]), err(gu[k][i], ru[k]))
+                worst = max(worst, e)
+                assert e <= 5e-5, ('child', c, k, e)
+            gain = gains[c]        # the library repeats the KW pass for interval gains above rounding only (gnnb_kw.cu)
+            if gain > 1e-5 or gain < 1e-7:
+                assert int(second[i]) == int(gain > 1e-5), ('second pass', c, int(second[i]), gain)
+            if gain > 1e-5:
+                assert int(z[f'{arch}_c{c}_interval_better']) == 1
+            for k in range(1, L + 1):
+                l, u = gl[k][i].cpu(), gu[k][i].cpu()
+                want = torch.where((l >= 0) & (u >= 0), 1, torch.where((l <= 0) & (u <= 0), 0, -1)).to(torch.int8)
+                assert torch.equal(masks[k - 1][i].cpu(), want), ('mask', c, k)
+            lay, idx, choice = z[f'{arch}_c{c}_decision'].tolist()
+            assert int(masks[lay][i][idx]) == choice, ('mask of the split node', c)
+        print(f'child_bounds {arch} B={B}: worst rel err {worst:.2e}, second passes {int(second.sum())}', flush=True)
+
+
+def check_frontier_step(arch):
+    """FrontierStep (pick -> split -> gnnb_child_bounds -> gnnb_score -> add, device-resident) against the pieces it is made
+    of: the first step's two children carry the oracle's child bounds of the root for the root's GNN decision; afterwards, over
+    several batched steps, every child's lower bound is at least its parent's, the queue holds exactly the children that were
+    kept, and its global lower bound never decreases."""
+    import numpy as np
+    from golden_io import GOLDEN
+    from gnn_branching_b200 import FrontierStep
+    from oracle import kw_bounds_oracle as KW
+    net, lbs, ubs, wp, bp = load_root(arch)
+    x = torch.from_numpy(np.load(os.path.join(GOLDEN, 'nets.npz'))[f'{arch}_x'].copy()).reshape(-1)
+    model = GraphNet(2, 64, math='tc')
+    model.load_state_dict(load_gnn('random'))
+    model = model.eval().cuda()
+    fs = FrontierStep(model, net, x, 0.145, wp, bp, capacity=4096, decision_bound=float('inf'))
+    fs.seed_root(lbs, ubs)
+    assert len(fs.queue) == 1
+    root = fs.queue.pick(1, float('inf'))
+    dec = root.decision[0].tolist()
+    fs.queue.add(root)
+    st = fs.step(8)
+    assert (st.picked, st.children, st.added) == (1, 2, 2) and len(fs.queue) == 2, st
+    kids = fs.queue.pick(2, float('inf'))
+    for i in range(2):
+        # which side is this child?  the split node's bound is 0 on the fixed side
+        side = 0 if float(kids.ub[dec[0] + 1][i, dec[1]]) == 0.0 else 1
+        ol, ou, _ = KW.child_bounds(net, x, 0.145, wp, bp, lbs, ubs, dec, side)
+        for k in range(net.L + 2):
+            e = max(float((kids.lb[k][i].cpu() - ol[k]).abs().max()), float((kids.ub[k][i].cpu() - ou[k]).abs().max())) / max(1.0, float(ou[k].abs().max()))
+            assert e <= 5e-5, ('child', i, k, e)
+        assert float(kids.lower_bound[i]) == float(kids.lb[net.L + 1][i, 0])
+        assert int(kids.mask[i, sum(net.hidden_sizes[:dec[0]]) + dec[1]]) == side
+    assert {0 if float(kids.ub[dec[0] + 1][i, dec[1]]) == 0.0 else 1 for i in range(2)} == {0, 1}
+    fs.queue.add(kids)
+    glb, size = fs.queue.global_lb, 2
+    for B in (2, 4, 8, 16):
+        st = fs.step(B)
+        size += st.added - st.picked
+        assert st.children == 2 * st.picked and st.added <= st.children and len(fs.queue) == size, (st, size)
+        assert st.global_lb >= glb - 1e-6, (st.global_lb, glb)      # children are never looser than their parents
+        glb = st.global_lb
+    print(f'frontier_step {arch}: queue {len(fs.queue)} domains, global lb {glb:.4f}', flush=True)
+
+
 if __name__ == '__main__':
-    {'gather_prefetch': check_gather_prefetch, 'kw_bounds': check_kw_bounds, 'fused': check_fused}[sys.argv[1]](sys.argv[2])
+    {'gather_prefetch': check_gather_prefetch, 'frontier_step': check_frontier_step, 'kw_bounds': check_kw_bounds, 'fused': check_fused,
+     'child_bounds': check_child_bounds}[sys.argv[1]](sys.argv[2])
     print('ok')

@@ -639,3 +639,13 @@ def test_gather_prefetch_variant_is_bit_identical(arch):
 @pytest.mark.parametrize('arch', ARCHS)
 def test_kw_bounds_match_reference(arch):
     _run_isolated('kw_bounds', arch, timeout=180)
+
+
+@pytest.mark.parametrize('arch', ARCHS)
+def test_child_bounds_match_reference_update_the_model(arch):
+    _run_isolated('child_bounds', arch, timeout=240)
+
+
+@pytest.mark.parametrize('arch', ['base', 'deep'])
+def test_frontier_step_is_made_of_its_pieces(arch):
+    _run_isolated('frontier_step', arch, timeout=240)

@@ -150,7 +150,7 @@ def test_queue_oracle_matches_reference_traces():
         assert left == z[f't{t}_left'].tolist()
 
 
-# ---- KW intermediate bounds (oracle and pins only, no CUDA implementation yet) ---------------------
+# ---- KW intermediate bounds -----------------------------------------------------------------------
 def _kw_err(a, b):
     return float((a.reshape(-1) - b.reshape(-1)).abs().max()) / max(1.0, float(b.abs().max()))
 
@@ -191,3 +191,43 @@ def test_kw_bounds_oracle_matches_reference_children(arch):
             assert _kw_err(got_l[k], rl) <= 2e-5 and _kw_err(got_u[k], ru) <= 2e-5, (c, k)
         fixed_l, fixed_u = got_l[lay + 1][idx], got_u[lay + 1][idx]
         assert (float(fixed_u) == 0.0) if choice == 0 else (float(fixed_l) == 0.0)
+
+
+def _child_cases(arch):
+    """(net, x, wp, bp, get(case) -> (lbs, ubs), z, ncases) of tests/golden/child_bounds.npz."""
+    import numpy as np
+    from golden_io import GOLDEN, load_root
+    z = dict(np.load(os.path.join(GOLDEN, 'child_bounds.npz')))
+    net, _, _, wp, bp = load_root(arch)
+    x = torch.from_numpy(np.load(os.path.join(GOLDEN, 'nets.npz'))[f'{arch}_x'].copy()).reshape(-1)
+
+    def get(c):
+        lbs = [x - 0.145] + [torch.from_numpy(z[f'{arch}_c{c}_lb{k}'].copy()) for k in range(1, net.L + 2)]
+        ubs = [x + 0.145] + [torch.from_numpy(z[f'{arch}_c{c}_ub{k}'].copy()) for k in range(1, net.L + 2)]
+        return lbs, ubs
+    return net, x, wp, bp, get, z, int(z[f'{arch}_ncases'])
+
+
+@pytest.mark.parametrize('arch', ARCHS)
+def test_child_bounds_oracle_matches_reference_update_the_model(arch):
+    """oracle child_bounds / root_bounds against the bounds computed by the UNMODIFIED KWConvGen.build_the_model /
+    update_the_model of the reference, executed up to their first Gurobi access (tests/golden/make_golden_child.py): root and
+    chains of three splits, including the cases that take the interval-triggered second KW pass."""
+    from oracle import kw_bounds_oracle as KW
+    net, x, wp, bp, get, z, nc = _child_cases(arch)
+    rl, ru = KW.root_bounds(net, x, 0.145, wp, bp)
+    gl, gu = get(0)
+    for k in range(1, net.L + 2):
+        assert _kw_err(rl[k], gl[k]) <= 2e-5 and _kw_err(ru[k], gu[k]) <= 2e-5, ('root', k)
+    seconds = 0
+    for c in range(1, nc):
+        lay, idx, choice = z[f'{arch}_c{c}_decision'].tolist()
+        pl, pu = get(int(z[f'{arch}_c{c}_parent']))
+        cl, cu, second = KW.child_bounds(net, x, 0.145, wp, bp, pl, pu, (lay, idx), choice)
+        gl, gu = get(c)
+        assert bool(second) == bool(int(z[f'{arch}_c{c}_interval_better'])), c
+        seconds += int(second)
+        for k in range(1, net.L + 2):
+            assert _kw_err(cl[k], gl[k]) <= 2e-5 and _kw_err(cu[k], gu[k]) <= 2e-5, (c, k)
+    if arch == 'deep':
+        assert seconds >= 2
