@@ -45,6 +45,7 @@ def parse():
     ap.add_argument('--no-babsr', action='store_true')
     ap.add_argument('--no-online', action='store_true')
     ap.add_argument('--no-queue', action='store_true')
+    ap.add_argument('--no-step', action='store_true', help='skip the device-resident branch-and-bound step (pick, bound, score, add)')
     ap.add_argument('--no-secondary', action='store_true', help='skip the wide / deep x 4096 secondary objects of the default line')
     ap.add_argument('--opt', action='append', default=[], help='library option key=value (e.g. fuse=0, prop_share=40)')
     return ap.parse_args()
@@ -425,6 +426,94 @@ def measure_e2e(model, host_fronts, B, K, W, world, dev, gather):
                    'Scorer.score_winners(pinned host Frontier) + dist.gather_winner_records + read-back of all winners'}
 
 
+def measure_frontier_step(model, workload, dev, world, parents=256, steps=4):
+    """Secondary object: the device-resident branch-and-bound step (gnn_branching_b200/bab_step.py) — every rank grows its own
+    queue from the root of the same property, then `steps` steps of `parents` parents (2 x parents children: bounds part of
+    update_the_model, GNN decision, add) are timed by the wall clock around the calls, max over ranks; and gnnb_child_bounds
+    alone on one such batch.  LP values are surrogates (no Gurobi): see bab_step.py."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from golden_io import GOLDEN
+    from gnn_branching_b200 import FrontierStep
+    net, lbs, ubs, wp, bp = load_problem(workload)
+    x = torch.from_numpy(np.load(os.path.join(GOLDEN, 'nets.npz'))[f'{workload}_x'].copy()).reshape(-1)
+
+    def sync_ranks(v):          # every rank reaches every collective, whatever happened to it in between: max over ranks
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    fs, err = None, None
+    try:
+        fs = FrontierStep(model, net, x, 0.145, wp, bp, capacity=(steps + 4) * 2 * parents, decision_bound=float('inf'), device=dev.index)
+        fs.seed_root(lbs, ubs)
+        while len(fs.queue) < parents:
+            fs.step(parents)
+        fs.step(parents)                              # one warm step at the timed size
+        torch.cuda.synchronize()
+    except Exception as e:
+        err = e
+    failed = sync_ranks(0.0 if err is None else 1.0)   # doubles as the barrier in front of the timed region
+    dt, second, launches = float('inf'), 0, 0
+    if not failed:
+        try:
+            l0, t0 = fs.scorer.launches, time.perf_counter()
+            for _ in range(steps):
+                st = fs.step(parents)
+                second += st.second_pass
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            launches = fs.scorer.launches - l0
+        except Exception as e:
+            err = e
+    dt = sync_ranks(dt)
+    if err is not None or failed or dt == float('inf'):
+        raise RuntimeError(f'frontier step failed on a rank: {err!r}')
+    children = 2 * parents * steps
+    # the bound producer alone, on the children of one more batch of parents
+    par = fs.queue.pick(parents, float('inf'))
+    rep = lambda t: t.repeat_interleave(2, dim=0)
+    n2 = 2 * par.B
+    args = (fs.x, fs.eps, fs.Wp.expand(n2, -1), fs.bp.expand(n2), [rep(t) for t in par.lb], [rep(t) for t in par.ub],
+            rep(par.decision)[:, 0], rep(par.decision)[:, 1], torch.arange(n2, device=dev, dtype=torch.int32) & 1)
+    fs.scorer.child_bounds(*args)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        fs.scorer.child_bounds(*args)
+    torch.cuda.synchronize()
+    cb_ms = (time.perf_counter() - t0) / 3 * 1e3
+    # executed work of the transposed KW recursion (dense 64-column groups): per recomputed layer k >= 2 and the property output,
+    # ceil(n_k / 64) groups, each pushed through A_j^T for every layer j < k; bytes = fp32 [n, 64] column blocks read / written
+    n = [net.n0] + net.hidden_sizes
+    mac = [a.weight.numel() * (a.out_shape[1] * a.out_shape[2] if a.kind == 'conv' else 1) for a in net.affine]
+    flop = byts = 0
+    for k in list(range(2, net.L + 1)) + [net.L + 1]:
+        groups = 1 if k == net.L + 1 else -(-n[k] // 64)
+        top = net.L if k == net.L + 1 else k
+        for j in range(top, 0, -1):                   # A_j^T: layer j -> layer j - 1
+            flop += groups * 2 * 64 * mac[j - 1]
+            byts += groups * 256 * (n[j] + 3 * n[j - 1])
+    peaks = load_peaks()
+    return {'value': world * children / dt, 'unit': 'children/s', 'n_gpus': world, 'parents_per_step': parents, 'steps': steps, 'ms_per_step': dt / steps * 1e3,
+            'launches_per_step': launches // steps, 'second_kw_passes': second, 'queue_domains_at_end': len(fs.queue),
+            'api': 'FrontierStep.step: gnnb_queue_pick -> split -> gnnb_child_bounds -> gnnb_score -> gnnb_queue_add, all device-resident',
+            'host_traffic': 'three counts read back per step (picked, second-pass domains, added); no bounds, masks or scores cross PCIe',
+            'lp': 'surrogate (no Gurobi): lower bound = KW / interval bound of the property output, zero duals, primals = activations of the ball centre',
+            'child_bounds': {'value': n2 / (cb_ms * 1e-3), 'unit': 'children/s', 'ms_per_call': cb_ms, 'children': n2,
+                             'executed_gflop_per_child': flop / 1e9, 'achieved_tflops_fp32': flop * n2 / (cb_ms * 1e-3) / 1e12,
+                             'roofline': {'bound': 'hbm', 'achieved': byts * n2 / (cb_ms * 1e-3) / 1e9, 'peak': peaks['gbs'], 'unit': 'GB/s',
+                                          'frac': byts * n2 / (cb_ms * 1e-3) / 1e9 / peaks['gbs'], 'traffic': None,
+                                          'note': 'bytes of the executed schedule (fp32 [n, 64] column blocks written and re-read by every '
+                                                  'transposed-propagation and reduction launch), not compulsory bytes'},
+                             'note': 'bounds part of KWConvGen.update_the_model (plnn/conv_kwinter_gen.py:558-660) for a batch of children: exact-fp32 '
+                                     'transposed KW recursion on the SIMT propagation kernels + interval pass + masks'}}
+
+
+
 def load_peaks():
     peaks = {}
     try:
@@ -513,6 +602,15 @@ def main():
         host_fronts = [f.cpu().pin() for f in fronts]
         e2e = measure_e2e(model, host_fronts, B, K, W, world, dev, gather_winner_records)
         del host_fronts
+
+    # ---- the device-resident branch-and-bound step (every rank takes part: its own queue, its own subtree) ----
+    fstep = None
+    if not args.no_step and not args.domains and math_mode == 'tc':
+        try:
+            fstep = measure_frontier_step(model, args.workload, dev, world)
+            scorer.set_network(net, key=net.key)
+        except Exception as e:              # a secondary object must never take the headline down
+            fstep = {'error': repr(e)[:300]}
 
     if rank != 0:
         if world > 1:
@@ -686,7 +784,7 @@ def main():
                        'sharding': f'{world} ranks x {B} subdomains, winners all-gathered (8 B/subdomain)'},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cb,
             'b1_latency_ms': b1, 'wide': others.get('wide'), 'deep': others.get('deep'),
-            'babsr': babsr, 'online': online, 'queue': queue}
+            'babsr': babsr, 'online': online, 'queue': queue, 'frontier_step': fstep}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

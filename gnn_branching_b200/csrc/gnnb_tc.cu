@@ -1639,9 +1639,9 @@ void tc_fused(const GnnParams& g, const PropPlan* plan, const float* mu_in, bool
     const int ns = (int)((fz::SMEM_MAX - fz::smem_for(wbytes, staging, 0)) / fz::STAGE);
     fa.n_stages = ns > fz::NS_MAX ? fz::NS_MAX : ns;
     // layers with long K loops are bound by the propagation's issue loop, layers with short ones by the chains, whose GEMMs queue
-    // behind whatever the propagation has issued: groups of 4 K steps for the former, single steps for the latter
+    // behind whatever the propagation has issued: groups of 4 K steps for the former, pairs of steps for the latter
     // (a chain takes ~11 000 cycles per item, a K step 192 cycles of tensor time: only K loops of 48+ steps outlast the chains)
-    fa.mma_group = prop_plan_ksteps_per_tile(plan) >= 48.0 ? 4 : (prop_plan_ksteps_per_tile(plan) >= 32.0 ? 2 : 1);
+    fa.mma_group = prop_plan_ksteps_per_tile(plan) >= 48.0 ? 4 : 2;      // (2 instead of 1 for the short loops: +1 % on the base step)
     if (g_fused_tune.mma_group > 0) fa.mma_group = g_fused_tune.mma_group;
     if (fa.mma_group > fa.n_stages / 2) fa.mma_group = fa.n_stages / 2;
     const int64_t nitems = (int64_t)fa.plan.ntiles * ((fa.u.Bc + fz::PD - 1) / fz::PD);
