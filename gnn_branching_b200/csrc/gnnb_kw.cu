@@ -261,6 +261,189 @@ __global__ void k_mask_from_bounds(const float* __restrict__ lb, const float* __
     mask[i] = (l >= 0.f && u >= 0.f) ? 1 : ((l <= 0.f && u <= 0.f) ? 0 : -1);
 }
 
+
+// ---- conv layers: one column's backward cone is local -------------------------------------------------------------------
+// For a conv layer k whose predecessors are all conv layers, the column e_o of output o = (co, y, x) touches only the kernel
+// footprint of (y, x) in layer k - 1, the footprint of that in layer k - 2, ... : a window of a few hundred nodes per layer
+// instead of the whole layer (base conv2: 128 of 2 048 nodes of layer 1, 300 of 3 072 input pixels).  The dense recursion above
+// spends > 95 % of its work on zeros there.  This kernel runs the same recursion on the windows: one block per (domain,
+// position (y, x)), columns = the C_k output channels at that position (they share the cone), the window tensors
+// [element][column] in shared memory, ping-pong.  Same sums as the dense form, different summation order.
+constexpr int CONE_MAX_DEPTH = 8;
+struct ConeArgs {
+    LayerDev layer[CONE_MAX_DEPTH];      // A_1 .. A_k
+    const float* zl[CONE_MAX_DEPTH];     // bounds of layers 1 .. k - 1 (index j - 1), [B, n_j]
+    const float* zu[CONE_MAX_DEPTH];
+    int k;                               // the layer whose bounds are computed (1-based), 2 <= k <= CONE_MAX_DEPTH
+    int cols, R;                         // columns = C_k; threads = cols * R
+    int buf_elems;                       // floats per ping-pong buffer
+    const float* x;                      // [B, n0]
+    float eps;
+    float* out_lb; float* out_ub;        // [B, n_k], provided bounds on entry (intersection in place)
+    const int32_t* dom_list; const int32_t* keep_upto;
+};
+
+__global__ void __launch_bounds__(256) k_kw_cone(const __grid_constant__ ConeArgs a) {
+    extern __shared__ float cone_smem[];
+    const int k = a.k, cols = a.cols;
+    const int bl = blockIdx.y, b = a.dom_list ? a.dom_list[bl] : bl;
+    if (a.keep_upto && a.keep_upto[b] >= k) return;
+    const LayerDev& Lk = a.layer[k - 1];
+    const int y = blockIdx.x / Lk.w_out, x = blockIdx.x % Lk.w_out;
+    // windows of layers k-1 .. 0: [ylo, yhi] x [xlo, xhi], all channels
+    int ylo[CONE_MAX_DEPTH + 1], yhi[CONE_MAX_DEPTH + 1], xlo[CONE_MAX_DEPTH + 1], xhi[CONE_MAX_DEPTH + 1];
+    ylo[k] = yhi[k] = y; xlo[k] = xhi[k] = x;
+#pragma unroll
+    for (int j = CONE_MAX_DEPTH; j >= 1; --j) {
+        if (j > k) continue;
+        const LayerDev& L = a.layer[j - 1];
+        ylo[j - 1] = max(0, ylo[j] * L.stride - L.pad); yhi[j - 1] = min(L.h_in - 1, yhi[j] * L.stride - L.pad + L.ksize - 1);
+        xlo[j - 1] = max(0, xlo[j] * L.stride - L.pad); xhi[j - 1] = min(L.w_in - 1, xhi[j] * L.stride - L.pad + L.ksize - 1);
+    }
+    float* cur = cone_smem;
+    float* nxt = cone_smem + a.buf_elems;
+    const int tid = threadIdx.x, nthr = cols * a.R, col = tid % cols;
+    float acc_bias = 0.f, acc_low = 0.f, acc_up = 0.f, acc_cx = 0.f, acc_l1 = 0.f;
+    // t_{k-1} = A_k^T e_o: the kernel footprint of (y, x), column co = row co of the kernel
+    {
+        const int hj = yhi[k - 1] - ylo[k - 1] + 1, wj = xhi[k - 1] - xlo[k - 1] + 1, E = Lk.c_in * hj * wj;
+        for (int idx = tid; idx < E * cols; idx += nthr) {
+            const int e = idx / cols, ci = e / (hj * wj), wy = (e / wj) % hj, wx = e % wj;
+            const int ky = ylo[k - 1] + wy - (y * Lk.stride - Lk.pad), kx = xlo[k - 1] + wx - (x * Lk.stride - Lk.pad);
+            cur[idx] = Lk.weight[((col * Lk.c_in + ci) * Lk.ksize + ky) * Lk.ksize + kx];
+        }
+    }
+    __syncthreads();
+    for (int j = k - 1; j >= 1; --j) {
+        const LayerDev& Lj = a.layer[j - 1];          // A_j: layer j - 1 -> layer j
+        const int hj = yhi[j] - ylo[j] + 1, wj = xhi[j] - xlo[j] + 1, E = Lj.c_out * hj * wj;
+        const float* zl = a.zl[j - 1] + (int64_t)b * Lj.n_out;
+        const float* zu = a.zu[j - 1] + (int64_t)b * Lj.n_out;
+        // s_j = d_j t_j and the layer's three sums
+        for (int idx = tid; idx < E * cols; idx += nthr) {
+            const int e = idx / cols, c = e / (hj * wj), wy = (e / wj) % hj, wx = e % wj;
+            const int node = (c * Lj.h_out + ylo[j] + wy) * Lj.w_out + xlo[j] + wx;
+            const float l = zl[node], u = zu[node];
+            const bool I = (u > 0.f) && (l < 0.f);
+            float d = (l >= 0.f) ? 1.0f : 0.0f;
+            if (I) d += __fdiv_rn(u, u - l);
+            const float sv = cur[idx] * d;
+            cur[idx] = sv;
+            acc_bias = fmaf(sv, Lj.bias_node[node], acc_bias);
+            if (I) { acc_low = fmaf(l, fmaxf(-sv, 0.f), acc_low); acc_up = fmaf(l, fmaxf(sv, 0.f), acc_up); }
+        }
+        __syncthreads();
+        // t_{j-1} = A_j^T s_j on the window of layer j - 1
+        const int hi = yhi[j - 1] - ylo[j - 1] + 1, wi = xhi[j - 1] - xlo[j - 1] + 1, Ei = Lj.c_in * hi * wi;
+        for (int idx = tid; idx < Ei * cols; idx += nthr) {
+            const int e = idx / cols, ci = e / (hi * wi), yy = ylo[j - 1] + (e / wi) % hi, xx = xlo[j - 1] + e % wi;
+            float sum = 0.f;
+            for (int ky = 0; ky < Lj.ksize; ++ky) {
+                const int ty = yy + Lj.pad - ky;
+                if (ty < 0 || ty % Lj.stride != 0) continue;
+                const int oy = ty / Lj.stride;
+                if (oy < ylo[j] || oy > yhi[j]) continue;
+                for (int kx = 0; kx < Lj.ksize; ++kx) {
+                    const int tx = xx + Lj.pad - kx;
+                    if (tx < 0 || tx % Lj.stride != 0) continue;
+                    const int ox = tx / Lj.stride;
+                    if (ox < xlo[j] || ox > xhi[j]) continue;
+                    const float* w = Lj.weight + (ci * Lj.ksize + ky) * Lj.ksize + kx;
+                    const float* sp = cur + ((oy - ylo[j]) * wj + (ox - xlo[j])) * cols + col;
+                    for (int c = 0; c < Lj.c_out; ++c)
+                        sum = fmaf(w[(int64_t)c * Lj.c_in * Lj.ksize * Lj.ksize], sp[(int64_t)c * hj * wj * cols], sum);
+                }
+            }
+            nxt[idx] = sum;
+        }
+        __syncthreads();
+        float* t = cur; cur = nxt; nxt = t;
+    }
+    // t_0 . x and |t_0|_1 on the input window
+    {
+        const LayerDev& L1 = a.layer[0];
+        const int hi = yhi[0] - ylo[0] + 1, wi = xhi[0] - xlo[0] + 1, Ei = L1.c_in * hi * wi;
+        const float* xb = a.x + (int64_t)b * L1.n_in;
+        for (int idx = tid; idx < Ei * cols; idx += nthr) {
+            const int e = idx / cols, ci = e / (hi * wi), yy = ylo[0] + (e / wi) % hi, xx = xlo[0] + e % wi;
+            const float v = cur[idx];
+            acc_cx = fmaf(v, xb[(ci * L1.h_in + yy) * L1.w_in + xx], acc_cx);
+            acc_l1 += fabsf(v);
+        }
+    }
+    __syncthreads();
+    // the R partial sums of every column
+    float* red = cone_smem;                   // 5 * nthr floats <= buf_elems (checked on the host)
+    red[0 * nthr + tid] = acc_bias; red[1 * nthr + tid] = acc_low; red[2 * nthr + tid] = acc_up; red[3 * nthr + tid] = acc_cx; red[4 * nthr + tid] = acc_l1;
+    __syncthreads();
+    if (tid < cols) {
+        float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int r = 0; r < a.R; ++r)
+#pragma unroll
+            for (int q = 0; q < 5; ++q) v[q] += red[q * nthr + r * cols + tid];
+        const int node = (tid * Lk.h_out + y) * Lk.w_out + x;
+        const float centre = v[3] + (v[0] + Lk.bias_node[node]);
+        const int64_t at = (int64_t)b * Lk.n_out + node;
+        a.out_lb[at] = fmaxf(centre - a.eps * v[4] + v[1], a.out_lb[at]);
+        a.out_ub[at] = fminf(centre + a.eps * v[4] - v[2], a.out_ub[at]);
+    }
+}
+
+// bounds of conv layer k through the cone kernel; false when the layer does not qualify (a linear layer in front of it, too
+// deep, too many channels, windows too large for shared memory): the caller takes the dense path
+bool kw_cone_layer(const std::vector<LayerDev>& layers, const std::vector<int>& n, int k, int ND, const float* x, float eps,
+                   float* const* out_lb, float* const* out_ub, const int32_t* dom_list, const int32_t* keep_upto, cudaStream_t st,
+                   int64_t* launches) {
+    if (k < 2 || k > CONE_MAX_DEPTH) return false;
+    for (int j = 1; j <= k; ++j) if (layers[j - 1].kind != GNNB_LAYER_CONV) return false;
+    const LayerDev& Lk = layers[k - 1];
+    const int cols = Lk.c_out;
+    if (cols > 256) return false;
+    const int R = 256 / cols < 1 ? 1 : 256 / cols;
+    // largest (unclipped) window per layer
+    int h = 1, w = 1;
+    size_t max_elems = 0;
+    for (int j = k; j >= 1; --j) {
+        const LayerDev& L = layers[j - 1];
+        h = (h - 1) * L.stride + L.ksize; w = (w - 1) * L.stride + L.ksize;
+        h = h < L.h_in ? h : L.h_in; w = w < L.w_in ? w : L.w_in;
+        const size_t e = (size_t)L.c_in * h * w;
+        max_elems = e > max_elems ? e : max_elems;
+    }
+    size_t buf = max_elems * cols;
+    if (buf < (size_t)5 * cols * R) buf = (size_t)5 * cols * R;
+    const size_t smem = 2 * buf * sizeof(float);
+    if (smem > 200 * 1024) return false;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k_kw_cone, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return false;
+        attr_set = true;
+    }
+    ConeArgs a{};
+    for (int j = 1; j <= k; ++j) a.layer[j - 1] = layers[j - 1];
+    for (int j = 1; j < k; ++j) { a.zl[j - 1] = out_lb[j]; a.zu[j - 1] = out_ub[j]; }
+    a.k = k; a.cols = cols; a.R = R; a.buf_elems = (int)buf; a.x = x; a.eps = eps;
+    a.out_lb = out_lb[k]; a.out_ub = out_ub[k]; a.dom_list = dom_list; a.keep_upto = keep_upto;
+    for (int d0 = 0; d0 < ND; d0 += 65535) {
+        const int nd = ND - d0 < 65535 ? ND - d0 : 65535;
+        ConeArgs b = a;
+        // domains beyond the first 65 535: shift the per-domain views (dom_list is indexed by the local domain; without it the
+        // arrays themselves are)
+        if (d0) {
+            if (dom_list) b.dom_list = dom_list + d0;
+            else {
+                b.x = x + (size_t)d0 * n[0];
+                for (int j = 1; j < k; ++j) { b.zl[j - 1] = out_lb[j] + (size_t)d0 * n[j]; b.zu[j - 1] = out_ub[j] + (size_t)d0 * n[j]; }
+                b.out_lb = out_lb[k] + (size_t)d0 * n[k]; b.out_ub = out_ub[k] + (size_t)d0 * n[k];
+                if (keep_upto) b.keep_upto = keep_upto + d0;
+            }
+        }
+        k_kw_cone<<<dim3((unsigned)(Lk.h_out * Lk.w_out), (unsigned)nd), cols * R, smem, st>>>(b);
+        ++*launches;
+    }
+    return true;
+}
+
 }  // namespace
 
 // One KW pass.  Every pointer is a device pointer.  x [B, n0]; wp [B, n_L]; bp [B]; prov_lb / prov_ub: L + 1 arrays [B, n_k]
@@ -275,6 +458,7 @@ int kw_pass(const std::vector<LayerDev>& layers, const std::vector<int>& n, int 
             std::string* err) {
     const int L = (int)layers.size();
     const int ND = dom_list ? n_dom : B;          // domains of this pass
+    static const bool use_cone = !(getenv("GNNB_KW_DENSE") && atoi(getenv("GNNB_KW_DENSE")) != 0);      // debugging: dense recursion everywhere
     if (ND < 1) return GNNB_OK;
     int nmax = 0;
     for (int k = 0; k <= L; ++k) nmax = n[k] > nmax ? n[k] : nmax;
@@ -306,6 +490,11 @@ int kw_pass(const std::vector<LayerDev>& layers, const std::vector<int>& n, int 
         const int ncols = out_layer ? 1 : n[k];
         const int G = (ncols + KW_COLS - 1) / KW_COLS;
         const int64_t pairs = (int64_t)ND * G;
+        // conv layers behind conv layers: the windowed recursion.  It intersects with the bounds already in out_*, so it needs them
+        // there: true for every caller that provides bounds (they alias out_*); without provided bounds the dense path runs.
+        if (use_cone && !out_layer && prov_lb && prov_ub && prov_lb[k - 1] == out_lb[k] && prov_ub[k - 1] == out_ub[k] &&
+            kw_cone_layer(layers, n, k, ND, x, eps, out_lb, out_ub, dom_list, keep_upto, st, launches))
+            continue;
         for (int64_t p0 = 0; p0 < pairs; p0 += PMAX) {
             const int64_t np = (pairs - p0) < PMAX ? (pairs - p0) : PMAX;
             cudaMemsetAsync(accp, 0, 5 * acc_elems * sizeof(float), st);

@@ -169,6 +169,56 @@ def check_child_bounds(arch):
         print(f'child_bounds {arch} B={B}: worst rel err {worst:.2e}, second passes {int(second.sum())}', flush=True)
 
 
+def check_child_bounds_shapes(case):
+    """gnnb_child_bounds on networks that are not the CIFAR ones (odd spatial sizes and channel counts, 5x5 / 3x3 / 4x4 kernels,
+    stride 1 and 2, windows clipped at every border, three conv layers in a row) against the oracle, domain by domain."""
+    from torch import nn
+    from gnn_branching_b200 import Flatten, Scorer, netspec_from_modules
+    from gnn_branching_b200.frontier import interval_root_bounds
+    from oracle import kw_bounds_oracle as KW
+    if case == 'odd_shapes':
+        layers = [nn.Conv2d(2, 5, 3, stride=1, padding=1), nn.ReLU(), nn.Conv2d(5, 6, 3, stride=2, padding=1), nn.ReLU(),
+                  Flatten(), nn.Linear(6 * 5 * 4, 37), nn.ReLU()]
+        shape = (2, 9, 7)
+    else:
+        layers = [nn.Conv2d(1, 4, 5, stride=1, padding=2), nn.ReLU(), nn.Conv2d(4, 4, 3, stride=1, padding=1), nn.ReLU(),
+                  nn.Conv2d(4, 3, 4, stride=2, padding=1), nn.ReLU(), Flatten(), nn.Linear(3 * 6 * 6, 150), nn.ReLU(),
+                  nn.Linear(150, 9), nn.ReLU()]
+        shape = (1, 12, 12)
+    g = torch.Generator().manual_seed(5)
+    for m in layers:
+        for q in m.parameters():
+            q.data = torch.randn(q.shape, generator=g) * (0.3 if q.dim() > 1 else 0.1)
+    net = netspec_from_modules(layers, shape, name='custom')
+    x = torch.randn(shape, generator=g).reshape(-1)
+    wp, bp, eps = torch.randn(net.hidden_sizes[-1], generator=g) * 0.3, 0.1, 0.05
+    lbs, ubs = KW.root_bounds(net, x, eps, wp, bp)
+    L = net.L
+    decs = []
+    for lay in range(L):
+        amb = ((lbs[lay + 1] < 0) & (ubs[lay + 1] > 0)).nonzero().view(-1)
+        for choice in (0, 1):
+            if amb.numel():
+                decs.append((lay, int(amb[int(torch.randint(0, amb.numel(), (1,), generator=g))]), choice))
+    B = len(decs)
+    assert B >= 4
+    sc = Scorer(0)
+    sc.set_network(net, key=net.key)
+    dec = torch.tensor(decs, dtype=torch.int32)
+    gl, gu, masks, second = sc.child_bounds(x.reshape(1, -1), eps, wp.reshape(1, -1).repeat(B, 1), torch.full((B,), bp),
+                                            [t.reshape(1, -1).repeat(B, 1) for t in lbs], [t.reshape(1, -1).repeat(B, 1) for t in ubs],
+                                            dec[:, 0], dec[:, 1], dec[:, 2])
+    torch.cuda.synchronize()
+    worst = 0.0
+    for i, (lay, idx, choice) in enumerate(decs):
+        ol, ou, _ = KW.child_bounds(net, x, eps, wp, bp, lbs, ubs, (lay, idx), choice)
+        for k in range(L + 2):
+            e = max(float((gl[k][i].cpu() - ol[k]).abs().max()), float((gu[k][i].cpu() - ou[k]).abs().max())) / max(1.0, float(ou[k].abs().max()))
+            worst = max(worst, e)
+            assert e <= 5e-5, (case, i, k, e)
+    print(f'child_bounds {case}: {B} children, worst rel err {worst:.2e}', flush=True)
+
+
 def check_frontier_step(arch):
     """FrontierStep (pick -> split -> gnnb_child_bounds -> gnnb_score -> add, device-resident) against the pieces it is made
     of: the first step's two children carry the oracle's child bounds of the root for the root's GNN decision; afterwards, over
@@ -215,5 +265,5 @@ def check_frontier_step(arch):
 
 if __name__ == '__main__':
     {'gather_prefetch': check_gather_prefetch, 'frontier_step': check_frontier_step, 'kw_bounds': check_kw_bounds, 'fused': check_fused,
-     'child_bounds': check_child_bounds}[sys.argv[1]](sys.argv[2])
+     'child_bounds': check_child_bounds, 'child_bounds_shapes': check_child_bounds_shapes}[sys.argv[1]](sys.argv[2])
     print('ok')

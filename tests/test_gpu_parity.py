@@ -649,3 +649,8 @@ def test_child_bounds_match_reference_update_the_model(arch):
 @pytest.mark.parametrize('arch', ['base', 'deep'])
 def test_frontier_step_is_made_of_its_pieces(arch):
     _run_isolated('frontier_step', arch, timeout=240)
+
+
+@pytest.mark.parametrize('case', ['odd_shapes', 'deep_narrow'])
+def test_child_bounds_other_network_shapes(case):
+    _run_isolated('child_bounds_shapes', case, timeout=240)
