@@ -639,9 +639,12 @@ __device__ long long g_e3_trace[4];          // e3 sub-phases of the tracing thr
 #else
 #define E3TR(i) do {} while (0)
 #endif
-template <bool TO_A>
+struct NoOp { __device__ __forceinline__ void operator()() const {} };
+// `between` runs after the accumulator columns have been read and the values staged, before the stores are issued (!TO_A only):
+// k_tc_fused starts its next tile there (the tile's first GEMM then runs under the fence, barrier and store issue below)
+template <bool TO_A, class Between = NoOp>
 __device__ __forceinline__ bool epilogue_to_mu_pair(const WG& c, int h, int pair_bar, uint32_t dcol, const float* __restrict__ bias_s,
-                                                    float rowscale, bool valid, unsigned char* img, uint32_t stage) {
+                                                    float rowscale, bool valid, unsigned char* img, uint32_t stage, Between between = Between()) {
     bool bad = false;
 #ifdef GNNB_TRACE
     long long e3t_ = clock64();
@@ -689,6 +692,7 @@ __device__ __forceinline__ bool epilogue_to_mu_pair(const WG& c, int h, int pair
         }
     }
     E3TR(2);
+    if (!TO_A) between();
     if (img != nullptr) {
         fence_proxy_async();             // the staging stores are generic-proxy writes, the bulk stores read through the async proxy
         named_bar(pair_bar, 64);
@@ -984,37 +988,29 @@ __device__ __forceinline__ void fused_body(const FusedArgs& fa) {
 #else
 #define CTR(i) do {} while (0)
 #endif
-        for (; cur.valid(); cur.next(), cur1.next(), cur2.next(), ++it) {
-            const uint32_t buf = it & 1u, bufph = (it >> 1) & 1u;
-            const uint32_t acc_full = smem_u32(&tl->acc_full[buf]), acc_empty = smem_u32(&tl->acc_empty[buf]);
-            const int dom = cur.pair * PD + j;
-            const int node = node_n;
-            const float l = l_n, u = u_n;
-            const int slot0 = slot0_n;
-            fetch_bounds(cur1, node_nn);
-            node_nn = fetch_node(cur2);
+        // The chain of a tile is software-pipelined by one stage: its first section — wait for the item's accumulator, nb -> A operand
+        // in place, first GEMM issued — runs inside the LAST epilogue of the tile before it, right after that epilogue has read its
+        // accumulator columns, so the GEMM executes under the store of the previous tile and the bookkeeping between two tiles
+        // (~1 500 cycles of a ~10 800-cycle chain otherwise spent with nothing of this pair in the tensor pipe).
+        // start_item: item `it_` at cursor `cu`, row inputs node_ / l_ / u_ (input-layer variant only).  Returns false when this
+        // pair has no subdomain in the item (odd batch).
+        auto start_item = [&](const ItemCursor& cu, uint32_t it_, int node_, float l_, float u_) -> bool {
+            const uint32_t buf = it_ & 1u, bufph = (it_ >> 1) & 1u;
+            const int dom_ = cu.pair * PD + j;
 #ifdef GNNB_TRACE
-            c0_ = clock64();
+            const long long w0_ = clock64();
 #endif
-            mbar_wait(acc_full, bufph);                           // the item's nb = A(mu) is complete in tensor memory
+            mbar_wait(smem_u32(&tl->acc_full[buf]), bufph);       // the item's nb = A(mu) is complete in tensor memory
 #ifdef GNNB_TRACE
-            c_wait += clock64() - c0_;
+            c_wait += clock64() - w0_;
 #endif
             tc_fence_after();
-            if (dom >= a.Bc) {                                    // odd batch: the last pair has one subdomain
-                if (h == 0 && c.t == 0) mbar_arrive(acc_empty);
-                continue;
+            if (dom_ >= a.Bc) {                                   // odd batch: the last pair has one subdomain
+                if (h == 0 && c.t == 0) mbar_arrive(smem_u32(&tl->acc_empty[buf]));
+                return false;
             }
-            const int64_t tile = (int64_t)dom * ntiles + cur.tile;
+            const int64_t tile = (int64_t)dom_ * ntiles + cu.tile;
             c.acol = ACC_COL + buf * ACC_WIN + 64u * (uint32_t)j;
-#ifdef GNNB_TRACE
-            c0_ = clock64(); ++c_tiles;
-#endif
-            const Ratio q = compute_ratio(l, u);
-            const float gate = (q.r0 != 0.0f) ? 1.0f : 0.0f;
-            const bool amb = (q.amb != 0.0f) && node >= 0;
-            const unsigned bal = __ballot_sync(0xffffffffu, amb);
-            if ((c.t & 31) == 0) tl->wcnt[j * 2 + h][c.t >> 5] = __popc(bal);
             // nb: accumulator columns -> fp16 hi / lo A operand, in place (K step qd = channels [16 qd, 16 qd + 16))
             {
                 unsigned char* dbg = fa.nb_dbg ? reinterpret_cast<unsigned char*>(fa.nb_dbg) + tile * (int64_t)ABUF + (uint32_t)c.t * 16u : nullptr;
@@ -1036,8 +1032,6 @@ __device__ __forceinline__ void fused_body(const FusedArgs& fa) {
                     }
                 }
             }
-            CTR(0);
-            unsigned char* img = a.mu_out ? reinterpret_cast<unsigned char*>(a.mu_out) + tile * (int64_t)ABUF : nullptr;
             if (inp) {
                 // ---- input-layer update (graph_conv.py:380-385): a second A operand relu(inp_b([l0, u0])) of this half's 32 channels
                 //      (K < 64 first layer on CUDA cores) goes to D[64:128); D[0:64) = nb Wn^T + that Wi^T, one commit ----
@@ -1051,7 +1045,7 @@ __device__ __forceinline__ void fused_body(const FusedArgs& fa) {
                         lds16(w0 + qd * 16, wl);
                         lds16(w0 + P + qd * 16, wu);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) o[i] = relu_nan(fmaf(node >= 0 ? l : 0.f, wl[i], fmaf(node >= 0 ? u : 0.f, wu[i], o[i])));
+                        for (int i = 0; i < 16; ++i) o[i] = relu_nan(fmaf(node_ >= 0 ? l_ : 0.f, wl[i], fmaf(node_ >= 0 ? u_ : 0.f, wu[i], o[i])));
                         uint32_t w[16];
                         split16(o, w);
                         tmem_st16(c.tmem + D + 64 + 16 * qd, w);
@@ -1069,6 +1063,38 @@ __device__ __forceinline__ void fused_body(const FusedArgs& fa) {
                     }
                     __syncwarp();
                 }
+            } else {
+                gemm_ts_start(c, W + UPD_W3, W + UPD_W3 + 2 * WPLANE, 128, D);      // D[0:128) = nb [W3a; W3b]^T
+            }
+            return true;
+        };
+        bool have = cur.valid() ? start_item(cur, 0, node_n, l_n, u_n) : false;
+        for (; cur.valid(); cur.next(), cur1.next(), cur2.next(), ++it) {
+            const uint32_t buf = it & 1u;
+            const uint32_t acc_empty = smem_u32(&tl->acc_empty[buf]);
+            const int dom = cur.pair * PD + j;
+            const int node = node_n;
+            const float l = l_n, u = u_n;
+            const int slot0 = slot0_n;
+            fetch_bounds(cur1, node_nn);               // from here on node_n / l_n / u_n / slot0_n belong to item it + 1
+            node_nn = fetch_node(cur2);
+            // the next tile's first section, run from inside this tile's last epilogue (or directly, when this pair has no tile here)
+            auto advance = [&]() { have = cur1.valid() ? start_item(cur1, it + 1, node_n, l_n, u_n) : false; };
+            if (!have) {
+                advance();
+                continue;
+            }
+            const int64_t tile = (int64_t)dom * ntiles + cur.tile;
+#ifdef GNNB_TRACE
+            c0_ = clock64(); ++c_tiles;
+#endif
+            const Ratio q = compute_ratio(l, u);
+            const float gate = (q.r0 != 0.0f) ? 1.0f : 0.0f;
+            const bool amb = (q.amb != 0.0f) && node >= 0;
+            const unsigned bal = __ballot_sync(0xffffffffu, amb);
+            if ((c.t & 31) == 0) tl->wcnt[j * 2 + h][c.t >> 5] = __popc(bal);
+            unsigned char* img = a.mu_out ? reinterpret_cast<unsigned char*>(a.mu_out) + tile * (int64_t)ABUF : nullptr;
+            if (inp) {
                 gemm_finish(c);
                 if (h == 0 && c.t == 0) mbar_arrive(acc_empty);    // nb has been read: the propagation may refill this accumulator
                 c.acol = D + 64;                                  // the remaining A operands live in the consumed half of the window
@@ -1091,28 +1117,17 @@ __device__ __forceinline__ void fused_body(const FusedArgs& fa) {
                 gemm_ts_start(c, W + INF_B22, W + INF_B22 + WPLANE, 64, D);
                 gemm_finish(c);
                 CTR(3);
-                bad |= epilogue_to_mu_pair<false>(c, h, pair_bar, D, tl->bias[1], 1.0f, node >= 0, img, stage);
+                bad |= epilogue_to_mu_pair<false>(c, h, pair_bar, D, tl->bias[1], 1.0f, node >= 0, img, stage, advance);
                 CTR(6);
                 continue;
             }
-            // D[0:128) = nb [W3a; W3b]^T
-            gemm_ts_start(c, W + UPD_W3, W + UPD_W3 + 2 * WPLANE, 128, D);
-            gemm_finish(c);
+            gemm_finish(c);                                       // D[0:128) = nb [W3a; W3b]^T (issued by start_item)
             // nb has been read: the propagation may refill this accumulator while the chain goes on.  The remaining A operands
             // (h3, g, and the embeddings of the score head) live in D[64:128), each 16-column piece written by the thread that has
             // just consumed it in the first epilogue
             if (h == 0 && c.t == 0) mbar_arrive(acc_empty);
             c.acol = D + 64;
             CTR(1);
-            // slot of this row's relax' = first slot of the tile + number of ambiguous rows before it
-            int slot = slot0 + __popc(bal & ((1u << (c.t & 31)) - 1u));
-#pragma unroll
-            for (int w = 0; w < 3; ++w) slot += (w < (c.t >> 5)) ? tl->wcnt[j * 2 + h][w] : 0;
-            const float* rt = rlx + (size_t)(slot >> 7) * (TILE * P) + (size_t)(slot & (TILE - 1)) * 4 + (size_t)(8 * h) * (TILE * 4);
-            if (amb) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(rt + (size_t)i * (TILE * 4)));
-            }
             // h3 = relu(r0 * D[0:64) + r1 * D[64:128) + b3) -> A (graph_conv.py:169-170 / 331-336)
 #pragma unroll
             for (int qq = 0; qq < 2; ++qq) {
@@ -1133,6 +1148,12 @@ __device__ __forceinline__ void fused_body(const FusedArgs& fa) {
             CTR(2);
             // D[0:64) = h3 Wc^T; meanwhile fetch this row's relax'
             gemm_ts_start(c, W + UPD_WC, W + UPD_WC + WPLANE, 64, D);
+            // slot of this row's relax' = first slot of the tile + number of ambiguous rows before it (the warps' counts were written
+            // at the top of the iteration; the barrier of the GEMM above orders them)
+            int slot = slot0 + __popc(bal & ((1u << (c.t & 31)) - 1u));
+#pragma unroll
+            for (int w = 0; w < 3; ++w) slot += (w < (c.t >> 5)) ? tl->wcnt[j * 2 + h][w] : 0;
+            const float* rt = rlx + (size_t)(slot >> 7) * (TILE * P) + (size_t)(slot & (TILE - 1)) * 4 + (size_t)(8 * h) * (TILE * 4);
             float4 rx[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) rx[i] = amb ? ldg4_now(rt + (size_t)i * (TILE * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1165,7 +1186,7 @@ __device__ __forceinline__ void fused_body(const FusedArgs& fa) {
             gemm_finish(c);
             CTR(5);
             if (!with_score) {
-                bad |= epilogue_to_mu_pair<false>(c, h, pair_bar, D, tl->bias[2], gate, node >= 0, img, stage);
+                bad |= epilogue_to_mu_pair<false>(c, h, pair_bar, D, tl->bias[2], gate, node >= 0, img, stage, advance);
             } else {      // score head on the new embeddings (graph_conv.py:448-449)
                 bad |= epilogue_to_mu_pair<true>(c, h, pair_bar, D, tl->bias[2], gate, node >= 0, img, stage);
                 gemm_ts_start(c, W + UPD_FN, W + UPD_FN + WPLANE, 64, D);
@@ -1196,6 +1217,7 @@ __device__ __forceinline__ void fused_body(const FusedArgs& fa) {
                     sc += __uint_as_float(tmem_ld1_sync(c.tmem + D + 64));
                     if (node >= 0) scores[(int64_t)dom * a.score_stride + a.score_off + node] = fmaf(sc, AINV, bscore);
                 }
+                advance();                                        // (its GEMM is issued behind a barrier of the pair: both halves have read D)
             }
             CTR(6);
         }
