@@ -322,10 +322,17 @@ def kernel_rooflines(net, fr, prof, n_domains, T, peak_tf, peak_gbs, p=64):
                           'algorithmic_bytes_per_subdomain': byts[gname], 'algorithmic_flop_per_subdomain': flop[gname]}
     top = max(classes, key=lambda k: classes[k]['ms'])
     c = classes[top]
-    return {'bound': 'hbm', 'kernel': names[top], 'kernel_class': top, 'achieved': c['hbm_gbs'], 'peak': peak_gbs, 'unit': 'GB/s',
-            'frac': c['hbm_frac'], 'launches': c['launches'], 'avg_launch_ms': c['avg_launch_ms'],
-            'share_of_step': c['share_of_step'],
-            'tensor': {'achieved': c['tflops'], 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': c['tensor_frac']},
+    # which roof is the nearer one: every product costs three fp16 MMA passes (fp32 accuracy), so the tensor pipe is 3 x as busy as
+    # the algorithmic FLOPs say; the fused layer kernel sits closer to that roof than to the HBM one (ncu: tensor pipe 58 % active,
+    # DRAM 42 %), the stand-alone kernels of the two-launch path closer to HBM
+    hbm = {'achieved': c['hbm_gbs'], 'peak': peak_gbs, 'unit': 'GB/s', 'frac': c['hbm_frac'],
+           'algorithmic_bytes_per_subdomain': c['algorithmic_bytes_per_subdomain']}
+    tensor = {'achieved': c['tflops'], 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': c['tensor_frac'], 'frac_of_3_pass_ceiling': 3 * c['tensor_frac'],
+              'algorithmic_flop_per_subdomain': c['algorithmic_flop_per_subdomain']}
+    head = dict(tensor, bound='tensor') if 3 * c['tensor_frac'] >= c['hbm_frac'] else dict(hbm, bound='hbm')
+    return {'bound': head['bound'], 'kernel': names[top], 'kernel_class': top, 'achieved': head['achieved'], 'peak': head['peak'],
+            'unit': head['unit'], 'frac': head['frac'], 'launches': c['launches'], 'avg_launch_ms': c['avg_launch_ms'],
+            'share_of_step': c['share_of_step'], 'tensor': tensor, 'hbm': hbm,
             'classes': classes, 'ambiguous_fraction': [round(a, 3) for a in amb],
             'kernel_ms': {k: round(v['ms'], 3) for k, v in prof.items()},
             '_bytes_per_subdomain': sum(byts.values())}
@@ -486,12 +493,27 @@ def measure_frontier_step(model, workload, dev, world, parents=256, steps=4):
         fs.scorer.child_bounds(*args)
     torch.cuda.synchronize()
     cb_ms = (time.perf_counter() - t0) / 3 * 1e3
-    # executed work of the transposed KW recursion (dense 64-column groups): per recomputed layer k >= 2 and the property output,
-    # ceil(n_k / 64) groups, each pushed through A_j^T for every layer j < k; bytes = fp32 [n, 64] column blocks read / written
+    # executed work of the bound producer.  Conv layers behind conv layers take the windowed recursion (k_kw_cone: per position
+    # and output channel, the footprint windows of the layers in front); the other layers and the property output the dense
+    # recursion: ceil(n_k / 64) groups of 64 columns, each pushed through A_j^T for every layer j < k as fp32 [n, 64] column blocks
     n = [net.n0] + net.hidden_sizes
     mac = [a.weight.numel() * (a.out_shape[1] * a.out_shape[2] if a.kind == 'conv' else 1) for a in net.affine]
     flop = byts = 0
     for k in list(range(2, net.L + 1)) + [net.L + 1]:
+        cone = k <= net.L and all(a.kind == 'conv' for a in net.affine[:k])
+        if cone:
+            a_k = net.affine[k - 1]
+            h = w = 1
+            for j in range(k, 0, -1):                 # window of layer j - 1 under one position of layer k (unclipped)
+                a_j = net.affine[j - 1]
+                ks = a_j.weight.shape[2]
+                taps = -(-ks // a_j.stride) ** 2 if j < k else 0
+                if j < k:                             # A_j^T on the window: every element of window j - 1 x valid taps x C_j x columns
+                    hh, ww = (h - 1) * a_j.stride + ks, (w - 1) * a_j.stride + ks
+                    flop += a_k.out_shape[1] * a_k.out_shape[2] * 2 * a_k.out_shape[0] * a_j.in_shape[0] * hh * ww * taps * a_j.out_shape[0]
+                h, w = (h - 1) * a_j.stride + ks, (w - 1) * a_j.stride + ks
+            byts += 2 * 4 * n[k] + sum(8 * n[j] for j in range(1, k))          # bounds read / written once (windows stay in shared memory)
+            continue
         groups = 1 if k == net.L + 1 else -(-n[k] // 64)
         top = net.L if k == net.L + 1 else k
         for j in range(top, 0, -1):                   # A_j^T: layer j -> layer j - 1
@@ -507,10 +529,12 @@ def measure_frontier_step(model, workload, dev, world, parents=256, steps=4):
                              'executed_gflop_per_child': flop / 1e9, 'achieved_tflops_fp32': flop * n2 / (cb_ms * 1e-3) / 1e12,
                              'roofline': {'bound': 'hbm', 'achieved': byts * n2 / (cb_ms * 1e-3) / 1e9, 'peak': peaks['gbs'], 'unit': 'GB/s',
                                           'frac': byts * n2 / (cb_ms * 1e-3) / 1e9 / peaks['gbs'], 'traffic': None,
-                                          'note': 'bytes of the executed schedule (fp32 [n, 64] column blocks written and re-read by every '
-                                                  'transposed-propagation and reduction launch), not compulsory bytes'},
+                                          'note': 'bytes of the executed schedule (dense layers: fp32 [n, 64] column blocks written and re-read by every '
+                                                  'transposed-propagation and reduction launch), not compulsory bytes; the windowed conv-layer kernel is '
+                                                  'issue-bound (ncu: 79 % of issue slots, no DRAM traffic to speak of, profiles/r03g_ncu_kw_cone.txt)'},
                              'note': 'bounds part of KWConvGen.update_the_model (plnn/conv_kwinter_gen.py:558-660) for a batch of children: exact-fp32 '
-                                     'transposed KW recursion on the SIMT propagation kernels + interval pass + masks'}}
+                                     'KW recursion (windowed kernel for conv layers, transposed propagation on the SIMT kernels for the rest) + '
+                                     'interval pass + masks'}}
 
 
 

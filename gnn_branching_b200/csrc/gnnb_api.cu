@@ -32,7 +32,7 @@ struct gnnb_ctx {
     int chunk = 0;
     int snapshot = 0;
     int fuse = 1;                   // propagation + node update of a layer in one launch, nb handed over in tensor memory (k_tc_fused); 0 = two launches
-    int gather_prefetch = 0;        // propagation kernel variant that fetches the gather indices one chunk ahead (not validated on a GPU yet)
+    int gather_prefetch = 0;        // stand-alone propagation kernel variants that fetch the gather indices one chunk ahead (bit-identical, off)
     // GNN parameters
     bool have_gnn = false;
     float* d_gnn = nullptr;

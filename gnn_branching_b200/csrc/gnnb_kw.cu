@@ -290,16 +290,18 @@ __global__ void __launch_bounds__(256) k_kw_cone(const __grid_constant__ ConeArg
     if (a.keep_upto && a.keep_upto[b] >= k) return;
     const LayerDev& Lk = a.layer[k - 1];
     const int y = blockIdx.x / Lk.w_out, x = blockIdx.x % Lk.w_out;
-    // windows of layers k-1 .. 0: [ylo, yhi] x [xlo, xhi], all channels
-    int ylo[CONE_MAX_DEPTH + 1], yhi[CONE_MAX_DEPTH + 1], xlo[CONE_MAX_DEPTH + 1], xhi[CONE_MAX_DEPTH + 1];
-    ylo[k] = yhi[k] = y; xlo[k] = xhi[k] = x;
-#pragma unroll
-    for (int j = CONE_MAX_DEPTH; j >= 1; --j) {
-        if (j > k) continue;
-        const LayerDev& L = a.layer[j - 1];
-        ylo[j - 1] = max(0, ylo[j] * L.stride - L.pad); yhi[j - 1] = min(L.h_in - 1, yhi[j] * L.stride - L.pad + L.ksize - 1);
-        xlo[j - 1] = max(0, xlo[j] * L.stride - L.pad); xhi[j - 1] = min(L.w_in - 1, xhi[j] * L.stride - L.pad + L.ksize - 1);
+    // windows of layers k-1 .. 0: [ylo, yhi] x [xlo, xhi], all channels (one table per block in shared memory: indexed by a loop
+    // variable, a per-thread copy would live in local memory)
+    __shared__ int ylo[CONE_MAX_DEPTH + 1], yhi[CONE_MAX_DEPTH + 1], xlo[CONE_MAX_DEPTH + 1], xhi[CONE_MAX_DEPTH + 1];
+    if (threadIdx.x == 0) {
+        ylo[k] = yhi[k] = y; xlo[k] = xhi[k] = x;
+        for (int j = k; j >= 1; --j) {
+            const LayerDev& L = a.layer[j - 1];
+            ylo[j - 1] = max(0, ylo[j] * L.stride - L.pad); yhi[j - 1] = min(L.h_in - 1, yhi[j] * L.stride - L.pad + L.ksize - 1);
+            xlo[j - 1] = max(0, xlo[j] * L.stride - L.pad); xhi[j - 1] = min(L.w_in - 1, xhi[j] * L.stride - L.pad + L.ksize - 1);
+        }
     }
+    __syncthreads();
     float* cur = cone_smem;
     float* nxt = cone_smem + a.buf_elems;
     const int tid = threadIdx.x, nthr = cols * a.R, col = tid % cols;

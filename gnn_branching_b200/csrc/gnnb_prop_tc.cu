@@ -34,8 +34,8 @@ __global__ void __launch_bounds__(prop::PROP_THREADS, 1) k_tc_prop(PropPlanDev p
     prop::prop_body<false>(plan, mu_img, nb_img, Bc, smem_raw, (int)blockIdx.x, (int)gridDim.x, true);
 }
 
-// the same kernel with the gather indices fetched one chunk ahead (option "gather_prefetch", off by default until it has been
-// validated and measured on the GPU)
+// the same kernel with the gather indices fetched one chunk ahead (option "gather_prefetch": bit-identical results, measured
+// no faster, off by default)
 __global__ void __launch_bounds__(prop::PROP_THREADS, 1) k_tc_prop_pf(PropPlanDev plan, const uint16_t* __restrict__ mu_img,
                                                                       uint16_t* __restrict__ nb_img, int Bc) {
     extern __shared__ unsigned char smem_raw[];
@@ -199,7 +199,7 @@ LayerTiling make_tiling(int C, int H, int W) {
 }
 
 // prefetched indices + 2 weight stages / 5 gather stages (the same shared memory): more gathered rows in flight, the weight
-// ring is rarely what the MMA warp waits for (option "gather_prefetch" = 2; not validated on a GPU yet either)
+// ring is rarely what the MMA warp waits for (option "gather_prefetch" = 2)
 __global__ void __launch_bounds__(prop::PROP_THREADS, 1) k_tc_prop_pf25(PropPlanDev plan, const uint16_t* __restrict__ mu_img,
                                                                         uint16_t* __restrict__ nb_img, int Bc) {
     extern __shared__ unsigned char smem_raw[];

@@ -5,7 +5,7 @@ set -u
 TAG=${1:-r02a}
 O=gpurun_out
 mkdir -p $O
-# 1. the whole GPU suite; -rxX lists the xfail / xpass outcomes of the isolated checks (gather_prefetch, kw_bounds)
+# 1. the whole GPU suite (the isolated checks run in their own processes)
 python -m pytest tests -m gpu -q -rxX > $O/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; tail -15 $O/${TAG}_pytest.log
 # 2. the isolated checks again, verbosely, so that a failure shows its assertion
 for a in base deep wide; do

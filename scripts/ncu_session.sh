@@ -14,3 +14,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_(tc|amb|ou
 $CMD > $O/${TAG}_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"k_tc_(fused|update|relax|input)" -s 16 -c 16 -o $O/${TAG}_prof -f $CMD > $O/${TAG}_ncu_full.log 2>&1
 echo "ncu rc=$?"
+# the bound producer: two launches of the windowed KW kernel (conv layers) of gnnb_child_bounds
+KW="python scripts/kw_probe.py base 256"
+$KW > $O/${TAG}_kw_plain.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:"k_kw_cone" -s 2 -c 2 -o $O/${TAG}_kw_prof -f $KW > $O/${TAG}_kw_ncu.log 2>&1
+echo "ncu kw rc=$?"
