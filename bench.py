@@ -252,11 +252,18 @@ def run_reference(args):
         return
     cb, times = cpu_baseline(args.workload, args.weights, reps=max(1, args.steps), warmup=max(1, args.warmup))
     per = sum(times) / len(times)
+    # the same config keys as the B200 arm's line (the workload the rate stands for), with the bounded sample that was actually
+    # timed stated beside it: the CPU rate per subdomain is flat in the batch size from B = 4 on
+    world = max(1, args.gpus)
+    strong = world > 1 and not args.domains and args.workload == 'base'
+    B = args.domains or (FRONTIER_TOTAL // world if strong else DEFAULT_DOMAINS[args.workload])
+    wl_name = (f'cifar_base_kw frontier of {B * world} synthetic subdomains sharded across {world} GPUs ({B} per GPU per step)' if strong
+               else f'cifar_{args.workload}_kw x {B} synthetic subdomains per GPU per step')
     line = {'impl': 'reference', 'metric': METRIC, 'value': CPU_SAMPLE / per, 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': len(times), 'warmup': args.warmup, 'ms_per_step': per * 1e3, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'cifar_{args.workload}_kw, {CPU_SAMPLE}-subdomain sample per step on the host CPU',
-                       'gnn': 'GraphNet(T=2,p=64)', 'weights': args.weights},
+            'scaling': 'strong' if strong else 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': wl_name, 'gnn': 'GraphNet(T=2,p=64)', 'weights': args.weights,
+                       'sample': f'{CPU_SAMPLE}-subdomain sample of that workload per step, host CPU only (rank 0)'},
             'cpu_baseline': {**cb, 'value': CPU_SAMPLE / per},
             'e2e': {'value': CPU_SAMPLE / per, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}

@@ -1,6 +1,6 @@
 #!/bin/bash
 set -u
-O=gpurun_out/r03f; mkdir -p $O
+O=gpurun_out/${TAG:-r03i}; mkdir -p $O
 SEL="scores_and_decisions or every_stage or fused_layer or other_network_shapes or host_buffers or empty_candidate or other_round or full_size"
 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "$SEL" > $O/pytest.log 2>&1; echo "pytest rc=$?"; tail -2 $O/pytest.log
 for w in base wide deep; do bash scripts/sweep_opts.sh $w "fuse=1" 2>&1 | tee -a $O/sweep.log; done
