@@ -471,13 +471,14 @@ def measure_frontier_step(model, workload, dev, world, parents=256, steps=4):
     except Exception as e:
         err = e
     failed = sync_ranks(0.0 if err is None else 1.0)   # doubles as the barrier in front of the timed region
-    dt, second, launches = float('inf'), 0, 0
+    dt, second, launches, infeasible = float('inf'), 0, 0, 0
     if not failed:
         try:
             l0, t0 = fs.scorer.launches, time.perf_counter()
             for _ in range(steps):
                 st = fs.step(parents)
                 second += st.second_pass
+                infeasible += st.infeasible
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             launches = fs.scorer.launches - l0
@@ -528,7 +529,7 @@ def measure_frontier_step(model, workload, dev, world, parents=256, steps=4):
             byts += groups * 256 * (n[j] + 3 * n[j - 1])
     peaks = load_peaks()
     return {'value': world * children / dt, 'unit': 'children/s', 'n_gpus': world, 'parents_per_step': parents, 'steps': steps, 'ms_per_step': dt / steps * 1e3,
-            'launches_per_step': launches // steps, 'second_kw_passes': second, 'queue_domains_at_end': len(fs.queue),
+            'launches_per_step': launches // steps, 'second_kw_passes': second, 'infeasible_children_dropped': infeasible, 'queue_domains_at_end': len(fs.queue),
             'api': 'FrontierStep.step: gnnb_queue_pick -> split -> gnnb_child_bounds -> gnnb_score -> gnnb_queue_add, all device-resident',
             'host_traffic': 'three counts read back per step (picked, second-pass domains, added); no bounds, masks or scores cross PCIe',
             'lp': 'surrogate (no Gurobi): lower bound = KW / interval bound of the property output, zero duals, primals = activations of the ball centre',

@@ -38,6 +38,7 @@ class StepStats:
     picked: int              # parents taken from the queue
     children: int            # 2 * picked
     second_pass: int         # children whose interval bounds triggered the second KW pass
+    infeasible: int          # children dropped because their bounds cross (or pin a node to exactly zero)
     added: int               # children put back into the queue
     global_lb: float         # smallest lower bound left in the queue (nan when it is empty)
 
@@ -82,7 +83,7 @@ class FrontierStep:
         parents = self.queue.pick(max_B, threshold)
         B = parents.B
         if B == 0:
-            return StepStats(0, 0, 0, 0, float('nan'))
+            return StepStats(0, 0, 0, 0, 0, float('nan'))
         rep = lambda t: t.repeat_interleave(2, dim=0)
         choice = torch.arange(2 * B, device=self.dev, dtype=torch.int32) & 1
         dec = rep(parents.decision)
@@ -92,13 +93,24 @@ class FrontierStep:
         # ReLUs the ancestors fixed stay fixed (their bounds say so already); this child's own split is in `masks` too, because
         # its bound is exactly 0 on the fixed side (conv_kwinter_gen.py:572: relu_mask[decision] = choice)
         mask = torch.cat(masks, dim=1)
-        new_dec, ok = self._decide(lbs, ubs, mask)
+        # Infeasible children (the split contradicts the parent's other constraints: intersected bounds cross, l > u) are where the
+        # reference's LP reports infeasibility and the child is never added; here they are dropped by the same sign.  So are
+        # children with a node pinned to exactly zero from both sides (l = u = 0): compute_ratio is 0 / 0 there, in the
+        # reference as well (its NaN trap, graph_conv.py:184-186).  Neither kind may reach the scorer, whose NaN flag is an error:
+        # they are scored on their parent's bounds instead (no host round trip to compact them away) and then not kept.
+        bad = lbs[L + 1].reshape(-1) > ubs[L + 1].reshape(-1)
+        for k in range(1, L + 1):
+            bad |= ((lbs[k] > ubs[k]) | ((lbs[k] >= 0) & (ubs[k] <= 0))).any(dim=1)
+        sel = bad[:, None]
+        s_lbs = [torch.where(sel, rep(p), c) for p, c in zip(parents.lb, lbs)]
+        s_ubs = [torch.where(sel, rep(p), c) for p, c in zip(parents.ub, ubs)]
+        new_dec, ok = self._decide(s_lbs, s_ubs, torch.where(sel, rep(parents.mask), mask))
         lower = lbs[L + 1].reshape(-1)
-        keep = ok & (lower < self.decision_bound)
+        keep = ok & ~bad & (lower < self.decision_bound)
         children = DomainBatch(lower.contiguous(), rep(parents.upper_bound).contiguous(), lbs, ubs, mask, new_dec)
         added = self.queue.add(children, keep=keep)
         glb = self.queue.global_lb if len(self.queue) else float('nan')
-        return StepStats(B, 2 * B, int(second.sum()), added, glb)
+        return StepStats(B, 2 * B, int(second.sum()), int(bad.sum()), added, glb)
 
     # ---- helpers ----
     @staticmethod

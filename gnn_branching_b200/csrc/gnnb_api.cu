@@ -55,6 +55,8 @@ struct gnnb_ctx {
     float* d_net = nullptr;
     std::vector<LayerDev> layers;
     std::vector<PropPlan*> plan_fwd, plan_bwd;   // tensor-core propagation plans per layer
+    std::vector<PropPlan*> plan_kw_own;          // un-normalised transposed plans of the conv layers k > 0 (bound producer), else null
+    std::vector<PropPlan*> plan_kw;              // per layer: plan_kw_own[k] or plan_bwd[k] (already un-normalised: layer 0, linear layers)
     std::vector<int> n;             // n[0] = input nodes, n[1..L] hidden, n[L+1] = 1
     // slot order of the tensor-core path (gnnb_common.cuh): tiling and device map of layers 0..L
     std::vector<LayerTiling> tiling;
@@ -605,6 +607,7 @@ void gnnb_destroy(gnnb_ctx* ctx) {
     if (ctx->d_nan) cudaFree(ctx->d_nan);
     for (PropPlan* p : ctx->plan_fwd) prop_plan_free(p);
     for (PropPlan* p : ctx->plan_bwd) prop_plan_free(p);
+    for (PropPlan* p : ctx->plan_kw_own) prop_plan_free(p);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->res_best) cudaFree(ctx->res_best);
     if (ctx->res_idx) cudaFree(ctx->res_idx);
@@ -691,7 +694,7 @@ int gnnb_set_network(gnnb_ctx* ctx, const gnnb_layer_desc* layers, int n_layers,
         LayerDev* d_layers = nullptr;
         int32_t *d_hidden_off = nullptr, *d_random_order = nullptr;
         const float** d_ptrs = nullptr;
-        std::vector<PropPlan*> plan_fwd, plan_bwd;
+        std::vector<PropPlan*> plan_fwd, plan_bwd, plan_kw_own;
         bool keep = false;
         ~Staged() {
             if (keep) return;
@@ -703,6 +706,7 @@ int gnnb_set_network(gnnb_ctx* ctx, const gnnb_layer_desc* layers, int n_layers,
             if (d_ptrs) cudaFree(d_ptrs);
             for (PropPlan* p : plan_fwd) prop_plan_free(p);
             for (PropPlan* p : plan_bwd) prop_plan_free(p);
+            for (PropPlan* p : plan_kw_own) prop_plan_free(p);
         }
     } sg;
     CU(cudaMalloc(&sg.d_net, total * sizeof(float)));
@@ -710,6 +714,7 @@ int gnnb_set_network(gnnb_ctx* ctx, const gnnb_layer_desc* layers, int n_layers,
     for (int k = 0; k < n_layers; ++k) { devs[k].weight = sg.d_net + o_w[k]; devs[k].bias_node = sg.d_net + o_b[k]; }
     sg.plan_fwd.assign(n_layers, nullptr);
     sg.plan_bwd.assign(n_layers, nullptr);
+    sg.plan_kw_own.assign(n_layers, nullptr);
     // slot order of layers 0..L (gnnb_common.cuh) and the device copies of the slot -> node maps
     std::vector<LayerTiling> tiling(n_layers + 1);
     std::vector<RowMap> rowmap(n_layers + 1, RowMap{nullptr, 0, 0});
@@ -734,6 +739,11 @@ int gnnb_set_network(gnnb_ctx* ctx, const gnnb_layer_desc* layers, int n_layers,
         sg.plan_fwd[k] = prop_plan_build(devs[k], layers[k].weight, false, false, tiling[k + 1], tiling[k]);
         sg.plan_bwd[k] = prop_plan_build(devs[k], layers[k].weight, true, k > 0, tiling[k], tiling[k + 1]);
         if (!sg.plan_fwd[k] || !sg.plan_bwd[k]) return fail(ctx, GNNB_ERR_CUDA, "building the propagation plans failed");
+        // the bound producer's dense recursion needs A_{k+1}^T without the tap-count normalisation (gnnb_kw.cu)
+        if (k > 0 && devs[k].kind == GNNB_LAYER_CONV) {
+            sg.plan_kw_own[k] = prop_plan_build(devs[k], layers[k].weight, true, false, tiling[k], tiling[k + 1]);
+            if (!sg.plan_kw_own[k]) return fail(ctx, GNNB_ERR_CUDA, "building the propagation plans failed");
+        }
     }
     std::vector<int> hidden_off(n_layers + 2, 0);
     int n_hidden = 0;
@@ -757,10 +767,13 @@ int gnnb_set_network(gnnb_ctx* ctx, const gnnb_layer_desc* layers, int n_layers,
     if (ctx->d_ptrs) cudaFree(ctx->d_ptrs);
     for (PropPlan* p : ctx->plan_fwd) prop_plan_free(p);
     for (PropPlan* p : ctx->plan_bwd) prop_plan_free(p);
+    for (PropPlan* p : ctx->plan_kw_own) prop_plan_free(p);
     sg.keep = true;
     ctx->d_net = sg.d_net; ctx->d_maps = sg.d_maps; ctx->d_layers = sg.d_layers; ctx->d_hidden_off = sg.d_hidden_off;
     ctx->d_random_order = sg.d_random_order; ctx->d_ptrs = sg.d_ptrs;
-    ctx->plan_fwd = sg.plan_fwd; ctx->plan_bwd = sg.plan_bwd;
+    ctx->plan_fwd = sg.plan_fwd; ctx->plan_bwd = sg.plan_bwd; ctx->plan_kw_own = sg.plan_kw_own;
+    ctx->plan_kw.assign(n_layers, nullptr);
+    for (int k = 0; k < n_layers; ++k) ctx->plan_kw[k] = sg.plan_kw_own[k] ? sg.plan_kw_own[k] : sg.plan_bwd[k];
     ctx->tiling = tiling; ctx->rowmap = rowmap;
     ctx->layers = devs;
     ctx->n = n;
@@ -1257,8 +1270,9 @@ int gnnb_kw_bounds(gnnb_ctx* ctx, int32_t B, const float* x, float eps, const fl
         for (int k = 0; k < L; ++k) if (!provided_lb[k] || !provided_ub[k]) return fail(ctx, GNNB_ERR_INVALID, "null provided-bounds array");
     CU(cudaSetDevice(ctx->device));
     std::string err;
-    const int rc = kw_bounds(ctx->layers, ctx->n, B, x, eps, wp, bp, provided_lb, provided_ub, out_lb, out_ub, &ctx->kw_ws, &ctx->kw_ws_cap,
-                             (cudaStream_t)stream, &ctx->launches, &err);
+    const KwTc tc{&ctx->plan_kw, &ctx->rowmap};
+    const int rc = kw_bounds(ctx->layers, ctx->n, B, x, eps, wp, bp, provided_lb, provided_ub, out_lb, out_ub,
+                             ctx->math == GNNB_MATH_TC_FP16X3 ? &tc : nullptr, &ctx->kw_ws, &ctx->kw_ws_cap, (cudaStream_t)stream, &ctx->launches, &err);
     if (rc != GNNB_OK) return fail(ctx, rc, err);
     return GNNB_OK;
 }
@@ -1283,8 +1297,10 @@ int gnnb_child_bounds(gnnb_ctx* ctx, int32_t B, const float* x, float eps, const
         ctx->kw_iscratch_cap = B;
     }
     std::string err;
+    const KwTc tc{&ctx->plan_kw, &ctx->rowmap};
     const int rc = child_bounds(ctx->layers, ctx->n, B, x, eps, wp, bp, parent_lb, parent_ub, dec_layer, dec_index, choice, out_lb, out_ub, out_mask,
-                                second_pass, ctx->kw_iscratch, &ctx->kw_ws, &ctx->kw_ws_cap, st, &ctx->launches, &err);
+                                second_pass, ctx->kw_iscratch, ctx->math == GNNB_MATH_TC_FP16X3 ? &tc : nullptr, &ctx->kw_ws, &ctx->kw_ws_cap, st,
+                                &ctx->launches, &err);
     if (rc != GNNB_OK) return fail(ctx, rc, err);
     return GNNB_OK;
 }

@@ -204,16 +204,19 @@ int queue_pick(DomainQueue* q, int max_B, float threshold, bool discard, int32_t
 int queue_prune(DomainQueue* q, float threshold, cudaStream_t st, int64_t* launches);
 float* queue_stage(DomainQueue* q, size_t bytes);
 
-// batched KW intermediate bounds (gnnb_kw.cu); every pointer is a device pointer
+// batched KW intermediate bounds (gnnb_kw.cu); every pointer is a device pointer.  KwTc (or null): the dense layers' column
+// blocks go through the tensor-core propagation kernel — plans[j] = un-normalised transposed plan of layer j + 1 -> j, maps[k] =
+// slot order of layer k
+struct KwTc { const std::vector<PropPlan*>* plans; const std::vector<RowMap>* maps; };
 int kw_bounds(const std::vector<LayerDev>& layers, const std::vector<int>& n, int B, const float* x, float eps, const float* wp, const float* bp,
-              const float* const* prov_lb, const float* const* prov_ub, float* const* out_lb, float* const* out_ub, float** ws,
+              const float* const* prov_lb, const float* const* prov_ub, float* const* out_lb, float* const* out_ub, const KwTc* tc, float** ws,
               size_t* ws_cap, cudaStream_t st, int64_t* launches, std::string* err);
 // bounds part of update_the_model for B children (KW pass with the split, interval pass, second KW pass where needed); iscratch:
 // 3 B + 1 int32 of device scratch; synchronises `st` once
 int child_bounds(const std::vector<LayerDev>& layers, const std::vector<int>& n, int B, const float* x, float eps, const float* wp, const float* bp,
                  const float* const* parent_lb, const float* const* parent_ub, const int32_t* dec_layer, const int32_t* dec_index,
                  const int32_t* choice, float* const* out_lb, float* const* out_ub, int8_t* const* out_mask, int32_t* second_pass,
-                 int32_t* iscratch, float** ws, size_t* ws_cap, cudaStream_t st, int64_t* launches, std::string* err);
+                 int32_t* iscratch, const KwTc* tc, float** ws, size_t* ws_cap, cudaStream_t st, int64_t* launches, std::string* err);
 
 // ---- device helpers ---------------------------------------------------------------------------
 // compute_ratio of graph_conv.py:499-514 in the reference's operation order (IEEE division, no fast-math)

@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "gnnb_common.cuh"
+#include "gnnb_umma.cuh"
 
 namespace gnnb {
 namespace {
@@ -262,6 +263,131 @@ __global__ void k_mask_from_bounds(const float* __restrict__ lb, const float* __
 }
 
 
+// ---- dense layers on the tensor cores ------------------------------------------------------------------------------------
+// The column blocks of the dense recursion are exactly what the GNN's propagation kernel moves: [pairs, n, 64] with 64 columns
+// in the 64 "embedding channels".  With the un-normalised transposed plans (KwTc::plans) k_tc_prop computes t_j = A_{j+1}^T s_{j+1}
+// on the tensor cores (fp16 hi / lo split, three passes, fp32 accumulate: 2^-22 per product, bounds are held to 2e-5); the
+// tensors travel in the tile-image formats of that kernel (gnnb_umma.cuh): s_j as a mu image (slot order, K-major
+// SWIZZLE_128B planes), t_j as the piece-major nb image.  Unscaled values: |t| stays far below fp16's range.
+using namespace tcx;
+
+// s_k of a column group as a mu image: row of slot r, channel c = (node_of_slot[r] == g * 64 + c)
+__global__ void k_kw_img_onehot(uint16_t* __restrict__ mu_img, RowMap map, int G, int64_t p0, int64_t total) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // (pair-local row, chunk of 8 channels)
+    if (i >= total) return;
+    const int chunk = (int)(i & 7);
+    const int64_t row = i >> 3, pl = row / map.nslots;
+    const int slot = (int)(row - pl * map.nslots);
+    const int node = map.node_of_slot[slot];
+    const int g = (int)((p0 + pl) % G);
+    const int c = node - g * KW_COLS - chunk * 8;                            // position of the 1 inside this chunk, if any
+    uint4 hi = make_uint4(0u, 0u, 0u, 0u);
+    if (node >= 0 && c >= 0 && c < 8) reinterpret_cast<uint16_t*>(&hi)[c] = 0x3C00u;      // fp16 1.0
+    unsigned char* img = reinterpret_cast<unsigned char*>(mu_img) + (row / TILE) * (int64_t)ABUF;
+    const uint32_t off = swz((uint32_t)(row % TILE), (uint32_t)chunk);
+    *reinterpret_cast<uint4*>(img + off) = hi;
+    *reinterpret_cast<uint4*>(img + APLANE + off) = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// t_L of the property output as an nb image: channel 0 = Wp[b, node], the other channels 0 (one pair per domain)
+__global__ void k_kw_img_wp(uint16_t* __restrict__ nb_img, const float* __restrict__ wp, RowMap map, int64_t p0, int64_t total,
+                            const int32_t* __restrict__ dom_list) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // (pair-local row, piece of 8 channels)
+    if (i >= total) return;
+    const int piece = (int)(i & 7);
+    const int64_t row = i >> 3, pl = row / map.nslots;
+    const int slot = (int)(row - pl * map.nslots);
+    const int node = map.node_of_slot[slot];
+    const int64_t b = dom_list ? dom_list[p0 + pl] : p0 + pl;
+    uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+    if (piece == 0 && node >= 0) split2(wp[b * map.n + node], 0.f, hi.x, lo.x);
+    unsigned char* img = reinterpret_cast<unsigned char*>(nb_img) + (row / TILE) * (int64_t)ABUF;
+    const uint32_t off = (uint32_t)piece * NB_PIECE + (uint32_t)(row % TILE) * 16u;
+    *reinterpret_cast<uint4*>(img + off) = hi;
+    *reinterpret_cast<uint4*>(img + APLANE + off) = lo;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& hi, const uint4& lo, float (&v)[8]) {
+    const __half2* h = reinterpret_cast<const __half2*>(&hi);
+    const __half2* l = reinterpret_cast<const __half2*>(&lo);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        v[2 * q] = __low2float(h[q]) + __low2float(l[q]);
+        v[2 * q + 1] = __high2float(h[q]) + __high2float(l[q]);
+    }
+}
+
+// t_j (nb image) -> s_j = d_j * t_j (mu image) and the layer's three sums per column.  One block per pair, which walks the tiles of
+// the layer in order (deterministic sums): thread = (row of the tile, half of the channels) in phase 1, (row quarter, column)
+// in phase 2.  layer_is_input: t_0 instead — t_0 . x and |t_0|_1, nothing written back.
+__global__ void __launch_bounds__(256) k_kw_img_reduce(const uint16_t* __restrict__ t_img, uint16_t* __restrict__ s_img, RowMap map,
+                                                       const float* __restrict__ zl, const float* __restrict__ zu,
+                                                       const float* __restrict__ bias_node, const float* __restrict__ x, int G, int64_t p0,
+                                                       KwAcc acc, const int32_t* __restrict__ dom_list, int layer_is_input) {
+    __shared__ float S[TILE][KW_COLS + 1];
+    __shared__ float rowA[TILE], rowB[TILE];        // hidden: l (0 unless the row is in I) and bias; input: x and unused
+    __shared__ float red[3][4][KW_COLS];
+    const int64_t pl = blockIdx.x, bl = (p0 + pl) / G, b = dom_list ? dom_list[bl] : bl;
+    const int tid = threadIdx.x, r = tid >> 1, half = tid & 1;
+    const int q = tid >> 6, c = tid & 63;
+    const int ntiles = map.nslots / TILE;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int tile = 0; tile < ntiles; ++tile) {
+        const int node = map.node_of_slot[tile * TILE + r];
+        float d = 0.f, la = 0.f, bi = 0.f;
+        if (node >= 0) {
+            if (layer_is_input) { la = x[b * map.n + node]; d = 1.0f; }
+            else {
+                const float l = zl[b * map.n + node], u = zu[b * map.n + node];
+                const bool I = (u > 0.f) && (l < 0.f);
+                d = (l >= 0.f) ? 1.0f : 0.0f;
+                if (I) { d += __fdiv_rn(u, u - l); la = l; }
+                bi = bias_node[node];
+            }
+        }
+        if (half == 0) { rowA[r] = la; rowB[r] = bi; }
+        const unsigned char* ti = reinterpret_cast<const unsigned char*>(t_img) + ((int64_t)pl * ntiles + tile) * ABUF;
+        unsigned char* si = reinterpret_cast<unsigned char*>(s_img) + ((int64_t)pl * ntiles + tile) * ABUF;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const int chunk = half * 4 + cc;
+            const uint32_t toff = (uint32_t)chunk * NB_PIECE + (uint32_t)r * 16u;
+            float v[8];
+            unpack8(*reinterpret_cast<const uint4*>(ti + toff), *reinterpret_cast<const uint4*>(ti + APLANE + toff), v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { v[e] *= d; S[r][chunk * 8 + e] = v[e]; }
+            if (!layer_is_input) {
+                uint4 hi, lo;
+                split2(v[0], v[1], hi.x, lo.x); split2(v[2], v[3], hi.y, lo.y); split2(v[4], v[5], hi.z, lo.z); split2(v[6], v[7], hi.w, lo.w);
+                const uint32_t soff = swz((uint32_t)r, (uint32_t)chunk);
+                *reinterpret_cast<uint4*>(si + soff) = hi;
+                *reinterpret_cast<uint4*>(si + APLANE + soff) = lo;
+            }
+        }
+        __syncthreads();
+        for (int rr = q * 32; rr < q * 32 + 32; ++rr) {
+            const float sv = S[rr][c], a = rowA[rr];
+            if (layer_is_input) { s0 = fmaf(sv, a, s0); s1 += fabsf(sv); }
+            else {
+                s0 = fmaf(sv, rowB[rr], s0);
+                s1 = fmaf(a, fmaxf(-sv, 0.f), s1);        // a = l for rows in I, 0 otherwise
+                s2 = fmaf(a, fmaxf(sv, 0.f), s2);
+            }
+        }
+        __syncthreads();
+    }
+    red[0][q][c] = s0; red[1][q][c] = s1; red[2][q][c] = s2;
+    __syncthreads();
+    if (q == 0) {
+        const int64_t o = pl * KW_COLS + c;
+        const float a0 = (red[0][0][c] + red[0][1][c]) + (red[0][2][c] + red[0][3][c]);
+        const float a1 = (red[1][0][c] + red[1][1][c]) + (red[1][2][c] + red[1][3][c]);
+        const float a2 = (red[2][0][c] + red[2][1][c]) + (red[2][2][c] + red[2][3][c]);
+        if (layer_is_input) { acc.cx[o] = a0; acc.l1[o] = a1; }
+        else { acc.bias[o] += a0; acc.low[o] += a1; acc.up[o] += a2; }
+    }
+}
+
 // ---- conv layers: one column's backward cone is local -------------------------------------------------------------------
 // For a conv layer k whose predecessors are all conv layers, the column e_o of output o = (co, y, x) touches only the kernel
 // footprint of (y, x) in layer k - 1, the footprint of that in layer k - 2, ... : a window of a few hundred nodes per layer
@@ -335,28 +461,62 @@ __global__ void __launch_bounds__(256) k_kw_cone(const __grid_constant__ ConeArg
             if (I) { acc_low = fmaf(l, fmaxf(-sv, 0.f), acc_low); acc_up = fmaf(l, fmaxf(sv, 0.f), acc_up); }
         }
         __syncthreads();
-        // t_{j-1} = A_j^T s_j on the window of layer j - 1
+        // t_{j-1} = A_j^T s_j on the window of layer j - 1.  Columns in blocks of 8 per thread when they come in eights (a weight is
+        // loaded once per 8 products, the 8 column values with two 16-byte shared-memory loads), one by one otherwise
         const int hi = yhi[j - 1] - ylo[j - 1] + 1, wi = xhi[j - 1] - xlo[j - 1] + 1, Ei = Lj.c_in * hi * wi;
-        for (int idx = tid; idx < Ei * cols; idx += nthr) {
-            const int e = idx / cols, ci = e / (hi * wi), yy = ylo[j - 1] + (e / wi) % hi, xx = xlo[j - 1] + e % wi;
-            float sum = 0.f;
-            for (int ky = 0; ky < Lj.ksize; ++ky) {
-                const int ty = yy + Lj.pad - ky;
-                if (ty < 0 || ty % Lj.stride != 0) continue;
-                const int oy = ty / Lj.stride;
-                if (oy < ylo[j] || oy > yhi[j]) continue;
-                for (int kx = 0; kx < Lj.ksize; ++kx) {
-                    const int tx = xx + Lj.pad - kx;
-                    if (tx < 0 || tx % Lj.stride != 0) continue;
-                    const int ox = tx / Lj.stride;
-                    if (ox < xlo[j] || ox > xhi[j]) continue;
-                    const float* w = Lj.weight + (ci * Lj.ksize + ky) * Lj.ksize + kx;
-                    const float* sp = cur + ((oy - ylo[j]) * wj + (ox - xlo[j])) * cols + col;
-                    for (int c = 0; c < Lj.c_out; ++c)
-                        sum = fmaf(w[(int64_t)c * Lj.c_in * Lj.ksize * Lj.ksize], sp[(int64_t)c * hj * wj * cols], sum);
+        const int64_t wstride = (int64_t)Lj.c_in * Lj.ksize * Lj.ksize;
+        const int cstride = hj * wj * cols;
+        if ((cols & 7) == 0) {
+            const int CG = cols >> 3;
+            for (int idx = tid; idx < Ei * CG; idx += nthr) {
+                const int e = idx / CG, cg = idx - e * CG, ci = e / (hi * wi), yy = ylo[j - 1] + (e / wi) % hi, xx = xlo[j - 1] + e % wi;
+                float sum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                for (int ky = 0; ky < Lj.ksize; ++ky) {
+                    const int ty = yy + Lj.pad - ky;
+                    if (ty < 0 || ty % Lj.stride != 0) continue;
+                    const int oy = ty / Lj.stride;
+                    if (oy < ylo[j] || oy > yhi[j]) continue;
+                    for (int kx = 0; kx < Lj.ksize; ++kx) {
+                        const int tx = xx + Lj.pad - kx;
+                        if (tx < 0 || tx % Lj.stride != 0) continue;
+                        const int ox = tx / Lj.stride;
+                        if (ox < xlo[j] || ox > xhi[j]) continue;
+                        const float* w = Lj.weight + (ci * Lj.ksize + ky) * Lj.ksize + kx;
+                        const float* sp = cur + ((oy - ylo[j]) * wj + (ox - xlo[j])) * cols + cg * 8;
+                        for (int c = 0; c < Lj.c_out; ++c) {
+                            const float wv = __ldg(w + c * wstride);
+                            const float4 s0 = *reinterpret_cast<const float4*>(sp + c * cstride);
+                            const float4 s1 = *reinterpret_cast<const float4*>(sp + c * cstride + 4);
+                            sum[0] = fmaf(wv, s0.x, sum[0]); sum[1] = fmaf(wv, s0.y, sum[1]); sum[2] = fmaf(wv, s0.z, sum[2]); sum[3] = fmaf(wv, s0.w, sum[3]);
+                            sum[4] = fmaf(wv, s1.x, sum[4]); sum[5] = fmaf(wv, s1.y, sum[5]); sum[6] = fmaf(wv, s1.z, sum[6]); sum[7] = fmaf(wv, s1.w, sum[7]);
+                        }
+                    }
                 }
+                float4* o = reinterpret_cast<float4*>(nxt + e * cols + cg * 8);
+                o[0] = make_float4(sum[0], sum[1], sum[2], sum[3]);
+                o[1] = make_float4(sum[4], sum[5], sum[6], sum[7]);
             }
-            nxt[idx] = sum;
+        } else {
+            for (int idx = tid; idx < Ei * cols; idx += nthr) {
+                const int e = idx / cols, ci = e / (hi * wi), yy = ylo[j - 1] + (e / wi) % hi, xx = xlo[j - 1] + e % wi;
+                float sum = 0.f;
+                for (int ky = 0; ky < Lj.ksize; ++ky) {
+                    const int ty = yy + Lj.pad - ky;
+                    if (ty < 0 || ty % Lj.stride != 0) continue;
+                    const int oy = ty / Lj.stride;
+                    if (oy < ylo[j] || oy > yhi[j]) continue;
+                    for (int kx = 0; kx < Lj.ksize; ++kx) {
+                        const int tx = xx + Lj.pad - kx;
+                        if (tx < 0 || tx % Lj.stride != 0) continue;
+                        const int ox = tx / Lj.stride;
+                        if (ox < xlo[j] || ox > xhi[j]) continue;
+                        const float* w = Lj.weight + (ci * Lj.ksize + ky) * Lj.ksize + kx;
+                        const float* sp = cur + ((oy - ylo[j]) * wj + (ox - xlo[j])) * cols + col;
+                        for (int c = 0; c < Lj.c_out; ++c) sum = fmaf(w[c * wstride], sp[c * cstride], sum);
+                    }
+                }
+                nxt[idx] = sum;
+            }
         }
         __syncthreads();
         float* t = cur; cur = nxt; nxt = t;
@@ -456,14 +616,19 @@ bool kw_cone_layer(const std::vector<LayerDev>& layers, const std::vector<int>& 
 // *ws / *ws_cap (floats): caller-kept scratch, grown when too small.
 int kw_pass(const std::vector<LayerDev>& layers, const std::vector<int>& n, int B, const float* x, float eps, const float* wp, const float* bp,
             const float* const* prov_lb, const float* const* prov_ub, float* const* out_lb, float* const* out_ub, int first_layer,
-            const int32_t* dom_list, int n_dom, const int32_t* keep_upto, float** ws, size_t* ws_cap, cudaStream_t st, int64_t* launches,
-            std::string* err) {
+            const int32_t* dom_list, int n_dom, const int32_t* keep_upto, const KwTc* tc, float** ws, size_t* ws_cap, cudaStream_t st,
+            int64_t* launches, std::string* err) {
     const int L = (int)layers.size();
     const int ND = dom_list ? n_dom : B;          // domains of this pass
     static const bool use_cone = !(getenv("GNNB_KW_DENSE") && atoi(getenv("GNNB_KW_DENSE")) != 0);      // debugging: dense recursion everywhere
     if (ND < 1) return GNNB_OK;
+    static const bool use_tc = !(getenv("GNNB_KW_SIMT") && atoi(getenv("GNNB_KW_SIMT")) != 0);        // debugging: exact-fp32 propagation everywhere
+    if (!use_tc) tc = nullptr;
     int nmax = 0;
-    for (int k = 0; k <= L; ++k) nmax = n[k] > nmax ? n[k] : nmax;
+    for (int k = 0; k <= L; ++k) {
+        const int rows = tc ? (*tc->maps)[k].nslots : n[k];          // the tile images are padded to whole tiles
+        nmax = rows > nmax ? rows : nmax;
+    }
     int64_t max_pairs = 0;
     for (int k = 1; k <= L; ++k) {
         const int64_t pairs = (int64_t)ND * ((n[k] + KW_COLS - 1) / KW_COLS);
@@ -502,6 +667,30 @@ int kw_pass(const std::vector<LayerDev>& layers, const std::vector<int>& n, int 
             cudaMemsetAsync(accp, 0, 5 * acc_elems * sizeof(float), st);
             int cur = 0;
             int j = k - 1;                          // layer whose post-activation space buf[cur] is about to hold (t_j)
+            if (tc) {
+                // tensor-core form: buf[0] holds mu images (s), buf[1] nb images (t)
+                uint16_t* s_img = reinterpret_cast<uint16_t*>(buf[0]);
+                uint16_t* t_img = reinterpret_cast<uint16_t*>(buf[1]);
+                const std::vector<RowMap>& M = *tc->maps;
+                if (!out_layer) {
+                    const int64_t total = np * M[k].nslots * 8;
+                    k_kw_img_onehot<<<blocks_of(total, 256), 256, 0, st>>>(s_img, M[k], G, p0, total);                  // s_k
+                    ++*launches;
+                    prop_tc_run((*tc->plans)[k - 1], buf[0], buf[1], (int)np, st, launches);                            // t_{k-1} = A_k^T s_k
+                } else {
+                    const int64_t total = np * M[L].nslots * 8;
+                    k_kw_img_wp<<<blocks_of(total, 256), 256, 0, st>>>(t_img, wp, M[L], p0, total, dom_list);           // t_L (G = 1: pair = domain)
+                    ++*launches;
+                }
+                for (; j >= 1; --j) {
+                    k_kw_img_reduce<<<(unsigned)np, 256, 0, st>>>(t_img, s_img, M[j], out_lb[j], out_ub[j], layers[j - 1].bias_node, nullptr, G, p0, acc,
+                                                                  dom_list, 0);                                       // s_j = d_j t_j
+                    ++*launches;
+                    prop_tc_run((*tc->plans)[j - 1], buf[0], buf[1], (int)np, st, launches);                            // t_{j-1} = A_j^T s_j
+                }
+                k_kw_img_reduce<<<(unsigned)np, 256, 0, st>>>(t_img, s_img, M[0], nullptr, nullptr, nullptr, x, G, p0, acc, dom_list, 1);
+                ++*launches;
+            } else {
             if (!out_layer) {
                 const int64_t total4 = np * n[k] * 16;
                 k_kw_onehot<<<blocks_of(total4, 256), 256, 0, st>>>(buf[cur], n[k], G, p0, total4);        // s_k
@@ -525,10 +714,12 @@ int kw_pass(const std::vector<LayerDev>& layers, const std::vector<int>& n, int 
             prop_backward(layers[0], buf[cur], buf[cur ^ 1], (int)np, false, st, launches);                  // t_0 = A_1^T s_1
             cur ^= 1;
             k_kw_reduce_input<<<(unsigned)np, 256, 0, st>>>(buf[cur], x, n[0], G, p0, acc, dom_list);
+            ++*launches;
+            }
             k_kw_finish<<<blocks_of(np * KW_COLS, 256), 256, 0, st>>>(acc, ncols, G, p0, np, eps, out_layer ? nullptr : layers[k - 1].bias_node, bp,
                                                                       prov_lb ? prov_lb[k - 1] : nullptr, prov_ub ? prov_ub[k - 1] : nullptr,
                                                                       out_lb[k], out_ub[k], dom_list, keep_upto, k);
-            *launches += 2;
+            ++*launches;
         }
     }
     const cudaError_t e = cudaGetLastError();
@@ -538,13 +729,13 @@ int kw_pass(const std::vector<LayerDev>& layers, const std::vector<int>& n, int 
 
 // init_kw_bounds for B domains: all layers, optional provided bounds of the hidden layers (L arrays)
 int kw_bounds(const std::vector<LayerDev>& layers, const std::vector<int>& n, int B, const float* x, float eps, const float* wp, const float* bp,
-              const float* const* prov_lb, const float* const* prov_ub, float* const* out_lb, float* const* out_ub, float** ws,
+              const float* const* prov_lb, const float* const* prov_ub, float* const* out_lb, float* const* out_ub, const KwTc* tc, float** ws,
               size_t* ws_cap, cudaStream_t st, int64_t* launches, std::string* err) {
     const int L = (int)layers.size();
     const float* pl[KW_MAX_LAYERS + 1];
     const float* pu[KW_MAX_LAYERS + 1];
     for (int k = 0; k <= L; ++k) { pl[k] = (prov_lb && k < L) ? prov_lb[k] : nullptr; pu[k] = (prov_ub && k < L) ? prov_ub[k] : nullptr; }
-    return kw_pass(layers, n, B, x, eps, wp, bp, prov_lb ? pl : nullptr, prov_ub ? pu : nullptr, out_lb, out_ub, 1, nullptr, 0, nullptr, ws, ws_cap,
+    return kw_pass(layers, n, B, x, eps, wp, bp, prov_lb ? pl : nullptr, prov_ub ? pu : nullptr, out_lb, out_ub, 1, nullptr, 0, nullptr, tc, ws, ws_cap,
                    st, launches, err);
 }
 
@@ -556,7 +747,7 @@ int kw_bounds(const std::vector<LayerDev>& layers, const std::vector<int>& n, in
 int child_bounds(const std::vector<LayerDev>& layers, const std::vector<int>& n, int B, const float* x, float eps, const float* wp, const float* bp,
                  const float* const* parent_lb, const float* const* parent_ub, const int32_t* dec_layer, const int32_t* dec_index,
                  const int32_t* choice, float* const* out_lb, float* const* out_ub, int8_t* const* out_mask, int32_t* second_pass,
-                 int32_t* iscratch, float** ws, size_t* ws_cap, cudaStream_t st, int64_t* launches, std::string* err) {
+                 int32_t* iscratch, const KwTc* tc, float** ws, size_t* ws_cap, cudaStream_t st, int64_t* launches, std::string* err) {
     const int L = (int)layers.size();
     if (L > KW_MAX_LAYERS) { *err = "child bounds: too many layers"; return GNNB_ERR_UNSUPPORTED; }
     int32_t* keep = iscratch;
@@ -575,7 +766,7 @@ int child_bounds(const std::vector<LayerDev>& layers, const std::vector<int>& n,
     const float* pl[KW_MAX_LAYERS + 1];
     const float* pu[KW_MAX_LAYERS + 1];
     for (int k = 1; k <= L + 1; ++k) { pl[k - 1] = out_lb[k]; pu[k - 1] = out_ub[k]; }
-    int rc = kw_pass(layers, n, B, x, eps, wp, bp, pl, pu, out_lb, out_ub, 2, nullptr, 0, keep, ws, ws_cap, st, launches, err);
+    int rc = kw_pass(layers, n, B, x, eps, wp, bp, pl, pu, out_lb, out_ub, 2, nullptr, 0, keep, tc, ws, ws_cap, st, launches, err);
     if (rc != GNNB_OK) return rc;
     // interval pass, layer by layer behind the split
     for (int k = 2; k <= L + 1; ++k) {
@@ -598,7 +789,7 @@ int child_bounds(const std::vector<LayerDev>& layers, const std::vector<int>& n,
     cudaMemcpyAsync(&h_count, count, sizeof h_count, cudaMemcpyDeviceToHost, st);
     if (cudaStreamSynchronize(st) != cudaSuccess) { *err = std::string("child bounds: ") + cudaGetErrorString(cudaGetLastError()); return GNNB_ERR_CUDA; }
     if (h_count > 0) {
-        rc = kw_pass(layers, n, B, x, eps, wp, bp, pl, pu, out_lb, out_ub, 2, list, h_count, keep, ws, ws_cap, st, launches, err);
+        rc = kw_pass(layers, n, B, x, eps, wp, bp, pl, pu, out_lb, out_ub, 2, list, h_count, keep, tc, ws, ws_cap, st, launches, err);
         if (rc != GNNB_OK) return rc;
     }
     if (second_pass) cudaMemcpyAsync(second_pass, changed, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);

@@ -19,4 +19,4 @@ for _ in range(2):
     torch.cuda.synchronize(); t0 = time.time()
     st = fs.step(PB)
     torch.cuda.synchronize(); dt = time.time() - t0
-    print(f'step {arch}: {st.picked} parents -> {st.children} children in {dt * 1e3:.1f} ms = {st.children / dt:.0f} children/s; second pass {st.second_pass}, added {st.added}, queue {len(fs.queue)}', flush=True)
+    print(f'step {arch}: {st.picked} parents -> {st.children} children in {dt * 1e3:.1f} ms = {st.children / dt:.0f} children/s; second pass {st.second_pass}, infeasible {st.infeasible}, added {st.added}, queue {len(fs.queue)}', flush=True)

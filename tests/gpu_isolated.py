@@ -75,6 +75,7 @@ def check_kw_bounds(arch):
     x = torch.from_numpy(np.load(os.path.join(GOLDEN, 'nets.npz'))[f'{arch}_x'].copy()).reshape(1, -1)
     sc = Scorer(0)
     sc.set_network(net, key=net.key)
+    sc.set_option('math', int(os.environ.get('GNNB_TEST_MATH', '0')))      # 0: dense layers on the tensor cores, 1: exact-fp32 kernels
 
     def err(a, b):
         return float((a.reshape(-1).cpu() - b.reshape(-1)).abs().max()) / max(1.0, float(b.abs().max()))
@@ -115,6 +116,7 @@ def check_child_bounds(arch):
     L, nc = net.L, int(z[f'{arch}_ncases'])
     sc = Scorer(0)
     sc.set_network(net, key=net.key)
+    sc.set_option('math', int(os.environ.get('GNNB_TEST_MATH', '0')))      # 0: dense layers on the tensor cores, 1: exact-fp32 kernels
 
     def get(c):
         lbs = [x[0] - 0.145] + [torch.from_numpy(z[f'{arch}_c{c}_lb{k}'].copy()) for k in range(1, L + 2)]
@@ -166,7 +168,7 @@ def check_child_bounds(arch):
                 assert torch.equal(masks[k - 1][i].cpu(), want), ('mask', c, k)
             lay, idx, choice = z[f'{arch}_c{c}_decision'].tolist()
             assert int(masks[lay][i][idx]) == choice, ('mask of the split node', c)
-        print(f'child_bounds {arch} B={B}: worst rel err {worst:.2e}, second passes {int(second.sum())}', flush=True)
+        print(f'child_bounds {arch} B={B} math={sc.get_option("math")}: worst rel err {worst:.2e}, second passes {int(second.sum())}', flush=True)
 
 
 def check_child_bounds_shapes(case):
@@ -204,6 +206,7 @@ def check_child_bounds_shapes(case):
     assert B >= 4
     sc = Scorer(0)
     sc.set_network(net, key=net.key)
+    sc.set_option('math', int(os.environ.get('GNNB_TEST_MATH', '0')))
     dec = torch.tensor(decs, dtype=torch.int32)
     gl, gu, masks, second = sc.child_bounds(x.reshape(1, -1), eps, wp.reshape(1, -1).repeat(B, 1), torch.full((B,), bp),
                                             [t.reshape(1, -1).repeat(B, 1) for t in lbs], [t.reshape(1, -1).repeat(B, 1) for t in ubs],
@@ -233,14 +236,14 @@ def check_frontier_step(arch):
     model = GraphNet(2, 64, math='tc')
     model.load_state_dict(load_gnn('random'))
     model = model.eval().cuda()
-    fs = FrontierStep(model, net, x, 0.145, wp, bp, capacity=4096, decision_bound=float('inf'))
+    fs = FrontierStep(model, net, x, 0.145, wp, bp, capacity=8192, decision_bound=float('inf'))
     fs.seed_root(lbs, ubs)
     assert len(fs.queue) == 1
     root = fs.queue.pick(1, float('inf'))
     dec = root.decision[0].tolist()
     fs.queue.add(root)
     st = fs.step(8)
-    assert (st.picked, st.children, st.added) == (1, 2, 2) and len(fs.queue) == 2, st
+    assert (st.picked, st.children, st.added, st.infeasible) == (1, 2, 2, 0) and len(fs.queue) == 2, st
     kids = fs.queue.pick(2, float('inf'))
     for i in range(2):
         # which side is this child?  the split node's bound is 0 on the fixed side
@@ -254,13 +257,15 @@ def check_frontier_step(arch):
     assert {0 if float(kids.ub[dec[0] + 1][i, dec[1]]) == 0.0 else 1 for i in range(2)} == {0, 1}
     fs.queue.add(kids)
     glb, size = fs.queue.global_lb, 2
-    for B in (2, 4, 8, 16):
+    dropped = 0
+    for B in (2, 4, 8, 16, 32, 64, 128, 256):           # deep enough for splits that contradict each other (infeasible children)
         st = fs.step(B)
         size += st.added - st.picked
-        assert st.children == 2 * st.picked and st.added <= st.children and len(fs.queue) == size, (st, size)
+        dropped += st.infeasible
+        assert st.children == 2 * st.picked and st.added <= st.children - st.infeasible and len(fs.queue) == size, (st, size)
         assert st.global_lb >= glb - 1e-6, (st.global_lb, glb)      # children are never looser than their parents
         glb = st.global_lb
-    print(f'frontier_step {arch}: queue {len(fs.queue)} domains, global lb {glb:.4f}', flush=True)
+    print(f'frontier_step {arch}: queue {len(fs.queue)} domains, {dropped} infeasible children dropped, global lb {glb:.4f}', flush=True)
 
 
 if __name__ == '__main__':

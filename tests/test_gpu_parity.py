@@ -179,9 +179,11 @@ def test_full_size_frontier_properties(arch, B, math):
     fr = synthetic_frontier(net, lbs, ubs, wp, bp, B, seed=1000 * (2 + ARCHS.index(arch)), device='cuda')
     model = _model('random', math)
     best, idx, scores = model.score_frontier(fr)
-    sl = fr.slice(B - 3, B).cpu().contiguous()
+    # oracle parity on 12 subdomains spread over the whole frontier (first and last wave items, ragged tail included)
+    ids = torch.tensor(sorted({0, 1, B // 7, B // 3, B // 2 - 1, B // 2, (2 * B) // 3, B - 130, B - 129, B - 3, B - 2, B - 1}), device='cuda')
+    sl = fr._map(lambda t: t[ids]).cpu().contiguous()
     s_or, _ = O.gnn_forward(load_gnn('random'), sl)
-    rep = O.parity_report(scores[B - 3:].cpu(), s_or, sl.mask, idx[B - 3:].cpu(), rtol=RTOL[math])
+    rep = O.parity_report(scores[ids].cpu(), s_or, sl.mask, idx[ids].cpu(), rtol=RTOL[math])
     assert rep['ok'], rep
     b2, i2, s2 = model.score_frontier(fr.slice(B - 3, B).contiguous())
     assert torch.equal(s2, scores[B - 3:]) and torch.equal(i2, idx[B - 3:])
@@ -210,9 +212,13 @@ def test_frontier_of_65536_subdomains():
         assert torch.equal(b2, best[start:start + 5]) and torch.equal(i2, idx[start:start + 5])
         masked = torch.where(sl.mask != 0, s2, torch.full_like(s2, float('-inf')))
         assert torch.equal(masked.max(1).values, b2)
-    sl = fr.slice(B - 2, B).cpu().contiguous()
+    # oracle parity on 10 subdomains spread over the 64 waves
+    ids = torch.tensor([0, 1023, 1024, 20000, 32767, 32768, 50001, B - 1025, B - 2, B - 1], device='cuda')
+    pick = fr._map(lambda t: t[ids].contiguous())
+    sl = pick.cpu().contiguous()
     s_or, _ = O.gnn_forward(load_gnn('random'), sl)
-    _, i3, s3 = model.score_frontier(fr.slice(B - 2, B).contiguous())
+    b3, i3, s3 = model.score_frontier(pick)
+    assert torch.equal(b3, best[ids]) and torch.equal(i3, idx[ids])
     rep = O.parity_report(s3.cpu(), s_or, sl.mask, i3.cpu(), rtol=RTOL['tc'])
     assert rep['ok'], rep
 
@@ -615,7 +621,7 @@ def test_domain_queue_reference_function_api():
 _ISO_TIMED_OUT = set()
 
 
-def _run_isolated(what, arg, timeout=120):
+def _run_isolated(what, arg, timeout=120, env=None):
     """Run a check in its own process (its own CUDA context) with a timeout: a hang or a sticky CUDA error there cannot take
     the rest of the suite with it.  After one time-out of a kind of check the others of that kind fail at once."""
     import subprocess
@@ -624,7 +630,8 @@ def _run_isolated(what, arg, timeout=120):
         pytest.fail(f'{what}: an earlier isolated check timed out')
     here = os.path.dirname(os.path.abspath(__file__))
     try:
-        r = subprocess.run([sys.executable, os.path.join(here, 'gpu_isolated.py'), what, arg], capture_output=True, text=True, timeout=timeout)
+        r = subprocess.run([sys.executable, os.path.join(here, 'gpu_isolated.py'), what, arg], capture_output=True, text=True, timeout=timeout,
+                           env=dict(os.environ, **(env or {})))
     except subprocess.TimeoutExpired:
         _ISO_TIMED_OUT.add(what)
         raise
@@ -636,14 +643,17 @@ def test_gather_prefetch_variant_is_bit_identical(arch):
     _run_isolated('gather_prefetch', arch)
 
 
+@pytest.mark.parametrize('math', ['0', '1'])
 @pytest.mark.parametrize('arch', ARCHS)
-def test_kw_bounds_match_reference(arch):
-    _run_isolated('kw_bounds', arch, timeout=180)
+def test_kw_bounds_match_reference(arch, math):
+    """math 0: the dense layers' column blocks on the tensor-core propagation kernel (fp16 x 3), 1: exact-fp32 kernels."""
+    _run_isolated('kw_bounds', arch, timeout=180, env={'GNNB_TEST_MATH': math})
 
 
+@pytest.mark.parametrize('math', ['0', '1'])
 @pytest.mark.parametrize('arch', ARCHS)
-def test_child_bounds_match_reference_update_the_model(arch):
-    _run_isolated('child_bounds', arch, timeout=240)
+def test_child_bounds_match_reference_update_the_model(arch, math):
+    _run_isolated('child_bounds', arch, timeout=240, env={'GNNB_TEST_MATH': math})
 
 
 @pytest.mark.parametrize('arch', ['base', 'deep'])
@@ -651,6 +661,7 @@ def test_frontier_step_is_made_of_its_pieces(arch):
     _run_isolated('frontier_step', arch, timeout=240)
 
 
+@pytest.mark.parametrize('math', ['0', '1'])
 @pytest.mark.parametrize('case', ['odd_shapes', 'deep_narrow'])
-def test_child_bounds_other_network_shapes(case):
-    _run_isolated('child_bounds_shapes', case, timeout=240)
+def test_child_bounds_other_network_shapes(case, math):
+    _run_isolated('child_bounds_shapes', case, timeout=240, env={'GNNB_TEST_MATH': math})
