@@ -534,15 +534,16 @@ def measure_frontier_step(model, workload, dev, world, parents=256, steps=4):
             'host_traffic': 'three counts read back per step (picked, second-pass domains, added); no bounds, masks or scores cross PCIe',
             'lp': 'surrogate (no Gurobi): lower bound = KW / interval bound of the property output, zero duals, primals = activations of the ball centre',
             'child_bounds': {'value': n2 / (cb_ms * 1e-3), 'unit': 'children/s', 'ms_per_call': cb_ms, 'children': n2,
-                             'executed_gflop_per_child': flop / 1e9, 'achieved_tflops_fp32': flop * n2 / (cb_ms * 1e-3) / 1e12,
+                             'executed_gflop_per_child': flop / 1e9, 'achieved_tflops': flop * n2 / (cb_ms * 1e-3) / 1e12,
                              'roofline': {'bound': 'hbm', 'achieved': byts * n2 / (cb_ms * 1e-3) / 1e9, 'peak': peaks['gbs'], 'unit': 'GB/s',
                                           'frac': byts * n2 / (cb_ms * 1e-3) / 1e9 / peaks['gbs'], 'traffic': None,
-                                          'note': 'bytes of the executed schedule (dense layers: fp32 [n, 64] column blocks written and re-read by every '
-                                                  'transposed-propagation and reduction launch), not compulsory bytes; the windowed conv-layer kernel is '
-                                                  'issue-bound (ncu: 79 % of issue slots, no DRAM traffic to speak of, profiles/r03g_ncu_kw_cone.txt)'},
-                             'note': 'bounds part of KWConvGen.update_the_model (plnn/conv_kwinter_gen.py:558-660) for a batch of children: exact-fp32 '
-                                     'KW recursion (windowed kernel for conv layers, transposed propagation on the SIMT kernels for the rest) + '
-                                     'interval pass + masks'}}
+                                          'note': 'bytes of the executed schedule (dense layers: [n, 64] column blocks as 256-byte-per-row tile images written '
+                                                  'and re-read by every transposed-propagation and reduction launch), not compulsory bytes; the windowed '
+                                                  'conv-layer kernel is issue-bound (ncu: 79 % of issue slots, no DRAM traffic to speak of, '
+                                                  'profiles/r03g_ncu_kw_cone.txt)'},
+                             'note': 'bounds part of KWConvGen.update_the_model (plnn/conv_kwinter_gen.py:558-660) for a batch of children: KW recursion '
+                                     '(windowed fp32 kernel for conv layers; the linear layers and the property output as 64-column blocks through the '
+                                     'tensor-core propagation kernel, fp16 x 3) + interval pass + masks'}}
 
 
 
