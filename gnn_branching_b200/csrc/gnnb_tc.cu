@@ -560,8 +560,10 @@ __global__ void __launch_bounds__(128 * NWG, 1) k_tc_update(UpdArgs a) {
 // Registers: 768 threads x 80; with half a row's channels per thread the chain fits (no setmaxnreg needed).
 // Tensor memory: 2 x 128 (propagation accumulators = the chains' A operands) + 2 x 128 (chain accumulators) = 512 columns.
 // Shared memory: chain weights 64 KB (80 KB with the score head) + staging 64 KB (32 KB) + ring 96 KB (112 KB) — all of it.
-// Accumulator b is free for item i + 2 when both chains of item i have completed their last GEMM that reads its A columns
-// (acc_empty[b], 2 arrivals).
+// Accumulator b is free for item i + 2 when both chains of item i have completed their FIRST GEMM, the only one that reads its
+// A columns (acc_empty[b], 2 arrivals): the later A operands live in columns [64, 128) of the chain's own window, which the
+// first epilogue has just consumed.  The chains are software-pipelined by one stage (start_item below): a tile's accumulator
+// wait, conversion and first GEMM issue run inside the last epilogue of the tile before it.
 namespace fz {
 constexpr int PD = 2;                               // subdomains per item = accumulator columns / 64
 constexpr int CW = 2;                               // chain warpgroups = PD
