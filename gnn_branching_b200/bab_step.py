@@ -12,6 +12,14 @@ for the next ``max_B`` domains of the queue at once, and nothing but four intege
     GraphNet.score_frontier            gnnb_score            each child's GNN decision (argmax over its undecided ReLUs)
     DomainQueue.add(children, keep)    gnnb_queue_add        children whose lower bound is still below the decision bound
 
+With ``kw_fallback=True`` the step also carries the reference's threshold rule (:145-203): where the GNN's split improved the
+lower bound by less than ``branching_threshold`` (``(min(lb0, 0) + min(lb1, 0) - 2 lb) / (-2 lb)``), the BaBSR / KW heuristic's
+decision (``gnnb_babsr`` = ``choose_node_conv``) is tried on the same parent — unless that ReLU has already proved ineffective
+``kwbd_threshold`` times — and replaces the GNN's when its children improve the bound more; a KW decision that does worse than
+the GNN's and improves by less than 0.05 is counted as ineffective.  The counters live on the device, per ReLU (the reference
+keeps a dict keyed by "layer-index"); the intercept counter of ``choose_node_conv`` (``icp_score``), which the reference carries
+from one iteration to the next, starts at zero for every parent of a batch.
+
 What is NOT here is the LP: Gurobi is out of scope, so the values the reference takes from the LP solution are
 SURROGATES and the step is labelled as such wherever it is reported — the child's lower bound is the lower bound of the
 property output from the KW / interval pass (valid, but looser than the LP's), its upper bound is the parent's, the GNN's
@@ -41,12 +49,17 @@ class StepStats:
     infeasible: int          # children dropped because their bounds cross (or pin a node to exactly zero)
     added: int               # children put back into the queue
     global_lb: float         # smallest lower bound left in the queue (nan when it is empty)
+    kw_tried: int = 0        # parents whose GNN split improved too little: the KW decision was bounded as well
+    kw_used: int = 0         # ... and won
 
 
 class FrontierStep:
     def __init__(self, model: GraphNet, net: NetSpec, x: torch.Tensor, eps: float, Wp: torch.Tensor, bp: float,
-                 capacity: int = 1 << 16, decision_bound: float = 0.0, device: int = 0):
+                 capacity: int = 1 << 16, decision_bound: float = 0.0, device: int = 0, kw_fallback: bool = False,
+                 branching_threshold: float = 0.2, kwbd_threshold: int = 20, sparsest_layer: int = 0):
         self.model, self.net, self.eps, self.decision_bound = model, net, float(eps), float(decision_bound)
+        self.kw_fallback, self.branching_threshold, self.kwbd_threshold = bool(kw_fallback), float(branching_threshold), int(kwbd_threshold)
+        self.sparsest_layer = int(sparsest_layer)
         self.dev = torch.device('cuda', device)
         self.scorer = model.scorer(device)
         self.scorer.set_network(net, key=net.key)
@@ -67,6 +80,7 @@ class FrontierStep:
         self.prim_pre, self.prim_post = pre, post
         self.prim_out = (post[-1] @ self.Wp.t()).reshape(1) + self.bp
         self._zeros = {}
+        self.ineff_kw = torch.zeros(net.n_hidden, dtype=torch.int32, device=self.dev)      # relu_conv_gnnkwthreshold.py:134 ineff_kw_dc
 
     # ---- seeding ----
     def seed_root(self, lbs: List[torch.Tensor], ubs: List[torch.Tensor]) -> None:
@@ -90,6 +104,9 @@ class FrontierStep:
         lbs, ubs, masks, second = self.scorer.child_bounds(self.x, self.eps, self.Wp.expand(2 * B, -1), self.bp.expand(2 * B),
                                                            [rep(t) for t in parents.lb], [rep(t) for t in parents.ub],
                                                            dec[:, 0], dec[:, 1], choice)
+        kw_tried = kw_used = 0
+        if self.kw_fallback:
+            kw_tried, kw_used = self._kw_fallback(parents, lbs, ubs, masks, second)
         # ReLUs the ancestors fixed stay fixed (their bounds say so already); this child's own split is in `masks` too, because
         # its bound is exactly 0 on the fixed side (conv_kwinter_gen.py:572: relu_mask[decision] = choice)
         mask = torch.cat(masks, dim=1)
@@ -110,7 +127,59 @@ class FrontierStep:
         children = DomainBatch(lower.contiguous(), rep(parents.upper_bound).contiguous(), lbs, ubs, mask, new_dec)
         added = self.queue.add(children, keep=keep)
         glb = self.queue.global_lb if len(self.queue) else float('nan')
-        return StepStats(B, 2 * B, int(second.sum()), int(bad.sum()), added, glb)
+        return StepStats(B, 2 * B, int(second.sum()), int(bad.sum()), added, glb, kw_tried, kw_used)
+
+    # ---- the threshold rule (relu_conv_gnnkwthreshold.py:145-203) ----
+    def _improvement(self, plb: torch.Tensor, lbs, ubs) -> torch.Tensor:
+        """(min(lb0, 0) + min(lb1, 0) - 2 lb) / (-2 lb) per parent from its two children's output bounds; an infeasible child
+        (crossing output bounds) counts as fully resolved (min(., 0) = 0); parents with lb >= 0 need no fallback (1)."""
+        L = self.net.L
+        low = lbs[L + 1].reshape(-1)
+        low = torch.where(low > ubs[L + 1].reshape(-1), torch.zeros_like(low), low).clamp(max=0)
+        imp = (low[0::2] + low[1::2] - 2 * plb) / (-2 * plb)
+        return torch.where(plb < 0, imp, torch.ones_like(imp))
+
+    def _kw_fallback(self, parents: DomainBatch, lbs, ubs, masks, second):
+        """Replaces, in place, the children of the parents whose KW decision beats their GNN decision.  One count is read back
+        (how many parents need the second opinion)."""
+        from .kw_score_conv import babsr_frontier
+        L, dev = self.net.L, self.dev
+        gnn_imp = self._improvement(parents.lower_bound, lbs, ubs)
+        idx = (gnn_imp < self.branching_threshold).nonzero().view(-1)
+        m = int(idx.numel())
+        if m == 0:
+            return 0, 0
+        plb_all = [t[idx] for t in parents.lb]
+        pub_all = [t[idx] for t in parents.ub]
+        pmask = parents.mask[idx]
+        empty = torch.empty(0, device=dev)
+        fr = Frontier(net=self.net, lb=plb_all, ub=pub_all, dual=[], prim_pre=[], prim_post=[], prim_out=empty, primal_input=empty,
+                      Wp=self.Wp.expand(m, -1).contiguous(), bp=self.bp.expand(m).contiguous(), mask=(pmask == -1).float())
+        kw_dec, _, _, _ = babsr_frontier(fr, None, None, self.sparsest_layer, scorer=self.scorer)
+        flat = (self.offsets[kw_dec[:, 0].clamp(min=0).long()] + kw_dec[:, 1].clamp(min=0).long())
+        gnn_dec = parents.decision[idx]
+        ok = (kw_dec[:, 0] >= 0) & (self.ineff_kw[flat] < self.kwbd_threshold) & (kw_dec != gnn_dec).any(dim=1)
+        rep = lambda t: t.repeat_interleave(2, dim=0)
+        choice = torch.arange(2 * m, device=dev, dtype=torch.int32) & 1
+        # parents without a usable KW decision are bounded on their GNN decision again (no second count read back); their result
+        # is discarded below
+        dec = rep(torch.where(ok[:, None], kw_dec, gnn_dec))
+        k_lbs, k_ubs, k_masks, k_second = self.scorer.child_bounds(self.x, self.eps, self.Wp.expand(2 * m, -1), self.bp.expand(2 * m),
+                                                                   [rep(t) for t in plb_all], [rep(t) for t in pub_all],
+                                                                   dec[:, 0], dec[:, 1], choice)
+        kw_imp = self._improvement(parents.lower_bound[idx], k_lbs, k_ubs)
+        use = ok & (kw_imp > gnn_imp[idx])                                                        # :177-190
+        bad_kw = ok & (kw_imp < gnn_imp[idx]) & (kw_imp < 0.05)                                   # :171-176
+        self.ineff_kw.index_add_(0, flat, bad_kw.to(torch.int32))
+        rows = rep(2 * idx) + (torch.arange(2 * m, device=dev) & 1)
+        sel = rep(use)
+        for k in range(1, L + 2):
+            lbs[k][rows] = torch.where(sel[:, None], k_lbs[k], lbs[k][rows])
+            ubs[k][rows] = torch.where(sel[:, None], k_ubs[k], ubs[k][rows])
+        for k in range(L):
+            masks[k][rows] = torch.where(sel[:, None], k_masks[k], masks[k][rows])
+        second[rows] = torch.where(sel, k_second, second[rows])
+        return m, int(use.sum())
 
     # ---- helpers ----
     @staticmethod

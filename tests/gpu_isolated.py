@@ -266,6 +266,51 @@ def check_frontier_step(arch):
         assert st.global_lb >= glb - 1e-6, (st.global_lb, glb)      # children are never looser than their parents
         glb = st.global_lb
     print(f'frontier_step {arch}: queue {len(fs.queue)} domains, {dropped} infeasible children dropped, global lb {glb:.4f}', flush=True)
+    del fs
+    # the threshold rule (relu_conv_gnnkwthreshold.py:145-203) with a threshold nothing passes: the KW decision is bounded for
+    # every parent and wins exactly where its children improve the bound more.  First step against the oracles (BaBSR decision,
+    # child bounds of both decisions, the improvement formula), then batched steps on invariants.
+    from oracle import babsr_oracle as BO
+    fs = FrontierStep(model, net, x, 0.145, wp, bp, capacity=8192, decision_bound=float('inf'), kw_fallback=True, branching_threshold=1e9)
+    fs.seed_root(lbs, ubs)
+    root = fs.queue.pick(1, float('inf'))
+    gdec = root.decision[0].tolist()
+    fs.queue.add(root)
+    st = fs.step(1)
+    assert st.kw_tried == 1 and st.added == 2, st
+    L = net.L
+    from gnn_branching_b200 import Frontier
+    m_cpu = torch.cat([torch.where((lbs[k] < 0) & (ubs[k] > 0), 1.0, 0.0) for k in range(1, L + 1)]).reshape(1, -1)
+    e = torch.empty(0)
+    fr_cpu = Frontier(net=net, lb=[t.reshape(1, -1) for t in lbs], ub=[t.reshape(1, -1) for t in ubs], dual=[], prim_pre=[], prim_post=[],
+                      prim_out=e, primal_input=e, Wp=wp.reshape(1, -1), bp=torch.tensor([bp]), mask=m_cpu)
+    sc_, ic_ = BO.babsr_scores(fr_cpu)
+    kdec = BO.babsr_decide(sc_, ic_, m_cpu, net.hidden_sizes, [0], [0] + list(range(1, L)), 0)[0][0]
+    kdec = [int(kdec[0]), int(kdec[1])]
+
+    def improvement(dec):
+        lows = []
+        for side in (0, 1):
+            ol, ou, _ = KW.child_bounds(net, x, 0.145, wp, bp, lbs, ubs, dec, side)
+            lows.append(min(float(ol[L + 1]), 0.0))
+        plb = float(lbs[L + 1])
+        return (lows[0] + lows[1] - 2 * plb) / (-2 * plb)
+    gi, ki = improvement(gdec), improvement(kdec)
+    want = kdec if (kdec != gdec and ki > gi) else gdec
+    assert st.kw_used == int(want == kdec and kdec != gdec), (st, gdec, kdec, gi, ki)
+    kids = fs.queue.pick(2, float('inf'))
+    sides = {0 if float(kids.ub[want[0] + 1][i, want[1]]) == 0.0 else (1 if float(kids.lb[want[0] + 1][i, want[1]]) == 0.0 else -1) for i in range(2)}
+    assert sides == {0, 1}, ('the children are not the two sides of the winning decision', want, gdec, kdec)
+    fs.queue.add(kids)
+    glb, size, tried, used = fs.queue.global_lb, 2, 0, 0
+    for B in (2, 4, 8, 16, 32, 64):
+        st = fs.step(B)
+        size += st.added - st.picked
+        tried += st.kw_tried; used += st.kw_used
+        assert st.kw_tried == st.picked and st.kw_used <= st.kw_tried and len(fs.queue) == size, (st, size)
+        assert st.global_lb >= glb - 1e-6
+        glb = st.global_lb
+    print(f'frontier_step {arch} with the KW threshold rule: root gnn {gdec} ({gi:.4f}) kw {kdec} ({ki:.4f}); {used} of {tried} parents took the KW decision', flush=True)
 
 
 if __name__ == '__main__':
