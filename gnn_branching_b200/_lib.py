@@ -18,7 +18,7 @@ EXPORTS = ['gnnb_create', 'gnnb_destroy', 'gnnb_set_gnn_weights', 'gnnb_set_netw
            'gnnb_get_option', 'gnnb_score', 'gnnb_score_winners', 'gnnb_check', 'gnnb_launch_count', 'gnnb_last_error',
            'gnnb_debug_snapshot', 'gnnb_abi_version', 'gnnb_profile_read', 'gnnb_profile_reset', 'gnnb_babsr',
            'gnnb_score_grad', 'gnnb_get_gradients', 'gnnb_get_gnn_weights', 'gnnb_adam_step', 'gnnb_adam_reset',
-           'gnnb_kw_bounds', 'gnnb_child_bounds', 'gnnb_queue_create', 'gnnb_queue_destroy', 'gnnb_queue_add', 'gnnb_queue_pick', 'gnnb_queue_prune', 'gnnb_queue_stats']
+           'gnnb_kw_bounds', 'gnnb_child_bounds', 'gnnb_root_bounds', 'gnnb_queue_create', 'gnnb_queue_destroy', 'gnnb_queue_add', 'gnnb_queue_pick', 'gnnb_queue_prune', 'gnnb_queue_stats']
 
 _fp = C.POINTER(C.c_float)
 _fpp = C.POINTER(_fp)
@@ -82,6 +82,7 @@ def load() -> C.CDLL:
     lib.gnnb_kw_bounds.argtypes = [vp, C.c_int32, _fp, C.c_float, _fp, _fp, _fpp, _fpp, _fpp, _fpp, vp]
     lib.gnnb_child_bounds.argtypes = [vp, C.c_int32, _fp, C.c_float, _fp, _fp, _fpp, _fpp, _ip, _ip, _ip, _fpp, _fpp,
                                       C.POINTER(C.POINTER(C.c_int8)), _ip, vp]
+    lib.gnnb_root_bounds.argtypes = [vp, C.c_int32, _fp, C.c_float, _fp, _fp, _fpp, _fpp, C.POINTER(C.POINTER(C.c_int8)), _ip, vp]
     lib.gnnb_queue_create.argtypes = [vp, C.c_int64, C.POINTER(vp)]
     lib.gnnb_queue_destroy.argtypes = [vp]
     lib.gnnb_queue_destroy.restype = None

@@ -83,8 +83,11 @@ class FrontierStep:
         self.ineff_kw = torch.zeros(net.n_hidden, dtype=torch.int32, device=self.dev)      # relu_conv_gnnkwthreshold.py:134 ineff_kw_dc
 
     # ---- seeding ----
-    def seed_root(self, lbs: List[torch.Tensor], ubs: List[torch.Tensor]) -> None:
-        """Put the root domain into the queue: its bounds (L + 2 flat tensors), mask from the bounds, GNN decision."""
+    def seed_root(self, lbs: List[torch.Tensor] = None, ubs: List[torch.Tensor] = None) -> None:
+        """Put the root domain into the queue: its bounds (L + 2 flat tensors; computed on the device by ``gnnb_root_bounds``, the
+        bounds part of ``build_the_model``, when not given), mask from the bounds, GNN decision."""
+        if lbs is None:
+            lbs, ubs, _, _ = self.scorer.root_bounds(self.x, self.eps, self.Wp, self.bp, with_mask=False)
         lb = [t.reshape(1, -1).to(self.dev, torch.float32) for t in lbs]
         ub = [t.reshape(1, -1).to(self.dev, torch.float32) for t in ubs]
         mask = torch.cat([self._bab_mask(lb[k], ub[k]) for k in range(1, self.net.L + 1)], dim=1)

@@ -1305,6 +1305,30 @@ int gnnb_child_bounds(gnnb_ctx* ctx, int32_t B, const float* x, float eps, const
     return GNNB_OK;
 }
 
+int gnnb_root_bounds(gnnb_ctx* ctx, int32_t B, const float* x, float eps, const float* wp, const float* bp, float* const* out_lb,
+                     float* const* out_ub, int8_t* const* out_mask, int32_t* second_pass, void* stream) {
+    if (!ctx || !x || !wp || !bp || !out_lb || !out_ub) return fail(ctx, GNNB_ERR_INVALID, "null argument");
+    if (!ctx->have_net) return fail(ctx, GNNB_ERR_STATE, "gnnb_set_network must be called first");
+    if (B < 1) return fail(ctx, GNNB_ERR_INVALID, "need at least one domain");
+    const int L = (int)ctx->layers.size();
+    for (int k = 0; k <= L + 1; ++k) if (!out_lb[k] || !out_ub[k]) return fail(ctx, GNNB_ERR_INVALID, "null bounds array");
+    if (out_mask)
+        for (int k = 0; k < L; ++k) if (!out_mask[k]) return fail(ctx, GNNB_ERR_INVALID, "null mask array");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ctx->kw_iscratch_cap < B) {
+        if (ctx->kw_iscratch) { CU(cudaStreamSynchronize(st)); cudaFree(ctx->kw_iscratch); ctx->kw_iscratch = nullptr; ctx->kw_iscratch_cap = 0; }
+        CU(cudaMalloc(&ctx->kw_iscratch, (3 * (size_t)B + 1) * sizeof(int32_t)));
+        ctx->kw_iscratch_cap = B;
+    }
+    std::string err;
+    const KwTc tc{&ctx->plan_kw, &ctx->rowmap};
+    const int rc = root_bounds(ctx->layers, ctx->n, B, x, eps, wp, bp, out_lb, out_ub, out_mask, second_pass, ctx->kw_iscratch,
+                               ctx->math == GNNB_MATH_TC_FP16X3 ? &tc : nullptr, &ctx->kw_ws, &ctx->kw_ws_cap, st, &ctx->launches, &err);
+    if (rc != GNNB_OK) return fail(ctx, rc, err);
+    return GNNB_OK;
+}
+
 int gnnb_check(gnnb_ctx* ctx, void* stream, int64_t* nan_count) {
     if (!ctx) return GNNB_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));

@@ -218,6 +218,11 @@ int child_bounds(const std::vector<LayerDev>& layers, const std::vector<int>& n,
                  const int32_t* choice, float* const* out_lb, float* const* out_ub, int8_t* const* out_mask, int32_t* second_pass,
                  int32_t* iscratch, const KwTc* tc, float** ws, size_t* ws_cap, cudaStream_t st, int64_t* launches, std::string* err);
 
+// bounds part of build_the_model for B root domains (KW bounds, interval pass from the input box, KW pass where a hidden layer moved)
+int root_bounds(const std::vector<LayerDev>& layers, const std::vector<int>& n, int B, const float* x, float eps, const float* wp, const float* bp,
+                float* const* out_lb, float* const* out_ub, int8_t* const* out_mask, int32_t* second_pass, int32_t* iscratch, const KwTc* tc,
+                float** ws, size_t* ws_cap, cudaStream_t st, int64_t* launches, std::string* err);
+
 // ---- device helpers ---------------------------------------------------------------------------
 // compute_ratio of graph_conv.py:499-514 in the reference's operation order (IEEE division, no fast-math)
 struct Ratio { float r0, r1, beta, amb; };

@@ -168,12 +168,23 @@ __device__ __forceinline__ bool interval_gain_counts(float better, float current
     return fabsf(better - current) > 1e-6f * fmaxf(1.0f, fabsf(current));
 }
 
+// the tighter of the interval and the current bound, and the note for the second KW pass.  Child domains (root = 0): changed = 1
+// when a hidden layer's bound moved (conv_kwinter_gen.py:652).  Root (build_the_model, :262-267): changed = the FIRST hidden
+// layer whose bound moved by more than 1e-4 (the reference's test), kept as a minimum over the nodes.
+__device__ __forceinline__ void interval_commit(float lo, float hi, float* lb, float* ub, int32_t* changed, int layer, bool hidden, int root) {
+    bool ch = false;
+    const float l0 = *lb, u0 = *ub;
+    if (lo > l0) { ch |= root ? (lo - l0 > 1e-4f) : interval_gain_counts(lo, l0); *lb = lo; }
+    if (hi < u0) { ch |= root ? (u0 - hi > 1e-4f) : interval_gain_counts(hi, u0); *ub = hi; }
+    if (ch && hidden) { if (root) atomicMin(changed, layer); else *changed = 1; }
+}
+
 // interval bounds of one layer from the post-ReLU box of the layer in front of it, intersected with the current bounds
 // (plnn/conv_kwinter_gen.py:594-641: W+ l + W- u + b / W+ u + W- l + b); only for domains whose split lies in front of the
 // layer; changed[b] is raised when a HIDDEN layer's bound moved (:652: only then the KW pass is repeated)
 __global__ void __launch_bounds__(256) k_interval_conv(LayerDev Ld, const float* __restrict__ lb_in, const float* __restrict__ ub_in,
                                                        float* __restrict__ lb, float* __restrict__ ub, int B, int layer,
-                                                       const int32_t* __restrict__ keep_upto, int32_t* __restrict__ changed) {
+                                                       const int32_t* __restrict__ keep_upto, int32_t* __restrict__ changed, int root) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)B * Ld.n_out) return;
     const int b = (int)(i / Ld.n_out), node = (int)(i % Ld.n_out);
@@ -191,22 +202,20 @@ __global__ void __launch_bounds__(256) k_interval_conv(LayerDev Ld, const float*
                 if (xx < 0 || xx >= Ld.w_in) continue;
                 const float w = Ld.weight[((co * Ld.c_in + ci) * Ld.ksize + ky) * Ld.ksize + kx];
                 const int at = (ci * Ld.h_in + yy) * Ld.w_in + xx;
-                const float l = fmaxf(li[at], 0.f), u = fmaxf(ui[at], 0.f);
+                const bool raw = root && layer == 1;                     // the first layer reads the input box itself
+                const float l = raw ? li[at] : fmaxf(li[at], 0.f), u = raw ? ui[at] : fmaxf(ui[at], 0.f);
                 lo = fmaf(w, w > 0.f ? l : u, lo);
                 hi = fmaf(w, w > 0.f ? u : l, hi);
             }
         }
-    bool ch = false;
-    if (lo > lb[i]) { ch |= interval_gain_counts(lo, lb[i]); lb[i] = lo; }
-    if (hi < ub[i]) { ch |= interval_gain_counts(hi, ub[i]); ub[i] = hi; }
-    if (ch) changed[b] = 1;
+    interval_commit(lo, hi, lb + i, ub + i, changed + b, layer, true, root);
 }
 
 // linear layer (and, with per-domain weights wp / bias bp, the property output): one warp per (domain, output)
 __global__ void __launch_bounds__(256) k_interval_linear(const float* __restrict__ W, const float* __restrict__ bias, int64_t w_dom_stride,
                                                          int n_in, int n_out, const float* __restrict__ lb_in, const float* __restrict__ ub_in,
                                                          float* __restrict__ lb, float* __restrict__ ub, int B, int layer, bool hidden,
-                                                         const int32_t* __restrict__ keep_upto, int32_t* __restrict__ changed) {
+                                                         const int32_t* __restrict__ keep_upto, int32_t* __restrict__ changed, int root) {
     const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (wid >= (int64_t)B * n_out) return;
@@ -217,7 +226,8 @@ __global__ void __launch_bounds__(256) k_interval_linear(const float* __restrict
     const float* ui = ub_in + (int64_t)b * n_in;
     float lo = 0.f, hi = 0.f;
     for (int i = lane; i < n_in; i += 32) {
-        const float wv = w[i], l = fmaxf(li[i], 0.f), u = fmaxf(ui[i], 0.f);
+        const bool raw = root && layer == 1;
+        const float wv = w[i], l = raw ? li[i] : fmaxf(li[i], 0.f), u = raw ? ui[i] : fmaxf(ui[i], 0.f);
         lo = fmaf(wv, wv > 0.f ? l : u, lo);
         hi = fmaf(wv, wv > 0.f ? u : l, hi);
     }
@@ -225,10 +235,7 @@ __global__ void __launch_bounds__(256) k_interval_linear(const float* __restrict
     if (lane != 0) return;
     const float bv = w_dom_stride ? bias[b] : bias[o];
     lo += bv; hi += bv;
-    bool ch = false;
-    if (lo > lb[wid]) { ch |= interval_gain_counts(lo, lb[wid]); lb[wid] = lo; }
-    if (hi < ub[wid]) { ch |= interval_gain_counts(hi, ub[wid]); ub[wid] = hi; }
-    if (ch && hidden) changed[b] = 1;
+    interval_commit(lo, hi, lb + wid, ub + wid, changed + b, layer, hidden, root);
 }
 
 // the domains whose hidden bounds moved, in index order (one block; B is a frontier batch, thousands at most)
@@ -251,6 +258,16 @@ __global__ void __launch_bounds__(1024) k_collect_changed(const int32_t* __restr
         __syncthreads();
     }
     if (threadIdx.x == 0) *count = base;
+}
+
+// root: first changed layer (or INT_MAX) -> keep_upto (that layer stays as the interval pass left it; nothing to redo: L) and the
+// 0 / 1 flag of the domains that need the KW pass
+__global__ void k_root_prepare(int32_t* __restrict__ changed, int32_t* __restrict__ keep, int B, int L) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int c = changed[b];
+    keep[b] = c <= L ? c : L;
+    changed[b] = c <= L ? 1 : 0;
 }
 
 // ReLU phase of every hidden node from its pre-activation bounds, in the BaB convention (plnn/conv_kwinter_gen.py:696-713:
@@ -773,13 +790,13 @@ int child_bounds(const std::vector<LayerDev>& layers, const std::vector<int>& n,
         if (k <= L) {
             const LayerDev& Ld = layers[k - 1];
             if (Ld.kind == GNNB_LAYER_CONV)
-                k_interval_conv<<<blocks_of((int64_t)B * n[k], 256), 256, 0, st>>>(Ld, out_lb[k - 1], out_ub[k - 1], out_lb[k], out_ub[k], B, k, keep, changed);
+                k_interval_conv<<<blocks_of((int64_t)B * n[k], 256), 256, 0, st>>>(Ld, out_lb[k - 1], out_ub[k - 1], out_lb[k], out_ub[k], B, k, keep, changed, 0);
             else
                 k_interval_linear<<<blocks_of((int64_t)B * n[k] * 32, 256), 256, 0, st>>>(Ld.weight, Ld.bias_node, 0, n[k - 1], n[k], out_lb[k - 1], out_ub[k - 1],
-                                                                                           out_lb[k], out_ub[k], B, k, true, keep, changed);
+                                                                                           out_lb[k], out_ub[k], B, k, true, keep, changed, 0);
         } else {
             k_interval_linear<<<blocks_of((int64_t)B * 32, 256), 256, 0, st>>>(wp, bp, n[L], n[L], 1, out_lb[L], out_ub[L], out_lb[k], out_ub[k], B, k, false,
-                                                                                keep, changed);
+                                                                                keep, changed, 0);
         }
         ++*launches;
     }
@@ -801,6 +818,61 @@ int child_bounds(const std::vector<LayerDev>& layers, const std::vector<int>& n,
         }
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { *err = std::string("child bounds: ") + cudaGetErrorString(e); return GNNB_ERR_CUDA; }
+    return GNNB_OK;
+}
+
+// Bounds part of build_the_model (plnn/conv_kwinter_gen.py:199-270) for B root domains: KW bounds (init_kw_bounds), intersected
+// layer by layer with interval bounds (the first layer from the input box itself); where a hidden layer moved by more than
+// 1e-4, one KW pass from the first such layer with the intersected bounds provided.  Same arrays and scratch as child_bounds.
+int root_bounds(const std::vector<LayerDev>& layers, const std::vector<int>& n, int B, const float* x, float eps, const float* wp, const float* bp,
+                float* const* out_lb, float* const* out_ub, int8_t* const* out_mask, int32_t* second_pass, int32_t* iscratch, const KwTc* tc,
+                float** ws, size_t* ws_cap, cudaStream_t st, int64_t* launches, std::string* err) {
+    const int L = (int)layers.size();
+    if (L > KW_MAX_LAYERS) { *err = "root bounds: too many layers"; return GNNB_ERR_UNSUPPORTED; }
+    int32_t* keep = iscratch;
+    int32_t* changed = iscratch + B;
+    int32_t* list = iscratch + 2 * (size_t)B;
+    int32_t* count = iscratch + 3 * (size_t)B;
+    int rc = kw_bounds(layers, n, B, x, eps, wp, bp, nullptr, nullptr, out_lb, out_ub, tc, ws, ws_cap, st, launches, err);
+    if (rc != GNNB_OK) return rc;
+    cudaMemsetAsync(keep, 0, (size_t)B * sizeof(int32_t), st);                 // every layer takes part in the interval pass
+    cudaMemsetAsync(changed, 0x7f, (size_t)B * sizeof(int32_t), st);           // "no layer moved"
+    for (int k = 1; k <= L + 1; ++k) {
+        if (k <= L) {
+            const LayerDev& Ld = layers[k - 1];
+            if (Ld.kind == GNNB_LAYER_CONV)
+                k_interval_conv<<<blocks_of((int64_t)B * n[k], 256), 256, 0, st>>>(Ld, out_lb[k - 1], out_ub[k - 1], out_lb[k], out_ub[k], B, k, keep, changed, 1);
+            else
+                k_interval_linear<<<blocks_of((int64_t)B * n[k] * 32, 256), 256, 0, st>>>(Ld.weight, Ld.bias_node, 0, n[k - 1], n[k], out_lb[k - 1], out_ub[k - 1],
+                                                                                           out_lb[k], out_ub[k], B, k, true, keep, changed, 1);
+        } else {
+            k_interval_linear<<<blocks_of((int64_t)B * 32, 256), 256, 0, st>>>(wp, bp, n[L], n[L], 1, out_lb[L], out_ub[L], out_lb[k], out_ub[k], B, k, false,
+                                                                                keep, changed, 1);
+        }
+        ++*launches;
+    }
+    k_root_prepare<<<blocks_of(B, 256), 256, 0, st>>>(changed, keep, B, L);
+    k_collect_changed<<<1, 1024, 0, st>>>(changed, B, list, count);
+    *launches += 2;
+    int32_t h_count = 0;
+    cudaMemcpyAsync(&h_count, count, sizeof h_count, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) { *err = std::string("root bounds: ") + cudaGetErrorString(cudaGetLastError()); return GNNB_ERR_CUDA; }
+    if (h_count > 0) {
+        const float* pl[KW_MAX_LAYERS + 1];
+        const float* pu[KW_MAX_LAYERS + 1];
+        for (int k = 1; k <= L + 1; ++k) { pl[k - 1] = out_lb[k]; pu[k - 1] = out_ub[k]; }
+        rc = kw_pass(layers, n, B, x, eps, wp, bp, pl, pu, out_lb, out_ub, 2, list, h_count, keep, tc, ws, ws_cap, st, launches, err);
+        if (rc != GNNB_OK) return rc;
+    }
+    if (second_pass) cudaMemcpyAsync(second_pass, changed, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
+    if (out_mask)
+        for (int k = 1; k <= L; ++k) {
+            const int64_t total = (int64_t)B * n[k];
+            k_mask_from_bounds<<<blocks_of(total, 256), 256, 0, st>>>(out_lb[k], out_ub[k], out_mask[k - 1], total);
+            ++*launches;
+        }
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { *err = std::string("root bounds: ") + cudaGetErrorString(e); return GNNB_ERR_CUDA; }
     return GNNB_OK;
 }
 

@@ -352,6 +352,37 @@ class Scorer:
         del keep, k3, k4
         return lbs, ubs
 
+    def root_bounds(self, x: torch.Tensor, eps: float, Wp: torch.Tensor, bp: torch.Tensor, with_mask: bool = True):
+        """Bounds of B root domains — the bounds part of ``KWConvGen.build_the_model`` (plnn/conv_kwinter_gen.py:199-270):
+        KW bounds intersected with interval bounds, and a KW pass where that moved a hidden layer.  ``x`` [B, n0] (or [n0]),
+        ``Wp`` [B, n_L], ``bp`` [B].  Returns (lbs, ubs, masks, second_pass) like ``child_bounds``."""
+        if self.net is None:
+            raise RuntimeError('set_network first')
+        net, L = self.net, self.net.L
+        dev = torch.device('cuda', self.device)
+        sizes = [net.n0] + net.hidden_sizes + [1]
+        Wp = Wp.to(dev, torch.float32).reshape(-1, sizes[L]).contiguous()
+        B = int(Wp.shape[0])
+        x = x.to(dev, torch.float32).reshape(-1, net.n0)
+        x = (x.expand(B, net.n0) if x.shape[0] == 1 else x).contiguous()
+        bp = bp.to(dev, torch.float32).reshape(B).contiguous()
+        lbs = [torch.empty(B, n, dtype=torch.float32, device=dev) for n in sizes]
+        ubs = [torch.empty(B, n, dtype=torch.float32, device=dev) for n in sizes]
+        masks = [torch.empty(B, n, dtype=torch.int8, device=dev) for n in sizes[1:L + 1]] if with_mask else None
+        second = torch.empty(B, dtype=torch.int32, device=dev)
+        olb, k3 = _lib.fptr_array(lbs)
+        oub, k4 = _lib.fptr_array(ubs)
+        mptr = None
+        if with_mask:
+            marr = (C.POINTER(C.c_int8) * L)(*[C.cast(m.data_ptr(), C.POINTER(C.c_int8)) for m in masks])
+            mptr = C.cast(marr, C.POINTER(C.POINTER(C.c_int8)))
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            self._ok(self.lib.gnnb_root_bounds(self.h, B, _lib.fptr(x), float(eps), _lib.fptr(Wp), _lib.fptr(bp), olb, oub, mptr,
+                                               C.cast(second.data_ptr(), C.POINTER(C.c_int32)), C.c_void_p(stream)))
+        del k3, k4
+        return lbs, ubs, masks, second
+
     def child_bounds(self, x: torch.Tensor, eps: float, Wp: torch.Tensor, bp: torch.Tensor, parent_lb, parent_ub,
                      dec_layer: torch.Tensor, dec_index: torch.Tensor, choice: torch.Tensor, with_mask: bool = True):
         """Bounds of B child domains — the bounds part of ``KWConvGen.update_the_model`` (plnn/conv_kwinter_gen.py:558-660),

@@ -236,6 +236,15 @@ int gnnb_kw_bounds(gnnb_ctx* ctx, int32_t B, const float* x, float eps, const fl
                    const float* const* provided_lb, const float* const* provided_ub, float* const* out_lb,
                    float* const* out_ub, void* stream);
 
+/* Bounds of B root domains: the bounds part of KWConvGen.build_the_model(input_domain, x, ball_eps, bounded)
+ * (plnn/conv_kwinter_gen.py:199-270) — init_kw_bounds, intersected layer by layer with interval bounds (the first layer from
+ * the input box x -+ eps), and, for the domains where a hidden layer moved by more than 1e-4, update_kw_bounds from the first
+ * such layer (:262-267).  Arrays as in gnnb_child_bounds (DEVICE pointers; out_mask and second_pass may be NULL).
+ * Synchronises `stream` once. */
+int gnnb_root_bounds(gnnb_ctx* ctx, int32_t B, const float* x, float eps, const float* wp, const float* bp,
+                     float* const* out_lb, float* const* out_ub, int8_t* const* out_mask, int32_t* second_pass,
+                     void* stream);
+
 /* Bounds of B child domains: the bounds part of KWConvGen.update_the_model(relu_mask, pre_lb_all, pre_ub_all, decision,
  * choice) (plnn/conv_kwinter_gen.py:558-660), i.e. update_kw_bounds (plnn/dual_network_linear_approximation.py:296-439) with
  * the decided ReLU fixed — layers up to the split keep the parent's bounds, later layers get KW bounds intersected with the

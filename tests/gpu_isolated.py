@@ -126,6 +126,16 @@ def check_child_bounds(arch):
     def err(a, b):
         return float((a.reshape(-1).cpu() - b.reshape(-1)).abs().max()) / max(1.0, float(b.abs().max()))
 
+    # the root first: gnnb_root_bounds against the bounds the reference's build_the_model had computed when it reached Gurobi
+    # (KW bounds, interval pass from the input box, KW pass from the first layer that moved by more than 1e-4: layer 2 on all
+    # three nets)
+    rl, ru, rmask, rsecond = sc.root_bounds(x, 0.145, wp.reshape(1, -1), torch.tensor([bp]))
+    torch.cuda.synchronize()
+    gl0, gu0 = get(0)
+    for k in range(L + 2):
+        e = max(err(rl[k][0], gl0[k]), err(ru[k][0], gu0[k]))
+        assert e <= 5e-5, ('root', k, e)
+    assert int(rsecond[0]) == 1, 'the reference repeats the KW pass at the root of this net (initial kw: change_idx at 3)'
     # largest interval gain on a hidden layer after the first KW pass, per case (CPU, oracle pieces)
     from oracle import kw_bounds_oracle as KW
     gains = {}
