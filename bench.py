@@ -576,7 +576,8 @@ def roofline_of(net, fr, m, n_domains, world, scorer, peaks):
                        'note': 'fp32 accuracy needs 3 fp16 MMA passes per product: the tensor ceiling is 1/3 of the bf16 peak'}
     try:      # DRAM bytes per launch of that kernel class from the committed ncu --set full capture, scaled to this run's wave size
         kt = json.load(open(os.path.join(ROOT, 'profiles', 'kernel_traffic.json')))
-        r['traffic'] = kt[r['kernel_class']]['dram_bytes_per_launch_per_subdomain'] * min(fr.B, scorer.get_option('workspace_domains'))
+        wave = min(fr.B, scorer.get_option('chunk') or 1024)          # subdomains per launch (gnnb_api.cu: waves of `chunk`, default 1 024)
+        r['traffic'] = kt[r['kernel_class']]['dram_bytes_per_launch_per_subdomain'] * wave
         r['traffic_source'] = kt['_source']
     except (OSError, ValueError, KeyError):
         r['traffic'] = None
@@ -812,7 +813,7 @@ def main():
             'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'strong' if strong else 'weak', 'vs_baseline': None,
             'dtype': 'fp16x3 (fp32 accumulate)' if math_mode == 'tc' else 'f32', 'data': 'synthetic',
             'config': {'workload': wl_name, 'gnn': 'GraphNet(T=2,p=64)', 'weights': args.weights, 'math': math_mode,
-                       'chunk': scorer.get_option('workspace_domains'), 'fuse': scorer.get_option('fuse'),
+                       'chunk': min(B, scorer.get_option('chunk') or 1024), 'fuse': scorer.get_option('fuse'),
                        'l2': f'{n_fronts} frontier(s) of {B} subdomains used alternately; inputs + per-wave workspace exceed the 126 MB L2',
                        'sharding': f'{world} ranks x {B} subdomains, winners all-gathered (8 B/subdomain)'},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cb,

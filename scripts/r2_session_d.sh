@@ -6,7 +6,7 @@ timeout 900 python bench.py > $O/bench_default.json 2> $O/bench_default.err; ech
 tail -c 600 $O/bench_default.err
 python - <<'PY'
 import json
-d=json.loads(open('gpurun_out/r03o/bench_default.json').read().strip().splitlines()[-1])
+d=json.loads(open("gpurun_out/'+os.environ.get("TAG","r03o")+'/bench_default.json").read().strip().splitlines()[-1])
 print('value',round(d['value']),'e2e',round(d['e2e']['value']),'wide',d['wide'].get('value'),d['wide'].get('e2e',{}).get('value'),'deep',d['deep'].get('value'),d['deep'].get('e2e',{}).get('value'))
 print('step',json.dumps(d['frontier_step'])[:1500])
 PY
