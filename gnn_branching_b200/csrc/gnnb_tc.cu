@@ -816,6 +816,10 @@ __device__ __forceinline__ void fused_body(const FusedArgs& fa) {
         const uint32_t idesc = (1u << 4) | (1u << 16) | ((uint32_t)(PD * 64 >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
         uint32_t t = 0, it = 0, slot = 0, ph = 0;
         const int group = fa.mma_group;
+        // operand descriptors of ring stage 0; stage s adds s * STAGE / 16 to the 14-bit address field (the whole ring lies below
+        // 256 KB, so the field never carries): one add per descriptor and K step instead of rebuilding four descriptors
+        const uint64_t d_a_hi = make_desc_nosw(ring, NB_PIECE, 128u), d_a_lo = make_desc_nosw(ring + W_KS / 2, NB_PIECE, 128u);
+        const uint64_t d_b_hi = make_desc_mn(ring + W_KS, B_DOM), d_b_lo = make_desc_mn(ring + W_KS + B_PLANE, B_DOM);
         uint32_t lag_slot0 = 0, lag_slot1 = 0, lag_ph0 = 0, lag_ph1 = 0;       // last step of the group before the previous one / of the previous one
         bool have_lag = false, have_prev = false;
 #ifdef GNNB_TRACE
@@ -850,9 +854,8 @@ __device__ __forceinline__ void fused_body(const FusedArgs& fa) {
                     mbar_wait(smem_u32(&tl->full[slot]), ph);
                     FTR_END(t_b);
                     tc_fence_after();
-                    const uint32_t sa = ring + slot * STAGE, sb = sa + W_KS;
-                    const uint64_t a_hi = make_desc_nosw(sa, NB_PIECE, 128u), a_lo = make_desc_nosw(sa + W_KS / 2, NB_PIECE, 128u);
-                    const uint64_t b_hi = make_desc_mn(sb, B_DOM), b_lo = make_desc_mn(sb + B_PLANE, B_DOM);
+                    const uint64_t soff = (uint64_t)(slot * (STAGE >> 4));
+                    const uint64_t a_hi = d_a_hi + soff, a_lo = d_a_lo + soff, b_hi = d_b_hi + soff, b_lo = d_b_lo + soff;
                     if (elect_one()) {
                         umma(d, a_hi, b_hi, idesc, accum);               // Wh Mh
                         umma(d, a_lo, b_hi, idesc, 1u);                  // Wl Mh
