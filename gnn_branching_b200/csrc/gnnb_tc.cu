@@ -885,6 +885,11 @@ __device__ __forceinline__ void fused_body(const FusedArgs& fa) {
         //      commit-group-tracked; L2 prefetches share the budget; the rate scales with the number of warps), so the six warps
         //      work on six different stages: 48 KB in flight ----
         const int gw = warp - GATHER_WARP0;
+        // A gather warp may run at most one revolution of the ring ahead of the others: it waits for "the previous use of my stage
+        // has been consumed" by the PARITY of that use, and a warp that skipped a whole revolution would read the parity of the use
+        // before as its own (measured the hard way: seven warps on a six-stage ring arrive twice on one `full` barrier and fault).
+        // So never more owners than stages.
+        const int GW = GATHER_WARPS < NS ? GATHER_WARPS : NS;
         const unsigned char* mu_bytes = reinterpret_cast<const unsigned char*>(fa.mu_in);
 #ifdef GNNB_TRACE
         long long g_wait = 0, g_all = clock64();
@@ -898,7 +903,7 @@ __device__ __forceinline__ void fused_body(const FusedArgs& fa) {
                 const uint32_t slot_ = slot, ph_ = ph;
                 const bool mine = turn == gw;
                 if (++slot == (uint32_t)NS) { slot = 0; ph ^= 1u; }
-                if (++turn == GATHER_WARPS) turn = 0;
+                if (++turn == GW) turn = 0;
                 if (!mine) continue;
                 const int idx = __ldg(plan.ks_rows + (size_t)ks * 16 + (lane & 15));      // issued before the wait below
 #ifdef GNNB_TRACE
