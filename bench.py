@@ -539,8 +539,8 @@ def measure_frontier_step(model, workload, dev, world, parents=256, steps=4):
                                           'frac': byts * n2 / (cb_ms * 1e-3) / 1e9 / peaks['gbs'], 'traffic': None,
                                           'note': 'bytes of the executed schedule (dense layers: [n, 64] column blocks as 256-byte-per-row tile images written '
                                                   'and re-read by every transposed-propagation and reduction launch), not compulsory bytes; the windowed '
-                                                  'conv-layer kernel is issue-bound (ncu: 79 % of issue slots, no DRAM traffic to speak of, '
-                                                  'profiles/r03g_ncu_kw_cone.txt)'},
+                                                  'conv-layer kernel is issue-bound (ncu: 72 % of issue slots, no DRAM traffic to speak of, '
+                                                  'profiles/r03t_ncu_kw_cone.txt)'},
                              'note': 'bounds part of KWConvGen.update_the_model (plnn/conv_kwinter_gen.py:558-660) for a batch of children: KW recursion '
                                      '(windowed fp32 kernel for conv layers; the linear layers and the property output as 64-column blocks through the '
                                      'tensor-core propagation kernel, fp16 x 3) + interval pass + masks'}}
