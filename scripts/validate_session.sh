@@ -1,4 +1,5 @@
 #!/bin/bash
+# Full validation on one GPU (under gpurun): the whole GPU test suite, then the default bench line.  TAG=<name> bash scripts/validate_session.sh
 set -u
 export TAG=${TAG:-r03o}; O=gpurun_out/$TAG; mkdir -p $O
 timeout 1500 python -m pytest tests -m gpu -x -q > $O/pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest.log
