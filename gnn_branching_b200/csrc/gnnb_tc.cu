@@ -899,6 +899,13 @@ __device__ __forceinline__ void fused_body(const FusedArgs& fa) {
         for (ItemCursor cur(rank, nranks, ntiles, npairs); cur.valid(); cur.next()) {
             const int ks0 = __ldg(plan.tile_ks0 + cur.tile), ks1 = __ldg(plan.tile_ks0 + cur.tile + 1);
             const int dm0 = cur.pair * PD;
+            // per item: this lane's 16-byte column of the two subdomains' mu images, and what a copy from them reads (0 = zero fill:
+            // the second subdomain of an odd batch).  Per row only its byte offset inside a subdomain's image is left to add: slot s
+            // sits in tile s >> 7 (32 KB: hi plane, lo plane) at row s & 127 of 128 bytes
+            const uint32_t jp = (uint32_t)(lane & 7);               // physical 16-byte chunk of the row in the mu image
+            const unsigned char* base0 = mu_bytes + (int64_t)dm0 * (plan.nslots_in >> 7) * (int64_t)ABUF + jp * 16u;
+            const uint32_t sz0 = dm0 < a.Bc ? 16u : 0u, sz1 = dm0 + 1 < a.Bc ? 16u : 0u;
+            const unsigned char* base1 = sz1 ? base0 + (int64_t)(plan.nslots_in >> 7) * (int64_t)ABUF : base0;      // (a zero-fill copy still names an address)
             for (int ks = ks0; ks < ks1; ++ks) {
                 const uint32_t slot_ = slot, ph_ = ph;
                 const bool mine = turn == gw;
@@ -906,6 +913,7 @@ __device__ __forceinline__ void fused_body(const FusedArgs& fa) {
                 if (++turn == GW) turn = 0;
                 if (!mine) continue;
                 const int idx = __ldg(plan.ks_rows + (size_t)ks * 16 + (lane & 15));      // issued before the wait below
+                const int off = idx < 0 ? -1 : (idx << 7) + ((idx >> 7) << 14);           // (s >> 7) * 32 KB + (s & 127) * 128
 #ifdef GNNB_TRACE
                 const long long g0_ = clock64();
 #endif
@@ -915,18 +923,17 @@ __device__ __forceinline__ void fused_body(const FusedArgs& fa) {
 #endif
                 const uint32_t dst0 = ring + slot_ * STAGE + W_KS;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int sub = i >> 2;
-                    const int k = (i & 3) * 4 + (lane >> 3);             // row of the stage: 4 rows x 8 chunks per instruction
-                    const int node = __shfl_sync(0xffffffffu, idx, k);
-                    const bool ok = node >= 0 && dm0 + sub < a.Bc;
-                    const int64_t grow = ok ? (int64_t)(dm0 + sub) * plan.nslots_in + node : 0;
-                    const uint32_t r = (uint32_t)(grow & (TILE - 1));
-                    const uint32_t jp = (uint32_t)(lane & 7);           // physical 16-byte chunk of the row in the mu image
-                    const unsigned char* src = mu_bytes + (grow >> 7) * (int64_t)ABUF + (r >> 3) * 1024u + (r & 7u) * 128u + jp * 16u;
-                    const uint32_t dst = dst0 + (uint32_t)sub * B_DOM + swz((uint32_t)k, jp ^ (r & 7u));   // logical chunk = physical ^ (row & 7)
-                    cp_async16(dst, src, ok);
-                    cp_async16(dst + B_PLANE, src + APLANE, ok);
+                for (int q = 0; q < 4; ++q) {                            // 4 rows x 8 chunks per instruction, both subdomains, both planes
+                    const int k = q * 4 + (lane >> 3);                   // row of the stage
+                    const int o = __shfl_sync(0xffffffffu, off, k);
+                    const bool ok = o >= 0;
+                    const uint32_t oo = ok ? (uint32_t)o : 0u, r7 = (oo >> 7) & 7u;       // logical chunk = physical ^ (row & 7)
+                    const uint32_t dst = dst0 + swz((uint32_t)k, jp ^ r7);
+                    const uint32_t z0 = ok ? sz0 : 0u, z1 = ok ? sz1 : 0u;
+                    cp_async16_sz(dst, base0 + oo, z0);
+                    cp_async16_sz(dst + B_PLANE, base0 + oo + APLANE, z0);
+                    cp_async16_sz(dst + B_DOM, base1 + oo, z1);
+                    cp_async16_sz(dst + B_DOM + B_PLANE, base1 + oo + APLANE, z1);
                 }
                 cp_async_arrive(smem_u32(&tl->full[slot_]));
             }

@@ -210,6 +210,9 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16u : 0u) : "memory");
 }
+__device__ __forceinline__ void cp_async16_sz(uint32_t dst, const void* src, uint32_t src_bytes) {      // src_bytes 16, or 0 = zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_arrive(uint32_t mbar) {      // arrives when this thread's earlier cp.async have landed
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(mbar) : "memory");
 }
